@@ -1,0 +1,474 @@
+#!/usr/bin/env python
+"""bench.py -- precond update+apply steps/s for the PSGD hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload uvd|kron] [--impl ours|reference]
+
+One "step" = one preconditioner update followed by one preconditioned-gradient apply on fresh synthetic
+(v, h, g) / (dX, dG, G), state carried across steps.
+
+Workloads
+  uvd  (default)  UVd rank-10 on a flattened 100M-parameter vector (BASELINE.json configs[3]); at N GPUs the vector
+                  is sharded by contiguous chunk (strong scaling) with all-reduces of the r x r / r-length partials.
+  kron            synthetic 24-layer 4096x4096 stack, dense-dense Kron update+apply (configs[2]), layers sharded.
+
+Prints ONE JSON line (rank 0).  `value` is device-timed with inputs resident in HBM; `e2e` is the same metric through
+the public API with HOST (pinned) inputs and a host read-back of the result inside the timed region; `roofline`
+describes the dominant kernel (CUDA-event timed per launch inside the timed region); `cpu_baseline` is the CPU oracle
+timed on this box's host cores on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+METRIC = "precond update+apply steps/s"
+UNIT = "steps/s"
+KERNEL_NAMES = {1: "uvd_gram_update", 2: "uvd_map_update2", 3: "uvd_map_update3", 4: "uvd_gram_apply", 5: "uvd_map_apply",
+                10: "gemm", 11: "trsm"}
+
+
+# ---------------------------------------------------------------------------------------------
+# helpers
+# ---------------------------------------------------------------------------------------------
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        try:
+            d = json.load(open(p))
+            return dict(hbm=float(d["hbm_gbs"]), bf16=float(d.get("bf16_tflops", 1590.0)),
+                        bf16_sustained=float(d.get("bf16_tflops_sustained", 1400.0)), source="measured")
+        except Exception:
+            pass
+    return dict(hbm=6650.0, bf16=1590.0, bf16_sustained=1400.0, source="fallback")
+
+
+class ClockSampler:
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device_index: int):
+        self.proc, self.idx = None, device_index
+        self.path = f"/tmp/psgd_bench_clocks_{os.getpid()}.csv"
+
+    def start(self):
+        try:
+            self.fh = open(self.path, "w")
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        if self.proc is None:
+            return None
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        self.fh.close()
+        sm, mx, reasons = [], [], set()
+        for line in open(self.path):
+            f = [x.strip() for x in line.split(",")]
+            if len(f) < 9:
+                continue
+            try:
+                sm.append(float(f[1])); mx.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        try:
+            os.remove(self.path)
+        except OSError:
+            pass
+        if not sm:
+            return None
+        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+
+
+def dist_env():
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    return rank, world, local
+
+
+# ---------------------------------------------------------------------------------------------
+# UVd workload
+# ---------------------------------------------------------------------------------------------
+def uvd_bytes(n, r):
+    """Algorithmic bytes: big inputs read twice (reduce, then map), outputs written once."""
+    per_kernel = {1: 4 * n * (2 * r + 3), 2: 4 * n * (2 * r + 3), 3: 4 * n * (r + 1), 4: 4 * n * (2 * r + 2),
+                  5: 4 * n * (2 * r + 2) + 4 * n}
+    return per_kernel, sum(per_kernel.values())          # total = 4n(9r+12)
+
+
+def chunk_of(n, world, rank, align=256):
+    per = -(-n // world)
+    per = -(-per // align) * align
+    lo = min(n, rank * per)
+    hi = min(n, lo + per)
+    return lo, hi
+
+
+def run_uvd(args, rank, world, local):
+    import torch
+    import torch.distributed as dist
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    N, r = args.n, args.rank
+    if args.scaling == "weak":
+        lo, hi = 0, N
+        N_total = N * world
+    else:
+        lo, hi = chunk_of(N, world, rank)
+        N_total = N
+    n = hi - lo
+    gen = torch.Generator(device=dev).manual_seed(2024 + rank)
+    uv = (1.0 / (N_total * r)) ** 0.5                                   # psgd.py:687
+    U0 = torch.randn(n, r, device=dev, generator=gen) * uv
+    V0 = torch.randn(n, r, device=dev, generator=gen) * uv
+    d0 = torch.ones(n, 1, device=dev)
+    POOL = 4
+    pool = []
+    for _ in range(POOL):
+        v = torch.randn(n, 1, device=dev, generator=gen)
+        c = 0.5 + 1.5 * torch.rand(n, 1, device=dev, generator=gen)
+        h = c * v + 0.1 * torch.randn(n, 1, device=dev, generator=gen)
+        g = torch.randn(n, 1, device=dev, generator=gen)
+        pool.append((v, h, g))
+        del c
+    ctx = psgd.get_context(local)
+    if world > 1:
+        partition.install_allreduce(ctx)
+
+    def step(i, U, V, d, v, h, g):
+        psgd.update_precond_UVd_math_(U, V, d, v, h, 0.01, psgd._tiny, balance=(i % 100 == 99), update_U=(i % 2 == 0))
+        return psgd.precond_grad_UVd_math(U, V, d, g)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing -----------------------------------------------------------------
+    U, V, d = U0.clone(), V0.clone(), d0.clone()
+    for i in range(args.warmup):
+        step(i, U, V, d, *pool[i % POOL])
+    ctx.set_option("profile", 1)
+    ctx.profile_read()
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        pre = step(args.warmup + i, U, V, d, *pool[i % POOL])
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    prof = ctx.profile_read(cap=65536)
+    ctx.set_option("profile", 0)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    assert torch.isfinite(pre).all(), "non-finite preconditioned gradient"
+    value = args.steps / (ms / 1e3)
+
+    # ---- per-kernel roofline ----------------------------------------------------------------------
+    peaks = load_peaks()
+    per_kernel_bytes, step_bytes = uvd_bytes(n, r)
+    agg = {}
+    for kid, kms in prof:
+        a = agg.setdefault(kid, [0.0, 0])
+        a[0] += kms; a[1] += 1
+    kernels = []
+    for kid, (tot, cnt) in sorted(agg.items()):
+        avg = tot / cnt
+        ach = per_kernel_bytes.get(kid, 0) / (avg * 1e-3) / 1e9
+        kernels.append(dict(kernel=KERNEL_NAMES.get(kid, str(kid)), launches=cnt, avg_ms=round(avg, 4),
+                            algorithmic_GB=round(per_kernel_bytes.get(kid, 0) / 1e9, 3), achieved_GBps=round(ach, 1),
+                            frac=round(ach / peaks["hbm"], 4), share_of_step=round(tot / ms, 4)))
+    dom = max(kernels, key=lambda k: k["avg_ms"] * k["launches"]) if kernels else None
+    roofline = None
+    if dom:
+        roofline = dict(bound="hbm", kernel=dom["kernel"], achieved=dom["achieved_GBps"], peak=peaks["hbm"], unit="GB/s",
+                        frac=dom["frac"], traffic=None, peak_source=f"of {peaks['source']}",
+                        step_achieved=round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
+                        step_frac=round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
+                        step_algorithmic_GB=round(step_bytes / 1e9, 3))
+
+    # ---- end to end: host (pinned) inputs, host read-back, copies inside the timed region -----------
+    e2e = None
+    if not args.no_e2e:
+        del pool
+        torch.cuda.empty_cache()
+        NB = 2
+        hv = [torch.randn(n, 1).pin_memory() for _ in range(NB)]
+        hh = [(1.3 * hv[k] + 0.1 * torch.randn(n, 1)).pin_memory() for k in range(NB)]
+        hg = [torch.randn(n, 1).pin_memory() for _ in range(NB)]
+        hout = [torch.empty(n, 1).pin_memory() for _ in range(NB)]
+        dv = [torch.empty(n, 1, device=dev) for _ in range(NB)]
+        dh = [torch.empty(n, 1, device=dev) for _ in range(NB)]
+        dg = [torch.empty(n, 1, device=dev) for _ in range(NB)]
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
+        U, V, d = U0.clone(), V0.clone(), d0.clone()
+
+        def e2e_loop(steps, base):
+            in_ready = [None] * NB
+            buf_free = [None] * NB
+            out_done = [None] * NB
+            pres = [None] * NB
+
+            def upload(i):
+                k = i % NB
+                with torch.cuda.stream(s_h2d):
+                    if buf_free[k] is not None:
+                        s_h2d.wait_event(buf_free[k])
+                    dv[k].copy_(hv[k], non_blocking=True); dh[k].copy_(hh[k], non_blocking=True)
+                    dg[k].copy_(hg[k], non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(s_h2d); in_ready[k] = ev
+
+            upload(0)
+            for i in range(steps):
+                k = i % NB
+                if i + 1 < steps:
+                    upload(i + 1)
+                cur.wait_event(in_ready[k])
+                if out_done[k] is not None:
+                    cur.wait_event(out_done[k])         # the previous result in this slot has left the device
+                pres[k] = step(base + i, U, V, d, dv[k], dh[k], dg[k])
+                ev = torch.cuda.Event(); ev.record(cur); buf_free[k] = ev
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev)
+                    hout[k].copy_(pres[k], non_blocking=True)
+                    ev2 = torch.cuda.Event(); ev2.record(s_d2h); out_done[k] = ev2
+            cur.wait_stream(s_d2h)
+
+        e2e_loop(max(2, min(args.warmup, 3)), 0)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        f0.record()
+        e2e_loop(args.steps, args.warmup)
+        f1.record()
+        barrier()
+        ems = f0.elapsed_time(f1)
+        t = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        assert np.isfinite(hout[0].numpy()).all()
+        e2e = dict(value=round(args.steps / (ems / 1e3), 3), unit=UNIT, h2d_bytes_per_step=int(3 * 4 * N_total),
+                   d2h_bytes_per_step=int(4 * N_total), ms_per_step=round(ems / args.steps, 3),
+                   note="v,h,g uploaded from pinned host memory and pre_grad read back to host every step; U,V,d are "
+                        "device-resident optimizer state; copies double-buffered on side streams")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_uvd(N_total, r, budget_s=20.0, steps=2, warmup=1)
+
+    if rank != 0:
+        return None
+    return dict(
+        metric=METRIC, value=round(value, 3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling=args.scaling, vs_baseline=None,
+        dtype="f32", data="synthetic",
+        config=dict(workload=f"UVd rank-{r} update+apply on a flattened {N_total:,}-parameter vector (BASELINE configs[3])",
+                    n_params=N_total, rank=r, rows_per_gpu=n, parallelism=f"chunk-sharded x{world}",
+                    l2_policy="inputs larger than L2: >= %.1f GB of state+inputs streamed per GPU per step vs 126 MB L2" %
+                              ((4 * n * (2 * r + 4)) / 1e9),
+                    coin_flips="update_U alternates, balance every 100th step", step_size=0.01),
+        roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+
+
+# ---------------------------------------------------------------------------------------------
+# CPU baseline / reference arm: the oracle (port of the reference's TF op sequence) on host cores
+# ---------------------------------------------------------------------------------------------
+def _blas_threads():
+    try:
+        from threadpoolctl import threadpool_info
+        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def _oracle_uvd_step(O, st, i):
+    U, V, d, v, h, g = st
+    U, V, d = O.update_precond_UVd_math(U, V, d, v, h, 0.01, balance=(i % 100 == 99), update_U=(i % 2 == 0))
+    pre = O.precond_grad_UVd_math(U, V, d, g)
+    return (U, V, d, v, h, g), pre
+
+
+def _uvd_host_state(n, r, n_total):
+    rng = np.random.default_rng(2024)
+    uv = (1.0 / (n_total * r)) ** 0.5
+    U = (rng.standard_normal((n, r), dtype=np.float32) * uv)
+    V = (rng.standard_normal((n, r), dtype=np.float32) * uv)
+    d = np.ones((n, 1), np.float32)
+    v = rng.standard_normal((n, 1), dtype=np.float32)
+    h = ((0.5 + 1.5 * rng.random((n, 1), dtype=np.float32)) * v + 0.1 * rng.standard_normal((n, 1), dtype=np.float32)).astype(np.float32)
+    g = rng.standard_normal((n, 1), dtype=np.float32)
+    return (U, V, d, v, h, g)
+
+
+def cpu_baseline_uvd(n_total, r, budget_s, steps, warmup):
+    """Time the oracle on a bounded row sample and scale linearly in N (every op of the path is O(N r^2))."""
+    from oracle import psgd_oracle as O
+    st = _uvd_host_state(200_000, r, n_total)
+    t0 = time.perf_counter(); _oracle_uvd_step(O, st, 0); per_row = (time.perf_counter() - t0) / 200_000
+    n_s = int(min(n_total, max(200_000, budget_s / max(per_row, 1e-12) / (steps + warmup))))
+    n_s = min(n_s, 20_000_000)
+    st = _uvd_host_state(n_s, r, n_total)
+    for i in range(warmup):
+        st, _ = _oracle_uvd_step(O, st, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        st, pre = _oracle_uvd_step(O, st, warmup + i)
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * (n_total / n_s)
+    return dict(value=round(1.0 / full, 5), unit=UNIT, cores=_blas_threads(), kind="port",
+                sample=f"oracle (NumPy float32 restatement of psgd.py:554-627) on {n_s:,} of {n_total:,} rows, "
+                       f"{steps} timed steps, {dt * 1e3:.0f} ms/step on the sample, scaled linearly to the full vector; "
+                       f"host has {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}",
+                ms_per_step_sample=round(dt * 1e3, 2), sample_rows=n_s)
+
+
+def run_reference(args, rank, world):
+    """--impl reference: the reference's own CPU implementation of the path.  TensorFlow is not installable in this
+    image (no network), so this is the oracle port, on all host threads NumPy/BLAS will use; rank 0 only."""
+    if rank != 0:
+        return None
+    n_total, r = args.n, args.rank
+    if args.workload == "kron":
+        return run_reference_kron(args)
+    from oracle import psgd_oracle as O
+    st = _uvd_host_state(200_000, r, n_total)
+    t0 = time.perf_counter(); _oracle_uvd_step(O, st, 0); per_row = (time.perf_counter() - t0) / 200_000
+    budget = 100.0
+    n_s = int(min(n_total, max(100_000, budget / max(per_row, 1e-12) / (args.steps + args.warmup)), 20_000_000))
+    st = _uvd_host_state(n_s, r, n_total)
+    for i in range(args.warmup):
+        st, _ = _oracle_uvd_step(O, st, i)
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        st, pre = _oracle_uvd_step(O, st, args.warmup + i)
+    dt = (time.perf_counter() - t0) / args.steps
+    full_ms = dt * 1e3 * (n_total / n_s)
+    value = 1e3 / full_ms
+    sample = (f"oracle port (TensorFlow unavailable) on {n_s:,} of {n_total:,} rows per step, scaled linearly to the full "
+              f"vector; {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}")
+    return dict(impl="reference", metric=METRIC, value=round(value, 5), unit=UNIT, n_gpus=world, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(full_ms, 2), higher_is_better=True, scaling=args.scaling,
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"UVd rank-{r} update+apply on a flattened {n_total:,}-parameter vector (BASELINE configs[3])",
+                            n_params=n_total, rank=r),
+                cpu_baseline=dict(value=round(value, 5), unit=UNIT, cores=_blas_threads(), kind="port", sample=sample),
+                e2e=dict(value=round(value, 5), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+
+
+def run_reference_kron(args):
+    from oracle import psgd_oracle as O
+    n = args.kron_n
+    L = args.layers
+    rng = np.random.default_rng(1000)
+    # bounded sample: one layer at reduced size, scaled by the cubic flop count (26 n^3 per layer-step)
+    ns = min(n, 1024)
+    Ql = np.eye(ns, dtype=np.float32); Qr = np.eye(ns, dtype=np.float32)
+    def one(Ql, Qr):
+        dX = rng.standard_normal((ns, ns), dtype=np.float32); dG = rng.standard_normal((ns, ns), dtype=np.float32)
+        G = rng.standard_normal((ns, ns), dtype=np.float32)
+        Ql, Qr = O.update_precond_kron(Ql, Qr, dX, dG, 0.01)
+        return Ql, Qr, O.precond_grad_kron(Ql, Qr, G)
+    for _ in range(args.warmup):
+        Ql, Qr, _p = one(Ql, Qr)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        Ql, Qr, _p = one(Ql, Qr)
+    dt = (time.perf_counter() - t0) / args.steps
+    full = dt * (n / ns) ** 3 * L
+    value = 1.0 / full
+    sample = (f"oracle port (TensorFlow unavailable): one {ns}x{ns} dense-dense layer per step, scaled by (n/{ns})^3 x {L} "
+              f"layers; {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}")
+    return dict(impl="reference", metric=METRIC, value=round(value, 6), unit=UNIT, n_gpus=1, steps=args.steps,
+                warmup=args.warmup, ms_per_step=round(full * 1e3, 1), higher_is_better=True, scaling=args.scaling,
+                vs_baseline=None, dtype="f32", data="synthetic",
+                config=dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply (BASELINE configs[2])"),
+                cpu_baseline=dict(value=round(value, 6), unit=UNIT, cores=_blas_threads(), kind="port", sample=sample),
+                e2e=dict(value=round(value, 6), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
+
+
+# ---------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="uvd", choices=["uvd", "kron"])
+    ap.add_argument("--n", type=int, default=100_000_000, help="UVd: parameters in the flattened vector")
+    ap.add_argument("--rank", type=int, default=10)
+    ap.add_argument("--layers", type=int, default=24)
+    ap.add_argument("--kron-n", type=int, default=4096)
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    rank, world, local = dist_env()
+
+    if args.impl == "reference":
+        out = run_reference(args, rank, world)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+        return 0
+
+    args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps
+    import torch
+    if not torch.cuda.is_available():
+        print(json.dumps({"error": "no CUDA device: psgd_tf_b200 has no CPU path"}), flush=True)
+        return 1
+    if world > 1:
+        import torch.distributed as dist
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        torch.cuda.set_device(local)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    try:
+        if args.workload == "uvd":
+            out = run_uvd(args, rank, world, local)
+        else:
+            from bench_kron import run_kron
+            out = run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler)
+        if out is not None:
+            print(json.dumps(out), flush=True)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -1,0 +1,141 @@
+/*
+ * psgd_b200.h -- C ABI of the B200-native PSGD preconditioner hot path.
+ *
+ * Drop-in boundary for lixilinx/psgd_tf's `preconditioned_stochastic_gradient_descent.py`
+ * (called psgd.py below; citations are file:line in the reference tree).  The reference has no
+ * FFI of its own: its operator interface is a set of Python functions whose arithmetic is delegated
+ * to TensorFlow ops.  Each entry point here replaces the TensorFlow op sequence of one such function;
+ * the Python mirror in psgd_tf_b200/ binds them with ctypes (see INTEGRATION.md for the stub a
+ * reference maintainer would add).
+ *
+ * Rules of the ABI
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer to float32, row-major,
+ *     contiguous, 16-byte aligned (what DLPack hands over for a compact tensor);
+ *   - every call enqueues work on the context's CUDA stream and returns without a host sync;
+ *   - every call returns 0 on success or a psgd_status code; psgd_last_error() gives the
+ *     thread-local message;
+ *   - there is NO CPU fallback: a context cannot be created without a CUDA device.
+ */
+#ifndef PSGD_B200_H_
+#define PSGD_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PSGD_B200_ABI_VERSION 1
+
+typedef enum psgd_status {
+  PSGD_OK = 0,
+  PSGD_ERR_BAD_SHAPE = 1,     /* sizes inconsistent / unsupported rank                    */
+  PSGD_ERR_BAD_POINTER = 2,   /* null or misaligned device pointer                         */
+  PSGD_ERR_UNSUPPORTED = 3,   /* unknown Kron factor combination (psgd.py:89-91 semantics) */
+  PSGD_ERR_CUDA = 4,          /* a CUDA runtime call failed                                */
+  PSGD_ERR_COMM = 5,          /* the registered all-reduce hook failed                     */
+  PSGD_ERR_NO_DEVICE = 6      /* no CUDA device: there is no CPU path                      */
+} psgd_status;
+
+/* Kronecker factor formats (README.md:37-39 of the reference; psgd.py:80-110). */
+typedef enum psgd_factor_kind {
+  PSGD_FACTOR_DENSE = 0, /* [N,N] upper-triangular Cholesky-like factor */
+  PSGD_FACTOR_SCALE = 1, /* [1,N] diagonal                               */
+  PSGD_FACTOR_NORM = 2   /* [2,N] diagonal + last column                 */
+} psgd_factor_kind;
+
+typedef struct psgd_ctx psgd_ctx;
+
+/* ---- context ------------------------------------------------------------------------------ */
+int psgd_abi_version(void);
+const char* psgd_last_error(void);
+/* stream: a cudaStream_t (0 = legacy default stream). */
+int psgd_create(int device, void* stream, psgd_ctx** out);
+int psgd_destroy(psgd_ctx* ctx);
+int psgd_set_stream(psgd_ctx* ctx, void* stream);
+/* Number of kernels this library has launched through ctx since creation (bench "gpu_launches"). */
+int64_t psgd_launch_count(const psgd_ctx* ctx);
+/* Bytes of device workspace currently owned by ctx. */
+int64_t psgd_workspace_bytes(const psgd_ctx* ctx);
+/* Kernel path selector for the streaming kernels: 0 = TMA bulk-copy pipeline (default),
+ * 1 = direct global loads (debug cross-check; same arithmetic). */
+int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
+
+/* Per-kernel device timing.  After psgd_set_option(ctx, "profile", 1) every large kernel launch is bracketed
+ * by CUDA events on ctx's stream; psgd_profile_read synchronises on them, writes up to `cap` (kernel id,
+ * milliseconds) records in launch order, clears the log and returns the number written.  Kernel ids: */
+#define PSGD_K_UVD_GRAM_UPDATE 1 /* update sweep 1: Gram/vector reductions over U,V,d,h,v  */
+#define PSGD_K_UVD_MAP_UPDATE2 2 /* update sweep 2: per-row a,b,nablaD + max/sums            */
+#define PSGD_K_UVD_MAP_UPDATE3 3 /* update sweep 3: write d and U (or V)                      */
+#define PSGD_K_UVD_GRAM_APPLY 4  /* apply sweep 1: U^T U, U^T(dg), V^T(dg)                    */
+#define PSGD_K_UVD_MAP_APPLY 5   /* apply sweep 2: write the preconditioned gradient          */
+#define PSGD_K_GEMM 10           /* one dense-factor GEMM launch (either engine)              */
+#define PSGD_K_TRSM 11           /* one triangular-solve step                                 */
+int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, int cap);
+
+/* Cross-rank reduction hook for the chunk-sharded (multi-GPU) streaming paths.  When set, the
+ * library calls it on ctx's stream between kernels with a device buffer of `count` float64
+ * (op 0 = sum) or float32 (op 1 = max) values that must be all-reduced in place over all ranks.
+ * Return 0 on success.  With no hook the library runs single-GPU. */
+typedef int (*psgd_allreduce_fn)(void* user, void* device_buf, int64_t count, int op, void* stream);
+int psgd_set_allreduce(psgd_ctx* ctx, psgd_allreduce_fn fn, void* user);
+
+/* ---- UVd: Q = (I + U V^T) diag(d) ---------------------------------------------------------- */
+/* Replaces update_precond_UVd_math_ (psgd.py:554-617).  U,V:[n,r]  d,v,h:[n].  In place on U,V,d.
+ * The reference's two coin flips are arguments: balance = (uniform < 0.01) (psgd.py:562),
+ * update_U = (uniform < 0.5) (psgd.py:588). */
+int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h,
+                    int64_t n, int r, float step, float tiny, int balance, int update_U);
+/* Replaces precond_grad_UVd_math (psgd.py:619-627): out = d*(I+VU^T)(I+UV^T)(d*g). */
+int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,
+                   float* out, int64_t n, int r);
+/* Replaces IpUVtmatvec (psgd.py:540-544): out = x + U (V^T x), x:[n,k] row-major. */
+int psgd_ipuvt_matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out,
+                      int64_t n, int r, int k);
+
+/* ---- diagonal and X-shape (README.md:11-15, :35; no reference code -- SURVEY.md appendix B) - */
+int psgd_diag_update(psgd_ctx* ctx, float* q, const float* v, const float* h, int64_t n, float step, float tiny);
+int psgd_diag_apply(psgd_ctx* ctx, const float* q, const float* g, float* out, int64_t n);
+int psgd_xmat_update(psgd_ctx* ctx, float* a, float* b, const float* v, const float* h, int64_t n,
+                     float step, float tiny);
+int psgd_xmat_apply(psgd_ctx* ctx, const float* a, const float* b, const float* g, float* out, int64_t n);
+
+/* ---- dense full-matrix preconditioner ------------------------------------------------------ */
+/* Replaces update_precond_dense (psgd.py:26-42) on the already concatenated vectors dx, dg:[n]. */
+int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx, const float* dg, float* Q_out,
+                      int64_t n, float step, float tiny);
+/* Replaces precond_grad_dense (psgd.py:45-63): out = Q^T (Q g). */
+int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n);
+
+/* ---- Kronecker-product preconditioners ----------------------------------------------------- */
+/* One layer.  dX,dG,G,out are [M,N].  A DENSE left factor is [M,M], SCALE [1,M], NORM [2,M];
+ * right factors likewise with N.  All seven combinations the reference dispatches
+ * (psgd.py:82-110, :124-152) are accepted; (NORM,NORM), (SCALE,SCALE) return PSGD_ERR_UNSUPPORTED.
+ * Functional: inputs untouched, results written to Ql_out / Qr_out (same shapes as Ql / Qr). */
+int psgd_kron_update(psgd_ctx* ctx, int kind_l, int kind_r, const float* Ql, const float* Qr,
+                     const float* dX, const float* dG, float* Ql_out, float* Qr_out, int64_t M, int64_t N,
+                     float step, float tiny);
+int psgd_kron_apply(psgd_ctx* ctx, int kind_l, int kind_r, const float* Ql, const float* Qr,
+                    const float* G, float* out, int64_t M, int64_t N);
+
+/* A ragged list of layers in one call ("batched launch over all layers").  Arrays are HOST arrays
+ * of length count. */
+typedef struct psgd_kron_layer {
+  int32_t kind_l, kind_r;
+  int64_t M, N;
+  const float* Ql;
+  const float* Qr;
+  const float* dX; /* update only */
+  const float* dG; /* update only */
+  const float* G;  /* apply only  */
+  float* Ql_out;   /* update only */
+  float* Qr_out;   /* update only */
+  float* out;      /* apply only  */
+} psgd_kron_layer;
+int psgd_kron_update_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count, float step, float tiny);
+int psgd_kron_apply_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PSGD_B200_H_ */

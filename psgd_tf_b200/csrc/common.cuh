@@ -1,0 +1,195 @@
+// Shared host/device plumbing for the PSGD B200 kernels: context, workspace, error reporting,
+// PTX wrappers for mbarrier + TMA bulk copies (sm_100a).
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+#include <vector>
+
+#include "../../include/psgd_b200.h"
+
+namespace psgd {
+
+// ---------------------------------------------------------------------------------------------
+// error reporting
+// ---------------------------------------------------------------------------------------------
+void set_error(const char* fmt, ...);
+
+#define PSGD_CUDA_CHECK(expr)                                                              \
+  do {                                                                                     \
+    cudaError_t _e = (expr);                                                               \
+    if (_e != cudaSuccess) {                                                               \
+      ::psgd::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__,  \
+                        __LINE__);                                                         \
+      return PSGD_ERR_CUDA;                                                                \
+    }                                                                                      \
+  } while (0)
+
+#define PSGD_RETURN_IF(status_expr)     \
+  do {                                  \
+    int _s = (status_expr);             \
+    if (_s != PSGD_OK) return _s;       \
+  } while (0)
+
+#define PSGD_REQUIRE(cond, code, ...)   \
+  do {                                  \
+    if (!(cond)) {                      \
+      ::psgd::set_error(__VA_ARGS__);   \
+      return (code);                    \
+    }                                   \
+  } while (0)
+
+static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+}  // namespace psgd
+
+// ---------------------------------------------------------------------------------------------
+// context
+// ---------------------------------------------------------------------------------------------
+struct psgd_ctx {
+  int device = 0;
+  cudaStream_t stream = nullptr;
+  int num_sms = 148;
+  int64_t launches = 0;
+  // growable device workspace (cudaMalloc'ed, owned)
+  void* ws = nullptr;
+  size_t ws_bytes = 0;
+  // small pinned/ device scratch is carved from ws by each op
+  int opt_direct = 0;        // streaming kernels: 1 = direct global loads instead of TMA pipeline
+  int opt_gemm_path = 0;     // dense GEMMs: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32
+  psgd_allreduce_fn allreduce = nullptr;
+  void* allreduce_user = nullptr;
+  // optional per-kernel timing (psgd_set_option("profile", 1)): CUDA event pairs around the large kernels
+  int opt_profile = 0;
+  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  std::vector<ProfRec> prof;
+
+  // Ensure at least `bytes` of workspace; contents are NOT preserved across growth.
+  int reserve(size_t bytes);
+};
+
+namespace psgd {
+
+// Bump allocator over ctx->ws (256-byte granularity).
+struct WsCarver {
+  char* base;
+  size_t off = 0;
+  explicit WsCarver(void* b) : base(static_cast<char*>(b)) {}
+  template <typename T>
+  T* take(size_t count) {
+    T* p = reinterpret_cast<T*>(base + off);
+    off += ((count * sizeof(T) + 255) / 256) * 256;
+    return p;
+  }
+  static size_t padded(size_t bytes) { return ((bytes + 255) / 256) * 256; }
+};
+
+// Brackets one kernel launch with CUDA events when profiling is on (kernel ids: psgd_b200.h).
+struct ProfScope {
+  psgd_ctx* c;
+  psgd_ctx::ProfRec r;
+  bool on;
+  ProfScope(psgd_ctx* ctx, int id) : c(ctx), on(ctx->opt_profile != 0) {
+    if (!on) return;
+    r.id = id;
+    cudaEventCreate(&r.e0);
+    cudaEventCreate(&r.e1);
+    cudaEventRecord(r.e0, c->stream);
+  }
+  ~ProfScope() {
+    if (!on) return;
+    cudaEventRecord(r.e1, c->stream);
+    c->prof.push_back(r);
+  }
+};
+
+#define PSGD_LAUNCH_CHECK(ctx)                \
+  do {                                        \
+    (ctx)->launches += 1;                     \
+    PSGD_CUDA_CHECK(cudaGetLastError());      \
+  } while (0)
+
+#ifdef __CUDACC__
+// ---------------------------------------------------------------------------------------------
+// device helpers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) {
+  return static_cast<uint32_t>(__cvta_generic_to_shared(p));
+}
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init() {
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+// TMA bulk copy (no tensor map): global -> shared, completion counted in bytes on an mbarrier.
+// Requires 16-byte aligned src/dst and size % 16 == 0.   SASS: UBLKCP.
+__device__ __forceinline__ void bulk_g2s(void* smem_dst, const void* gmem_src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+                   smem_u32(smem_dst)),
+               "l"(gmem_src), "r"(bytes), "r"(smem_u32(bar))
+               : "memory");
+}
+// shared -> global, tracked by the issuing thread's bulk async-group.
+__device__ __forceinline__ void bulk_s2g(void* gmem_dst, const void* smem_src, uint32_t bytes) {
+  asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(gmem_dst),
+               "r"(smem_u32(smem_src)), "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait_read0() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void bulk_wait0() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+// generic-proxy writes to shared memory -> visible to the async proxy (TMA store / tcgen05)
+__device__ __forceinline__ void fence_proxy_async_smem() {
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+}
+__device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+// atomic max for non-negative floats (bit pattern order == value order); NaN poisons to NaN-ish max.
+__device__ __forceinline__ void atomic_max_nonneg(float* addr, float v) {
+  atomicMax(reinterpret_cast<unsigned int*>(addr), __float_as_uint(v));
+}
+#endif  // __CUDACC__
+
+}  // namespace psgd

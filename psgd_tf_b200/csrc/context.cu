@@ -1,0 +1,116 @@
+// Context, workspace and error plumbing of the C ABI (include/psgd_b200.h).
+#include <stdarg.h>
+#include <string.h>
+
+#include "common.cuh"
+
+namespace psgd {
+static thread_local char g_error[512] = "";
+
+void set_error(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_error, sizeof(g_error), fmt, ap);
+  va_end(ap);
+}
+}  // namespace psgd
+
+int psgd_ctx::reserve(size_t bytes) {
+  if (bytes <= ws_bytes) return PSGD_OK;
+  // the old block may still be in use by enqueued kernels: free it stream-ordered
+  if (ws) PSGD_CUDA_CHECK(cudaFreeAsync(ws, stream));
+  ws = nullptr;
+  ws_bytes = 0;
+  size_t want = bytes + bytes / 8;
+  PSGD_CUDA_CHECK(cudaMallocAsync(&ws, want, stream));
+  ws_bytes = want;
+  return PSGD_OK;
+}
+
+extern "C" int psgd_abi_version(void) { return PSGD_B200_ABI_VERSION; }
+
+extern "C" const char* psgd_last_error(void) { return psgd::g_error; }
+
+extern "C" int psgd_create(int device, void* stream, psgd_ctx** out) {
+  PSGD_REQUIRE(out != nullptr, PSGD_ERR_BAD_POINTER, "psgd_create: out is null");
+  int count = 0;
+  cudaError_t e = cudaGetDeviceCount(&count);
+  if (e != cudaSuccess || count == 0) {
+    psgd::set_error("psgd_create: no CUDA device available (%s); this library has no CPU path",
+                    e == cudaSuccess ? "device count 0" : cudaGetErrorString(e));
+    return PSGD_ERR_NO_DEVICE;
+  }
+  PSGD_REQUIRE(device >= 0 && device < count, PSGD_ERR_NO_DEVICE, "psgd_create: device %d out of range [0,%d)",
+               device, count);
+  PSGD_CUDA_CHECK(cudaSetDevice(device));
+  cudaDeviceProp prop;
+  PSGD_CUDA_CHECK(cudaGetDeviceProperties(&prop, device));
+  PSGD_REQUIRE(prop.major == 10, PSGD_ERR_NO_DEVICE,
+               "psgd_create: device %d is sm_%d%d; this build targets sm_100a (B200) only", device, prop.major,
+               prop.minor);
+  psgd_ctx* ctx = new psgd_ctx();
+  ctx->device = device;
+  ctx->stream = static_cast<cudaStream_t>(stream);
+  ctx->num_sms = prop.multiProcessorCount;
+  *out = ctx;
+  return PSGD_OK;
+}
+
+extern "C" int psgd_destroy(psgd_ctx* ctx) {
+  if (!ctx) return PSGD_OK;
+  cudaSetDevice(ctx->device);
+  if (ctx->ws) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaFree(ctx->ws);
+  }
+  delete ctx;
+  return PSGD_OK;
+}
+
+extern "C" int psgd_set_stream(psgd_ctx* ctx, void* stream) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  if (ctx->stream != static_cast<cudaStream_t>(stream)) {
+    // the workspace is stream-ordered: drain the old stream before switching
+    PSGD_CUDA_CHECK(cudaStreamSynchronize(ctx->stream));
+    ctx->stream = static_cast<cudaStream_t>(stream);
+  }
+  return PSGD_OK;
+}
+
+extern "C" int64_t psgd_launch_count(const psgd_ctx* ctx) { return ctx ? ctx->launches : 0; }
+extern "C" int64_t psgd_workspace_bytes(const psgd_ctx* ctx) { return ctx ? (int64_t)ctx->ws_bytes : 0; }
+
+extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
+  PSGD_REQUIRE(ctx && key, PSGD_ERR_BAD_POINTER, "null context or key");
+  if (strcmp(key, "direct") == 0) { ctx->opt_direct = value ? 1 : 0; return PSGD_OK; }
+  if (strcmp(key, "profile") == 0) { ctx->opt_profile = value ? 1 : 0; return PSGD_OK; }
+  if (strcmp(key, "gemm_path") == 0) {
+    PSGD_REQUIRE(value >= 0 && value <= 2, PSGD_ERR_BAD_SHAPE, "gemm_path must be 0 (auto), 1 (simt) or 2 (tcgen05)");
+    ctx->opt_gemm_path = (int)value;
+    return PSGD_OK;
+  }
+  psgd::set_error("unknown option '%s'", key);
+  return PSGD_ERR_BAD_SHAPE;
+}
+
+extern "C" int psgd_set_allreduce(psgd_ctx* ctx, psgd_allreduce_fn fn, void* user) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  ctx->allreduce = fn;
+  ctx->allreduce_user = user;
+  return PSGD_OK;
+}
+
+extern "C" int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, int cap) {
+  if (!ctx) return 0;
+  int n = 0;
+  for (auto& r : ctx->prof) {
+    cudaEventSynchronize(r.e1);
+    float t = 0.f;
+    cudaEventElapsedTime(&t, r.e0, r.e1);
+    if (n < cap && ids && ms) { ids[n] = r.id; ms[n] = t; ++n; }
+    cudaEventDestroy(r.e0);
+    cudaEventDestroy(r.e1);
+  }
+  ctx->prof.clear();
+  return n;
+}

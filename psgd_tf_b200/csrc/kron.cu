@@ -1,0 +1,657 @@
+// Kronecker-product and dense (full-matrix) preconditioners: host orchestration + the structured-factor
+// kernels ([2,N] normalization and [1,N] scaling formats).
+//
+// Replaces the TensorFlow op sequences of
+//   update_precond_kron / precond_grad_kron dispatch   psgd.py:72-152
+//   _update_precond_dense_dense / _precond_grad_...    psgd.py:156-192
+//   _update_precond_norm_dense  / _precond_grad_...    psgd.py:198-270
+//   _update_precond_dense_scale / _precond_grad_...    psgd.py:276-322
+//   _update_precond_norm_scale  / _precond_grad_...    psgd.py:328-391
+//   update_precond_dense / precond_grad_dense          psgd.py:26-63
+// Large contractions go through the GEMM/TRSM vocabulary of linalg.cuh (SIMT fp32 or tcgen05 3xTF32,
+// chosen per layer size); everything touching a [2,N]/[1,N] factor is a bandwidth-bound kernel here.
+#include <vector>
+
+#include "linalg.cuh"
+#include "gemm_tc.cuh"
+
+namespace psgd {
+namespace kron {
+
+struct Scal {
+  float max_l, max_r, rho;
+  float max1, max2;
+  float pad[3];
+};
+
+// ---------------------------------------------------------------------------------------------
+// balance: rho = sqrt(max_l / max_r)            psgd.py:166-168, :211-213, :288-290, :342-344
+// kind: 0 dense (diag of [n,n]), 1 scale ([1,n] row), 2 norm (row 0 of [2,n]).  max is taken WITHOUT abs.
+// ---------------------------------------------------------------------------------------------
+__device__ float factor_max(int kind, const float* Q, int n) {
+  __shared__ float red[8];
+  float m = -INFINITY;
+  const size_t stride = (kind == PSGD_FACTOR_DENSE) ? (size_t)n + 1 : 1;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) m = fmaxf(m, Q[(size_t)i * stride]);
+  m = warp_max(m);
+  __syncthreads();
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = m;
+  __syncthreads();
+  float r = red[0];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) r = fmaxf(r, red[w]);
+  return r;
+}
+
+__global__ void __launch_bounds__(256) balance_kernel(int kind_l, const float* Ql, int nl, int kind_r, const float* Qr,
+                                                       int nr, Scal* sc) {
+  const float ml = factor_max(kind_l, Ql, nl);
+  const float mr = factor_max(kind_r, Qr, nr);
+  if (threadIdx.x == 0) {
+    sc->max_l = ml; sc->max_r = mr;
+    sc->rho = sqrtf(ml / mr);
+    sc->max1 = 0.f; sc->max2 = 0.f;
+  }
+}
+
+// out = in / rho  (left factor)   or   out = rho * in  (right factor)
+__global__ void __launch_bounds__(256) rescale_kernel(const float* __restrict__ in, float* __restrict__ out,
+                                                       int64_t count, const Scal* __restrict__ sc, int divide) {
+  const float rho = sc->rho;
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += (int64_t)gridDim.x * blockDim.x)
+    out[i] = divide ? in[i] / rho : rho * in[i];
+}
+
+// ---------------------------------------------------------------------------------------------
+// normalization-format left factor: Ql = diag(ql0) + e_last-column ql1  (ql1[M-1] == 0)
+// ---------------------------------------------------------------------------------------------
+// out[i,j] = (ql0[i] X[i,j] + ql1[i] X[M-1,j]) * cs(j)           psgd.py:218-219 (+ :351, :385)
+// cs: none / qr[j] / qr[j]^2
+__global__ void __launch_bounds__(256) norm_left_mul_kernel(const float* __restrict__ ql, const float* __restrict__ X,
+                                                             float* __restrict__ out, int M, int N,
+                                                             const float* __restrict__ qr, int qr_mode) {
+  const int64_t total = (int64_t)M * N;
+  const float* ql1 = ql + M;
+  const float* Xlast = X + (size_t)(M - 1) * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    float v = ql[i] * X[e];
+    v = v + ql1[i] * Xlast[j];
+    if (qr_mode == 1) v = v * qr[j];
+    else if (qr_mode == 2) v = v * (qr[j] * qr[j]);
+    out[e] = v;
+  }
+}
+
+// chunked, deterministic weighted column reductions: partial[chunk][which][j]
+//   mode 0: sum_i w(i) X[i,j]            w = ql1[i] / (ql0[i] ql0[M-1])       psgd.py:232
+//   mode 1: sum_i ql1[i] X[i,j]                                               psgd.py:265
+//   mode 2: (sum_i X[i,j]^2, sum_i Y[i,j]^2)                                  psgd.py:304
+constexpr int kColChunkRows = 128;
+__global__ void __launch_bounds__(128) col_reduce_kernel(int mode, const float* __restrict__ ql,
+                                                          const float* __restrict__ X, const float* __restrict__ Y,
+                                                          int M, int N, float* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int i0 = chunk * kColChunkRows, i1 = min(M, i0 + kColChunkRows);
+  if (j >= N) return;
+  float s0 = 0.f, s1 = 0.f;
+  const float qlast = (mode == 0) ? ql[M - 1] : 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float x = X[(size_t)i * N + j];
+    if (mode == 0) s0 = fmaf(ql[M + i] / (ql[i] * qlast), x, s0);
+    else if (mode == 1) s0 = fmaf(ql[M + i], x, s0);
+    else { const float y = Y[(size_t)i * N + j]; s0 = fmaf(x, x, s0); s1 = fmaf(y, y, s1); }
+  }
+  partial[((size_t)chunk * 2 + 0) * N + j] = s0;
+  partial[((size_t)chunk * 2 + 1) * N + j] = s1;
+}
+// out0[j] = sum_chunks partial[.][0][j]  (and out1 for mode 2)
+__global__ void __launch_bounds__(128) col_finish_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                          float* __restrict__ out0, float* __restrict__ out1) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j >= N) return;
+  float s0 = 0.f, s1 = 0.f;
+  for (int c = 0; c < chunks; ++c) { s0 += partial[((size_t)c * 2) * N + j]; s1 += partial[((size_t)c * 2 + 1) * N + j]; }
+  out0[j] = s0;
+  if (out1) out1[j] = s1;
+}
+
+// Bt = Ql^-T dX (closed form), optionally times 1/qr[j]          psgd.py:230-232 (+ :356)
+__global__ void __launch_bounds__(256) norm_left_solve_kernel(const float* __restrict__ ql, const float* __restrict__ X,
+                                                               const float* __restrict__ cvec, float* __restrict__ out,
+                                                               int M, int N, const float* __restrict__ qr) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    float v = (1.0f / ql[i]) * X[e];
+    if (i == M - 1) v = v - cvec[j];
+    if (qr) v = v * (1.0f / qr[j]);
+    out[e] = v;
+  }
+}
+
+// per-row statistics of A, Bt                                    psgd.py:235-239
+//   g1d[i] = sum_j A^2 - sum_j Bt^2 ; g1b[i] = A[i].A[last] - Bt[i].Bt[last] (0 for the last row)
+__global__ void __launch_bounds__(128) row_stats_kernel(const float* __restrict__ A, const float* __restrict__ Bt,
+                                                         int M, int N, float* __restrict__ g1d,
+                                                         float* __restrict__ g1b, Scal* __restrict__ sc) {
+  __shared__ float red[4][4];
+  const float* Al = A + (size_t)(M - 1) * N;
+  const float* Bl = Bt + (size_t)(M - 1) * N;
+  float mx = 0.f;
+  for (int i = blockIdx.x; i < M; i += gridDim.x) {
+    float sa = 0.f, sb = 0.f, da = 0.f, db = 0.f;
+    for (int j = threadIdx.x; j < N; j += blockDim.x) {
+      const float a = A[(size_t)i * N + j], b = Bt[(size_t)i * N + j];
+      sa = fmaf(a, a, sa); sb = fmaf(b, b, sb);
+      da = fmaf(a, Al[j], da); db = fmaf(b, Bl[j], db);
+    }
+    sa = warp_sum(sa); sb = warp_sum(sb); da = warp_sum(da); db = warp_sum(db);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) {
+      const int w = threadIdx.x >> 5;
+      red[w][0] = sa; red[w][1] = sb; red[w][2] = da; red[w][3] = db;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float t[4];
+      for (int q = 0; q < 4; ++q) t[q] = red[0][q] + red[1][q] + red[2][q] + red[3][q];
+      const float d = t[0] - t[1];
+      const float b = (i == M - 1) ? 0.f : (t[2] - t[3]);
+      g1d[i] = d; g1b[i] = b;
+      mx = fmaxf(mx, fmaxf(fabsf(d), fabsf(b)));
+    }
+  }
+  if (threadIdx.x == 0) atomic_max_nonneg(&sc->max1, mx);
+}
+
+// new ql rows                                                     psgd.py:240-241
+__global__ void __launch_bounds__(256) norm_new_ql_kernel(const float* __restrict__ ql, const float* __restrict__ g1d,
+                                                           const float* __restrict__ g1b, float* __restrict__ out, int M,
+                                                           float step, float tiny, const Scal* __restrict__ sc) {
+  const float step1 = step / (sc->max1 + tiny);
+  const float qlast = ql[M - 1];
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
+    out[i] = ql[i] - step1 * g1d[i] * ql[i];
+    out[M + i] = ql[M + i] - step1 * (g1d[i] * ql[M + i] + qlast * g1b[i]);
+  }
+}
+
+// grad2 = colsumA2 - colsumB2 ; max |grad2| -> sc->max2           psgd.py:304-305
+__global__ void __launch_bounds__(128) scale_grad_kernel(const float* __restrict__ sa, const float* __restrict__ sb, int N,
+                                                          float* __restrict__ grad2, Scal* __restrict__ sc) {
+  float mx = 0.f;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    const float g = sa[j] - sb[j];
+    grad2[j] = g;
+    mx = fmaxf(mx, fabsf(g));
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&sc->max2, mx);
+}
+// qr' = qr - step2 grad2 qr                                       psgd.py:307
+__global__ void __launch_bounds__(128) scale_new_qr_kernel(const float* __restrict__ qr, const float* __restrict__ grad2,
+                                                            float* __restrict__ out, int N, float step, float tiny,
+                                                            const Scal* __restrict__ sc) {
+  const float step2 = step / (sc->max2 + tiny);
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
+    out[j] = qr[j] - step2 * grad2[j] * qr[j];
+}
+
+// out[i,j] = ql0[i] P[i,j]  (+ addlast[j] on the last row)        psgd.py:266-268
+__global__ void __launch_bounds__(256) norm_left_out_kernel(const float* __restrict__ ql, const float* __restrict__ P,
+                                                             const float* __restrict__ addlast, float* __restrict__ out,
+                                                             int M, int N) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const int i = (int)(e / N), j = (int)(e % N);
+    float v = ql[i] * P[e];
+    if (i == M - 1) v = v + addlast[j];
+    out[e] = v;
+  }
+}
+
+// out[i,j] = P[i,j] * qr[j]^2                                     psgd.py:322
+__global__ void __launch_bounds__(256) col_scale_sq_kernel(const float* __restrict__ P, const float* __restrict__ qr,
+                                                            float* __restrict__ out, int M, int N) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    out[e] = P[e] * (qr[e % N] * qr[e % N]);
+}
+
+// X[i,j] *= 1/qr[j]                                              psgd.py:299
+__global__ void __launch_bounds__(256) col_scale_recip_kernel(float* __restrict__ X, const float* __restrict__ qr,
+                                                               int M, int N) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
+    X[e] = X[e] * (1.0f / qr[e % N]);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host helpers
+// ---------------------------------------------------------------------------------------------
+static int ew_grid(const psgd_ctx* ctx, int64_t total, int threads) {
+  int64_t b = (total + threads - 1) / threads;
+  const int64_t cap = (int64_t)ctx->num_sms * 8;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+static int col_reduce(psgd_ctx* ctx, int mode, const float* ql, const float* X, const float* Y, int M, int N,
+                      float* partial, float* out0, float* out1) {
+  const int chunks = (M + kColChunkRows - 1) / kColChunkRows;
+  dim3 grid((N + 127) / 128, chunks);
+  col_reduce_kernel<<<grid, 128, 0, ctx->stream>>>(mode, ql, X, Y, M, N, partial);
+  PSGD_LAUNCH_CHECK(ctx);
+  col_finish_kernel<<<(N + 127) / 128, 128, 0, ctx->stream>>>(partial, chunks, N, out0, out1);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+static size_t col_partial_floats(int M, int N) {
+  return (size_t)((M + kColChunkRows - 1) / kColChunkRows) * 2 * N;
+}
+
+static int gemm(psgd_ctx* ctx, const la::Gemm& g) { return tc::gemm_auto(ctx, g); }
+
+// triu(X X^T - Y Y^T) (rows) or triu(X^T X - Y^T Y) (cols) with max|.| -> *mx
+static int gram_diff(psgd_ctx* ctx, const float* X, const float* Y, int M, int N, bool rows, float* out, float* mx) {
+  la::Gemm g;
+  if (rows) { g.M = M; g.N = M; g.K = N; g.ta = false; g.tb = true; }
+  else      { g.M = N; g.N = N; g.K = M; g.ta = true;  g.tb = false; }
+  g.A = X; g.lda = N; g.B = X; g.ldb = N;
+  g.K2 = g.K; g.A2 = Y; g.lda2 = N; g.ta2 = g.ta; g.B2 = Y; g.ldb2 = N; g.tb2 = g.tb;
+  g.C = out; g.ldc = g.N; g.triu = true; g.maxabs = mx;
+  return gemm(ctx, g);
+}
+
+// Qout = Q - step/(max+tiny) * grad * Q                            psgd.py:179
+static int factor_step(psgd_ctx* ctx, const float* grad, const float* Q, int n, const float* mx, float step,
+                       float tiny, float* Qout) {
+  la::Gemm g;
+  g.M = n; g.N = n; g.K = n; g.A = grad; g.lda = n; g.B = Q; g.ldb = n;
+  g.C = Qout; g.ldc = n; g.D = Q; g.ldd = n; g.mu_max = mx; g.step = step; g.tiny = tiny;
+  return gemm(ctx, g);
+}
+
+static int balance(psgd_ctx* ctx, int kl, const float* Ql, int M, int kr, const float* Qr, int N, Scal* sc,
+                   float* Qlb, float* Qrb) {
+  balance_kernel<<<1, 256, 0, ctx->stream>>>(kl, Ql, M, kr, Qr, N, sc);
+  PSGD_LAUNCH_CHECK(ctx);
+  const int64_t cl = kl == PSGD_FACTOR_DENSE ? (int64_t)M * M : (kl == PSGD_FACTOR_NORM ? 2 * (int64_t)M : M);
+  const int64_t cr = kr == PSGD_FACTOR_DENSE ? (int64_t)N * N : (kr == PSGD_FACTOR_NORM ? 2 * (int64_t)N : N);
+  rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, ctx->stream>>>(Ql, Qlb, cl, sc, 1);
+  PSGD_LAUNCH_CHECK(ctx);
+  rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, ctx->stream>>>(Qr, Qrb, cr, sc, 0);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+static size_t fsize(int kind, int64_t n) {
+  return kind == PSGD_FACTOR_DENSE ? (size_t)n * n : (kind == PSGD_FACTOR_NORM ? 2 * (size_t)n : (size_t)n);
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical updates (left kind, right kind) in {(D,D), (N,D), (D,S), (N,S)}
+// ---------------------------------------------------------------------------------------------
+static int update_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* dX,
+                            const float* dG, float* Ql_out, float* Qr_out, int M, int N, float step, float tiny,
+                            WsCarver& c) {
+  const size_t MN = (size_t)M * N;
+  Scal* sc = c.take<Scal>(1);
+  float* Qlb = c.take<float>(fsize(kl, M));
+  float* Qrb = c.take<float>(fsize(kr, N));
+  float* A = c.take<float>(MN);
+  float* Bt = c.take<float>(MN);
+  PSGD_RETURN_IF(balance(ctx, kl, Ql, M, kr, Qr, N, sc, Qlb, Qrb));
+  cudaStream_t st = ctx->stream;
+
+  // ---- A = Ql dG Qr^T  and  Bt = Ql^-T dX Qr^-1 ------------------------------------------------
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
+    float* T1 = c.take<float>(MN);
+    la::Gemm g1;                                                           // T1 = dG Qr^T     psgd.py:173
+    g1.M = M; g1.N = N; g1.K = N; g1.A = dG; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = T1; g1.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    la::Gemm g2;                                                           // A = Ql T1
+    g2.M = M; g2.N = N; g2.K = M; g2.A = Qlb; g2.lda = M; g2.B = T1; g2.ldb = N; g2.C = A; g2.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g2));
+    PSGD_RETURN_IF(tc::trsm_right_auto(ctx, Qrb, N, dX, N, T1, N, M, N));          // W = dX Qr^-1   psgd.py:174
+    PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, T1, N, Bt, N, M, N));           // Bt = Ql^-T W
+  } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
+    float* T1 = c.take<float>(MN);
+    float* cvec = c.take<float>(N);
+    float* part = c.take<float>(col_partial_floats(M, N));
+    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dG, T1, M, N, nullptr, 0);     // :218-219
+    PSGD_LAUNCH_CHECK(ctx);
+    la::Gemm g1;                                                           // A = (Ql dG) Qr^T  psgd.py:220
+    g1.M = M; g1.N = N; g1.K = N; g1.A = T1; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = A; g1.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(col_reduce(ctx, 0, Qlb, dX, nullptr, M, N, part, cvec, nullptr));
+    norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dX, cvec, T1, M, N, nullptr); // :230-232
+    PSGD_LAUNCH_CHECK(ctx);
+    PSGD_RETURN_IF(tc::trsm_right_auto(ctx, Qrb, N, T1, N, Bt, N, M, N));                            // :233
+  } else if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {
+    la::Gemm g1;                                                           // A = (Ql dG) * qr  psgd.py:295-296
+    g1.M = M; g1.N = N; g1.K = M; g1.A = Qlb; g1.lda = M; g1.B = dG; g1.ldb = N; g1.C = A; g1.ldc = N;
+    g1.colscale = Qrb;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, dX, N, Bt, N, M, N));                             // :298
+    col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Bt, Qrb, M, N);                   // :299
+    PSGD_LAUNCH_CHECK(ctx);
+  } else {  // (NORM, SCALE)
+    float* cvec = c.take<float>(N);
+    float* part = c.take<float>(col_partial_floats(M, N));
+    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dG, A, M, N, Qrb, 1);          // :349-351
+    PSGD_LAUNCH_CHECK(ctx);
+    PSGD_RETURN_IF(col_reduce(ctx, 0, Qlb, dX, nullptr, M, N, part, cvec, nullptr));
+    norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dX, cvec, Bt, M, N, Qrb);    // :353-356
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+
+  // ---- left factor -----------------------------------------------------------------------------
+  if (kl == PSGD_FACTOR_DENSE) {
+    float* grad1 = c.take<float>((size_t)M * M);
+    PSGD_RETURN_IF(gram_diff(ctx, A, Bt, M, N, true, grad1, &sc->max1));                // psgd.py:175 / :301
+    PSGD_RETURN_IF(factor_step(ctx, grad1, Qlb, M, &sc->max1, step, tiny, Ql_out));     // psgd.py:177, :179
+  } else {
+    float* g1d = c.take<float>(M);
+    float* g1b = c.take<float>(M);
+    int rows_grid = M < ctx->num_sms * 8 ? M : ctx->num_sms * 8;
+    row_stats_kernel<<<rows_grid, 128, 0, st>>>(A, Bt, M, N, g1d, g1b, sc);             // psgd.py:235-239
+    PSGD_LAUNCH_CHECK(ctx);
+    norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(Qlb, g1d, g1b, Ql_out, M, step, tiny, sc);   // :240-241
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  // ---- right factor ----------------------------------------------------------------------------
+  if (kr == PSGD_FACTOR_DENSE) {
+    float* grad2 = c.take<float>((size_t)N * N);
+    PSGD_RETURN_IF(gram_diff(ctx, A, Bt, M, N, false, grad2, &sc->max2));               // psgd.py:176 / :243
+    PSGD_RETURN_IF(factor_step(ctx, grad2, Qrb, N, &sc->max2, step, tiny, Qr_out));
+  } else {
+    float* sa = c.take<float>(N);
+    float* sb = c.take<float>(N);
+    float* grad2 = c.take<float>(N);
+    float* part = c.take<float>(col_partial_floats(M, N));
+    PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, A, Bt, M, N, part, sa, sb));             // psgd.py:304 / :366
+    scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(sa, sb, N, grad2, sc);
+    PSGD_LAUNCH_CHECK(ctx);
+    scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(Qrb, grad2, Qr_out, N, step, tiny, sc);     // :307
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
+
+static size_t update_ws_bytes(int kl, int kr, int64_t M, int64_t N) {
+  const size_t MN = (size_t)M * N;
+  size_t f = fsize(kl, M) + fsize(kr, N) + 3 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
+             2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */;
+  return f * sizeof(float) + 64 * 256 + tc::extra_ws_bytes(M, N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// canonical applies
+// ---------------------------------------------------------------------------------------------
+// P = X (Qr^T Qr) with the reference's association switch           psgd.py:189-192, :260-263
+static int right_dense_apply(psgd_ctx* ctx, const float* X, const float* Qr, int M, int N, float* tmp_nn,
+                             float* tmp_mn, float* out) {
+  if (M < N) {
+    la::Gemm g1; g1.M = M; g1.N = N; g1.K = N; g1.A = X; g1.lda = N; g1.B = Qr; g1.ldb = N; g1.tb = true;
+    g1.C = tmp_mn; g1.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = tmp_mn; g2.lda = N; g2.B = Qr; g2.ldb = N; g2.C = out; g2.ldc = N;
+    return gemm(ctx, g2);
+  }
+  la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
+  g1.C = tmp_nn; g1.ldc = N;
+  PSGD_RETURN_IF(gemm(ctx, g1));
+  la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = X; g2.lda = N; g2.B = tmp_nn; g2.ldb = N; g2.C = out; g2.ldc = N;
+  return gemm(ctx, g2);
+}
+
+// P = (Ql^T Ql) X with the reference's association switch           psgd.py:318-321
+static int left_dense_apply(psgd_ctx* ctx, const float* Ql, const float* X, int M, int N, float* tmp_mm,
+                            float* tmp_mn, float* out, const float* colscale_sq) {
+  if (M < N) {
+    la::Gemm g1; g1.M = M; g1.N = M; g1.K = M; g1.A = Ql; g1.lda = M; g1.ta = true; g1.B = Ql; g1.ldb = M;
+    g1.C = tmp_mm; g1.ldc = M;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = tmp_mm; g2.lda = M; g2.B = X; g2.ldb = N; g2.C = out; g2.ldc = N;
+    g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
+    return gemm(ctx, g2);
+  }
+  la::Gemm g1; g1.M = M; g1.N = N; g1.K = M; g1.A = Ql; g1.lda = M; g1.B = X; g1.ldb = N; g1.C = tmp_mn; g1.ldc = N;
+  PSGD_RETURN_IF(gemm(ctx, g1));
+  la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = Ql; g2.lda = M; g2.ta = true; g2.B = tmp_mn; g2.ldb = N;
+  g2.C = out; g2.ldc = N;
+  g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
+  return gemm(ctx, g2);
+}
+
+static int apply_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* G,
+                           float* out, int M, int N, WsCarver& c) {
+  const size_t MN = (size_t)M * N;
+  cudaStream_t st = ctx->stream;
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
+    float* t1 = c.take<float>(MN);
+    float* t2 = c.take<float>(MN);
+    if (M < N) {                                                          // psgd.py:190
+      float* P = c.take<float>((size_t)M * M);
+      PSGD_RETURN_IF(left_dense_apply(ctx, Ql, G, M, N, P, nullptr, t1, nullptr));      // (Ql^T Ql) G
+      la::Gemm g3; g3.M = M; g3.N = N; g3.K = N; g3.A = t1; g3.lda = N; g3.B = Qr; g3.ldb = N; g3.tb = true;
+      g3.C = t2; g3.ldc = N;
+      PSGD_RETURN_IF(gemm(ctx, g3));
+      la::Gemm g4; g4.M = M; g4.N = N; g4.K = N; g4.A = t2; g4.lda = N; g4.B = Qr; g4.ldb = N; g4.C = out; g4.ldc = N;
+      return gemm(ctx, g4);
+    }
+    float* P = c.take<float>((size_t)N * N);                              // psgd.py:192
+    la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
+    g1.C = P; g1.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g1));
+    la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = G; g2.lda = N; g2.B = P; g2.ldb = N; g2.C = t1; g2.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g2));
+    la::Gemm g3; g3.M = M; g3.N = N; g3.K = M; g3.A = Ql; g3.lda = M; g3.B = t1; g3.ldb = N; g3.C = t2; g3.ldc = N;
+    PSGD_RETURN_IF(gemm(ctx, g3));
+    la::Gemm g4; g4.M = M; g4.N = N; g4.K = M; g4.A = Ql; g4.lda = M; g4.ta = true; g4.B = t2; g4.ldb = N;
+    g4.C = out; g4.ldc = N;
+    return gemm(ctx, g4);
+  }
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
+    float* P = c.take<float>((size_t)M * M);
+    float* t1 = c.take<float>(MN);
+    return left_dense_apply(ctx, Ql, G, M, N, P, t1, out, Qr);
+  }
+  // normalization-format left factor                                      psgd.py:258-270, :383-391
+  float* t1 = c.take<float>(MN);
+  float* t2 = c.take<float>(MN);
+  float* addlast = c.take<float>(N);
+  float* part = c.take<float>(col_partial_floats(M, N));
+  const float* P = nullptr;
+  if (kr == PSGD_FACTOR_DENSE) {
+    float* tnn = c.take<float>((size_t)N * N);
+    float* t3 = c.take<float>(MN);
+    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, G, t1, M, N, nullptr, 0);
+    PSGD_LAUNCH_CHECK(ctx);
+    PSGD_RETURN_IF(right_dense_apply(ctx, t1, Qr, M, N, tnn, t3, t2));
+    P = t2;
+  } else {
+    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, G, t1, M, N, Qr, 2);
+    PSGD_LAUNCH_CHECK(ctx);
+    P = t1;
+  }
+  PSGD_RETURN_IF(col_reduce(ctx, 1, Ql, P, nullptr, M, N, part, addlast, nullptr));     // psgd.py:265 / :386
+  norm_left_out_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, P, addlast, out, M, N);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+static size_t apply_ws_bytes(int64_t M, int64_t N) {
+  const size_t MN = (size_t)M * N;
+  size_t f = 5 * MN + (size_t)M * M + (size_t)N * N + 4 * (size_t)(M + N) + col_partial_floats((int)M, (int)N);
+  return f * sizeof(float) + 64 * 256 + tc::extra_ws_bytes(M, N);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dispatch with the reference's mirroring                              psgd.py:82-110, :124-152
+// ---------------------------------------------------------------------------------------------
+static bool is_canonical(int kl, int kr) {
+  return (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) || (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) ||
+         (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) || (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE);
+}
+static bool is_mirrored(int kl, int kr) { return is_canonical(kr, kl) && !is_canonical(kl, kr); }
+
+int update_layer(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* dX, const float* dG,
+                 float* Ql_out, float* Qr_out, int64_t M, int64_t N, float step, float tiny, WsCarver& c) {
+  if (is_canonical(kl, kr))
+    return update_canonical(ctx, kl, kr, Ql, Qr, dX, dG, Ql_out, Qr_out, (int)M, (int)N, step, tiny, c);
+  if (is_mirrored(kl, kr)) {
+    // (dense,norm) / (scale,dense) / (scale,norm): run the canonical kernel on (Qr, Ql, dX^T, dG^T)
+    float* dXt = c.take<float>((size_t)M * N);
+    float* dGt = c.take<float>((size_t)M * N);
+    PSGD_RETURN_IF(la::transpose(ctx, dX, (int)N, dXt, (int)M, (int)M, (int)N));
+    PSGD_RETURN_IF(la::transpose(ctx, dG, (int)N, dGt, (int)M, (int)M, (int)N));
+    return update_canonical(ctx, kr, kl, Qr, Ql, dXt, dGt, Qr_out, Ql_out, (int)N, (int)M, step, tiny, c);
+  }
+  set_error("Unknown Kronecker product preconditioner (left kind %d, right kind %d)", kl, kr);
+  return PSGD_ERR_UNSUPPORTED;
+}
+
+int apply_layer(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* G, float* out,
+                int64_t M, int64_t N, WsCarver& c) {
+  if (is_canonical(kl, kr)) return apply_canonical(ctx, kl, kr, Ql, Qr, G, out, (int)M, (int)N, c);
+  if (is_mirrored(kl, kr)) {
+    float* Gt = c.take<float>((size_t)M * N);
+    float* Ot = c.take<float>((size_t)M * N);
+    PSGD_RETURN_IF(la::transpose(ctx, G, (int)N, Gt, (int)M, (int)M, (int)N));
+    PSGD_RETURN_IF(apply_canonical(ctx, kr, kl, Qr, Ql, Gt, Ot, (int)N, (int)M, c));
+    return la::transpose(ctx, Ot, (int)M, out, (int)N, (int)N, (int)M);
+  }
+  set_error("Unknown Kronecker product preconditioner (left kind %d, right kind %d)", kl, kr);
+  return PSGD_ERR_UNSUPPORTED;
+}
+
+static int check_layer(const char* what, int kl, int kr, int64_t M, int64_t N) {
+  PSGD_REQUIRE(M >= 1 && N >= 1 && M < (1LL << 30) && N < (1LL << 30), PSGD_ERR_BAD_SHAPE, "%s: bad shape [%lld,%lld]",
+               what, (long long)M, (long long)N);
+  PSGD_REQUIRE(kl >= 0 && kl <= 2 && kr >= 0 && kr <= 2, PSGD_ERR_BAD_SHAPE, "%s: bad factor kinds %d,%d", what, kl, kr);
+  return PSGD_OK;
+}
+
+}  // namespace kron
+}  // namespace psgd
+
+using namespace psgd;
+
+extern "C" int psgd_kron_update(psgd_ctx* ctx, int kind_l, int kind_r, const float* Ql, const float* Qr,
+                                const float* dX, const float* dG, float* Ql_out, float* Qr_out, int64_t M, int64_t N,
+                                float step, float tiny) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_RETURN_IF(kron::check_layer("kron update", kind_l, kind_r, M, N));
+  PSGD_REQUIRE(Ql && Qr && dX && dG && Ql_out && Qr_out, PSGD_ERR_BAD_POINTER, "kron update: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  PSGD_RETURN_IF(ctx->reserve(kron::update_ws_bytes(kind_l, kind_r, M, N)));
+  WsCarver c(ctx->ws);
+  return kron::update_layer(ctx, kind_l, kind_r, Ql, Qr, dX, dG, Ql_out, Qr_out, M, N, step, tiny, c);
+}
+
+extern "C" int psgd_kron_apply(psgd_ctx* ctx, int kind_l, int kind_r, const float* Ql, const float* Qr,
+                               const float* G, float* out, int64_t M, int64_t N) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_RETURN_IF(kron::check_layer("kron apply", kind_l, kind_r, M, N));
+  PSGD_REQUIRE(Ql && Qr && G && out, PSGD_ERR_BAD_POINTER, "kron apply: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  PSGD_RETURN_IF(ctx->reserve(kron::apply_ws_bytes(M, N)));
+  WsCarver c(ctx->ws);
+  return kron::apply_layer(ctx, kind_l, kind_r, Ql, Qr, G, out, M, N, c);
+}
+
+// Ragged list of layers on one stream.  Layers are independent (mnist_with_lenet5.py:51-53), so they share
+// one workspace sized for the largest layer and run back to back; launch latency of small layers is hidden
+// by the caller capturing the call into a CUDA graph (see psgd_tf_b200.KronBatch).
+extern "C" int psgd_kron_update_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count, float step,
+                                        float tiny) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(count >= 0 && (layers || count == 0), PSGD_ERR_BAD_POINTER, "kron batched update: null layer list");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t need = 0;
+  for (int i = 0; i < count; ++i) {
+    const psgd_kron_layer& L = layers[i];
+    PSGD_RETURN_IF(kron::check_layer("kron batched update", L.kind_l, L.kind_r, L.M, L.N));
+    PSGD_REQUIRE(L.Ql && L.Qr && L.dX && L.dG && L.Ql_out && L.Qr_out, PSGD_ERR_BAD_POINTER,
+                 "kron batched update: null device pointer in layer %d", i);
+    size_t b = kron::update_ws_bytes(L.kind_l, L.kind_r, L.M, L.N);
+    if (b > need) need = b;
+  }
+  PSGD_RETURN_IF(ctx->reserve(need));
+  for (int i = 0; i < count; ++i) {
+    const psgd_kron_layer& L = layers[i];
+    WsCarver c(ctx->ws);
+    PSGD_RETURN_IF(kron::update_layer(ctx, L.kind_l, L.kind_r, L.Ql, L.Qr, L.dX, L.dG, L.Ql_out, L.Qr_out, L.M, L.N,
+                                      step, tiny, c));
+  }
+  return PSGD_OK;
+}
+
+extern "C" int psgd_kron_apply_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(count >= 0 && (layers || count == 0), PSGD_ERR_BAD_POINTER, "kron batched apply: null layer list");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  size_t need = 0;
+  for (int i = 0; i < count; ++i) {
+    const psgd_kron_layer& L = layers[i];
+    PSGD_RETURN_IF(kron::check_layer("kron batched apply", L.kind_l, L.kind_r, L.M, L.N));
+    PSGD_REQUIRE(L.Ql && L.Qr && L.G && L.out, PSGD_ERR_BAD_POINTER, "kron batched apply: null device pointer in layer %d", i);
+    size_t b = kron::apply_ws_bytes(L.M, L.N);
+    if (b > need) need = b;
+  }
+  PSGD_RETURN_IF(ctx->reserve(need));
+  for (int i = 0; i < count; ++i) {
+    const psgd_kron_layer& L = layers[i];
+    WsCarver c(ctx->ws);
+    PSGD_RETURN_IF(kron::apply_layer(ctx, L.kind_l, L.kind_r, L.Ql, L.Qr, L.G, L.out, L.M, L.N, c));
+  }
+  return PSGD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// dense full-matrix preconditioner                                      psgd.py:26-63
+// ---------------------------------------------------------------------------------------------
+extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx, const float* dg, float* Q_out,
+                                 int64_t n64, float step, float tiny) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n64 >= 1 && n64 < (1 << 20), PSGD_ERR_BAD_SHAPE, "dense update: n=%lld", (long long)n64);
+  PSGD_REQUIRE(Q && dx && dg && Q_out, PSGD_ERR_BAD_POINTER, "dense update: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int n = (int)n64;
+  PSGD_RETURN_IF(ctx->reserve(((size_t)n * n + 4 * (size_t)n) * sizeof(float) + 16 * 256 + tc::extra_ws_bytes(n, n)));
+  WsCarver c(ctx->ws);
+  kron::Scal* sc = c.take<kron::Scal>(1);
+  float* a = c.take<float>(n);
+  float* b = c.take<float>(n);
+  float* grad = c.take<float>((size_t)n * n);
+  PSGD_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(kron::Scal), ctx->stream));
+  la::Gemm g1;                                                             // a = Q dg          psgd.py:38
+  g1.M = n; g1.N = 1; g1.K = n; g1.A = Q; g1.lda = n; g1.B = dg; g1.ldb = 1; g1.C = a; g1.ldc = 1;
+  PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
+  PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx    psgd.py:39
+  la::Gemm g2;                                                             // triu(a a^T - b b^T)   psgd.py:40
+  g2.M = n; g2.N = n; g2.K = 1; g2.A = a; g2.lda = 1; g2.B = a; g2.ldb = 1; g2.tb = true;
+  g2.K2 = 1; g2.A2 = b; g2.lda2 = 1; g2.B2 = b; g2.ldb2 = 1; g2.tb2 = true;
+  g2.C = grad; g2.ldc = n; g2.triu = true; g2.maxabs = &sc->max1;
+  PSGD_RETURN_IF(la::gemm_simt(ctx, g2));
+  return kron::factor_step(ctx, grad, Q, n, &sc->max1, step, tiny, Q_out);   // psgd.py:41-42
+}
+
+extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n64) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n64 >= 1 && n64 < (1 << 20), PSGD_ERR_BAD_SHAPE, "dense apply: n=%lld", (long long)n64);
+  PSGD_REQUIRE(Q && g && out, PSGD_ERR_BAD_POINTER, "dense apply: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int n = (int)n64;
+  PSGD_RETURN_IF(ctx->reserve((size_t)n * sizeof(float) + 1024));
+  float* t = static_cast<float*>(ctx->ws);
+  la::Gemm g1;                                                             // t = Q g            psgd.py:55
+  g1.M = n; g1.N = 1; g1.K = n; g1.A = Q; g1.lda = n; g1.B = g; g1.ldb = 1; g1.C = t; g1.ldc = 1;
+  PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
+  la::Gemm g2;                                                             // out = Q^T t
+  g2.M = n; g2.N = 1; g2.K = n; g2.A = Q; g2.lda = n; g2.ta = true; g2.B = t; g2.ldb = 1; g2.C = out; g2.ldc = 1;
+  return la::gemm_simt(ctx, g2);
+}

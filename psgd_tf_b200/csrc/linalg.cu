@@ -1,0 +1,278 @@
+// SIMT fp32 engine of the device linear-algebra vocabulary (see linalg.cuh).
+#include "linalg.cuh"
+
+namespace psgd {
+namespace la {
+
+// ---------------------------------------------------------------------------------------------
+// GEMM: 64x64x16 tiles, 256 threads, 4x4 outputs per thread, fp32 FMA accumulation
+// ---------------------------------------------------------------------------------------------
+constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+
+struct GemmDev {
+  Gemm g;
+};
+
+__device__ __forceinline__ void load_tiles(const float* __restrict__ A, int lda, bool ta, const float* __restrict__ B,
+                                           int ldb, bool tb, int M, int N, int K, int m0, int n0, int k0,
+                                           float (*As)[BM + PAD], float (*Bs)[BN + PAD], int tid) {
+#pragma unroll
+  for (int e = 0; e < (BM * BK) / 256; ++e) {
+    const int idx = tid + 256 * e;
+    int m, k;
+    if (ta) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
+    const int gm = m0 + m, gk = k0 + k;
+    float v = 0.f;
+    if (gm < M && gk < K) v = ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
+    As[k][m] = v;
+  }
+#pragma unroll
+  for (int e = 0; e < (BN * BK) / 256; ++e) {
+    const int idx = tid + 256 * e;
+    int n, k;
+    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+    const int gn = n0 + n, gk = k0 + k;
+    float v = 0.f;
+    if (gn < N && gk < K) v = tb ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
+    Bs[k][n] = v;
+  }
+}
+
+__global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
+  __shared__ __align__(16) float As[BK][BM + PAD];
+  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  const int tid = threadIdx.x;
+  const int tx = tid % 16, ty = tid / 16;
+  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
+  if (g.triu && m0 >= n0 + BN) {
+    // tile entirely below the diagonal: result is zero after masking
+    for (int e = tid; e < BM * BN; e += 256) {
+      const int m = m0 + e / BN, n = n0 + e % BN;
+      if (m < g.M && n < g.N) g.C[(size_t)m * g.ldc + n] = 0.f;
+    }
+    return;
+  }
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  for (int pass = 0; pass < 2; ++pass) {
+    const float* A = pass ? g.A2 : g.A;
+    const float* B = pass ? g.B2 : g.B;
+    const int lda = pass ? g.lda2 : g.lda, ldb = pass ? g.ldb2 : g.ldb;
+    const bool ta = pass ? g.ta2 : g.ta, tb = pass ? g.tb2 : g.tb;
+    const int K = pass ? g.K2 : g.K;
+    const float sign = pass ? -1.f : 1.f;
+    if (K <= 0 || A == nullptr) continue;
+    for (int k0 = 0; k0 < K; k0 += BK) {
+      load_tiles(A, lda, ta, B, ldb, tb, g.M, g.N, K, m0, n0, k0, As, Bs, tid);
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < BK; ++k) {
+        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+        const float a[4] = {sign * a4.x, sign * a4.y, sign * a4.z, sign * a4.w};
+        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      }
+      __syncthreads();
+    }
+  }
+
+  float mu = 0.f;
+  if (g.D) mu = g.step / (*g.mu_max + g.tiny);
+  float mx = 0.f;
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= g.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= g.N) continue;
+      float v = acc[i][j];
+      if (g.colscale) {
+        float s = g.colscale[n];
+        if (g.colscale_sq) s = s * s;
+        v = g.colscale_recip ? v * (1.0f / s) : v * s;
+      }
+      if (g.triu && m > n) v = 0.f;
+      if (g.D) v = g.D[(size_t)m * g.ldd + n] - mu * v;
+      mx = fmaxf(mx, fabsf(v));
+      g.C[(size_t)m * g.ldc + n] = v;
+    }
+  }
+  if (g.maxabs) {
+    mx = warp_max(mx);
+    if ((tid & 31) == 0 && mx > 0.f) atomic_max_nonneg(g.maxabs, mx);
+  }
+}
+
+int gemm_simt(psgd_ctx* ctx, const Gemm& g) {
+  if (g.M <= 0 || g.N <= 0) return PSGD_OK;
+  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
+  gemm_simt_kernel<<<grid, 256, 0, ctx->stream>>>(g);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// triangular solves, left-looking, 32-row blocks: one launch per block step
+// ---------------------------------------------------------------------------------------------
+constexpr int NB = 32;
+
+// X[I,:] = Qii^-T ( B[I,:] - sum_{k < i0} Q[k, I]^T X[k, :] ),   CTA = 32 block rows x 32 columns
+__global__ void __launch_bounds__(256) trsm_left_step_kernel(const float* __restrict__ Q, int ldq,
+                                                             const float* __restrict__ B, int ldb,
+                                                             float* __restrict__ X, int ldx, int n, int m, int i0) {
+  __shared__ float Qs[NB][NB + 1];   // Qs[k][i] = Q[k0+k, i0+i]
+  __shared__ float Xs[NB][NB + 1];   // Xs[k][c] = X[k0+k, c0+c]
+  const int tid = threadIdx.x;
+  const int c0 = blockIdx.x * NB;
+  const int lr = tid / NB;          // 0..7
+  const int lc = tid % NB;          // 0..31
+  const int ib = min(NB, n - i0);   // rows in this block
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr, lr+8, lr+16, lr+24 ; column lc
+  for (int k0 = 0; k0 < i0; k0 += NB) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int k = lr + 8 * e;
+      Qs[k][lc] = (i0 + lc < n) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;       // k0+k < i0 <= n always
+      Xs[k][lc] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const float x = Xs[k][lc];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(Qs[k][lr + 8 * e], x, acc[e]);
+    }
+    __syncthreads();
+  }
+  // diagonal block: forward substitution with Qii^T (only the upper triangle of Qii is read)
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int i = lr + 8 * e;
+    Qs[i][lc] = (i < ib && lc < ib && i <= lc) ? Q[(size_t)(i0 + i) * ldq + i0 + lc] : 0.f;   // Qs[k][i], k<=i
+    float b = 0.f;
+    if (i < ib && c0 + lc < m) b = B[(size_t)(i0 + i) * ldb + c0 + lc] - acc[e];
+    Xs[i][lc] = b;
+  }
+  __syncthreads();
+  if (tid < NB && c0 + tid < m) {
+    const int c = tid;
+    for (int i = 0; i < ib; ++i) {
+      float s = Xs[i][c];
+      for (int k = 0; k < i; ++k) s = fmaf(-Qs[k][i], Xs[k][c], s);
+      s = s / Qs[i][i];
+      Xs[i][c] = s;
+      X[(size_t)(i0 + i) * ldx + c0 + c] = s;
+    }
+  }
+}
+
+// X[:,J] = ( B[:,J] - sum_{k < j0} X[:, k] Q[k, J] ) Qjj^-1,   CTA = 32 rows x 32 block columns
+__global__ void __launch_bounds__(256) trsm_right_step_kernel(const float* __restrict__ Q, int ldq,
+                                                              const float* __restrict__ B, int ldb,
+                                                              float* __restrict__ X, int ldx, int m, int n, int j0) {
+  __shared__ float Qs[NB][NB + 1];   // Qs[k][j] = Q[k0+k, j0+j]
+  __shared__ float Xs[NB][NB + 1];   // Xs[r][k] = X[r0+r, k0+k]
+  const int tid = threadIdx.x;
+  const int r0 = blockIdx.x * NB;
+  const int lr = tid / NB;          // 0..7
+  const int lc = tid % NB;          // 0..31
+  const int jb = min(NB, n - j0);
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr+8e, column lc
+  for (int k0 = 0; k0 < j0; k0 += NB) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const int r = lr + 8 * e;
+      Qs[r][lc] = (j0 + lc < n) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
+      Xs[r][lc] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int k = 0; k < NB; ++k) {
+      const float q = Qs[k][lc];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) acc[e] = fmaf(Xs[lr + 8 * e][k], q, acc[e]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = lr + 8 * e;
+    Qs[r][lc] = (r < jb && lc < jb && r <= lc) ? Q[(size_t)(j0 + r) * ldq + j0 + lc] : 0.f;   // Qs[k][j], k<=j
+    float b = 0.f;
+    if (r0 + r < m && lc < jb) b = B[(size_t)(r0 + r) * ldb + j0 + lc] - acc[e];
+    Xs[r][lc] = b;
+  }
+  __syncthreads();
+  if (tid < NB && r0 + tid < m) {
+    const int r = tid;
+    for (int j = 0; j < jb; ++j) {
+      float s = Xs[r][j];
+      for (int k = 0; k < j; ++k) s = fmaf(-Xs[r][k], Qs[k][j], s);
+      s = s / Qs[j][j];
+      Xs[r][j] = s;
+      X[(size_t)(r0 + r) * ldx + j0 + j] = s;
+    }
+  }
+}
+
+int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx,
+                            int n, int m) {
+  if (n <= 0 || m <= 0) return PSGD_OK;
+  const int grid = (m + NB - 1) / NB;
+  for (int i0 = 0; i0 < n; i0 += NB) {
+    trsm_left_step_kernel<<<grid, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, n, m, i0);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
+
+int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
+                     int n) {
+  if (n <= 0 || m <= 0) return PSGD_OK;
+  const int grid = (m + NB - 1) / NB;
+  for (int j0 = 0; j0 < n; j0 += NB) {
+    trsm_right_step_kernel<<<grid, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, n, j0);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) transpose_kernel(const float* __restrict__ in, int ld_in,
+                                                        float* __restrict__ out, int ld_out, int rows, int cols) {
+  __shared__ float t[32][33];
+  const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;
+  const int tx = threadIdx.x % 32, ty = threadIdx.x / 32;
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int r = r0 + ty + 8 * e, c = c0 + tx;
+    t[ty + 8 * e][tx] = (r < rows && c < cols) ? in[(size_t)r * ld_in + c] : 0.f;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int e = 0; e < 4; ++e) {
+    const int c = c0 + ty + 8 * e, r = r0 + tx;
+    if (r < rows && c < cols) out[(size_t)c * ld_out + r] = t[tx][ty + 8 * e];
+  }
+}
+
+int transpose(psgd_ctx* ctx, const float* in, int ld_in, float* out, int ld_out, int rows, int cols) {
+  if (rows <= 0 || cols <= 0) return PSGD_OK;
+  dim3 grid((cols + 31) / 32, (rows + 31) / 32);
+  transpose_kernel<<<grid, 256, 0, ctx->stream>>>(in, ld_in, out, ld_out, rows, cols);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+}  // namespace la
+}  // namespace psgd

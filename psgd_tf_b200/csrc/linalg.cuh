@@ -1,0 +1,49 @@
+// Small device linear-algebra vocabulary shared by the Kronecker / dense preconditioner paths.
+// Everything is float32, row-major with explicit leading dimensions, enqueued on ctx->stream.
+//
+// Two GEMM engines sit behind the same descriptor:
+//   * SIMT fp32 (this header + linalg.cu): exact fp32 FMA accumulation, any shape/alignment; the
+//     engine for small/ragged layers (LeNet, NMT factors) and the cross-check for the tensor path;
+//   * tcgen05 3xTF32 (gemm_tc.cu): TMA-staged, TMEM-accumulated split-precision GEMM for large layers.
+#pragma once
+
+#include "common.cuh"
+
+namespace psgd {
+namespace la {
+
+// C = epilogue( op(A) op(B)  -  op(A2) op(B2) )
+struct Gemm {
+  int M = 0, N = 0, K = 0;
+  const float* A = nullptr; int lda = 0; bool ta = false;   // op(A): [M,K]
+  const float* B = nullptr; int ldb = 0; bool tb = false;   // op(B): [K,N]
+  int K2 = 0;                                               // optional second product, subtracted
+  const float* A2 = nullptr; int lda2 = 0; bool ta2 = false;
+  const float* B2 = nullptr; int ldb2 = 0; bool tb2 = false;
+  float* C = nullptr; int ldc = 0;
+  // epilogue
+  bool triu = false;              // zero the strictly lower triangle (tf.linalg.band_part(., 0, -1))
+  float* maxabs = nullptr;        // atomic max of |C| (after masking) -- must be zeroed by the caller
+  const float* D = nullptr; int ldd = 0;     // if set: C = D - mu * acc
+  const float* mu_max = nullptr;  // mu = step / (*mu_max + tiny)
+  float step = 0.f, tiny = 0.f;
+  const float* colscale = nullptr;   // acc *= colscale[n]   (or its reciprocal)
+  bool colscale_recip = false;
+  bool colscale_sq = false;          // use colscale[n]^2
+};
+
+int gemm_simt(psgd_ctx* ctx, const Gemm& g);
+
+// X = Q^-T B  (tf.linalg.triangular_solve(Q, B, lower=False, adjoint=True)): Q [n,n] upper, B,X [n,m].
+// Reads only the upper triangle of Q.  X may alias B.
+int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx,
+                            int n, int m);
+// X = B Q^-1 : Q [n,n] upper, B,X [m,n].  (== transpose of the above applied to B^T.)  X may alias B.
+int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
+                     int n);
+
+// out[c, r] = in[r, c]
+int transpose(psgd_ctx* ctx, const float* in, int ld_in, float* out, int ld_out, int rows, int cols);
+
+}  // namespace la
+}  // namespace psgd

@@ -1,0 +1,1047 @@
+// UVd preconditioner  Q = (I + U V^T) diag(d)  -- streaming sm_100a kernels.
+//
+// Replaces the TensorFlow op sequences of update_precond_UVd_math_ (psgd.py:554-617),
+// precond_grad_UVd_math (psgd.py:619-627) and IpUVtmatvec (psgd.py:540-544).
+//
+// Design (DESIGN.md section "UVd"): every big operand is indexed by parameter row, so each call is a
+// short chain of bandwidth-bound sweeps separated by tiny r x r solves:
+//
+//   update:  sweep 1  (reduce)  G = [U V]^T [U V | d*h | v/d]              -> r-sized Grams/vectors
+//            small 1            p, t, s1, s2  (two r x r LU solves)
+//            sweep 2  (map+reduce) a=Qh, b=Q^-T v, nablaD per row; max|nablaD|, a.a, b.b, a.b, a^T V ...
+//            small 2            mu_d, mu, rank-2 coefficient vectors
+//            sweep 3  (map)     d -= mu_d d nablaD ;  U (or V) -= rank-2 update
+//   apply:   sweep A1 (reduce)  U^T U, U^T(d g), V^T(d g)
+//            small A
+//            sweep A2 (map)     out = d (y + V t),  y = d g + U p
+//
+// Sweeps stage row tiles in shared memory with TMA bulk copies (cp.async.bulk, mbarrier pipeline,
+// one producer lane per CTA) so every global access is a full-line coalesced transaction although
+// rows are only 4r bytes; consumer warps read rows conflict-free from shared memory.  Cross-CTA
+// reductions are two-stage and fixed-order (per-CTA float partials -> one CTA summing in float64),
+// so results are deterministic and identical for any grid size.
+#include <math.h>
+
+#include "common.cuh"
+
+namespace psgd {
+namespace uvd {
+
+constexpr int kMapTile = 256;        // rows per pipeline stage of the map sweeps (one row per consumer lane)
+constexpr int kMaxStages = 8;
+constexpr int kMaxRank = 16;
+constexpr size_t kSmemBudget = 160 * 1024;
+
+enum Mode { kUpdate = 0, kApply = 1, kMatvec = 2 };
+
+// ---------------------------------------------------------------------------------------------
+// compile-time plan for the Gram sweep: which entries of  Z^T [Z | X]  (Z = [U V]) are needed and
+// how rows of that (upper-trapezoidal) table are split across warp roles.
+// ---------------------------------------------------------------------------------------------
+__host__ __device__ constexpr bool gp_needed(int R, int MODE, int i, int j) {
+  const int W = 2 * R;
+  if (MODE == kUpdate) return j >= i;                                   // full upper triangle + both X columns
+  if (MODE == kApply) return (j >= W) || (i < R && j < R && j >= i);    // U^T U, U^T x, V^T x
+  return (i >= R) && (j >= W);                                          // kMatvec: V^T x only
+}
+__host__ __device__ constexpr int gp_nx(int MODE) { return MODE == kUpdate ? 2 : 1; }
+__host__ __device__ constexpr int gp_row_count(int R, int MODE, int i) {
+  int c = 0;
+  for (int j = 0; j < 2 * R + gp_nx(MODE); ++j) c += gp_needed(R, MODE, i, j) ? 1 : 0;
+  return c;
+}
+__host__ __device__ constexpr int gp_total(int R, int MODE) {
+  int c = 0;
+  for (int i = 0; i < 2 * R; ++i) c += gp_row_count(R, MODE, i);
+  return c;
+}
+constexpr int kAccPerRole = 96;
+__host__ __device__ constexpr int gp_nroles(int R, int MODE) { return (gp_total(R, MODE) + kAccPerRole - 1) / kAccPerRole; }
+// first table row of role `role` (role >= nroles gives W)
+__host__ __device__ constexpr int gp_begin(int R, int MODE, int role) {
+  const int nroles = gp_nroles(R, MODE);
+  if (role >= nroles) return 2 * R;
+  const int target = (gp_total(R, MODE) * role) / nroles;
+  int c = 0;
+  for (int i = 0; i < 2 * R; ++i) {
+    if (c >= target) return i;
+    c += gp_row_count(R, MODE, i);
+  }
+  return 2 * R;
+}
+
+template <int R, int MODE>
+struct GramPlan {
+  static constexpr int W = 2 * R;
+  static constexpr int NX = gp_nx(MODE);
+  static constexpr int E = W + NX;
+  static constexpr int NROLES = gp_nroles(R, MODE);
+  // warps per role: keep the CTA at <= 12 warps so ptxas may use > 128 registers per thread
+  static constexpr int WPR = NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES <= 5 ? 2 : 1)));
+  static constexpr int ROWS_PER_LANE = (WPR >= 4) ? 1 : (WPR >= 2 ? 2 : 4);
+  static constexpr int TILE = WPR * 32 * ROWS_PER_LANE;          // rows per pipeline stage
+  static constexpr int CONSUMER_WARPS = NROLES * WPR;
+  static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
+  __host__ __device__ static constexpr bool needed(int i, int j) { return gp_needed(R, MODE, i, j); }
+  __host__ __device__ static constexpr int begin(int role) { return gp_begin(R, MODE, role); }
+};
+
+// ---------------------------------------------------------------------------------------------
+// row loaders (rows are 4R bytes; with a 16-byte aligned base the row start is aligned to
+// gcd(4R,16) bytes, which is the vector width used)
+// ---------------------------------------------------------------------------------------------
+template <int R>
+__device__ __forceinline__ void load_row(const float* __restrict__ p, float (&out)[R]) {
+  if constexpr (R % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k) {
+      float4 t = reinterpret_cast<const float4*>(p)[k];
+      out[4 * k] = t.x; out[4 * k + 1] = t.y; out[4 * k + 2] = t.z; out[4 * k + 3] = t.w;
+    }
+  } else if constexpr (R % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) {
+      float2 t = reinterpret_cast<const float2*>(p)[k];
+      out[2 * k] = t.x; out[2 * k + 1] = t.y;
+    }
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; ++k) out[k] = p[k];
+  }
+}
+template <int R>
+__device__ __forceinline__ void store_row(float* __restrict__ p, const float (&in)[R]) {
+  if constexpr (R % 4 == 0) {
+#pragma unroll
+    for (int k = 0; k < R / 4; ++k)
+      reinterpret_cast<float4*>(p)[k] = make_float4(in[4 * k], in[4 * k + 1], in[4 * k + 2], in[4 * k + 3]);
+  } else if constexpr (R % 2 == 0) {
+#pragma unroll
+    for (int k = 0; k < R / 2; ++k) reinterpret_cast<float2*>(p)[k] = make_float2(in[2 * k], in[2 * k + 1]);
+  } else {
+#pragma unroll
+    for (int k = 0; k < R; ++k) p[k] = in[k];
+  }
+}
+template <int R>
+__device__ __forceinline__ float dot_row(const float (&a)[R], const float* __restrict__ b) {
+  float s = 0.f;
+#pragma unroll
+  for (int k = 0; k < R; ++k) s = fmaf(a[k], b[k], s);
+  return s;
+}
+
+// ---------------------------------------------------------------------------------------------
+// shared-memory tile pipeline: NM matrices [kTile, R] + NV vectors [kTile] per stage
+// ---------------------------------------------------------------------------------------------
+template <int R, int NM, int NV, int TILE>
+struct TileLayout {
+  static constexpr int kTile = TILE;
+  static constexpr int kMatFloats = kTile * R;
+  static constexpr int kStageFloats = NM * kMatFloats + NV * kTile;
+  static constexpr uint32_t kStageBytes = kStageFloats * 4;
+  static constexpr int kStages =
+      (kSmemBudget / kStageBytes) < (size_t)kMaxStages ? (int)(kSmemBudget / kStageBytes) : kMaxStages;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 2 * kMaxStages * sizeof(uint64_t) + 16;
+  __device__ static float* mat(float* stage_base, int m) { return stage_base + m * kMatFloats; }
+  __device__ static float* vec(float* stage_base, int v) { return stage_base + NM * kMatFloats + v * kTile; }
+};
+
+struct SweepArgs {
+  const float* mat[2];
+  const float* vec[4];
+  int64_t n;          // rows
+  int direct;         // 1: bypass the TMA pipeline (debug / cross-check)
+};
+
+// Producer lane: stream this CTA's full tiles into the ring.
+template <int R, int NM, int NV, int TILE>
+__device__ __forceinline__ void producer_loop(const SweepArgs& a, float* smem, uint64_t* full, uint64_t* empty,
+                                              int64_t n_full_tiles) {
+  using L = TileLayout<R, NM, NV, TILE>;
+  constexpr int kTile = TILE;
+  int it = 0;
+  for (int64_t tile = blockIdx.x; tile < n_full_tiles; tile += gridDim.x, ++it) {
+    const int stage = it % L::kStages;
+    const uint32_t phase = (it / L::kStages) & 1;
+    mbar_wait(&empty[stage], phase ^ 1);
+    mbar_arrive_expect_tx(&full[stage], L::kStageBytes);
+    float* sb = smem + (size_t)stage * L::kStageFloats;
+#pragma unroll
+    for (int m = 0; m < NM; ++m)
+      bulk_g2s(L::mat(sb, m), a.mat[m] + tile * (int64_t)L::kMatFloats, L::kMatFloats * 4, &full[stage]);
+#pragma unroll
+    for (int v = 0; v < NV; ++v) bulk_g2s(L::vec(sb, v), a.vec[v] + tile * (int64_t)kTile, kTile * 4, &full[stage]);
+  }
+}
+
+template <int R, int NM, int NV, int TILE>
+__device__ __forceinline__ void pipeline_init(float*& smem, uint64_t*& full, uint64_t*& empty, unsigned char* raw,
+                                              int consumer_arrivals) {
+  using L = TileLayout<R, NM, NV, TILE>;
+  smem = reinterpret_cast<float*>(raw);
+  full = reinterpret_cast<uint64_t*>(raw + (size_t)L::kStages * L::kStageBytes);
+  empty = full + kMaxStages;
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < L::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&empty[s], consumer_arrivals);
+    }
+    mbar_fence_init();
+  }
+  __syncthreads();
+}
+
+// =============================================================================================
+// Sweep 1 / A1 / matvec-reduce:  G += Z^T [Z | X]  restricted to GramPlan::needed
+// =============================================================================================
+template <int R, int MODE>
+struct RowX {  // the X columns of one row
+  float x[GramPlan<R, MODE>::NX];
+};
+
+// X columns from the per-row vectors: update: (d*h, v/d) ; apply: d*g ; matvec: x
+template <int R, int MODE>
+__device__ __forceinline__ RowX<R, MODE> make_x(float v0, float v1, float v2) {
+  RowX<R, MODE> o;
+  if constexpr (MODE == kUpdate) {
+    o.x[0] = v0 * v1;   // d*h           psgd.py:569
+    o.x[1] = v2 / v0;   // v/d           psgd.py:576
+  } else if constexpr (MODE == kApply) {
+    o.x[0] = v0 * v1;   // d*g           psgd.py:625
+  } else {
+    o.x[0] = v0;
+  }
+  return o;
+}
+
+template <int R, int MODE, int ROLE>
+struct GramRole {
+  using P = GramPlan<R, MODE>;
+  static constexpr int I0 = P::begin(ROLE);
+  static constexpr int I1 = P::begin(ROLE + 1);
+  static constexpr int NI = (I1 - I0) > 0 ? (I1 - I0) : 1;
+  float acc[NI][P::E];
+
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int i = 0; i < NI; ++i)
+#pragma unroll
+      for (int j = 0; j < P::E; ++j) acc[i][j] = 0.f;
+  }
+  __device__ __forceinline__ void row(const float* __restrict__ urow, const float* __restrict__ vrow,
+                                      const RowX<R, MODE>& rx) {
+    float z[P::E];
+    {
+      float u[R], v[R];
+      load_row<R>(urow, u);
+      load_row<R>(vrow, v);
+#pragma unroll
+      for (int k = 0; k < R; ++k) { z[k] = u[k]; z[R + k] = v[k]; }
+#pragma unroll
+      for (int k = 0; k < P::NX; ++k) z[P::W + k] = rx.x[k];
+    }
+#pragma unroll
+    for (int i = I0; i < I1; ++i)
+#pragma unroll
+      for (int j = 0; j < P::E; ++j)
+        if (P::needed(i, j)) acc[i - I0][j] = fmaf(z[i], z[j], acc[i - I0][j]);
+  }
+  // warp butterfly, then lane 0 writes this warp's table rows into `dst` ([W][E] floats)
+  __device__ __forceinline__ void flush(float* dst, int lane) {
+#pragma unroll
+    for (int i = I0; i < I1; ++i)
+#pragma unroll
+      for (int j = 0; j < P::E; ++j)
+        if (P::needed(i, j)) {
+          float s = warp_sum(acc[i - I0][j]);
+          if (lane == 0) dst[i * P::E + j] = s;
+        }
+  }
+};
+
+template <int R, int MODE, int ROLE>
+__device__ __forceinline__ void gram_consumer(const SweepArgs& a, float* smem, uint64_t* full, uint64_t* empty,
+                                              int64_t n_full_tiles, int warp_in_role, int lane, float* warp_out) {
+  using P = GramPlan<R, MODE>;
+  constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
+  using L = TileLayout<R, 2, NV, P::TILE>;
+  GramRole<R, MODE, ROLE> role;
+  role.zero();
+  if (!a.direct) {
+    int it = 0;
+    for (int64_t tile = blockIdx.x; tile < n_full_tiles; tile += gridDim.x, ++it) {
+      const int stage = it % L::kStages;
+      const uint32_t phase = (it / L::kStages) & 1;
+      mbar_wait(&full[stage], phase);
+      float* sb = smem + (size_t)stage * L::kStageFloats;
+      const float* su = L::mat(sb, 0);
+      const float* sv = L::mat(sb, 1);
+#pragma unroll
+      for (int r0 = warp_in_role * 32 + lane; r0 < P::TILE; r0 += P::WPR * 32) {
+        const float v0 = L::vec(sb, 0)[r0];
+        const float v1 = NV > 1 ? L::vec(sb, NV > 1 ? 1 : 0)[r0] : 0.f;
+        const float v2 = NV > 2 ? L::vec(sb, NV > 2 ? 2 : 0)[r0] : 0.f;
+        role.row(su + r0 * R, sv + r0 * R, make_x<R, MODE>(v0, v1, v2));
+      }
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&empty[stage]);
+    }
+  }
+  // rows not covered by full tiles (one CTA owns that tail), or every row in direct mode:
+  // straight from global memory
+  {
+    int64_t first, step;
+    if (a.direct) {
+      first = ((int64_t)blockIdx.x * P::WPR + warp_in_role) * 32 + lane;
+      step = (int64_t)gridDim.x * P::WPR * 32;
+    } else {
+      const bool owner = blockIdx.x == (unsigned)(n_full_tiles % gridDim.x);
+      first = owner ? n_full_tiles * P::TILE + warp_in_role * 32 + lane : a.n;
+      step = P::WPR * 32;
+    }
+    for (int64_t r0 = first; r0 < a.n; r0 += step) {
+      const float v0 = a.vec[0][r0];
+      const float v1 = NV > 1 ? a.vec[NV > 1 ? 1 : 0][r0] : 0.f;
+      const float v2 = NV > 2 ? a.vec[NV > 2 ? 2 : 0][r0] : 0.f;
+      role.row(a.mat[0] + r0 * R, a.mat[1] + r0 * R, make_x<R, MODE>(v0, v1, v2));
+    }
+  }
+  role.flush(warp_out, lane);
+}
+
+template <int R, int MODE, int ROLE>
+__device__ __forceinline__ void gram_dispatch(int role, const SweepArgs& a, float* smem, uint64_t* full,
+                                              uint64_t* empty, int64_t n_full_tiles, int warp_in_role, int lane,
+                                              float* warp_out) {
+  using P = GramPlan<R, MODE>;
+  if constexpr (ROLE < P::NROLES) {
+    if (role == ROLE)
+      gram_consumer<R, MODE, ROLE>(a, smem, full, empty, n_full_tiles, warp_in_role, lane, warp_out);
+    else
+      gram_dispatch<R, MODE, ROLE + 1>(role, a, smem, full, empty, n_full_tiles, warp_in_role, lane, warp_out);
+  }
+}
+
+// partial: [gridDim.x][W*E] floats
+template <int R, int MODE>
+__global__ void __launch_bounds__(GramPlan<R, MODE>::THREADS, 1)
+    gram_sweep_kernel(SweepArgs a, float* __restrict__ partial) {
+  using P = GramPlan<R, MODE>;
+  constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float warp_tab[P::WPR][P::W * P::E];   // per (warp-in-role) table, rows owned by its role
+
+  float* smem; uint64_t* full; uint64_t* empty;
+  pipeline_init<R, 2, NV, P::TILE>(smem, full, empty, smem_raw, P::CONSUMER_WARPS);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_full_tiles = a.n / P::TILE;
+  if (warp == P::CONSUMER_WARPS) {
+    if (lane == 0 && !a.direct) producer_loop<R, 2, NV, P::TILE>(a, smem, full, empty, n_full_tiles);
+    __syncwarp();
+  } else {
+    const int role = warp / P::WPR, wir = warp % P::WPR;
+    gram_dispatch<R, MODE, 0>(role, a, smem, full, empty, n_full_tiles, wir, lane, warp_tab[wir]);
+  }
+  __syncthreads();
+  // fixed-order sum over the WPR warps of each role -> CTA partial
+  for (int k = threadIdx.x; k < P::W * P::E; k += blockDim.x) {
+    const int i = k / P::E, j = k % P::E;
+    float s = 0.f;
+    if (P::needed(i, j)) {
+#pragma unroll
+      for (int w = 0; w < P::WPR; ++w) s += warp_tab[w][k];
+    }
+    partial[(size_t)blockIdx.x * (P::W * P::E) + k] = s;
+  }
+}
+
+// =============================================================================================
+// small kernels (one CTA): fixed-order float64 reduction of CTA partials, r x r algebra
+// =============================================================================================
+__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int count,
+                                       double* __restrict__ out) {
+  for (int k = threadIdx.x; k < count; k += blockDim.x) {
+    double s = 0.0;
+    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * count + k];
+    out[k] = s;
+  }
+}
+
+// LU with partial pivoting (the algorithm class of tf.linalg.solve / LAPACK gesv), n <= kMaxRank.
+__device__ void lu_solve(int n, double* A /*n*n row-major, destroyed*/, double* b /*in: rhs, out: x*/) {
+  for (int k = 0; k < n; ++k) {
+    int piv = k;
+    double best = fabs(A[k * n + k]);
+    for (int i = k + 1; i < n; ++i)
+      if (fabs(A[i * n + k]) > best) { best = fabs(A[i * n + k]); piv = i; }
+    if (piv != k) {
+      for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[piv * n + j]; A[piv * n + j] = t; }
+      double t = b[k]; b[k] = b[piv]; b[piv] = t;
+    }
+    const double inv = 1.0 / A[k * n + k];
+    for (int i = k + 1; i < n; ++i) {
+      const double f = A[i * n + k] * inv;
+      for (int j = k + 1; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
+      b[i] -= f * b[k];
+    }
+  }
+  for (int i = n - 1; i >= 0; --i) {
+    double s = b[i];
+    for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * b[j];
+    b[i] = s / A[i * n + i];
+  }
+}
+
+// device-resident r-sized state shared by the sweeps of one call
+struct SmallState {
+  // after small 1
+  float p[kMaxRank];     // V^T (d h)
+  float t[kMaxRank];     // U^T Qh
+  float s1[kMaxRank];    // solve(IpVtU^T, U^T (v/d))
+  float s2[kMaxRank];    // solve(IpVtU,  V^T invQtv)
+  double IpVtU[kMaxRank * kMaxRank];
+  double UtU[kMaxRank * kMaxRank];
+  double VtV[kMaxRank * kMaxRank];
+  // after small 2
+  float mu_d;
+  float mu;              // V branch
+  float c1[kMaxRank];    // U branch: mu * atV IpVtU    | V branch: atU
+  float c2[kMaxRank];    // U branch: mu * btV IpVtU    | V branch: btU
+  float max_nabla;       // atomic max target of sweep 2
+  float maxU, maxV;      // balance
+  float rho;
+};
+
+// table accessors for G = Z^T [Z | X] stored [W][E] with only j >= i filled
+__device__ __forceinline__ double Gsym(const double* G, int E, int i, int j) { return i <= j ? G[i * E + j] : G[j * E + i]; }
+
+__global__ void uvd_small1_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
+  if (threadIdx.x != 0) return;
+  const int W = 2 * r, E = W + 2;
+  double A[kMaxRank * kMaxRank], rhs[kMaxRank], p[kMaxRank], s1[kMaxRank];
+  for (int i = 0; i < r; ++i)
+    for (int j = 0; j < r; ++j) {
+      st->UtU[i * r + j] = Gsym(G, E, i, j);
+      st->VtV[i * r + j] = Gsym(G, E, r + i, r + j);
+      // VtU[i][j] = sum_k V[k,i] U[k,j] = G[U_j][V_i]                       psgd.py:574-575
+      st->IpVtU[i * r + j] = G[j * E + (r + i)] + (i == j ? 1.0 : 0.0);
+    }
+  // p = V^T(dh);  t = U^T Qh = U^T dh + (U^T U) p                            psgd.py:569-570
+  for (int i = 0; i < r; ++i) p[i] = G[(r + i) * E + W];
+  for (int i = 0; i < r; ++i) {
+    double s = G[i * E + W];
+    for (int j = 0; j < r; ++j) s += st->UtU[i * r + j] * p[j];
+    st->p[i] = (float)p[i];
+    st->t[i] = (float)s;
+  }
+  // s1 = solve(IpVtU^T, U^T w)                                               psgd.py:577
+  for (int i = 0; i < r; ++i) {
+    for (int j = 0; j < r; ++j) A[i * r + j] = st->IpVtU[j * r + i];
+    rhs[i] = G[i * E + W + 1];
+  }
+  lu_solve(r, A, rhs);
+  for (int i = 0; i < r; ++i) { s1[i] = rhs[i]; st->s1[i] = (float)rhs[i]; }
+  // s2 = solve(IpVtU, V^T invQtv),  V^T invQtv = V^T w - (V^T V) s1          psgd.py:578
+  for (int i = 0; i < r; ++i) {
+    double s = G[(r + i) * E + W + 1];
+    for (int j = 0; j < r; ++j) { s -= st->VtV[i * r + j] * s1[j]; A[i * r + j] = st->IpVtU[i * r + j]; }
+    rhs[i] = s;
+  }
+  lu_solve(r, A, rhs);
+  for (int i = 0; i < r; ++i) st->s2[i] = (float)rhs[i];
+  st->max_nabla = 0.f;
+}
+
+// G2 layout: [0]=a.a [1]=b.b [2]=a.b [3..3+r)=a^T X  [3+r..3+2r)=b^T X   (X = V on the U branch, U on the V branch)
+__global__ void uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step, float tiny,
+                                  SmallState* __restrict__ st) {
+  if (threadIdx.x != 0) return;
+  st->mu_d = step / (st->max_nabla + tiny);                                  // psgd.py:582
+  const double aa = G2[0], bb = G2[1], ab = G2[2];
+  const double* atX = G2 + 3;
+  const double* btX = G2 + 3 + r;
+  const double* XtX = update_U ? st->VtV : st->UtU;
+  // ||X atX^T||^2 = atX (X^T X) atX^T  etc.                                  psgd.py:594-596 / :608-610
+  double qaa = 0, qbb = 0, qab = 0;
+  for (int i = 0; i < r; ++i) {
+    double ra = 0, rb = 0;
+    for (int j = 0; j < r; ++j) { ra += XtX[i * r + j] * atX[j]; rb += XtX[i * r + j] * btX[j]; }
+    qaa += atX[i] * ra; qbb += btX[i] * rb; qab += atX[i] * rb;
+  }
+  const float norm = sqrtf(fabsf((float)(aa * qaa + bb * qbb - 2.0 * ab * qab)));
+  const float mu = step / (norm + tiny);                                      // psgd.py:597 / :611
+  st->mu = mu;
+  if (update_U) {
+    for (int j = 0; j < r; ++j) {                                            // psgd.py:600-601
+      double s1 = 0, s2 = 0;
+      for (int i = 0; i < r; ++i) { s1 += atX[i] * st->IpVtU[i * r + j]; s2 += btX[i] * st->IpVtU[i * r + j]; }
+      st->c1[j] = mu * (float)s1;
+      st->c2[j] = mu * (float)s2;
+    }
+  } else {
+    for (int j = 0; j < r; ++j) { st->c1[j] = (float)atX[j]; st->c2[j] = (float)btX[j]; }
+  }
+}
+
+// apply / matvec: p = V^T x ; t = U^T x + (U^T U) p
+__global__ void uvd_small_apply_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
+  if (threadIdx.x != 0) return;
+  const int W = 2 * r, E = W + 1;
+  double p[kMaxRank];
+  for (int i = 0; i < r; ++i) p[i] = G[(r + i) * E + W];
+  for (int i = 0; i < r; ++i) {
+    double s = G[i * E + W];
+    for (int j = 0; j < r; ++j) s += Gsym(G, E, i, j) * p[j];
+    st->p[i] = (float)p[i];
+    st->t[i] = (float)s;
+  }
+}
+
+// =============================================================================================
+// map sweeps: one lane per row, all consumer warps equal
+// =============================================================================================
+constexpr int kMapConsumerWarps = 8;
+constexpr int kMapThreads = (kMapConsumerWarps + 1) * 32;
+
+enum MapKind { kMapUpd2 = 0, kMapUpd3U = 1, kMapUpd3V = 2, kMapApply2 = 3, kMapMatvec2 = 4 };
+
+template <int KIND> struct MapTraits;
+template <> struct MapTraits<kMapUpd2>   { static constexpr int NM = 2, NV = 3; static constexpr bool kStore = false; };
+template <> struct MapTraits<kMapUpd3U>  { static constexpr int NM = 1, NV = 4; static constexpr bool kStore = true; };
+template <> struct MapTraits<kMapUpd3V>  { static constexpr int NM = 1, NV = 4; static constexpr bool kStore = true; };
+template <> struct MapTraits<kMapApply2> { static constexpr int NM = 2, NV = 2; static constexpr bool kStore = false; };
+template <> struct MapTraits<kMapMatvec2>{ static constexpr int NM = 1, NV = 1; static constexpr bool kStore = false; };
+
+struct MapOut {
+  float* o0; float* o1; float* o2;   // per-row outputs (coalesced direct stores)
+  float* mat_out;                    // kStore kinds: updated matrix
+  float* vec_out;                    // kStore kinds: updated d
+  float* partial;                    // Upd2: [grid][3+2r] sums
+  SmallState* st;
+};
+
+// per-lane accumulators of sweep 2
+template <int R>
+struct Upd2Acc {
+  float aa = 0.f, bb = 0.f, ab = 0.f, mx = 0.f;
+  float atX[R], btX[R];
+  __device__ __forceinline__ void zero() {
+#pragma unroll
+    for (int k = 0; k < R; ++k) { atX[k] = 0.f; btX[k] = 0.f; }
+  }
+};
+
+template <int R, int KIND>
+struct MapBody {
+  // r-sized constants in registers
+  float k0[R], k1[R], k2[R], k3[R];
+  float mu_d, mu;
+  Upd2Acc<R> acc;
+  int update_U;
+
+  __device__ __forceinline__ void init(const SmallState* st, int upd_u) {
+    update_U = upd_u;
+    if constexpr (KIND == kMapUpd2) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; k2[k] = st->s1[k]; k3[k] = st->s2[k]; }
+      acc.zero();
+    } else if constexpr (KIND == kMapUpd3U || KIND == kMapUpd3V) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { k0[k] = st->c1[k]; k1[k] = st->c2[k]; }
+      mu_d = st->mu_d; mu = st->mu;
+    } else {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; }
+    }
+  }
+
+  // m0/m1: row pointers (shared or global); vec values v0..v3; `row` global row index;
+  // m0w: where to write the updated matrix row (shared tile or global)
+  __device__ __forceinline__ void row(const float* m0, const float* m1, float v0, float v1, float v2, float v3,
+                                      int64_t row, const MapOut& o, float* m0w, float* vecw) {
+    if constexpr (KIND == kMapUpd2) {
+      // v0=d v1=h v2=v                                                       psgd.py:569-581
+      float u[R], vv[R];
+      load_row<R>(m0, u);
+      load_row<R>(m1, vv);
+      const float dh = v0 * v1;
+      const float Qh = dh + dot_row<R>(u, k0);
+      const float Ph = v0 * (Qh + dot_row<R>(vv, k1));
+      const float w = v2 / v0;
+      const float b = w - dot_row<R>(vv, k2);
+      const float invPv = (b - dot_row<R>(u, k3)) / v0;
+      const float nd = Ph * v1 - v2 * invPv;
+      o.o0[row] = Qh; o.o1[row] = b; o.o2[row] = nd;
+      acc.mx = fmaxf(acc.mx, fabsf(nd));
+      acc.aa = fmaf(Qh, Qh, acc.aa); acc.bb = fmaf(b, b, acc.bb); acc.ab = fmaf(Qh, b, acc.ab);
+      if (update_U) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { acc.atX[k] = fmaf(Qh, vv[k], acc.atX[k]); acc.btX[k] = fmaf(b, vv[k], acc.btX[k]); }
+      } else {
+#pragma unroll
+        for (int k = 0; k < R; ++k) { acc.atX[k] = fmaf(Qh, u[k], acc.atX[k]); acc.btX[k] = fmaf(b, u[k], acc.btX[k]); }
+      }
+    } else if constexpr (KIND == kMapUpd3U) {
+      // v0=a v1=b v2=nablaD v3=d ; U -= mu (a c1 - b c2) (c pre-scaled)      psgd.py:584, :600-601
+      float u[R];
+      load_row<R>(m0, u);
+#pragma unroll
+      for (int k = 0; k < R; ++k) u[k] = u[k] - (v0 * k0[k] - v1 * k1[k]);
+      store_row<R>(m0w, u);
+      *vecw = v3 - (mu_d * v3) * v2;
+    } else if constexpr (KIND == kMapUpd3V) {
+      // V -= mu ((a + V atU^T) atU - (b + V btU^T) btU)                       psgd.py:584, :614-615
+      float vv[R];
+      load_row<R>(m0, vv);
+      const float sa = v0 + dot_row<R>(vv, k0);
+      const float sb = v1 + dot_row<R>(vv, k1);
+#pragma unroll
+      for (int k = 0; k < R; ++k) vv[k] = vv[k] - mu * (sa * k0[k] - sb * k1[k]);
+      store_row<R>(m0w, vv);
+      *vecw = v3 - (mu_d * v3) * v2;
+    } else if constexpr (KIND == kMapApply2) {
+      // v0=d v1=g                                                            psgd.py:625-626
+      float u[R], vv[R];
+      load_row<R>(m0, u);
+      load_row<R>(m1, vv);
+      const float dg = v0 * v1;
+      const float y = dg + dot_row<R>(u, k0);
+      o.o0[row] = v0 * (y + dot_row<R>(vv, k1));
+    } else {
+      // matvec: out = x + U_row . p   (m0 = U)                               psgd.py:544
+      float u[R];
+      load_row<R>(m0, u);
+      o.o0[row] = v0 + dot_row<R>(u, k0);
+    }
+  }
+};
+
+template <int R, int KIND>
+__global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, MapOut o, int update_U) {
+  using T = MapTraits<KIND>;
+  using L = TileLayout<R, T::NM, T::NV, kMapTile>;
+  static_assert(kMapTile == kMapConsumerWarps * 32, "one row per consumer lane per tile");
+  extern __shared__ __align__(128) unsigned char smem_raw[];
+  __shared__ float red[kMapConsumerWarps][4 + 2 * kMaxRank];
+
+  float* smem; uint64_t* full; uint64_t* empty;
+  // kStore kinds: one elected lane releases the stage after its bulk store has drained the tile
+  pipeline_init<R, T::NM, T::NV, kMapTile>(smem, full, empty, smem_raw, T::kStore ? 1 : kMapConsumerWarps);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int64_t n_full_tiles = a.n / kMapTile;
+
+  if (warp == kMapConsumerWarps) {
+    if (lane == 0 && !a.direct) producer_loop<R, T::NM, T::NV, kMapTile>(a, smem, full, empty, n_full_tiles);
+    __syncwarp();
+  } else {
+    MapBody<R, KIND> body;
+    body.init(o.st, update_U);
+    const int ct = warp * 32 + lane;                   // consumer thread id == row within tile
+    if (!a.direct) {
+      int it = 0;
+      for (int64_t tile = blockIdx.x; tile < n_full_tiles; tile += gridDim.x, ++it) {
+        const int stage = it % L::kStages;
+        const uint32_t phase = (it / L::kStages) & 1;
+        mbar_wait(&full[stage], phase);
+        float* sb = smem + (size_t)stage * L::kStageFloats;
+        {
+          const int r0 = ct;
+          float* m0 = L::mat(sb, 0);
+          const float* m1 = L::mat(sb, T::NM > 1 ? 1 : 0);
+          const float v0 = L::vec(sb, 0)[r0];
+          const float v1 = T::NV > 1 ? L::vec(sb, T::NV > 1 ? 1 : 0)[r0] : 0.f;
+          const float v2 = T::NV > 2 ? L::vec(sb, T::NV > 2 ? 2 : 0)[r0] : 0.f;
+          const float v3 = T::NV > 3 ? L::vec(sb, T::NV > 3 ? 3 : 0)[r0] : 0.f;
+          body.row(m0 + r0 * R, m1 + r0 * R, v0, v1, v2, v3, tile * kMapTile + r0, o, m0 + r0 * R,
+                   &L::vec(sb, T::NV > 3 ? 3 : 0)[r0]);
+        }
+        if constexpr (T::kStore) {
+          // rows were updated in place in the shared tile: publish to the async proxy, then one lane
+          // stores the tile with TMA and frees the stage once the engine has read it
+          fence_proxy_async_smem();
+          named_bar_sync(1, kMapConsumerWarps * 32);
+          if (ct == 0) {
+            bulk_s2g(o.mat_out + tile * (int64_t)L::kMatFloats, L::mat(sb, 0), L::kMatFloats * 4);
+            bulk_s2g(o.vec_out + tile * (int64_t)kMapTile, L::vec(sb, 3), kMapTile * 4);
+            bulk_commit();
+            bulk_wait_read0();
+            mbar_arrive(&empty[stage]);
+          }
+        } else {
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&empty[stage]);
+        }
+      }
+      if constexpr (T::kStore) {
+        if (ct == 0) bulk_wait0();
+      }
+    }
+    // tail rows (one CTA) / every row in direct mode: straight from and to global memory
+    {
+      int64_t first, step;
+      if (a.direct) {
+        first = (int64_t)blockIdx.x * kMapTile + ct;
+        step = (int64_t)gridDim.x * kMapTile;
+      } else {
+        first = (blockIdx.x == (unsigned)(n_full_tiles % gridDim.x)) ? n_full_tiles * kMapTile + ct : a.n;
+        step = kMapTile;
+      }
+      for (int64_t r0 = first; r0 < a.n; r0 += step) {
+        const float* m0 = a.mat[0] + r0 * R;
+        const float* m1 = a.mat[T::NM > 1 ? 1 : 0] + r0 * R;
+        const float v0 = a.vec[0][r0];
+        const float v1 = T::NV > 1 ? a.vec[T::NV > 1 ? 1 : 0][r0] : 0.f;
+        const float v2 = T::NV > 2 ? a.vec[T::NV > 2 ? 2 : 0][r0] : 0.f;
+        const float v3 = T::NV > 3 ? a.vec[T::NV > 3 ? 3 : 0][r0] : 0.f;
+        body.row(m0, m1, v0, v1, v2, v3, r0, o, T::kStore ? o.mat_out + r0 * R : nullptr,
+                 T::kStore ? o.vec_out + r0 : nullptr);
+      }
+    }
+    if constexpr (KIND == kMapUpd2) {
+      // warp butterflies -> per-warp slots -> fixed-order CTA partial
+      float mx = warp_max(body.acc.mx);
+      float s0 = warp_sum(body.acc.aa), s1 = warp_sum(body.acc.bb), s2 = warp_sum(body.acc.ab);
+      if (lane == 0) { red[warp][0] = s0; red[warp][1] = s1; red[warp][2] = s2; red[warp][3] = mx; }
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        float ta = warp_sum(body.acc.atX[k]), tb = warp_sum(body.acc.btX[k]);
+        if (lane == 0) { red[warp][4 + k] = ta; red[warp][4 + R + k] = tb; }
+      }
+    }
+  }
+  if constexpr (KIND == kMapUpd2) {
+    __syncthreads();
+    const int cnt = 3 + 2 * R;
+    if (threadIdx.x < cnt) {
+      const int src = threadIdx.x < 3 ? threadIdx.x : threadIdx.x + 1;
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kMapConsumerWarps; ++w) s += red[w][src];
+      o.partial[(size_t)blockIdx.x * cnt + threadIdx.x] = s;
+    }
+    if (threadIdx.x == 0) {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < kMapConsumerWarps; ++w) mx = fmaxf(mx, red[w][3]);
+      atomic_max_nonneg(&o.st->max_nabla, mx);
+    }
+  }
+}
+
+// =============================================================================================
+// balance (psgd.py:562-567): rho = sqrt(max|U| / max|V|); U /= rho; V *= rho
+// =============================================================================================
+__global__ void maxabs2_kernel(const float* __restrict__ A, const float* __restrict__ B, int64_t count,
+                               SmallState* st) {
+  float ma = 0.f, mb = 0.f;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = count / 4;
+  const float4* A4 = reinterpret_cast<const float4*>(A);
+  const float4* B4 = reinterpret_cast<const float4*>(B);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 x = A4[i], y = B4[i];
+    ma = fmaxf(ma, fmaxf(fmaxf(fabsf(x.x), fabsf(x.y)), fmaxf(fabsf(x.z), fabsf(x.w))));
+    mb = fmaxf(mb, fmaxf(fmaxf(fabsf(y.x), fabsf(y.y)), fmaxf(fabsf(y.z), fabsf(y.w))));
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    ma = fmaxf(ma, fabsf(A[i])); mb = fmaxf(mb, fabsf(B[i]));
+  }
+  ma = warp_max(ma); mb = warp_max(mb);
+  if ((threadIdx.x & 31) == 0) { atomic_max_nonneg(&st->maxU, ma); atomic_max_nonneg(&st->maxV, mb); }
+}
+__global__ void balance_rho_kernel(SmallState* st) { st->rho = sqrtf(st->maxU / st->maxV); }
+__global__ void balance_scale_kernel(float* __restrict__ U, float* __restrict__ V, int64_t count,
+                                     const SmallState* __restrict__ st) {
+  const float rho = st->rho;
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t n4 = count / 4;
+  float4* U4 = reinterpret_cast<float4*>(U);
+  float4* V4 = reinterpret_cast<float4*>(V);
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+    float4 x = U4[i], y = V4[i];
+    x.x /= rho; x.y /= rho; x.z /= rho; x.w /= rho;
+    y.x *= rho; y.y *= rho; y.z *= rho; y.w *= rho;
+    U4[i] = x; V4[i] = y;
+  }
+  for (int64_t i = n4 * 4 + (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < count; i += stride) {
+    U[i] = U[i] / rho; V[i] = rho * V[i];
+  }
+}
+__global__ void zero_small_kernel(SmallState* st) { st->maxU = 0.f; st->maxV = 0.f; st->max_nabla = 0.f; }
+
+// =============================================================================================
+// host orchestration
+// =============================================================================================
+static int grid_for(const psgd_ctx* ctx, int64_t n) {
+  int64_t tiles = (n + kMapTile - 1) / kMapTile;
+  int64_t g = ctx->num_sms;
+  if (tiles < g) g = tiles > 0 ? tiles : 1;
+  return (int)g;
+}
+
+template <int R, int MODE>
+static int launch_gram(psgd_ctx* ctx, const SweepArgs& a, float* partial, int grid) {
+  ProfScope prof(ctx, MODE == kUpdate ? PSGD_K_UVD_GRAM_UPDATE : PSGD_K_UVD_GRAM_APPLY);
+  using P = GramPlan<R, MODE>;
+  constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
+  using L = TileLayout<R, 2, NV, P::TILE>;
+  auto kern = gram_sweep_kernel<R, MODE>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes));
+    attr_done = true;
+  }
+  kern<<<grid, P::THREADS, L::kSmemBytes, ctx->stream>>>(a, partial);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+template <int R, int KIND>
+static int launch_map(psgd_ctx* ctx, const SweepArgs& a, const MapOut& o, int update_U, int grid) {
+  ProfScope prof(ctx, KIND == kMapUpd2 ? PSGD_K_UVD_MAP_UPDATE2
+                      : (KIND == kMapApply2 || KIND == kMapMatvec2) ? PSGD_K_UVD_MAP_APPLY : PSGD_K_UVD_MAP_UPDATE3);
+  using T = MapTraits<KIND>;
+  using L = TileLayout<R, T::NM, T::NV, kMapTile>;
+  auto kern = map_sweep_kernel<R, KIND>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes));
+    attr_done = true;
+  }
+  kern<<<grid, kMapThreads, L::kSmemBytes, ctx->stream>>>(a, o, update_U);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+static int hook_allreduce(psgd_ctx* ctx, void* buf, int64_t count, int op) {
+  if (!ctx->allreduce) return PSGD_OK;
+  int rc = ctx->allreduce(ctx->allreduce_user, buf, count, op, (void*)ctx->stream);
+  PSGD_REQUIRE(rc == 0, PSGD_ERR_COMM, "all-reduce hook returned %d", rc);
+  return PSGD_OK;
+}
+
+struct Scratch {
+  float* partial;      // [grid][max table] floats
+  double* G;           // reduced table
+  SmallState* st;
+  float* a; float* b; float* nd;   // N-vectors (update only)
+};
+
+static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, bool update, Scratch* s) {
+  const size_t table = (size_t)(2 * r) * (2 * r + 2);
+  size_t bytes = WsCarver::padded(sizeof(float) * table * grid) + WsCarver::padded(sizeof(double) * table) +
+                 WsCarver::padded(sizeof(SmallState)) + (update ? 3 * WsCarver::padded(sizeof(float) * (size_t)n) : 0);
+  PSGD_RETURN_IF(ctx->reserve(bytes));
+  WsCarver c(ctx->ws);
+  s->partial = c.take<float>(table * grid);
+  s->G = c.take<double>(table);
+  s->st = c.take<SmallState>(1);
+  if (update) { s->a = c.take<float>(n); s->b = c.take<float>(n); s->nd = c.take<float>(n); }
+  return PSGD_OK;
+}
+
+template <int R>
+static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, int64_t n,
+                       float step, float tiny, int balance, int update_U) {
+  const int grid = grid_for(ctx, n);
+  Scratch s;
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, true, &s));
+  cudaStream_t st = ctx->stream;
+
+  if (balance) {
+    zero_small_kernel<<<1, 1, 0, st>>>(s.st);
+    PSGD_LAUNCH_CHECK(ctx);
+    maxabs2_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
+    PSGD_LAUNCH_CHECK(ctx);
+    PSGD_RETURN_IF(hook_allreduce(ctx, &s.st->maxU, 2, 1));
+    balance_rho_kernel<<<1, 1, 0, st>>>(s.st);
+    PSGD_LAUNCH_CHECK(ctx);
+    balance_scale_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+
+  // sweep 1
+  SweepArgs a1{};
+  a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.n = n; a1.direct = ctx->opt_direct;
+  PSGD_RETURN_IF((launch_gram<R, kUpdate>(ctx, a1, s.partial, grid)));
+  constexpr int table = GramPlan<R, kUpdate>::W * GramPlan<R, kUpdate>::E;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
+
+  // sweep 2
+  MapOut o2{};
+  o2.o0 = s.a; o2.o1 = s.b; o2.o2 = s.nd; o2.partial = s.partial; o2.st = s.st;
+  PSGD_RETURN_IF((launch_map<R, kMapUpd2>(ctx, a1, o2, update_U, grid)));
+  constexpr int cnt2 = 3 + 2 * R;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, cnt2, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, cnt2, 0));
+  PSGD_RETURN_IF(hook_allreduce(ctx, &s.st->max_nabla, 1, 1));
+  uvd_small2_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
+
+  // sweep 3
+  SweepArgs a3{};
+  a3.mat[0] = update_U ? U : V; a3.vec[0] = s.a; a3.vec[1] = s.b; a3.vec[2] = s.nd; a3.vec[3] = d;
+  a3.n = n; a3.direct = ctx->opt_direct;
+  MapOut o3{};
+  o3.mat_out = update_U ? U : V; o3.vec_out = d; o3.st = s.st;
+  if (update_U) PSGD_RETURN_IF((launch_map<R, kMapUpd3U>(ctx, a3, o3, 1, grid)));
+  else PSGD_RETURN_IF((launch_map<R, kMapUpd3V>(ctx, a3, o3, 0, grid)));
+  return PSGD_OK;
+}
+
+template <int R>
+static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* out,
+                      int64_t n) {
+  const int grid = grid_for(ctx, n);
+  Scratch s;
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
+  cudaStream_t st = ctx->stream;
+  SweepArgs a{};
+  a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
+  PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
+  constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
+  MapOut o{};
+  o.o0 = out; o.st = s.st;
+  PSGD_RETURN_IF((launch_map<R, kMapApply2>(ctx, a, o, 0, grid)));
+  return PSGD_OK;
+}
+
+// IpUVtmatvec for one column: out = x + U (V^T x)
+template <int R>
+static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out, int64_t n) {
+  const int grid = grid_for(ctx, n);
+  Scratch s;
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
+  cudaStream_t st = ctx->stream;
+  SweepArgs a{};
+  a.mat[0] = U; a.mat[1] = V; a.vec[0] = x; a.n = n; a.direct = ctx->opt_direct;
+  PSGD_RETURN_IF((launch_gram<R, kMatvec>(ctx, a, s.partial, grid)));
+  constexpr int table = GramPlan<R, kMatvec>::W * GramPlan<R, kMatvec>::E;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);   // p = V^T x (t unused)
+  PSGD_LAUNCH_CHECK(ctx);
+  SweepArgs a2{};
+  a2.mat[0] = U; a2.vec[0] = x; a2.n = n; a2.direct = ctx->opt_direct;
+  MapOut o{};
+  o.o0 = out; o.st = s.st;
+  PSGD_RETURN_IF((launch_map<R, kMapMatvec2>(ctx, a2, o, 0, grid)));
+  return PSGD_OK;
+}
+
+#define PSGD_RANK_SWITCH(r, CALL)                                                              \
+  switch (r) {                                                                                 \
+    case 1: return CALL(1);   case 2: return CALL(2);   case 3: return CALL(3);                \
+    case 4: return CALL(4);   case 5: return CALL(5);   case 6: return CALL(6);                \
+    case 7: return CALL(7);   case 8: return CALL(8);   case 9: return CALL(9);                \
+    case 10: return CALL(10); case 11: return CALL(11); case 12: return CALL(12);              \
+    case 13: return CALL(13); case 14: return CALL(14); case 15: return CALL(15);              \
+    case 16: return CALL(16);                                                                  \
+    default:                                                                                   \
+      ::psgd::set_error("UVd rank %d not supported (1..%d)", (int)(r), kMaxRank);              \
+      return PSGD_ERR_BAD_SHAPE;                                                               \
+  }
+
+int update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, int64_t n, int r,
+           float step, float tiny, int balance, int update_U) {
+#define CALL(R) update_impl<R>(ctx, U, V, d, v, h, n, step, tiny, balance, update_U)
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
+}
+int apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* out, int64_t n,
+          int r) {
+#define CALL(R) apply_impl<R>(ctx, U, V, d, g, out, n)
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
+}
+int matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out, int64_t n, int r) {
+#define CALL(R) matvec_impl<R>(ctx, U, V, x, out, n)
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
+}
+
+}  // namespace uvd
+}  // namespace psgd
+
+// ---------------------------------------------------------------------------------------------
+// C ABI
+// ---------------------------------------------------------------------------------------------
+using namespace psgd;
+
+static int check_uvd_ptrs(const void* const* ptrs, int count) {
+  for (int i = 0; i < count; ++i) {
+    PSGD_REQUIRE(ptrs[i] != nullptr, PSGD_ERR_BAD_POINTER, "UVd: null device pointer (arg %d)", i);
+    PSGD_REQUIRE(aligned16(ptrs[i]), PSGD_ERR_BAD_POINTER, "UVd: device pointer %d is not 16-byte aligned", i);
+  }
+  return PSGD_OK;
+}
+
+extern "C" int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h,
+                               int64_t n, int r, float step, float tiny, int balance, int update_U) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd update: bad sizes n=%lld r=%d", (long long)n, r);
+  if (n == 0) return PSGD_OK;
+  const void* ptrs[] = {U, V, d, v, h};
+  PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return uvd::update(ctx, U, V, d, v, h, n, r, step, tiny, balance, update_U);
+}
+
+extern "C" int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,
+                              float* out, int64_t n, int r) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd apply: bad sizes n=%lld r=%d", (long long)n, r);
+  if (n == 0) return PSGD_OK;
+  const void* ptrs[] = {U, V, d, g, out};
+  PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return uvd::apply(ctx, U, V, d, g, out, n, r);
+}
+
+// strided column gather/scatter for k > 1 right-hand sides
+__global__ void psgd_col_copy_kernel(const float* __restrict__ src, int64_t sstride, float* __restrict__ dst,
+                                     int64_t dstride, int64_t n) {
+  for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x)
+    dst[i * dstride] = src[i * sstride];
+}
+
+extern "C" int psgd_ipuvt_matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out,
+                                 int64_t n, int r, int k) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n >= 0 && r >= 1 && k >= 1, PSGD_ERR_BAD_SHAPE, "IpUVtmatvec: bad sizes n=%lld r=%d k=%d",
+               (long long)n, r, k);
+  if (n == 0) return PSGD_OK;
+  const void* ptrs[] = {U, V, x, out};
+  PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 4));
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  if (k == 1) return uvd::matvec(ctx, U, V, x, out, n, r);
+  // k columns: gather each column to a contiguous vector, run the single-column path, scatter back
+  float *xc = nullptr, *oc = nullptr;
+  PSGD_CUDA_CHECK(cudaMallocAsync(&xc, sizeof(float) * n, ctx->stream));
+  PSGD_CUDA_CHECK(cudaMallocAsync(&oc, sizeof(float) * n, ctx->stream));
+  int rc = PSGD_OK;
+  for (int c = 0; c < k && rc == PSGD_OK; ++c) {
+    psgd_col_copy_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(x + c, k, xc, 1, n);
+    ctx->launches++;
+    rc = uvd::matvec(ctx, U, V, xc, oc, n, r);
+    psgd_col_copy_kernel<<<ctx->num_sms * 4, 256, 0, ctx->stream>>>(oc, 1, out + c, k, n);
+    ctx->launches++;
+  }
+  cudaFreeAsync(xc, ctx->stream);
+  cudaFreeAsync(oc, ctx->stream);
+  return rc;
+}

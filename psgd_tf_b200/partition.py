@@ -1,0 +1,118 @@
+"""Multi-GPU partitioners for one 8 x B200 box: one process per GPU, ``torch.distributed`` (NCCL over NVLink 5 /
+NVSwitch) as the plumbing.
+
+* **UVd / diagonal / X-shape** shard the flattened parameter vector by contiguous chunk.  Every big operand is indexed
+  by parameter row, so the only exchange is an all-reduce of the r x r / r-length partial sums (float64, a few hundred
+  values) and of one max per phase.  The C library calls back into :func:`install_allreduce`'s hook between its
+  kernels, on its own stream, so the collective is stream-ordered with the sweeps and nothing syncs the host.
+* **Kron stacks** shard layer-wise: layers are independent (mnist_with_lenet5.py:51-53), so each rank updates and
+  applies only the layers it owns and the preconditioned gradients are all-gathered afterwards.
+* **Dense full-matrix** preconditioners are replicas only (n < 1e4; not worth sharding).
+"""
+from __future__ import annotations
+
+from typing import List, Sequence, Tuple
+
+import torch
+
+
+class _DevBuf:
+    """A raw device pointer dressed up for ``torch.as_tensor`` (zero-copy via __cuda_array_interface__)."""
+
+    def __init__(self, ptr: int, count: int, typestr: str):
+        self.__cuda_array_interface__ = {"shape": (count,), "typestr": typestr, "data": (ptr, False), "version": 3,
+                                         "strides": None}
+
+
+def install_allreduce(ctx, group=None) -> None:
+    """Route the library's cross-rank reductions through ``torch.distributed.all_reduce`` on ``group``."""
+    import torch.distributed as dist
+
+    cache = {}
+
+    def hook(ptr: int, count: int, op: int, stream: int) -> int:
+        key = (ptr, count, op)
+        t = cache.get(key)
+        if t is None:
+            t = torch.as_tensor(_DevBuf(ptr, count, "<f8" if op == 0 else "<f4"), device=torch.device("cuda", ctx.device))
+            cache[key] = t
+        # the library's stream is torch's current stream (psgd.get_context sets it), so the collective is ordered
+        # after the partial-sum kernel and before the kernel that consumes the result
+        dist.all_reduce(t, op=dist.ReduceOp.SUM if op == 0 else dist.ReduceOp.MAX, group=group)
+        return 0
+
+    ctx.set_allreduce(hook)
+
+
+def chunk_bounds(n: int, world: int, rank: int, align: int = 256) -> Tuple[int, int]:
+    """Contiguous row chunk [lo, hi) of rank ``rank``; chunk starts are multiples of ``align`` rows so every shard's
+    U/V/d base pointers stay 16-byte aligned for the TMA bulk copies."""
+    per = -(-n // world)
+    per = -(-per // align) * align
+    lo = min(n, rank * per)
+    return lo, min(n, lo + per)
+
+
+def mirrored_chunk_bounds(n: int, world: int, rank: int, align: int = 256) -> Tuple[Tuple[int, int], Tuple[int, int]]:
+    """X-shape sharding: element i only ever meets n-1-i, so rank k owns a chunk of the first half and its mirror
+    image in the second half; no data exchange is needed, only the max all-reduce."""
+    half = (n + 1) // 2
+    lo, hi = chunk_bounds(half, world, rank, align)
+    return (lo, hi), (n - hi, n - lo)
+
+
+def assign_layers(costs: Sequence[float], world: int) -> List[List[int]]:
+    """Longest-processing-time bin packing of layers onto ranks by cost (e.g. the 26 n^3 flop count of a dense-dense
+    layer).  Uniform stacks reduce to round-robin blocks."""
+    order = sorted(range(len(costs)), key=lambda i: (-costs[i], i))
+    loads = [0.0] * world
+    owned: List[List[int]] = [[] for _ in range(world)]
+    for i in order:
+        k = min(range(world), key=lambda j: (loads[j], j))
+        owned[k].append(i)
+        loads[k] += costs[i]
+    for o in owned:
+        o.sort()
+    return owned
+
+
+def kron_layer_cost(M: int, N: int, kind_l: int = 0, kind_r: int = 0) -> float:
+    """Dense flop count of one update+apply; structured factors cost O(MN)."""
+    c = 20.0 * M * N
+    if kind_l == 0:
+        c += 2.0 * M * M * N * 4 + 2.0 * M ** 3
+    if kind_r == 0:
+        c += 2.0 * M * N * N * 4 + 2.0 * N ** 3
+    return c
+
+
+def all_gather_layers(outs_local: Sequence[torch.Tensor], owned: List[List[int]], shapes: Sequence[Tuple[int, int]],
+                      rank: int, group=None) -> List[torch.Tensor]:
+    """All-gather of preconditioned gradients for a layer-sharded Kron stack: every rank ends up with every layer's
+    result.  Ragged layer sizes are handled by one broadcast per layer from its owner (grouped into one NCCL group
+    call by torch's coalescing manager when available)."""
+    import torch.distributed as dist
+
+    dev = outs_local[0].device if outs_local else torch.device("cuda", torch.cuda.current_device())
+    full: List[torch.Tensor] = [None] * len(shapes)  # type: ignore
+    for k, layer_ids in enumerate(owned):
+        for j, li in enumerate(layer_ids):
+            full[li] = outs_local[j] if k == rank else torch.empty(shapes[li], device=dev, dtype=torch.float32)
+    uniform = len({tuple(s) for s in shapes}) == 1 and len({len(o) for o in owned}) == 1
+    if uniform:
+        # uniform stack (24 x 4096^2): one all_gather_into_tensor of the stacked local results
+        per = len(owned[0])
+        local = torch.stack([full[li] for li in owned[rank]]) if per else torch.empty(0, device=dev)
+        gathered = torch.empty((len(owned),) + tuple(local.shape), device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, local, group=group)
+        for k, layer_ids in enumerate(owned):
+            for j, li in enumerate(layer_ids):
+                full[li] = gathered[k, j]
+        return full
+    works = []
+    for k, layer_ids in enumerate(owned):
+        for li in layer_ids:
+            works.append(dist.broadcast(full[li], src=k, group=group, async_op=True))
+    for w in works:
+        w.wait()
+    return full

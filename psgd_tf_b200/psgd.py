@@ -1,0 +1,398 @@
+"""Drop-in functional API of lixilinx/psgd_tf's ``preconditioned_stochastic_gradient_descent.py``
+(``psgd.py`` below), executed by hand-written sm_100a CUDA behind ``include/psgd_b200.h``.
+
+Same names, argument order, defaults and value semantics as the reference:
+
+* Kron / dense functions are *functional*: inputs untouched, new tensors returned (psgd.py:42, :179);
+* ``update_precond_UVd_math_`` updates U, V, d *in place* and returns None (psgd.py:554-617);
+* an unknown Kronecker factor combination prints a warning and returns its inputs (psgd.py:89-91).
+
+Tensors are exchanged zero-copy through DLPack: any object with ``__dlpack__`` living on a CUDA device
+(torch, TF via ``tf.experimental.dlpack``, cupy, jax ...) is viewed as a ``torch.Tensor`` without a copy;
+results come back as torch CUDA tensors (``tf_adapter.py`` converts them to TF).  torch is plumbing only
+(device memory, streams); every arithmetic operation runs in this package's CUDA kernels.  There is no
+CPU fallback: CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import random as _random
+import threading
+
+import torch
+
+from . import _lib
+from ._lib import FACTOR_DENSE, FACTOR_NORM, FACTOR_SCALE, KronLayer, PsgdError, check
+
+dtype = torch.float32                      # psgd.py:20
+_tiny = float(2.0 ** -126)                 # psgd.py:21-22: smallest normal float32
+
+_ctx_local = threading.local()
+_rng = _random.Random()
+
+
+def seed(s: int) -> None:
+    """Seed the host RNG that draws the two coin flips of ``update_precond_UVd_math_``."""
+    _rng.seed(s)
+
+
+# ---------------------------------------------------------------------------------------------
+# plumbing
+# ---------------------------------------------------------------------------------------------
+def get_context(device: int | None = None) -> _lib.Context:
+    """The calling thread's context for ``device`` (created on first use)."""
+    if not torch.cuda.is_available():
+        raise RuntimeError("psgd_tf_b200 needs a CUDA device (sm_100a); there is no CPU path")
+    if device is None:
+        device = torch.cuda.current_device()
+    table = getattr(_ctx_local, "table", None)
+    if table is None:
+        table = _ctx_local.table = {}
+    ctx = table.get(device)
+    if ctx is None:
+        ctx = table[device] = _lib.Context(device)
+    ctx.set_stream(torch.cuda.current_stream(device).cuda_stream)
+    return ctx
+
+
+def _as_tensor(x, name: str) -> torch.Tensor:
+    """Zero-copy view of a DLPack-capable CUDA array as a contiguous float32 torch tensor."""
+    if not isinstance(x, torch.Tensor):
+        if hasattr(x, "__dlpack__"):
+            x = torch.from_dlpack(x)
+        else:
+            raise TypeError(f"{name}: expected a tensor supporting DLPack, got {type(x).__name__}")
+    if not x.is_cuda:
+        raise RuntimeError(f"{name}: tensor is on {x.device}; psgd_tf_b200 runs on CUDA only (no CPU fallback)")
+    if x.dtype != torch.float32:
+        raise TypeError(f"{name}: dtype {x.dtype} is not float32 (psgd.py:20, README.md:37)")
+    return x
+
+
+def _in(x, name: str) -> torch.Tensor:
+    t = _as_tensor(x, name)
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _inplace(x, name: str) -> torch.Tensor:
+    t = _as_tensor(x, name)
+    if not t.is_contiguous():
+        raise RuntimeError(f"{name}: in-place state tensors must be contiguous")
+    return t
+
+
+def _p(t: torch.Tensor) -> C.c_void_p:
+    return C.c_void_p(t.data_ptr())
+
+
+def _scalar(x) -> float:
+    return float(x.item()) if hasattr(x, "item") else float(x)
+
+
+def _kind(Q: torch.Tensor) -> int:
+    """Factor format from its shape, in the reference's test order: square => dense first
+    (psgd.py:82-83), then first dim 2 => normalization, 1 => scaling."""
+    m, n = Q.shape
+    if m == n:
+        return FACTOR_DENSE
+    if m == 2:
+        return FACTOR_NORM
+    if m == 1:
+        return FACTOR_SCALE
+    return -1
+
+
+_SUPPORTED = {(FACTOR_DENSE, FACTOR_DENSE), (FACTOR_DENSE, FACTOR_NORM), (FACTOR_DENSE, FACTOR_SCALE),
+              (FACTOR_NORM, FACTOR_DENSE), (FACTOR_NORM, FACTOR_SCALE), (FACTOR_SCALE, FACTOR_DENSE),
+              (FACTOR_SCALE, FACTOR_NORM)}
+
+
+# ---------------------------------------------------------------------------------------------
+# dense (full matrix) preconditioner                                        psgd.py:26-63
+# ---------------------------------------------------------------------------------------------
+def update_precond_dense(Q, dxs, dgs, step=0.01):
+    """psgd.py:26-42.  ``dxs``/``dgs``: lists of arbitrarily shaped tensors, flattened and concatenated
+    in list order (psgd.py:34-35)."""
+    Q = _in(Q, "Q")
+    dx = torch.cat([_in(x, "dxs").reshape(-1) for x in dxs])
+    dg = torch.cat([_in(g, "dgs").reshape(-1) for g in dgs])
+    n = Q.shape[0]
+    if Q.shape != (n, n) or dx.numel() != n or dg.numel() != n:
+        raise ValueError(f"update_precond_dense: Q {tuple(Q.shape)} vs {dx.numel()} parameters")
+    out = torch.empty_like(Q)
+    ctx = get_context(Q.device.index)
+    check(ctx.lib.psgd_dense_update(ctx.handle, _p(Q), _p(dx), _p(dg), _p(out), n, _scalar(step), _tiny))
+    return out
+
+
+def precond_grad_dense(Q, grads):
+    """psgd.py:45-63: ``Q^T Q g`` reshaped back to the shapes of ``grads``."""
+    Q = _in(Q, "Q")
+    gs = [_in(g, "grads") for g in grads]
+    flat = torch.cat([g.reshape(-1) for g in gs])
+    n = Q.shape[0]
+    if flat.numel() != n:
+        raise ValueError(f"precond_grad_dense: Q {tuple(Q.shape)} vs {flat.numel()} parameters")
+    out = torch.empty_like(flat)
+    ctx = get_context(Q.device.index)
+    check(ctx.lib.psgd_dense_apply(ctx.handle, _p(Q), _p(flat), _p(out), n))
+    pre, idx = [], 0
+    for g in gs:
+        pre.append(out[idx: idx + g.numel()].reshape(g.shape))
+        idx += g.numel()
+    return pre
+
+
+# ---------------------------------------------------------------------------------------------
+# Kronecker product preconditioners                                          psgd.py:67-391
+# ---------------------------------------------------------------------------------------------
+def _kron_update(Ql, Qr, dX, dG, step, kinds=None):
+    Ql, Qr, dX, dG = _in(Ql, "Ql"), _in(Qr, "Qr"), _in(dX, "dX"), _in(dG, "dG")
+    for t, nm in ((Ql, "Ql"), (Qr, "Qr"), (dX, "dX"), (dG, "dG")):
+        if t.dim() != 2:
+            raise ValueError(f"{nm} must be rank-2 (psgd.py:67-70), got shape {tuple(t.shape)}")
+    kl, kr = kinds if kinds is not None else (_kind(Ql), _kind(Qr))
+    M, N = dX.shape
+    if (kl, kr) not in _SUPPORTED:
+        print("Unknown Kronecker product preconditioner, no update")          # psgd.py:90
+        return Ql, Qr
+    if dG.shape != dX.shape or Ql.shape[1] != M or Qr.shape[1] != N:
+        raise ValueError(f"update_precond_kron: Ql {tuple(Ql.shape)}, Qr {tuple(Qr.shape)}, dX {tuple(dX.shape)}, "
+                         f"dG {tuple(dG.shape)} are inconsistent")
+    Ql_out, Qr_out = torch.empty_like(Ql), torch.empty_like(Qr)
+    ctx = get_context(Ql.device.index)
+    check(ctx.lib.psgd_kron_update(ctx.handle, kl, kr, _p(Ql), _p(Qr), _p(dX), _p(dG), _p(Ql_out), _p(Qr_out),
+                                   M, N, _scalar(step), _tiny))
+    return Ql_out, Qr_out
+
+
+def _kron_apply(Ql, Qr, Grad, kinds=None):
+    Ql, Qr, Grad = _in(Ql, "Ql"), _in(Qr, "Qr"), _in(Grad, "Grad")
+    for t, nm in ((Ql, "Ql"), (Qr, "Qr"), (Grad, "Grad")):
+        if t.dim() != 2:
+            raise ValueError(f"{nm} must be rank-2 (psgd.py:113-115), got shape {tuple(t.shape)}")
+    kl, kr = kinds if kinds is not None else (_kind(Ql), _kind(Qr))
+    M, N = Grad.shape
+    if (kl, kr) not in _SUPPORTED:
+        print("Unknown Kronecker product preconditioner, no preconditioning")  # psgd.py:132
+        return Grad
+    if Ql.shape[1] != M or Qr.shape[1] != N:
+        raise ValueError(f"precond_grad_kron: Ql {tuple(Ql.shape)}, Qr {tuple(Qr.shape)}, Grad {tuple(Grad.shape)} "
+                         "are inconsistent")
+    out = torch.empty_like(Grad)
+    ctx = get_context(Ql.device.index)
+    check(ctx.lib.psgd_kron_apply(ctx.handle, kl, kr, _p(Ql), _p(Qr), _p(Grad), _p(out), M, N))
+    return out
+
+
+def update_precond_kron(Ql, Qr, dX, dG, step=0.01):
+    """psgd.py:72-110: shape-dispatched update of ``P = kron(Qr^T Qr, Ql^T Ql)``; returns ``(Ql', Qr')``."""
+    return _kron_update(Ql, Qr, dX, dG, step)
+
+
+def precond_grad_kron(Ql, Qr, Grad):
+    """psgd.py:116-152: ``Ql^T Ql Grad Qr^T Qr`` for any supported factor-format combination."""
+    return _kron_apply(Ql, Qr, Grad)
+
+
+def _update_precond_dense_dense(Ql, Qr, dX, dG, step=0.01):
+    """psgd.py:156-179."""
+    return _kron_update(Ql, Qr, dX, dG, step, (FACTOR_DENSE, FACTOR_DENSE))
+
+
+def _precond_grad_dense_dense(Ql, Qr, Grad):
+    """psgd.py:182-192."""
+    return _kron_apply(Ql, Qr, Grad, (FACTOR_DENSE, FACTOR_DENSE))
+
+
+def _update_precond_norm_dense(ql, Qr, dX, dG, step=0.01):
+    """psgd.py:198-246."""
+    return _kron_update(ql, Qr, dX, dG, step, (FACTOR_NORM, FACTOR_DENSE))
+
+
+def _precond_grad_norm_dense(ql, Qr, Grad):
+    """psgd.py:249-270."""
+    return _kron_apply(ql, Qr, Grad, (FACTOR_NORM, FACTOR_DENSE))
+
+
+def _update_precond_dense_scale(Ql, qr, dX, dG, step=0.01):
+    """psgd.py:276-307."""
+    return _kron_update(Ql, qr, dX, dG, step, (FACTOR_DENSE, FACTOR_SCALE))
+
+
+def _precond_grad_dense_scale(Ql, qr, Grad):
+    """psgd.py:310-322."""
+    return _kron_apply(Ql, qr, Grad, (FACTOR_DENSE, FACTOR_SCALE))
+
+
+def _update_precond_norm_scale(ql, qr, dX, dG, step=0.01):
+    """psgd.py:328-369."""
+    return _kron_update(ql, qr, dX, dG, step, (FACTOR_NORM, FACTOR_SCALE))
+
+
+def _precond_grad_norm_scale(ql, qr, Grad):
+    """psgd.py:372-391."""
+    return _kron_apply(ql, qr, Grad, (FACTOR_NORM, FACTOR_SCALE))
+
+
+# ---- batched ("all layers in one call") forms: new API surface ----------------------
+def _layer_array(ctx_fields):
+    arr = (KronLayer * len(ctx_fields))()
+    for i, f in enumerate(ctx_fields):
+        for k, v in f.items():
+            setattr(arr[i], k, v)
+    return arr
+
+
+def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
+    """Update every layer's factor pair in one library call.  Lists of tensors in, list of ``(Ql', Qr')`` out.
+    Equivalent to ``[update_precond_kron(*a, step) for a in zip(Qls, Qrs, dXs, dGs)]``
+    (mnist_with_lenet5.py:51)."""
+    n = len(Qls)
+    Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
+    dXs = [_in(x, "dX") for x in dXs]; dGs = [_in(g, "dG") for g in dGs]
+    outs, fields, keep = [None] * n, [], []
+    for i in range(n):
+        kl, kr = _kind(Qls[i]), _kind(Qrs[i])
+        if (kl, kr) not in _SUPPORTED:
+            print("Unknown Kronecker product preconditioner, no update")
+            outs[i] = (Qls[i], Qrs[i])
+            continue
+        M, N = dXs[i].shape
+        lo, ro = torch.empty_like(Qls[i]), torch.empty_like(Qrs[i])
+        outs[i] = (lo, ro)
+        fields.append(dict(kind_l=kl, kind_r=kr, M=M, N=N, Ql=Qls[i].data_ptr(), Qr=Qrs[i].data_ptr(),
+                           dX=dXs[i].data_ptr(), dG=dGs[i].data_ptr(), Ql_out=lo.data_ptr(), Qr_out=ro.data_ptr()))
+    if fields:
+        ctx = get_context(Qls[0].device.index)
+        arr = _layer_array(fields)
+        check(ctx.lib.psgd_kron_update_batched(ctx.handle, arr, len(fields), _scalar(step), _tiny))
+    return outs
+
+
+def precond_grad_kron_batched(Qls, Qrs, Grads):
+    """``[precond_grad_kron(Ql, Qr, G) for ...]`` in one library call (mnist_with_lenet5.py:53)."""
+    n = len(Qls)
+    Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
+    Grads = [_in(g, "Grad") for g in Grads]
+    outs, fields = [None] * n, []
+    for i in range(n):
+        kl, kr = _kind(Qls[i]), _kind(Qrs[i])
+        if (kl, kr) not in _SUPPORTED:
+            print("Unknown Kronecker product preconditioner, no preconditioning")
+            outs[i] = Grads[i]
+            continue
+        M, N = Grads[i].shape
+        o = torch.empty_like(Grads[i])
+        outs[i] = o
+        fields.append(dict(kind_l=kl, kind_r=kr, M=M, N=N, Ql=Qls[i].data_ptr(), Qr=Qrs[i].data_ptr(),
+                           G=Grads[i].data_ptr(), out=o.data_ptr()))
+    if fields:
+        ctx = get_context(Qls[0].device.index)
+        arr = _layer_array(fields)
+        check(ctx.lib.psgd_kron_apply_batched(ctx.handle, arr, len(fields)))
+    return outs
+
+
+# ---------------------------------------------------------------------------------------------
+# UVd: Q = (I + U V^T) diag(d)                                               psgd.py:540-627
+# ---------------------------------------------------------------------------------------------
+def _col(x: torch.Tensor, n: int, name: str) -> torch.Tensor:
+    if x.numel() != n:
+        raise ValueError(f"{name}: expected {n} elements, got shape {tuple(x.shape)}")
+    return x
+
+
+def IpUVtmatvec(U, V, x):
+    """psgd.py:540-544: ``x + U (V^T x)`` for a column vector or an [N, k] matrix ``x``."""
+    U, V, x = _in(U, "U"), _in(V, "V"), _in(x, "x")
+    n, r = U.shape
+    k = 1 if x.dim() == 1 else x.shape[1]
+    if V.shape != U.shape or x.shape[0] != n:
+        raise ValueError("IpUVtmatvec: shapes are inconsistent")
+    out = torch.empty_like(x)
+    ctx = get_context(U.device.index)
+    check(ctx.lib.psgd_ipuvt_matvec(ctx.handle, _p(U), _p(V), _p(x), _p(out), n, r, k))
+    return out
+
+
+def update_precond_UVd_math_(U, V, d, v, h, step, tiny=_tiny, *, balance=None, update_U=None):
+    """psgd.py:554-617.  Updates U, V ([N, r]) and d ([N, 1]) in place; returns None.
+
+    The reference draws two coin flips from TF's RNG inside this function (psgd.py:562, :588).  Here they
+    come from this module's host RNG (see :func:`seed`) unless given explicitly: ``balance`` stands for
+    ``uniform() < 0.01`` and ``update_U`` for ``uniform() < 0.5``."""
+    U, V, d = _inplace(U, "U"), _inplace(V, "V"), _inplace(d, "d")
+    v, h = _in(v, "v"), _in(h, "h")
+    n, r = U.shape
+    if V.shape != U.shape:
+        raise ValueError("update_precond_UVd_math_: U and V must have the same shape")
+    _col(d, n, "d"); _col(v, n, "v"); _col(h, n, "h")
+    if balance is None:
+        balance = _rng.random() < 0.01
+    if update_U is None:
+        update_U = _rng.random() < 0.5
+    ctx = get_context(U.device.index)
+    check(ctx.lib.psgd_uvd_update(ctx.handle, _p(U), _p(V), _p(d), _p(v), _p(h), n, r, _scalar(step), _scalar(tiny),
+                                  int(bool(balance)), int(bool(update_U))))
+    return None
+
+
+def precond_grad_UVd_math(U, V, d, g):
+    """psgd.py:619-627: ``d * (I + V U^T)(I + U V^T)(d * g)``; same shape as ``g``."""
+    U, V, d, g = _in(U, "U"), _in(V, "V"), _in(d, "d"), _in(g, "g")
+    n, r = U.shape
+    _col(d, n, "d"); _col(g, n, "g")
+    out = torch.empty_like(g)
+    ctx = get_context(U.device.index)
+    check(ctx.lib.psgd_uvd_apply(ctx.handle, _p(U), _p(V), _p(d), _p(g), _p(out), n, r))
+    return out
+
+
+# north-star spellings (BASELINE.json) of the same two functions
+update_precond_UVd = update_precond_UVd_math_
+precond_grad_UVd = precond_grad_UVd_math
+
+
+# ---------------------------------------------------------------------------------------------
+# diagonal and X-shape preconditioners (README.md:11-15, :35) -- in place, like UVd
+# ---------------------------------------------------------------------------------------------
+def update_precond_diag(q, v, h, step=0.01, tiny=_tiny):
+    """Q = diag(q): ``q -= mu * ((q h)^2 - (v/q)^2) * q``, ``mu = step / (max|.| + tiny)``.  In place."""
+    q = _inplace(q, "q"); v, h = _in(v, "v"), _in(h, "h")
+    n = q.numel()
+    _col(v, n, "v"); _col(h, n, "h")
+    ctx = get_context(q.device.index)
+    check(ctx.lib.psgd_diag_update(ctx.handle, _p(q), _p(v), _p(h), n, _scalar(step), _scalar(tiny)))
+    return None
+
+
+def precond_grad_diag(q, g):
+    """``q^2 * g``."""
+    q, g = _in(q, "q"), _in(g, "g")
+    _col(g, q.numel(), "g")
+    out = torch.empty_like(g)
+    ctx = get_context(q.device.index)
+    check(ctx.lib.psgd_diag_apply(ctx.handle, _p(q), _p(g), _p(out), q.numel()))
+    return out
+
+
+def update_precond_Xmat(a, b, v, h, step=0.01, tiny=_tiny):
+    """Q = diag(a) + adiag(b) (subgroup {e, flipping}, README.md:13).  Updates a, b in place."""
+    a, b = _inplace(a, "a"), _inplace(b, "b"); v, h = _in(v, "v"), _in(h, "h")
+    n = a.numel()
+    _col(b, n, "b"); _col(v, n, "v"); _col(h, n, "h")
+    ctx = get_context(a.device.index)
+    check(ctx.lib.psgd_xmat_update(ctx.handle, _p(a), _p(b), _p(v), _p(h), n, _scalar(step), _scalar(tiny)))
+    return None
+
+
+def precond_grad_Xmat(a, b, g):
+    """``Q^T Q g`` for Q = diag(a) + adiag(b)."""
+    a, b, g = _in(a, "a"), _in(b, "b"), _in(g, "g")
+    n = a.numel()
+    _col(b, n, "b"); _col(g, n, "g")
+    out = torch.empty_like(g)
+    ctx = get_context(a.device.index)
+    check(ctx.lib.psgd_xmat_apply(ctx.handle, _p(a), _p(b), _p(g), _p(out), n))
+    return out
