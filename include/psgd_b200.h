@@ -107,6 +107,14 @@ int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx, const floa
 /* Replaces precond_grad_dense (psgd.py:45-63): out = Q^T (Q g). */
 int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n);
 
+/* ---- building block ------------------------------------------------------------------------ */
+/* C[M,N] = op(A) op(B), row-major fp32 (ta/tb: transpose flags as in tf.matmul(transpose_a, transpose_b)), through
+ * engine 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32.  triu: zero the strictly lower triangle of C.  a_tri/b_tri:
+ * 0 none, 1 = op(A)/op(B) is upper triangular, 2 = lower (lets the engine skip structurally-zero K blocks).
+ * This is what every tf.matmul call site of psgd.py lowers to; exported for engine cross-checks. */
+int psgd_gemm(psgd_ctx* ctx, int engine, int M, int N, int K, const float* A, int lda, int ta, const float* B,
+              int ldb, int tb, float* C, int ldc, int triu, int a_tri, int b_tri);
+
 /* ---- Kronecker-product preconditioners ----------------------------------------------------- */
 /* One layer.  dX,dG,G,out are [M,N].  A DENSE left factor is [M,M], SCALE [1,M], NORM [2,M];
  * right factors likewise with N.  All seven combinations the reference dispatches

@@ -59,6 +59,7 @@ struct psgd_ctx {
   // small pinned/ device scratch is carved from ws by each op
   int opt_direct = 0;        // streaming kernels: 1 = direct global loads instead of TMA pipeline
   int opt_gemm_path = 0;     // dense GEMMs: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32
+  int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   psgd_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   // optional per-kernel timing (psgd_set_option("profile", 1)): CUDA event pairs around the large kernels

@@ -84,6 +84,11 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   PSGD_REQUIRE(ctx && key, PSGD_ERR_BAD_POINTER, "null context or key");
   if (strcmp(key, "direct") == 0) { ctx->opt_direct = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "profile") == 0) { ctx->opt_profile = value ? 1 : 0; return PSGD_OK; }
+  if (strcmp(key, "tc_bn") == 0) {
+    PSGD_REQUIRE(value == 128 || value == 256, PSGD_ERR_BAD_SHAPE, "tc_bn must be 128 or 256");
+    ctx->opt_tc_bn = (int)value;
+    return PSGD_OK;
+  }
   if (strcmp(key, "gemm_path") == 0) {
     PSGD_REQUIRE(value >= 0 && value <= 2, PSGD_ERR_BAD_SHAPE, "gemm_path must be 0 (auto), 1 (simt) or 2 (tcgen05)");
     ctx->opt_gemm_path = (int)value;

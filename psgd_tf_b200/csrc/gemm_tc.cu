@@ -1,11 +1,537 @@
-// tcgen05 3xTF32 GEMM engine -- engine selection.  (Tensor-core kernels land here; until a shape is
-// covered by them the SIMT fp32 engine runs it.)
+// tcgen05 3xTF32 GEMM engine for the dense Kronecker factors (sm_100a).
+//
+//   C = epilogue( op(A) op(B)  -  op(A2) op(B2) )          float32 in, float32-faithful out
+//
+// Replaces the large tf.matmul call sites of psgd.py (:173, :175-176, :179, :190, :192, :220, :243, :246, :261,
+// :263, :295, :301, :307, :319, :321) for layers big enough to fill 128-wide tensor-core tiles.
+//
+// Kernel anatomy (one persistent CTA per SM, 10 warps, warp-specialised):
+//   warp 0      TMA producer   cp.async.bulk.tensor 2D (SWIZZLE_128B) of raw fp32 operand tiles -> shared memory
+//   warps 6-9   splitter       hi = rna_tf32(x) (in place), lo = rna_tf32(x - hi) (second tile): the 3xTF32 split is
+//                              done on chip, so operands are read from HBM/L2 exactly once, as plain fp32
+//   warp 1      MMA issuer     one lane issues tcgen05.mma.kind::tf32: lo*hi + hi*lo + hi*hi per K=8 atom, fp32
+//                              accumulators in TMEM (double buffered: 2 x BN columns)
+//   warps 2-5   epilogue       tcgen05.ld -> registers -> triu mask / max|.| / (D - mu*acc) / column scale -> global
+// Pipelines: full[s] (TMA -> splitter), conv[s] (splitter -> MMA), empty[s] (tcgen05.commit -> TMA),
+//            tmem_full[a] / tmem_empty[a] (MMA <-> epilogue).
+// Both operands may be K-major or MN-major (tf32 supports both), so every transposition the reference asks for
+// (transpose_a / transpose_b) is a descriptor flag, never a copy.  Triangular operands restrict each tile's K range
+// and triu outputs skip tiles below the diagonal.
+#include <cuda.h>
+
 #include "gemm_tc.cuh"
 
 namespace psgd {
 namespace tc {
 
-int gemm_auto(psgd_ctx* ctx, const la::Gemm& g) { return la::gemm_simt(ctx, g); }
+constexpr int BM = 128;
+constexpr int BK = 32;                 // floats per stage along K = one 128-byte swizzle span
+constexpr int UMMA_K = 8;              // tf32
+constexpr int kThreads = 320;          // 10 warps
+constexpr int kEpiWarp0 = 2, kSplitWarp0 = 6;
+constexpr int kChunkKB = 4;            // K-blocks (of 32) per tensor-core accumulation chain
+
+template <int BN>
+struct Cfg {
+  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kTileABytes = BM * BK * 4;             // 16 KB
+  static constexpr int kTileBBytes = BN * BK * 4;
+  static constexpr int kStageBytes = 2 * (kTileABytes + kTileBBytes);   // raw(hi) + lo
+  static constexpr int kTxBytes = kTileABytes + kTileBBytes;
+  static constexpr int kTmemCols = 2 * BN;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+struct Params {
+  int M, N;
+  int K[2];                 // K of product 0 and of the (subtracted) product 1; K[1] == 0 when absent
+  int a_mn[2], b_mn[2];     // 1: operand is MN-major in memory (op = transpose of the row-major array)
+  int a_tri, b_tri;         // K-range hints for product 0: 0 none, 1 op(A)/op(B) upper triangular, 2 lower
+  float* C; int ldc;
+  int triu;
+  float* maxabs;
+  const float* D; int ldd;
+  const float* mu_max; float step, tiny;
+  const float* colscale; int colscale_recip, colscale_sq;
+  int tiles_m, tiles_n;
+};
+
+// ---------------------------------------------------------------------------------------------
+// PTX wrappers
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+// D[tmem] (+)= A[smem] * B[smem], tf32 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                          uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 lanes x 32 consecutive columns -> 32 registers per thread
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Shared-memory matrix descriptor, SWIZZLE_128B (cute::UMMA::SmemDescriptor bit layout, version 1).
+//   K-major : rows of 128 B, 8-row groups 1024 B apart            -> LBO = 1 (unused), SBO = 1024 B
+//   MN-major: 32-float (128 B) runs along M/N, 8 K-rows per 1024 B atom, next 32-wide run `lbo_bytes` away
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr, uint32_t lbo_bytes, uint32_t sbo_bytes,
+                                                   uint32_t layout_type) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3FFF);
+  d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+  d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+  d |= (uint64_t)1 << 46;          // descriptor version (Blackwell)
+  d |= (uint64_t)layout_type << 61;
+  return d;
+}
+// K-major operand tile: TMA SWIZZLE_128B, rows of 128 B, 8-row groups 1024 B apart.
+// MN-major operand tile (32-bit elements): the only legal layout is SWIZZLE_128B_BASE32B (TMA
+// SWIZZLE_128B_ATOM_32B): 128-byte runs along M/N, 4 K-rows per 512-byte swizzle atom; our tile stores each
+// 32-wide M/N run as a contiguous [32 k x 128 B] block of 4096 B.
+__device__ __forceinline__ uint64_t operand_desc(uint32_t tile_addr, int mn_major, int kk) {
+  return mn_major ? make_smem_desc(tile_addr + kk * 1024, /*LBO*/ 4096, /*SBO*/ 512, /*SW128_BASE32B*/ 1)
+                  : make_smem_desc(tile_addr + kk * 32, /*LBO*/ 16, /*SBO*/ 1024, /*SW128*/ 2);
+}
+// Instruction descriptor (cute::UMMA::InstrDescriptor): F32 accumulate, TF32 x TF32.
+__device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn, int negate_a) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format  = F32
+  d |= 2u << 7;                        // a_format  = TF32
+  d |= 2u << 10;                       // b_format  = TF32
+  d |= (uint32_t)(negate_a & 1) << 13; // a_negate
+  d |= (uint32_t)(a_mn & 1) << 15;     // a_major   (1 = MN-major)
+  d |= (uint32_t)(b_mn & 1) << 16;     // b_major
+  d |= (uint32_t)(n >> 3) << 17;       // n_dim
+  d |= (uint32_t)(BM >> 4) << 24;      // m_dim
+  return d;
+}
+
+__device__ __forceinline__ float to_tf32_rna(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return __uint_as_float(r);
+}
+
+// K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
+template <int BN>
+__device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1) {
+  const int K = p.K[prod];
+  int lo = 0, hi = K;
+  if (prod == 0) {
+    if (p.a_tri == 1) lo = max(lo, m0);                 // op(A)[m,k] = 0 for k < m
+    if (p.a_tri == 2) hi = min(hi, m0 + BM);            // op(A)[m,k] = 0 for k > m
+    if (p.b_tri == 1) hi = min(hi, n0 + BN);            // op(B)[k,n] = 0 for k > n
+    if (p.b_tri == 2) lo = max(lo, n0);                 // op(B)[k,n] = 0 for k < n
+  }
+  kb0 = lo / BK;
+  kb1 = (hi + BK - 1) / BK;
+  if (kb1 < kb0) kb1 = kb0;
+}
+
+template <int BN>
+__global__ void __launch_bounds__(kThreads, 1)
+    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
+                   const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const Params p) {
+  using C = Cfg<BN>;
+  extern __shared__ unsigned char smem_raw[];
+  // SWIZZLE_128B tiles need 1024-byte alignment
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]
+  uint64_t* conv = bars + C::kStages;            // [kStages]
+  uint64_t* empty = bars + 2 * C::kStages;       // [kStages]
+  uint64_t* tmem_full = bars + 3 * C::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 4);
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 4);
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc(tmem_ptr, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int num_tiles = p.tiles_m * p.tiles_n;
+
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
+  // stage layout: [A hi | B hi | A lo | B lo]
+
+  if (warp == 0) {
+    // ===================================== TMA producer =====================================
+    if (lane == 0) {
+      int it = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        if (p.triu && m0 >= n0 + BN) continue;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          const CUtensorMap* ma = prod ? &tmA1 : &tmA0;
+          const CUtensorMap* mb = prod ? &tmB1 : &tmB0;
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], C::kTxBytes);
+            unsigned char* sa = stage_ptr(s);
+            unsigned char* sb = sa + C::kTileABytes;
+            const int k0 = kb * BK;
+            if (!p.a_mn[prod]) {
+              tma_load_2d(sa, ma, k0, m0, &full[s]);                       // box {32 k, 128 m}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, m0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
+            }
+            if (!p.b_mn[prod]) {
+              tma_load_2d(sb, mb, k0, n0, &full[s]);                       // box {32 k, BN n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BN / 32; ++j) tma_load_2d(sb + j * 4096, mb, n0 + 32 * j, k0, &full[s]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer =======================================
+    if (lane == 0) {
+      int it = 0, tcount = 0;
+      for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int m0 = tm * BM, n0 = tn * BN;
+        if (p.triu && m0 >= n0 + BN) continue;
+        int total_kb = 0;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          total_kb += kb1 - kb0;
+        }
+        if (total_kb == 0) continue;                      // epilogue writes zeros without touching TMEM
+        // The tensor core adds into its fp32 accumulator with truncation, a bias that grows linearly with the chain
+        // length; chains are therefore cut every kChunkKB K-blocks and the chunk results are summed in registers
+        // (round-to-nearest) by the epilogue warps while the next chunk accumulates in the other TMEM buffer.
+        int a = 0;
+        uint32_t tmem_d = 0;
+        uint32_t accumulate = 0;
+        int done = 0, in_chunk = 0;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          const uint32_t idesc = make_idesc(BN, p.a_mn[prod], p.b_mn[prod], prod);   // product 1 is subtracted
+          for (int kb = kb0; kb < kb1; ++kb, ++it, ++done) {
+            const int s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            if (in_chunk == 0) {
+              a = tcount & 1;
+              const uint32_t aph = (tcount >> 1) & 1;
+              ++tcount;
+              mbar_wait(&tmem_empty[a], aph ^ 1);
+              tmem_d = tmem_base + (uint32_t)(a * BN);
+              accumulate = 0;
+            }
+            mbar_wait(&conv[s], ph);
+            tc_fence_after();
+            const uint32_t a_hi = smem_u32(stage_ptr(s));
+            const uint32_t b_hi = a_hi + C::kTileABytes;
+            const uint32_t a_lo = b_hi + C::kTileBBytes;
+            const uint32_t b_lo = a_lo + C::kTileABytes;
+#pragma unroll
+            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+              const uint64_t dah = operand_desc(a_hi, p.a_mn[prod], kk);
+              const uint64_t dal = operand_desc(a_lo, p.a_mn[prod], kk);
+              const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
+              const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
+              umma_tf32(tmem_d, dal, dbh, idesc, accumulate);     // small terms first
+              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+              accumulate = 1u;
+            }
+            umma_commit(&empty[s]);                               // frees the stage when these MMAs retire
+            if (++in_chunk == kChunkKB || done + 1 == total_kb) {
+              umma_commit(&tmem_full[a]);                         // chunk complete -> epilogue
+              in_chunk = 0;
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp >= kSplitWarp0) {
+    // ===================================== 3xTF32 splitter ==================================
+    const int st = threadIdx.x - kSplitWarp0 * 32;            // 0..127
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      if (p.triu && m0 >= n0 + BN) continue;
+      for (int prod = 0; prod < 2; ++prod) {
+        if (p.K[prod] <= 0) continue;
+        int kb0, kb1;
+        k_range<BN>(p, prod, m0, n0, kb0, kb1);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full[s], ph);
+          float4* hi = reinterpret_cast<float4*>(stage_ptr(s));
+          float4* lo = reinterpret_cast<float4*>(stage_ptr(s) + C::kTxBytes);
+#pragma unroll 4
+          for (int i = st; i < C::kTxBytes / 16; i += 128) {
+            const float4 x = hi[i];
+            float4 h, l;
+            h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
+            l.x = to_tf32_rna(x.x - h.x); l.y = to_tf32_rna(x.y - h.y);
+            l.z = to_tf32_rna(x.z - h.z); l.w = to_tf32_rna(x.w - h.w);
+            hi[i] = h;
+            lo[i] = l;
+          }
+          fence_proxy_async_smem();       // generic-proxy writes -> visible to tcgen05 (async proxy)
+          __syncwarp();
+          if (lane == 0) mbar_arrive(&conv[s]);
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue =========================================
+    const int q = warp & 3;                                   // TMEM lane quarter this warp may access
+    int tcount = 0;
+    float mx = 0.f;
+    float mu = 0.f;
+    if (p.D) mu = p.step / (*p.mu_max + p.tiny);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int m0 = tm * BM, n0 = tn * BN;
+      const int m = m0 + q * 32 + lane;
+      int total_kb = 0;
+      if (!(p.triu && m0 >= n0 + BN)) {
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          total_kb += kb1 - kb0;
+        }
+      }
+      float racc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int done = 0; done < total_kb; done += kChunkKB) {
+        const int a = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        ++tcount;
+        mbar_wait(&tmem_full[a], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tmem_empty[a]);
+      }
+      if (m < p.M) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int nbase = n0 + c * 32;
+          if (nbase >= p.N) continue;
+          float* crow = p.C + (size_t)m * p.ldc + nbase;
+          const float* drow = p.D ? p.D + (size_t)m * p.ldd + nbase : nullptr;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nbase + j;
+            float x = racc[c * 32 + j];
+            if (p.colscale && n < p.N) {
+              float sc = p.colscale[n];
+              if (p.colscale_sq) sc = sc * sc;
+              x = p.colscale_recip ? x * (1.0f / sc) : x * sc;
+            }
+            if (p.triu && m > n) x = 0.f;
+            if (drow && n < p.N) x = drow[j] - mu * x;
+            if (n < p.N) mx = fmaxf(mx, fabsf(x));
+            v[j] = x;
+          }
+          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < p.N) crow[j] = v[j];
+          }
+        }
+      }
+    }
+    if (p.maxabs) {
+      mx = warp_max(mx);
+      if (lane == 0 && mx > 0.f) atomic_max_nonneg(p.maxabs, mx);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
+}
+
+// ---------------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------------
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* p = nullptr;
+  cudaDriverEntryPointQueryResult q;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) != cudaSuccess ||
+      q != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(p);
+  return fn;
+}
+
+// Row-major [rows, cols] fp32 matrix with leading dimension ld; box = {32 floats along cols, box_rows rows}.
+static int make_map(CUtensorMap* map, const float* base, int rows, int cols, int ld, int box_rows, bool mn_major) {
+  EncodeTiledFn fn = get_encode_fn();
+  PSGD_REQUIRE(fn != nullptr, PSGD_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+  cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+  cuuint64_t gstride[1] = {(cuuint64_t)ld * 4};
+  cuuint32_t box[2] = {32u, (cuuint32_t)box_rows};
+  cuuint32_t estr[2] = {1u, 1u};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, mn_major ? CU_TENSOR_MAP_SWIZZLE_128B_ATOM_32B : CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  PSGD_REQUIRE(r == CUDA_SUCCESS, PSGD_ERR_CUDA, "cuTensorMapEncodeTiled failed with %d (rows=%d cols=%d ld=%d)", (int)r,
+               rows, cols, ld);
+  return PSGD_OK;
+}
+
+static bool operand_ok(const float* p, int ld) { return p && aligned16(p) && (ld % 4) == 0; }
+
+bool gemm_tc_supported(const la::Gemm& g) {
+  if (g.M < 1 || g.N < 1 || g.K < 1) return false;
+  if (!operand_ok(g.A, g.lda) || !operand_ok(g.B, g.ldb)) return false;
+  if (g.K2 > 0 && (!operand_ok(g.A2, g.lda2) || !operand_ok(g.B2, g.ldb2))) return false;
+  return true;
+}
+
+template <int BN>
+static int launch(psgd_ctx* ctx, const la::Gemm& g) {
+  using C = Cfg<BN>;
+  Params p{};
+  p.M = g.M; p.N = g.N;
+  p.K[0] = g.K; p.K[1] = g.K2;
+  // op(A) is [M,K]: !ta -> A stored [M,K] (K-major); ta -> A stored [K,M] (MN-major)
+  p.a_mn[0] = g.ta ? 1 : 0;
+  // op(B) is [K,N]: tb -> B stored [N,K] (K-major); !tb -> B stored [K,N] (MN-major)
+  p.b_mn[0] = g.tb ? 0 : 1;
+  p.a_mn[1] = g.ta2 ? 1 : 0;
+  p.b_mn[1] = g.tb2 ? 0 : 1;
+  p.a_tri = g.a_tri; p.b_tri = g.b_tri;
+  p.C = g.C; p.ldc = g.ldc; p.triu = g.triu ? 1 : 0; p.maxabs = g.maxabs;
+  p.D = g.D; p.ldd = g.ldd; p.mu_max = g.mu_max; p.step = g.step; p.tiny = g.tiny;
+  p.colscale = g.colscale; p.colscale_recip = g.colscale_recip; p.colscale_sq = g.colscale_sq;
+  p.tiles_m = (g.M + BM - 1) / BM;
+  p.tiles_n = (g.N + BN - 1) / BN;
+
+  CUtensorMap tA[2], tB[2];
+  for (int prod = 0; prod < 2; ++prod) {
+    const float* A = prod ? g.A2 : g.A;
+    const float* B = prod ? g.B2 : g.B;
+    const int lda = prod ? g.lda2 : g.lda, ldb = prod ? g.ldb2 : g.ldb;
+    const int K = prod ? g.K2 : g.K;
+    if (K <= 0) { tA[prod] = tA[0]; tB[prod] = tB[0]; continue; }
+    if (!p.a_mn[prod]) PSGD_RETURN_IF(make_map(&tA[prod], A, g.M, K, lda, BM, false));     // [M,K], box {32k, 128m}
+    else               PSGD_RETURN_IF(make_map(&tA[prod], A, K, g.M, lda, BK, true));     // [K,M], box {32m, 32k}
+    if (!p.b_mn[prod]) PSGD_RETURN_IF(make_map(&tB[prod], B, g.N, K, ldb, BN, false));     // [N,K], box {32k, BN n}
+    else               PSGD_RETURN_IF(make_map(&tB[prod], B, K, g.N, ldb, BK, true));     // [K,N], box {32n, 32k}
+  }
+  auto kern = gemm_tc_kernel<BN>;
+  static bool attr_done = false;
+  if (!attr_done) {
+    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    attr_done = true;
+  }
+  int grid = p.tiles_m * p.tiles_n;
+  if (grid > ctx->num_sms) grid = ctx->num_sms;
+  ProfScope prof(ctx, PSGD_K_GEMM);
+  kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(tA[0], tB[0], tA[1], tB[1], p);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+int gemm_tc(psgd_ctx* ctx, const la::Gemm& g) {
+  PSGD_REQUIRE(gemm_tc_supported(g), PSGD_ERR_BAD_SHAPE,
+               "tcgen05 GEMM needs 16-byte aligned operands with leading dimensions that are multiples of 4");
+  if (g.M <= 0 || g.N <= 0) return PSGD_OK;
+  return launch<128>(ctx, g);
+}
+
+int gemm_auto(psgd_ctx* ctx, const la::Gemm& g) {
+  const bool big = g.M >= 256 && g.N >= 256 && g.K >= 256;
+  const bool use_tc = gemm_tc_supported(g) && (ctx->opt_gemm_path == 2 || (ctx->opt_gemm_path == 0 && big));
+  if (use_tc) return gemm_tc(ctx, g);
+  ProfScope prof(ctx, PSGD_K_GEMM);
+  return la::gemm_simt(ctx, g);
+}
 
 int trsm_right_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int n) {
   return la::trsm_right_upper(ctx, Q, ldq, B, ldb, X, ldx, m, n);
@@ -17,3 +543,18 @@ size_t extra_ws_bytes(int64_t, int64_t) { return 0; }
 
 }  // namespace tc
 }  // namespace psgd
+
+// Diagnostic / building-block entry point: C = op(A) op(B) through a chosen engine (tests compare the engines).
+extern "C" int psgd_gemm(psgd_ctx* ctx, int engine, int M, int N, int K, const float* A, int lda, int ta,
+                         const float* B, int ldb, int tb, float* C, int ldc, int triu, int a_tri, int b_tri) {
+  using namespace psgd;
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(A && B && C, PSGD_ERR_BAD_POINTER, "psgd_gemm: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  la::Gemm g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.ta = ta != 0; g.B = B; g.ldb = ldb; g.tb = tb != 0;
+  g.C = C; g.ldc = ldc; g.triu = triu != 0; g.a_tri = a_tri; g.b_tri = b_tri;
+  if (engine == 1) return la::gemm_simt(ctx, g);
+  if (engine == 2) return tc::gemm_tc(ctx, g);
+  return tc::gemm_auto(ctx, g);
+}

@@ -27,6 +27,9 @@ struct Gemm {
   const float* D = nullptr; int ldd = 0;     // if set: C = D - mu * acc
   const float* mu_max = nullptr;  // mu = step / (*mu_max + tiny)
   float step = 0.f, tiny = 0.f;
+  // K-range hints (product 0 only; the engines may skip structurally-zero K blocks, never required for correctness
+  // of dense data): 0 none, 1 = op(.) upper triangular, 2 = lower triangular, viewed as op(A)[M,K] / op(B)[K,N]
+  int a_tri = 0, b_tri = 0;
   const float* colscale = nullptr;   // acc *= colscale[n]   (or its reciprocal)
   bool colscale_recip = false;
   bool colscale_sq = false;          // use colscale[n]^2

