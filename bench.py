@@ -201,7 +201,7 @@ def run_uvd(args, rank, world, local):
     peaks = load_peaks()
     per_kernel_bytes, step_bytes = uvd_bytes(n, r)
     agg = {}
-    for kid, kms in prof:
+    for kid, kms, _w in prof:
         a = agg.setdefault(kid, [0.0, 0])
         a[0] += kms; a[1] += 1
     kernels = []

@@ -1,0 +1,210 @@
+"""Kron-stack workload of bench.py: synthetic L-layer n x n MLP gradient stack, batched dense-dense Kron update+apply
+(BASELINE.json configs[2]); layers sharded layer-wise over the ranks, preconditioned gradients all-gathered."""
+from __future__ import annotations
+
+import os
+import time
+
+import numpy as np
+
+
+def tf32_peak_tflops(torch, n=8192, iters=10):
+    """cuBLAS TF32 GEMM throughput on this GPU: calibration of the 3xTF32 roofline denominator only (MEASURED_PEAKS.json
+    records bf16 but no TF32 figure); never on the product path."""
+    prev = torch.backends.cuda.matmul.allow_tf32
+    torch.backends.cuda.matmul.allow_tf32 = True
+    a = torch.randn(n, n, device="cuda"); b = torch.randn(n, n, device="cuda")
+    for _ in range(3):
+        a @ b
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    best = 1e9
+    for _ in range(3):
+        e0.record()
+        for _ in range(iters):
+            a @ b
+        e1.record(); torch.cuda.synchronize()
+        best = min(best, e0.elapsed_time(e1) / iters)
+    torch.backends.cuda.matmul.allow_tf32 = prev
+    del a, b
+    return 2.0 * n ** 3 / best / 1e9
+
+
+def kron_flops(n):
+    """Dense flop count of the reference's op sequence for one square dense-dense layer:
+    update 18 n^3 + apply 8 n^3."""
+    return 26.0 * n ** 3
+
+
+def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
+    import torch
+    import torch.distributed as dist
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    L, n = args.layers, args.kron_n
+    owned = partition.assign_layers([partition.kron_layer_cost(n, n)] * L, world)
+    mine = owned[rank]
+    gen = torch.Generator(device=dev).manual_seed(1000 + rank)
+    ctx = psgd.get_context(local)
+
+    Ql = [torch.eye(n, device=dev) for _ in mine]                    # identity init (mnist_with_lenet5.py:61-62)
+    Qr = [torch.eye(n, device=dev) for _ in mine]
+    S = [0.5 + 1.5 * torch.rand(n, 1, device=dev, generator=gen) for _ in mine]
+    T = [0.5 + 1.5 * torch.rand(1, n, device=dev, generator=gen) for _ in mine]
+    POOL = 2
+    pool = []
+    for _ in range(POOL):
+        dX = [torch.randn(n, n, device=dev, generator=gen) for _ in mine]
+        dG = [s * x * t + 0.1 * torch.randn(n, n, device=dev, generator=gen) for s, x, t in zip(S, dX, T)]
+        G = [torch.randn(n, n, device=dev, generator=gen) for _ in mine]
+        pool.append((dX, dG, G))
+    shapes = [(n, n)] * L
+
+    def step(i, Ql, Qr, dX, dG, G):
+        new = psgd.update_precond_kron_batched(Ql, Qr, dX, dG, 0.01)
+        Ql2, Qr2 = [a for a, _ in new], [b for _, b in new]
+        pre = psgd.precond_grad_kron_batched(Ql2, Qr2, G)
+        if world > 1:
+            pre = partition.all_gather_layers(pre, owned, shapes, rank)
+        return Ql2, Qr2, pre
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(args.warmup):
+        Ql, Qr, pre = step(i, Ql, Qr, *pool[i % POOL])
+    ctx.set_option("profile", 1)
+    ctx.profile_read(cap=1 << 20)
+    clocks = ClockSampler(local)
+    barrier()
+    if rank == 0:
+        clocks.start()
+    launches0 = ctx.launch_count
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        Ql, Qr, pre = step(args.warmup + i, Ql, Qr, *pool[i % POOL])
+    e1.record()
+    barrier()
+    clk = clocks.stop() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = ctx.launch_count - launches0
+    prof = ctx.profile_read(cap=1 << 20)
+    ctx.set_option("profile", 0)
+    t = torch.tensor([ms], device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    assert all(torch.isfinite(p).all() for p in pre[:1])
+    value = args.steps / (ms / 1e3)
+
+    # ---- roofline: tensor pipe, 3xTF32 => ceiling = measured TF32 GEMM peak / 3 ---------------------
+    tf32 = tf32_peak_tflops(torch)
+    ceiling = tf32 / 3.0
+    names = {10: "gemm_tc_kernel (tcgen05 3xTF32)", 11: "trsm_block_kernel (SIMT diagonal blocks)", 12: "gemm_simt_kernel"}
+    agg = {}
+    for kid, kms, work in prof:
+        a = agg.setdefault(kid, [0.0, 0, 0.0])
+        a[0] += kms; a[1] += 1; a[2] += work
+    kernels = []
+    for kid, (tot, cnt, work) in sorted(agg.items()):
+        ach = work / (tot * 1e-3) / 1e12 if tot > 0 else 0.0
+        kernels.append(dict(kernel=names.get(kid, str(kid)), launches=cnt, total_ms=round(tot, 3), avg_ms=round(tot / cnt, 4),
+                            algorithmic_TFLOP=round(work / 1e12, 3), achieved_TFLOPs=round(ach, 1),
+                            frac=round(ach / ceiling, 4), share_of_step=round(tot / ms, 4)))
+    dom = max(kernels, key=lambda k: k["total_ms"]) if kernels else None
+    step_flops = kron_flops(n) * len(mine)
+    step_ach = step_flops / (ms / args.steps * 1e-3) / 1e12
+    roofline = None
+    if dom:
+        roofline = dict(bound="tensor", kernel=dom["kernel"], achieved=dom["achieved_TFLOPs"], peak=round(ceiling, 1),
+                        unit="TFLOP/s", frac=dom["frac"], traffic=None,
+                        peak_source=f"cuBLAS TF32 8192^3 measured in this run = {tf32:.0f} TFLOP/s, divided by 3 (3xTF32); "
+                                    f"MEASURED_PEAKS.json has no TF32 figure (bf16 burst {load_peaks()['bf16']:.0f})",
+                        step_achieved=round(step_ach, 1), step_frac=round(step_ach / ceiling, 4),
+                        step_algorithmic_TFLOP=round(step_flops / 1e12, 2),
+                        note="flops are the dense count of the reference's op sequence (26 n^3 per layer-step); "
+                             "triangular tile skipping legitimately raises the fraction")
+
+    # ---- end to end: host (pinned) dX, dG, G per step, preconditioned gradients read back ----------------
+    e2e = None
+    if not args.no_e2e:
+        nb = min(len(mine), 2)              # bounded pinned staging: stream layer by layer through 2 slots
+        h_in = [[torch.randn(n, n).pin_memory() for _ in range(3)] for _ in range(nb)]
+        h_out = [torch.empty(n, n).pin_memory() for _ in range(nb)]
+        d_in = [[torch.empty(n, n, device=dev) for _ in range(3)] for _ in range(nb)]
+
+        def e2e_step(Ql, Qr):
+            outQl, outQr = [], []
+            for li in range(len(mine)):
+                k = li % nb
+                for a, b in zip(d_in[k], h_in[k]):
+                    a.copy_(b, non_blocking=True)
+                ql, qr = psgd.update_precond_kron(Ql[li], Qr[li], d_in[k][0], d_in[k][1], 0.01)
+                p = psgd.precond_grad_kron(ql, qr, d_in[k][2])
+                h_out[k].copy_(p, non_blocking=True)
+                outQl.append(ql); outQr.append(qr)
+            return outQl, outQr
+
+        Ql, Qr = e2e_step(Ql, Qr)
+        barrier()
+        f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ksteps = max(1, min(args.steps, 3))
+        f0.record()
+        for _ in range(ksteps):
+            Ql, Qr = e2e_step(Ql, Qr)
+        f1.record()
+        barrier()
+        ems = f0.elapsed_time(f1)
+        t = torch.tensor([ems], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ems = float(t.item())
+        e2e = dict(value=round(ksteps / (ems / 1e3), 4), unit=UNIT, h2d_bytes_per_step=int(3 * 4 * n * n * L),
+                   d2h_bytes_per_step=int(4 * n * n * L), ms_per_step=round(ems / ksteps, 2), steps=ksteps,
+                   note="dX, dG, G of every layer uploaded from pinned host memory and the preconditioned gradient read "
+                        "back to host every step through the per-layer public API; factors stay device-resident")
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_baseline_kron(L, n)
+    if rank != 0:
+        return None
+    return dict(
+        metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
+        ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="strong", vs_baseline=None,
+        dtype="f32 (3xTF32 tensor-core products, fp32 accumulate)", data="synthetic",
+        config=dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply, batched (BASELINE configs[2])", layers=L, n=n,
+                    layers_per_gpu=len(mine), parallelism=f"layer-sharded x{world} + all-gather of preconditioned gradients",
+                    l2_policy=f"inputs larger than L2: {len(mine) * 5 * 4 * n * n / 1e9:.1f} GB of factors+inputs per GPU per step vs 126 MB L2",
+                    step_size=0.01),
+        roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+
+
+def cpu_baseline_kron(L, n, ns=1024, steps=2):
+    from oracle import psgd_oracle as O
+    from bench import _blas_threads, UNIT
+    rng = np.random.default_rng(1000)
+    ns = min(ns, n)
+    Ql = np.eye(ns, dtype=np.float32); Qr = np.eye(ns, dtype=np.float32)
+
+    def one(Ql, Qr):
+        dX = rng.standard_normal((ns, ns), dtype=np.float32); dG = rng.standard_normal((ns, ns), dtype=np.float32)
+        G = rng.standard_normal((ns, ns), dtype=np.float32)
+        Ql, Qr = O.update_precond_kron(Ql, Qr, dX, dG, 0.01)
+        return Ql, Qr, O.precond_grad_kron(Ql, Qr, G)
+
+    Ql, Qr, _ = one(Ql, Qr)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        Ql, Qr, _ = one(Ql, Qr)
+    dt = (time.perf_counter() - t0) / steps
+    full = dt * (n / ns) ** 3 * L
+    return dict(value=round(1.0 / full, 6), unit=UNIT, cores=_blas_threads(), kind="port",
+                sample=f"oracle (NumPy/SciPy float32 restatement of psgd.py:156-192) on one {ns}x{ns} layer, {steps} timed "
+                       f"steps ({dt * 1e3:.0f} ms each), scaled by (n/{ns})^3 x {L} layers; host has {os.cpu_count()} logical "
+                       f"cores, BLAS threads = {_blas_threads()}")

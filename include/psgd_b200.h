@@ -63,15 +63,18 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 
 /* Per-kernel device timing.  After psgd_set_option(ctx, "profile", 1) every large kernel launch is bracketed
  * by CUDA events on ctx's stream; psgd_profile_read synchronises on them, writes up to `cap` (kernel id,
- * milliseconds) records in launch order, clears the log and returns the number written.  Kernel ids: */
+ * milliseconds, work) records in launch order, clears the log and returns the number written.  `work` (may be
+ * NULL) is the launch's algorithmic work: dense-count flops for GEMM/TRSM launches, 0 where the caller knows the
+ * byte count from the shapes (UVd sweeps).  Kernel ids: */
 #define PSGD_K_UVD_GRAM_UPDATE 1 /* update sweep 1: Gram/vector reductions over U,V,d,h,v  */
 #define PSGD_K_UVD_MAP_UPDATE2 2 /* update sweep 2: per-row a,b,nablaD + max/sums            */
 #define PSGD_K_UVD_MAP_UPDATE3 3 /* update sweep 3: write d and U (or V)                      */
 #define PSGD_K_UVD_GRAM_APPLY 4  /* apply sweep 1: U^T U, U^T(dg), V^T(dg)                    */
 #define PSGD_K_UVD_MAP_APPLY 5   /* apply sweep 2: write the preconditioned gradient          */
-#define PSGD_K_GEMM 10           /* one dense-factor GEMM launch (either engine)              */
+#define PSGD_K_GEMM 10           /* one tcgen05 3xTF32 GEMM launch                            */
+#define PSGD_K_GEMM_SIMT 12      /* one SIMT fp32 GEMM launch                                 */
 #define PSGD_K_TRSM 11           /* one triangular-solve step                                 */
-int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, int cap);
+int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, double* work, int cap);
 
 /* Cross-rank reduction hook for the chunk-sharded (multi-GPU) streaming paths.  When set, the
  * library calls it on ctx's stream between kernels with a device buffer of `count` float64

@@ -40,7 +40,7 @@ SIGNATURES = {
     "psgd_launch_count": (C.c_int64, [C.c_void_p]),
     "psgd_workspace_bytes": (C.c_int64, [C.c_void_p]),
     "psgd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
-    "psgd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.c_int]),
+    "psgd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
     "psgd_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
     "psgd_uvd_update": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]),
     "psgd_uvd_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int]),
@@ -133,11 +133,12 @@ class Context:
         return int(self.lib.psgd_workspace_bytes(self.handle))
 
     def profile_read(self, cap: int = 4096):
-        """[(kernel id, milliseconds)] recorded since the last read (needs set_option("profile", 1))."""
+        """[(kernel id, milliseconds, work)] recorded since the last read (needs set_option("profile", 1))."""
         ids = (C.c_int * cap)()
         ms = (C.c_float * cap)()
-        n = self.lib.psgd_profile_read(self.handle, ids, ms, cap)
-        return [(int(ids[i]), float(ms[i])) for i in range(n)]
+        work = (C.c_double * cap)()
+        n = self.lib.psgd_profile_read(self.handle, ids, ms, work, cap)
+        return [(int(ids[i]), float(ms[i]), float(work[i])) for i in range(n)]
 
     def set_allreduce(self, pyfunc):
         """pyfunc(device_ptr:int, count:int, op:int, stream:int) -> int, or None to clear."""

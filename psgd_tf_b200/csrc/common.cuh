@@ -60,11 +60,12 @@ struct psgd_ctx {
   int opt_direct = 0;        // streaming kernels: 1 = direct global loads instead of TMA pipeline
   int opt_gemm_path = 0;     // dense GEMMs: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
+  int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks
   psgd_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
   // optional per-kernel timing (psgd_set_option("profile", 1)): CUDA event pairs around the large kernels
   int opt_profile = 0;
-  struct ProfRec { int id; cudaEvent_t e0, e1; };
+  struct ProfRec { int id; cudaEvent_t e0, e1; double work; };
   std::vector<ProfRec> prof;
 
   // Ensure at least `bytes` of workspace; contents are NOT preserved across growth.
@@ -92,9 +93,11 @@ struct ProfScope {
   psgd_ctx* c;
   psgd_ctx::ProfRec r;
   bool on;
-  ProfScope(psgd_ctx* ctx, int id) : c(ctx), on(ctx->opt_profile != 0) {
+  // work: algorithmic bytes or flops of the launch (dense count), reported back by psgd_profile_read
+  ProfScope(psgd_ctx* ctx, int id, double work = 0.0) : c(ctx), on(ctx->opt_profile != 0) {
     if (!on) return;
     r.id = id;
+    r.work = work;
     cudaEventCreate(&r.e0);
     cudaEventCreate(&r.e1);
     cudaEventRecord(r.e0, c->stream);

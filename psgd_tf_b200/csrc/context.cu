@@ -84,6 +84,7 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   PSGD_REQUIRE(ctx && key, PSGD_ERR_BAD_POINTER, "null context or key");
   if (strcmp(key, "direct") == 0) { ctx->opt_direct = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "profile") == 0) { ctx->opt_profile = value ? 1 : 0; return PSGD_OK; }
+  if (strcmp(key, "assume_triangular") == 0) { ctx->opt_assume_tri = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_bn") == 0) {
     PSGD_REQUIRE(value == 128 || value == 256, PSGD_ERR_BAD_SHAPE, "tc_bn must be 128 or 256");
     ctx->opt_tc_bn = (int)value;
@@ -105,14 +106,14 @@ extern "C" int psgd_set_allreduce(psgd_ctx* ctx, psgd_allreduce_fn fn, void* use
   return PSGD_OK;
 }
 
-extern "C" int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, int cap) {
+extern "C" int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, double* work, int cap) {
   if (!ctx) return 0;
   int n = 0;
   for (auto& r : ctx->prof) {
     cudaEventSynchronize(r.e1);
     float t = 0.f;
     cudaEventElapsedTime(&t, r.e0, r.e1);
-    if (n < cap && ids && ms) { ids[n] = r.id; ms[n] = t; ++n; }
+    if (n < cap && ids && ms) { ids[n] = r.id; ms[n] = t; if (work) work[n] = r.work; ++n; }
     cudaEventDestroy(r.e0);
     cudaEventDestroy(r.e1);
   }

@@ -349,7 +349,7 @@ __global__ void __launch_bounds__(kThreads, 1)
     int tcount = 0;
     float mx = 0.f;
     float mu = 0.f;
-    if (p.D) mu = p.step / (*p.mu_max + p.tiny);
+    if (p.D) mu = p.mu_max ? p.step / (*p.mu_max + p.tiny) : 1.0f;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
@@ -512,7 +512,7 @@ static int launch(psgd_ctx* ctx, const la::Gemm& g) {
   }
   int grid = p.tiles_m * p.tiles_n;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
-  ProfScope prof(ctx, PSGD_K_GEMM);
+  ProfScope prof(ctx, PSGD_K_GEMM, 2.0 * g.M * g.N * ((double)g.K + g.K2));
   kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(tA[0], tB[0], tA[1], tB[1], p);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
@@ -529,15 +529,71 @@ int gemm_auto(psgd_ctx* ctx, const la::Gemm& g) {
   const bool big = g.M >= 256 && g.N >= 256 && g.K >= 256;
   const bool use_tc = gemm_tc_supported(g) && (ctx->opt_gemm_path == 2 || (ctx->opt_gemm_path == 0 && big));
   if (use_tc) return gemm_tc(ctx, g);
-  ProfScope prof(ctx, PSGD_K_GEMM);
+  ProfScope prof(ctx, PSGD_K_GEMM_SIMT, 2.0 * g.M * g.N * ((double)g.K + g.K2));
   return la::gemm_simt(ctx, g);
 }
 
+// ---------------------------------------------------------------------------------------------
+// triangular solves: recursive blocking.  The two half-size solves recurse down to kTrsmBase-wide diagonal blocks
+// (SIMT substitution, one launch per block); everything off the diagonal is one large tcgen05 GEMM per level, so
+// ~95 % of the m*n^2 multiply-adds run on the tensor cores.   Replaces tf.linalg.triangular_solve (psgd.py:174, :233,
+// :298) for large factors.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTrsmBase = 128;
+
+static int split_point(int lo, int hi) {
+  const int half = (hi - lo) / 2;
+  return lo + ((half + kTrsmBase - 1) / kTrsmBase) * kTrsmBase;
+}
+
+// X[:, j0:j1] (in place) <- X[:, j0:j1] Q[j0:j1, j0:j1]^-1
+static int trsm_right_rec(psgd_ctx* ctx, const float* Q, int ldq, float* X, int ldx, int m, int j0, int j1) {
+  if (j1 - j0 <= kTrsmBase) return la::trsm_right_block(ctx, Q, ldq, X, ldx, X, ldx, m, j0, j1);
+  const int mid = split_point(j0, j1);
+  PSGD_RETURN_IF(trsm_right_rec(ctx, Q, ldq, X, ldx, m, j0, mid));
+  la::Gemm g;                                   // X[:, mid:j1] -= X[:, j0:mid] Q[j0:mid, mid:j1]
+  g.M = m; g.N = j1 - mid; g.K = mid - j0;
+  g.A = X + j0; g.lda = ldx;
+  g.B = Q + (size_t)j0 * ldq + mid; g.ldb = ldq;
+  g.C = X + mid; g.ldc = ldx; g.D = X + mid; g.ldd = ldx;
+  PSGD_RETURN_IF(gemm_tc(ctx, g));
+  return trsm_right_rec(ctx, Q, ldq, X, ldx, m, mid, j1);
+}
+
+// X[i0:i1, :] (in place) <- Q[i0:i1, i0:i1]^-T X[i0:i1, :]
+static int trsm_left_rec(psgd_ctx* ctx, const float* Q, int ldq, float* X, int ldx, int m, int i0, int i1) {
+  if (i1 - i0 <= kTrsmBase) return la::trsm_left_block(ctx, Q, ldq, X, ldx, X, ldx, m, i0, i1);
+  const int mid = split_point(i0, i1);
+  PSGD_RETURN_IF(trsm_left_rec(ctx, Q, ldq, X, ldx, m, i0, mid));
+  la::Gemm g;                                   // X[mid:i1, :] -= Q[i0:mid, mid:i1]^T X[i0:mid, :]
+  g.M = i1 - mid; g.N = m; g.K = mid - i0;
+  g.A = Q + (size_t)i0 * ldq + mid; g.lda = ldq; g.ta = true;
+  g.B = X + (size_t)i0 * ldx; g.ldb = ldx;
+  g.C = X + (size_t)mid * ldx; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
+  PSGD_RETURN_IF(gemm_tc(ctx, g));
+  return trsm_left_rec(ctx, Q, ldq, X, ldx, m, mid, i1);
+}
+
+static bool trsm_tc_ok(psgd_ctx* ctx, const float* Q, int ldq, const float* X, int ldx, int n, int m) {
+  if (ctx->opt_gemm_path == 1) return false;
+  const bool big = n >= 512 && m >= 256;
+  if (!(ctx->opt_gemm_path == 2 || big)) return false;
+  return n > kTrsmBase && aligned16(Q) && aligned16(X) && (ldq % 4) == 0 && (ldx % 4) == 0;
+}
+
 int trsm_right_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int n) {
-  return la::trsm_right_upper(ctx, Q, ldq, B, ldb, X, ldx, m, n);
+  if (!trsm_tc_ok(ctx, Q, ldq, X, ldx, n, m)) return la::trsm_right_upper(ctx, Q, ldq, B, ldb, X, ldx, m, n);
+  if (X != B)
+    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 4, B, (size_t)ldb * 4, (size_t)n * 4, m, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+  return trsm_right_rec(ctx, Q, ldq, X, ldx, m, 0, n);
 }
 int trsm_left_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int n, int m) {
-  return la::trsm_left_upper_adjoint(ctx, Q, ldq, B, ldb, X, ldx, n, m);
+  if (!trsm_tc_ok(ctx, Q, ldq, X, ldx, n, m)) return la::trsm_left_upper_adjoint(ctx, Q, ldq, B, ldb, X, ldx, n, m);
+  if (X != B)
+    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 4, B, (size_t)ldb * 4, (size_t)m * 4, n, cudaMemcpyDeviceToDevice,
+                                      ctx->stream));
+  return trsm_left_rec(ctx, Q, ldq, X, ldx, m, 0, n);
 }
 size_t extra_ws_bytes(int64_t, int64_t) { return 0; }
 

@@ -251,7 +251,14 @@ static size_t col_partial_floats(int M, int N) {
   return (size_t)((M + kColChunkRows - 1) / kColChunkRows) * 2 * N;
 }
 
-static int gemm(psgd_ctx* ctx, const la::Gemm& g) { return tc::gemm_auto(ctx, g); }
+// Dense Kron/Cholesky factors are upper triangular by construction (identity-initialised and only ever updated as
+// Q - triu(.) Q), which lets the tensor-core engine skip structurally zero K blocks.  The hints
+// are dropped with psgd_set_option(ctx, "assume_triangular", 0) for callers that feed arbitrary square matrices.
+static int gemm(psgd_ctx* ctx, la::Gemm g, int a_tri = 0, int b_tri = 0) {
+  if (ctx->opt_assume_tri) { g.a_tri = a_tri; g.b_tri = b_tri; }
+  return tc::gemm_auto(ctx, g);
+}
+constexpr int kUpper = 1, kLower = 2;
 
 // triu(X X^T - Y Y^T) (rows) or triu(X^T X - Y^T Y) (cols) with max|.| -> *mx
 static int gram_diff(psgd_ctx* ctx, const float* X, const float* Y, int M, int N, bool rows, float* out, float* mx) {
@@ -270,7 +277,7 @@ static int factor_step(psgd_ctx* ctx, const float* grad, const float* Q, int n, 
   la::Gemm g;
   g.M = n; g.N = n; g.K = n; g.A = grad; g.lda = n; g.B = Q; g.ldb = n;
   g.C = Qout; g.ldc = n; g.D = Q; g.ldd = n; g.mu_max = mx; g.step = step; g.tiny = tiny;
-  return gemm(ctx, g);
+  return gemm(ctx, g, kUpper, kUpper);
 }
 
 static int balance(psgd_ctx* ctx, int kl, const float* Ql, int M, int kr, const float* Qr, int N, Scal* sc,
@@ -310,10 +317,10 @@ static int update_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, cons
     float* T1 = c.take<float>(MN);
     la::Gemm g1;                                                           // T1 = dG Qr^T     psgd.py:173
     g1.M = M; g1.N = N; g1.K = N; g1.A = dG; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = T1; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
     la::Gemm g2;                                                           // A = Ql T1
     g2.M = M; g2.N = N; g2.K = M; g2.A = Qlb; g2.lda = M; g2.B = T1; g2.ldb = N; g2.C = A; g2.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g2));
+    PSGD_RETURN_IF(gemm(ctx, g2, kUpper, 0));
     PSGD_RETURN_IF(tc::trsm_right_auto(ctx, Qrb, N, dX, N, T1, N, M, N));          // W = dX Qr^-1   psgd.py:174
     PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, T1, N, Bt, N, M, N));           // Bt = Ql^-T W
   } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
@@ -324,7 +331,7 @@ static int update_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, cons
     PSGD_LAUNCH_CHECK(ctx);
     la::Gemm g1;                                                           // A = (Ql dG) Qr^T  psgd.py:220
     g1.M = M; g1.N = N; g1.K = N; g1.A = T1; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = A; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
     PSGD_RETURN_IF(col_reduce(ctx, 0, Qlb, dX, nullptr, M, N, part, cvec, nullptr));
     norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dX, cvec, T1, M, N, nullptr); // :230-232
     PSGD_LAUNCH_CHECK(ctx);
@@ -333,7 +340,7 @@ static int update_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, cons
     la::Gemm g1;                                                           // A = (Ql dG) * qr  psgd.py:295-296
     g1.M = M; g1.N = N; g1.K = M; g1.A = Qlb; g1.lda = M; g1.B = dG; g1.ldb = N; g1.C = A; g1.ldc = N;
     g1.colscale = Qrb;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, kUpper, 0));
     PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, dX, N, Bt, N, M, N));                             // :298
     col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Bt, Qrb, M, N);                   // :299
     PSGD_LAUNCH_CHECK(ctx);
@@ -396,13 +403,13 @@ static int right_dense_apply(psgd_ctx* ctx, const float* X, const float* Qr, int
   if (M < N) {
     la::Gemm g1; g1.M = M; g1.N = N; g1.K = N; g1.A = X; g1.lda = N; g1.B = Qr; g1.ldb = N; g1.tb = true;
     g1.C = tmp_mn; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
     la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = tmp_mn; g2.lda = N; g2.B = Qr; g2.ldb = N; g2.C = out; g2.ldc = N;
-    return gemm(ctx, g2);
+    return gemm(ctx, g2, 0, kUpper);
   }
   la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
   g1.C = tmp_nn; g1.ldc = N;
-  PSGD_RETURN_IF(gemm(ctx, g1));
+  PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
   la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = X; g2.lda = N; g2.B = tmp_nn; g2.ldb = N; g2.C = out; g2.ldc = N;
   return gemm(ctx, g2);
 }
@@ -413,17 +420,17 @@ static int left_dense_apply(psgd_ctx* ctx, const float* Ql, const float* X, int 
   if (M < N) {
     la::Gemm g1; g1.M = M; g1.N = M; g1.K = M; g1.A = Ql; g1.lda = M; g1.ta = true; g1.B = Ql; g1.ldb = M;
     g1.C = tmp_mm; g1.ldc = M;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
     la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = tmp_mm; g2.lda = M; g2.B = X; g2.ldb = N; g2.C = out; g2.ldc = N;
     g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
     return gemm(ctx, g2);
   }
   la::Gemm g1; g1.M = M; g1.N = N; g1.K = M; g1.A = Ql; g1.lda = M; g1.B = X; g1.ldb = N; g1.C = tmp_mn; g1.ldc = N;
-  PSGD_RETURN_IF(gemm(ctx, g1));
+  PSGD_RETURN_IF(gemm(ctx, g1, kUpper, 0));
   la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = Ql; g2.lda = M; g2.ta = true; g2.B = tmp_mn; g2.ldb = N;
   g2.C = out; g2.ldc = N;
   g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
-  return gemm(ctx, g2);
+  return gemm(ctx, g2, kLower, 0);
 }
 
 static int apply_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* G,
@@ -438,21 +445,21 @@ static int apply_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const
       PSGD_RETURN_IF(left_dense_apply(ctx, Ql, G, M, N, P, nullptr, t1, nullptr));      // (Ql^T Ql) G
       la::Gemm g3; g3.M = M; g3.N = N; g3.K = N; g3.A = t1; g3.lda = N; g3.B = Qr; g3.ldb = N; g3.tb = true;
       g3.C = t2; g3.ldc = N;
-      PSGD_RETURN_IF(gemm(ctx, g3));
+      PSGD_RETURN_IF(gemm(ctx, g3, 0, kLower));
       la::Gemm g4; g4.M = M; g4.N = N; g4.K = N; g4.A = t2; g4.lda = N; g4.B = Qr; g4.ldb = N; g4.C = out; g4.ldc = N;
-      return gemm(ctx, g4);
+      return gemm(ctx, g4, 0, kUpper);
     }
     float* P = c.take<float>((size_t)N * N);                              // psgd.py:192
     la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
     g1.C = P; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1));
+    PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
     la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = G; g2.lda = N; g2.B = P; g2.ldb = N; g2.C = t1; g2.ldc = N;
     PSGD_RETURN_IF(gemm(ctx, g2));
     la::Gemm g3; g3.M = M; g3.N = N; g3.K = M; g3.A = Ql; g3.lda = M; g3.B = t1; g3.ldb = N; g3.C = t2; g3.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g3));
+    PSGD_RETURN_IF(gemm(ctx, g3, kUpper, 0));
     la::Gemm g4; g4.M = M; g4.N = N; g4.K = M; g4.A = Ql; g4.lda = M; g4.ta = true; g4.B = t2; g4.ldb = N;
     g4.C = out; g4.ldc = N;
-    return gemm(ctx, g4);
+    return gemm(ctx, g4, kLower, 0);
   }
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
     float* P = c.take<float>((size_t)M * M);

@@ -85,7 +85,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
   }
 
   float mu = 0.f;
-  if (g.D) mu = g.step / (*g.mu_max + g.tiny);
+  if (g.D) mu = g.mu_max ? g.step / (*g.mu_max + g.tiny) : 1.0f;
   float mx = 0.f;
 #pragma unroll
   for (int i = 0; i < 4; ++i) {
@@ -126,125 +126,140 @@ int gemm_simt(psgd_ctx* ctx, const Gemm& g) {
 // ---------------------------------------------------------------------------------------------
 constexpr int NB = 32;
 
-// X[I,:] = Qii^-T ( B[I,:] - sum_{k < i0} Q[k, I]^T X[k, :] ),   CTA = 32 block rows x 32 columns
-__global__ void __launch_bounds__(256) trsm_left_step_kernel(const float* __restrict__ Q, int ldq,
-                                                             const float* __restrict__ B, int ldb,
-                                                             float* __restrict__ X, int ldx, int n, int m, int i0) {
+// Rows [ib0, ib1) of  X = Q^-T B  for one 32-column slab per CTA, assuming rows < ib0 of the right-hand side have
+// already been eliminated (B holds B - Q[0:ib0, :]^T X[0:ib0, :] there).  Left-looking over 32-row steps:
+//   X[I,:] = Qii^-T ( B[I,:] - sum_{ib0 <= k < i0} Q[k, I]^T X[k, :] )
+// Columns are independent, so the whole row range is solved in one launch.
+__global__ void __launch_bounds__(256) trsm_left_block_kernel(const float* __restrict__ Q, int ldq,
+                                                              const float* B, int ldb, float* X, int ldx, int m,
+                                                              int ib0, int ib1) {
   __shared__ float Qs[NB][NB + 1];   // Qs[k][i] = Q[k0+k, i0+i]
   __shared__ float Xs[NB][NB + 1];   // Xs[k][c] = X[k0+k, c0+c]
   const int tid = threadIdx.x;
   const int c0 = blockIdx.x * NB;
   const int lr = tid / NB;          // 0..7
   const int lc = tid % NB;          // 0..31
-  const int ib = min(NB, n - i0);   // rows in this block
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr, lr+8, lr+16, lr+24 ; column lc
-  for (int k0 = 0; k0 < i0; k0 += NB) {
+  for (int i0 = ib0; i0 < ib1; i0 += NB) {
+    const int ib = min(NB, ib1 - i0);   // rows in this step
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr, lr+8, lr+16, lr+24 ; column lc
+    for (int k0 = ib0; k0 < i0; k0 += NB) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = lr + 8 * e;
+        Qs[k][lc] = (i0 + lc < ib1) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;
+        Xs[k][lc] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const float x = Xs[k][lc];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = fmaf(Qs[k][lr + 8 * e], x, acc[e]);
+      }
+      __syncthreads();
+    }
+    // diagonal block: forward substitution with Qii^T (only the upper triangle of Qii is read)
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      const int k = lr + 8 * e;
-      Qs[k][lc] = (i0 + lc < n) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;       // k0+k < i0 <= n always
-      Xs[k][lc] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
+      const int i = lr + 8 * e;
+      Qs[i][lc] = (i < ib && lc < ib && i <= lc) ? Q[(size_t)(i0 + i) * ldq + i0 + lc] : 0.f;   // Qs[k][i], k<=i
+      float b = 0.f;
+      if (i < ib && c0 + lc < m) b = B[(size_t)(i0 + i) * ldb + c0 + lc] - acc[e];
+      Xs[i][lc] = b;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const float x = Xs[k][lc];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = fmaf(Qs[k][lr + 8 * e], x, acc[e]);
+    if (tid < NB && c0 + tid < m) {
+      const int c = tid;
+      for (int i = 0; i < ib; ++i) {
+        float s = Xs[i][c];
+        for (int k = 0; k < i; ++k) s = fmaf(-Qs[k][i], Xs[k][c], s);
+        s = s / Qs[i][i];
+        Xs[i][c] = s;
+        X[(size_t)(i0 + i) * ldx + c0 + c] = s;
+      }
     }
-    __syncthreads();
-  }
-  // diagonal block: forward substitution with Qii^T (only the upper triangle of Qii is read)
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int i = lr + 8 * e;
-    Qs[i][lc] = (i < ib && lc < ib && i <= lc) ? Q[(size_t)(i0 + i) * ldq + i0 + lc] : 0.f;   // Qs[k][i], k<=i
-    float b = 0.f;
-    if (i < ib && c0 + lc < m) b = B[(size_t)(i0 + i) * ldb + c0 + lc] - acc[e];
-    Xs[i][lc] = b;
-  }
-  __syncthreads();
-  if (tid < NB && c0 + tid < m) {
-    const int c = tid;
-    for (int i = 0; i < ib; ++i) {
-      float s = Xs[i][c];
-      for (int k = 0; k < i; ++k) s = fmaf(-Qs[k][i], Xs[k][c], s);
-      s = s / Qs[i][i];
-      Xs[i][c] = s;
-      X[(size_t)(i0 + i) * ldx + c0 + c] = s;
-    }
+    __syncthreads();   // X rows of this step are visible to the next step's k-loop (same CTA)
   }
 }
 
-// X[:,J] = ( B[:,J] - sum_{k < j0} X[:, k] Q[k, J] ) Qjj^-1,   CTA = 32 rows x 32 block columns
-__global__ void __launch_bounds__(256) trsm_right_step_kernel(const float* __restrict__ Q, int ldq,
-                                                              const float* __restrict__ B, int ldb,
-                                                              float* __restrict__ X, int ldx, int m, int n, int j0) {
+// Columns [jb0, jb1) of  X = B Q^-1  for one 32-row slab per CTA, assuming columns < jb0 have been eliminated.
+//   X[:,J] = ( B[:,J] - sum_{jb0 <= k < j0} X[:, k] Q[k, J] ) Qjj^-1
+__global__ void __launch_bounds__(256) trsm_right_block_kernel(const float* __restrict__ Q, int ldq,
+                                                               const float* B, int ldb, float* X, int ldx, int m,
+                                                               int jb0, int jb1) {
   __shared__ float Qs[NB][NB + 1];   // Qs[k][j] = Q[k0+k, j0+j]
   __shared__ float Xs[NB][NB + 1];   // Xs[r][k] = X[r0+r, k0+k]
   const int tid = threadIdx.x;
   const int r0 = blockIdx.x * NB;
   const int lr = tid / NB;          // 0..7
   const int lc = tid % NB;          // 0..31
-  const int jb = min(NB, n - j0);
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr+8e, column lc
-  for (int k0 = 0; k0 < j0; k0 += NB) {
+  for (int j0 = jb0; j0 < jb1; j0 += NB) {
+    const int jb = min(NB, jb1 - j0);
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr+8e, column lc
+    for (int k0 = jb0; k0 < j0; k0 += NB) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = lr + 8 * e;
+        Qs[r][lc] = (j0 + lc < jb1) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
+        Xs[r][lc] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int k = 0; k < NB; ++k) {
+        const float q = Qs[k][lc];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) acc[e] = fmaf(Xs[lr + 8 * e][k], q, acc[e]);
+      }
+      __syncthreads();
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       const int r = lr + 8 * e;
-      Qs[r][lc] = (j0 + lc < n) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
-      Xs[r][lc] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
+      Qs[r][lc] = (r < jb && lc < jb && r <= lc) ? Q[(size_t)(j0 + r) * ldq + j0 + lc] : 0.f;   // Qs[k][j], k<=j
+      float b = 0.f;
+      if (r0 + r < m && lc < jb) b = B[(size_t)(r0 + r) * ldb + j0 + lc] - acc[e];
+      Xs[r][lc] = b;
     }
     __syncthreads();
-#pragma unroll
-    for (int k = 0; k < NB; ++k) {
-      const float q = Qs[k][lc];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) acc[e] = fmaf(Xs[lr + 8 * e][k], q, acc[e]);
+    if (tid < NB && r0 + tid < m) {
+      const int r = tid;
+      for (int j = 0; j < jb; ++j) {
+        float s = Xs[r][j];
+        for (int k = 0; k < j; ++k) s = fmaf(-Xs[r][k], Qs[k][j], s);
+        s = s / Qs[j][j];
+        Xs[r][j] = s;
+        X[(size_t)(r0 + r) * ldx + j0 + j] = s;
+      }
     }
     __syncthreads();
   }
-#pragma unroll
-  for (int e = 0; e < 4; ++e) {
-    const int r = lr + 8 * e;
-    Qs[r][lc] = (r < jb && lc < jb && r <= lc) ? Q[(size_t)(j0 + r) * ldq + j0 + lc] : 0.f;   // Qs[k][j], k<=j
-    float b = 0.f;
-    if (r0 + r < m && lc < jb) b = B[(size_t)(r0 + r) * ldb + j0 + lc] - acc[e];
-    Xs[r][lc] = b;
-  }
-  __syncthreads();
-  if (tid < NB && r0 + tid < m) {
-    const int r = tid;
-    for (int j = 0; j < jb; ++j) {
-      float s = Xs[r][j];
-      for (int k = 0; k < j; ++k) s = fmaf(-Xs[r][k], Qs[k][j], s);
-      s = s / Qs[j][j];
-      Xs[r][j] = s;
-      X[(size_t)(r0 + r) * ldx + j0 + j] = s;
-    }
-  }
+}
+
+int trsm_left_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int ib0,
+                    int ib1) {
+  if (ib1 <= ib0 || m <= 0) return PSGD_OK;
+  ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (ib1 - ib0) * (ib1 - ib0));
+  trsm_left_block_kernel<<<(m + NB - 1) / NB, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, ib0, ib1);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+int trsm_right_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int jb0,
+                     int jb1) {
+  if (jb1 <= jb0 || m <= 0) return PSGD_OK;
+  ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (jb1 - jb0) * (jb1 - jb0));
+  trsm_right_block_kernel<<<(m + NB - 1) / NB, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, jb0, jb1);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
 }
 
 int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx,
                             int n, int m) {
-  if (n <= 0 || m <= 0) return PSGD_OK;
-  const int grid = (m + NB - 1) / NB;
-  for (int i0 = 0; i0 < n; i0 += NB) {
-    trsm_left_step_kernel<<<grid, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, n, m, i0);
-    PSGD_LAUNCH_CHECK(ctx);
-  }
-  return PSGD_OK;
+  return trsm_left_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, n);
 }
 
 int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
                      int n) {
-  if (n <= 0 || m <= 0) return PSGD_OK;
-  const int grid = (m + NB - 1) / NB;
-  for (int j0 = 0; j0 < n; j0 += NB) {
-    trsm_right_step_kernel<<<grid, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, n, j0);
-    PSGD_LAUNCH_CHECK(ctx);
-  }
-  return PSGD_OK;
+  return trsm_right_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, n);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -45,6 +45,13 @@ int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float*
 int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
                      int n);
 
+// Block forms used by the recursive tensor-core TRSM (gemm_tc.cu): solve only rows [ib0, ib1) / columns [jb0, jb1),
+// assuming the contribution of earlier rows / columns has already been subtracted from B.  One launch each.
+int trsm_left_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int ib0,
+                    int ib1);
+int trsm_right_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int jb0,
+                     int jb1);
+
 // out[c, r] = in[r, c]
 int transpose(psgd_ctx* ctx, const float* in, int ld_in, float* out, int ld_out, int rows, int cols);
 
