@@ -19,6 +19,8 @@
 // and triu outputs skip tiles below the diagonal.
 #include <cuda.h>
 
+#include <vector>
+
 #include "gemm_tc.cuh"
 
 namespace psgd {
@@ -42,18 +44,29 @@ struct Cfg {
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
+// One launch covers up to kMaxGroup problems of identical shape and flags ("batched launch over all layers"): a tile
+// index decodes to (problem, tile); only pointers and tensor maps differ per problem.
+constexpr int kMaxGroup = 24;
+
+struct GroupMaps {
+  CUtensorMap a0[kMaxGroup], b0[kMaxGroup], a1[kMaxGroup], b1[kMaxGroup];
+};
+
 struct Params {
   int M, N;
   int K[2];                 // K of product 0 and of the (subtracted) product 1; K[1] == 0 when absent
   int a_mn[2], b_mn[2];     // 1: operand is MN-major in memory (op = transpose of the row-major array)
   int a_tri, b_tri;         // K-range hints for product 0: 0 none, 1 op(A)/op(B) upper triangular, 2 lower
-  float* C; int ldc;
+  int ldc, ldd;
   int triu;
-  float* maxabs;
-  const float* D; int ldd;
-  const float* mu_max; float step, tiny;
-  const float* colscale; int colscale_recip, colscale_sq;
-  int tiles_m, tiles_n;
+  float step, tiny;
+  int colscale_recip, colscale_sq;
+  int tiles_m, tiles_n, count;
+  float* C[kMaxGroup];
+  float* maxabs[kMaxGroup];
+  const float* D[kMaxGroup];
+  const float* mu_max[kMaxGroup];
+  const float* colscale[kMaxGroup];
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -165,8 +178,7 @@ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n
 
 template <int BN>
 __global__ void __launch_bounds__(kThreads, 1)
-    gemm_tc_kernel(const __grid_constant__ CUtensorMap tmA0, const __grid_constant__ CUtensorMap tmB0,
-                   const __grid_constant__ CUtensorMap tmA1, const __grid_constant__ CUtensorMap tmB1, const Params p) {
+    gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ Params p) {
   using C = Cfg<BN>;
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
@@ -199,7 +211,8 @@ __global__ void __launch_bounds__(kThreads, 1)
   tc_fence_after();
   const uint32_t tmem_base = *tmem_ptr;
 
-  const int num_tiles = p.tiles_m * p.tiles_n;
+  const int tiles_per = p.tiles_m * p.tiles_n;
+  const int num_tiles = tiles_per * p.count;
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
   // stage layout: [A hi | B hi | A lo | B lo]
@@ -209,15 +222,16 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int grp = tile / tiles_per, lt = tile % tiles_per;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int m0 = tm * BM, n0 = tn * BN;
         if (p.triu && m0 >= n0 + BN) continue;
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
           k_range<BN>(p, prod, m0, n0, kb0, kb1);
-          const CUtensorMap* ma = prod ? &tmA1 : &tmA0;
-          const CUtensorMap* mb = prod ? &tmB1 : &tmB0;
+          const CUtensorMap* ma = prod ? &maps.a1[grp] : &maps.a0[grp];
+          const CUtensorMap* mb = prod ? &maps.b1[grp] : &maps.b0[grp];
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
             const int s = it % C::kStages;
             const uint32_t ph = (it / C::kStages) & 1;
@@ -248,7 +262,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     if (lane == 0) {
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+        const int grp = tile / tiles_per, lt = tile % tiles_per;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int m0 = tm * BM, n0 = tn * BN;
         if (p.triu && m0 >= n0 + BN) continue;
         int total_kb = 0;
@@ -314,7 +329,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int st = threadIdx.x - kSplitWarp0 * 32;            // 0..127
     int it = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int grp = tile / tiles_per, lt = tile % tiles_per;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
       if (p.triu && m0 >= n0 + BN) continue;
       for (int prod = 0; prod < 2; ++prod) {
@@ -348,12 +364,25 @@ __global__ void __launch_bounds__(kThreads, 1)
     const int q = warp & 3;                                   // TMEM lane quarter this warp may access
     int tcount = 0;
     float mx = 0.f;
-    float mu = 0.f;
-    if (p.D) mu = p.mu_max ? p.step / (*p.mu_max + p.tiny) : 1.0f;
+    int mx_grp = -1;
+    auto flush_max = [&]() {
+      if (mx_grp >= 0 && p.maxabs[mx_grp]) {
+        const float w = warp_max(mx);
+        if (lane == 0 && w > 0.f) atomic_max_nonneg(p.maxabs[mx_grp], w);
+      }
+      mx = 0.f;
+    };
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-      const int tm = tile / p.tiles_n, tn = tile % p.tiles_n;
+      const int grp = tile / tiles_per, lt = tile % tiles_per;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
       const int m = m0 + q * 32 + lane;
+      if (grp != mx_grp) { flush_max(); mx_grp = grp; }
+      float* const Cg = p.C[grp];
+      const float* const Dg = p.D[grp];
+      const float* const csg = p.colscale[grp];
+      float mu = 0.f;
+      if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
       int total_kb = 0;
       if (!(p.triu && m0 >= n0 + BN)) {
         for (int prod = 0; prod < 2; ++prod) {
@@ -388,15 +417,15 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int c = 0; c < BN / 32; ++c) {
           const int nbase = n0 + c * 32;
           if (nbase >= p.N) continue;
-          float* crow = p.C + (size_t)m * p.ldc + nbase;
-          const float* drow = p.D ? p.D + (size_t)m * p.ldd + nbase : nullptr;
+          float* crow = Cg + (size_t)m * p.ldc + nbase;
+          const float* drow = Dg ? Dg + (size_t)m * p.ldd + nbase : nullptr;
           float v[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const int n = nbase + j;
             float x = racc[c * 32 + j];
-            if (p.colscale && n < p.N) {
-              float sc = p.colscale[n];
+            if (csg && n < p.N) {
+              float sc = csg[n];
               if (p.colscale_sq) sc = sc * sc;
               x = p.colscale_recip ? x * (1.0f / sc) : x * sc;
             }
@@ -405,7 +434,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             if (n < p.N) mx = fmaxf(mx, fabsf(x));
             v[j] = x;
           }
-          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(p.C) & 15) == 0) {
+          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0) {
 #pragma unroll
             for (int j = 0; j < 8; ++j)
               reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
@@ -417,10 +446,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         }
       }
     }
-    if (p.maxabs) {
-      mx = warp_max(mx);
-      if (lane == 0 && mx > 0.f) atomic_max_nonneg(p.maxabs, mx);
-    }
+    flush_max();
   }
 
   tc_fence_before();
@@ -473,10 +499,22 @@ bool gemm_tc_supported(const la::Gemm& g) {
   return true;
 }
 
+static bool same_shape(const la::Gemm& x, const la::Gemm& y) {
+  return x.M == y.M && x.N == y.N && x.K == y.K && x.K2 == y.K2 && x.lda == y.lda && x.ldb == y.ldb && x.lda2 == y.lda2 &&
+         x.ldb2 == y.ldb2 && x.ldc == y.ldc && x.ldd == y.ldd && x.ta == y.ta && x.tb == y.tb && x.ta2 == y.ta2 &&
+         x.tb2 == y.tb2 && x.triu == y.triu && x.a_tri == y.a_tri && x.b_tri == y.b_tri && x.step == y.step &&
+         x.tiny == y.tiny && x.colscale_recip == y.colscale_recip && x.colscale_sq == y.colscale_sq &&
+         (x.D != nullptr) == (y.D != nullptr) && (x.K2 > 0) == (y.K2 > 0);
+}
+
+// gs[0..count): identical shapes/flags, count <= kMaxGroup
 template <int BN>
-static int launch(psgd_ctx* ctx, const la::Gemm& g) {
+static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   using C = Cfg<BN>;
-  Params p{};
+  const la::Gemm& g = gs[0];
+  static thread_local Params p;            // large by-value kernel parameters: keep them off the stack
+  static thread_local GroupMaps maps;
+  p = Params{};
   p.M = g.M; p.N = g.N;
   p.K[0] = g.K; p.K[1] = g.K2;
   // op(A) is [M,K]: !ta -> A stored [M,K] (K-major); ta -> A stored [K,M] (MN-major)
@@ -486,23 +524,30 @@ static int launch(psgd_ctx* ctx, const la::Gemm& g) {
   p.a_mn[1] = g.ta2 ? 1 : 0;
   p.b_mn[1] = g.tb2 ? 0 : 1;
   p.a_tri = g.a_tri; p.b_tri = g.b_tri;
-  p.C = g.C; p.ldc = g.ldc; p.triu = g.triu ? 1 : 0; p.maxabs = g.maxabs;
-  p.D = g.D; p.ldd = g.ldd; p.mu_max = g.mu_max; p.step = g.step; p.tiny = g.tiny;
-  p.colscale = g.colscale; p.colscale_recip = g.colscale_recip; p.colscale_sq = g.colscale_sq;
+  p.ldc = g.ldc; p.ldd = g.ldd; p.triu = g.triu ? 1 : 0;
+  p.step = g.step; p.tiny = g.tiny;
+  p.colscale_recip = g.colscale_recip; p.colscale_sq = g.colscale_sq;
   p.tiles_m = (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
-
-  CUtensorMap tA[2], tB[2];
-  for (int prod = 0; prod < 2; ++prod) {
-    const float* A = prod ? g.A2 : g.A;
-    const float* B = prod ? g.B2 : g.B;
-    const int lda = prod ? g.lda2 : g.lda, ldb = prod ? g.ldb2 : g.ldb;
-    const int K = prod ? g.K2 : g.K;
-    if (K <= 0) { tA[prod] = tA[0]; tB[prod] = tB[0]; continue; }
-    if (!p.a_mn[prod]) PSGD_RETURN_IF(make_map(&tA[prod], A, g.M, K, lda, BM, false));     // [M,K], box {32k, 128m}
-    else               PSGD_RETURN_IF(make_map(&tA[prod], A, K, g.M, lda, BK, true));     // [K,M], box {32m, 32k}
-    if (!p.b_mn[prod]) PSGD_RETURN_IF(make_map(&tB[prod], B, g.N, K, ldb, BN, false));     // [N,K], box {32k, BN n}
-    else               PSGD_RETURN_IF(make_map(&tB[prod], B, K, g.N, ldb, BK, true));     // [K,N], box {32n, 32k}
+  p.count = count;
+  double work = 0.0;
+  for (int i = 0; i < count; ++i) {
+    const la::Gemm& q = gs[i];
+    p.C[i] = q.C; p.maxabs[i] = q.maxabs; p.D[i] = q.D; p.mu_max[i] = q.mu_max; p.colscale[i] = q.colscale;
+    work += 2.0 * q.M * q.N * ((double)q.K + q.K2);
+    for (int prod = 0; prod < 2; ++prod) {
+      const float* A = prod ? q.A2 : q.A;
+      const float* B = prod ? q.B2 : q.B;
+      const int lda = prod ? q.lda2 : q.lda, ldb = prod ? q.ldb2 : q.ldb;
+      const int K = prod ? q.K2 : q.K;
+      CUtensorMap* ta = prod ? &maps.a1[i] : &maps.a0[i];
+      CUtensorMap* tb = prod ? &maps.b1[i] : &maps.b0[i];
+      if (K <= 0) continue;
+      if (!p.a_mn[prod]) PSGD_RETURN_IF(make_map(ta, A, q.M, K, lda, BM, false));     // [M,K], box {32k, 128m}
+      else               PSGD_RETURN_IF(make_map(ta, A, K, q.M, lda, BK, true));      // [K,M], box {32m, 32k}
+      if (!p.b_mn[prod]) PSGD_RETURN_IF(make_map(tb, B, q.N, K, ldb, BN, false));     // [N,K], box {32k, BN n}
+      else               PSGD_RETURN_IF(make_map(tb, B, K, q.N, ldb, BK, true));      // [K,N], box {32n, 32k}
+    }
   }
   auto kern = gemm_tc_kernel<BN>;
   static bool attr_done = false;
@@ -510,10 +555,10 @@ static int launch(psgd_ctx* ctx, const la::Gemm& g) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     attr_done = true;
   }
-  int grid = p.tiles_m * p.tiles_n;
+  int grid = p.tiles_m * p.tiles_n * count;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
-  ProfScope prof(ctx, PSGD_K_GEMM, 2.0 * g.M * g.N * ((double)g.K + g.K2));
-  kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(tA[0], tB[0], tA[1], tB[1], p);
+  ProfScope prof(ctx, PSGD_K_GEMM, work);
+  kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(maps, p);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -522,80 +567,200 @@ int gemm_tc(psgd_ctx* ctx, const la::Gemm& g) {
   PSGD_REQUIRE(gemm_tc_supported(g), PSGD_ERR_BAD_SHAPE,
                "tcgen05 GEMM needs 16-byte aligned operands with leading dimensions that are multiples of 4");
   if (g.M <= 0 || g.N <= 0) return PSGD_OK;
-  return launch<128>(ctx, g);
+  return launch<128>(ctx, &g, 1);
+}
+
+static bool want_tc(const psgd_ctx* ctx, const la::Gemm& g) {
+  const bool big = g.M >= 256 && g.N >= 256 && g.K >= 256;
+  return gemm_tc_supported(g) && (ctx->opt_gemm_path == 2 || (ctx->opt_gemm_path == 0 && big));
+}
+
+// Same GEMM for many layers.  Problems that are tensor-core eligible and share shape/flags with their neighbours go out
+// as grouped launches; everything else runs one by one.
+int gemm_many(psgd_ctx* ctx, const la::Gemm* gs, int count, bool force_tc) {
+  int i = 0;
+  while (i < count) {
+    const bool tcok = gemm_tc_supported(gs[i]) && (force_tc || want_tc(ctx, gs[i]));
+    if (!tcok) {
+      PSGD_RETURN_IF(gemm_auto(ctx, gs[i]));
+      ++i;
+      continue;
+    }
+    int j = i + 1;
+    while (j < count && j - i < kMaxGroup && same_shape(gs[i], gs[j]) && gemm_tc_supported(gs[j])) ++j;
+    if (gs[i].M > 0 && gs[i].N > 0) PSGD_RETURN_IF(launch<128>(ctx, gs + i, j - i));
+    i = j;
+  }
+  return PSGD_OK;
 }
 
 int gemm_auto(psgd_ctx* ctx, const la::Gemm& g) {
-  const bool big = g.M >= 256 && g.N >= 256 && g.K >= 256;
-  const bool use_tc = gemm_tc_supported(g) && (ctx->opt_gemm_path == 2 || (ctx->opt_gemm_path == 0 && big));
-  if (use_tc) return gemm_tc(ctx, g);
+  if (want_tc(ctx, g)) return gemm_tc(ctx, g);
   ProfScope prof(ctx, PSGD_K_GEMM_SIMT, 2.0 * g.M * g.N * ((double)g.K + g.K2));
   return la::gemm_simt(ctx, g);
 }
 
 // ---------------------------------------------------------------------------------------------
-// triangular solves: recursive blocking.  The two half-size solves recurse down to kTrsmBase-wide diagonal blocks
-// (SIMT substitution, one launch per block); everything off the diagonal is one large tcgen05 GEMM per level, so
-// ~95 % of the m*n^2 multiply-adds run on the tensor cores.   Replaces tf.linalg.triangular_solve (psgd.py:174, :233,
-// :298) for large factors.
+// triangular solves: recursive blocking, grouped over layers.  Replaces tf.linalg.triangular_solve (psgd.py:174,
+// :233, :298) for large factors.  The two half-size solves recurse down to kTrsmBase-wide diagonal blocks; a diagonal
+// block is applied as a GEMM with its explicit inverse (computed once per solve by a small SIMT kernel, the approach
+// of blocked BLAS TRSMs), and everything off the diagonal is one large tcgen05 GEMM per recursion level, so every
+// multiply-add of the solve runs on the tensor cores and every step is ONE launch for the whole group of layers.
 // ---------------------------------------------------------------------------------------------
 constexpr int kTrsmBase = 128;
+
+size_t trsm_scratch_floats(int n) { return (size_t)((n + kTrsmBase - 1) / kTrsmBase) * kTrsmBase * kTrsmBase; }
+
+// Z_b = inv(Q[b0:b0+jb, b0:b0+jb]) for every diagonal block b (only the upper triangle of Q is read); grid = blocks.
+__global__ void __launch_bounds__(kTrsmBase) tri_inv_blocks_kernel(const float* __restrict__ Q, int ldq, int n,
+                                                                   float* __restrict__ Z) {
+  extern __shared__ float sm[];
+  float (*T)[kTrsmBase + 1] = reinterpret_cast<float (*)[kTrsmBase + 1]>(sm);
+  float (*Zs)[kTrsmBase + 1] = reinterpret_cast<float (*)[kTrsmBase + 1]>(sm + kTrsmBase * (kTrsmBase + 1));
+  const int b0 = blockIdx.x * kTrsmBase;
+  const int jb = min(kTrsmBase, n - b0);
+  const int j = threadIdx.x;
+  for (int i = 0; i < kTrsmBase; ++i) {
+    T[i][j] = (i < jb && j < jb && i <= j) ? Q[(size_t)(b0 + i) * ldq + b0 + j] : (i == j ? 1.f : 0.f);
+    Zs[i][j] = 0.f;
+  }
+  __syncthreads();
+  if (j < jb) {
+    // column j of the inverse by back substitution, rows i = j .. 0 (each thread only reads its own column of Zs)
+    Zs[j][j] = 1.0f / T[j][j];
+    for (int i = j - 1; i >= 0; --i) {
+      float s = 0.f;
+      for (int k = i + 1; k <= j; ++k) s = fmaf(T[i][k], Zs[k][j], s);
+      Zs[i][j] = -s / T[i][i];
+    }
+  }
+  __syncthreads();
+  float* Zb = Z + (size_t)blockIdx.x * kTrsmBase * kTrsmBase;
+  for (int i = 0; i < kTrsmBase; ++i) Zb[(size_t)i * kTrsmBase + j] = Zs[i][j];
+}
+
+static int invert_diag_blocks(psgd_ctx* ctx, const float* Q, int ldq, int n, float* Z) {
+  const int blocks = (n + kTrsmBase - 1) / kTrsmBase;
+  const size_t smem = 2 * (size_t)kTrsmBase * (kTrsmBase + 1) * sizeof(float);
+  static bool attr_done = false;
+  if (!attr_done) {
+    PSGD_CUDA_CHECK(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    attr_done = true;
+  }
+  ProfScope prof(ctx, PSGD_K_TRSM, (double)n * kTrsmBase * kTrsmBase / 3.0);
+  tri_inv_blocks_kernel<<<blocks, kTrsmBase, smem, ctx->stream>>>(Q, ldq, n, Z);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
 
 static int split_point(int lo, int hi) {
   const int half = (hi - lo) / 2;
   return lo + ((half + kTrsmBase - 1) / kTrsmBase) * kTrsmBase;
 }
 
-// X[:, j0:j1] (in place) <- X[:, j0:j1] Q[j0:j1, j0:j1]^-1
-static int trsm_right_rec(psgd_ctx* ctx, const float* Q, int ldq, float* X, int ldx, int m, int j0, int j1) {
-  if (j1 - j0 <= kTrsmBase) return la::trsm_right_block(ctx, Q, ldq, X, ldx, X, ldx, m, j0, j1);
+// X[:, j0:j1] (in place) <- X[:, j0:j1] Q[j0:j1, j0:j1]^-1      for every problem of the group
+static int trsm_right_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int j0, int j1) {
+  std::vector<la::Gemm> gs(count);
+  if (j1 - j0 <= kTrsmBase) {
+    const int jb = j1 - j0;
+    for (int t = 0; t < count; ++t) {       // in place is safe: one column tile, each CTA reads and writes its own rows
+      la::Gemm& g = gs[t];
+      g = la::Gemm{};
+      g.M = m; g.N = jb; g.K = jb;
+      g.A = ts[t].X + j0; g.lda = ldx;
+      g.B = ts[t].zinv + (size_t)(j0 / kTrsmBase) * kTrsmBase * kTrsmBase; g.ldb = kTrsmBase;
+      g.C = ts[t].X + j0; g.ldc = ldx;
+      g.b_tri = 1;
+    }
+    return gemm_many(ctx, gs.data(), count, true);
+  }
   const int mid = split_point(j0, j1);
-  PSGD_RETURN_IF(trsm_right_rec(ctx, Q, ldq, X, ldx, m, j0, mid));
-  la::Gemm g;                                   // X[:, mid:j1] -= X[:, j0:mid] Q[j0:mid, mid:j1]
-  g.M = m; g.N = j1 - mid; g.K = mid - j0;
-  g.A = X + j0; g.lda = ldx;
-  g.B = Q + (size_t)j0 * ldq + mid; g.ldb = ldq;
-  g.C = X + mid; g.ldc = ldx; g.D = X + mid; g.ldd = ldx;
-  PSGD_RETURN_IF(gemm_tc(ctx, g));
-  return trsm_right_rec(ctx, Q, ldq, X, ldx, m, mid, j1);
+  PSGD_RETURN_IF(trsm_right_rec(ctx, ts, count, ldq, ldx, m, j0, mid));
+  for (int t = 0; t < count; ++t) {         // X[:, mid:j1] -= X[:, j0:mid] Q[j0:mid, mid:j1]
+    la::Gemm& g = gs[t];
+    g = la::Gemm{};
+    g.M = m; g.N = j1 - mid; g.K = mid - j0;
+    g.A = ts[t].X + j0; g.lda = ldx;
+    g.B = ts[t].Q + (size_t)j0 * ldq + mid; g.ldb = ldq;
+    g.C = ts[t].X + mid; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
+  }
+  PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
+  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, mid, j1);
 }
 
 // X[i0:i1, :] (in place) <- Q[i0:i1, i0:i1]^-T X[i0:i1, :]
-static int trsm_left_rec(psgd_ctx* ctx, const float* Q, int ldq, float* X, int ldx, int m, int i0, int i1) {
-  if (i1 - i0 <= kTrsmBase) return la::trsm_left_block(ctx, Q, ldq, X, ldx, X, ldx, m, i0, i1);
+static int trsm_left_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int i0, int i1) {
+  std::vector<la::Gemm> gs(count);
+  if (i1 - i0 <= kTrsmBase) {
+    const int ib = i1 - i0;
+    for (int t = 0; t < count; ++t) {       // in place is safe: one row tile, each CTA reads and writes its own columns
+      la::Gemm& g = gs[t];
+      g = la::Gemm{};
+      g.M = ib; g.N = m; g.K = ib;
+      g.A = ts[t].zinv + (size_t)(i0 / kTrsmBase) * kTrsmBase * kTrsmBase; g.lda = kTrsmBase; g.ta = true;
+      g.B = ts[t].X + (size_t)i0 * ldx; g.ldb = ldx;
+      g.C = ts[t].X + (size_t)i0 * ldx; g.ldc = ldx;
+      g.a_tri = 2;
+    }
+    return gemm_many(ctx, gs.data(), count, true);
+  }
   const int mid = split_point(i0, i1);
-  PSGD_RETURN_IF(trsm_left_rec(ctx, Q, ldq, X, ldx, m, i0, mid));
-  la::Gemm g;                                   // X[mid:i1, :] -= Q[i0:mid, mid:i1]^T X[i0:mid, :]
-  g.M = i1 - mid; g.N = m; g.K = mid - i0;
-  g.A = Q + (size_t)i0 * ldq + mid; g.lda = ldq; g.ta = true;
-  g.B = X + (size_t)i0 * ldx; g.ldb = ldx;
-  g.C = X + (size_t)mid * ldx; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
-  PSGD_RETURN_IF(gemm_tc(ctx, g));
-  return trsm_left_rec(ctx, Q, ldq, X, ldx, m, mid, i1);
+  PSGD_RETURN_IF(trsm_left_rec(ctx, ts, count, ldq, ldx, m, i0, mid));
+  for (int t = 0; t < count; ++t) {         // X[mid:i1, :] -= Q[i0:mid, mid:i1]^T X[i0:mid, :]
+    la::Gemm& g = gs[t];
+    g = la::Gemm{};
+    g.M = i1 - mid; g.N = m; g.K = mid - i0;
+    g.A = ts[t].Q + (size_t)i0 * ldq + mid; g.lda = ldq; g.ta = true;
+    g.B = ts[t].X + (size_t)i0 * ldx; g.ldb = ldx;
+    g.C = ts[t].X + (size_t)mid * ldx; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
+  }
+  PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
+  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, mid, i1);
 }
 
-static bool trsm_tc_ok(psgd_ctx* ctx, const float* Q, int ldq, const float* X, int ldx, int n, int m) {
+static bool trsm_tc_ok(const psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int n, int m) {
   if (ctx->opt_gemm_path == 1) return false;
   const bool big = n >= 512 && m >= 256;
   if (!(ctx->opt_gemm_path == 2 || big)) return false;
-  return n > kTrsmBase && aligned16(Q) && aligned16(X) && (ldq % 4) == 0 && (ldx % 4) == 0;
+  if (n <= kTrsmBase || (ldq % 4) != 0 || (ldx % 4) != 0) return false;
+  for (int t = 0; t < count; ++t)
+    if (!aligned16(ts[t].Q) || !aligned16(ts[t].X) || !ts[t].zinv) return false;
+  return true;
 }
 
-int trsm_right_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int n) {
-  if (!trsm_tc_ok(ctx, Q, ldq, X, ldx, n, m)) return la::trsm_right_upper(ctx, Q, ldq, B, ldb, X, ldx, m, n);
-  if (X != B)
-    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 4, B, (size_t)ldb * 4, (size_t)n * 4, m, cudaMemcpyDeviceToDevice,
-                                      ctx->stream));
-  return trsm_right_rec(ctx, Q, ldq, X, ldx, m, 0, n);
+// X = B Q^-1 : Q [n,n] upper, B,X [m,n]
+int trsm_right_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, int ldx, int m, int n) {
+  if (count <= 0) return PSGD_OK;
+  if (!trsm_tc_ok(ctx, ts, count, ldq, ldx, n, m)) {
+    for (int t = 0; t < count; ++t)
+      PSGD_RETURN_IF(la::trsm_right_upper(ctx, ts[t].Q, ldq, ts[t].B, ldb, ts[t].X, ldx, m, n));
+    return PSGD_OK;
+  }
+  for (int t = 0; t < count; ++t) {
+    if (ts[t].X != ts[t].B)
+      PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].X, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)n * 4, m,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    PSGD_RETURN_IF(invert_diag_blocks(ctx, ts[t].Q, ldq, n, ts[t].zinv));
+  }
+  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, 0, n);
 }
-int trsm_left_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int n, int m) {
-  if (!trsm_tc_ok(ctx, Q, ldq, X, ldx, n, m)) return la::trsm_left_upper_adjoint(ctx, Q, ldq, B, ldb, X, ldx, n, m);
-  if (X != B)
-    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(X, (size_t)ldx * 4, B, (size_t)ldb * 4, (size_t)m * 4, n, cudaMemcpyDeviceToDevice,
-                                      ctx->stream));
-  return trsm_left_rec(ctx, Q, ldq, X, ldx, m, 0, n);
+
+// X = Q^-T B : Q [n,n] upper, B,X [n,m]
+int trsm_left_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, int ldx, int n, int m) {
+  if (count <= 0) return PSGD_OK;
+  if (!trsm_tc_ok(ctx, ts, count, ldq, ldx, n, m)) {
+    for (int t = 0; t < count; ++t)
+      PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, ts[t].Q, ldq, ts[t].B, ldb, ts[t].X, ldx, n, m));
+    return PSGD_OK;
+  }
+  for (int t = 0; t < count; ++t) {
+    if (ts[t].X != ts[t].B)
+      PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].X, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)m * 4, n,
+                                        cudaMemcpyDeviceToDevice, ctx->stream));
+    PSGD_RETURN_IF(invert_diag_blocks(ctx, ts[t].Q, ldq, n, ts[t].zinv));
+  }
+  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, 0, n);
 }
-size_t extra_ws_bytes(int64_t, int64_t) { return 0; }
 
 }  // namespace tc
 }  // namespace psgd

@@ -13,10 +13,24 @@ int gemm_auto(psgd_ctx* ctx, const la::Gemm& g);
 // tcgen05 engine directly; operands must be 16-byte aligned with leading dimensions that are multiples of 4
 bool gemm_tc_supported(const la::Gemm& g);
 int gemm_tc(psgd_ctx* ctx, const la::Gemm& g);
-int trsm_right_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int n);
-int trsm_left_auto(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int n, int m);
-// extra workspace (bytes) the tensor-core engine may carve for hi/lo operand planes of an [M,N] layer
-size_t extra_ws_bytes(int64_t M, int64_t N);
+// The same GEMM for many layers: tensor-core eligible problems that share shape/flags go out as grouped launches
+// (one kernel for up to 24 problems); the rest run one by one through gemm_auto.  force_tc: use the tensor-core
+// engine whenever the operands allow it, regardless of size (TRSM recursion).
+int gemm_many(psgd_ctx* ctx, const la::Gemm* gs, int count, bool force_tc);
+
+// Grouped triangular solves.  zinv: per-problem scratch of trsm_scratch_floats(n) floats (inverses of the diagonal
+// blocks); B may alias X.
+struct Trsm {
+  const float* Q;
+  const float* B;
+  float* X;
+  float* zinv;
+};
+size_t trsm_scratch_floats(int n);
+// X = B Q^-1 : Q [n,n] upper, B,X [m,n]
+int trsm_right_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, int ldx, int m, int n);
+// X = Q^-T B : Q [n,n] upper, B,X [n,m]   (tf.linalg.triangular_solve(Q, B, lower=False, adjoint=True))
+int trsm_left_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, int ldx, int n, int m);
 
 }  // namespace tc
 }  // namespace psgd

@@ -251,253 +251,311 @@ static size_t col_partial_floats(int M, int N) {
   return (size_t)((M + kColChunkRows - 1) / kColChunkRows) * 2 * N;
 }
 
+constexpr int kUpper = 1, kLower = 2;
+
 // Dense Kron/Cholesky factors are upper triangular by construction (identity-initialised and only ever updated as
 // Q - triu(.) Q), which lets the tensor-core engine skip structurally zero K blocks.  The hints
 // are dropped with psgd_set_option(ctx, "assume_triangular", 0) for callers that feed arbitrary square matrices.
-static int gemm(psgd_ctx* ctx, la::Gemm g, int a_tri = 0, int b_tri = 0) {
-  if (ctx->opt_assume_tri) { g.a_tri = a_tri; g.b_tri = b_tri; }
-  return tc::gemm_auto(ctx, g);
-}
-constexpr int kUpper = 1, kLower = 2;
-
-// triu(X X^T - Y Y^T) (rows) or triu(X^T X - Y^T Y) (cols) with max|.| -> *mx
-static int gram_diff(psgd_ctx* ctx, const float* X, const float* Y, int M, int N, bool rows, float* out, float* mx) {
-  la::Gemm g;
-  if (rows) { g.M = M; g.N = M; g.K = N; g.ta = false; g.tb = true; }
-  else      { g.M = N; g.N = N; g.K = M; g.ta = true;  g.tb = false; }
-  g.A = X; g.lda = N; g.B = X; g.ldb = N;
-  g.K2 = g.K; g.A2 = Y; g.lda2 = N; g.ta2 = g.ta; g.B2 = Y; g.ldb2 = N; g.tb2 = g.tb;
-  g.C = out; g.ldc = g.N; g.triu = true; g.maxabs = mx;
-  return gemm(ctx, g);
-}
-
-// Qout = Q - step/(max+tiny) * grad * Q                            psgd.py:179
-static int factor_step(psgd_ctx* ctx, const float* grad, const float* Q, int n, const float* mx, float step,
-                       float tiny, float* Qout) {
-  la::Gemm g;
-  g.M = n; g.N = n; g.K = n; g.A = grad; g.lda = n; g.B = Q; g.ldb = n;
-  g.C = Qout; g.ldc = n; g.D = Q; g.ldd = n; g.mu_max = mx; g.step = step; g.tiny = tiny;
-  return gemm(ctx, g, kUpper, kUpper);
-}
-
-static int balance(psgd_ctx* ctx, int kl, const float* Ql, int M, int kr, const float* Qr, int N, Scal* sc,
-                   float* Qlb, float* Qrb) {
-  balance_kernel<<<1, 256, 0, ctx->stream>>>(kl, Ql, M, kr, Qr, N, sc);
-  PSGD_LAUNCH_CHECK(ctx);
-  const int64_t cl = kl == PSGD_FACTOR_DENSE ? (int64_t)M * M : (kl == PSGD_FACTOR_NORM ? 2 * (int64_t)M : M);
-  const int64_t cr = kr == PSGD_FACTOR_DENSE ? (int64_t)N * N : (kr == PSGD_FACTOR_NORM ? 2 * (int64_t)N : N);
-  rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, ctx->stream>>>(Ql, Qlb, cl, sc, 1);
-  PSGD_LAUNCH_CHECK(ctx);
-  rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, ctx->stream>>>(Qr, Qrb, cr, sc, 0);
-  PSGD_LAUNCH_CHECK(ctx);
-  return PSGD_OK;
+// All layers of a group share shapes, so each op of the reference's sequence is ONE (grouped) launch over the group.
+static int gemm_all(psgd_ctx* ctx, std::vector<la::Gemm>& gs, int a_tri = 0, int b_tri = 0) {
+  if (ctx->opt_assume_tri)
+    for (auto& g : gs) { g.a_tri = a_tri; g.b_tri = b_tri; }
+  return tc::gemm_many(ctx, gs.data(), (int)gs.size(), false);
 }
 
 static size_t fsize(int kind, int64_t n) {
   return kind == PSGD_FACTOR_DENSE ? (size_t)n * n : (kind == PSGD_FACTOR_NORM ? 2 * (size_t)n : (size_t)n);
 }
 
+// One layer in canonical orientation ((D,D), (N,D), (D,S), (N,S)); mirrored formats arrive here transposed/swapped.
+struct Layer {
+  const float *Ql, *Qr, *dX, *dG, *G;
+  float *Ql_out, *Qr_out, *out;
+  // scratch
+  Scal* sc;
+  float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv;
+  float *t1, *t2, *t3, *P, *addlast;
+};
+
+static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
+                   int ldc) {
+  la::Gemm g;
+  g.M = M; g.N = N; g.K = K; g.A = A; g.lda = lda; g.ta = ta; g.B = B; g.ldb = ldb; g.tb = tb; g.C = C; g.ldc = ldc;
+  return g;
+}
+
 // ---------------------------------------------------------------------------------------------
-// canonical updates (left kind, right kind) in {(D,D), (N,D), (D,S), (N,S)}
+// canonical update of a group of same-shape layers
 // ---------------------------------------------------------------------------------------------
-static int update_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* dX,
-                            const float* dG, float* Ql_out, float* Qr_out, int M, int N, float step, float tiny,
-                            WsCarver& c) {
+static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
   const size_t MN = (size_t)M * N;
-  Scal* sc = c.take<Scal>(1);
-  float* Qlb = c.take<float>(fsize(kl, M));
-  float* Qrb = c.take<float>(fsize(kr, N));
-  float* A = c.take<float>(MN);
-  float* Bt = c.take<float>(MN);
-  PSGD_RETURN_IF(balance(ctx, kl, Ql, M, kr, Qr, N, sc, Qlb, Qrb));
+  size_t f = 64 + fsize(kl, M) + fsize(kr, N) + 3 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
+             2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
+  f += tc::trsm_scratch_floats((int)M) + tc::trsm_scratch_floats((int)N);
+  return f;
+}
+
+static void carve_update(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
+  const size_t MN = (size_t)M * N;
+  L.sc = c.take<Scal>(1);
+  L.Qlb = c.take<float>(fsize(kl, M));
+  L.Qrb = c.take<float>(fsize(kr, N));
+  L.A = c.take<float>(MN);
+  L.Bt = c.take<float>(MN);
+  L.T1 = c.take<float>(MN);
+  L.cvec = c.take<float>(N);
+  L.part = c.take<float>(col_partial_floats(M, N));
+  L.grad1 = kl == PSGD_FACTOR_DENSE ? c.take<float>((size_t)M * M) : nullptr;
+  L.grad2 = kr == PSGD_FACTOR_DENSE ? c.take<float>((size_t)N * N) : nullptr;
+  L.g1d = c.take<float>(M);
+  L.g1b = c.take<float>(M);
+  L.sa = c.take<float>(N);
+  L.sb = c.take<float>(N);
+  L.gvec = c.take<float>(N);
+  L.zinv = c.take<float>(tc::trsm_scratch_floats(M > N ? M : N));
+}
+
+static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, int M, int N, float step, float tiny) {
+  const size_t MN = (size_t)M * N;
   cudaStream_t st = ctx->stream;
+  std::vector<la::Gemm> gs;
+  std::vector<tc::Trsm> ts;
+  const int64_t cl = (int64_t)fsize(kl, M), cr = (int64_t)fsize(kr, N);
+
+  // ---- balance: Ql /= rho, Qr *= rho                          psgd.py:166-170, :211-215, :288-292, :342-346
+  for (auto& L : Ls) {
+    balance_kernel<<<1, 256, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, L.sc);
+    PSGD_LAUNCH_CHECK(ctx);
+    rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, st>>>(L.Ql, L.Qlb, cl, L.sc, 1);
+    PSGD_LAUNCH_CHECK(ctx);
+    rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, st>>>(L.Qr, L.Qrb, cr, L.sc, 0);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
 
   // ---- A = Ql dG Qr^T  and  Bt = Ql^-T dX Qr^-1 ------------------------------------------------
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
-    float* T1 = c.take<float>(MN);
-    la::Gemm g1;                                                           // T1 = dG Qr^T     psgd.py:173
-    g1.M = M; g1.N = N; g1.K = N; g1.A = dG; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = T1; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
-    la::Gemm g2;                                                           // A = Ql T1
-    g2.M = M; g2.N = N; g2.K = M; g2.A = Qlb; g2.lda = M; g2.B = T1; g2.ldb = N; g2.C = A; g2.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g2, kUpper, 0));
-    PSGD_RETURN_IF(tc::trsm_right_auto(ctx, Qrb, N, dX, N, T1, N, M, N));          // W = dX Qr^-1   psgd.py:174
-    PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, T1, N, Bt, N, M, N));           // Bt = Ql^-T W
+    gs.clear();                                                          // T1 = dG Qr^T            psgd.py:173
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.dG, N, false, L.Qrb, N, true, L.T1, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    gs.clear();                                                          // A = Ql T1
+    for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Qlb, M, false, L.T1, N, false, L.A, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    ts.clear();                                                          // W = dX Qr^-1            psgd.py:174
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.T1, L.zinv});
+    PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
+    ts.clear();                                                          // Bt = Ql^-T W
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.T1, L.Bt, L.zinv});
+    PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
   } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
-    float* T1 = c.take<float>(MN);
-    float* cvec = c.take<float>(N);
-    float* part = c.take<float>(col_partial_floats(M, N));
-    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dG, T1, M, N, nullptr, 0);     // :218-219
-    PSGD_LAUNCH_CHECK(ctx);
-    la::Gemm g1;                                                           // A = (Ql dG) Qr^T  psgd.py:220
-    g1.M = M; g1.N = N; g1.K = N; g1.A = T1; g1.lda = N; g1.B = Qrb; g1.ldb = N; g1.tb = true; g1.C = A; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
-    PSGD_RETURN_IF(col_reduce(ctx, 0, Qlb, dX, nullptr, M, N, part, cvec, nullptr));
-    norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dX, cvec, T1, M, N, nullptr); // :230-232
-    PSGD_LAUNCH_CHECK(ctx);
-    PSGD_RETURN_IF(tc::trsm_right_auto(ctx, Qrb, N, T1, N, Bt, N, M, N));                            // :233
+    for (auto& L : Ls) {
+      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dG, L.T1, M, N, nullptr, 0);   // :218-219
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    gs.clear();                                                          // A = (Ql dG) Qr^T        psgd.py:220
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.T1, N, false, L.Qrb, N, true, L.A, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    for (auto& L : Ls) {
+      PSGD_RETURN_IF(col_reduce(ctx, 0, L.Qlb, L.dX, nullptr, M, N, L.part, L.cvec, nullptr));
+      norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dX, L.cvec, L.T1, M, N, nullptr);   // :230-232
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    ts.clear();                                                          // Bt = (.) Qr^-1          psgd.py:233
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.T1, L.Bt, L.zinv});
+    PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
   } else if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {
-    la::Gemm g1;                                                           // A = (Ql dG) * qr  psgd.py:295-296
-    g1.M = M; g1.N = N; g1.K = M; g1.A = Qlb; g1.lda = M; g1.B = dG; g1.ldb = N; g1.C = A; g1.ldc = N;
-    g1.colscale = Qrb;
-    PSGD_RETURN_IF(gemm(ctx, g1, kUpper, 0));
-    PSGD_RETURN_IF(tc::trsm_left_auto(ctx, Qlb, M, dX, N, Bt, N, M, N));                             // :298
-    col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Bt, Qrb, M, N);                   // :299
-    PSGD_LAUNCH_CHECK(ctx);
-  } else {  // (NORM, SCALE)
-    float* cvec = c.take<float>(N);
-    float* part = c.take<float>(col_partial_floats(M, N));
-    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dG, A, M, N, Qrb, 1);          // :349-351
-    PSGD_LAUNCH_CHECK(ctx);
-    PSGD_RETURN_IF(col_reduce(ctx, 0, Qlb, dX, nullptr, M, N, part, cvec, nullptr));
-    norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Qlb, dX, cvec, Bt, M, N, Qrb);    // :353-356
-    PSGD_LAUNCH_CHECK(ctx);
+    gs.clear();                                                          // A = (Ql dG) * qr        psgd.py:295-296
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, N, M, L.Qlb, M, false, L.dG, N, false, L.A, N);
+      g.colscale = L.Qrb;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    ts.clear();                                                          // Bt = Ql^-T dX           psgd.py:298
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv});
+    PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
+    for (auto& L : Ls) {
+      col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Bt, L.Qrb, M, N);                  // :299
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+  } else {  // (NORM, SCALE): no dense factor at all
+    for (auto& L : Ls) {
+      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dG, L.A, M, N, L.Qrb, 1);     // :349-351
+      PSGD_LAUNCH_CHECK(ctx);
+      PSGD_RETURN_IF(col_reduce(ctx, 0, L.Qlb, L.dX, nullptr, M, N, L.part, L.cvec, nullptr));
+      norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dX, L.cvec, L.Bt, M, N, L.Qrb);   // :353-356
+      PSGD_LAUNCH_CHECK(ctx);
+    }
   }
 
   // ---- left factor -----------------------------------------------------------------------------
   if (kl == PSGD_FACTOR_DENSE) {
-    float* grad1 = c.take<float>((size_t)M * M);
-    PSGD_RETURN_IF(gram_diff(ctx, A, Bt, M, N, true, grad1, &sc->max1));                // psgd.py:175 / :301
-    PSGD_RETURN_IF(factor_step(ctx, grad1, Qlb, M, &sc->max1, step, tiny, Ql_out));     // psgd.py:177, :179
+    gs.clear();                                                          // grad1 = triu(A A^T - Bt Bt^T)   psgd.py:175
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, M, N, L.A, N, false, L.A, N, true, L.grad1, M);
+      g.K2 = N; g.A2 = L.Bt; g.lda2 = N; g.ta2 = false; g.B2 = L.Bt; g.ldb2 = N; g.tb2 = true;
+      g.triu = true; g.maxabs = &L.sc->max1;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs));
+    gs.clear();                                                          // Ql' = Ql - step1 grad1 Ql       psgd.py:177, :179
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, M, M, L.grad1, M, false, L.Qlb, M, false, L.Ql_out, M);
+      g.D = L.Qlb; g.ldd = M; g.mu_max = &L.sc->max1; g.step = step; g.tiny = tiny;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper));
   } else {
-    float* g1d = c.take<float>(M);
-    float* g1b = c.take<float>(M);
-    int rows_grid = M < ctx->num_sms * 8 ? M : ctx->num_sms * 8;
-    row_stats_kernel<<<rows_grid, 128, 0, st>>>(A, Bt, M, N, g1d, g1b, sc);             // psgd.py:235-239
-    PSGD_LAUNCH_CHECK(ctx);
-    norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(Qlb, g1d, g1b, Ql_out, M, step, tiny, sc);   // :240-241
-    PSGD_LAUNCH_CHECK(ctx);
+    const int rows_grid = M < ctx->num_sms * 8 ? M : ctx->num_sms * 8;
+    for (auto& L : Ls) {
+      row_stats_kernel<<<rows_grid, 128, 0, st>>>(L.A, L.Bt, M, N, L.g1d, L.g1b, L.sc);                  // :235-239
+      PSGD_LAUNCH_CHECK(ctx);
+      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :240-241
+      PSGD_LAUNCH_CHECK(ctx);
+    }
   }
   // ---- right factor ----------------------------------------------------------------------------
   if (kr == PSGD_FACTOR_DENSE) {
-    float* grad2 = c.take<float>((size_t)N * N);
-    PSGD_RETURN_IF(gram_diff(ctx, A, Bt, M, N, false, grad2, &sc->max2));               // psgd.py:176 / :243
-    PSGD_RETURN_IF(factor_step(ctx, grad2, Qrb, N, &sc->max2, step, tiny, Qr_out));
+    gs.clear();                                                          // grad2 = triu(A^T A - Bt^T Bt)   psgd.py:176
+    for (auto& L : Ls) {
+      la::Gemm g = mk(N, N, M, L.A, N, true, L.A, N, false, L.grad2, N);
+      g.K2 = M; g.A2 = L.Bt; g.lda2 = N; g.ta2 = true; g.B2 = L.Bt; g.ldb2 = N; g.tb2 = false;
+      g.triu = true; g.maxabs = &L.sc->max2;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs));
+    gs.clear();                                                          // Qr' = Qr - step2 grad2 Qr       psgd.py:178-179
+    for (auto& L : Ls) {
+      la::Gemm g = mk(N, N, N, L.grad2, N, false, L.Qrb, N, false, L.Qr_out, N);
+      g.D = L.Qrb; g.ldd = N; g.mu_max = &L.sc->max2; g.step = step; g.tiny = tiny;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper));
   } else {
-    float* sa = c.take<float>(N);
-    float* sb = c.take<float>(N);
-    float* grad2 = c.take<float>(N);
-    float* part = c.take<float>(col_partial_floats(M, N));
-    PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, A, Bt, M, N, part, sa, sb));             // psgd.py:304 / :366
-    scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(sa, sb, N, grad2, sc);
-    PSGD_LAUNCH_CHECK(ctx);
-    scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(Qrb, grad2, Qr_out, N, step, tiny, sc);     // :307
-    PSGD_LAUNCH_CHECK(ctx);
+    for (auto& L : Ls) {
+      PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, L.A, L.Bt, M, N, L.part, L.sa, L.sb));                  // :304 / :366
+      scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.sa, L.sb, N, L.gvec, L.sc);
+      PSGD_LAUNCH_CHECK(ctx);
+      scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);   // :307
+      PSGD_LAUNCH_CHECK(ctx);
+    }
   }
   return PSGD_OK;
 }
 
-static size_t update_ws_bytes(int kl, int kr, int64_t M, int64_t N) {
+// ---------------------------------------------------------------------------------------------
+// canonical apply of a group of same-shape layers
+// ---------------------------------------------------------------------------------------------
+static size_t apply_ws_floats(int64_t M, int64_t N) {
   const size_t MN = (size_t)M * N;
-  size_t f = fsize(kl, M) + fsize(kr, N) + 3 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
-             2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */;
-  return f * sizeof(float) + 64 * 256 + tc::extra_ws_bytes(M, N);
+  return 64 * 64 + 5 * MN + (size_t)M * M + (size_t)N * N + 4 * (size_t)(M + N) + col_partial_floats((int)M, (int)N);
 }
 
-// ---------------------------------------------------------------------------------------------
-// canonical applies
-// ---------------------------------------------------------------------------------------------
-// P = X (Qr^T Qr) with the reference's association switch           psgd.py:189-192, :260-263
-static int right_dense_apply(psgd_ctx* ctx, const float* X, const float* Qr, int M, int N, float* tmp_nn,
-                             float* tmp_mn, float* out) {
+static void carve_apply(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
+  const size_t MN = (size_t)M * N;
+  L.t1 = c.take<float>(MN);
+  L.t2 = c.take<float>(MN);
+  L.t3 = c.take<float>(MN);
+  const size_t side = (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) ? (size_t)(M < N ? M : N) * (M < N ? M : N)
+                      : (kl == PSGD_FACTOR_DENSE ? (size_t)M * M : (kr == PSGD_FACTOR_DENSE ? (size_t)N * N : 0));
+  L.P = c.take<float>(side ? side : 1);
+  L.addlast = c.take<float>(N);
+  L.part = c.take<float>(col_partial_floats(M, N));
+}
+
+// out = X (Qr^T Qr) with the reference's association switch          psgd.py:189-192, :260-263
+static int right_dense_apply(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N, bool from_t1, bool to_out) {
+  std::vector<la::Gemm> gs;
+  auto X = [&](Layer& L) { return from_t1 ? L.t1 : L.G; };
+  auto O = [&](Layer& L) { return to_out ? L.out : L.t2; };
   if (M < N) {
-    la::Gemm g1; g1.M = M; g1.N = N; g1.K = N; g1.A = X; g1.lda = N; g1.B = Qr; g1.ldb = N; g1.tb = true;
-    g1.C = tmp_mn; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1, 0, kLower));
-    la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = tmp_mn; g2.lda = N; g2.B = Qr; g2.ldb = N; g2.C = out; g2.ldc = N;
-    return gemm(ctx, g2, 0, kUpper);
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, X(L), N, false, L.Qr, N, true, L.t3, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    gs.clear();
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t3, N, false, L.Qr, N, false, O(L), N));
+    return gemm_all(ctx, gs, 0, kUpper);
   }
-  la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
-  g1.C = tmp_nn; g1.ldc = N;
-  PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
-  la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = X; g2.lda = N; g2.B = tmp_nn; g2.ldb = N; g2.C = out; g2.ldc = N;
-  return gemm(ctx, g2);
+  for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));
+  PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+  gs.clear();
+  for (auto& L : Ls) gs.push_back(mk(M, N, N, X(L), N, false, L.P, N, false, O(L), N));
+  return gemm_all(ctx, gs);
 }
 
-// P = (Ql^T Ql) X with the reference's association switch           psgd.py:318-321
-static int left_dense_apply(psgd_ctx* ctx, const float* Ql, const float* X, int M, int N, float* tmp_mm,
-                            float* tmp_mn, float* out, const float* colscale_sq) {
-  if (M < N) {
-    la::Gemm g1; g1.M = M; g1.N = M; g1.K = M; g1.A = Ql; g1.lda = M; g1.ta = true; g1.B = Ql; g1.ldb = M;
-    g1.C = tmp_mm; g1.ldc = M;
-    PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
-    la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = tmp_mm; g2.lda = M; g2.B = X; g2.ldb = N; g2.C = out; g2.ldc = N;
-    g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
-    return gemm(ctx, g2);
-  }
-  la::Gemm g1; g1.M = M; g1.N = N; g1.K = M; g1.A = Ql; g1.lda = M; g1.B = X; g1.ldb = N; g1.C = tmp_mn; g1.ldc = N;
-  PSGD_RETURN_IF(gemm(ctx, g1, kUpper, 0));
-  la::Gemm g2; g2.M = M; g2.N = N; g2.K = M; g2.A = Ql; g2.lda = M; g2.ta = true; g2.B = tmp_mn; g2.ldb = N;
-  g2.C = out; g2.ldc = N;
-  g2.colscale = colscale_sq; g2.colscale_sq = colscale_sq != nullptr;
-  return gemm(ctx, g2, kLower, 0);
-}
-
-static int apply_canonical(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* G,
-                           float* out, int M, int N, WsCarver& c) {
+static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, int M, int N) {
   const size_t MN = (size_t)M * N;
   cudaStream_t st = ctx->stream;
+  std::vector<la::Gemm> gs;
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
-    float* t1 = c.take<float>(MN);
-    float* t2 = c.take<float>(MN);
     if (M < N) {                                                          // psgd.py:190
-      float* P = c.take<float>((size_t)M * M);
-      PSGD_RETURN_IF(left_dense_apply(ctx, Ql, G, M, N, P, nullptr, t1, nullptr));      // (Ql^T Ql) G
-      la::Gemm g3; g3.M = M; g3.N = N; g3.K = N; g3.A = t1; g3.lda = N; g3.B = Qr; g3.ldb = N; g3.tb = true;
-      g3.C = t2; g3.ldc = N;
-      PSGD_RETURN_IF(gemm(ctx, g3, 0, kLower));
-      la::Gemm g4; g4.M = M; g4.N = N; g4.K = N; g4.A = t2; g4.lda = N; g4.B = Qr; g4.ldb = N; g4.C = out; g4.ldc = N;
-      return gemm(ctx, g4, 0, kUpper);
+      for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, M, L.P, M, false, L.G, N, false, L.t1, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t1, N, false, L.Qr, N, true, L.t2, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t2, N, false, L.Qr, N, false, L.out, N));
+      return gemm_all(ctx, gs, 0, kUpper);
     }
-    float* P = c.take<float>((size_t)N * N);                              // psgd.py:192
-    la::Gemm g1; g1.M = N; g1.N = N; g1.K = N; g1.A = Qr; g1.lda = N; g1.ta = true; g1.B = Qr; g1.ldb = N;
-    g1.C = P; g1.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g1, kLower, kUpper));
-    la::Gemm g2; g2.M = M; g2.N = N; g2.K = N; g2.A = G; g2.lda = N; g2.B = P; g2.ldb = N; g2.C = t1; g2.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g2));
-    la::Gemm g3; g3.M = M; g3.N = N; g3.K = M; g3.A = Ql; g3.lda = M; g3.B = t1; g3.ldb = N; g3.C = t2; g3.ldc = N;
-    PSGD_RETURN_IF(gemm(ctx, g3, kUpper, 0));
-    la::Gemm g4; g4.M = M; g4.N = N; g4.K = M; g4.A = Ql; g4.lda = M; g4.ta = true; g4.B = t2; g4.ldb = N;
-    g4.C = out; g4.ldc = N;
-    return gemm(ctx, g4, kLower, 0);
+    for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));       // psgd.py:192
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+    gs.clear();
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.P, N, false, L.t1, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs));
+    gs.clear();
+    for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.t1, N, false, L.t2, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    gs.clear();
+    for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t2, N, false, L.out, N));
+    return gemm_all(ctx, gs, kLower, 0);
   }
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
-    float* P = c.take<float>((size_t)M * M);
-    float* t1 = c.take<float>(MN);
-    return left_dense_apply(ctx, Ql, G, M, N, P, t1, out, Qr);
+    if (M < N) {
+      for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+      gs.clear();
+      for (auto& L : Ls) {
+        la::Gemm g = mk(M, N, M, L.P, M, false, L.G, N, false, L.out, N);
+        g.colscale = L.Qr; g.colscale_sq = true;
+        gs.push_back(g);
+      }
+      return gemm_all(ctx, gs);
+    }
+    for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.G, N, false, L.t1, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    gs.clear();
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, N, M, L.Ql, M, true, L.t1, N, false, L.out, N);
+      g.colscale = L.Qr; g.colscale_sq = true;
+      gs.push_back(g);
+    }
+    return gemm_all(ctx, gs, kLower, 0);
   }
   // normalization-format left factor                                      psgd.py:258-270, :383-391
-  float* t1 = c.take<float>(MN);
-  float* t2 = c.take<float>(MN);
-  float* addlast = c.take<float>(N);
-  float* part = c.take<float>(col_partial_floats(M, N));
-  const float* P = nullptr;
   if (kr == PSGD_FACTOR_DENSE) {
-    float* tnn = c.take<float>((size_t)N * N);
-    float* t3 = c.take<float>(MN);
-    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, G, t1, M, N, nullptr, 0);
-    PSGD_LAUNCH_CHECK(ctx);
-    PSGD_RETURN_IF(right_dense_apply(ctx, t1, Qr, M, N, tnn, t3, t2));
-    P = t2;
+    for (auto& L : Ls) {
+      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.G, L.t1, M, N, nullptr, 0);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    PSGD_RETURN_IF(right_dense_apply(ctx, Ls, M, N, true, false));        // -> t2
   } else {
-    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, G, t1, M, N, Qr, 2);
-    PSGD_LAUNCH_CHECK(ctx);
-    P = t1;
+    for (auto& L : Ls) {
+      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.G, L.t2, M, N, L.Qr, 2);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
   }
-  PSGD_RETURN_IF(col_reduce(ctx, 1, Ql, P, nullptr, M, N, part, addlast, nullptr));     // psgd.py:265 / :386
-  norm_left_out_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(Ql, P, addlast, out, M, N);
-  PSGD_LAUNCH_CHECK(ctx);
+  for (auto& L : Ls) {
+    PSGD_RETURN_IF(col_reduce(ctx, 1, L.Ql, L.t2, nullptr, M, N, L.part, L.addlast, nullptr));   // psgd.py:265 / :386
+    norm_left_out_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.t2, L.addlast, L.out, M, N);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
   return PSGD_OK;
 }
 
-static size_t apply_ws_bytes(int64_t M, int64_t N) {
-  const size_t MN = (size_t)M * N;
-  size_t f = 5 * MN + (size_t)M * M + (size_t)N * N + 4 * (size_t)(M + N) + col_partial_floats((int)M, (int)N);
-  return f * sizeof(float) + 64 * 256 + tc::extra_ws_bytes(M, N);
-}
-
 // ---------------------------------------------------------------------------------------------
-// dispatch with the reference's mirroring                              psgd.py:82-110, :124-152
+// dispatch with the reference's mirroring, grouping of same-shape layers     psgd.py:82-110, :124-152
 // ---------------------------------------------------------------------------------------------
 static bool is_canonical(int kl, int kr) {
   return (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) || (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) ||
@@ -505,40 +563,106 @@ static bool is_canonical(int kl, int kr) {
 }
 static bool is_mirrored(int kl, int kr) { return is_canonical(kr, kl) && !is_canonical(kl, kr); }
 
-int update_layer(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* dX, const float* dG,
-                 float* Ql_out, float* Qr_out, int64_t M, int64_t N, float step, float tiny, WsCarver& c) {
-  if (is_canonical(kl, kr))
-    return update_canonical(ctx, kl, kr, Ql, Qr, dX, dG, Ql_out, Qr_out, (int)M, (int)N, step, tiny, c);
-  if (is_mirrored(kl, kr)) {
-    // (dense,norm) / (scale,dense) / (scale,norm): run the canonical kernel on (Qr, Ql, dX^T, dG^T)
-    float* dXt = c.take<float>((size_t)M * N);
-    float* dGt = c.take<float>((size_t)M * N);
-    PSGD_RETURN_IF(la::transpose(ctx, dX, (int)N, dXt, (int)M, (int)M, (int)N));
-    PSGD_RETURN_IF(la::transpose(ctx, dG, (int)N, dGt, (int)M, (int)M, (int)N));
-    return update_canonical(ctx, kr, kl, Qr, Ql, dXt, dGt, Qr_out, Ql_out, (int)N, (int)M, step, tiny, c);
-  }
-  set_error("Unknown Kronecker product preconditioner (left kind %d, right kind %d)", kl, kr);
-  return PSGD_ERR_UNSUPPORTED;
-}
-
-int apply_layer(psgd_ctx* ctx, int kl, int kr, const float* Ql, const float* Qr, const float* G, float* out,
-                int64_t M, int64_t N, WsCarver& c) {
-  if (is_canonical(kl, kr)) return apply_canonical(ctx, kl, kr, Ql, Qr, G, out, (int)M, (int)N, c);
-  if (is_mirrored(kl, kr)) {
-    float* Gt = c.take<float>((size_t)M * N);
-    float* Ot = c.take<float>((size_t)M * N);
-    PSGD_RETURN_IF(la::transpose(ctx, G, (int)N, Gt, (int)M, (int)M, (int)N));
-    PSGD_RETURN_IF(apply_canonical(ctx, kr, kl, Qr, Ql, Gt, Ot, (int)N, (int)M, c));
-    return la::transpose(ctx, Ot, (int)M, out, (int)N, (int)N, (int)M);
-  }
-  set_error("Unknown Kronecker product preconditioner (left kind %d, right kind %d)", kl, kr);
-  return PSGD_ERR_UNSUPPORTED;
-}
-
 static int check_layer(const char* what, int kl, int kr, int64_t M, int64_t N) {
   PSGD_REQUIRE(M >= 1 && N >= 1 && M < (1LL << 30) && N < (1LL << 30), PSGD_ERR_BAD_SHAPE, "%s: bad shape [%lld,%lld]",
                what, (long long)M, (long long)N);
   PSGD_REQUIRE(kl >= 0 && kl <= 2 && kr >= 0 && kr <= 2, PSGD_ERR_BAD_SHAPE, "%s: bad factor kinds %d,%d", what, kl, kr);
+  PSGD_REQUIRE(is_canonical(kl, kr) || is_mirrored(kl, kr), PSGD_ERR_UNSUPPORTED,
+               "Unknown Kronecker product preconditioner (left kind %d, right kind %d)", kl, kr);
+  return PSGD_OK;
+}
+
+struct Key { int kl, kr, M, N; };
+
+// Runs update (is_update) or apply over a ragged list of layers.  Mirrored formats ((dense,norm), (scale,dense),
+// (scale,norm)) are brought to canonical orientation by transposing dX,dG / G into scratch and swapping the factors
+// (exactly what the reference does, psgd.py:86, :102, :104, :128, :144, :146); layers with equal canonical
+// (kinds, shape) then run as one group so every GEMM/TRSM of the op sequence is a single grouped launch.
+static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool is_update, float step, float tiny) {
+  if (count == 0) return PSGD_OK;
+  size_t need = 0;
+  for (int i = 0; i < count; ++i) {
+    const psgd_kron_layer& q = in[i];
+    PSGD_RETURN_IF(check_layer(is_update ? "kron update" : "kron apply", q.kind_l, q.kind_r, q.M, q.N));
+    if (is_update)
+      PSGD_REQUIRE(q.Ql && q.Qr && q.dX && q.dG && q.Ql_out && q.Qr_out, PSGD_ERR_BAD_POINTER,
+                   "kron update: null device pointer in layer %d", i);
+    else
+      PSGD_REQUIRE(q.Ql && q.Qr && q.G && q.out, PSGD_ERR_BAD_POINTER, "kron apply: null device pointer in layer %d", i);
+    const size_t f = is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N) : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N;
+    need += f * sizeof(float) + 48 * 256;
+  }
+  // Bound the workspace: process the list in slices whose scratch fits the budget (large uniform stacks still group)
+  const size_t budget = (size_t)48 << 30;
+  int begin = 0;
+  while (begin < count) {
+    size_t bytes = 0;
+    int end = begin;
+    while (end < count) {
+      const psgd_kron_layer& q = in[end];
+      const size_t f = (is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N)
+                                  : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N) * sizeof(float) + 48 * 256;
+      if (end > begin && bytes + f > budget) break;
+      bytes += f;
+      ++end;
+    }
+    PSGD_RETURN_IF(ctx->reserve(bytes));
+    WsCarver c(ctx->ws);
+    std::vector<Layer> Ls(end - begin);
+    std::vector<Key> keys(end - begin);
+    std::vector<float*> untranspose_src(end - begin, nullptr);
+    for (int i = begin; i < end; ++i) {
+      const psgd_kron_layer& q = in[i];
+      Layer& L = Ls[i - begin];
+      L = Layer{};
+      int kl = q.kind_l, kr = q.kind_r, M = (int)q.M, N = (int)q.N;
+      if (is_canonical(kl, kr)) {
+        L.Ql = q.Ql; L.Qr = q.Qr; L.dX = q.dX; L.dG = q.dG; L.G = q.G;
+        L.Ql_out = q.Ql_out; L.Qr_out = q.Qr_out; L.out = q.out;
+      } else {
+        // canonical kernel on (Qr, Ql, X^T); results come back swapped / transposed
+        const size_t MN = (size_t)M * N;
+        L.Ql = q.Qr; L.Qr = q.Ql; L.Ql_out = q.Qr_out; L.Qr_out = q.Ql_out;
+        if (is_update) {
+          float* dXt = c.take<float>(MN);
+          float* dGt = c.take<float>(MN);
+          PSGD_RETURN_IF(la::transpose(ctx, q.dX, N, dXt, M, M, N));
+          PSGD_RETURN_IF(la::transpose(ctx, q.dG, N, dGt, M, M, N));
+          L.dX = dXt; L.dG = dGt;
+        } else {
+          float* Gt = c.take<float>(MN);
+          float* Ot = c.take<float>(MN);
+          PSGD_RETURN_IF(la::transpose(ctx, q.G, N, Gt, M, M, N));
+          L.G = Gt; L.out = Ot;
+          untranspose_src[i - begin] = Ot;
+        }
+        std::swap(kl, kr);
+        std::swap(M, N);
+      }
+      keys[i - begin] = Key{kl, kr, M, N};
+      if (is_update) carve_update(c, L, kl, kr, M, N);
+      else carve_apply(c, L, kl, kr, M, N);
+    }
+    // group equal keys (stable)
+    std::vector<char> done(end - begin, 0);
+    for (int i = 0; i < end - begin; ++i) {
+      if (done[i]) continue;
+      std::vector<Layer> grp;
+      std::vector<int> idx;
+      for (int j = i; j < end - begin; ++j)
+        if (!done[j] && keys[j].kl == keys[i].kl && keys[j].kr == keys[i].kr && keys[j].M == keys[i].M && keys[j].N == keys[i].N) {
+          grp.push_back(Ls[j]); idx.push_back(j); done[j] = 1;
+        }
+      if (is_update) PSGD_RETURN_IF(update_group(ctx, keys[i].kl, keys[i].kr, grp, keys[i].M, keys[i].N, step, tiny));
+      else PSGD_RETURN_IF(apply_group(ctx, keys[i].kl, keys[i].kr, grp, keys[i].M, keys[i].N));
+    }
+    if (!is_update)
+      for (int i = begin; i < end; ++i)
+        if (untranspose_src[i - begin])   // canonical result is [N,M]; give the caller [M,N]
+          PSGD_RETURN_IF(la::transpose(ctx, untranspose_src[i - begin], (int)in[i].M, in[i].out, (int)in[i].N, (int)in[i].N, (int)in[i].M));
+    begin = end;
+  }
+  (void)need;
   return PSGD_OK;
 }
 
@@ -551,71 +675,38 @@ extern "C" int psgd_kron_update(psgd_ctx* ctx, int kind_l, int kind_r, const flo
                                 const float* dX, const float* dG, float* Ql_out, float* Qr_out, int64_t M, int64_t N,
                                 float step, float tiny) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
-  PSGD_RETURN_IF(kron::check_layer("kron update", kind_l, kind_r, M, N));
-  PSGD_REQUIRE(Ql && Qr && dX && dG && Ql_out && Qr_out, PSGD_ERR_BAD_POINTER, "kron update: null device pointer");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  PSGD_RETURN_IF(ctx->reserve(kron::update_ws_bytes(kind_l, kind_r, M, N)));
-  WsCarver c(ctx->ws);
-  return kron::update_layer(ctx, kind_l, kind_r, Ql, Qr, dX, dG, Ql_out, Qr_out, M, N, step, tiny, c);
+  psgd_kron_layer L{};
+  L.kind_l = kind_l; L.kind_r = kind_r; L.M = M; L.N = N;
+  L.Ql = Ql; L.Qr = Qr; L.dX = dX; L.dG = dG; L.Ql_out = Ql_out; L.Qr_out = Qr_out;
+  return kron::run_layers(ctx, &L, 1, true, step, tiny);
 }
 
 extern "C" int psgd_kron_apply(psgd_ctx* ctx, int kind_l, int kind_r, const float* Ql, const float* Qr,
                                const float* G, float* out, int64_t M, int64_t N) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
-  PSGD_RETURN_IF(kron::check_layer("kron apply", kind_l, kind_r, M, N));
-  PSGD_REQUIRE(Ql && Qr && G && out, PSGD_ERR_BAD_POINTER, "kron apply: null device pointer");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  PSGD_RETURN_IF(ctx->reserve(kron::apply_ws_bytes(M, N)));
-  WsCarver c(ctx->ws);
-  return kron::apply_layer(ctx, kind_l, kind_r, Ql, Qr, G, out, M, N, c);
+  psgd_kron_layer L{};
+  L.kind_l = kind_l; L.kind_r = kind_r; L.M = M; L.N = N;
+  L.Ql = Ql; L.Qr = Qr; L.G = G; L.out = out;
+  return kron::run_layers(ctx, &L, 1, false, 0.f, 0.f);
 }
 
-// Ragged list of layers on one stream.  Layers are independent (mnist_with_lenet5.py:51-53), so they share
-// one workspace sized for the largest layer and run back to back; launch latency of small layers is hidden
-// by the caller capturing the call into a CUDA graph (see psgd_tf_b200.KronBatch).
+// A ragged list of layers on one stream.  Layers are independent (mnist_with_lenet5.py:51-53); layers of equal format
+// and shape are processed as a group in which every GEMM / triangular-solve step is ONE launch over the whole group.
 extern "C" int psgd_kron_update_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count, float step,
                                         float tiny) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(count >= 0 && (layers || count == 0), PSGD_ERR_BAD_POINTER, "kron batched update: null layer list");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  size_t need = 0;
-  for (int i = 0; i < count; ++i) {
-    const psgd_kron_layer& L = layers[i];
-    PSGD_RETURN_IF(kron::check_layer("kron batched update", L.kind_l, L.kind_r, L.M, L.N));
-    PSGD_REQUIRE(L.Ql && L.Qr && L.dX && L.dG && L.Ql_out && L.Qr_out, PSGD_ERR_BAD_POINTER,
-                 "kron batched update: null device pointer in layer %d", i);
-    size_t b = kron::update_ws_bytes(L.kind_l, L.kind_r, L.M, L.N);
-    if (b > need) need = b;
-  }
-  PSGD_RETURN_IF(ctx->reserve(need));
-  for (int i = 0; i < count; ++i) {
-    const psgd_kron_layer& L = layers[i];
-    WsCarver c(ctx->ws);
-    PSGD_RETURN_IF(kron::update_layer(ctx, L.kind_l, L.kind_r, L.Ql, L.Qr, L.dX, L.dG, L.Ql_out, L.Qr_out, L.M, L.N,
-                                      step, tiny, c));
-  }
-  return PSGD_OK;
+  return kron::run_layers(ctx, layers, count, true, step, tiny);
 }
 
 extern "C" int psgd_kron_apply_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(count >= 0 && (layers || count == 0), PSGD_ERR_BAD_POINTER, "kron batched apply: null layer list");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  size_t need = 0;
-  for (int i = 0; i < count; ++i) {
-    const psgd_kron_layer& L = layers[i];
-    PSGD_RETURN_IF(kron::check_layer("kron batched apply", L.kind_l, L.kind_r, L.M, L.N));
-    PSGD_REQUIRE(L.Ql && L.Qr && L.G && L.out, PSGD_ERR_BAD_POINTER, "kron batched apply: null device pointer in layer %d", i);
-    size_t b = kron::apply_ws_bytes(L.M, L.N);
-    if (b > need) need = b;
-  }
-  PSGD_RETURN_IF(ctx->reserve(need));
-  for (int i = 0; i < count; ++i) {
-    const psgd_kron_layer& L = layers[i];
-    WsCarver c(ctx->ws);
-    PSGD_RETURN_IF(kron::apply_layer(ctx, L.kind_l, L.kind_r, L.Ql, L.Qr, L.G, L.out, L.M, L.N, c));
-  }
-  return PSGD_OK;
+  return kron::run_layers(ctx, layers, count, false, 0.f, 0.f);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -628,23 +719,25 @@ extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx,
   PSGD_REQUIRE(Q && dx && dg && Q_out, PSGD_ERR_BAD_POINTER, "dense update: null device pointer");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   const int n = (int)n64;
-  PSGD_RETURN_IF(ctx->reserve(((size_t)n * n + 4 * (size_t)n) * sizeof(float) + 16 * 256 + tc::extra_ws_bytes(n, n)));
+  PSGD_RETURN_IF(ctx->reserve(((size_t)n * n + 4 * (size_t)n) * sizeof(float) + 16 * 256));
   WsCarver c(ctx->ws);
   kron::Scal* sc = c.take<kron::Scal>(1);
   float* a = c.take<float>(n);
   float* b = c.take<float>(n);
   float* grad = c.take<float>((size_t)n * n);
   PSGD_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(kron::Scal), ctx->stream));
-  la::Gemm g1;                                                             // a = Q dg          psgd.py:38
-  g1.M = n; g1.N = 1; g1.K = n; g1.A = Q; g1.lda = n; g1.B = dg; g1.ldb = 1; g1.C = a; g1.ldc = 1;
+  la::Gemm g1 = kron::mk(n, 1, n, Q, n, false, dg, 1, false, a, 1);          // a = Q dg          psgd.py:38
   PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
-  PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx    psgd.py:39
-  la::Gemm g2;                                                             // triu(a a^T - b b^T)   psgd.py:40
-  g2.M = n; g2.N = n; g2.K = 1; g2.A = a; g2.lda = 1; g2.B = a; g2.ldb = 1; g2.tb = true;
+  PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx       psgd.py:39
+  la::Gemm g2 = kron::mk(n, n, 1, a, 1, false, a, 1, true, grad, n);          // triu(a a^T - b b^T)   psgd.py:40
   g2.K2 = 1; g2.A2 = b; g2.lda2 = 1; g2.B2 = b; g2.ldb2 = 1; g2.tb2 = true;
-  g2.C = grad; g2.ldc = n; g2.triu = true; g2.maxabs = &sc->max1;
+  g2.triu = true; g2.maxabs = &sc->max1;
   PSGD_RETURN_IF(la::gemm_simt(ctx, g2));
-  return kron::factor_step(ctx, grad, Q, n, &sc->max1, step, tiny, Q_out);   // psgd.py:41-42
+  std::vector<la::Gemm> gs;                                                   // Q - step0 grad Q  psgd.py:41-42
+  la::Gemm g3 = kron::mk(n, n, n, grad, n, false, Q, n, false, Q_out, n);
+  g3.D = Q; g3.ldd = n; g3.mu_max = &sc->max1; g3.step = step; g3.tiny = tiny;
+  gs.push_back(g3);
+  return kron::gemm_all(ctx, gs, kron::kUpper, kron::kUpper);
 }
 
 extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n64) {
@@ -655,10 +748,8 @@ extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, f
   const int n = (int)n64;
   PSGD_RETURN_IF(ctx->reserve((size_t)n * sizeof(float) + 1024));
   float* t = static_cast<float*>(ctx->ws);
-  la::Gemm g1;                                                             // t = Q g            psgd.py:55
-  g1.M = n; g1.N = 1; g1.K = n; g1.A = Q; g1.lda = n; g1.B = g; g1.ldb = 1; g1.C = t; g1.ldc = 1;
+  la::Gemm g1 = kron::mk(n, 1, n, Q, n, false, g, 1, false, t, 1);           // t = Q g            psgd.py:55
   PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
-  la::Gemm g2;                                                             // out = Q^T t
-  g2.M = n; g2.N = 1; g2.K = n; g2.A = Q; g2.lda = n; g2.ta = true; g2.B = t; g2.ldb = 1; g2.C = out; g2.ldc = 1;
+  la::Gemm g2 = kron::mk(n, 1, n, Q, n, true, t, 1, false, out, 1);          // out = Q^T t
   return la::gemm_simt(ctx, g2);
 }
