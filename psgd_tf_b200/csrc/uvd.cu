@@ -994,9 +994,10 @@ extern "C" int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, cons
                                int64_t n, int r, float step, float tiny, int balance, int update_U) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd update: bad sizes n=%lld r=%d", (long long)n, r);
-  if (n == 0) return PSGD_OK;
+  // an empty shard still takes part in the cross-rank reductions when a hook is installed
+  if (n == 0 && !ctx->allreduce) return PSGD_OK;
   const void* ptrs[] = {U, V, d, v, h};
-  PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
+  if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   return uvd::update(ctx, U, V, d, v, h, n, r, step, tiny, balance, update_U);
 }
@@ -1005,9 +1006,9 @@ extern "C" int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, con
                               float* out, int64_t n, int r) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd apply: bad sizes n=%lld r=%d", (long long)n, r);
-  if (n == 0) return PSGD_OK;
+  if (n == 0 && !ctx->allreduce) return PSGD_OK;
   const void* ptrs[] = {U, V, d, g, out};
-  PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
+  if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   return uvd::apply(ctx, U, V, d, g, out, n, r);
 }

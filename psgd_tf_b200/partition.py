@@ -103,11 +103,11 @@ def all_gather_layers(outs_local: Sequence[torch.Tensor], owned: List[List[int]]
         # uniform stack (24 x 4096^2): one all_gather_into_tensor of the stacked local results
         per = len(owned[0])
         local = torch.stack([full[li] for li in owned[rank]]) if per else torch.empty(0, device=dev)
-        gathered = torch.empty((len(owned),) + tuple(local.shape), device=dev, dtype=torch.float32)
-        dist.all_gather_into_tensor(gathered, local, group=group)
+        gathered = torch.empty((len(owned) * per,) + tuple(local.shape[1:]), device=dev, dtype=torch.float32)
+        dist.all_gather_into_tensor(gathered, local, group=group)          # rank k's layers land at rows [k*per, (k+1)*per)
         for k, layer_ids in enumerate(owned):
             for j, li in enumerate(layer_ids):
-                full[li] = gathered[k, j]
+                full[li] = gathered[k * per + j]
         return full
     works = []
     for k, layer_ids in enumerate(owned):

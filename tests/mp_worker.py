@@ -1,0 +1,152 @@
+"""Multi-process worker used by the distributed tests (launched with torch.distributed.run / mp.spawn).
+
+mode "cpu-protocol": gloo, no GPU -- checks the host-side sharding logic: chunk bounds tile the vector, the layer
+  assignment covers every layer once, ragged/uniform all-gathers return every layer on every rank, and the reduction
+  protocol of the chunk-sharded UVd update (what is summed, what is maxed) reproduces the unsharded oracle.
+mode "gpu-uvd" / "gpu-kron": nccl, one GPU per rank -- the real CUDA path with the all-reduce hook / layer sharding
+  against the oracle on the full problem.
+"""
+import os
+import sys
+
+import numpy as np
+import torch
+import torch.distributed as dist
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle import psgd_oracle as O          # noqa: E402
+from tests import cases                       # noqa: E402
+
+
+def cpu_protocol(rank, world):
+    from psgd_tf_b200 import partition
+    # ---- chunk bounds tile [0, n) -------------------------------------------------------------------
+    for n in (1, 255, 256, 1021, 100_003):
+        bounds = [partition.chunk_bounds(n, world, r) for r in range(world)]
+        assert bounds[0][0] == 0 and bounds[-1][1] == n
+        for a, b in zip(bounds, bounds[1:]):
+            assert a[1] == b[0] and (a[0] % 256 == 0 or a[0] == a[1])
+    (lo, hi), (mlo, mhi) = partition.mirrored_chunk_bounds(1001, world, rank)
+    assert (mlo, mhi) == (1001 - hi, 1001 - lo)
+    # ---- layer assignment + all-gather -----------------------------------------------------------------
+    shapes = cases.LENET_SHAPES
+    owned = partition.assign_layers([partition.kron_layer_cost(m, n) for m, n in shapes], world)
+    assert sorted(i for o in owned for i in o) == list(range(len(shapes)))
+    local = [torch.full(shapes[i], float(i)) for i in owned[rank]]
+    full = partition.all_gather_layers(local, owned, shapes, rank)
+    for i, t in enumerate(full):
+        assert tuple(t.shape) == shapes[i] and torch.all(t == float(i))
+    uni = [(8, 8)] * 4
+    owned_u = partition.assign_layers([1.0] * 4, world)
+    full = partition.all_gather_layers([torch.full((8, 8), float(i)) for i in owned_u[rank]], owned_u, uni, rank)
+    for i, t in enumerate(full):
+        assert torch.all(t == float(i))
+    # ---- reduction protocol of the sharded UVd update (mirrors psgd_tf_b200/csrc/uvd.cu) ------------------------
+    n, r = 1021, 4
+    c = cases.uvd_case(42, n, r)
+    lo, hi = partition.chunk_bounds(n, world, rank)
+    U, V, d, v, h = (c[k][lo:hi].astype(np.float64) for k in ("U", "V", "d", "v", "h"))
+    Z = np.concatenate([U, V], 1)
+    X = np.concatenate([d * h, v / d], 1)
+    G = torch.from_numpy(Z.T @ np.concatenate([Z, X], 1))
+    dist.all_reduce(G)                                                  # sweep 1: sums
+    G = G.numpy()
+    UtU, VtU, VtV = G[:r, :r], G[r:2 * r, :r], G[r:2 * r, r:2 * r]
+    p, Utdh, Utw, Vtw = G[r:2 * r, 2 * r], G[:r, 2 * r], G[:r, 2 * r + 1], G[r:2 * r, 2 * r + 1]
+    IpVtU = np.eye(r) + VtU
+    t = Utdh + UtU @ p
+    s1 = np.linalg.solve(IpVtU.T, Utw)
+    s2 = np.linalg.solve(IpVtU, Vtw - VtV @ s1)
+    Qh = (d * h)[:, 0] + U @ p
+    Ph = d[:, 0] * (Qh + V @ t)
+    b = (v / d)[:, 0] - V @ s1
+    invPv = (b - U @ s2) / d[:, 0]
+    nabla = Ph * h[:, 0] - v[:, 0] * invPv
+    mx = torch.tensor([np.abs(nabla).max() if hi > lo else 0.0], dtype=torch.float64)
+    dist.all_reduce(mx, op=dist.ReduceOp.MAX)                           # sweep 2: one max ...
+    sums = torch.from_numpy(np.concatenate([[Qh @ Qh, b @ b, Qh @ b], Qh @ V, b @ V]))
+    dist.all_reduce(sums)                                               # ... and 3 + 2r sums
+    sums = sums.numpy()
+    aa, bb, ab, atV, btV = sums[0], sums[1], sums[2], sums[3:3 + r], sums[3 + r:]
+    norm = np.sqrt(abs(aa * (atV @ VtV @ atV) + bb * (btV @ VtV @ btV) - 2 * ab * (atV @ VtV @ btV)))
+    tiny = float(O.TINY)
+    d_new = d[:, 0] - 0.01 / (mx.item() + tiny) * d[:, 0] * nabla
+    U_new = U - 0.01 / (norm + tiny) * (np.outer(Qh, atV @ IpVtU) - np.outer(b, btV @ IpVtU))
+    f64 = {k: c[k].astype(np.float64) for k in c}
+    Ur, Vr, dr = O.update_precond_UVd_math(f64["U"], f64["V"], f64["d"], f64["v"], f64["h"], 0.01, update_U=True)
+    np.testing.assert_allclose(U_new, Ur[lo:hi], rtol=1e-9, atol=1e-15)
+    np.testing.assert_allclose(d_new, dr[lo:hi, 0], rtol=1e-9)
+
+
+def gpu_uvd(rank, world):
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+    torch.cuda.set_device(rank)
+    ctx = psgd.get_context(rank)
+    partition.install_allreduce(ctx)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    for n, r in ((100_003, 10), (1021, 10), (5000, 16)):
+        c = cases.uvd_case(600 + n, n, r)
+        lo, hi = partition.chunk_bounds(n, world, rank)
+        for kw in (dict(update_U=True, balance=False), dict(update_U=False, balance=True)):
+            U, V, d = dev(c["U"][lo:hi]), dev(c["V"][lo:hi]), dev(c["d"][lo:hi])
+            psgd.update_precond_UVd_math_(U, V, d, dev(c["v"][lo:hi]), dev(c["h"][lo:hi]), 0.01, psgd._tiny, **kw)
+            pre = psgd.precond_grad_UVd_math(U, V, d, dev(c["g"][lo:hi]))
+            Ur, Vr, dr = O.update_precond_UVd_math(c["U"], c["V"], c["d"], c["v"], c["h"], 0.01, **kw)
+            pr = O.precond_grad_UVd_math(Ur, Vr, dr, c["g"])
+            for got, want in ((U, Ur), (V, Vr), (d, dr), (pre, pr)):
+                if hi > lo:
+                    e = np.linalg.norm(got.cpu().numpy().astype(np.float64) - want[lo:hi]) / np.linalg.norm(want)
+                    assert e < 1e-5, (n, r, kw, e)
+    # X-shape on mirrored chunk pairs, diagonal on plain chunks: only the max is exchanged
+    n = 20_001
+    c = cases.vec_case(7, n)
+    lo, hi = partition.chunk_bounds(n, world, rank)
+    q = dev(c["a"][lo:hi])
+    psgd.update_precond_diag(q, dev(c["v"][lo:hi]), dev(c["h"][lo:hi]), 0.01)
+    want = O.update_precond_diag(c["a"], c["v"], c["h"], 0.01)
+    assert np.allclose(q.cpu().numpy(), want[lo:hi], rtol=1e-5)
+    ctx.set_allreduce(None)
+
+
+def gpu_kron(rank, world):
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+    torch.cuda.set_device(rank)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    for shapes in (cases.LENET_SHAPES, [(512, 512)] * 4):
+        cs = [cases.kron_case(900 + i, "dense", "dense", M, N) for i, (M, N) in enumerate(shapes)]
+        owned = partition.assign_layers([partition.kron_layer_cost(M, N) for M, N in shapes], world)
+        mine = owned[rank]
+        new = psgd.update_precond_kron_batched([dev(cs[i]["Ql"]) for i in mine], [dev(cs[i]["Qr"]) for i in mine],
+                                               [dev(cs[i]["dX"]) for i in mine], [dev(cs[i]["dG"]) for i in mine], 0.01)
+        pre = psgd.precond_grad_kron_batched([a for a, _ in new], [b for _, b in new], [dev(cs[i]["G"]) for i in mine])
+        full = partition.all_gather_layers(pre, owned, shapes, rank)
+        for i, c in enumerate(cs):
+            ql, qr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
+            want = O.precond_grad_kron(ql, qr, c["G"])
+            e = cases.rel_err(full[i].cpu().numpy(), want)
+            assert e < 1e-5, (shapes[i], e)
+
+
+def main():
+    mode = sys.argv[1]
+    rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"])
+    os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+    if mode == "cpu-protocol":
+        dist.init_process_group("gloo")
+        cpu_protocol(rank, world)
+    else:
+        torch.cuda.set_device(rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
+        {"gpu-uvd": gpu_uvd, "gpu-kron": gpu_kron}[mode](rank, world)
+    dist.barrier()
+    dist.destroy_process_group()
+    if rank == 0:
+        print(f"MP_OK {mode} world={world}")
+
+
+if __name__ == "__main__":
+    main()
