@@ -6,8 +6,8 @@
 One "step" = one preconditioner update followed by one preconditioned-gradient apply on fresh synthetic
 (v, h, g) / (dX, dG, G), state carried across steps.
 
-Workloads
-  uvd  (default)  UVd rank-10 on a flattened 100M-parameter vector (BASELINE.json configs[3]); at N GPUs the vector
+Workloads (default "all": the UVd line is the headline JSON, the Kron stack result is nested under its "kron" key)
+  uvd             UVd rank-10 on a flattened 100M-parameter vector (BASELINE.json configs[3]); at N GPUs the vector
                   is sharded by contiguous chunk (strong scaling) with all-reduces of the r x r / r-length partials.
   kron            synthetic 24-layer 4096x4096 stack, dense-dense Kron update+apply (configs[2]), layers sharded.
 
@@ -364,6 +364,13 @@ def run_reference(args, rank, world):
     n_total, r = args.n, args.rank
     if args.workload == "kron":
         return run_reference_kron(args)
+    if args.workload == "all":
+        args.workload = "uvd"
+        out = run_reference(args, rank, world)
+        kr = run_reference_kron(args)
+        out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "config", "cpu_baseline", "e2e")}
+        args.workload = "all"
+        return out
     from oracle import psgd_oracle as O
     st = _uvd_host_state(200_000, r, n_total)
     t0 = time.perf_counter(); _oracle_uvd_step(O, st, 0); per_row = (time.perf_counter() - t0) / 200_000
@@ -427,7 +434,8 @@ def main():
     ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="uvd", choices=["uvd", "kron"])
+    ap.add_argument("--workload", default="all", choices=["all", "uvd", "kron"],
+                    help="all (default): UVd 100M is the headline line, the Kron stack result is nested under 'kron'")
     ap.add_argument("--n", type=int, default=100_000_000, help="UVd: parameters in the flattened vector")
     ap.add_argument("--rank", type=int, default=10)
     ap.add_argument("--layers", type=int, default=24)
@@ -456,11 +464,20 @@ def main():
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
-        if args.workload == "uvd":
+        out = None
+        if args.workload in ("uvd", "all"):
             out = run_uvd(args, rank, world, local)
-        else:
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+        if args.workload in ("kron", "all"):
             from bench_kron import run_kron
-            out = run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler)
+            kr = run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler)
+            if args.workload == "kron":
+                out = kr
+            elif out is not None and kr is not None:
+                out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "scaling", "dtype", "config", "roofline",
+                                                   "kernels", "cpu_baseline", "e2e", "gpu_launches", "clocks")}
         if out is not None:
             print(json.dumps(out), flush=True)
     finally:
