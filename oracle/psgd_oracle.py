@@ -6,14 +6,16 @@ This is an op-for-op NumPy restatement of the reference module
 ``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
 product package ``psgd_tf_b200`` never does.
 
-PARITY UNPINNED at the TensorFlow boundary: the reference ships no tests, no
-golden vectors and TensorFlow cannot be installed in this image (no network),
-so the restatement cannot be executed side by side with the real thing.  It is
-pinned instead by (1) following the reference's operation order/association
-line by line (citations on every function), (2) the algebraic invariants of
-SURVEY.md section 4 (tests/test_oracle.py), (3) dense-densification cross
-checks of every structured variant and (4) a float64 twin (``dtype=np.float64``)
-that bounds the float32 rounding of the oracle itself.
+Pin status.  PINNED AT SOURCE LEVEL, UNPINNED AT TENSORFLOW-KERNEL LEVEL: the reference ships no tests
+or golden vectors and TensorFlow cannot be installed in this image (no network).  The restatement is pinned by
+(0) ``tests/golden/reference_outputs.npz`` -- outputs of the reference's UNMODIFIED source file executed in this
+container on a NumPy stand-in for the TensorFlow ops it calls (``tests/golden/make_reference_golden.py``,
+``tests/golden/tf_numpy_shim``); this oracle reproduces all of them bit for bit (tests/test_reference_golden.py),
+so dispatch, operation order and association are the reference's; (1) line-by-line citations on every function;
+(2) the algebraic invariants of SURVEY.md section 4 (tests/test_oracle.py); (3) dense-densification cross checks of
+every structured variant; (4) a float64 twin (``dtype=np.float64``) that bounds the float32 rounding of the oracle
+itself.  What remains unpinned is the rounding of TensorFlow's own CPU kernels (Eigen contraction order), which
+the 1e-5 tolerance absorbs.  The diagonal / X-shape functions have no reference code at all (spec-derived).
 
 Every function takes ``dtype`` implicitly from its inputs: feed float32 arrays to
 mirror the reference (psgd.py:20), float64 arrays for the twin.
@@ -37,6 +39,7 @@ __all__ = [
     "TINY", "update_precond_dense", "precond_grad_dense", "update_precond_kron",
     "precond_grad_kron", "IpUVtmatvec", "update_precond_UVd_math", "precond_grad_UVd_math",
     "update_precond_Xmat", "precond_grad_Xmat", "update_precond_diag", "precond_grad_diag",
+    "update_precond_splu", "precond_grad_splu",
 ]
 
 
@@ -281,6 +284,83 @@ def _precond_grad_norm_scale(ql, qr, Grad):
     preG = _norm_left_apply_in(ql, Grad)
     preG = preG * (qr * qr)                                                  # :385
     return _norm_left_apply_out(ql, preG)
+
+
+# ----------------------------------------------------------------------------------------
+# sparse LU preconditioner Q = L U                                        psgd.py:396-524
+# ----------------------------------------------------------------------------------------
+def _tri_solve(T, B, lower, adjoint):
+    """tf.linalg.triangular_solve(T, B, lower=..., adjoint=...)."""
+    if B.size == 0:
+        return B.copy()
+    return _solve_triangular(T, B, lower=lower, trans="T" if adjoint else "N", check_finite=False).astype(T.dtype, copy=False)
+
+
+def update_precond_splu(L12, l3, U12, u3, dxs, dgs, step=0.01):
+    """psgd.py:396-477.  L = [L1 0; L2 diag(l3)], U = [U1 U2; 0 diag(u3)]; returns (L12', l3', U12', u3')."""
+    t = L12.dtype.type
+    max_l = np.maximum(np.max(np.diag(L12)), np.max(l3))                     # :411
+    max_u = np.maximum(np.max(np.diag(U12)), np.max(u3))                     # :412
+    rho = np.sqrt(max_l / max_u)                                             # :413
+    L12 = L12 / rho; l3 = l3 / rho; U12 = rho * U12; u3 = rho * u3           # :414-417
+    r = U12.shape[0]                                                         # :420
+    L1, L2, U1, U2 = L12[:r], L12[r:], U12[:, :r], U12[:, r:]                # :421-424
+    dx = np.concatenate([np.reshape(x, [-1, 1]) for x in dxs], 0)            # :426
+    dg = np.concatenate([np.reshape(g, [-1, 1]) for g in dgs], 0)            # :427
+    Ug1 = U1 @ dg[:r] + U2 @ dg[r:]                                          # :430
+    Ug2 = u3 * dg[r:]                                                        # :431
+    Qg1 = L1 @ Ug1                                                           # :433
+    Qg2 = L2 @ Ug1 + l3 * Ug2                                                # :434
+    iUtx1 = _tri_solve(U1, dx[:r], lower=False, adjoint=True)                # :436
+    iUtx2 = (dx[r:] - U2.T @ iUtx1) / u3                                     # :437
+    iQtx2 = iUtx2 / l3                                                       # :439
+    iQtx1 = _tri_solve(L1, iUtx1 - L2.T @ iQtx2, lower=True, adjoint=True)   # :440
+    LtQg1 = L1.T @ Qg1 + L2.T @ Qg2                                          # :442
+    LtQg2 = l3 * Qg2                                                         # :443
+    Pg1 = U1.T @ LtQg1                                                       # :445
+    Pg2 = U2.T @ LtQg1 + u3 * LtQg2                                          # :446
+    iLiQtx1 = _tri_solve(L1, iQtx1, lower=True, adjoint=False)               # :448
+    iLiQtx2 = (iQtx2 - L2 @ iLiQtx1) / l3                                    # :449
+    iPx2 = iLiQtx2 / u3                                                      # :451
+    iPx1 = _tri_solve(U1, iLiQtx1 - U2 @ iPx2, lower=False, adjoint=False)   # :452
+    grad1 = np.tril(Qg1 @ Qg1.T - iQtx1 @ iQtx1.T)                           # :455-456
+    grad2 = Qg2 @ Qg1.T - iQtx2 @ iQtx1.T                                    # :457
+    grad3 = Qg2 * Qg2 - iQtx2 * iQtx2                                        # :458
+    max_abs_grad = np.maximum(np.maximum(_max_abs(grad1), _max_abs(grad2)), _max_abs(grad3))   # :459-461
+    step0 = t(step) / (max_abs_grad + _tiny(L12))                            # :462
+    newL1 = L1 - (step0 * grad1) @ L1                                        # :463
+    newL2 = L2 - (step0 * grad2) @ L1 - step0 * grad3 * L2                   # :464
+    newl3 = l3 - step0 * grad3 * l3                                          # :465
+    grad1 = np.triu(Pg1 @ dg[:r].T - dx[:r] @ iPx1.T)                        # :468-469
+    grad2 = Pg1 @ dg[r:].T - dx[:r] @ iPx2.T                                 # :470
+    grad3 = Pg2 * dg[r:] - dx[r:] * iPx2                                     # :471
+    max_abs_grad = np.maximum(np.maximum(_max_abs(grad1), _max_abs(grad2)), _max_abs(grad3))   # :472-474
+    step0 = t(step) / (max_abs_grad + _tiny(L12))                            # :475
+    newU1 = U1 - U1 @ (step0 * grad1)                                        # :476
+    newU2 = U2 - U1 @ (step0 * grad2) - step0 * grad3.T * U2                 # :477
+    newu3 = u3 - step0 * grad3 * u3                                          # :478
+    return np.concatenate([newL1, newL2], axis=0), newl3, np.concatenate([newU1, newU2], axis=1), newu3   # :480
+
+
+def precond_grad_splu(L12, l3, U12, u3, grads):
+    """psgd.py:483-524."""
+    grad = [np.reshape(g, [-1, 1]) for g in grads]                           # :495
+    lens = [g.shape[0] for g in grad]                                        # :496
+    grad = np.concatenate(grad, 0)                                           # :497
+    r = U12.shape[0]
+    L1, L2, U1, U2 = L12[:r], L12[r:], U12[:, :r], U12[:, r:]                # :499-503
+    Ug1 = U1 @ grad[:r] + U2 @ grad[r:]                                      # :506
+    Ug2 = u3 * grad[r:]                                                      # :507
+    Qg1 = L1 @ Ug1                                                           # :509
+    Qg2 = L2 @ Ug1 + l3 * Ug2                                                # :510
+    LtQg1 = L1.T @ Qg1 + L2.T @ Qg2                                          # :512
+    LtQg2 = l3 * Qg2                                                         # :513
+    pre_grad = np.concatenate([U1.T @ LtQg1, U2.T @ LtQg1 + u3 * LtQg2], axis=0)   # :515-516
+    pre_grads, idx = [], 0
+    for i in range(len(grads)):                                              # :518-522
+        pre_grads.append(np.reshape(pre_grad[idx: idx + lens[i]], np.shape(grads[i])))
+        idx += lens[i]
+    return pre_grads
 
 
 # ----------------------------------------------------------------------------------------
