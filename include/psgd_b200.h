@@ -83,6 +83,22 @@ int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, double* work, int cap)
 typedef int (*psgd_allreduce_fn)(void* user, void* device_buf, int64_t count, int op, void* stream);
 int psgd_set_allreduce(psgd_ctx* ctx, psgd_allreduce_fn fn, void* user);
 
+/* Peer-memory exchange: the B200-native alternative to the hook on one NVSwitch box (one process per GPU).  Each
+ * rank exports a small device slab through CUDA IPC, gathers every rank's 64-byte handle with whatever host plumbing
+ * it has (torch.distributed.all_gather_object in psgd_tf_b200/partition.py) and attaches.  From then on the
+ * cross-rank reductions of the sharded paths are ONE tiny kernel per phase that stores the partials straight into the
+ * peers' slabs over NVLink, waits on epoch flags and reduces in fixed rank order (bit-identical on every rank, no host
+ * round trip, CUDA-graph capturable).  Takes precedence over the hook while attached.
+ *   psgd_comm_export : allocate/zero the local slab, write its cudaIpcMemHandle_t (PSGD_COMM_HANDLE_BYTES) to handle_out
+ *   psgd_comm_attach : handles = world x PSGD_COMM_HANDLE_BYTES, in rank order (this rank's own entry is ignored)
+ *   psgd_comm_status : synchronises ctx's stream; error if a peer failed to publish within the in-kernel timeout;
+ *                      epoch_out (may be NULL) = exchanges completed so far                                         */
+#define PSGD_COMM_HANDLE_BYTES 64
+int psgd_comm_export(psgd_ctx* ctx, void* handle_out);
+int psgd_comm_attach(psgd_ctx* ctx, int rank, int world, const void* handles);
+int psgd_comm_detach(psgd_ctx* ctx);
+int psgd_comm_status(psgd_ctx* ctx, int64_t* epoch_out);
+
 /* ---- UVd: Q = (I + U V^T) diag(d) ---------------------------------------------------------- */
 /* Replaces update_precond_UVd_math_ (psgd.py:554-617).  U,V:[n,r]  d,v,h:[n].  In place on U,V,d.
  * The reference's two coin flips are arguments: balance = (uniform < 0.01) (psgd.py:562),
@@ -92,6 +108,15 @@ int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v,
 /* Replaces precond_grad_UVd_math (psgd.py:619-627): out = d*(I+VU^T)(I+UV^T)(d*g). */
 int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,
                    float* out, int64_t n, int r);
+/* Tail of UVd.step (psgd.py:747-762) on the flattened parameter vector: pre = precond_grad_UVd_math(U,V,d,g);
+ * lr = lr_params * min(grad_clip_max_norm / (||pre||_2 + tiny), 1) (psgd.py:750-754; pass INFINITY for "no clipping",
+ * then lr = lr_params); param -= lr * pre (+ v when v != NULL: the finite-difference perturbation, psgd.py:760-762).
+ * Without clipping the parameter update is fused into the second apply sweep and pre is only written if pre_out is
+ * given; with clipping the norm is reduced on the device (all-reduced when sharded) -- never a host sync.
+ * v and pre_out may be NULL. */
+int psgd_uvd_step_tail(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* param,
+                       const float* v, float* pre_out, int64_t n, int r, float lr_params, float grad_clip_max_norm,
+                       float tiny);
 /* Replaces IpUVtmatvec (psgd.py:540-544): out = x + U (V^T x), x:[n,k] row-major. */
 int psgd_ipuvt_matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out,
                       int64_t n, int r, int k);

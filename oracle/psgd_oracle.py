@@ -37,7 +37,7 @@ TINY = np.float32(2.0 ** -126)
 
 __all__ = [
     "TINY", "update_precond_dense", "precond_grad_dense", "update_precond_kron",
-    "precond_grad_kron", "IpUVtmatvec", "update_precond_UVd_math", "precond_grad_UVd_math",
+    "precond_grad_kron", "IpUVtmatvec", "update_precond_UVd_math", "precond_grad_UVd_math", "uvd_step_tail",
     "update_precond_Xmat", "precond_grad_Xmat", "update_precond_diag", "precond_grad_diag",
     "update_precond_splu", "precond_grad_splu",
 ]
@@ -427,6 +427,26 @@ def precond_grad_UVd_math(U, V, d, g):
     g = IpUVtmatvec(U, V, d * g)                                             # :625
     g = d * IpUVtmatvec(V, U, g)                                             # :626
     return g
+
+
+def uvd_step_tail(U, V, d, grad, params, lr_params, grad_clip_max_norm=np.inf, v=None, tiny=None):
+    """Tail of ``UVd.step`` (psgd.py:747-762) on the flattened vectors (``grad``, ``params``, ``v``: [N, 1]).
+    Returns ``(new_params, pre_grad)``.  ``v``: the finite-difference perturbation still sitting on the parameters
+    (psgd.py:760-762) or None.  Restated arithmetic; the class itself needs tf.GradientTape, so this tail is not
+    covered by the reference-generated golden vectors (its ``precond_grad_UVd_math`` call is)."""
+    dt = U.dtype
+    tiny = _tiny(U) if tiny is None else dt.type(tiny)
+    pre_grad = precond_grad_UVd_math(U, V, d, grad)                          # :748
+    if np.isinf(grad_clip_max_norm):                                         # :750-751
+        lr = dt.type(lr_params)
+    else:
+        grad_norm = np.sqrt(np.sum(pre_grad * pre_grad, dtype=dt)) + tiny    # :753
+        lr = dt.type(lr_params) * min(dt.type(grad_clip_max_norm) / grad_norm, dt.type(1.0))   # :754
+    if v is None:
+        new_params = params - lr * pre_grad                                  # :757-759
+    else:
+        new_params = params - (lr * pre_grad + v)                            # :760-762
+    return new_params.astype(dt, copy=False), pre_grad
 
 
 # ----------------------------------------------------------------------------------------

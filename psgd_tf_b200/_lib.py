@@ -42,8 +42,13 @@ SIGNATURES = {
     "psgd_set_option": (C.c_int, [C.c_void_p, C.c_char_p, C.c_int64]),
     "psgd_profile_read": (C.c_int, [C.c_void_p, C.POINTER(C.c_int), C.POINTER(C.c_float), C.POINTER(C.c_double), C.c_int]),
     "psgd_set_allreduce": (C.c_int, [C.c_void_p, ALLREDUCE_FN, C.c_void_p]),
+    "psgd_comm_export": (C.c_int, [C.c_void_p, C.c_void_p]),
+    "psgd_comm_attach": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "psgd_comm_detach": (C.c_int, [C.c_void_p]),
+    "psgd_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "psgd_uvd_update": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]),
     "psgd_uvd_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int]),
+    "psgd_uvd_step_tail": (C.c_int, [C.c_void_p] + [c_float_p] * 7 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float]),
     "psgd_ipuvt_matvec": (C.c_int, [C.c_void_p] + [c_float_p] * 4 + [C.c_int64, C.c_int, C.c_int]),
     "psgd_diag_update": (C.c_int, [C.c_void_p] + [c_float_p] * 3 + [C.c_int64, C.c_float, C.c_float]),
     "psgd_diag_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 3 + [C.c_int64]),
@@ -139,6 +144,31 @@ class Context:
         work = (C.c_double * cap)()
         n = self.lib.psgd_profile_read(self.handle, ids, ms, work, cap)
         return [(int(ids[i]), float(ms[i]), float(work[i])) for i in range(n)]
+
+    # ---- peer-memory exchange (include/psgd_b200.h, csrc/comm.cu) -----------------------------------
+    COMM_HANDLE_BYTES = 64
+
+    def comm_export(self) -> bytes:
+        """Allocate this rank's exchange slab and return its CUDA IPC handle (64 bytes)."""
+        buf = C.create_string_buffer(self.COMM_HANDLE_BYTES)
+        check(self.lib.psgd_comm_export(self.handle, buf))
+        return buf.raw
+
+    def comm_attach(self, rank: int, world: int, handles):
+        """``handles``: every rank's ``comm_export()`` bytes, in rank order."""
+        blob = b"".join(bytes(h) for h in handles)
+        if len(blob) != world * self.COMM_HANDLE_BYTES:
+            raise ValueError(f"comm_attach: expected {world} handles of {self.COMM_HANDLE_BYTES} bytes")
+        check(self.lib.psgd_comm_attach(self.handle, int(rank), int(world), blob))
+
+    def comm_detach(self):
+        check(self.lib.psgd_comm_detach(self.handle))
+
+    def comm_status(self) -> int:
+        """Synchronise and return the number of exchanges completed; raises if a peer wait timed out."""
+        e = C.c_int64(0)
+        check(self.lib.psgd_comm_status(self.handle, C.byref(e)))
+        return int(e.value)
 
     def set_allreduce(self, pyfunc):
         """pyfunc(device_ptr:int, count:int, op:int, stream:int) -> int, or None to clear."""

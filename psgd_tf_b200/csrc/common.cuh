@@ -63,6 +63,8 @@ struct psgd_ctx {
   int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks
   psgd_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;
+  void* comm = nullptr;      // psgd::comm::State of the peer-memory exchange (comm.cu)
+  int comm_world = 0;        // > 0 once attached
   // optional per-kernel timing (psgd_set_option("profile", 1)): CUDA event pairs around the large kernels
   int opt_profile = 0;
   struct ProfRec { int id; cudaEvent_t e0, e1; double work; };
@@ -87,6 +89,12 @@ struct WsCarver {
   }
   static size_t padded(size_t bytes) { return ((bytes + 255) / 256) * 256; }
 };
+
+// Cross-rank reduction between two kernels of a chunk-sharded sweep (comm.cu): n_sum float64 sums and n_max
+// non-negative float maxima, reduced in place over all ranks -- by the peer-memory exchange kernel when attached, else
+// by the registered all-reduce hook, else a single-GPU no-op.
+int cross_rank_reduce(psgd_ctx* ctx, double* sum_buf, int n_sum, float* max_buf, int n_max);
+static inline bool is_sharded(const psgd_ctx* ctx) { return ctx->comm_world > 0 || ctx->allreduce != nullptr; }
 
 // Brackets one kernel launch with CUDA events when profiling is on (kernel ids: psgd_b200.h).
 struct ProfScope {
@@ -178,6 +186,18 @@ __device__ __forceinline__ void fence_proxy_async_smem() {
 }
 __device__ __forceinline__ void named_bar_sync(uint32_t id, uint32_t nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+// Packed fp32 FMA (sm_100+): d.x = a.x*b.x + c.x, d.y = a.y*b.y + c.y, each an IEEE round-to-nearest fma.   SASS: FFMA2.
+__device__ __forceinline__ float2 ffma2(float2 a, float2 b, float2 c) {
+  unsigned long long ra, rb, rc, rd;
+  asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+  asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+  asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+  float2 d;
+  asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+  return d;
 }
 
 __device__ __forceinline__ float warp_sum(float v) {

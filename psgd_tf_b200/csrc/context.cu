@@ -59,6 +59,7 @@ extern "C" int psgd_create(int device, void* stream, psgd_ctx** out) {
 extern "C" int psgd_destroy(psgd_ctx* ctx) {
   if (!ctx) return PSGD_OK;
   cudaSetDevice(ctx->device);
+  psgd_comm_detach(ctx);
   if (ctx->ws) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->ws);

@@ -157,13 +157,6 @@ static int grid_for(const psgd_ctx* ctx, int64_t work_items) {
   return (int)blocks;
 }
 
-static int hook_max(psgd_ctx* ctx, float* p) {
-  if (!ctx->allreduce) return PSGD_OK;
-  int rc = ctx->allreduce(ctx->allreduce_user, p, 1, 1, (void*)ctx->stream);
-  PSGD_REQUIRE(rc == 0, PSGD_ERR_COMM, "all-reduce hook returned %d", rc);
-  return PSGD_OK;
-}
-
 }  // namespace ew
 }  // namespace psgd
 
@@ -181,9 +174,9 @@ extern "C" int psgd_diag_update(psgd_ctx* ctx, float* q, const float* v, const f
                                 float tiny) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0, PSGD_ERR_BAD_SHAPE, "diag update: n=%lld", (long long)n);
-  if (n == 0) return PSGD_OK;
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;      // an empty shard still takes part in the max exchange
   const void* ptrs[] = {q, v, h};
-  PSGD_RETURN_IF(check_ptrs("diag update", ptrs, 3));
+  if (n > 0) PSGD_RETURN_IF(check_ptrs("diag update", ptrs, 3));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   PSGD_RETURN_IF(ctx->reserve(256));
   ew::Scalars* sc = static_cast<ew::Scalars*>(ctx->ws);
@@ -192,7 +185,7 @@ extern "C" int psgd_diag_update(psgd_ctx* ctx, float* q, const float* v, const f
   PSGD_LAUNCH_CHECK(ctx);
   ew::diag_kernel<false><<<grid, ew::kThreads, 0, ctx->stream>>>(q, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(ew::hook_max(ctx, &sc->max_abs));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &sc->max_abs, 1));
   ew::diag_kernel<true><<<grid, ew::kThreads, 0, ctx->stream>>>(q, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
@@ -214,9 +207,9 @@ extern "C" int psgd_xmat_update(psgd_ctx* ctx, float* a, float* b, const float* 
                                 float step, float tiny) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0, PSGD_ERR_BAD_SHAPE, "xmat update: n=%lld", (long long)n);
-  if (n == 0) return PSGD_OK;
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;
   const void* ptrs[] = {a, b, v, h};
-  PSGD_RETURN_IF(check_ptrs("xmat update", ptrs, 4));
+  if (n > 0) PSGD_RETURN_IF(check_ptrs("xmat update", ptrs, 4));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   PSGD_RETURN_IF(ctx->reserve(256));
   ew::Scalars* sc = static_cast<ew::Scalars*>(ctx->ws);
@@ -225,7 +218,7 @@ extern "C" int psgd_xmat_update(psgd_ctx* ctx, float* a, float* b, const float* 
   PSGD_LAUNCH_CHECK(ctx);
   ew::xmat_kernel<false><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(ew::hook_max(ctx, &sc->max_abs));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &sc->max_abs, 1));
   ew::xmat_kernel<true><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;

@@ -462,12 +462,20 @@ static void carve_apply(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
   L.part = c.take<float>(col_partial_floats(M, N));
 }
 
+// The reference forms the small Gram matrix (Q^T Q) first whenever that saves dense flops (psgd.py:189, :260, :318).
+// On the tensor-core path the factors' triangularity is exploited instead: X Q^T Q as two triangular products
+// executes n^3 + n^3 multiply-adds, against 2/3 n^3 + 2 n^3 through the (dense, symmetric) Gram matrix, so large
+// factors always take the chained association.  The two associations differ only in fp32 rounding (~1e-7 relative).
+static bool chain_preferred(const psgd_ctx* ctx, int n, int other) {
+  return ctx->opt_assume_tri && ctx->opt_gemm_path != 1 && n >= 512 && other >= 256 && (n % 4) == 0 && (other % 4) == 0;
+}
+
 // out = X (Qr^T Qr) with the reference's association switch          psgd.py:189-192, :260-263
 static int right_dense_apply(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N, bool from_t1, bool to_out) {
   std::vector<la::Gemm> gs;
   auto X = [&](Layer& L) { return from_t1 ? L.t1 : L.G; };
   auto O = [&](Layer& L) { return to_out ? L.out : L.t2; };
-  if (M < N) {
+  if (M < N || chain_preferred(ctx, N, M)) {
     for (auto& L : Ls) gs.push_back(mk(M, N, N, X(L), N, false, L.Qr, N, true, L.t3, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
     gs.clear();
@@ -487,11 +495,19 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
   std::vector<la::Gemm> gs;
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
     if (M < N) {                                                          // psgd.py:190
-      for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
-      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
-      gs.clear();
-      for (auto& L : Ls) gs.push_back(mk(M, N, M, L.P, M, false, L.G, N, false, L.t1, N));
-      PSGD_RETURN_IF(gemm_all(ctx, gs));
+      if (chain_preferred(ctx, M, N)) {                                   // Ql^T (Ql G) instead of (Ql^T Ql) G
+        for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.G, N, false, L.t3, N));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+        gs.clear();
+        for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t3, N, false, L.t1, N));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, 0));
+      } else {
+        for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+        gs.clear();
+        for (auto& L : Ls) gs.push_back(mk(M, N, M, L.P, M, false, L.G, N, false, L.t1, N));
+        PSGD_RETURN_IF(gemm_all(ctx, gs));
+      }
       gs.clear();
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t1, N, false, L.Qr, N, true, L.t2, N));
       PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
@@ -499,11 +515,19 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t2, N, false, L.Qr, N, false, L.out, N));
       return gemm_all(ctx, gs, 0, kUpper);
     }
-    for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));       // psgd.py:192
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
-    gs.clear();
-    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.P, N, false, L.t1, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs));
+    if (chain_preferred(ctx, N, M)) {                                     // (G Qr^T) Qr instead of G (Qr^T Qr)
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.Qr, N, true, L.t3, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t3, N, false, L.Qr, N, false, L.t1, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kUpper));
+    } else {
+      for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));     // psgd.py:192
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.P, N, false, L.t1, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs));
+    }
     gs.clear();
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.t1, N, false, L.t2, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
@@ -512,7 +536,7 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
     return gemm_all(ctx, gs, kLower, 0);
   }
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
-    if (M < N) {
+    if (M < N && !chain_preferred(ctx, M, N)) {
       for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
       PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
       gs.clear();

@@ -45,9 +45,17 @@ __host__ __device__ constexpr bool gp_needed(int R, int MODE, int i, int j) {
   return (i >= R) && (j >= W);                                          // kMatvec: V^T x only
 }
 __host__ __device__ constexpr int gp_nx(int MODE) { return MODE == kUpdate ? 2 : 1; }
+// Accumulators are kept as float2 pairs (columns 2k, 2k+1) so that one packed FFMA2 (fma.rn.f32x2, sm_100) updates
+// two table entries; a pair is live when either of its columns is needed.
+__host__ __device__ constexpr bool gp_pair_needed(int R, int MODE, int i, int k) {
+  const int E = 2 * R + gp_nx(MODE);
+  return gp_needed(R, MODE, i, 2 * k) || (2 * k + 1 < E && gp_needed(R, MODE, i, 2 * k + 1));
+}
+// registers (floats) held for table row i
 __host__ __device__ constexpr int gp_row_count(int R, int MODE, int i) {
   int c = 0;
-  for (int j = 0; j < 2 * R + gp_nx(MODE); ++j) c += gp_needed(R, MODE, i, j) ? 1 : 0;
+  const int E2 = (2 * R + gp_nx(MODE) + 1) / 2;
+  for (int k = 0; k < E2; ++k) c += gp_pair_needed(R, MODE, i, k) ? 2 : 0;
   return c;
 }
 __host__ __device__ constexpr int gp_total(int R, int MODE) {
@@ -55,7 +63,7 @@ __host__ __device__ constexpr int gp_total(int R, int MODE) {
   for (int i = 0; i < 2 * R; ++i) c += gp_row_count(R, MODE, i);
   return c;
 }
-constexpr int kAccPerRole = 96;
+constexpr int kAccPerRole = 104;
 __host__ __device__ constexpr int gp_nroles(int R, int MODE) { return (gp_total(R, MODE) + kAccPerRole - 1) / kAccPerRole; }
 // first table row of role `role` (role >= nroles gives W)
 __host__ __device__ constexpr int gp_begin(int R, int MODE, int role) {
@@ -75,6 +83,7 @@ struct GramPlan {
   static constexpr int W = 2 * R;
   static constexpr int NX = gp_nx(MODE);
   static constexpr int E = W + NX;
+  static constexpr int E2 = (E + 1) / 2;          // float2 column pairs
   static constexpr int NROLES = gp_nroles(R, MODE);
   // warps per role: keep the CTA at <= 12 warps so ptxas may use > 128 registers per thread
   static constexpr int WPR = NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES <= 5 ? 2 : 1)));
@@ -83,6 +92,7 @@ struct GramPlan {
   static constexpr int CONSUMER_WARPS = NROLES * WPR;
   static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
   __host__ __device__ static constexpr bool needed(int i, int j) { return gp_needed(R, MODE, i, j); }
+  __host__ __device__ static constexpr bool pair_needed(int i, int k) { return gp_pair_needed(R, MODE, i, k); }
   __host__ __device__ static constexpr int begin(int role) { return gp_begin(R, MODE, role); }
 };
 
@@ -221,17 +231,17 @@ struct GramRole {
   static constexpr int I0 = P::begin(ROLE);
   static constexpr int I1 = P::begin(ROLE + 1);
   static constexpr int NI = (I1 - I0) > 0 ? (I1 - I0) : 1;
-  float acc[NI][P::E];
+  float2 acc[NI][P::E2];
 
   __device__ __forceinline__ void zero() {
 #pragma unroll
     for (int i = 0; i < NI; ++i)
 #pragma unroll
-      for (int j = 0; j < P::E; ++j) acc[i][j] = 0.f;
+      for (int k = 0; k < P::E2; ++k) acc[i][k] = make_float2(0.f, 0.f);
   }
   __device__ __forceinline__ void row(const float* __restrict__ urow, const float* __restrict__ vrow,
                                       const RowX<R, MODE>& rx) {
-    float z[P::E];
+    float z[2 * P::E2];
     {
       float u[R], v[R];
       load_row<R>(urow, u);
@@ -240,12 +250,15 @@ struct GramRole {
       for (int k = 0; k < R; ++k) { z[k] = u[k]; z[R + k] = v[k]; }
 #pragma unroll
       for (int k = 0; k < P::NX; ++k) z[P::W + k] = rx.x[k];
+      if constexpr (P::E & 1) z[P::E] = 0.f;
     }
+    // acc[i][2k..2k+1] += z[i] * (z[2k], z[2k+1]): one FFMA2 per pair (SASS: FFMA2 with a scalar-broadcast operand)
 #pragma unroll
     for (int i = I0; i < I1; ++i)
 #pragma unroll
-      for (int j = 0; j < P::E; ++j)
-        if (P::needed(i, j)) acc[i - I0][j] = fmaf(z[i], z[j], acc[i - I0][j]);
+      for (int k = 0; k < P::E2; ++k)
+        if (P::pair_needed(i, k))
+          acc[i - I0][k] = ffma2(make_float2(z[i], z[i]), make_float2(z[2 * k], z[2 * k + 1]), acc[i - I0][k]);
   }
   // warp butterfly, then lane 0 writes this warp's table rows into `dst` ([W][E] floats)
   __device__ __forceinline__ void flush(float* dst, int lane) {
@@ -254,7 +267,7 @@ struct GramRole {
 #pragma unroll
       for (int j = 0; j < P::E; ++j)
         if (P::needed(i, j)) {
-          float s = warp_sum(acc[i - I0][j]);
+          float s = warp_sum((j & 1) ? acc[i - I0][j / 2].y : acc[i - I0][j / 2].x);
           if (lane == 0) dst[i * P::E + j] = s;
         }
   }
@@ -505,7 +518,9 @@ __global__ void uvd_small_apply_kernel(const double* __restrict__ G, int r, Smal
 constexpr int kMapConsumerWarps = 8;
 constexpr int kMapThreads = (kMapConsumerWarps + 1) * 32;
 
-enum MapKind { kMapUpd2 = 0, kMapUpd3U = 1, kMapUpd3V = 2, kMapApply2 = 3, kMapMatvec2 = 4 };
+enum MapKind { kMapUpd2 = 0, kMapUpd3U = 1, kMapUpd3V = 2, kMapApply2 = 3, kMapMatvec2 = 4,
+               kMapApplyNorm = 5,    // apply + sum of squares of the preconditioned gradient (UVd.step clip, psgd.py:752)
+               kMapApplyParam = 6 }; // apply fused with the parameter update (UVd.step without clipping, psgd.py:757-762)
 
 template <int KIND> struct MapTraits;
 template <> struct MapTraits<kMapUpd2>   { static constexpr int NM = 2, NV = 3; static constexpr bool kStore = false; };
@@ -513,13 +528,17 @@ template <> struct MapTraits<kMapUpd3U>  { static constexpr int NM = 1, NV = 4; 
 template <> struct MapTraits<kMapUpd3V>  { static constexpr int NM = 1, NV = 4; static constexpr bool kStore = true; };
 template <> struct MapTraits<kMapApply2> { static constexpr int NM = 2, NV = 2; static constexpr bool kStore = false; };
 template <> struct MapTraits<kMapMatvec2>{ static constexpr int NM = 1, NV = 1; static constexpr bool kStore = false; };
+template <> struct MapTraits<kMapApplyNorm>  { static constexpr int NM = 2, NV = 2; static constexpr bool kStore = false; };
+template <> struct MapTraits<kMapApplyParam> { static constexpr int NM = 2, NV = 4; static constexpr bool kStore = false; };
 
 struct MapOut {
   float* o0; float* o1; float* o2;   // per-row outputs (coalesced direct stores)
   float* mat_out;                    // kStore kinds: updated matrix
   float* vec_out;                    // kStore kinds: updated d
-  float* partial;                    // Upd2: [grid][3+2r] sums
+  float* partial;                    // Upd2: [grid][3+2r] sums; ApplyNorm: [grid] sums of squares
   SmallState* st;
+  float lr;                          // ApplyParam: learning rate
+  int has_v;                         // ApplyParam: vec[3] holds the finite-difference perturbation to remove
 };
 
 // per-lane accumulators of sweep 2
@@ -551,6 +570,10 @@ struct MapBody {
 #pragma unroll
       for (int k = 0; k < R; ++k) { k0[k] = st->c1[k]; k1[k] = st->c2[k]; }
       mu_d = st->mu_d; mu = st->mu;
+    } else if constexpr (KIND == kMapApplyNorm) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; }
+      acc.aa = 0.f;
     } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; }
@@ -601,14 +624,24 @@ struct MapBody {
       for (int k = 0; k < R; ++k) vv[k] = vv[k] - mu * (sa * k0[k] - sb * k1[k]);
       store_row<R>(m0w, vv);
       *vecw = v3 - (mu_d * v3) * v2;
-    } else if constexpr (KIND == kMapApply2) {
+    } else if constexpr (KIND == kMapApply2 || KIND == kMapApplyNorm || KIND == kMapApplyParam) {
       // v0=d v1=g                                                            psgd.py:625-626
       float u[R], vv[R];
       load_row<R>(m0, u);
       load_row<R>(m1, vv);
       const float dg = v0 * v1;
       const float y = dg + dot_row<R>(u, k0);
-      o.o0[row] = v0 * (y + dot_row<R>(vv, k1));
+      const float pre = v0 * (y + dot_row<R>(vv, k1));
+      if constexpr (KIND == kMapApplyParam) {
+        // v2=param v3=perturbation: param -= lr*pre (+ v)                     psgd.py:757-762
+        float upd = o.lr * pre;
+        if (o.has_v) upd = upd + v3;
+        o.o0[row] = v2 - upd;
+        if (o.o1) o.o1[row] = pre;
+      } else {
+        o.o0[row] = pre;
+        if constexpr (KIND == kMapApplyNorm) acc.aa = fmaf(pre, pre, acc.aa);     // psgd.py:752
+      }
     } else {
       // matvec: out = x + U_row . p   (m0 = U)                               psgd.py:544
       float u[R];
@@ -700,6 +733,10 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
                  T::kStore ? o.vec_out + r0 : nullptr);
       }
     }
+    if constexpr (KIND == kMapApplyNorm) {
+      const float s0 = warp_sum(body.acc.aa);
+      if (lane == 0) red[warp][0] = s0;
+    }
     if constexpr (KIND == kMapUpd2) {
       // warp butterflies -> per-warp slots -> fixed-order CTA partial
       float mx = warp_max(body.acc.mx);
@@ -710,6 +747,15 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
         float ta = warp_sum(body.acc.atX[k]), tb = warp_sum(body.acc.btX[k]);
         if (lane == 0) { red[warp][4 + k] = ta; red[warp][4 + R + k] = tb; }
       }
+    }
+  }
+  if constexpr (KIND == kMapApplyNorm) {
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      float s = 0.f;
+#pragma unroll
+      for (int w = 0; w < kMapConsumerWarps; ++w) s += red[w][0];
+      o.partial[blockIdx.x] = s;
     }
   }
   if constexpr (KIND == kMapUpd2) {
@@ -789,11 +835,6 @@ static int launch_gram(psgd_ctx* ctx, const SweepArgs& a, float* partial, int gr
   constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
   using L = TileLayout<R, 2, NV, P::TILE>;
   auto kern = gram_sweep_kernel<R, MODE>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes));
-    attr_done = true;
-  }
   kern<<<grid, P::THREADS, L::kSmemBytes, ctx->stream>>>(a, partial);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
@@ -802,24 +843,45 @@ static int launch_gram(psgd_ctx* ctx, const SweepArgs& a, float* partial, int gr
 template <int R, int KIND>
 static int launch_map(psgd_ctx* ctx, const SweepArgs& a, const MapOut& o, int update_U, int grid) {
   ProfScope prof(ctx, KIND == kMapUpd2 ? PSGD_K_UVD_MAP_UPDATE2
-                      : (KIND == kMapApply2 || KIND == kMapMatvec2) ? PSGD_K_UVD_MAP_APPLY : PSGD_K_UVD_MAP_UPDATE3);
+                      : (KIND == kMapUpd3U || KIND == kMapUpd3V) ? PSGD_K_UVD_MAP_UPDATE3 : PSGD_K_UVD_MAP_APPLY);
   using T = MapTraits<KIND>;
   using L = TileLayout<R, T::NM, T::NV, kMapTile>;
   auto kern = map_sweep_kernel<R, KIND>;
-  static bool attr_done = false;
-  if (!attr_done) {
-    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes));
-    attr_done = true;
-  }
   kern<<<grid, kMapThreads, L::kSmemBytes, ctx->stream>>>(a, o, update_U);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 
-static int hook_allreduce(psgd_ctx* ctx, void* buf, int64_t count, int op) {
-  if (!ctx->allreduce) return PSGD_OK;
-  int rc = ctx->allreduce(ctx->allreduce_user, buf, count, op, (void*)ctx->stream);
-  PSGD_REQUIRE(rc == 0, PSGD_ERR_COMM, "all-reduce hook returned %d", rc);
+// Opt every sweep kernel of rank R into its dynamic shared-memory size once, up front, so that no attribute call
+// happens later inside a CUDA-graph stream capture.
+template <int R, int KIND>
+static cudaError_t map_attr() {
+  using T = MapTraits<KIND>;
+  using L = TileLayout<R, T::NM, T::NV, kMapTile>;
+  return cudaFuncSetAttribute(map_sweep_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes);
+}
+template <int R, int MODE>
+static cudaError_t gram_attr() {
+  using P = GramPlan<R, MODE>;
+  constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
+  using L = TileLayout<R, 2, NV, P::TILE>;
+  return cudaFuncSetAttribute(gram_sweep_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes);
+}
+template <int R>
+static int ensure_attrs() {
+  static bool done = false;
+  if (done) return PSGD_OK;
+  PSGD_CUDA_CHECK((gram_attr<R, kUpdate>()));
+  PSGD_CUDA_CHECK((gram_attr<R, kApply>()));
+  PSGD_CUDA_CHECK((gram_attr<R, kMatvec>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpd2>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpd3U>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpd3V>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapApply2>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapMatvec2>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapApplyNorm>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapApplyParam>()));
+  done = true;
   return PSGD_OK;
 }
 
@@ -830,22 +892,25 @@ struct Scratch {
   float* a; float* b; float* nd;   // N-vectors (update only)
 };
 
-static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, bool update, Scratch* s) {
+static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, bool update, Scratch* s, int64_t extra_vec = 0) {
   const size_t table = (size_t)(2 * r) * (2 * r + 2);
   size_t bytes = WsCarver::padded(sizeof(float) * table * grid) + WsCarver::padded(sizeof(double) * table) +
-                 WsCarver::padded(sizeof(SmallState)) + (update ? 3 * WsCarver::padded(sizeof(float) * (size_t)n) : 0);
+                 WsCarver::padded(sizeof(SmallState)) + (update ? 3 * WsCarver::padded(sizeof(float) * (size_t)n) : 0) +
+                 WsCarver::padded(sizeof(float) * (size_t)extra_vec);
   PSGD_RETURN_IF(ctx->reserve(bytes));
   WsCarver c(ctx->ws);
   s->partial = c.take<float>(table * grid);
   s->G = c.take<double>(table);
   s->st = c.take<SmallState>(1);
   if (update) { s->a = c.take<float>(n); s->b = c.take<float>(n); s->nd = c.take<float>(n); }
+  else if (extra_vec) s->a = c.take<float>(extra_vec);
   return PSGD_OK;
 }
 
 template <int R>
 static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, int64_t n,
                        float step, float tiny, int balance, int update_U) {
+  PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, true, &s));
@@ -856,7 +921,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
     PSGD_LAUNCH_CHECK(ctx);
     maxabs2_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
     PSGD_LAUNCH_CHECK(ctx);
-    PSGD_RETURN_IF(hook_allreduce(ctx, &s.st->maxU, 2, 1));
+    PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &s.st->maxU, 2));
     balance_rho_kernel<<<1, 1, 0, st>>>(s.st);
     PSGD_LAUNCH_CHECK(ctx);
     balance_scale_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
@@ -870,7 +935,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   constexpr int table = GramPlan<R, kUpdate>::W * GramPlan<R, kUpdate>::E;
   reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
   PSGD_LAUNCH_CHECK(ctx);
 
@@ -881,8 +946,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   constexpr int cnt2 = 3 + 2 * R;
   reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, cnt2, s.G);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, cnt2, 0));
-  PSGD_RETURN_IF(hook_allreduce(ctx, &s.st->max_nabla, 1, 1));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, cnt2, &s.st->max_nabla, 1));
   uvd_small2_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
   PSGD_LAUNCH_CHECK(ctx);
 
@@ -900,6 +964,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
 template <int R>
 static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* out,
                       int64_t n) {
+  PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
@@ -910,7 +975,7 @@ static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float
   constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
   reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
   PSGD_LAUNCH_CHECK(ctx);
   MapOut o{};
@@ -919,9 +984,78 @@ static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float
   return PSGD_OK;
 }
 
+// param -= lr_params * min(max_norm / (||pre||_2 + tiny), 1) * pre (+ v)         psgd.py:750-762
+__global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ param, const float* __restrict__ pre,
+                                                          const float* __restrict__ v, int64_t n, float lr_params,
+                                                          float max_norm, float tiny, const double* __restrict__ sumsq) {
+  const float grad_norm = sqrtf((float)sumsq[0]) + tiny;
+  const float lr = lr_params * fminf(max_norm / grad_norm, 1.0f);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = n / 4;
+  float4* p4 = reinterpret_cast<float4*>(param);
+  const float4* g4 = reinterpret_cast<const float4*>(pre);
+  const float4* v4 = reinterpret_cast<const float4*>(v);
+  for (int64_t i = tid; i < n4; i += stride) {
+    float4 P = p4[i];
+    const float4 G = g4[i];
+    float4 u = make_float4(lr * G.x, lr * G.y, lr * G.z, lr * G.w);
+    if (v) { const float4 X = v4[i]; u.x += X.x; u.y += X.y; u.z += X.z; u.w += X.w; }
+    P.x -= u.x; P.y -= u.y; P.z -= u.z; P.w -= u.w;
+    p4[i] = P;
+  }
+  for (int64_t i = n4 * 4 + tid; i < n; i += stride) {
+    float u = lr * pre[i];
+    if (v) u += v[i];
+    param[i] -= u;
+  }
+}
+
+// Tail of UVd.step (psgd.py:747-762): pre = P g, optional clipping by ||pre||_2, param -= lr pre (+ v).
+//   no clipping (max_norm = inf): the parameter update is fused into the second apply sweep -- pre_grad is never
+//                                 written unless the caller asks for it (pre_out);
+//   clipping: the second sweep writes pre_grad and reduces its sum of squares (all-reduced when sharded), a streaming
+//             kernel then applies the clipped learning rate computed on the device (no host sync).
+template <int R>
+static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* param,
+                          const float* v, float* pre_out, int64_t n, float lr_params, float max_norm, float tiny) {
+  PSGD_RETURN_IF(ensure_attrs<R>());
+  const int grid = grid_for(ctx, n);
+  const bool clip = !isinf(max_norm);
+  Scratch s;
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s, (clip && !pre_out) ? n : 0));
+  cudaStream_t st = ctx->stream;
+  SweepArgs a{};
+  a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
+  PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
+  constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
+  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
+  MapOut o{};
+  o.st = s.st;
+  if (!clip) {
+    a.vec[2] = param; a.vec[3] = v ? v : param;
+    o.o0 = param; o.o1 = pre_out; o.lr = lr_params; o.has_v = v ? 1 : 0;
+    return launch_map<R, kMapApplyParam>(ctx, a, o, 0, grid);
+  }
+  float* pre = pre_out ? pre_out : s.a;
+  o.o0 = pre; o.partial = s.partial;
+  PSGD_RETURN_IF((launch_map<R, kMapApplyNorm>(ctx, a, o, 0, grid)));
+  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, 1, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, 1, nullptr, 0));
+  clip_update_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(param, pre, v, n, lr_params, max_norm, tiny, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
 // IpUVtmatvec for one column: out = x + U (V^T x)
 template <int R>
 static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out, int64_t n) {
+  PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
@@ -932,7 +1066,7 @@ static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const floa
   constexpr int table = GramPlan<R, kMatvec>::W * GramPlan<R, kMatvec>::E;
   reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(hook_allreduce(ctx, s.G, table, 0));
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);   // p = V^T x (t unused)
   PSGD_LAUNCH_CHECK(ctx);
   SweepArgs a2{};
@@ -968,6 +1102,12 @@ int apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const f
   PSGD_RANK_SWITCH(r, CALL)
 #undef CALL
 }
+int step_tail(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* param, const float* v,
+              float* pre_out, int64_t n, int r, float lr_params, float max_norm, float tiny) {
+#define CALL(R) step_tail_impl<R>(ctx, U, V, d, g, param, v, pre_out, n, lr_params, max_norm, tiny)
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
+}
 int matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out, int64_t n, int r) {
 #define CALL(R) matvec_impl<R>(ctx, U, V, x, out, n)
   PSGD_RANK_SWITCH(r, CALL)
@@ -995,7 +1135,7 @@ extern "C" int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, cons
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd update: bad sizes n=%lld r=%d", (long long)n, r);
   // an empty shard still takes part in the cross-rank reductions when a hook is installed
-  if (n == 0 && !ctx->allreduce) return PSGD_OK;
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;
   const void* ptrs[] = {U, V, d, v, h};
   if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
@@ -1006,11 +1146,28 @@ extern "C" int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, con
                               float* out, int64_t n, int r) {
   PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
   PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd apply: bad sizes n=%lld r=%d", (long long)n, r);
-  if (n == 0 && !ctx->allreduce) return PSGD_OK;
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;
   const void* ptrs[] = {U, V, d, g, out};
   if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   return uvd::apply(ctx, U, V, d, g, out, n, r);
+}
+
+extern "C" int psgd_uvd_step_tail(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,
+                                  float* param, const float* v, float* pre_out, int64_t n, int r, float lr_params,
+                                  float grad_clip_max_norm, float tiny) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd step tail: bad sizes n=%lld r=%d", (long long)n, r);
+  PSGD_REQUIRE(grad_clip_max_norm > 0.f, PSGD_ERR_BAD_SHAPE, "UVd step tail: grad_clip_max_norm must be > 0 (inf = none)");
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;
+  const void* ptrs[] = {U, V, d, g, param};
+  if (n > 0) {
+    PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
+    PSGD_REQUIRE((!v || aligned16(v)) && (!pre_out || aligned16(pre_out)), PSGD_ERR_BAD_POINTER,
+                 "UVd step tail: v / pre_out must be 16-byte aligned");
+  }
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return uvd::step_tail(ctx, U, V, d, g, param, v, pre_out, n, r, lr_params, grad_clip_max_norm, tiny);
 }
 
 // strided column gather/scatter for k > 1 right-hand sides

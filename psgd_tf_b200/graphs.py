@@ -1,0 +1,75 @@
+"""CUDA-graph replay of the UVd update+apply step.
+
+One step of the UVd path is a fixed chain of ~12 kernels (3 sweeps + small r x r kernels for the update, 2 sweeps for
+the apply, plus one peer-exchange kernel per phase when the vector is sharded over GPUs, csrc/comm.cu).  At 100 M
+parameters on one GPU the chain runs ~7 ms and launch latency is noise; sharded 8 ways it runs < 1 ms and the ~12
+launches + two Python/ctypes calls become a visible fraction.  The chain has no host dependency (coin flips are
+arguments, the cross-rank epoch counter lives in device memory), so it is captured once per (input buffers, coin
+flips) and replayed with a single ``cudaGraphLaunch``.
+
+This is plumbing around the reference API, not a different algorithm: the graph contains exactly the kernels that
+``update_precond_UVd_math_`` (psgd.py:554-617) followed by ``precond_grad_UVd_math`` (psgd.py:619-627) launch.
+"""
+from __future__ import annotations
+
+from typing import Dict, Tuple
+
+import torch
+
+from . import psgd as _psgd
+
+
+class UVdStepGraphs:
+    """``step(v, h, g, balance, update_U)`` == ``update_precond_UVd_math_(U, V, d, v, h, step, tiny, ...)`` followed by
+    ``precond_grad_UVd_math(U, V, d, g)`` on the state tensors given at construction, replayed from a CUDA graph.
+
+    Graphs are keyed by the input buffers' addresses and the two coin flips, so callers should cycle through a fixed
+    set of (v, h, g) buffers (e.g. double-buffered uploads).  The first call for a shape runs eagerly (it sizes the
+    library workspace); later calls capture on first use of a key and replay afterwards.  The returned tensor belongs
+    to the graph: consume it before the same key is replayed again.
+    """
+
+    def __init__(self, U: torch.Tensor, V: torch.Tensor, d: torch.Tensor, step: float = 0.01, tiny: float = _psgd._tiny):
+        if not (U.is_cuda and V.is_cuda and d.is_cuda):
+            raise RuntimeError("UVdStepGraphs: state must live on a CUDA device (no CPU path)")
+        self.U, self.V, self.d = U, V, d
+        self.step_size, self.tiny = float(step), float(tiny)
+        self._stream = torch.cuda.Stream(device=U.device)
+        self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor]] = {}
+        self._warm = False
+        self._ws_bytes = -1
+        self.replays = 0
+
+    def _eager(self, v, h, g, balance, update_U):
+        _psgd.update_precond_UVd_math_(self.U, self.V, self.d, v, h, self.step_size, self.tiny, balance=balance,
+                                       update_U=update_U)
+        return _psgd.precond_grad_UVd_math(self.U, self.V, self.d, g)
+
+    def step(self, v: torch.Tensor, h: torch.Tensor, g: torch.Tensor, balance: bool, update_U: bool) -> torch.Tensor:
+        cur = torch.cuda.current_stream(self.U.device)
+        s = self._stream
+        s.wait_stream(cur)
+        with torch.cuda.stream(s):          # the library context follows torch's current stream
+            ctx = _psgd.get_context(self.U.device.index)      # switch (and drain) streams BEFORE any capture begins
+            if ctx.workspace_bytes != self._ws_bytes:
+                # the library workspace was re-allocated by a larger call since capture: its address is baked into
+                # the graphs, so they are stale
+                self._graphs.clear()
+                self._warm = False
+            if not self._warm:
+                out = self._eager(v, h, g, balance, update_U)
+                self._warm = True
+                self._ws_bytes = ctx.workspace_bytes
+            else:
+                key = (v.data_ptr(), h.data_ptr(), g.data_ptr(), bool(balance), bool(update_U))
+                entry = self._graphs.get(key)
+                if entry is None:
+                    graph = torch.cuda.CUDAGraph()
+                    with torch.cuda.graph(graph, stream=s):
+                        out = self._eager(v, h, g, balance, update_U)
+                    entry = self._graphs[key] = (graph, out)
+                graph, out = entry
+                graph.replay()
+                self.replays += 1
+        cur.wait_stream(s)
+        return out

@@ -44,6 +44,41 @@ def install_allreduce(ctx, group=None) -> None:
     ctx.set_allreduce(hook)
 
 
+def install_peer_exchange(ctx, group=None) -> None:
+    """Attach the library's peer-memory exchange (csrc/comm.cu) across the ranks of ``group`` (one process per GPU
+    on ONE NVSwitch box): every rank exports a small device slab through CUDA IPC, the 64-byte handles are
+    all-gathered with torch.distributed (host plumbing, once), and from then on each cross-rank reduction of the
+    sharded UVd / diagonal / X-shape paths is one tiny kernel that stores the partials straight into the peers'
+    slabs over NVLink and reduces in fixed rank order -- no host callback, no NCCL launch, CUDA-graph capturable,
+    bit-identical results on every rank.  Takes precedence over :func:`install_allreduce` while attached."""
+    import torch.distributed as dist
+
+    rank, world = dist.get_rank(group), dist.get_world_size(group)
+    handles = [None] * world
+    dist.all_gather_object(handles, ctx.comm_export(), group=group)
+    err = None
+    try:
+        ctx.comm_attach(rank, world, handles)
+    except Exception as e:              # keep the collective sequence identical on every rank
+        err = e
+    ok = torch.tensor([0.0 if err else 1.0], device=torch.device("cuda", ctx.device))
+    dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=group)   # also the barrier: every rank has mapped every slab
+    if ok.item() < 1:
+        ctx.comm_detach()
+        raise RuntimeError(f"peer-memory exchange unavailable on this box: {err or 'CUDA IPC failed on another rank'}")
+
+
+def install_exchange(ctx, group=None) -> str:
+    """Peer-memory exchange when CUDA IPC between the ranks works, else the torch.distributed hook.  Returns which."""
+    try:
+        install_peer_exchange(ctx, group)
+        return "peer-memory"
+    except RuntimeError as e:
+        print(f"psgd_tf_b200: {e}; using the torch.distributed all-reduce hook")
+    install_allreduce(ctx, group)
+    return "all-reduce hook"
+
+
 def chunk_bounds(n: int, world: int, rank: int, align: int = 256) -> Tuple[int, int]:
     """Contiguous row chunk [lo, hi) of rank ``rank``; chunk starts are multiples of ``align`` rows so every shard's
     U/V/d base pointers stay 16-byte aligned for the TMA bulk copies."""

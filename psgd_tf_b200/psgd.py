@@ -396,3 +396,154 @@ def precond_grad_Xmat(a, b, g):
     ctx = get_context(a.device.index)
     check(ctx.lib.psgd_xmat_apply(ctx.handle, _p(a), _p(b), _p(g), _p(out), n))
     return out
+
+
+# ---------------------------------------------------------------------------------------------
+# class UVd: the reference's stateful wrapper                                psgd.py:630-764
+# ---------------------------------------------------------------------------------------------
+class _Hyper:
+    """A mutable scalar hyper-parameter with the ``.assign`` spelling the reference's callers use on its
+    ``tf.Variable`` members (psgd.py:660-661 note 4; rnn_xor_UVd_preconditioner.py:62-69)."""
+
+    def __init__(self, value):
+        self.value = value
+
+    def assign(self, value):
+        self.value = value.value if isinstance(value, _Hyper) else value
+        return self
+
+    def numpy(self):
+        return self.value
+
+    def __float__(self):
+        return float(self.value)
+
+    def __bool__(self):
+        return bool(self.value)
+
+    def __repr__(self):
+        return f"_Hyper({self.value!r})"
+
+
+class UVd:
+    """Low-rank modification (UVd) preconditioner as a class -- mirror of psgd.py:630-764 for callers whose parameters
+    are CUDA torch tensors (torch.autograd plays the part of tf.GradientTape; it is plumbing, every preconditioner
+    operation runs in this package's CUDA kernels).
+
+    Same constructor arguments, hyper-parameter members (changed with ``.assign``, psgd.py note 4), state layout
+    (``_U, _V: [N, r]``, ``_d: [N, 1]``, ``uv_scale = (1/(N r))^0.5``, psgd.py:684-690) and ``step(closure)`` contract as
+    the reference.  Two additions:
+
+    * the parameters are re-homed into ONE flat device buffer (each ``param.data`` becomes a view of it), so the tail
+      of ``step`` -- preconditioned gradient, optional clipping, ``param -= lr * pre_grad (+ v)`` (psgd.py:747-762) --
+      is the fused ``psgd_uvd_step_tail`` call: without clipping the preconditioned gradient is never materialised;
+    * ``step_with(grads, vs, Hvs)`` exposes that hot path to callers that bring their own gradients and
+      Hessian-vector products (another autodiff system, or a TF caller through DLPack).
+    """
+
+    def __init__(self, params_with_grad, rank_of_modification: int = 10, preconditioner_init_scale=1.0,
+                 lr_params=0.01, lr_preconditioner=0.01, grad_clip_max_norm=None,
+                 preconditioner_update_probability=1.0, exact_hessian_vector_product: bool = True):
+        params = [params_with_grad] if isinstance(params_with_grad, torch.Tensor) else list(params_with_grad)
+        flat_list = []
+        for p in params:                                   # tf.nest.flatten (psgd.py:669)
+            flat_list.extend(p if isinstance(p, (list, tuple)) else [p])
+        self._params_with_grad = [p for p in flat_list if p.requires_grad]            # psgd.py:670
+        if not self._params_with_grad:
+            raise ValueError("UVd: no parameter requires gradients")
+        for p in self._params_with_grad:
+            _as_tensor(p, "params_with_grad")
+        self._dtype = self._params_with_grad[0].dtype
+        dev = self._params_with_grad[0].device
+        self.lr_params = _Hyper(lr_params)
+        self.lr_preconditioner = _Hyper(lr_preconditioner)
+        self.grad_clip_max_norm = _Hyper(float("inf") if grad_clip_max_norm is None else grad_clip_max_norm)   # psgd.py:675-678
+        self.preconditioner_update_probability = _Hyper(preconditioner_update_probability)
+        self.exact_hessian_vector_product = _Hyper(bool(exact_hessian_vector_product))
+        self._tiny = _tiny                                                             # psgd.py:682
+        self._delta_param_scale = float(2.0 ** -23) ** 0.5                             # psgd.py:683: sqrt(eps)
+        self._param_sizes = [p.numel() for p in self._params_with_grad]
+        self._param_cumsizes = []
+        tot = 0
+        for s in self._param_sizes:
+            tot += s
+            self._param_cumsizes.append(tot)
+        num_params = tot
+        # one flat buffer holding every parameter; each param becomes a view (same values, same shapes)
+        self._flat_params = torch.empty(num_params, device=dev, dtype=torch.float32)
+        off = 0
+        with torch.no_grad():
+            for p, s in zip(self._params_with_grad, self._param_sizes):
+                self._flat_params[off: off + s].copy_(p.detach().reshape(-1))
+                p.data = self._flat_params[off: off + s].view(p.shape)
+                off += s
+        uv_scale = (1.0 / (num_params * rank_of_modification)) ** 0.5                 # psgd.py:687
+        self._U = torch.randn(num_params, rank_of_modification, device=dev, dtype=torch.float32) * uv_scale
+        self._V = torch.randn(num_params, rank_of_modification, device=dev, dtype=torch.float32) * uv_scale
+        self._d = torch.ones(num_params, 1, device=dev, dtype=torch.float32) * preconditioner_init_scale
+
+    # -- the hot path, autodiff-agnostic -----------------------------------------------------------
+    @staticmethod
+    def _flatten(ts):
+        ts = [_in(t, "tensor").reshape(-1) for t in ts]
+        return ts[0] if len(ts) == 1 else torch.cat(ts)                               # psgd.py:729-730, :747
+
+    def step_with(self, grads, vs=None, Hvs=None, params_perturbed: bool = False, *, balance=None, update_U=None,
+                  return_pre_grad: bool = False):
+        """Preconditioner update with ``(vs, Hvs)`` when given (psgd.py:729-736), then preconditioned gradient,
+        optional clipping and parameter update (psgd.py:747-762).  ``grads``/``vs``/``Hvs``: lists shaped like the
+        parameters, or single flat tensors.  ``params_perturbed``: the parameters currently hold ``param + v`` (the
+        finite-difference mode, psgd.py:717-718), so ``v`` is removed again by the update (psgd.py:760-762)."""
+        flat = lambda x: self._flatten(x if isinstance(x, (list, tuple)) else [x])
+        n, r = self._U.shape
+        v = None
+        if vs is not None:
+            v, h = flat(vs), flat(Hvs)
+            if params_perturbed:      # compensate the levels of v and h (psgd.py:734-736)
+                update_precond_UVd_math_(self._U, self._V, self._d, v / self._delta_param_scale, h / self._delta_param_scale,
+                                         float(self.lr_preconditioner), self._tiny, balance=balance, update_U=update_U)
+            else:
+                update_precond_UVd_math_(self._U, self._V, self._d, v, h, float(self.lr_preconditioner), self._tiny,
+                                         balance=balance, update_U=update_U)
+        g = flat(grads)
+        _col(g, n, "grads")
+        pre = torch.empty_like(g) if return_pre_grad else None
+        ctx = get_context(self._U.device.index)
+        vp = _p(v) if (params_perturbed and v is not None) else None
+        check(ctx.lib.psgd_uvd_step_tail(ctx.handle, _p(self._U), _p(self._V), _p(self._d), _p(g), _p(self._flat_params),
+                                         vp, _p(pre) if pre is not None else None, n, r, float(self.lr_params),
+                                         float(self.grad_clip_max_norm), self._tiny))
+        return pre
+
+    # -- the reference's step(closure), with torch.autograd in the role of tf.GradientTape ------------------------
+    def step(self, closure):
+        """psgd.py:692-764.  ``closure`` evaluates the loss of the parameters (a scalar tensor, or an iterable whose
+        first element is the loss); whatever it returns is handed back unchanged."""
+        params = self._params_with_grad
+        first = lambda ret: ret if isinstance(ret, torch.Tensor) else ret[0]
+        if _rng.random() < float(self.preconditioner_update_probability):               # psgd.py:703
+            if bool(self.exact_hessian_vector_product):                                # psgd.py:706-714
+                with torch.enable_grad():
+                    closure_returns = closure()
+                    grads = torch.autograd.grad(first(closure_returns), params, create_graph=True)
+                    vs = [torch.randn_like(p) for p in params]
+                    Hvs = torch.autograd.grad(grads, params, vs)
+                grads = [g.detach() for g in grads]
+                self.step_with(grads, vs, Hvs, params_perturbed=False)
+            else:                                                                      # psgd.py:715-727
+                with torch.enable_grad():
+                    closure_returns = closure()
+                    grads = torch.autograd.grad(first(closure_returns), params)
+                vs = [torch.randn_like(p) * self._delta_param_scale for p in params]
+                with torch.no_grad():
+                    self._flat_params.add_(self._flatten(vs))
+                with torch.enable_grad():
+                    perturbed_grads = torch.autograd.grad(first(closure()), params)
+                Hvs = [pg - g for pg, g in zip(perturbed_grads, grads)]
+                self.step_with(grads, vs, Hvs, params_perturbed=True)
+        else:                                                                          # psgd.py:737-744
+            with torch.enable_grad():
+                closure_returns = closure()
+                grads = torch.autograd.grad(first(closure_returns), params)
+            self.step_with(grads)
+        return closure_returns

@@ -80,12 +80,15 @@ def cpu_protocol(rank, world):
     np.testing.assert_allclose(d_new, dr[lo:hi, 0], rtol=1e-9)
 
 
-def gpu_uvd(rank, world):
+def gpu_uvd(rank, world, exchange="hook"):
     import psgd_tf_b200 as psgd
     from psgd_tf_b200 import partition
     torch.cuda.set_device(rank)
     ctx = psgd.get_context(rank)
-    partition.install_allreduce(ctx)
+    if exchange == "peer":
+        partition.install_peer_exchange(ctx)      # must work on a multi-GPU box: no silent fallback in this test
+    else:
+        partition.install_allreduce(ctx)
     dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
     for n, r in ((100_003, 10), (1021, 10), (5000, 16)):
         c = cases.uvd_case(600 + n, n, r)
@@ -108,7 +111,38 @@ def gpu_uvd(rank, world):
     psgd.update_precond_diag(q, dev(c["v"][lo:hi]), dev(c["h"][lo:hi]), 0.01)
     want = O.update_precond_diag(c["a"], c["v"], c["h"], 0.01)
     assert np.allclose(q.cpu().numpy(), want[lo:hi], rtol=1e-5)
-    ctx.set_allreduce(None)
+    if exchange == "peer":
+        done = ctx.comm_status()                  # raises if any in-kernel wait timed out
+        assert done == 3 * (3 + 4) + 1, done        # per size: 2+1 exchanges (plain step) + 3+1 (balance step); + diag
+        gpu_uvd_graph(rank, world, ctx)
+        ctx.comm_detach()
+    else:
+        ctx.set_allreduce(None)
+
+
+def gpu_uvd_graph(rank, world, ctx):
+    """The sharded step replayed from CUDA graphs (peer exchange inside the graph) is bit-identical to the eager one."""
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+    from psgd_tf_b200.graphs import UVdStepGraphs
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    n, r = 300_007, 10
+    c = cases.uvd_case(77, n, r)
+    lo, hi = partition.chunk_bounds(n, world, rank)
+    ins = [tuple(dev(np.roll(c[k][lo:hi], s, 0)) for k in ("v", "h", "g")) for s in (0, 1)]
+    Ue, Ve, de = dev(c["U"][lo:hi]), dev(c["V"][lo:hi]), dev(c["d"][lo:hi])
+    Ug, Vg, dg = Ue.clone(), Ve.clone(), de.clone()
+    gs = UVdStepGraphs(Ug, Vg, dg, 0.01)
+    e0 = ctx.comm_status()
+    for i in range(8):
+        v, h, g = ins[i % 2]
+        psgd.update_precond_UVd_math_(Ue, Ve, de, v, h, 0.01, psgd._tiny, balance=False, update_U=(i % 2 == 0))
+        want = psgd.precond_grad_UVd_math(Ue, Ve, de, g)
+        got = gs.step(v, h, g, False, i % 2 == 0)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want) and torch.equal(Ug, Ue) and torch.equal(Vg, Ve) and torch.equal(dg, de), i
+    assert gs.replays >= 5, gs.replays
+    assert ctx.comm_status() - e0 == 8 * 2 * 3, (ctx.comm_status(), e0)   # 3 exchanges per update+apply, eager + graph
 
 
 def gpu_kron(rank, world):
@@ -141,7 +175,10 @@ def main():
     else:
         torch.cuda.set_device(rank)
         dist.init_process_group("nccl", device_id=torch.device("cuda", rank))
-        {"gpu-uvd": gpu_uvd, "gpu-kron": gpu_kron}[mode](rank, world)
+        if mode == "gpu-uvd-peer":
+            gpu_uvd(rank, world, exchange="peer")
+        else:
+            {"gpu-uvd": gpu_uvd, "gpu-kron": gpu_kron}[mode](rank, world)
     dist.barrier()
     dist.destroy_process_group()
     if rank == 0:

@@ -35,7 +35,7 @@ def _ngpu():
 
 
 @pytest.mark.gpu
-@pytest.mark.parametrize("mode", ["gpu-uvd", "gpu-kron"])
+@pytest.mark.parametrize("mode", ["gpu-uvd", "gpu-uvd-peer", "gpu-kron"])
 def test_sharded_cuda_paths_two_gpus(mode):
     if _ngpu() < 2:
         pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")

@@ -77,6 +77,27 @@ def test_uvd_update_and_apply(psgd, n, r, direct):
         ctx.set_option("direct", 0)
 
 
+def test_uvd_step_graph_replay_matches_eager(psgd):
+    """graphs.UVdStepGraphs replays exactly the kernels of update + apply: bit-identical state and output."""
+    from psgd_tf_b200.graphs import UVdStepGraphs
+    n, r = 50_021, 10
+    c = cases.uvd_case(4242, n, r)
+    ins = [tuple(dev(np.roll(c[k], s, 0)) for k in ("v", "h", "g")) for s in (0, 3)]
+    Ue, Ve, de = dev(c["U"]), dev(c["V"]), dev(c["d"])
+    Ug, Vg, dg = Ue.clone(), Ve.clone(), de.clone()
+    gs = UVdStepGraphs(Ug, Vg, dg, 0.01)
+    for i in range(9):
+        v, h, g = ins[i % 2]
+        flips = dict(balance=(i == 6), update_U=(i % 3 != 0))
+        psgd.update_precond_UVd_math_(Ue, Ve, de, v, h, 0.01, psgd._tiny, **flips)
+        want = psgd.precond_grad_UVd_math(Ue, Ve, de, g)
+        got = gs.step(v, h, g, **flips)
+        torch.cuda.synchronize()
+        assert torch.equal(got, want), i
+        assert torch.equal(Ug, Ue) and torch.equal(Vg, Ve) and torch.equal(dg, de), i
+    assert gs.replays >= 6
+
+
 def test_uvd_golden(psgd):
     for seed, n, r in MG.UVD_GOLDEN:
         c = cases.uvd_case(seed, n, r)
