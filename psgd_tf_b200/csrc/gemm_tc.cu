@@ -7,8 +7,13 @@
 //
 // Kernel anatomy (one persistent CTA per SM, 10 warps, warp-specialised):
 //   warp 0      TMA producer   cp.async.bulk.tensor 2D (SWIZZLE_128B) of raw fp32 operand tiles -> shared memory
-//   warps 6-9   splitter       hi = rna_tf32(x) (in place), lo = rna_tf32(x - hi) (second tile): the 3xTF32 split is
-//                              done on chip, so operands are read from HBM/L2 exactly once, as plain fp32
+//   warps 6-9   splitter       hi = rna_tf32(x), lo = rna_tf32(x - hi): the 3xTF32 split is done on chip, so operands
+//                              are read from HBM/L2 exactly once, as plain fp32.  B is split in shared memory (hi in
+//                              place, lo in a second tile).  A is split in REGISTERS and stored to TENSOR MEMORY
+//                              (tcgen05.st; one thread per A row = TMEM lane), so the tensor core reads A from TMEM
+//                              ("TS" mode) and A never costs shared-memory bandwidth again -- the kernel is bound by
+//                              shared-memory bandwidth (ncu: profiles/), and this takes the per-stage traffic from
+//                              224 KB to 144 KB.  An MN-major A (transpose_a) is transposed by the same register pass.
 //   warp 1      MMA issuer     one lane issues tcgen05.mma.kind::tf32: lo*hi + hi*lo + hi*hi per K=8 atom, fp32
 //                              accumulators in TMEM (double buffered: 2 x BN columns)
 //   warps 2-5   epilogue       tcgen05.ld -> registers -> triu mask / max|.| / (D - mu*acc) / column scale -> global
@@ -33,14 +38,23 @@ constexpr int kThreads = 320;          // 10 warps
 constexpr int kEpiWarp0 = 2, kSplitWarp0 = 6;
 constexpr int kChunkKB = 4;            // K-blocks (of 32) per tensor-core accumulation chain
 
-template <int BN>
+// TS = true : A operand through tensor memory.  Stage = [A raw | B hi | B lo]; TMEM = 2 accumulators (2 x BN columns)
+//             + per stage 32 columns of A hi and 32 of A lo (BK = 32 tf32 values per row).
+// TS = false: both operands from shared memory ("SS").  Stage = [A hi | B hi | A lo | B lo].
+template <int BN, bool TS>
 struct Cfg {
-  static constexpr int kStages = (BN == 256) ? 2 : 3;
+  static constexpr int kStages = TS ? 4 : ((BN == 256) ? 2 : 3);
   static constexpr int kTileABytes = BM * BK * 4;             // 16 KB
   static constexpr int kTileBBytes = BN * BK * 4;
-  static constexpr int kStageBytes = 2 * (kTileABytes + kTileBBytes);   // raw(hi) + lo
+  static constexpr int kStageBytes = TS ? (kTileABytes + 2 * kTileBBytes) : 2 * (kTileABytes + kTileBBytes);
   static constexpr int kTxBytes = kTileABytes + kTileBBytes;
-  static constexpr int kTmemCols = 2 * BN;
+  static constexpr int kBHiOff = kTileABytes;
+  static constexpr int kBLoOff = TS ? (kTileABytes + kTileBBytes) : (2 * kTileABytes + kTileBBytes);
+  static constexpr int kALoOff = kTileABytes + kTileBBytes;   // SS only
+  static constexpr int kAccCols = 2 * BN;
+  static constexpr int kATmemCol0 = kAccCols;                 // TS only: first column of the A stages
+  static constexpr int kTmemCols = TS ? 512 : 2 * BN;
+  static_assert(!TS || kAccCols + kStages * 2 * BK <= 512, "TMEM budget");
   static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 };
 
@@ -104,6 +118,31 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t desc_a, uint
       "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// D[tmem] (+)= A[tmem] * B[smem]: A is [128 lanes = rows] x [8 columns = K values] of 32-bit tf32, K-major only
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                             uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// 32 registers per thread -> 32 lanes x 32 consecutive columns (thread i of the warp owns lane base+i)
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+      "{%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, "
+      "%17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31, %32};" ::"r"(taddr),
+      "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]), "r"(r[9]),
+      "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]), "r"(r[18]),
+      "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]), "r"(r[27]),
+      "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
 // 32 lanes x 32 consecutive columns -> 32 registers per thread
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32]) {
   asm volatile(
@@ -154,10 +193,38 @@ __device__ __forceinline__ uint32_t make_idesc(int n, int a_mn, int b_mn, int ne
   return d;
 }
 
-__device__ __forceinline__ float to_tf32_rna(float x) {
-  uint32_t r;
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
-  return __uint_as_float(r);
+// 3xTF32 split of one fp32 value: hi = x rounded to tf32 (nearest, ties away from zero -- exactly cvt.rna.tf32.f32 for
+// finite values: add half an ulp of the 10-bit mantissa to the sign-magnitude bit pattern and drop the low 13 bits;
+// two integer ops where ptxas expands the cvt to four with its Inf/NaN select), lo = x - hi (exact in fp32).  lo is
+// handed to the tensor core unrounded: kind::tf32 ignores the low 13 mantissa bits of its operands, which truncates
+// lo at 2^-21 |x| -- below the dropped lo*lo term.
+__device__ __forceinline__ void split_tf32(uint32_t x, uint32_t& hi, uint32_t& lo) {
+  hi = (x + 0x1000u) & 0xffffe000u;
+  lo = __float_as_uint(__uint_as_float(x) - __uint_as_float(hi));
+}
+__device__ __forceinline__ uint4 lds128(uint32_t addr) {
+  uint4 v;
+  asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t addr) {
+  uint32_t v;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");
+  return v;
+}
+__device__ __forceinline__ void sts128(uint32_t addr, const uint4& v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+}
+// in-place hi + second-tile lo for `bytes` of raw fp32 in shared memory, 128 threads, conflict-free 16-byte accesses
+__device__ __forceinline__ void split_tile_smem(uint32_t hi_addr, uint32_t lo_addr, int bytes, int st) {
+#pragma unroll 4
+  for (int off = st * 16; off < bytes; off += 128 * 16) {
+    const uint4 x = lds128(hi_addr + off);
+    uint4 h, l;
+    split_tf32(x.x, h.x, l.x); split_tf32(x.y, h.y, l.y); split_tf32(x.z, h.z, l.z); split_tf32(x.w, h.w, l.w);
+    sts128(hi_addr + off, h);
+    sts128(lo_addr + off, l);
+  }
 }
 
 // K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
@@ -176,10 +243,10 @@ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n
   if (kb1 < kb0) kb1 = kb0;
 }
 
-template <int BN>
+template <int BN, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ Params p) {
-  using C = Cfg<BN>;
+  using C = Cfg<BN, TS>;
   extern __shared__ unsigned char smem_raw[];
   // SWIZZLE_128B tiles need 1024-byte alignment
   unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
@@ -215,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   const int num_tiles = tiles_per * p.count;
 
   auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
-  // stage layout: [A hi | B hi | A lo | B lo]
+  // stage layout: SS [A hi | B hi | A lo | B lo], TS [A raw | B hi | B lo]
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
@@ -285,7 +352,8 @@ __global__ void __launch_bounds__(kThreads, 1)
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
           k_range<BN>(p, prod, m0, n0, kb0, kb1);
-          const uint32_t idesc = make_idesc(BN, p.a_mn[prod], p.b_mn[prod], prod);   // product 1 is subtracted
+          // product 1 is subtracted (a_negate); an A operand in TMEM is always K-major (the splitter transposes)
+          const uint32_t idesc = make_idesc(BN, TS ? 0 : p.a_mn[prod], p.b_mn[prod], prod);
           for (int kb = kb0; kb < kb1; ++kb, ++it, ++done) {
             const int s = it % C::kStages;
             const uint32_t ph = (it / C::kStages) & 1;
@@ -299,20 +367,35 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             mbar_wait(&conv[s], ph);
             tc_fence_after();
-            const uint32_t a_hi = smem_u32(stage_ptr(s));
-            const uint32_t b_hi = a_hi + C::kTileABytes;
-            const uint32_t a_lo = b_hi + C::kTileBBytes;
-            const uint32_t b_lo = a_lo + C::kTileABytes;
+            const uint32_t st_base = smem_u32(stage_ptr(s));
+            const uint32_t b_hi = st_base + C::kBHiOff;
+            const uint32_t b_lo = st_base + C::kBLoOff;
+            if constexpr (TS) {
+              const uint32_t a_hi_t = tmem_base + (uint32_t)(C::kATmemCol0 + s * 2 * BK);   // lane 0, this stage's A hi
+              const uint32_t a_lo_t = a_hi_t + BK;
 #pragma unroll
-            for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-              const uint64_t dah = operand_desc(a_hi, p.a_mn[prod], kk);
-              const uint64_t dal = operand_desc(a_lo, p.a_mn[prod], kk);
-              const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
-              const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
-              umma_tf32(tmem_d, dal, dbh, idesc, accumulate);     // small terms first
-              umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-              umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-              accumulate = 1u;
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
+                const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
+                umma_tf32_ts(tmem_d, a_lo_t + kk * UMMA_K, dbh, idesc, accumulate);     // small terms first
+                umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbl, idesc, 1u);
+                umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbh, idesc, 1u);
+                accumulate = 1u;
+              }
+            } else {
+              const uint32_t a_hi = st_base;
+              const uint32_t a_lo = st_base + C::kALoOff;
+#pragma unroll
+              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                const uint64_t dah = operand_desc(a_hi, p.a_mn[prod], kk);
+                const uint64_t dal = operand_desc(a_lo, p.a_mn[prod], kk);
+                const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
+                const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
+                umma_tf32(tmem_d, dal, dbh, idesc, accumulate);     // small terms first
+                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
+                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
+                accumulate = 1u;
+              }
             }
             umma_commit(&empty[s]);                               // frees the stage when these MMAs retire
             if (++in_chunk == kChunkKB || done + 1 == total_kb) {
@@ -341,17 +424,38 @@ __global__ void __launch_bounds__(kThreads, 1)
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
           mbar_wait(&full[s], ph);
-          float4* hi = reinterpret_cast<float4*>(stage_ptr(s));
-          float4* lo = reinterpret_cast<float4*>(stage_ptr(s) + C::kTxBytes);
-#pragma unroll 4
-          for (int i = st; i < C::kTxBytes / 16; i += 128) {
-            const float4 x = hi[i];
-            float4 h, l;
-            h.x = to_tf32_rna(x.x); h.y = to_tf32_rna(x.y); h.z = to_tf32_rna(x.z); h.w = to_tf32_rna(x.w);
-            l.x = to_tf32_rna(x.x - h.x); l.y = to_tf32_rna(x.y - h.y);
-            l.z = to_tf32_rna(x.z - h.z); l.w = to_tf32_rna(x.w - h.w);
-            hi[i] = h;
-            lo[i] = l;
+          if constexpr (TS) {
+            // ---- A: this thread owns row m = TMEM lane (warp & 3) * 32 + lane; 32 K values -> registers -> TMEM
+            const uint32_t sa = smem_u32(stage_ptr(s));
+            const int row = (warp & 3) * 32 + lane;
+            uint32_t ahi[32], alo[32];
+            if (!p.a_mn[prod]) {
+              // K-major tile, SWIZZLE_128B: row m is 128 B at m*128, its 16-byte chunk c sits at position c ^ (m & 7)
+              const uint32_t rp = sa + row * 128;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) {
+                const uint4 x = lds128(rp + ((c ^ (row & 7)) << 4));
+                split_tf32(x.x, ahi[4 * c], alo[4 * c]);         split_tf32(x.y, ahi[4 * c + 1], alo[4 * c + 1]);
+                split_tf32(x.z, ahi[4 * c + 2], alo[4 * c + 2]); split_tf32(x.w, ahi[4 * c + 3], alo[4 * c + 3]);
+              }
+            } else {
+              // MN-major tile: four [32 k][32 m] blocks of 128-byte rows, SWIZZLE_128B_ATOM_32B (32-byte atom index
+              // XOR (k & 3)); reading column m of every k row is the transposition (lanes hit 32 distinct banks)
+              const uint32_t blk = sa + (row >> 5) * 4096;
+              const int mb = (row & 31) * 4;
+#pragma unroll
+              for (int k = 0; k < 32; ++k) split_tf32(lds32(blk + k * 128 + (mb ^ ((k & 3) << 5))), ahi[k], alo[k]);
+            }
+            const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::kATmemCol0 + s * 2 * BK);
+            tmem_st32(t_a, ahi);
+            tmem_st32(t_a + BK, alo);
+            // ---- B: split in shared memory (hi in place, lo in the second tile)
+            split_tile_smem(sa + C::kBHiOff, sa + C::kBLoOff, C::kTileBBytes, st);
+            tmem_st_wait();
+            tc_fence_before();              // TMEM stores ordered before the MMA issuer's tcgen05.mma (via conv[s])
+          } else {
+            const uint32_t sa = smem_u32(stage_ptr(s));
+            split_tile_smem(sa, sa + C::kTxBytes, C::kTxBytes, st);
           }
           fence_proxy_async_smem();       // generic-proxy writes -> visible to tcgen05 (async proxy)
           __syncwarp();
@@ -508,9 +612,9 @@ static bool same_shape(const la::Gemm& x, const la::Gemm& y) {
 }
 
 // gs[0..count): identical shapes/flags, count <= kMaxGroup
-template <int BN>
-static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
-  using C = Cfg<BN>;
+template <int BN, bool TS>
+static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
+  using C = Cfg<BN, TS>;
   const la::Gemm& g = gs[0];
   static thread_local Params p;            // large by-value kernel parameters: keep them off the stack
   static thread_local GroupMaps maps;
@@ -549,7 +653,7 @@ static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
       else               PSGD_RETURN_IF(make_map(tb, B, K, q.N, ldb, BK, true));      // [K,N], box {32n, 32k}
     }
   }
-  auto kern = gemm_tc_kernel<BN>;
+  auto kern = gemm_tc_kernel<BN, TS>;
   static bool attr_done = false;
   if (!attr_done) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
@@ -561,6 +665,12 @@ static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(maps, p);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
+}
+
+// opt_tc_mode: 1 (default) = A operand through tensor memory ("TS"), 0 = both operands from shared memory ("SS")
+template <int BN>
+static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
+  return ctx->opt_tc_mode ? launch_impl<BN, true>(ctx, gs, count) : launch_impl<BN, false>(ctx, gs, count);
 }
 
 int gemm_tc(psgd_ctx* ctx, const la::Gemm& g) {

@@ -10,8 +10,9 @@ torch.manual_seed(0)
 ctx = psgd.get_context()
 
 
-def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128):
+def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128, mode=1):
     ctx.set_option("tc_bn", bn)
+    ctx.set_option("tc_mode", mode)
     A = torch.randn((K, M) if ta else (M, K), device="cuda")
     B = torch.randn((N, K) if tb else (K, N), device="cuda")
     if a_tri:
@@ -32,7 +33,7 @@ def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128):
     err = (Cm.double() - ref)
     rel = (err.norm() / ref.norm()).item()
     nan = torch.isnan(Cm).sum().item()
-    msg = f"M={M} N={N} K={K} ta={ta} tb={tb} eng={engine} bn={bn} triu={triu} tri=({a_tri},{b_tri}): rel={rel:.3e} nan={nan}"
+    msg = f"M={M} N={N} K={K} ta={ta} tb={tb} eng={engine} mode={'TS' if mode else 'SS'} triu={triu} tri=({a_tri},{b_tri}): rel={rel:.3e} nan={nan}"
     if not (rel < 1e-5):
         # where are the errors? per 32x32 block
         e = torch.nan_to_num(err, nan=1e3).abs()
@@ -50,19 +51,21 @@ if __name__ == "__main__":
     which = sys.argv[1] if len(sys.argv) > 1 else "basic"
     if which == "basic":
         run(256, 256, 256, 0, 1, engine=1)
-        for ta, tb in ((0, 1), (1, 1), (0, 0), (1, 0)):
-            run(256, 256, 256, ta, tb)
-        for ta, tb in ((0, 1), (1, 0)):
-            run(384, 640, 320, ta, tb)
-            run(1000, 520, 264, ta, tb)
-            run(512, 512, 512, ta, tb, bn=256)
-        run(512, 512, 512, 0, 1, triu=1)
-        run(512, 512, 512, 0, 0, a_tri=1, b_tri=1, triu=1)
-        run(4096, 4096, 4096, 0, 1)
+        for mode in (1, 0):
+            for ta, tb in ((0, 1), (1, 1), (0, 0), (1, 0)):
+                run(256, 256, 256, ta, tb, mode=mode)
+            for ta, tb in ((0, 1), (1, 0)):
+                run(384, 640, 320, ta, tb, mode=mode)
+                run(1000, 520, 264, ta, tb, mode=mode)
+            run(512, 512, 512, 0, 1, triu=1, mode=mode)
+            run(512, 512, 512, 0, 0, a_tri=1, b_tri=1, triu=1, mode=mode)
+            run(100, 4096, 2048, 1, 0, mode=mode)
+            run(4096, 4096, 4096, 0, 1, mode=mode)
     elif which == "perf":
         import time
-        for bn in (128, 256):
-            ctx.set_option("tc_bn", bn)
+        for mode in (1, 0):
+            ctx.set_option("tc_mode", mode)
+            bn = "TS" if mode else "SS"
             for (ta, tb) in ((0, 1), (0, 0), (1, 0)):
                 M = N = K = 4096
                 A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda"); Cm = torch.empty(M, N, device="cuda")
@@ -76,7 +79,7 @@ if __name__ == "__main__":
                     check(ctx.lib.psgd_gemm(*args))
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 10
-                print(f"bn={bn} ta={ta} tb={tb}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent "
+                print(f"mode={bn} ta={ta} tb={tb}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:.1f} TFLOP/s fp32-equivalent "
                       f"({3 * 2 * M * N * K / ms / 1e9:.1f} TF32 TFLOP/s issued)", flush=True)
         # cuBLAS TF32 calibration (roofline denominator; calibration only, not on the product path)
         torch.backends.cuda.matmul.allow_tf32 = True
