@@ -91,6 +91,7 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
     ctx->opt_tc_bn = (int)value;
     return PSGD_OK;
   }
+  if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }
   if (strcmp(key, "tc_mode") == 0) { ctx->opt_tc_mode = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "gemm_path") == 0) {
     PSGD_REQUIRE(value >= 0 && value <= 2, PSGD_ERR_BAD_SHAPE, "gemm_path must be 0 (auto), 1 (simt) or 2 (tcgen05)");

@@ -76,6 +76,7 @@ struct Params {
   float step, tiny;
   int colscale_recip, colscale_sq;
   int tiles_m, tiles_n, count;
+  int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs
   float* C[kMaxGroup];
   float* maxabs[kMaxGroup];
   const float* D[kMaxGroup];
@@ -99,6 +100,20 @@ __device__ __forceinline__ void tmem_alloc(uint32_t* smem_dst, uint32_t cols) {
 }
 __device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t cols) {
   asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// One lane of a fully converged warp.  Guarding the single-thread tcgen05 / TMA instructions with elect.sync (rather than
+// `lane == 0`) lets ptxas know exactly one lane is active, so their uniform-register operands need no per-lane
+// serialisation loop (with `lane == 0` every UTCHMMA was wrapped in an ELECT/BRA.U.ANY loop, ~20 extra instructions).
+__device__ __forceinline__ bool elect_one_sync() {
+  uint32_t pred = 0;
+  asm volatile(
+      "{\n"
+      ".reg .pred P;\n"
+      "elect.sync _|P, 0xffffffff;\n"
+      "selp.u32 %0, 1, 0, P;\n"
+      "}\n"
+      : "=r"(pred));
+  return pred != 0;
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -286,7 +301,7 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   if (warp == 0) {
     // ===================================== TMA producer =====================================
-    if (lane == 0) {
+    if (elect_one_sync()) {
       int it = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int grp = tile / tiles_per, lt = tile % tiles_per;
@@ -326,7 +341,8 @@ __global__ void __launch_bounds__(kThreads, 1)
     __syncwarp();
   } else if (warp == 1) {
     // ===================================== MMA issuer =======================================
-    if (lane == 0) {
+    // The whole warp walks the schedule (uniform control flow, all lanes poll the barriers); one elected lane issues.
+    {
       int it = 0, tcount = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int grp = tile / tiles_per, lt = tile % tiles_per;
@@ -354,6 +370,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           k_range<BN>(p, prod, m0, n0, kb0, kb1);
           // product 1 is subtracted (a_negate); an A operand in TMEM is always K-major (the splitter transposes)
           const uint32_t idesc = make_idesc(BN, TS ? 0 : p.a_mn[prod], p.b_mn[prod], prod);
+          // descriptors of K atom kk = descriptor of atom 0 + kk * step (start-address field, 16-byte units)
+          const uint64_t b_step = p.b_mn[prod] ? (1024 >> 4) : (32 >> 4);
+          const uint64_t a_step = p.a_mn[prod] ? (1024 >> 4) : (32 >> 4);
           for (int kb = kb0; kb < kb1; ++kb, ++it, ++done) {
             const int s = it % C::kStages;
             const uint32_t ph = (it / C::kStages) & 1;
@@ -367,46 +386,44 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             mbar_wait(&conv[s], ph);
             tc_fence_after();
-            const uint32_t st_base = smem_u32(stage_ptr(s));
-            const uint32_t b_hi = st_base + C::kBHiOff;
-            const uint32_t b_lo = st_base + C::kBLoOff;
-            if constexpr (TS) {
-              const uint32_t a_hi_t = tmem_base + (uint32_t)(C::kATmemCol0 + s * 2 * BK);   // lane 0, this stage's A hi
-              const uint32_t a_lo_t = a_hi_t + BK;
+            const bool chunk_end = (in_chunk + 1 == kChunkKB) || (done + 1 == total_kb);
+            if (elect_one_sync()) {
+              const uint32_t st_base = smem_u32(stage_ptr(s));
+              const uint64_t dbh0 = operand_desc(st_base + C::kBHiOff, p.b_mn[prod], 0);
+              const uint64_t dbl0 = operand_desc(st_base + C::kBLoOff, p.b_mn[prod], 0);
+              uint32_t acc = accumulate;
+              if (p.debug & 4) {
+              } else if constexpr (TS) {
+                const uint32_t a_hi_t = tmem_base + (uint32_t)(C::kATmemCol0 + s * 2 * BK);   // lane 0, this stage's A hi
+                const uint32_t a_lo_t = a_hi_t + BK;
 #pragma unroll
-              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
-                const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
-                umma_tf32_ts(tmem_d, a_lo_t + kk * UMMA_K, dbh, idesc, accumulate);     // small terms first
-                umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbl, idesc, 1u);
-                umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbh, idesc, 1u);
-                accumulate = 1u;
-              }
-            } else {
-              const uint32_t a_hi = st_base;
-              const uint32_t a_lo = st_base + C::kALoOff;
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                  umma_tf32_ts(tmem_d, a_lo_t + kk * UMMA_K, dbh0 + kk * b_step, idesc, acc);     // small terms first
+                  umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbl0 + kk * b_step, idesc, 1u);
+                  umma_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbh0 + kk * b_step, idesc, 1u);
+                  acc = 1u;
+                }
+              } else {
+                const uint64_t dah0 = operand_desc(st_base, p.a_mn[prod], 0);
+                const uint64_t dal0 = operand_desc(st_base + C::kALoOff, p.a_mn[prod], 0);
 #pragma unroll
-              for (int kk = 0; kk < BK / UMMA_K; ++kk) {
-                const uint64_t dah = operand_desc(a_hi, p.a_mn[prod], kk);
-                const uint64_t dal = operand_desc(a_lo, p.a_mn[prod], kk);
-                const uint64_t dbh = operand_desc(b_hi, p.b_mn[prod], kk);
-                const uint64_t dbl = operand_desc(b_lo, p.b_mn[prod], kk);
-                umma_tf32(tmem_d, dal, dbh, idesc, accumulate);     // small terms first
-                umma_tf32(tmem_d, dah, dbl, idesc, 1u);
-                umma_tf32(tmem_d, dah, dbh, idesc, 1u);
-                accumulate = 1u;
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                  umma_tf32(tmem_d, dal0 + kk * a_step, dbh0 + kk * b_step, idesc, acc);     // small terms first
+                  umma_tf32(tmem_d, dah0 + kk * a_step, dbl0 + kk * b_step, idesc, 1u);
+                  umma_tf32(tmem_d, dah0 + kk * a_step, dbh0 + kk * b_step, idesc, 1u);
+                  acc = 1u;
+                }
               }
+              umma_commit(&empty[s]);                               // frees the stage when these MMAs retire
+              if (chunk_end) umma_commit(&tmem_full[a]);            // chunk complete -> epilogue
             }
-            umma_commit(&empty[s]);                               // frees the stage when these MMAs retire
-            if (++in_chunk == kChunkKB || done + 1 == total_kb) {
-              umma_commit(&tmem_full[a]);                         // chunk complete -> epilogue
-              in_chunk = 0;
-            }
+            __syncwarp();
+            accumulate = 1u;
+            in_chunk = chunk_end ? 0 : in_chunk + 1;
           }
         }
       }
     }
-    __syncwarp();
   } else if (warp >= kSplitWarp0) {
     // ===================================== 3xTF32 splitter ==================================
     const int st = threadIdx.x - kSplitWarp0 * 32;            // 0..127
@@ -426,17 +443,24 @@ __global__ void __launch_bounds__(kThreads, 1)
           mbar_wait(&full[s], ph);
           if constexpr (TS) {
             // ---- A: this thread owns row m = TMEM lane (warp & 3) * 32 + lane; 32 K values -> registers -> TMEM
+            // ---- B: 128 threads split the tile in shared memory (hi in place, lo in the second tile)
+            // All shared-memory loads of the stage (A row + this thread's share of B) are issued up front so that
+            // their latency is paid once per stage, not once per 16 bytes: the splitter warps run one per scheduler.
             const uint32_t sa = smem_u32(stage_ptr(s));
             const int row = (warp & 3) * 32 + lane;
-            uint32_t ahi[32], alo[32];
-            if (!p.a_mn[prod]) {
+            constexpr int kBVec = C::kTileBBytes / (128 * 16);        // 16-byte vectors of B per thread (8 at BN = 128)
+            uint32_t araw[32];
+            uint4 braw[kBVec];
+            if (p.debug & 2) {
+#pragma unroll
+              for (int k = 0; k < 32; ++k) araw[k] = 0;
+            } else if (!p.a_mn[prod]) {
               // K-major tile, SWIZZLE_128B: row m is 128 B at m*128, its 16-byte chunk c sits at position c ^ (m & 7)
               const uint32_t rp = sa + row * 128;
 #pragma unroll
               for (int c = 0; c < 8; ++c) {
                 const uint4 x = lds128(rp + ((c ^ (row & 7)) << 4));
-                split_tf32(x.x, ahi[4 * c], alo[4 * c]);         split_tf32(x.y, ahi[4 * c + 1], alo[4 * c + 1]);
-                split_tf32(x.z, ahi[4 * c + 2], alo[4 * c + 2]); split_tf32(x.w, ahi[4 * c + 3], alo[4 * c + 3]);
+                araw[4 * c] = x.x; araw[4 * c + 1] = x.y; araw[4 * c + 2] = x.z; araw[4 * c + 3] = x.w;
               }
             } else {
               // MN-major tile: four [32 k][32 m] blocks of 128-byte rows, SWIZZLE_128B_ATOM_32B (32-byte atom index
@@ -444,13 +468,31 @@ __global__ void __launch_bounds__(kThreads, 1)
               const uint32_t blk = sa + (row >> 5) * 4096;
               const int mb = (row & 31) * 4;
 #pragma unroll
-              for (int k = 0; k < 32; ++k) split_tf32(lds32(blk + k * 128 + (mb ^ ((k & 3) << 5))), ahi[k], alo[k]);
+              for (int k = 0; k < 32; ++k) araw[k] = lds32(blk + k * 128 + (mb ^ ((k & 3) << 5)));
             }
-            const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::kATmemCol0 + s * 2 * BK);
-            tmem_st32(t_a, ahi);
-            tmem_st32(t_a + BK, alo);
-            // ---- B: split in shared memory (hi in place, lo in the second tile)
-            split_tile_smem(sa + C::kBHiOff, sa + C::kBLoOff, C::kTileBBytes, st);
+            const uint32_t bh = sa + C::kBHiOff + st * 16, bl = sa + C::kBLoOff + st * 16;
+            if (!(p.debug & 1)) {
+#pragma unroll
+              for (int j = 0; j < kBVec; ++j) braw[j] = lds128(bh + j * 2048);
+            }
+            {
+              uint32_t ahi[32], alo[32];
+#pragma unroll
+              for (int k = 0; k < 32; ++k) split_tf32(araw[k], ahi[k], alo[k]);
+              const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::kATmemCol0 + s * 2 * BK);
+              tmem_st32(t_a, ahi);
+              tmem_st32(t_a + BK, alo);
+            }
+            if (!(p.debug & 1)) {
+#pragma unroll
+              for (int j = 0; j < kBVec; ++j) {
+                uint4 h, l;
+                split_tf32(braw[j].x, h.x, l.x); split_tf32(braw[j].y, h.y, l.y);
+                split_tf32(braw[j].z, h.z, l.z); split_tf32(braw[j].w, h.w, l.w);
+                sts128(bh + j * 2048, h);
+                sts128(bl + j * 2048, l);
+              }
+            }
             tmem_st_wait();
             tc_fence_before();              // TMEM stores ordered before the MMA issuer's tcgen05.mma (via conv[s])
           } else {
@@ -634,6 +676,7 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   p.tiles_m = (g.M + BM - 1) / BM;
   p.tiles_n = (g.N + BN - 1) / BN;
   p.count = count;
+  p.debug = ctx->opt_tc_debug;
   double work = 0.0;
   for (int i = 0; i < count; ++i) {
     const la::Gemm& q = gs[i];

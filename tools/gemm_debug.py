@@ -61,6 +61,38 @@ if __name__ == "__main__":
             run(512, 512, 512, 0, 0, a_tri=1, b_tri=1, triu=1, mode=mode)
             run(100, 4096, 2048, 1, 0, mode=mode)
             run(4096, 4096, 4096, 0, 1, mode=mode)
+    elif which == "ablate":
+        # where does the time go?  (results are wrong with debug bits set)  + clocks/power under a sustained loop
+        import subprocess, time
+        M = N = K = 4096
+        A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda"); Cm = torch.empty(M, N, device="cuda")
+        args = (ctx.handle, 2, M, N, K, C.c_void_p(A.data_ptr()), K, 0, C.c_void_p(B.data_ptr()), N, 1,
+                C.c_void_p(Cm.data_ptr()), N, 0, 0, 0)
+        def loop(fn, n):
+            for _ in range(5):
+                fn()
+            torch.cuda.synchronize()
+            q = subprocess.Popen(["nvidia-smi", "--query-gpu=clocks.sm,power.draw", "--format=csv,noheader,nounits", "-lms", "50"],
+                                 stdout=subprocess.PIPE, text=True)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                fn()
+            e1.record(); torch.cuda.synchronize()
+            q.terminate()
+            lines = [l.split(",") for l in q.stdout.read().strip().splitlines() if "," in l]
+            clk = sorted(float(l[0]) for l in lines); pw = sorted(float(l[1]) for l in lines)
+            return e0.elapsed_time(e1) / n, (clk[len(clk) // 2] if clk else 0), (pw[len(pw) // 2] if pw else 0)
+        for mode in (1, 0):
+            ctx.set_option("tc_mode", mode)
+            for dbg, name in ((0, "full"), (1, "no B split"), (2, "no A split"), (3, "no split"), (4, "no MMA"), (7, "TMA + barriers only")):
+                ctx.set_option("tc_debug", dbg)
+                ms, clk, pw = loop(lambda: check(ctx.lib.psgd_gemm(*args)), 1500)
+                print(f"mode={'TS' if mode else 'SS'} {name:22s}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:6.1f} TFLOP/s-equiv   sm {clk:.0f} MHz  {pw:.0f} W", flush=True)
+            ctx.set_option("tc_debug", 0)
+        torch.backends.cuda.matmul.allow_tf32 = True
+        ms, clk, pw = loop(lambda: A @ B, 1500)
+        print(f"cuBLAS tf32 4096^3: {ms:.3f} ms {2 * M * N * K / ms / 1e9:.1f} TFLOP/s  sm {clk:.0f} MHz {pw:.0f} W", flush=True)
     elif which == "perf":
         import time
         for mode in (1, 0):
