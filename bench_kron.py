@@ -131,32 +131,65 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
                              "triangular tile skipping legitimately raises the fraction")
 
     # ---- end to end: host (pinned) dX, dG, G per step, preconditioned gradients read back ----------------
+    # Same public API (the batched calls); the step's inputs are uploaded from pinned host memory and its results read
+    # back to pinned host memory INSIDE the timed region, double-buffered on two copy streams so that the upload of
+    # step i+1 and the read-back of step i-1 overlap the tensor-core work of step i.
     e2e = None
     if not args.no_e2e:
-        nb = min(len(mine), 2)              # bounded pinned staging: stream layer by layer through 2 slots
-        h_in = [[torch.randn(n, n).pin_memory() for _ in range(3)] for _ in range(nb)]
-        h_out = [torch.empty(n, n).pin_memory() for _ in range(nb)]
-        d_in = [[torch.empty(n, n, device=dev) for _ in range(3)] for _ in range(nb)]
+        del pool
+        torch.cuda.empty_cache()
+        NB = 2
+        nl = len(mine)
+        h_in = [[torch.randn(n, n).pin_memory() for _ in range(nl)] for _ in range(3)]       # dX, dG, G (one host copy)
+        h_in[1] = [(1.3 * x + 0.1 * torch.randn(n, n)).pin_memory() for x in h_in[0]]
+        h_out = [[torch.empty(n, n).pin_memory() for _ in range(nl)] for _ in range(NB)]
+        d_in = [[[torch.empty(n, n, device=dev) for _ in range(nl)] for _ in range(3)] for _ in range(NB)]
+        s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+        cur = torch.cuda.current_stream()
 
-        def e2e_step(Ql, Qr):
-            outQl, outQr = [], []
-            for li in range(len(mine)):
-                k = li % nb
-                for a, b in zip(d_in[k], h_in[k]):
-                    a.copy_(b, non_blocking=True)
-                ql, qr = psgd.update_precond_kron(Ql[li], Qr[li], d_in[k][0], d_in[k][1], 0.01)
-                p = psgd.precond_grad_kron(ql, qr, d_in[k][2])
-                h_out[k].copy_(p, non_blocking=True)
-                outQl.append(ql); outQr.append(qr)
-            return outQl, outQr
+        def e2e_loop(steps, Ql, Qr):
+            in_ready, buf_free, out_done, keep = [None] * NB, [None] * NB, [None] * NB, [None] * NB
 
-        Ql, Qr = e2e_step(Ql, Qr)
+            def upload(i):
+                k = i % NB
+                with torch.cuda.stream(s_h2d):
+                    if buf_free[k] is not None:
+                        s_h2d.wait_event(buf_free[k])
+                    for dst, src in zip(d_in[k], h_in):
+                        for a, b in zip(dst, src):
+                            a.copy_(b, non_blocking=True)
+                    ev = torch.cuda.Event(); ev.record(s_h2d); in_ready[k] = ev
+
+            upload(0)
+            for i in range(steps):
+                k = i % NB
+                if i + 1 < steps:
+                    upload(i + 1)
+                cur.wait_event(in_ready[k])
+                new = psgd.update_precond_kron_batched(Ql, Qr, d_in[k][0], d_in[k][1], 0.01)
+                Ql, Qr = [a for a, _ in new], [b for _, b in new]
+                pre = psgd.precond_grad_kron_batched(Ql, Qr, d_in[k][2])
+                if world > 1:
+                    pre = [pre[j] for j in range(nl)]      # each rank reads back the layers it owns
+                ev = torch.cuda.Event(); ev.record(cur); buf_free[k] = ev
+                with torch.cuda.stream(s_d2h):
+                    s_d2h.wait_event(ev)
+                    if out_done[k] is not None:
+                        s_d2h.wait_event(out_done[k])
+                    for a, b in zip(h_out[k], pre):
+                        a.copy_(b, non_blocking=True)
+                        b.record_stream(s_d2h)
+                    ev2 = torch.cuda.Event(); ev2.record(s_d2h); out_done[k] = ev2
+                keep[k] = pre                                # alive until its read-back has been enqueued and replaced
+            cur.wait_stream(s_d2h)
+            return Ql, Qr
+
+        Ql, Qr = e2e_loop(2, Ql, Qr)
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        ksteps = max(1, min(args.steps, 3))
+        ksteps = max(2, min(args.steps, 6))
         f0.record()
-        for _ in range(ksteps):
-            Ql, Qr = e2e_step(Ql, Qr)
+        Ql, Qr = e2e_loop(ksteps, Ql, Qr)
         f1.record()
         barrier()
         ems = f0.elapsed_time(f1)
@@ -164,10 +197,12 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         if world > 1:
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ems = float(t.item())
+        assert np.isfinite(h_out[0][0].numpy()).all()
         e2e = dict(value=round(ksteps / (ems / 1e3), 4), unit=UNIT, h2d_bytes_per_step=int(3 * 4 * n * n * L),
                    d2h_bytes_per_step=int(4 * n * n * L), ms_per_step=round(ems / ksteps, 2), steps=ksteps,
-                   note="dX, dG, G of every layer uploaded from pinned host memory and the preconditioned gradient read "
-                        "back to host every step through the per-layer public API; factors stay device-resident")
+                   note="dX, dG, G of every layer uploaded from pinned host memory and every preconditioned gradient read "
+                        "back to pinned host memory each step, through the batched public API; factors stay "
+                        "device-resident; copies double-buffered on two side streams")
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:

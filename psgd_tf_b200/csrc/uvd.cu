@@ -373,37 +373,67 @@ __global__ void __launch_bounds__(GramPlan<R, MODE>::THREADS, 1)
 // =============================================================================================
 // small kernels (one CTA): fixed-order float64 reduction of CTA partials, r x r algebra
 // =============================================================================================
-__global__ void reduce_partials_kernel(const float* __restrict__ partial, int nblocks, int count,
-                                       double* __restrict__ out) {
-  for (int k = threadIdx.x; k < count; k += blockDim.x) {
-    double s = 0.0;
-    for (int b = 0; b < nblocks; ++b) s += (double)partial[(size_t)b * count + k];
-    out[k] = s;
+// out[k] = sum over CTAs of partial[b][k], in float64 and in an order that depends only on (nblocks, count): each of
+// `parts` threads per entry sums a strided subset of the CTAs (independent loads, pipelined), the subsets are then
+// combined in index order.  One CTA of 1024 threads; latency bound (a few microseconds).
+constexpr int kReduceThreads = 1024;
+constexpr int kReduceMaxParts = 32;
+__global__ void __launch_bounds__(kReduceThreads) reduce_partials_kernel(const float* __restrict__ partial, int nblocks,
+                                                                         int count, double* __restrict__ out) {
+  __shared__ double part_sum[kReduceThreads];
+  int parts = kReduceThreads / count;
+  if (parts > kReduceMaxParts) parts = kReduceMaxParts;
+  if (parts < 1) parts = 1;
+  for (int k0 = 0; k0 < count; k0 += kReduceThreads / parts) {       // count > 1024 never happens for r <= 16, but stay general
+    const int slots = min(count - k0, kReduceThreads / parts);
+    const int k = k0 + (int)threadIdx.x % slots;
+    const int part = (int)threadIdx.x / slots;
+    if (part < parts) {
+      double s = 0.0;
+#pragma unroll 8
+      for (int b = part; b < nblocks; b += parts) s += (double)partial[(size_t)b * count + k];
+      part_sum[part * slots + (k - k0)] = s;
+    }
+    __syncthreads();
+    if ((int)threadIdx.x < slots) {
+      double s = 0.0;
+      for (int q = 0; q < parts; ++q) s += part_sum[q * slots + threadIdx.x];
+      out[k0 + threadIdx.x] = s;
+    }
+    __syncthreads();
   }
 }
 
-// LU with partial pivoting (the algorithm class of tf.linalg.solve / LAPACK gesv), n <= kMaxRank.
-__device__ void lu_solve(int n, double* A /*n*n row-major, destroyed*/, double* b /*in: rhs, out: x*/) {
+// LU with partial pivoting (the algorithm class of tf.linalg.solve / LAPACK gesv), n <= kMaxRank, executed by ONE WARP on
+// an augmented system [A | b] in shared memory (row stride kLuLd); the solution replaces the last column.
+constexpr int kLuLd = kMaxRank + 1;
+__device__ __forceinline__ void warp_lu_solve(int n, double (*A)[kLuLd], int lane) {
   for (int k = 0; k < n; ++k) {
-    int piv = k;
-    double best = fabs(A[k * n + k]);
-    for (int i = k + 1; i < n; ++i)
-      if (fabs(A[i * n + k]) > best) { best = fabs(A[i * n + k]); piv = i; }
-    if (piv != k) {
-      for (int j = 0; j < n; ++j) { double t = A[k * n + j]; A[k * n + j] = A[piv * n + j]; A[piv * n + j] = t; }
-      double t = b[k]; b[k] = b[piv]; b[piv] = t;
+    // pivot: first row of maximal |A[i][k]|, i >= k
+    double v = (lane >= k && lane < n) ? fabs(A[lane][k]) : -1.0;
+    int idx = lane;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      const double ov = __shfl_xor_sync(0xffffffffu, v, o);
+      const int oi = __shfl_xor_sync(0xffffffffu, idx, o);
+      if (ov > v || (ov == v && oi < idx)) { v = ov; idx = oi; }
     }
-    const double inv = 1.0 / A[k * n + k];
-    for (int i = k + 1; i < n; ++i) {
-      const double f = A[i * n + k] * inv;
-      for (int j = k + 1; j < n; ++j) A[i * n + j] -= f * A[k * n + j];
-      b[i] -= f * b[k];
+    if (idx != k && lane <= n) { const double t = A[k][lane]; A[k][lane] = A[idx][lane]; A[idx][lane] = t; }
+    __syncwarp();
+    const double inv = 1.0 / A[k][k];
+    const int rows = n - k - 1, cols = n - k;          // columns k+1 .. n (the last one is the right-hand side)
+    for (int e = lane; e < rows * cols; e += 32) {
+      const int i = k + 1 + e / cols, j = k + 1 + e % cols;
+      A[i][j] -= (A[i][k] * inv) * A[k][j];
     }
+    __syncwarp();
   }
   for (int i = n - 1; i >= 0; --i) {
-    double s = b[i];
-    for (int j = i + 1; j < n; ++j) s -= A[i * n + j] * b[j];
-    b[i] = s / A[i * n + i];
+    double s = (lane > i && lane < n) ? A[i][lane] * A[lane][n] : 0.0;
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) A[i][n] = (A[i][n] - s) / A[i][i];
+    __syncwarp();
   }
 }
 
@@ -430,85 +460,107 @@ struct SmallState {
 // table accessors for G = Z^T [Z | X] stored [W][E] with only j >= i filled
 __device__ __forceinline__ double Gsym(const double* G, int E, int i, int j) { return i <= j ? G[i * E + j] : G[j * E + i]; }
 
-__global__ void uvd_small1_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
-  if (threadIdx.x != 0) return;
+// One warp.  G: reduced table of sweep 1.
+__global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
+  __shared__ double A[kMaxRank][kLuLd];
+  __shared__ double sp[kMaxRank], ss1[kMaxRank];
+  const int lane = threadIdx.x;
   const int W = 2 * r, E = W + 2;
-  double A[kMaxRank * kMaxRank], rhs[kMaxRank], p[kMaxRank], s1[kMaxRank];
-  for (int i = 0; i < r; ++i)
-    for (int j = 0; j < r; ++j) {
-      st->UtU[i * r + j] = Gsym(G, E, i, j);
-      st->VtV[i * r + j] = Gsym(G, E, r + i, r + j);
-      // VtU[i][j] = sum_k V[k,i] U[k,j] = G[U_j][V_i]                       psgd.py:574-575
-      st->IpVtU[i * r + j] = G[j * E + (r + i)] + (i == j ? 1.0 : 0.0);
-    }
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    st->UtU[e] = Gsym(G, E, i, j);
+    st->VtV[e] = Gsym(G, E, r + i, r + j);
+    // VtU[i][j] = sum_k V[k,i] U[k,j] = G[U_j][V_i]                         psgd.py:574-575
+    st->IpVtU[e] = G[j * E + (r + i)] + (i == j ? 1.0 : 0.0);
+  }
   // p = V^T(dh);  t = U^T Qh = U^T dh + (U^T U) p                            psgd.py:569-570
-  for (int i = 0; i < r; ++i) p[i] = G[(r + i) * E + W];
-  for (int i = 0; i < r; ++i) {
-    double s = G[i * E + W];
-    for (int j = 0; j < r; ++j) s += st->UtU[i * r + j] * p[j];
-    st->p[i] = (float)p[i];
-    st->t[i] = (float)s;
+  if (lane < r) sp[lane] = G[(r + lane) * E + W];
+  __syncwarp();
+  if (lane < r) {
+    double s = G[lane * E + W];
+    for (int j = 0; j < r; ++j) s += Gsym(G, E, lane, j) * sp[j];
+    st->p[lane] = (float)sp[lane];
+    st->t[lane] = (float)s;
   }
   // s1 = solve(IpVtU^T, U^T w)                                               psgd.py:577
-  for (int i = 0; i < r; ++i) {
-    for (int j = 0; j < r; ++j) A[i * r + j] = st->IpVtU[j * r + i];
-    rhs[i] = G[i * E + W + 1];
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    A[i][j] = G[i * E + (r + j)] + (i == j ? 1.0 : 0.0);      // IpVtU[j][i]
   }
-  lu_solve(r, A, rhs);
-  for (int i = 0; i < r; ++i) { s1[i] = rhs[i]; st->s1[i] = (float)rhs[i]; }
+  if (lane < r) A[lane][r] = G[lane * E + W + 1];
+  __syncwarp();
+  warp_lu_solve(r, A, lane);
+  if (lane < r) { ss1[lane] = A[lane][r]; st->s1[lane] = (float)A[lane][r]; }
+  __syncwarp();
   // s2 = solve(IpVtU, V^T invQtv),  V^T invQtv = V^T w - (V^T V) s1          psgd.py:578
-  for (int i = 0; i < r; ++i) {
-    double s = G[(r + i) * E + W + 1];
-    for (int j = 0; j < r; ++j) { s -= st->VtV[i * r + j] * s1[j]; A[i * r + j] = st->IpVtU[i * r + j]; }
-    rhs[i] = s;
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    A[i][j] = G[j * E + (r + i)] + (i == j ? 1.0 : 0.0);      // IpVtU[i][j]
   }
-  lu_solve(r, A, rhs);
-  for (int i = 0; i < r; ++i) st->s2[i] = (float)rhs[i];
-  st->max_nabla = 0.f;
+  if (lane < r) {
+    double s = G[(r + lane) * E + W + 1];
+    for (int j = 0; j < r; ++j) s -= Gsym(G, E, r + lane, r + j) * ss1[j];
+    A[lane][r] = s;
+  }
+  __syncwarp();
+  warp_lu_solve(r, A, lane);
+  if (lane < r) st->s2[lane] = (float)A[lane][r];
+  if (lane == 0) st->max_nabla = 0.f;
 }
 
 // G2 layout: [0]=a.a [1]=b.b [2]=a.b [3..3+r)=a^T X  [3+r..3+2r)=b^T X   (X = V on the U branch, U on the V branch)
-__global__ void uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step, float tiny,
-                                  SmallState* __restrict__ st) {
-  if (threadIdx.x != 0) return;
-  st->mu_d = step / (st->max_nabla + tiny);                                  // psgd.py:582
+__global__ void __launch_bounds__(32) uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step,
+                                                        float tiny, SmallState* __restrict__ st) {
+  const int lane = threadIdx.x;
   const double aa = G2[0], bb = G2[1], ab = G2[2];
   const double* atX = G2 + 3;
   const double* btX = G2 + 3 + r;
   const double* XtX = update_U ? st->VtV : st->UtU;
   // ||X atX^T||^2 = atX (X^T X) atX^T  etc.                                  psgd.py:594-596 / :608-610
   double qaa = 0, qbb = 0, qab = 0;
-  for (int i = 0; i < r; ++i) {
+  if (lane < r) {
     double ra = 0, rb = 0;
-    for (int j = 0; j < r; ++j) { ra += XtX[i * r + j] * atX[j]; rb += XtX[i * r + j] * btX[j]; }
-    qaa += atX[i] * ra; qbb += btX[i] * rb; qab += atX[i] * rb;
+    for (int j = 0; j < r; ++j) { ra += XtX[lane * r + j] * atX[j]; rb += XtX[lane * r + j] * btX[j]; }
+    qaa = atX[lane] * ra; qbb = btX[lane] * rb; qab = atX[lane] * rb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    qaa += __shfl_xor_sync(0xffffffffu, qaa, o);
+    qbb += __shfl_xor_sync(0xffffffffu, qbb, o);
+    qab += __shfl_xor_sync(0xffffffffu, qab, o);
   }
   const float norm = sqrtf(fabsf((float)(aa * qaa + bb * qbb - 2.0 * ab * qab)));
   const float mu = step / (norm + tiny);                                      // psgd.py:597 / :611
-  st->mu = mu;
-  if (update_U) {
-    for (int j = 0; j < r; ++j) {                                            // psgd.py:600-601
+  if (lane == 0) {
+    st->mu_d = step / (st->max_nabla + tiny);                                 // psgd.py:582
+    st->mu = mu;
+  }
+  if (lane < r) {
+    if (update_U) {                                                           // psgd.py:600-601
       double s1 = 0, s2 = 0;
-      for (int i = 0; i < r; ++i) { s1 += atX[i] * st->IpVtU[i * r + j]; s2 += btX[i] * st->IpVtU[i * r + j]; }
-      st->c1[j] = mu * (float)s1;
-      st->c2[j] = mu * (float)s2;
+      for (int i = 0; i < r; ++i) { s1 += atX[i] * st->IpVtU[i * r + lane]; s2 += btX[i] * st->IpVtU[i * r + lane]; }
+      st->c1[lane] = mu * (float)s1;
+      st->c2[lane] = mu * (float)s2;
+    } else {
+      st->c1[lane] = (float)atX[lane];
+      st->c2[lane] = (float)btX[lane];
     }
-  } else {
-    for (int j = 0; j < r; ++j) { st->c1[j] = (float)atX[j]; st->c2[j] = (float)btX[j]; }
   }
 }
 
 // apply / matvec: p = V^T x ; t = U^T x + (U^T U) p
-__global__ void uvd_small_apply_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
-  if (threadIdx.x != 0) return;
+__global__ void __launch_bounds__(32) uvd_small_apply_kernel(const double* __restrict__ G, int r,
+                                                             SmallState* __restrict__ st) {
+  __shared__ double sp[kMaxRank];
+  const int lane = threadIdx.x;
   const int W = 2 * r, E = W + 1;
-  double p[kMaxRank];
-  for (int i = 0; i < r; ++i) p[i] = G[(r + i) * E + W];
-  for (int i = 0; i < r; ++i) {
-    double s = G[i * E + W];
-    for (int j = 0; j < r; ++j) s += Gsym(G, E, i, j) * p[j];
-    st->p[i] = (float)p[i];
-    st->t[i] = (float)s;
+  if (lane < r) sp[lane] = G[(r + lane) * E + W];
+  __syncwarp();
+  if (lane < r) {
+    double s = G[lane * E + W];
+    for (int j = 0; j < r; ++j) s += Gsym(G, E, lane, j) * sp[j];
+    st->p[lane] = (float)sp[lane];
+    st->t[lane] = (float)s;
   }
 }
 
@@ -933,7 +985,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.n = n; a1.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kUpdate>(ctx, a1, s.partial, grid)));
   constexpr int table = GramPlan<R, kUpdate>::W * GramPlan<R, kUpdate>::E;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
@@ -944,7 +996,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   o2.o0 = s.a; o2.o1 = s.b; o2.o2 = s.nd; o2.partial = s.partial; o2.st = s.st;
   PSGD_RETURN_IF((launch_map<R, kMapUpd2>(ctx, a1, o2, update_U, grid)));
   constexpr int cnt2 = 3 + 2 * R;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, cnt2, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, cnt2, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, cnt2, &s.st->max_nabla, 1));
   uvd_small2_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
@@ -973,7 +1025,7 @@ static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
@@ -1029,7 +1081,7 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
@@ -1044,7 +1096,7 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
   float* pre = pre_out ? pre_out : s.a;
   o.o0 = pre; o.partial = s.partial;
   PSGD_RETURN_IF((launch_map<R, kMapApplyNorm>(ctx, a, o, 0, grid)));
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, 1, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, 1, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, 1, nullptr, 0));
   clip_update_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(param, pre, v, n, lr_params, max_norm, tiny, s.G);
@@ -1064,7 +1116,7 @@ static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const floa
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = x; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kMatvec>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kMatvec>::W * GramPlan<R, kMatvec>::E;
-  reduce_partials_kernel<<<1, 256, 0, st>>>(s.partial, grid, table, s.G);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
   uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);   // p = V^T x (t unused)
