@@ -34,6 +34,7 @@ import numpy as np  # noqa: E402
 METRIC = "precond update+apply steps/s"
 UNIT = "steps/s"
 KERNEL_NAMES = {1: "uvd_gram_update", 2: "uvd_map_update2", 3: "uvd_map_update3", 4: "uvd_gram_apply", 5: "uvd_map_apply",
+                6: "peer_exchange",
                 10: "gemm", 11: "trsm"}
 
 
@@ -100,6 +101,25 @@ class ClockSampler:
         return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
 
 
+def load_traffic():
+    """Per-launch DRAM traffic (dram__bytes_read.sum + dram__bytes_write.sum) of the dominant kernels, from the committed
+    ncu --set full capture (profiles/*_traffic.json, written by tools/summarise_profiles.py).  Only valid for the
+    default problem sizes the capture was taken at."""
+    best = None
+    pdir = os.path.join(ROOT, "profiles")
+    if os.path.isdir(pdir):
+        for f in sorted(os.listdir(pdir)):
+            if f.endswith("_traffic.json"):
+                best = os.path.join(pdir, f)
+    if not best:
+        return {}, None
+    try:
+        d = json.load(open(best))
+        return d.get("bytes_per_launch", {}), os.path.relpath(best, ROOT)
+    except Exception:
+        return {}, None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -156,11 +176,25 @@ def run_uvd(args, rank, world, local):
         pool.append((v, h, g))
         del c
     ctx = psgd.get_context(local)
+    exchange = "none (single GPU)"
     if world > 1:
-        partition.install_allreduce(ctx)
+        exchange = partition.install_exchange(ctx) if not args.nccl_hook else (partition.install_allreduce(ctx) or "all-reduce hook")
+
+    # CUDA graphs need a host-free chain: fine on one GPU and with the peer-memory exchange, not with the Python hook
+    # and only used where launch latency matters (sharded runs: < 1 ms of kernels per step at 8 GPUs).  On one GPU the
+    # timed loop stays eager so that every launch in it is bracketed by CUDA events for the per-kernel roofline.
+    use_graphs = (not args.no_graphs) and world > 1 and exchange == "peer-memory"
+    graphs = {}
 
     def step(i, U, V, d, v, h, g):
-        psgd.update_precond_UVd_math_(U, V, d, v, h, 0.01, psgd._tiny, balance=(i % 100 == 99), update_U=(i % 2 == 0))
+        balance, update_U = (i % 100 == 99), (i % 2 == 0)
+        if use_graphs:
+            gs = graphs.get(U.data_ptr())
+            if gs is None:
+                from psgd_tf_b200.graphs import UVdStepGraphs
+                gs = graphs[U.data_ptr()] = UVdStepGraphs(U, V, d, 0.01, psgd._tiny)
+            return gs.step(v, h, g, balance, update_U)
+        psgd.update_precond_UVd_math_(U, V, d, v, h, 0.01, psgd._tiny, balance=balance, update_U=update_U)
         return psgd.precond_grad_UVd_math(U, V, d, g)
 
     def barrier():
@@ -170,15 +204,17 @@ def run_uvd(args, rank, world, local):
 
     # ---- device-resident timing -----------------------------------------------------------------
     U, V, d = U0.clone(), V0.clone(), d0.clone()
-    for i in range(args.warmup):
+    for i in range(args.warmup + (2 * POOL if use_graphs else 0)):      # graphs: capture every (inputs, coin flip) key
         step(i, U, V, d, *pool[i % POOL])
-    ctx.set_option("profile", 1)
+    if not use_graphs:
+        ctx.set_option("profile", 1)
     ctx.profile_read()
     clocks = ClockSampler(local)
     barrier()
     if rank == 0:
         clocks.start()
     launches0 = ctx.launch_count
+    graph_launches0 = sum(g.kernel_launches for g in graphs.values())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
@@ -187,7 +223,19 @@ def run_uvd(args, rank, world, local):
     barrier()
     clk = clocks.stop() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    launches = ctx.launch_count - launches0
+    launches = ctx.launch_count - launches0 + sum(g.kernel_launches for g in graphs.values()) - graph_launches0
+    kernels_from = "CUDA events around every launch inside the timed region"
+    if use_graphs:
+        # the timed region replayed CUDA graphs (no per-launch events possible): per-kernel times come from a separate
+        # eager pass over the same inputs, right after it
+        use_graphs = False
+        ctx.set_option("profile", 1)
+        ctx.profile_read()
+        for i in range(min(args.steps, 6)):
+            step(args.warmup + i, U, V, d, *pool[i % POOL])
+        torch.cuda.synchronize()
+        use_graphs = True
+        kernels_from = "separate eager pass right after the (graph-replayed) timed region"
     prof = ctx.profile_read(cap=65536)
     ctx.set_option("profile", 0)
     t = torch.tensor([ms], device=dev)
@@ -214,8 +262,11 @@ def run_uvd(args, rank, world, local):
     dom = max(kernels, key=lambda k: k["avg_ms"] * k["launches"]) if kernels else None
     roofline = None
     if dom:
+        traffic_tab, traffic_src = load_traffic()
+        traffic = traffic_tab.get(dom["kernel"]) if (N == 100_000_000 and r == 10 and world == 1) else None
         roofline = dict(bound="hbm", kernel=dom["kernel"], achieved=dom["achieved_GBps"], peak=peaks["hbm"], unit="GB/s",
-                        frac=dom["frac"], traffic=None, peak_source=f"of {peaks['source']}",
+                        frac=dom["frac"], traffic=traffic, traffic_source=traffic_src if traffic else None,
+                        peak_source=f"of {peaks['source']}",
                         step_achieved=round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
                         step_frac=round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
                         step_algorithmic_GB=round(step_bytes / 1e9, 3))
@@ -300,8 +351,10 @@ def run_uvd(args, rank, world, local):
                     n_params=N_total, rank=r, rows_per_gpu=n, parallelism=f"chunk-sharded x{world}",
                     l2_policy="inputs larger than L2: >= %.1f GB of state+inputs streamed per GPU per step vs 126 MB L2" %
                               ((4 * n * (2 * r + 4)) / 1e9),
-                    coin_flips="update_U alternates, balance every 100th step", step_size=0.01),
-        roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+                    coin_flips="update_U alternates, balance every 100th step", step_size=0.01,
+                    cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
+        roofline=roofline, kernels=kernels, kernels_measured=kernels_from, cpu_baseline=cpu, e2e=e2e,
+        gpu_launches=int(launches), clocks=clk)
 
 
 # ---------------------------------------------------------------------------------------------
@@ -429,6 +482,8 @@ def run_reference_kron(args):
 
 # ---------------------------------------------------------------------------------------------
 def main():
+    if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
+        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -441,6 +496,10 @@ def main():
     ap.add_argument("--layers", type=int, default=24)
     ap.add_argument("--kron-n", type=int, default=4096)
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
+    ap.add_argument("--nccl-hook", action="store_true", help="UVd multi-GPU: use the torch.distributed all-reduce hook "
+                    "instead of the peer-memory exchange kernel")
+    ap.add_argument("--no-graphs", action="store_true", help="UVd: launch every kernel from Python instead of replaying "
+                    "the step from CUDA graphs")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -71,6 +71,7 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 #define PSGD_K_UVD_MAP_UPDATE3 3 /* update sweep 3: write d and U (or V)                      */
 #define PSGD_K_UVD_GRAM_APPLY 4  /* apply sweep 1: U^T U, U^T(dg), V^T(dg)                    */
 #define PSGD_K_UVD_MAP_APPLY 5   /* apply sweep 2: write the preconditioned gradient          */
+#define PSGD_K_EXCHANGE 6        /* one peer-memory exchange (push partials to all ranks, wait, reduce)  */
 #define PSGD_K_GEMM 10           /* one tcgen05 3xTF32 GEMM launch                            */
 #define PSGD_K_GEMM_SIMT 12      /* one SIMT fp32 GEMM launch                                 */
 #define PSGD_K_TRSM 11           /* one triangular-solve step                                 */

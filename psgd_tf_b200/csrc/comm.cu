@@ -111,6 +111,7 @@ int cross_rank_reduce(psgd_ctx* ctx, double* sum_buf, int n_sum, float* max_buf,
     auto* st = static_cast<comm::State*>(ctx->comm);
     PSGD_REQUIRE(n_sum <= comm::kMaxSum && n_max <= comm::kMaxMax, PSGD_ERR_COMM,
                  "peer exchange: %d sums / %d maxima exceed the slab (%d / %d)", n_sum, n_max, comm::kMaxSum, comm::kMaxMax);
+    ProfScope prof(ctx, PSGD_K_EXCHANGE);
     comm::exchange_kernel<<<1, 256, 0, ctx->stream>>>(st->peers, st->rank, st->world, sum_buf, n_sum, max_buf, n_max);
     PSGD_LAUNCH_CHECK(ctx);
     return PSGD_OK;

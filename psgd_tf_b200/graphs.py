@@ -39,6 +39,7 @@ class UVdStepGraphs:
         self._warm = False
         self._ws_bytes = -1
         self.replays = 0
+        self.kernel_launches = 0          # kernels executed through graph replays (the library's own counter sees only captures)
 
     def _eager(self, v, h, g, balance, update_U):
         _psgd.update_precond_UVd_math_(self.U, self.V, self.d, v, h, self.step_size, self.tiny, balance=balance,
@@ -65,11 +66,13 @@ class UVdStepGraphs:
                 entry = self._graphs.get(key)
                 if entry is None:
                     graph = torch.cuda.CUDAGraph()
+                    before = ctx.launch_count
                     with torch.cuda.graph(graph, stream=s):
                         out = self._eager(v, h, g, balance, update_U)
-                    entry = self._graphs[key] = (graph, out)
-                graph, out = entry
+                    entry = self._graphs[key] = (graph, out, ctx.launch_count - before)
+                graph, out, nk = entry
                 graph.replay()
                 self.replays += 1
+                self.kernel_launches += nk
         cur.wait_stream(s)
         return out
