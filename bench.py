@@ -537,6 +537,13 @@ def main():
             elif out is not None and kr is not None:
                 out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "scaling", "dtype", "config", "roofline",
                                                    "kernels", "cpu_baseline", "e2e", "gpu_launches", "clocks")}
+        if args.workload == "all" and world == 1 and out is not None:
+            # the other streaming rows of SURVEY.md section 8(a): diagonal, X-shape, (norm,scale) Kron pair, dense apply
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            from bench_aux import run_aux
+            out["aux"] = run_aux(load_peaks()["hbm"], steps=10)
         if out is not None:
             print(json.dumps(out), flush=True)
     finally:

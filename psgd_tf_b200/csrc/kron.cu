@@ -14,6 +14,7 @@
 
 #include "linalg.cuh"
 #include "gemm_tc.cuh"
+#include "kron_stream.cuh"
 
 namespace psgd {
 namespace kron {
@@ -275,6 +276,7 @@ struct Layer {
   Scal* sc;
   float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv;
   float *t1, *t2, *t3, *P, *addlast;
+  float* nspart;   // (normalization, scaling): partial tables of the fused streaming kernels
 };
 
 static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
@@ -292,6 +294,7 @@ static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
   size_t f = 64 + fsize(kl, M) + fsize(kr, N) + 3 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
              2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
   f += tc::trsm_scratch_floats((int)M) + tc::trsm_scratch_floats((int)N);
+  if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) f += ks::ns_update_scratch_floats((int)M, (int)N) + 64;
   return f;
 }
 
@@ -313,6 +316,7 @@ static void carve_update(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
   L.sb = c.take<float>(N);
   L.gvec = c.take<float>(N);
   L.zinv = c.take<float>(tc::trsm_scratch_floats(M > N ? M : N));
+  L.nspart = (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) ? c.take<float>(ks::ns_update_scratch_floats(M, N)) : nullptr;
 }
 
 static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, int M, int N, float step, float tiny) {
@@ -355,7 +359,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) gs.push_back(mk(M, N, N, L.T1, N, false, L.Qrb, N, true, L.A, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
     for (auto& L : Ls) {
-      PSGD_RETURN_IF(col_reduce(ctx, 0, L.Qlb, L.dX, nullptr, M, N, L.part, L.cvec, nullptr));
+      PSGD_RETURN_IF(ks::col_wsum(ctx, 0, L.Qlb, nullptr, L.dX, N, M, N, L.part, L.cvec));
       norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dX, L.cvec, L.T1, M, N, nullptr);   // :230-232
       PSGD_LAUNCH_CHECK(ctx);
     }
@@ -377,14 +381,17 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Bt, L.Qrb, M, N);                  // :299
       PSGD_LAUNCH_CHECK(ctx);
     }
-  } else {  // (NORM, SCALE): no dense factor at all
+  } else {  // (NORM, SCALE): no dense factor at all -- A and Bt are never materialised (kron_stream.cu)
     for (auto& L : Ls) {
-      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dG, L.A, M, N, L.Qrb, 1);     // :349-351
+      PSGD_RETURN_IF(ks::col_wsum(ctx, 0, L.Qlb, nullptr, L.dX, N, M, N, L.part, L.cvec));            // psgd.py:353-355
+      PSGD_RETURN_IF(ks::ns_update_stats(ctx, L.Qlb, L.Qrb, L.cvec, L.dX, L.dG, M, N, L.nspart, L.g1d, L.g1b, L.gvec,
+                                         &L.sc->max1, &L.sc->max2));                                  // :349-351, :356-366
+      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :362-364
       PSGD_LAUNCH_CHECK(ctx);
-      PSGD_RETURN_IF(col_reduce(ctx, 0, L.Qlb, L.dX, nullptr, M, N, L.part, L.cvec, nullptr));
-      norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dX, L.cvec, L.Bt, M, N, L.Qrb);   // :353-356
+      scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);        // :367-369
       PSGD_LAUNCH_CHECK(ctx);
     }
+    return PSGD_OK;
   }
 
   // ---- left factor -----------------------------------------------------------------------------
@@ -558,20 +565,17 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
     return gemm_all(ctx, gs, kLower, 0);
   }
   // normalization-format left factor                                      psgd.py:258-270, :383-391
-  if (kr == PSGD_FACTOR_DENSE) {
-    for (auto& L : Ls) {
-      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.G, L.t1, M, N, nullptr, 0);
-      PSGD_LAUNCH_CHECK(ctx);
-    }
-    PSGD_RETURN_IF(right_dense_apply(ctx, Ls, M, N, true, false));        // -> t2
-  } else {
-    for (auto& L : Ls) {
-      norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.G, L.t2, M, N, L.Qr, 2);
-      PSGD_LAUNCH_CHECK(ctx);
-    }
+  if (kr == PSGD_FACTOR_SCALE) {                                           // one pass over G (kron_stream.cu)
+    for (auto& L : Ls) PSGD_RETURN_IF(ks::ns_apply(ctx, L.Ql, L.Qr, L.G, L.out, M, N, L.part));
+    return PSGD_OK;
   }
   for (auto& L : Ls) {
-    PSGD_RETURN_IF(col_reduce(ctx, 1, L.Ql, L.t2, nullptr, M, N, L.part, L.addlast, nullptr));   // psgd.py:265 / :386
+    norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.G, L.t1, M, N, nullptr, 0);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  PSGD_RETURN_IF(right_dense_apply(ctx, Ls, M, N, true, false));          // -> t2
+  for (auto& L : Ls) {
+    PSGD_RETURN_IF(ks::col_wsum(ctx, 1, nullptr, L.Ql + M, L.t2, N, M, N, L.part, L.addlast));   // psgd.py:265
     norm_left_out_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Ql, L.t2, L.addlast, L.out, M, N);
     PSGD_LAUNCH_CHECK(ctx);
   }
@@ -750,8 +754,7 @@ extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx,
   float* b = c.take<float>(n);
   float* grad = c.take<float>((size_t)n * n);
   PSGD_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(kron::Scal), ctx->stream));
-  la::Gemm g1 = kron::mk(n, 1, n, Q, n, false, dg, 1, false, a, 1);          // a = Q dg          psgd.py:38
-  PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
+  PSGD_RETURN_IF(ks::row_dot(ctx, Q, n, dg, n, n, a));                        // a = Q dg          psgd.py:38
   PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx       psgd.py:39
   la::Gemm g2 = kron::mk(n, n, 1, a, 1, false, a, 1, true, grad, n);          // triu(a a^T - b b^T)   psgd.py:40
   g2.K2 = 1; g2.A2 = b; g2.lda2 = 1; g2.B2 = b; g2.ldb2 = 1; g2.tb2 = true;
@@ -770,10 +773,11 @@ extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, f
   PSGD_REQUIRE(Q && g && out, PSGD_ERR_BAD_POINTER, "dense apply: null device pointer");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   const int n = (int)n64;
-  PSGD_RETURN_IF(ctx->reserve((size_t)n * sizeof(float) + 1024));
-  float* t = static_cast<float*>(ctx->ws);
-  la::Gemm g1 = kron::mk(n, 1, n, Q, n, false, g, 1, false, t, 1);           // t = Q g            psgd.py:55
-  PSGD_RETURN_IF(la::gemm_simt(ctx, g1));
-  la::Gemm g2 = kron::mk(n, 1, n, Q, n, true, t, 1, false, out, 1);          // out = Q^T t
-  return la::gemm_simt(ctx, g2);
+  // two bandwidth-bound GEMVs: Q is read exactly twice (8 n^2 bytes), coalesced both times
+  PSGD_RETURN_IF(ctx->reserve(((size_t)n + (size_t)ks::row_tiles(n) * n) * sizeof(float) + 2048));
+  WsCarver c(ctx->ws);
+  float* t = c.take<float>(n);
+  float* part = c.take<float>((size_t)ks::row_tiles(n) * n);
+  PSGD_RETURN_IF(ks::row_dot(ctx, Q, n, g, n, n, t));                        // t = Q g            psgd.py:55
+  return ks::col_wsum(ctx, 1, nullptr, t, Q, n, n, n, part, out);            // out = Q^T t
 }

@@ -227,6 +227,37 @@ def test_kron_all_format_combinations(psgd, kl, kr, M, N):
     check(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"]), what="pre_grad")
 
 
+@pytest.mark.parametrize("M,N", [(2305, 1024), (1025, 4935), (300, 7), (5, 3000), (64, 256), (65, 257), (3, 1)])
+@pytest.mark.parametrize("mirror", [False, True])
+def test_kron_norm_scale_fused_streaming_kernels(psgd, M, N, mirror):
+    """(normalization, scaling) and its mirror (scaling, normalization) at NMT-like and ragged shapes: the fused
+    one-pass kernels of csrc/kron_stream.cu against the oracle (psgd.py:328-391)."""
+    kl, kr = ("scale", "norm") if mirror else ("norm", "scale")
+    if mirror:
+        M, N = N, M
+    if (kl == "norm" and M == 2) or (kr == "norm" and N == 2) or (kl == "scale" and M == 1) or (kr == "scale" and N == 1):
+        pytest.skip("square factors are dense by the reference's dispatch order")
+    c = cases.kron_case(5000 + M + N, kl, kr, M, N)
+    ql, qr = psgd.update_precond_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["dX"]), dev(c["dG"]), 0.01)
+    qlr, qrr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
+    check(ql, qlr, what="Ql"); check(qr, qrr, what="Qr")
+    pre = psgd.precond_grad_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["G"]))
+    check(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"]), what="pre_grad")
+
+
+def test_dense_apply_large_gemv_pair(psgd):
+    """precond_grad_dense at n = 3000 (not a multiple of the tile sizes): two coalesced GEMVs over Q."""
+    rng = np.random.default_rng(11)
+    n = 3000
+    Q = (np.triu(rng.standard_normal((n, n))) * 0.02 + np.eye(n)).astype(np.float32)
+    gs = [rng.standard_normal((40, 50)).astype(np.float32), rng.standard_normal((1000,)).astype(np.float32)]
+    got = psgd.precond_grad_dense(dev(Q), [dev(g) for g in gs])
+    want = O.precond_grad_dense(Q, gs)
+    for a, b in zip(got, want):
+        assert tuple(a.shape) == b.shape
+        check(a, b, what="dense apply")
+
+
 def test_kron_golden(psgd):
     for seed, kl, kr, M, N in MG.KRON_GOLDEN:
         c = cases.kron_case(seed, kl, kr, M, N)
