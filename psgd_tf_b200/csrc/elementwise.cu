@@ -149,6 +149,73 @@ __global__ void __launch_bounds__(kThreads) xmat_apply_kernel(const float* __res
   }
 }
 
+// 128-bit variants for n % 8 == 0 (16-byte aligned mirrored blocks): one thread owns elements i..i+3 and their mirror
+// images n-1-i .. n-4-i, i.e. one float4 from each half of every array; component e pairs with component 3-e.
+__device__ __forceinline__ void unpack(const float4& v, float (&x)[4]) { x[0] = v.x; x[1] = v.y; x[2] = v.z; x[3] = v.w; }
+__device__ __forceinline__ void unpack_rev(const float4& v, float (&x)[4]) { x[0] = v.w; x[1] = v.z; x[2] = v.y; x[3] = v.x; }
+__device__ __forceinline__ float4 pack(const float (&x)[4]) { return make_float4(x[0], x[1], x[2], x[3]); }
+__device__ __forceinline__ float4 pack_rev(const float (&x)[4]) { return make_float4(x[3], x[2], x[1], x[0]); }
+
+template <bool WRITE>
+__global__ void __launch_bounds__(kThreads) xmat_kernel_v4(float* __restrict__ a, float* __restrict__ b,
+                                                            const float* __restrict__ v, const float* __restrict__ h,
+                                                            int64_t n, float step, float tiny, Scalars* __restrict__ sc) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t groups = n / 8;        // float4 groups in the first half
+  float mu = 0.f, m = 0.f;
+  if (WRITE) mu = step / (sc->max_abs + tiny);
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += stride) {
+    const int64_t i = 4 * q, jb = n - 4 - i;
+    float ai[4], aj[4], bi[4], bj[4], vi[4], vj[4], hi[4], hj[4];
+    unpack(*reinterpret_cast<const float4*>(a + i), ai); unpack_rev(*reinterpret_cast<const float4*>(a + jb), aj);
+    unpack(*reinterpret_cast<const float4*>(b + i), bi); unpack_rev(*reinterpret_cast<const float4*>(b + jb), bj);
+    unpack(*reinterpret_cast<const float4*>(v + i), vi); unpack_rev(*reinterpret_cast<const float4*>(v + jb), vj);
+    unpack(*reinterpret_cast<const float4*>(h + i), hi); unpack_rev(*reinterpret_cast<const float4*>(h + jb), hj);
+    float nai[4], naj[4], nbi[4], nbj[4];
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      XPair p;
+      p.a_i = ai[e]; p.a_j = aj[e]; p.b_i = bi[e]; p.b_j = bj[e];
+      xmat_grad(p, vi[e], vj[e], hi[e], hj[e], false);
+      if (WRITE) {
+        nai[e] = p.a_i - mu * (p.na_i * p.a_i + p.nb * p.b_j);
+        nbi[e] = p.b_i - mu * (p.na_i * p.b_i + p.nb * p.a_j);
+        naj[e] = p.a_j - mu * (p.na_j * p.a_j + p.nb * p.b_i);
+        nbj[e] = p.b_j - mu * (p.na_j * p.b_j + p.nb * p.a_i);
+      } else {
+        m = fmaxf(m, fmaxf(fabsf(p.na_i), fmaxf(fabsf(p.na_j), fabsf(p.nb))));
+      }
+    }
+    if (WRITE) {
+      *reinterpret_cast<float4*>(a + i) = pack(nai); *reinterpret_cast<float4*>(a + jb) = pack_rev(naj);
+      *reinterpret_cast<float4*>(b + i) = pack(nbi); *reinterpret_cast<float4*>(b + jb) = pack_rev(nbj);
+    }
+  }
+  if (!WRITE) block_max_to(m, &sc->max_abs);
+}
+
+__global__ void __launch_bounds__(kThreads) xmat_apply_kernel_v4(const float* __restrict__ a, const float* __restrict__ b,
+                                                                  const float* __restrict__ g, float* __restrict__ out,
+                                                                  int64_t n) {
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t groups = n / 8;
+  for (int64_t q = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; q < groups; q += stride) {
+    const int64_t i = 4 * q, jb = n - 4 - i;
+    float ai[4], aj[4], bi[4], bj[4], gi[4], gj[4], oi[4], oj[4];
+    unpack(*reinterpret_cast<const float4*>(a + i), ai); unpack_rev(*reinterpret_cast<const float4*>(a + jb), aj);
+    unpack(*reinterpret_cast<const float4*>(b + i), bi); unpack_rev(*reinterpret_cast<const float4*>(b + jb), bj);
+    unpack(*reinterpret_cast<const float4*>(g + i), gi); unpack_rev(*reinterpret_cast<const float4*>(g + jb), gj);
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      const float ab_i = ai[e] * bi[e], ab_j = aj[e] * bj[e];
+      oi[e] = (ai[e] * ai[e] + bj[e] * bj[e]) * gi[e] + (ab_i + ab_j) * gj[e];
+      oj[e] = (aj[e] * aj[e] + bi[e] * bi[e]) * gj[e] + (ab_j + ab_i) * gi[e];
+    }
+    *reinterpret_cast<float4*>(out + i) = pack(oi);
+    *reinterpret_cast<float4*>(out + jb) = pack_rev(oj);
+  }
+}
+
 static int grid_for(const psgd_ctx* ctx, int64_t work_items) {
   int64_t blocks = (work_items + kThreads - 1) / kThreads;
   int64_t cap = (int64_t)ctx->num_sms * 8;
@@ -213,13 +280,16 @@ extern "C" int psgd_xmat_update(psgd_ctx* ctx, float* a, float* b, const float* 
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   PSGD_RETURN_IF(ctx->reserve(256));
   ew::Scalars* sc = static_cast<ew::Scalars*>(ctx->ws);
-  const int grid = ew::grid_for(ctx, (n + 1) / 2);
+  const bool v4 = n > 0 && (n % 8) == 0;                 // mirrored float4 blocks are 16-byte aligned
+  const int grid = ew::grid_for(ctx, v4 ? n / 8 : (n + 1) / 2);
   ew::reset_kernel<<<1, 1, 0, ctx->stream>>>(sc);
   PSGD_LAUNCH_CHECK(ctx);
-  ew::xmat_kernel<false><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
+  if (v4) ew::xmat_kernel_v4<false><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
+  else ew::xmat_kernel<false><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &sc->max_abs, 1));
-  ew::xmat_kernel<true><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
+  if (v4) ew::xmat_kernel_v4<true><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
+  else ew::xmat_kernel<true><<<grid, ew::kThreads, 0, ctx->stream>>>(a, b, v, h, n, step, tiny, sc);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -231,7 +301,10 @@ extern "C" int psgd_xmat_apply(psgd_ctx* ctx, const float* a, const float* b, co
   const void* ptrs[] = {a, b, g, out};
   PSGD_RETURN_IF(check_ptrs("xmat apply", ptrs, 4));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  ew::xmat_apply_kernel<<<ew::grid_for(ctx, (n + 1) / 2), ew::kThreads, 0, ctx->stream>>>(a, b, g, out, n);
+  if ((n % 8) == 0)
+    ew::xmat_apply_kernel_v4<<<ew::grid_for(ctx, n / 8), ew::kThreads, 0, ctx->stream>>>(a, b, g, out, n);
+  else
+    ew::xmat_apply_kernel<<<ew::grid_for(ctx, (n + 1) / 2), ew::kThreads, 0, ctx->stream>>>(a, b, g, out, n);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }

@@ -178,7 +178,7 @@ def test_uvd_rejects_bad_inputs(psgd):
 # ---------------------------------------------------------------------------------------------
 # diagonal / X-shape
 # ---------------------------------------------------------------------------------------------
-@pytest.mark.parametrize("n", [1, 2, 3, 8, 1001, 4096, 1_000_003])
+@pytest.mark.parametrize("n", [1, 2, 3, 8, 16, 1001, 4096, 1_000_000, 1_000_003])
 def test_xmat_and_diag(psgd, n):
     c = cases.vec_case(2000 + n, n)
     a, b = dev(c["a"]), dev(c["b"])
