@@ -172,6 +172,28 @@ typedef struct psgd_kron_layer {
 int psgd_kron_update_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count, float step, float tiny);
 int psgd_kron_apply_batched(psgd_ctx* ctx, const psgd_kron_layer* layers, int count);
 
+/* ---- caller-side tail of a Kron training step, over a ragged list of layers (HOST arrays of length count) ---------- */
+/* grad_norm = sqrt(sum_l sum(pre_l^2)); lr_adjust = min(grad_norm_clip_thr / grad_norm, 1) (mnist_with_lenet5.py:54-55;
+ * pass INFINITY for no clipping); W_l -= lr_adjust * lr * pre_l (+ v_l when v != NULL: the finite-difference perturbation,
+ * neural_machine_translation_with_attention.py:206).  One launch per phase for the whole list, norm reduced on the
+ * device (all-reduced across ranks when sharded). */
+typedef struct psgd_param_update {
+  float* W;          /* parameters, updated in place   */
+  const float* pre;  /* preconditioned gradient        */
+  const float* v;    /* perturbation to remove or NULL */
+  int64_t count;     /* elements                       */
+} psgd_param_update;
+int psgd_apply_updates(psgd_ctx* ctx, const psgd_param_update* items, int count, float lr, float grad_norm_clip_thr);
+/* out_l = a_l - b_l for a list: the finite-difference Hessian-vector products dG = perturbed_g - g
+ * (neural_machine_translation_with_attention.py:200). */
+typedef struct psgd_diff_item {
+  const float* a;
+  const float* b;
+  float* out;
+  int64_t count;
+} psgd_diff_item;
+int psgd_multi_sub(psgd_ctx* ctx, const psgd_diff_item* items, int count);
+
 #ifdef __cplusplus
 }
 #endif

@@ -30,6 +30,16 @@ class KronLayer(C.Structure):
     ]
 
 
+class ParamUpdate(C.Structure):
+    """Mirror of ``psgd_param_update``."""
+    _fields_ = [("W", C.c_void_p), ("pre", C.c_void_p), ("v", C.c_void_p), ("count", C.c_int64)]
+
+
+class DiffItem(C.Structure):
+    """Mirror of ``psgd_diff_item``."""
+    _fields_ = [("a", C.c_void_p), ("b", C.c_void_p), ("out", C.c_void_p), ("count", C.c_int64)]
+
+
 # name -> (restype, argtypes); every symbol include/psgd_b200.h declares
 SIGNATURES = {
     "psgd_abi_version": (C.c_int, []),
@@ -62,6 +72,8 @@ SIGNATURES = {
     "psgd_kron_apply": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [c_float_p] * 4 + [C.c_int64, C.c_int64]),
     "psgd_kron_update_batched": (C.c_int, [C.c_void_p, C.POINTER(KronLayer), C.c_int, C.c_float, C.c_float]),
     "psgd_kron_apply_batched": (C.c_int, [C.c_void_p, C.POINTER(KronLayer), C.c_int]),
+    "psgd_apply_updates": (C.c_int, [C.c_void_p, C.POINTER(ParamUpdate), C.c_int, C.c_float, C.c_float]),
+    "psgd_multi_sub": (C.c_int, [C.c_void_p, C.POINTER(DiffItem), C.c_int]),
 }
 
 _lib = None

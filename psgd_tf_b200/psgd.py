@@ -294,6 +294,50 @@ def precond_grad_kron_batched(Qls, Qrs, Grads):
     return outs
 
 
+# ---- caller-side tail of a Kron training step: one launch per phase for the whole layer list ----
+def apply_preconditioned_updates(Ws, pre_grads, lr, grad_norm_clip_thr=None, vs=None):
+    """``W -= lr_adjust*lr*g`` for every layer, in place, with the reference's optional global clipping
+    ``lr_adjust = min(grad_norm_clip_thr / sqrt(sum_l sum(g_l^2)), 1)`` (mnist_with_lenet5.py:54-56); ``vs``: the
+    finite-difference perturbations still sitting on the parameters, removed by the same pass
+    (neural_machine_translation_with_attention.py:206: ``W.assign_sub(lr*g + v)``).  The norm never visits the host."""
+    from ._lib import ParamUpdate
+    Ws = [_inplace(w, "W") for w in Ws]
+    gs = [_in(g, "pre_grad") for g in pre_grads]
+    vv = [_in(v, "v") for v in vs] if vs is not None else [None] * len(Ws)
+    if not (len(Ws) == len(gs) == len(vv)):
+        raise ValueError("apply_preconditioned_updates: lists differ in length")
+    arr = (ParamUpdate * max(len(Ws), 1))()
+    for i, (w, g, v) in enumerate(zip(Ws, gs, vv)):
+        if g.numel() != w.numel() or (v is not None and v.numel() != w.numel()):
+            raise ValueError(f"apply_preconditioned_updates: layer {i} shapes differ")
+        arr[i].W, arr[i].pre, arr[i].v, arr[i].count = w.data_ptr(), g.data_ptr(), (v.data_ptr() if v is not None else None), w.numel()
+    if not Ws:
+        return None
+    ctx = get_context(Ws[0].device.index)
+    clip = float("inf") if grad_norm_clip_thr is None else _scalar(grad_norm_clip_thr)
+    check(ctx.lib.psgd_apply_updates(ctx.handle, arr, len(Ws), _scalar(lr), clip))
+    return None
+
+
+def grad_differences(perturbed_grads, grads):
+    """``[pg - g for ...]`` in one launch: finite-difference Hessian-vector products
+    (neural_machine_translation_with_attention.py:200)."""
+    from ._lib import DiffItem
+    a = [_in(x, "perturbed_grad") for x in perturbed_grads]
+    b = [_in(x, "grad") for x in grads]
+    outs = [torch.empty_like(x) for x in a]
+    if not a:
+        return outs
+    arr = (DiffItem * len(a))()
+    for i, (x, y, o) in enumerate(zip(a, b, outs)):
+        if x.shape != y.shape:
+            raise ValueError(f"grad_differences: layer {i} shapes differ")
+        arr[i].a, arr[i].b, arr[i].out, arr[i].count = x.data_ptr(), y.data_ptr(), o.data_ptr(), x.numel()
+    ctx = get_context(a[0].device.index)
+    check(ctx.lib.psgd_multi_sub(ctx.handle, arr, len(a)))
+    return outs
+
+
 # ---------------------------------------------------------------------------------------------
 # UVd: Q = (I + U V^T) diag(d)                                               psgd.py:540-627
 # ---------------------------------------------------------------------------------------------
