@@ -60,6 +60,7 @@ struct psgd_ctx {
   int opt_direct = 0;        // streaming kernels: 1 = direct global loads instead of TMA pipeline
   int opt_gemm_path = 0;     // dense GEMMs: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
+  int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
   int opt_tc_mode = 1;       // tcgen05 GEMM A operand: 1 = through tensor memory (TS), 0 = from shared memory (SS)
   int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks

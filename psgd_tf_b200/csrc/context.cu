@@ -1,5 +1,6 @@
 // Context, workspace and error plumbing of the C ABI (include/psgd_b200.h).
 #include <stdarg.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "common.cuh"
@@ -52,6 +53,10 @@ extern "C" int psgd_create(int device, void* stream, psgd_ctx** out) {
   ctx->device = device;
   ctx->stream = static_cast<cudaStream_t>(stream);
   ctx->num_sms = prop.multiProcessorCount;
+  if (const char* e = getenv("PSGD_TRSM_BASE")) {          // tuning knob, same values as psgd_set_option("trsm_base")
+    const int v = atoi(e);
+    if (v == 128 || v == 256 || v == 512 || v == 1024 || v == 2048) ctx->opt_trsm_base = v;
+  }
   *out = ctx;
   return PSGD_OK;
 }
@@ -89,6 +94,12 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "tc_bn") == 0) {
     PSGD_REQUIRE(value == 128 || value == 256, PSGD_ERR_BAD_SHAPE, "tc_bn must be 128 or 256");
     ctx->opt_tc_bn = (int)value;
+    return PSGD_OK;
+  }
+  if (strcmp(key, "trsm_base") == 0) {
+    PSGD_REQUIRE(value == 128 || value == 256 || value == 512 || value == 1024 || value == 2048, PSGD_ERR_BAD_SHAPE,
+                 "trsm_base must be 128, 256, 512, 1024 or 2048");
+    ctx->opt_trsm_base = (int)value;
     return PSGD_OK;
   }
   if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }

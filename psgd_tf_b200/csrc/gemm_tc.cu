@@ -76,6 +76,9 @@ struct Params {
   float step, tiny;
   int colscale_recip, colscale_sq;
   int tiles_m, tiles_n, count;
+  int pair_b, pair_kind;    // block-pair mode (triangular block-inverse doubling): only tiles with (m0/b even, n0/b == m0/b + 1)
+                            // exist; K range = the n-block (kind 1) or the m-block (kind 2)
+  int negate;               // C = -(acc)
   int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs
   float* C[kMaxGroup];
   float* maxabs[kMaxGroup];
@@ -242,6 +245,21 @@ __device__ __forceinline__ void split_tile_smem(uint32_t hi_addr, uint32_t lo_ad
   }
 }
 
+// Does output tile (m0, n0) take part in the product at all?  (tiles skipped by triu are still WRITTEN, as zeros, by the
+// epilogue; tiles outside the block-pair pattern are not touched.)
+template <int BN>
+__device__ __forceinline__ bool tile_in_pattern(const Params& p, int m0, int n0) {
+  if (p.pair_b) {
+    const int bm = m0 / p.pair_b;
+    if ((bm & 1) || n0 / p.pair_b != bm + 1) return false;
+  }
+  return true;
+}
+template <int BN>
+__device__ __forceinline__ bool tile_computed(const Params& p, int m0, int n0) {
+  return tile_in_pattern<BN>(p, m0, n0) && !(p.triu && m0 >= n0 + BN);
+}
+
 // K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
 template <int BN>
 __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1) {
@@ -252,6 +270,11 @@ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n
     if (p.a_tri == 2) hi = min(hi, m0 + BM);            // op(A)[m,k] = 0 for k > m
     if (p.b_tri == 1) hi = min(hi, n0 + BN);            // op(B)[k,n] = 0 for k > n
     if (p.b_tri == 2) lo = max(lo, n0);                 // op(B)[k,n] = 0 for k < n
+    if (p.pair_b) {
+      const int base = (p.pair_kind == 1 ? n0 : m0) / p.pair_b * p.pair_b;
+      lo = max(lo, base);
+      hi = min(hi, base + p.pair_b);
+    }
   }
   kb0 = lo / BK;
   kb1 = (hi + BK - 1) / BK;
@@ -307,7 +330,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int grp = tile / tiles_per, lt = tile % tiles_per;
         const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int m0 = tm * BM, n0 = tn * BN;
-        if (p.triu && m0 >= n0 + BN) continue;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
@@ -348,7 +371,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         const int grp = tile / tiles_per, lt = tile % tiles_per;
         const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
         const int m0 = tm * BM, n0 = tn * BN;
-        if (p.triu && m0 >= n0 + BN) continue;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
         int total_kb = 0;
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
@@ -432,7 +455,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int grp = tile / tiles_per, lt = tile % tiles_per;
       const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
-      if (p.triu && m0 >= n0 + BN) continue;
+      if (!tile_computed<BN>(p, m0, n0)) continue;
       for (int prod = 0; prod < 2; ++prod) {
         if (p.K[prod] <= 0) continue;
         int kb0, kb1;
@@ -523,6 +546,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
       const int m = m0 + q * 32 + lane;
+      if (!tile_in_pattern<BN>(p, m0, n0)) continue;
       if (grp != mx_grp) { flush_max(); mx_grp = grp; }
       float* const Cg = p.C[grp];
       const float* const Dg = p.D[grp];
@@ -570,6 +594,7 @@ __global__ void __launch_bounds__(kThreads, 1)
           for (int j = 0; j < 32; ++j) {
             const int n = nbase + j;
             float x = racc[c * 32 + j];
+            if (p.negate) x = -x;
             if (csg && n < p.N) {
               float sc = csg[n];
               if (p.colscale_sq) sc = sc * sc;
@@ -650,7 +675,8 @@ static bool same_shape(const la::Gemm& x, const la::Gemm& y) {
          x.ldb2 == y.ldb2 && x.ldc == y.ldc && x.ldd == y.ldd && x.ta == y.ta && x.tb == y.tb && x.ta2 == y.ta2 &&
          x.tb2 == y.tb2 && x.triu == y.triu && x.a_tri == y.a_tri && x.b_tri == y.b_tri && x.step == y.step &&
          x.tiny == y.tiny && x.colscale_recip == y.colscale_recip && x.colscale_sq == y.colscale_sq &&
-         (x.D != nullptr) == (y.D != nullptr) && (x.K2 > 0) == (y.K2 > 0);
+         (x.D != nullptr) == (y.D != nullptr) && (x.K2 > 0) == (y.K2 > 0) && x.pair_b == y.pair_b &&
+         x.pair_kind == y.pair_kind && x.negate == y.negate;
 }
 
 // gs[0..count): identical shapes/flags, count <= kMaxGroup
@@ -677,6 +703,7 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   p.tiles_n = (g.N + BN - 1) / BN;
   p.count = count;
   p.debug = ctx->opt_tc_debug;
+  p.pair_b = g.pair_b; p.pair_kind = g.pair_kind; p.negate = g.negate ? 1 : 0;
   double work = 0.0;
   for (int i = 0; i < count; ++i) {
     const la::Gemm& q = gs[i];
@@ -760,20 +787,23 @@ int gemm_auto(psgd_ctx* ctx, const la::Gemm& g) {
 // of blocked BLAS TRSMs), and everything off the diagonal is one large tcgen05 GEMM per recursion level, so every
 // multiply-add of the solve runs on the tensor cores and every step is ONE launch for the whole group of layers.
 // ---------------------------------------------------------------------------------------------
-constexpr int kTrsmBase = 128;
+constexpr int kInvBlock = 128;         // diagonal blocks inverted by back-substitution in shared memory
 
-size_t trsm_scratch_floats(int n) { return (size_t)((n + kTrsmBase - 1) / kTrsmBase) * kTrsmBase * kTrsmBase; }
+static int round_up(int x, int m) { return (x + m - 1) / m * m; }
+// per problem: Z (n x n, explicit inverses of the diagonal base blocks) + T (n x n, scratch of the doubling steps)
+size_t trsm_scratch_floats(int n) { return 2 * (size_t)round_up(n, kInvBlock) * round_up(n, kInvBlock); }
 
-// Z_b = inv(Q[b0:b0+jb, b0:b0+jb]) for every diagonal block b (only the upper triangle of Q is read); grid = blocks.
-__global__ void __launch_bounds__(kTrsmBase) tri_inv_blocks_kernel(const float* __restrict__ Q, int ldq, int n,
-                                                                   float* __restrict__ Z) {
+// Z[b0:b0+jb, b0:b0+jb] = inv(Q[b0:b0+jb, b0:b0+jb]) for every 128-wide diagonal block b (only the upper triangle of Q is
+// read; the strictly lower part of the block is written as zeros); grid = blocks.
+__global__ void __launch_bounds__(kInvBlock) tri_inv_blocks_kernel(const float* __restrict__ Q, int ldq, int n,
+                                                                   float* __restrict__ Z, int ldz) {
   extern __shared__ float sm[];
-  float (*T)[kTrsmBase + 1] = reinterpret_cast<float (*)[kTrsmBase + 1]>(sm);
-  float (*Zs)[kTrsmBase + 1] = reinterpret_cast<float (*)[kTrsmBase + 1]>(sm + kTrsmBase * (kTrsmBase + 1));
-  const int b0 = blockIdx.x * kTrsmBase;
-  const int jb = min(kTrsmBase, n - b0);
+  float (*T)[kInvBlock + 1] = reinterpret_cast<float (*)[kInvBlock + 1]>(sm);
+  float (*Zs)[kInvBlock + 1] = reinterpret_cast<float (*)[kInvBlock + 1]>(sm + kInvBlock * (kInvBlock + 1));
+  const int b0 = blockIdx.x * kInvBlock;
+  const int jb = min(kInvBlock, n - b0);
   const int j = threadIdx.x;
-  for (int i = 0; i < kTrsmBase; ++i) {
+  for (int i = 0; i < kInvBlock; ++i) {
     T[i][j] = (i < jb && j < jb && i <= j) ? Q[(size_t)(b0 + i) * ldq + b0 + j] : (i == j ? 1.f : 0.f);
     Zs[i][j] = 0.f;
   }
@@ -788,96 +818,138 @@ __global__ void __launch_bounds__(kTrsmBase) tri_inv_blocks_kernel(const float* 
     }
   }
   __syncthreads();
-  float* Zb = Z + (size_t)blockIdx.x * kTrsmBase * kTrsmBase;
-  for (int i = 0; i < kTrsmBase; ++i) Zb[(size_t)i * kTrsmBase + j] = Zs[i][j];
+  if (j < jb)
+    for (int i = 0; i < jb; ++i) Z[(size_t)(b0 + i) * ldz + b0 + j] = Zs[i][j];
 }
 
-static int invert_diag_blocks(psgd_ctx* ctx, const float* Q, int ldq, int n, float* Z) {
-  const int blocks = (n + kTrsmBase - 1) / kTrsmBase;
-  const size_t smem = 2 * (size_t)kTrsmBase * (kTrsmBase + 1) * sizeof(float);
+static int invert_diag_blocks(psgd_ctx* ctx, const float* Q, int ldq, int n, float* Z, int ldz) {
+  const int blocks = (n + kInvBlock - 1) / kInvBlock;
+  const size_t smem = 2 * (size_t)kInvBlock * (kInvBlock + 1) * sizeof(float);
   static bool attr_done = false;
   if (!attr_done) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     attr_done = true;
   }
-  ProfScope prof(ctx, PSGD_K_TRSM, (double)n * kTrsmBase * kTrsmBase / 3.0);
-  tri_inv_blocks_kernel<<<blocks, kTrsmBase, smem, ctx->stream>>>(Q, ldq, n, Z);
+  ProfScope prof(ctx, PSGD_K_TRSM, (double)n * kInvBlock * kInvBlock / 3.0);
+  tri_inv_blocks_kernel<<<blocks, kInvBlock, smem, ctx->stream>>>(Q, ldq, n, Z, ldz);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 
-static int split_point(int lo, int hi) {
-  const int half = (hi - lo) / 2;
-  return lo + ((half + kTrsmBase - 1) / kTrsmBase) * kTrsmBase;
+// Base-block size of the solves: the recursion stops at `base`-wide diagonal blocks, which are applied as ONE GEMM with
+// their explicit inverse.  The inverses grow from the 128-wide ones by doubling,
+//     inv([A B; 0 C]) = [inv(A)  -inv(A) B inv(C); 0  inv(C)],
+// where every level is two grouped tcgen05 GEMMs over ALL block pairs of ALL layers at once (block-pair tile pattern of
+// gemm_tc_kernel): T = -(Q Z) on the (even, odd) blocks, then Z(even, odd) = Z T.  A larger base trades ~2 n base^2 / 3
+// extra flops per factor for far fewer, far larger launches: with 128-wide bases the 63 launches of a 4096-wide solve
+// spent 2/3 of their time in GEMMs with K <= 256 that run at 20-40 TFLOP/s.
+static int trsm_base(const psgd_ctx* ctx) { return ctx->opt_trsm_base; }
+
+static int build_block_inverses(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int n) {
+  const int base = trsm_base(ctx);
+  for (int t = 0; t < count; ++t) PSGD_RETURN_IF(invert_diag_blocks(ctx, ts[t].Q, ldq, n, ts[t].zinv, n));
+  std::vector<la::Gemm> gs(count);
+  const size_t toff = (size_t)round_up(n, kInvBlock) * round_up(n, kInvBlock);
+  for (int b = kInvBlock; b < base && b < n; b *= 2) {
+    for (int t = 0; t < count; ++t) {       // T(k, k+1) = -(Q(k, k+1) Z(k+1, k+1)),  k even
+      la::Gemm& g = gs[t];
+      g = la::Gemm{};
+      g.M = n; g.N = n; g.K = n;
+      g.A = ts[t].Q; g.lda = ldq;
+      g.B = ts[t].zinv; g.ldb = n;
+      g.C = ts[t].zinv + toff; g.ldc = n;
+      g.b_tri = 1; g.pair_b = b; g.pair_kind = 1; g.negate = true;
+    }
+    PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
+    for (int t = 0; t < count; ++t) {       // Z(k, k+1) = Z(k, k) T(k, k+1)
+      la::Gemm& g = gs[t];
+      g = la::Gemm{};
+      g.M = n; g.N = n; g.K = n;
+      g.A = ts[t].zinv; g.lda = n;
+      g.B = ts[t].zinv + toff; g.ldb = n;
+      g.C = ts[t].zinv; g.ldc = n;
+      g.a_tri = 1; g.pair_b = b; g.pair_kind = 2;
+    }
+    PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
+  }
+  return PSGD_OK;
 }
 
-// X[:, j0:j1] (in place) <- X[:, j0:j1] Q[j0:j1, j0:j1]^-1      for every problem of the group
-static int trsm_right_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int j0, int j1) {
+static int split_point(int lo, int hi, int base) {
+  const int half = (hi - lo) / 2;
+  return lo + ((half + base - 1) / base) * base;
+}
+
+// Solved columns live in X (the result), columns still to be solved in W (a working copy of the right-hand side):
+//   leaf    X[:, j0:j1]  = W[:, j0:j1] Z[j0:j1, j0:j1]            (out of place: a base block spans several tiles)
+//   update  W[:, mid:j1] -= X[:, j0:mid] Q[j0:mid, mid:j1]
+static int trsm_right_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int n, int j0, int j1) {
   std::vector<la::Gemm> gs(count);
-  if (j1 - j0 <= kTrsmBase) {
+  if (j1 - j0 <= trsm_base(ctx)) {
     const int jb = j1 - j0;
-    for (int t = 0; t < count; ++t) {       // in place is safe: one column tile, each CTA reads and writes its own rows
+    for (int t = 0; t < count; ++t) {
       la::Gemm& g = gs[t];
       g = la::Gemm{};
       g.M = m; g.N = jb; g.K = jb;
-      g.A = ts[t].X + j0; g.lda = ldx;
-      g.B = ts[t].zinv + (size_t)(j0 / kTrsmBase) * kTrsmBase * kTrsmBase; g.ldb = kTrsmBase;
+      g.A = ts[t].work + j0; g.lda = ldx;
+      g.B = ts[t].zinv + (size_t)j0 * n + j0; g.ldb = n;
       g.C = ts[t].X + j0; g.ldc = ldx;
       g.b_tri = 1;
     }
     return gemm_many(ctx, gs.data(), count, true);
   }
-  const int mid = split_point(j0, j1);
-  PSGD_RETURN_IF(trsm_right_rec(ctx, ts, count, ldq, ldx, m, j0, mid));
-  for (int t = 0; t < count; ++t) {         // X[:, mid:j1] -= X[:, j0:mid] Q[j0:mid, mid:j1]
+  const int mid = split_point(j0, j1, trsm_base(ctx));
+  PSGD_RETURN_IF(trsm_right_rec(ctx, ts, count, ldq, ldx, m, n, j0, mid));
+  for (int t = 0; t < count; ++t) {
     la::Gemm& g = gs[t];
     g = la::Gemm{};
     g.M = m; g.N = j1 - mid; g.K = mid - j0;
     g.A = ts[t].X + j0; g.lda = ldx;
     g.B = ts[t].Q + (size_t)j0 * ldq + mid; g.ldb = ldq;
-    g.C = ts[t].X + mid; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
+    g.C = ts[t].work + mid; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
   }
   PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
-  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, mid, j1);
+  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, n, mid, j1);
 }
 
-// X[i0:i1, :] (in place) <- Q[i0:i1, i0:i1]^-T X[i0:i1, :]
-static int trsm_left_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int i0, int i1) {
+//   leaf    X[i0:i1, :]  = Z[i0:i1, i0:i1]^T W[i0:i1, :]
+//   update  W[mid:i1, :] -= Q[i0:mid, mid:i1]^T X[i0:mid, :]
+static int trsm_left_rec(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int m, int n, int i0, int i1) {
   std::vector<la::Gemm> gs(count);
-  if (i1 - i0 <= kTrsmBase) {
+  if (i1 - i0 <= trsm_base(ctx)) {
     const int ib = i1 - i0;
-    for (int t = 0; t < count; ++t) {       // in place is safe: one row tile, each CTA reads and writes its own columns
+    for (int t = 0; t < count; ++t) {
       la::Gemm& g = gs[t];
       g = la::Gemm{};
       g.M = ib; g.N = m; g.K = ib;
-      g.A = ts[t].zinv + (size_t)(i0 / kTrsmBase) * kTrsmBase * kTrsmBase; g.lda = kTrsmBase; g.ta = true;
-      g.B = ts[t].X + (size_t)i0 * ldx; g.ldb = ldx;
+      g.A = ts[t].zinv + (size_t)i0 * n + i0; g.lda = n; g.ta = true;
+      g.B = ts[t].work + (size_t)i0 * ldx; g.ldb = ldx;
       g.C = ts[t].X + (size_t)i0 * ldx; g.ldc = ldx;
       g.a_tri = 2;
     }
     return gemm_many(ctx, gs.data(), count, true);
   }
-  const int mid = split_point(i0, i1);
-  PSGD_RETURN_IF(trsm_left_rec(ctx, ts, count, ldq, ldx, m, i0, mid));
-  for (int t = 0; t < count; ++t) {         // X[mid:i1, :] -= Q[i0:mid, mid:i1]^T X[i0:mid, :]
+  const int mid = split_point(i0, i1, trsm_base(ctx));
+  PSGD_RETURN_IF(trsm_left_rec(ctx, ts, count, ldq, ldx, m, n, i0, mid));
+  for (int t = 0; t < count; ++t) {
     la::Gemm& g = gs[t];
     g = la::Gemm{};
     g.M = i1 - mid; g.N = m; g.K = mid - i0;
     g.A = ts[t].Q + (size_t)i0 * ldq + mid; g.lda = ldq; g.ta = true;
     g.B = ts[t].X + (size_t)i0 * ldx; g.ldb = ldx;
-    g.C = ts[t].X + (size_t)mid * ldx; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
+    g.C = ts[t].work + (size_t)mid * ldx; g.ldc = ldx; g.D = g.C; g.ldd = ldx;
   }
   PSGD_RETURN_IF(gemm_many(ctx, gs.data(), count, true));
-  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, mid, i1);
+  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, n, mid, i1);
 }
 
 static bool trsm_tc_ok(const psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldx, int n, int m) {
   if (ctx->opt_gemm_path == 1) return false;
   const bool big = n >= 512 && m >= 256;
   if (!(ctx->opt_gemm_path == 2 || big)) return false;
-  if (n <= kTrsmBase || (ldq % 4) != 0 || (ldx % 4) != 0) return false;
+  if (n <= kInvBlock || (n % 4) != 0 || (ldq % 4) != 0 || (ldx % 4) != 0) return false;
   for (int t = 0; t < count; ++t)
-    if (!aligned16(ts[t].Q) || !aligned16(ts[t].X) || !ts[t].zinv) return false;
+    if (!aligned16(ts[t].Q) || !aligned16(ts[t].X) || !ts[t].zinv || !ts[t].work || !aligned16(ts[t].work)) return false;
   return true;
 }
 
@@ -889,13 +961,11 @@ int trsm_right_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, 
       PSGD_RETURN_IF(la::trsm_right_upper(ctx, ts[t].Q, ldq, ts[t].B, ldb, ts[t].X, ldx, m, n));
     return PSGD_OK;
   }
-  for (int t = 0; t < count; ++t) {
-    if (ts[t].X != ts[t].B)
-      PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].X, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)n * 4, m,
-                                        cudaMemcpyDeviceToDevice, ctx->stream));
-    PSGD_RETURN_IF(invert_diag_blocks(ctx, ts[t].Q, ldq, n, ts[t].zinv));
-  }
-  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, 0, n);
+  for (int t = 0; t < count; ++t)
+    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].work, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)n * 4, m,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  PSGD_RETURN_IF(build_block_inverses(ctx, ts, count, ldq, n));
+  return trsm_right_rec(ctx, ts, count, ldq, ldx, m, n, 0, n);
 }
 
 // X = Q^-T B : Q [n,n] upper, B,X [n,m]
@@ -906,13 +976,11 @@ int trsm_left_many(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int ldb, i
       PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, ts[t].Q, ldq, ts[t].B, ldb, ts[t].X, ldx, n, m));
     return PSGD_OK;
   }
-  for (int t = 0; t < count; ++t) {
-    if (ts[t].X != ts[t].B)
-      PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].X, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)m * 4, n,
-                                        cudaMemcpyDeviceToDevice, ctx->stream));
-    PSGD_RETURN_IF(invert_diag_blocks(ctx, ts[t].Q, ldq, n, ts[t].zinv));
-  }
-  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, 0, n);
+  for (int t = 0; t < count; ++t)
+    PSGD_CUDA_CHECK(cudaMemcpy2DAsync(ts[t].work, (size_t)ldx * 4, ts[t].B, (size_t)ldb * 4, (size_t)m * 4, n,
+                                      cudaMemcpyDeviceToDevice, ctx->stream));
+  PSGD_RETURN_IF(build_block_inverses(ctx, ts, count, ldq, n));
+  return trsm_left_rec(ctx, ts, count, ldq, ldx, m, n, 0, n);
 }
 
 }  // namespace tc

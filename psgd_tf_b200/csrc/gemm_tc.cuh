@@ -18,13 +18,15 @@ int gemm_tc(psgd_ctx* ctx, const la::Gemm& g);
 // engine whenever the operands allow it, regardless of size (TRSM recursion).
 int gemm_many(psgd_ctx* ctx, const la::Gemm* gs, int count, bool force_tc);
 
-// Grouped triangular solves.  zinv: per-problem scratch of trsm_scratch_floats(n) floats (inverses of the diagonal
-// blocks); B may alias X.
+// Grouped triangular solves.  zinv: per-problem scratch of trsm_scratch_floats(n) floats (explicit inverses of the
+// diagonal base blocks + doubling scratch); work: per-problem scratch shaped like X (working copy of the right-hand
+// side); B may alias X.
 struct Trsm {
   const float* Q;
   const float* B;
   float* X;
   float* zinv;
+  float* work;
 };
 size_t trsm_scratch_floats(int n);
 // X = B Q^-1 : Q [n,n] upper, B,X [m,n]

@@ -274,7 +274,7 @@ struct Layer {
   float *Ql_out, *Qr_out, *out;
   // scratch
   Scal* sc;
-  float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv;
+  float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv, *xwork;
   float *t1, *t2, *t3, *P, *addlast;
   float* nspart;   // (normalization, scaling): partial tables of the fused streaming kernels
 };
@@ -291,9 +291,9 @@ static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const 
 // ---------------------------------------------------------------------------------------------
 static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
   const size_t MN = (size_t)M * N;
-  size_t f = 64 + fsize(kl, M) + fsize(kr, N) + 3 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
+  size_t f = 64 + fsize(kl, M) + fsize(kr, N) + 4 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
              2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
-  f += tc::trsm_scratch_floats((int)M) + tc::trsm_scratch_floats((int)N);
+  f += tc::trsm_scratch_floats((int)(M > N ? M : N));
   if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) f += ks::ns_update_scratch_floats((int)M, (int)N) + 64;
   return f;
 }
@@ -316,6 +316,7 @@ static void carve_update(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
   L.sb = c.take<float>(N);
   L.gvec = c.take<float>(N);
   L.zinv = c.take<float>(tc::trsm_scratch_floats(M > N ? M : N));
+  L.xwork = c.take<float>(MN);
   L.nspart = (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) ? c.take<float>(ks::ns_update_scratch_floats(M, N)) : nullptr;
 }
 
@@ -345,10 +346,10 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Qlb, M, false, L.T1, N, false, L.A, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
     ts.clear();                                                          // W = dX Qr^-1            psgd.py:174
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.T1, L.zinv});
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.T1, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
     ts.clear();                                                          // Bt = Ql^-T W
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.T1, L.Bt, L.zinv});
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.T1, L.Bt, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
   } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
     for (auto& L : Ls) {
@@ -364,7 +365,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       PSGD_LAUNCH_CHECK(ctx);
     }
     ts.clear();                                                          // Bt = (.) Qr^-1          psgd.py:233
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.T1, L.Bt, L.zinv});
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.T1, L.Bt, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
   } else if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {
     gs.clear();                                                          // A = (Ql dG) * qr        psgd.py:295-296
@@ -375,7 +376,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     }
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
     ts.clear();                                                          // Bt = Ql^-T dX           psgd.py:298
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv});
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
     for (auto& L : Ls) {
       col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Bt, L.Qrb, M, N);                  // :299

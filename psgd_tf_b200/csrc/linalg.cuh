@@ -30,6 +30,10 @@ struct Gemm {
   // K-range hints (product 0 only; the engines may skip structurally-zero K blocks, never required for correctness
   // of dense data): 0 none, 1 = op(.) upper triangular, 2 = lower triangular, viewed as op(A)[M,K] / op(B)[K,N]
   int a_tri = 0, b_tri = 0;
+  // block-pair pattern (tensor-core engine only; triangular block-inverse doubling): only output tiles in blocks
+  // (k, k+1), k even, of size pair_b exist; K range = the block of the column (kind 1) or of the row (kind 2)
+  int pair_b = 0, pair_kind = 0;
+  bool negate = false;               // C = -acc
   const float* colscale = nullptr;   // acc *= colscale[n]   (or its reciprocal)
   bool colscale_recip = false;
   bool colscale_sq = false;          // use colscale[n]^2
