@@ -526,6 +526,27 @@ class UVd:
         self._V = torch.randn(num_params, rank_of_modification, device=dev, dtype=torch.float32) * uv_scale
         self._d = torch.ones(num_params, 1, device=dev, dtype=torch.float32) * preconditioner_init_scale
 
+    # -- state (de)serialisation: the reference leaves checkpointing to the caller (state = plain variables) -------
+    _HYPERS = ("lr_params", "lr_preconditioner", "grad_clip_max_norm", "preconditioner_update_probability",
+               "exact_hessian_vector_product")
+
+    def state_dict(self):
+        """Preconditioner state, flat parameters and hyper-parameters (tensors are the live buffers, not copies)."""
+        d = {"U": self._U, "V": self._V, "d": self._d, "params": self._flat_params}
+        d.update({k: getattr(self, k).value for k in self._HYPERS})
+        return d
+
+    def load_state_dict(self, state):
+        with torch.no_grad():
+            for name, dst in (("U", self._U), ("V", self._V), ("d", self._d), ("params", self._flat_params)):
+                src = state[name]
+                if tuple(src.shape) != tuple(dst.shape):
+                    raise ValueError(f"load_state_dict: {name} has shape {tuple(src.shape)}, expected {tuple(dst.shape)}")
+                dst.copy_(src)
+        for k in self._HYPERS:
+            if k in state:
+                getattr(self, k).assign(state[k])
+
     # -- the hot path, autodiff-agnostic -----------------------------------------------------------
     @staticmethod
     def _flatten(ts):
