@@ -136,6 +136,16 @@ int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx, const floa
 /* Replaces precond_grad_dense (psgd.py:45-63): out = Q^T (Q g). */
 int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n);
 
+/* ---- sparse-LU preconditioner Q = L U, L = [L1 0; L2 diag(l3)], U = [U1 U2; 0 diag(u3)] --------------------------- */
+/* Replaces update_precond_splu (psgd.py:396-477) on the already concatenated dx, dg: [n].  L12 = [L1; L2]: [n, r],
+ * U12 = [U1 U2]: [r, n], l3, u3: [n - r]; 1 <= r <= 32.  Functional: results in the *_out buffers (same shapes). */
+int psgd_splu_update(psgd_ctx* ctx, const float* L12, const float* l3, const float* U12, const float* u3,
+                     const float* dx, const float* dg, float* L12_out, float* l3_out, float* U12_out, float* u3_out,
+                     int64_t n, int r, float step, float tiny);
+/* Replaces precond_grad_splu (psgd.py:483-524): out = U^T L^T L U g, g, out: [n]. */
+int psgd_splu_apply(psgd_ctx* ctx, const float* L12, const float* l3, const float* U12, const float* u3,
+                    const float* g, float* out, int64_t n, int r);
+
 /* ---- building block ------------------------------------------------------------------------ */
 /* C[M,N] = op(A) op(B), row-major fp32 (ta/tb: transpose flags as in tf.matmul(transpose_a, transpose_b)), through
  * engine 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32.  triu: zero the strictly lower triangle of C.  a_tri/b_tri:

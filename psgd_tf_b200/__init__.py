@@ -8,6 +8,7 @@ functional API of lixilinx/psgd_tf's ``preconditioned_stochastic_gradient_descen
 from .psgd import (  # noqa: F401
     dtype, _tiny, seed, get_context,
     update_precond_dense, precond_grad_dense,
+    update_precond_splu, precond_grad_splu,
     update_precond_kron, precond_grad_kron,
     update_precond_kron_batched, precond_grad_kron_batched,
     _update_precond_dense_dense, _precond_grad_dense_dense,

@@ -66,6 +66,8 @@ SIGNATURES = {
     "psgd_xmat_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 4 + [C.c_int64]),
     "psgd_dense_update": (C.c_int, [C.c_void_p] + [c_float_p] * 4 + [C.c_int64, C.c_float, C.c_float]),
     "psgd_dense_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 3 + [C.c_int64]),
+    "psgd_splu_update": (C.c_int, [C.c_void_p] + [c_float_p] * 10 + [C.c_int64, C.c_int, C.c_float, C.c_float]),
+    "psgd_splu_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 6 + [C.c_int64, C.c_int]),
     "psgd_gemm": (C.c_int, [C.c_void_p, C.c_int, C.c_int, C.c_int, C.c_int, c_float_p, C.c_int, C.c_int, c_float_p, C.c_int,
                             C.c_int, c_float_p, C.c_int, C.c_int, C.c_int, C.c_int]),
     "psgd_kron_update": (C.c_int, [C.c_void_p, C.c_int, C.c_int] + [c_float_p] * 6 + [C.c_int64, C.c_int64, C.c_float, C.c_float]),

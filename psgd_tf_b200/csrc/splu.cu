@@ -1,0 +1,551 @@
+// Sparse-LU (SPLU) preconditioner  Q = L U,  L = [L1 0; L2 diag(l3)],  U = [U1 U2; 0 diag(u3)]   (SURVEY.md section 8f).
+//
+// Replaces the TensorFlow op sequences of update_precond_splu (psgd.py:396-477) and precond_grad_splu (psgd.py:483-524)
+// on the already concatenated vectors dx, dg, g: [n].  L12 = [L1; L2] is [n, r] row-major, U12 = [U1 U2] is [r, n]
+// row-major, l3, u3: [n - r].
+//
+// Same shape of computation as UVd: every big operand is indexed by the parameter index j, so a call is a short
+// chain of streaming passes over (L2, U2, l3, u3, dx2, dg2) separated by tiny r x r kernels (one warp):
+//
+//   update:  balance maxima -> small0 (rho, balanced corners)
+//            pass 1 (reduce)      U2 dg2                                                         psgd.py:430
+//            small 1              Ug1, Qg1, iUtx1                                                :430-436
+//            pass 2 (map+reduce)  Qg2, iQtx2 per j;  L2^T iQtx2, L2^T Qg2                        :431-442
+//            small 2              iQtx1, LtQg1, Pg1, iLiQtx1                                     :440-448
+//            pass 3 (map+reduce)  Pg2, iPx2 per j;  U2 iPx2;  max|grad2|, max|grad3| of both factors  :443-474
+//            small 3              iPx1, grad1 (both), steps, new L1 / U1, rank-2 coefficient vectors   :452-476
+//            pass 4 (map)         new L2, l3, U2, u3                                             :464-478
+//   apply:   pass A1 (reduce) U2 g2 -> small -> pass A2 (map+reduce) Qg2, L2^T Qg2 -> small -> pass A3 (map) result.
+//
+// The reference re-balances the factors first (L /= rho, U *= rho, :411-417); the passes apply rho on the fly, so the
+// balanced factors are never materialised.  Cross-block reductions are two-stage and fixed-order (float64 final stage).
+// r <= 32 (the reference's demo uses r = 10, demo_usage_of_all_preconditioners.py:45).
+#include <math.h>
+
+#include "common.cuh"
+
+namespace psgd {
+namespace splu {
+
+constexpr int kMaxR = 32;
+constexpr int kThreads = 256;
+constexpr int kWarps = kThreads / 32;
+
+struct State {
+  float rho;
+  float stepL, stepU;
+  float maxL, maxU;            // atomic max targets (grad2 / grad3 parts), non-negative
+  float L1[kMaxR * kMaxR];     // balanced corners, row-major r x r
+  float U1[kMaxR * kMaxR];
+  float dx1[kMaxR], dg1[kMaxR];
+  float Ug1[kMaxR], Qg1[kMaxR], iUtx1[kMaxR], iQtx1[kMaxR], LtQg1[kMaxR], Pg1[kMaxR], iLiQtx1[kMaxR];
+  float cL1[kMaxR], cL2[kMaxR], cU1[kMaxR], cU2[kMaxR];
+};
+
+struct Args {
+  const float* L12; const float* l3; const float* U12; const float* u3;   // inputs (unbalanced)
+  const float* dx; const float* dg;                                        // [n]
+  float* L12_out; float* l3_out; float* U12_out; float* u3_out;
+  float* v0; float* v1; float* v2; float* v3;                              // [m] scratch vectors
+  float* partial;                                                          // [grid][2 * kMaxR]
+  State* st;
+  long long n;
+  int r;
+  float step, tiny;
+};
+
+// block-wide fixed-order reduction of per-thread accumulators acc[0..cnt) -> partial[blockIdx.x][off + k]
+template <int RM>
+__device__ __forceinline__ void block_reduce_to(const float (&acc)[RM], int cnt, float* partial, int off) {
+  __shared__ float red[kWarps][RM];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __syncthreads();
+#pragma unroll
+  for (int k = 0; k < RM; ++k) {
+    if (k < cnt) {
+      const float s = warp_sum(acc[k]);
+      if (lane == 0) red[warp][k] = s;
+    }
+  }
+  __syncthreads();
+  if ((int)threadIdx.x < cnt) {
+    float s = 0.f;
+#pragma unroll
+    for (int w = 0; w < kWarps; ++w) s += red[w][threadIdx.x];
+    partial[(size_t)blockIdx.x * 2 * kMaxR + off + threadIdx.x] = s;
+  }
+}
+
+// out[k] = sum over blocks of partial[b][off + k], k < r, by one warp: lanes stride the blocks (independent loads), then a
+// fixed butterfly in float64 -- the order depends only on (nblocks, lane count), so results are deterministic.
+__device__ __forceinline__ void warp_sum_partials(const float* partial, int nblocks, int off, int r, float* out, int lane) {
+  for (int k = 0; k < r; ++k) {
+    double s = 0.0;
+    for (int b = lane; b < nblocks; b += 32) s += (double)partial[(size_t)b * 2 * kMaxR + off + k];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) out[k] = (float)s;
+  }
+  __syncwarp();
+}
+
+// ---- balance maxima (no abs, as the reference: psgd.py:411-412) ---------------------------------------------------
+__global__ void __launch_bounds__(kThreads) max_kernel(Args a, float* __restrict__ pmax) {
+  __shared__ float red[kWarps][2];
+  const long long m = a.n - a.r;
+  float ml = -INFINITY, mu = -INFINITY;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    ml = fmaxf(ml, a.l3[j]);
+    mu = fmaxf(mu, a.u3[j]);
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < a.r) {
+    ml = fmaxf(ml, a.L12[(size_t)threadIdx.x * a.r + threadIdx.x]);        // diag of L12 [n, r]
+    mu = fmaxf(mu, a.U12[(size_t)threadIdx.x * a.n + threadIdx.x]);        // diag of U12 [r, n]
+  }
+  ml = warp_max(ml); mu = warp_max(mu);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ml; red[threadIdx.x >> 5][1] = mu; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kWarps; ++w) { red[0][0] = fmaxf(red[0][0], red[w][0]); red[0][1] = fmaxf(red[0][1], red[w][1]); }
+    pmax[2 * blockIdx.x] = red[0][0];
+    pmax[2 * blockIdx.x + 1] = red[0][1];
+  }
+}
+
+// rho, balanced corners, leading r entries of dx / dg.  update: balance = 1; apply: balance = 0 (rho = 1, v1 = g)
+__global__ void __launch_bounds__(32) small0_kernel(Args a, const float* __restrict__ pmax, int nblocks, int balance) {
+  State* st = a.st;
+  const int lane = threadIdx.x, r = a.r;
+  float rho = 1.0f;
+  if (balance) {
+    float ml = -INFINITY, mu = -INFINITY;
+    for (int b = lane; b < nblocks; b += 32) { ml = fmaxf(ml, pmax[2 * b]); mu = fmaxf(mu, pmax[2 * b + 1]); }
+    ml = warp_max(ml); mu = warp_max(mu);
+    rho = sqrtf(ml / mu);                                                  // psgd.py:413
+  }
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    st->L1[e] = balance ? a.L12[(size_t)i * r + j] / rho : a.L12[(size_t)i * r + j];        // :414
+    st->U1[e] = balance ? rho * a.U12[(size_t)i * a.n + j] : a.U12[(size_t)i * a.n + j];    // :416
+  }
+  if (lane < r) {
+    st->dx1[lane] = a.dx ? a.dx[lane] : 0.f;
+    st->dg1[lane] = a.dg[lane];
+  }
+  if (lane == 0) { st->rho = rho; st->maxL = 0.f; st->maxU = 0.f; }
+}
+
+// ---- pass 1 / A1:  partial[b][k] = sum_j (rho U2[k, j]) w[j],  w = dg2 (update) or g2 (apply) ------------------------
+template <int RM>
+__global__ void __launch_bounds__(kThreads) pass1_kernel(Args a) {
+  const long long m = a.n - a.r;
+  const int r = a.r;
+  const float rho = a.st->rho;
+  const float* U2 = a.U12 + r;
+  const float* w = a.dg + r;
+  float acc[RM];
+#pragma unroll
+  for (int k = 0; k < RM; ++k) acc[k] = 0.f;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    const float wj = w[j];
+#pragma unroll
+    for (int k = 0; k < RM; ++k)
+      if (k < r) acc[k] = fmaf(rho * U2[(size_t)k * a.n + j], wj, acc[k]);
+  }
+  block_reduce_to<RM>(acc, r, a.partial, 0);
+}
+
+// ---- small 1: Ug1 = U1 dg1 + U2 dg2, Qg1 = L1 Ug1, iUtx1 = U1^-T dx1 (update only)          psgd.py:430-436 -----------
+__global__ void __launch_bounds__(32) small1_kernel(Args a, int nblocks, int update) {
+  State* st = a.st;
+  __shared__ float sUg1[kMaxR], sp[kMaxR];
+  const int lane = threadIdx.x, r = a.r;
+  warp_sum_partials(a.partial, nblocks, 0, r, sp, lane);
+  if (lane < r) {
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(st->U1[lane * r + k], st->dg1[k], s);
+    s = s + sp[lane];
+    sUg1[lane] = s;
+    st->Ug1[lane] = s;
+  }
+  __syncwarp();
+  if (lane < r) {
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(st->L1[lane * r + k], sUg1[k], s);
+    st->Qg1[lane] = s;
+  }
+  if (update && lane == 0) {
+    // U1^T x = dx1, reading only the upper triangle of U1 (U1^T lower -> forward substitution)
+    float x[kMaxR];
+    for (int i = 0; i < r; ++i) {
+      float s = st->dx1[i];
+      for (int k = 0; k < i; ++k) s -= st->U1[k * r + i] * x[k];
+      x[i] = s / st->U1[i * r + i];
+      st->iUtx1[i] = x[i];
+    }
+  }
+}
+
+// ---- pass 2: per j  Qg2, iQtx2 (stored);  partial sums L2^T iQtx2 (off 0) and L2^T Qg2 (off kMaxR)   psgd.py:431-442 ----
+// apply (update = 0): Qg2 = L2 Ug1 + l3 u3 g2 (stored), partial L2^T Qg2                       psgd.py:507-512
+template <int RM>
+__global__ void __launch_bounds__(kThreads) pass2_kernel(Args a, int update) {
+  const long long m = a.n - a.r;
+  const int r = a.r;
+  const State* st = a.st;
+  const float rho = st->rho;
+  const float* L2 = a.L12 + (size_t)r * r;
+  const float* U2 = a.U12 + r;
+  float ug1[RM], iu1[RM], pa[RM], pb[RM];
+#pragma unroll
+  for (int k = 0; k < RM; ++k) {
+    ug1[k] = k < r ? st->Ug1[k] : 0.f;
+    iu1[k] = (update && k < r) ? st->iUtx1[k] : 0.f;
+    pa[k] = 0.f; pb[k] = 0.f;
+  }
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    const float l3 = update ? a.l3[j] / rho : a.l3[j];
+    const float u3 = update ? rho * a.u3[j] : a.u3[j];
+    float lrow[RM];
+    float dotL = 0.f, dotU = 0.f;
+#pragma unroll
+    for (int k = 0; k < RM; ++k) {
+      if (k < r) {
+        lrow[k] = update ? L2[(size_t)j * r + k] / rho : L2[(size_t)j * r + k];
+        dotL = fmaf(lrow[k], ug1[k], dotL);
+        if (update) dotU = fmaf(rho * U2[(size_t)k * a.n + j], iu1[k], dotU);
+      }
+    }
+    const float Ug2 = u3 * a.dg[r + j];                                   // :431 / :507
+    const float Qg2 = dotL + l3 * Ug2;                                     // :434 / :510
+    a.v0[j] = Qg2;
+    float iQtx2 = 0.f;
+    if (update) {
+      const float iUtx2 = (a.dx[r + j] - dotU) / u3;                       // :437
+      iQtx2 = iUtx2 / l3;                                                  // :439
+      a.v1[j] = iQtx2;
+    }
+#pragma unroll
+    for (int k = 0; k < RM; ++k)
+      if (k < r) { pa[k] = fmaf(lrow[k], iQtx2, pa[k]); pb[k] = fmaf(lrow[k], Qg2, pb[k]); }
+  }
+  block_reduce_to<RM>(pa, update ? r : 0, a.partial, 0);
+  block_reduce_to<RM>(pb, r, a.partial, kMaxR);
+}
+
+// ---- small 2: iQtx1, LtQg1, Pg1, iLiQtx1                                                     psgd.py:440-448 ------------
+// apply: LtQg1 = L1^T Qg1 + L2^T Qg2; out[:r] = U1^T LtQg1                                     psgd.py:512-515
+__global__ void __launch_bounds__(32) small2_kernel(Args a, int nblocks, int update, float* __restrict__ out) {
+  State* st = a.st;
+  __shared__ float sLt[kMaxR], spa[kMaxR], spb[kMaxR];
+  const int lane = threadIdx.x, r = a.r;
+  if (update) warp_sum_partials(a.partial, nblocks, 0, r, spa, lane);
+  warp_sum_partials(a.partial, nblocks, kMaxR, r, spb, lane);
+  if (lane < r) {
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(st->L1[k * r + lane], st->Qg1[k], s);       // (L1^T Qg1)[lane]
+    s = s + spb[lane];
+    sLt[lane] = s;
+    st->LtQg1[lane] = s;
+  }
+  __syncwarp();
+  if (lane < r) {
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(st->U1[k * r + lane], sLt[k], s);           // (U1^T LtQg1)[lane]
+    st->Pg1[lane] = s;
+    if (!update) out[lane] = s;
+  }
+  if (update && lane == 0) {
+    float x[kMaxR], y[kMaxR];
+    // L1^T x = iUtx1 - L2^T iQtx2, lower triangle of L1 only (L1^T upper -> back substitution)      :440
+    for (int i = r - 1; i >= 0; --i) {
+      float s = st->iUtx1[i] - spa[i];
+      for (int k = i + 1; k < r; ++k) s -= st->L1[k * r + i] * x[k];
+      x[i] = s / st->L1[i * r + i];
+      st->iQtx1[i] = x[i];
+    }
+    // L1 y = iQtx1 : forward substitution                                                            :448
+    for (int i = 0; i < r; ++i) {
+      float s = x[i];
+      for (int k = 0; k < i; ++k) s -= st->L1[i * r + k] * y[k];
+      y[i] = s / st->L1[i * r + i];
+      st->iLiQtx1[i] = y[i];
+    }
+  }
+}
+
+// ---- pass 3: Pg2, iPx2 per j (stored); partial U2 iPx2; max |grad2|, |grad3| of both factors   psgd.py:443-474 ----------
+// apply (update = 0): out[r + j] = U2[:, j] . LtQg1 + u3 l3 Qg2                                   psgd.py:513-516
+template <int RM>
+__global__ void __launch_bounds__(kThreads) pass3_kernel(Args a, int update, float* __restrict__ out) {
+  __shared__ float redm[kWarps][2];
+  const long long m = a.n - a.r;
+  const int r = a.r;
+  State* st = a.st;
+  const float rho = st->rho;
+  const float* L2 = a.L12 + (size_t)r * r;
+  const float* U2 = a.U12 + r;
+  float lt1[RM], il1[RM], qg1[RM], iq1[RM], pg1[RM], dx1[RM], pc[RM];
+#pragma unroll
+  for (int k = 0; k < RM; ++k) {
+    const bool ok = k < r;
+    lt1[k] = ok ? st->LtQg1[k] : 0.f;
+    il1[k] = (ok && update) ? st->iLiQtx1[k] : 0.f;
+    qg1[k] = (ok && update) ? st->Qg1[k] : 0.f;
+    iq1[k] = (ok && update) ? st->iQtx1[k] : 0.f;
+    pg1[k] = (ok && update) ? st->Pg1[k] : 0.f;
+    dx1[k] = (ok && update) ? st->dx1[k] : 0.f;
+    pc[k] = 0.f;
+  }
+  float mxL = 0.f, mxU = 0.f;
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    const float l3 = update ? a.l3[j] / rho : a.l3[j];
+    const float u3 = update ? rho * a.u3[j] : a.u3[j];
+    const float Qg2 = a.v0[j];
+    float urow[RM];
+    float dotU = 0.f, dotL = 0.f;
+#pragma unroll
+    for (int k = 0; k < RM; ++k) {
+      if (k < r) {
+        urow[k] = update ? rho * U2[(size_t)k * a.n + j] : U2[(size_t)k * a.n + j];
+        dotU = fmaf(urow[k], lt1[k], dotU);
+        if (update) dotL = fmaf(L2[(size_t)j * r + k] / rho, il1[k], dotL);
+      }
+    }
+    const float LtQg2 = l3 * Qg2;                                           // :443 / :513
+    const float Pg2 = dotU + u3 * LtQg2;                                    // :446 / :516
+    if (!update) { out[r + j] = Pg2; continue; }
+    const float iQtx2 = a.v1[j];
+    const float iLiQtx2 = (iQtx2 - dotL) / l3;                              // :449
+    const float iPx2 = iLiQtx2 / u3;                                        // :451
+    a.v2[j] = Pg2;
+    a.v3[j] = iPx2;
+    const float dgj = a.dg[r + j], dxj = a.dx[r + j];
+    mxL = fmaxf(mxL, fabsf(Qg2 * Qg2 - iQtx2 * iQtx2));                     // grad3 of L   :458
+    mxU = fmaxf(mxU, fabsf(Pg2 * dgj - dxj * iPx2));                        // grad3 of U   :471
+#pragma unroll
+    for (int k = 0; k < RM; ++k) {
+      if (k < r) {
+        pc[k] = fmaf(urow[k], iPx2, pc[k]);
+        mxL = fmaxf(mxL, fabsf(Qg2 * qg1[k] - iQtx2 * iq1[k]));             // grad2 of L   :457
+        mxU = fmaxf(mxU, fabsf(pg1[k] * dgj - dx1[k] * iPx2));              // grad2 of U   :470
+      }
+    }
+  }
+  if (!update) return;
+  block_reduce_to<RM>(pc, r, a.partial, 0);
+  mxL = warp_max(mxL); mxU = warp_max(mxU);
+  if ((threadIdx.x & 31) == 0) { redm[threadIdx.x >> 5][0] = mxL; redm[threadIdx.x >> 5][1] = mxU; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    for (int w = 1; w < kWarps; ++w) { redm[0][0] = fmaxf(redm[0][0], redm[w][0]); redm[0][1] = fmaxf(redm[0][1], redm[w][1]); }
+    atomic_max_nonneg(&st->maxL, redm[0][0]);
+    atomic_max_nonneg(&st->maxU, redm[0][1]);
+  }
+}
+
+// ---- small 3: iPx1, grad1 of both factors, steps, new L1 / U1, coefficient vectors            psgd.py:452-476 ------------
+__global__ void __launch_bounds__(32) small3_kernel(Args a, int nblocks) {
+  State* st = a.st;
+  __shared__ float g1[kMaxR][kMaxR + 1];
+  __shared__ float sx[kMaxR];
+  __shared__ float spc[kMaxR];
+  const int lane = threadIdx.x, r = a.r;
+  warp_sum_partials(a.partial, nblocks, 0, r, spc, lane);
+  if (lane == 0) {
+    // U1 x = iLiQtx1 - U2 iPx2 : back substitution                                    :452
+    for (int i = r - 1; i >= 0; --i) {
+      float s = st->iLiQtx1[i] - spc[i];
+      for (int k = i + 1; k < r; ++k) s -= st->U1[i * r + k] * sx[k];
+      sx[i] = s / st->U1[i * r + i];
+    }
+  }
+  __syncwarp();
+  // ---- L: grad1 = tril(Qg1 Qg1^T - iQtx1 iQtx1^T)                                   :455-456
+  float mx = 0.f;
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    const float g = (j <= i) ? (st->Qg1[i] * st->Qg1[j] - st->iQtx1[i] * st->iQtx1[j]) : 0.f;
+    g1[i][j] = g;
+    mx = fmaxf(mx, fabsf(g));
+  }
+  mx = fmaxf(warp_max(mx), st->maxL);
+  const float stepL = a.step / (mx + a.tiny);                                          // :462
+  __syncwarp();
+  for (int e = lane; e < r * r; e += 32) {                                            // newL1 = L1 - (step0 grad1) L1   :463
+    const int i = e / r, j = e % r;
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(stepL * g1[i][k], st->L1[k * r + j], s);
+    a.L12_out[(size_t)i * r + j] = st->L1[e] - s;
+  }
+  if (lane < r) {                                                                      // row vectors Qg1^T L1, iQtx1^T L1
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < r; ++k) { s1 = fmaf(st->Qg1[k], st->L1[k * r + lane], s1); s2 = fmaf(st->iQtx1[k], st->L1[k * r + lane], s2); }
+    st->cL1[lane] = s1; st->cL2[lane] = s2;
+  }
+  __syncwarp();
+  // ---- U: grad1 = triu(Pg1 dg1^T - dx1 iPx1^T)                                      :468-469
+  mx = 0.f;
+  for (int e = lane; e < r * r; e += 32) {
+    const int i = e / r, j = e % r;
+    const float g = (j >= i) ? (st->Pg1[i] * st->dg1[j] - st->dx1[i] * sx[j]) : 0.f;
+    g1[i][j] = g;
+    mx = fmaxf(mx, fabsf(g));
+  }
+  mx = fmaxf(warp_max(mx), st->maxU);
+  const float stepU = a.step / (mx + a.tiny);                                          // :475
+  __syncwarp();
+  for (int e = lane; e < r * r; e += 32) {                                            // newU1 = U1 - U1 (step0 grad1)   :476
+    const int i = e / r, j = e % r;
+    float s = 0.f;
+    for (int k = 0; k < r; ++k) s = fmaf(st->U1[i * r + k], stepU * g1[k][j], s);
+    a.U12_out[(size_t)i * a.n + j] = st->U1[e] - s;
+  }
+  if (lane < r) {                                                                      // column vectors U1 Pg1, U1 dx1
+    float s1 = 0.f, s2 = 0.f;
+    for (int k = 0; k < r; ++k) { s1 = fmaf(st->U1[lane * r + k], st->Pg1[k], s1); s2 = fmaf(st->U1[lane * r + k], st->dx1[k], s2); }
+    st->cU1[lane] = s1; st->cU2[lane] = s2;
+  }
+  if (lane == 0) { st->stepL = stepL; st->stepU = stepU; }
+}
+
+// ---- pass 4: new L2, l3, U2, u3                                                               psgd.py:464-478 ------------
+template <int RM>
+__global__ void __launch_bounds__(kThreads) pass4_kernel(Args a) {
+  const long long m = a.n - a.r;
+  const int r = a.r;
+  const State* st = a.st;
+  const float rho = st->rho, stepL = st->stepL, stepU = st->stepU;
+  const float* L2 = a.L12 + (size_t)r * r;
+  const float* U2 = a.U12 + r;
+  float* L2o = a.L12_out + (size_t)r * r;
+  float* U2o = a.U12_out + r;
+  float cL1[RM], cL2[RM], cU1[RM], cU2[RM];
+#pragma unroll
+  for (int k = 0; k < RM; ++k) {
+    const bool ok = k < r;
+    cL1[k] = ok ? st->cL1[k] : 0.f; cL2[k] = ok ? st->cL2[k] : 0.f;
+    cU1[k] = ok ? st->cU1[k] : 0.f; cU2[k] = ok ? st->cU2[k] : 0.f;
+  }
+  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+    const float l3 = a.l3[j] / rho, u3 = rho * a.u3[j];
+    const float Qg2 = a.v0[j], iQtx2 = a.v1[j], Pg2 = a.v2[j], iPx2 = a.v3[j];
+    const float dgj = a.dg[r + j], dxj = a.dx[r + j];
+    const float g3L = Qg2 * Qg2 - iQtx2 * iQtx2;                           // :458
+    const float g3U = Pg2 * dgj - dxj * iPx2;                              // :471
+#pragma unroll
+    for (int k = 0; k < RM; ++k) {
+      if (k < r) {
+        const float l = L2[(size_t)j * r + k] / rho;
+        L2o[(size_t)j * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;          // :464
+        const float u = rho * U2[(size_t)k * a.n + j];
+        U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
+      }
+    }
+    a.l3_out[j] = l3 - stepL * g3L * l3;                                   // :465
+    a.u3_out[j] = u3 - stepU * g3U * u3;                                   // :478
+  }
+}
+
+static int grid_for(const psgd_ctx* ctx, long long m) {
+  long long b = (m + kThreads - 1) / kThreads;
+  const long long cap = (long long)ctx->num_sms * 4;
+  if (b > cap) b = cap;
+  return (int)(b < 1 ? 1 : b);
+}
+
+#define SPLU_DISPATCH(r, KERN, ...)                                   \
+  do {                                                                \
+    if ((r) <= 8) KERN<8><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);        \
+    else if ((r) <= 16) KERN<16><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
+    else KERN<32><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);                \
+  } while (0)
+
+static int check_common(psgd_ctx* ctx, long long n, int r) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(r >= 1 && r <= kMaxR && n >= r, PSGD_ERR_BAD_SHAPE, "SPLU: need 1 <= r <= %d and n >= r (n=%lld, r=%d)",
+               kMaxR, n, r);
+  return PSGD_OK;
+}
+
+}  // namespace splu
+}  // namespace psgd
+
+using namespace psgd;
+
+extern "C" int psgd_splu_update(psgd_ctx* ctx, const float* L12, const float* l3, const float* U12, const float* u3,
+                                const float* dx, const float* dg, float* L12_out, float* l3_out, float* U12_out,
+                                float* u3_out, int64_t n, int r, float step, float tiny) {
+  PSGD_RETURN_IF(splu::check_common(ctx, n, r));
+  const long long m = n - r;
+  PSGD_REQUIRE(L12 && U12 && dx && dg && L12_out && U12_out && (m == 0 || (l3 && u3 && l3_out && u3_out)),
+               PSGD_ERR_BAD_POINTER, "SPLU update: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int grid = splu::grid_for(ctx, m);
+  const size_t bytes = WsCarver::padded(sizeof(splu::State)) + 4 * WsCarver::padded(sizeof(float) * (size_t)(m > 0 ? m : 1)) +
+                       WsCarver::padded(sizeof(float) * (size_t)grid * 2 * splu::kMaxR) + WsCarver::padded(sizeof(float) * 2 * grid);
+  PSGD_RETURN_IF(ctx->reserve(bytes));
+  WsCarver c(ctx->ws);
+  splu::Args a{};
+  a.L12 = L12; a.l3 = l3; a.U12 = U12; a.u3 = u3; a.dx = dx; a.dg = dg;
+  a.L12_out = L12_out; a.l3_out = l3_out; a.U12_out = U12_out; a.u3_out = u3_out;
+  a.st = c.take<splu::State>(1);
+  a.v0 = c.take<float>(m > 0 ? m : 1); a.v1 = c.take<float>(m > 0 ? m : 1);
+  a.v2 = c.take<float>(m > 0 ? m : 1); a.v3 = c.take<float>(m > 0 ? m : 1);
+  a.partial = c.take<float>((size_t)grid * 2 * splu::kMaxR);
+  float* pmax = c.take<float>(2 * grid);
+  a.n = n; a.r = r; a.step = step; a.tiny = tiny;
+  cudaStream_t st = ctx->stream;
+  splu::max_kernel<<<grid, splu::kThreads, 0, st>>>(a, pmax);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small0_kernel<<<1, 32, 0, st>>>(a, pmax, grid, 1);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass1_kernel, a);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small1_kernel<<<1, 32, 0, st>>>(a, grid, 1);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass2_kernel, a, 1);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small2_kernel<<<1, 32, 0, st>>>(a, grid, 1, nullptr);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass3_kernel, a, 1, (float*)nullptr);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small3_kernel<<<1, 32, 0, st>>>(a, grid);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass4_kernel, a);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+extern "C" int psgd_splu_apply(psgd_ctx* ctx, const float* L12, const float* l3, const float* U12, const float* u3,
+                               const float* g, float* out, int64_t n, int r) {
+  PSGD_RETURN_IF(splu::check_common(ctx, n, r));
+  const long long m = n - r;
+  PSGD_REQUIRE(L12 && U12 && g && out && (m == 0 || (l3 && u3)), PSGD_ERR_BAD_POINTER, "SPLU apply: null device pointer");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  const int grid = splu::grid_for(ctx, m);
+  const size_t bytes = WsCarver::padded(sizeof(splu::State)) + WsCarver::padded(sizeof(float) * (size_t)(m > 0 ? m : 1)) +
+                       WsCarver::padded(sizeof(float) * (size_t)grid * 2 * splu::kMaxR);
+  PSGD_RETURN_IF(ctx->reserve(bytes));
+  WsCarver c(ctx->ws);
+  splu::Args a{};
+  a.L12 = L12; a.l3 = l3; a.U12 = U12; a.u3 = u3; a.dx = nullptr; a.dg = g;
+  a.st = c.take<splu::State>(1);
+  a.v0 = c.take<float>(m > 0 ? m : 1);
+  a.partial = c.take<float>((size_t)grid * 2 * splu::kMaxR);
+  a.n = n; a.r = r;
+  cudaStream_t st = ctx->stream;
+  splu::small0_kernel<<<1, 32, 0, st>>>(a, nullptr, 0, 0);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass1_kernel, a);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small1_kernel<<<1, 32, 0, st>>>(a, grid, 0);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass2_kernel, a, 0);
+  PSGD_LAUNCH_CHECK(ctx);
+  splu::small2_kernel<<<1, 32, 0, st>>>(a, grid, 0, out);
+  PSGD_LAUNCH_CHECK(ctx);
+  SPLU_DISPATCH(r, splu::pass3_kernel, a, 0, out);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}

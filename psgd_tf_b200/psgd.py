@@ -144,6 +144,51 @@ def precond_grad_dense(Q, grads):
 
 
 # ---------------------------------------------------------------------------------------------
+# sparse LU preconditioner                                                   psgd.py:396-524
+# ---------------------------------------------------------------------------------------------
+def _splu_check(L12, l3, U12, u3, n):
+    r = U12.shape[0]
+    if L12.shape != (n, r) or U12.shape != (r, n) or l3.numel() != n - r or u3.numel() != n - r:
+        raise ValueError(f"SPLU: L12 {tuple(L12.shape)}, l3 {tuple(l3.shape)}, U12 {tuple(U12.shape)}, u3 {tuple(u3.shape)} "
+                         f"do not describe a {n}-parameter preconditioner")
+    return r
+
+
+def update_precond_splu(L12, l3, U12, u3, dxs, dgs, step=0.01):
+    """psgd.py:396-477: Q = L U with L = [L1 0; L2 diag(l3)], U = [U1 U2; 0 diag(u3)].  Functional: returns
+    ``[L12', l3', U12', u3']`` (psgd.py:480)."""
+    L12, l3, U12, u3 = _in(L12, "L12"), _in(l3, "l3"), _in(U12, "U12"), _in(u3, "u3")
+    dx = torch.cat([_in(x, "dxs").reshape(-1) for x in dxs])                   # psgd.py:426
+    dg = torch.cat([_in(g, "dgs").reshape(-1) for g in dgs])                   # psgd.py:427
+    n = dx.numel()
+    if dg.numel() != n:
+        raise ValueError("update_precond_splu: dxs and dgs differ in size")
+    r = _splu_check(L12, l3, U12, u3, n)
+    outs = [torch.empty_like(t) for t in (L12, l3, U12, u3)]
+    ctx = get_context(L12.device.index)
+    check(ctx.lib.psgd_splu_update(ctx.handle, _p(L12), _p(l3), _p(U12), _p(u3), _p(dx), _p(dg), *[_p(o) for o in outs],
+                                   n, r, _scalar(step), _tiny))
+    return outs
+
+
+def precond_grad_splu(L12, l3, U12, u3, grads):
+    """psgd.py:483-524: ``U^T L^T L U g`` reshaped back to the shapes of ``grads``."""
+    L12, l3, U12, u3 = _in(L12, "L12"), _in(l3, "l3"), _in(U12, "U12"), _in(u3, "u3")
+    gs = [_in(g, "grads") for g in grads]
+    flat = torch.cat([g.reshape(-1) for g in gs])                              # psgd.py:495-497
+    n = flat.numel()
+    r = _splu_check(L12, l3, U12, u3, n)
+    out = torch.empty_like(flat)
+    ctx = get_context(L12.device.index)
+    check(ctx.lib.psgd_splu_apply(ctx.handle, _p(L12), _p(l3), _p(U12), _p(u3), _p(flat), _p(out), n, r))
+    pre, idx = [], 0
+    for g in gs:                                                               # psgd.py:518-522
+        pre.append(out[idx: idx + g.numel()].reshape(g.shape))
+        idx += g.numel()
+    return pre
+
+
+# ---------------------------------------------------------------------------------------------
 # Kronecker product preconditioners                                          psgd.py:67-391
 # ---------------------------------------------------------------------------------------------
 def _kron_update(Ql, Qr, dX, dG, step, kinds=None):
