@@ -34,7 +34,7 @@ import numpy as np  # noqa: E402
 METRIC = "precond update+apply steps/s"
 UNIT = "steps/s"
 KERNEL_NAMES = {1: "uvd_gram_update", 2: "uvd_map_update2", 3: "uvd_map_update3", 4: "uvd_gram_apply", 5: "uvd_map_apply",
-                6: "peer_exchange",
+                6: "peer_exchange", 7: "uvd_map_fused", 8: "uvd_d_update", 9: "uvd_map_updapp", 13: "uvd_map_apply_d",
                 10: "gemm", 11: "trsm"}
 
 
@@ -130,11 +130,19 @@ def dist_env():
 # ---------------------------------------------------------------------------------------------
 # UVd workload
 # ---------------------------------------------------------------------------------------------
-def uvd_bytes(n, r):
-    """Algorithmic bytes: big inputs read twice (reduce, then map), outputs written once."""
+def uvd_bytes(n, r, form="fused"):
+    """Algorithmic bytes per launch = what the kernel has to read + the RESULTS it has to write (intermediates such as
+    the stored nablaD are not counted; ncu's `traffic` shows them).
+    SURVEY.md section 8d's step figure 4n(9r+12) models update and apply as separate calls (big inputs read twice
+    each, outputs written once) and is what `step_frac_survey` is quoted against; the fused update+apply call needs
+    less -- 4n(7r+11): sweep 1 reads U V d h v, sweep 2 reads U V d h v g and writes U (or V), sweep 3 reads U V d g
+    and writes d and the preconditioned gradient."""
     per_kernel = {1: 4 * n * (2 * r + 3), 2: 4 * n * (2 * r + 3), 3: 4 * n * (r + 1), 4: 4 * n * (2 * r + 2),
-                  5: 4 * n * (2 * r + 2) + 4 * n}
-    return per_kernel, sum(per_kernel.values())          # total = 4n(9r+12)
+                  5: 4 * n * (2 * r + 2) + 4 * n,
+                  7: 4 * n * (2 * r + 3) + 4 * n * r, 8: 4 * n,
+                  9: 4 * n * (2 * r + 4) + 4 * n * r, 13: 4 * n * (2 * r + 2) + 8 * n}
+    step = 4 * n * (7 * r + 11) if form == "fused" else 4 * n * (9 * r + 12)
+    return per_kernel, step, 4 * n * (9 * r + 12)
 
 
 def chunk_of(n, world, rank, align=256):
@@ -186,14 +194,18 @@ def run_uvd(args, rank, world, local):
     use_graphs = (not args.no_graphs) and world > 1 and exchange == "peer-memory"
     graphs = {}
 
+    form = {"fused": "fused"}.get(args.uvd_form, "separate")
+
     def step(i, U, V, d, v, h, g):
         balance, update_U = (i % 100 == 99), (i % 2 == 0)
         if use_graphs:
             gs = graphs.get(U.data_ptr())
             if gs is None:
                 from psgd_tf_b200.graphs import UVdStepGraphs
-                gs = graphs[U.data_ptr()] = UVdStepGraphs(U, V, d, 0.01, psgd._tiny)
+                gs = graphs[U.data_ptr()] = UVdStepGraphs(U, V, d, 0.01, psgd._tiny, fused=(form == "fused"))
             return gs.step(v, h, g, balance, update_U)
+        if form == "fused":       # the sequence UVd.step runs (psgd.py:732-748) as one call: three sweeps over U, V
+            return psgd.update_precond_and_grad_UVd(U, V, d, v, h, g, 0.01, psgd._tiny, balance=balance, update_U=update_U)
         psgd.update_precond_UVd_math_(U, V, d, v, h, 0.01, psgd._tiny, balance=balance, update_U=update_U)
         return psgd.precond_grad_UVd_math(U, V, d, g)
 
@@ -203,6 +215,7 @@ def run_uvd(args, rank, world, local):
         torch.cuda.synchronize()
 
     # ---- device-resident timing -----------------------------------------------------------------
+    ctx.set_option("uvd_fused", 0 if args.uvd_form == "separate-3sweep" else 1)
     U, V, d = U0.clone(), V0.clone(), d0.clone()
     for i in range(args.warmup + (2 * POOL if use_graphs else 0)):      # graphs: capture every (inputs, coin flip) key
         step(i, U, V, d, *pool[i % POOL])
@@ -247,7 +260,7 @@ def run_uvd(args, rank, world, local):
 
     # ---- per-kernel roofline ----------------------------------------------------------------------
     peaks = load_peaks()
-    per_kernel_bytes, step_bytes = uvd_bytes(n, r)
+    per_kernel_bytes, step_bytes, survey_bytes = uvd_bytes(n, r, form)
     agg = {}
     for kid, kms, _w in prof:
         a = agg.setdefault(kid, [0.0, 0])
@@ -269,7 +282,33 @@ def run_uvd(args, rank, world, local):
                         peak_source=f"of {peaks['source']}",
                         step_achieved=round(step_bytes / (ms / args.steps * 1e-3) / 1e9, 1),
                         step_frac=round(step_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
-                        step_algorithmic_GB=round(step_bytes / 1e9, 3))
+                        step_algorithmic_GB=round(step_bytes / 1e9, 3),
+                        step_frac_survey=round(survey_bytes / (ms / args.steps * 1e-3) / 1e9 / peaks["hbm"], 4),
+                        step_survey_GB=round(survey_bytes / 1e9, 3),
+                        note="step_algorithmic_GB: bytes this call form has to move (see uvd_bytes); step_survey_GB: "
+                             "SURVEY.md 8d's 4N(9r+12) model of update and apply as two separate calls")
+
+    # ---- the same step through the reference's two separate calls (update_precond_UVd_math_, precond_grad_UVd_math) ----
+    separate = None
+    if form == "fused" and not use_graphs and not args.no_separate:
+        form = "separate"
+        for i in range(3):
+            step(i, U, V, d, *pool[i % POOL])
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for i in range(args.steps):
+            step(args.warmup + i, U, V, d, *pool[i % POOL])
+        s1.record()
+        barrier()
+        t = torch.tensor([s0.elapsed_time(s1)], device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        sms = float(t.item()) / args.steps
+        separate = dict(value=round(1e3 / sms, 3), unit=UNIT, ms_per_step=round(sms, 4),
+                        step_frac_survey=round(survey_bytes / (sms * 1e-3) / 1e9 / peaks["hbm"], 4),
+                        note="update_precond_UVd_math_ then precond_grad_UVd_math as two calls (4 sweeps + a pass over d)")
+        form = "fused"
 
     # ---- end to end: host (pinned) inputs, host read-back, copies inside the timed region -----------
     e2e = None
@@ -352,8 +391,11 @@ def run_uvd(args, rank, world, local):
                     l2_policy="inputs larger than L2: >= %.1f GB of state+inputs streamed per GPU per step vs 126 MB L2" %
                               ((4 * n * (2 * r + 4)) / 1e9),
                     coin_flips="update_U alternates, balance every 100th step", step_size=0.01,
+                    call_form=("update_precond_and_grad_UVd (psgd_uvd_update_apply): update + apply of psgd.py:732-748 "
+                               "fused into three sweeps" if form == "fused" else
+                               "update_precond_UVd_math_ + precond_grad_UVd_math as two calls (" + args.uvd_form + ")"),
                     cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
-        roofline=roofline, kernels=kernels, kernels_measured=kernels_from, cpu_baseline=cpu, e2e=e2e,
+        roofline=roofline, kernels=kernels, kernels_measured=kernels_from, separate_calls=separate, cpu_baseline=cpu, e2e=e2e,
         gpu_launches=int(launches), clocks=clk)
 
 
@@ -500,6 +542,9 @@ def main():
                     "instead of the peer-memory exchange kernel")
     ap.add_argument("--no-graphs", action="store_true", help="UVd: launch every kernel from Python instead of replaying "
                     "the step from CUDA graphs")
+    ap.add_argument("--uvd-form", default="fused", choices=["fused", "separate", "separate-3sweep"],
+                    help="UVd: fused update+apply call (default), the reference's two calls, or those with the three-sweep update")
+    ap.add_argument("--no-separate", action="store_true", help="UVd: skip the extra timing of the two-call form")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

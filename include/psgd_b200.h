@@ -57,8 +57,10 @@ int psgd_set_stream(psgd_ctx* ctx, void* stream);
 int64_t psgd_launch_count(const psgd_ctx* ctx);
 /* Bytes of device workspace currently owned by ctx. */
 int64_t psgd_workspace_bytes(const psgd_ctx* ctx);
-/* Kernel path selector for the streaming kernels: 0 = TMA bulk-copy pipeline (default),
- * 1 = direct global loads (debug cross-check; same arithmetic). */
+/* Options.  "direct": streaming kernels 0 = TMA bulk-copy pipeline (default), 1 = direct global loads (debug
+ * cross-check; same arithmetic).  "uvd_fused": psgd_uvd_update 1 = two sweeps + a pass over d, the rank-2 step's
+ * coefficients taken from the Gram table (default), 0 = three sweeps with direct reductions over a, b (cross-check).
+ * "profile": see below.  Others ("gemm_path", "tc_bn", "trsm_base", "assume_triangular", ...) tune the dense Kron engine. */
 int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 
 /* Per-kernel device timing.  After psgd_set_option(ctx, "profile", 1) every large kernel launch is bracketed
@@ -72,6 +74,10 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 #define PSGD_K_UVD_GRAM_APPLY 4  /* apply sweep 1: U^T U, U^T(dg), V^T(dg)                    */
 #define PSGD_K_UVD_MAP_APPLY 5   /* apply sweep 2: write the preconditioned gradient          */
 #define PSGD_K_EXCHANGE 6        /* one peer-memory exchange (push partials to all ranks, wait, reduce)  */
+#define PSGD_K_UVD_MAP_FUSED 7   /* fused update sweep 2: a,b,nablaD per row + rank-2 update of U (or V) */
+#define PSGD_K_UVD_D_UPDATE 8    /* fused update pass 3: d -= mu_d d nablaD                              */
+#define PSGD_K_UVD_MAP_UPDAPP 9  /* update+apply sweep 2: PSGD_K_UVD_MAP_FUSED + Gram sums of the updated factors */
+#define PSGD_K_UVD_MAP_APPLY_D 13 /* update+apply sweep 3: d update fused with the apply's map sweep     */
 #define PSGD_K_GEMM 10           /* one tcgen05 3xTF32 GEMM launch                            */
 #define PSGD_K_GEMM_SIMT 12      /* one SIMT fp32 GEMM launch                                 */
 #define PSGD_K_TRSM 11           /* one triangular-solve step                                 */
@@ -109,6 +115,12 @@ int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v,
 /* Replaces precond_grad_UVd_math (psgd.py:619-627): out = d*(I+VU^T)(I+UV^T)(d*g). */
 int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,
                    float* out, int64_t n, int r);
+/* psgd_uvd_update followed by psgd_uvd_apply on the updated state (the sequence UVd.step runs, psgd.py:732-748), fused
+ * into three sweeps: the apply's Gram sums of the UPDATED factors are accumulated in the sweep that writes them and the
+ * d update rides in the apply's map sweep, so U and V are each read three times per step instead of five.  Same
+ * results as the two calls.  g, out: [n]; out must not alias d or g. */
+int psgd_uvd_update_apply(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, const float* g,
+                          float* out, int64_t n, int r, float step, float tiny, int balance, int update_U);
 /* Tail of UVd.step (psgd.py:747-762) on the flattened parameter vector: pre = precond_grad_UVd_math(U,V,d,g);
  * lr = lr_params * min(grad_clip_max_norm / (||pre||_2 + tiny), 1) (psgd.py:750-754; pass INFINITY for "no clipping",
  * then lr = lr_params); param -= lr * pre (+ v when v != NULL: the finite-difference perturbation, psgd.py:760-762).

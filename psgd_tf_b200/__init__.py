@@ -16,7 +16,7 @@ from .psgd import (  # noqa: F401
     _update_precond_dense_scale, _precond_grad_dense_scale,
     _update_precond_norm_scale, _precond_grad_norm_scale,
     IpUVtmatvec, update_precond_UVd_math_, precond_grad_UVd_math,
-    update_precond_UVd, precond_grad_UVd,
+    update_precond_UVd, precond_grad_UVd, update_precond_and_grad_UVd,
     update_precond_diag, precond_grad_diag, update_precond_Xmat, precond_grad_Xmat,
     UVd, apply_preconditioned_updates, grad_differences,
 )

@@ -58,6 +58,7 @@ struct psgd_ctx {
   size_t ws_bytes = 0;
   // small pinned/ device scratch is carved from ws by each op
   int opt_direct = 0;        // streaming kernels: 1 = direct global loads instead of TMA pipeline
+  int opt_uvd_fused = 1;     // UVd update: 1 = two sweeps + d pass (rank-2 step from the Gram table), 0 = three sweeps
   int opt_gemm_path = 0;     // dense GEMMs: 0 = auto, 1 = SIMT fp32, 2 = tcgen05 3xTF32
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse

@@ -40,11 +40,14 @@ enum Mode { kUpdate = 0, kApply = 1, kMatvec = 2 };
 // ---------------------------------------------------------------------------------------------
 __host__ __device__ constexpr bool gp_needed(int R, int MODE, int i, int j) {
   const int W = 2 * R;
-  if (MODE == kUpdate) return j >= i;                                   // full upper triangle + both X columns
+  if (MODE == kUpdate) return j >= i;                                   // full upper triangle of [Z X]^T [Z X]
   if (MODE == kApply) return (j >= W) || (i < R && j < R && j >= i);    // U^T U, U^T x, V^T x
   return (i >= R) && (j >= W);                                          // kMatvec: V^T x only
 }
 __host__ __device__ constexpr int gp_nx(int MODE) { return MODE == kUpdate ? 2 : 1; }
+// table rows: the 2R columns of Z; the update also keeps the X rows (dh.dh, dh.w, w.w) so that every reduction over
+// a = dh + U p and b = w - V s1 can be expanded through the table (no second reduction sweep)
+__host__ __device__ constexpr int gp_nrows(int R, int MODE) { return MODE == kUpdate ? 2 * R + 2 : 2 * R; }
 // Accumulators are kept as float2 pairs (columns 2k, 2k+1) so that one packed FFMA2 (fma.rn.f32x2, sm_100) updates
 // two table entries; a pair is live when either of its columns is needed.
 __host__ __device__ constexpr bool gp_pair_needed(int R, int MODE, int i, int k) {
@@ -60,22 +63,23 @@ __host__ __device__ constexpr int gp_row_count(int R, int MODE, int i) {
 }
 __host__ __device__ constexpr int gp_total(int R, int MODE) {
   int c = 0;
-  for (int i = 0; i < 2 * R; ++i) c += gp_row_count(R, MODE, i);
+  for (int i = 0; i < gp_nrows(R, MODE); ++i) c += gp_row_count(R, MODE, i);
   return c;
 }
 constexpr int kAccPerRole = 104;
 __host__ __device__ constexpr int gp_nroles(int R, int MODE) { return (gp_total(R, MODE) + kAccPerRole - 1) / kAccPerRole; }
-// first table row of role `role` (role >= nroles gives W)
+// first table row of role `role` (role >= nroles gives the row count)
 __host__ __device__ constexpr int gp_begin(int R, int MODE, int role) {
   const int nroles = gp_nroles(R, MODE);
-  if (role >= nroles) return 2 * R;
+  const int nrows = gp_nrows(R, MODE);
+  if (role >= nroles) return nrows;
   const int target = (gp_total(R, MODE) * role) / nroles;
   int c = 0;
-  for (int i = 0; i < 2 * R; ++i) {
+  for (int i = 0; i < nrows; ++i) {
     if (c >= target) return i;
     c += gp_row_count(R, MODE, i);
   }
-  return 2 * R;
+  return nrows;
 }
 
 template <int R, int MODE>
@@ -84,6 +88,8 @@ struct GramPlan {
   static constexpr int NX = gp_nx(MODE);
   static constexpr int E = W + NX;
   static constexpr int E2 = (E + 1) / 2;          // float2 column pairs
+  static constexpr int NR = gp_nrows(R, MODE);    // table rows
+  static constexpr int TABLE = NR * E;            // floats per table ([NR][E], only the needed entries are meaningful)
   static constexpr int NROLES = gp_nroles(R, MODE);
   // warps per role: keep the CTA at <= 12 warps so ptxas may use > 128 registers per thread
   static constexpr int WPR = NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES <= 5 ? 2 : 1)));
@@ -260,7 +266,7 @@ struct GramRole {
         if (P::pair_needed(i, k))
           acc[i - I0][k] = ffma2(make_float2(z[i], z[i]), make_float2(z[2 * k], z[2 * k + 1]), acc[i - I0][k]);
   }
-  // warp butterfly, then lane 0 writes this warp's table rows into `dst` ([W][E] floats)
+  // warp butterfly, then lane 0 writes this warp's table rows into `dst` ([NR][E] floats)
   __device__ __forceinline__ void flush(float* dst, int lane) {
 #pragma unroll
     for (int i = I0; i < I1; ++i)
@@ -336,14 +342,14 @@ __device__ __forceinline__ void gram_dispatch(int role, const SweepArgs& a, floa
   }
 }
 
-// partial: [gridDim.x][W*E] floats
+// partial: [gridDim.x][NR*E] floats
 template <int R, int MODE>
 __global__ void __launch_bounds__(GramPlan<R, MODE>::THREADS, 1)
     gram_sweep_kernel(SweepArgs a, float* __restrict__ partial) {
   using P = GramPlan<R, MODE>;
   constexpr int NV = (MODE == kUpdate) ? 3 : (MODE == kApply ? 2 : 1);
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float warp_tab[P::WPR][P::W * P::E];   // per (warp-in-role) table, rows owned by its role
+  __shared__ float warp_tab[P::WPR][P::TABLE];      // per (warp-in-role) table, rows owned by its role
 
   float* smem; uint64_t* full; uint64_t* empty;
   pipeline_init<R, 2, NV, P::TILE>(smem, full, empty, smem_raw, P::CONSUMER_WARPS);
@@ -359,14 +365,14 @@ __global__ void __launch_bounds__(GramPlan<R, MODE>::THREADS, 1)
   }
   __syncthreads();
   // fixed-order sum over the WPR warps of each role -> CTA partial
-  for (int k = threadIdx.x; k < P::W * P::E; k += blockDim.x) {
+  for (int k = threadIdx.x; k < P::TABLE; k += blockDim.x) {
     const int i = k / P::E, j = k % P::E;
     float s = 0.f;
     if (P::needed(i, j)) {
 #pragma unroll
       for (int w = 0; w < P::WPR; ++w) s += warp_tab[w][k];
     }
-    partial[(size_t)blockIdx.x * (P::W * P::E) + k] = s;
+    partial[(size_t)blockIdx.x * P::TABLE + k] = s;
   }
 }
 
@@ -455,15 +461,58 @@ struct SmallState {
   float max_nabla;       // atomic max target of sweep 2
   float maxU, maxV;      // balance
   float rho;
+  // fused forms: reductions over a = Qh, b = invQtv expanded through the Gram table (uvd_small1_kernel)
+  double aa, bb, ab;     // a.a, b.b, a.b
+  double Uta[kMaxRank];  // U^T a
+  double Utb[kMaxRank];  // U^T b
 };
 
 // table accessors for G = Z^T [Z | X] stored [W][E] with only j >= i filled
 __device__ __forceinline__ double Gsym(const double* G, int E, int i, int j) { return i <= j ? G[i * E + j] : G[j * E + i]; }
 
-// One warp.  G: reduced table of sweep 1.
-__global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict__ G, int r, SmallState* __restrict__ st) {
+// Rank-2 step of U (or V) from the r-sized reductions over a = Qh, b = invQtv (one warp; psgd.py:589-615):
+//   normaliser ||(a atX - b btX) X^T||_F evaluated through the r x r Gram X^T X (X = V on the U branch, U on the V
+//   branch), mu = step / (norm + tiny), coefficient vectors of the row update.
+__device__ __forceinline__ void rank2_coeffs(double aa, double bb, double ab, const double* atX, const double* btX, int r,
+                                             int update_U, float step, float tiny, SmallState* st, int lane) {
+  const double* XtX = update_U ? st->VtV : st->UtU;
+  // ||X atX^T||^2 = atX (X^T X) atX^T  etc.                                  psgd.py:594-596 / :608-610
+  double qaa = 0, qbb = 0, qab = 0;
+  if (lane < r) {
+    double ra = 0, rb = 0;
+    for (int j = 0; j < r; ++j) { ra += XtX[lane * r + j] * atX[j]; rb += XtX[lane * r + j] * btX[j]; }
+    qaa = atX[lane] * ra; qbb = btX[lane] * rb; qab = atX[lane] * rb;
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    qaa += __shfl_xor_sync(0xffffffffu, qaa, o);
+    qbb += __shfl_xor_sync(0xffffffffu, qbb, o);
+    qab += __shfl_xor_sync(0xffffffffu, qab, o);
+  }
+  const float norm = sqrtf(fabsf((float)(aa * qaa + bb * qbb - 2.0 * ab * qab)));
+  const float mu = step / (norm + tiny);                                      // psgd.py:597 / :611
+  if (lane == 0) st->mu = mu;
+  if (lane < r) {
+    if (update_U) {                                                           // psgd.py:600-601
+      double s1 = 0, s2 = 0;
+      for (int i = 0; i < r; ++i) { s1 += atX[i] * st->IpVtU[i * r + lane]; s2 += btX[i] * st->IpVtU[i * r + lane]; }
+      st->c1[lane] = mu * (float)s1;
+      st->c2[lane] = mu * (float)s2;
+    } else {
+      st->c1[lane] = (float)atX[lane];
+      st->c2[lane] = (float)btX[lane];
+    }
+  }
+}
+
+// One warp.  G: reduced table of sweep 1, [2r+2][2r+2] with the upper triangle filled.
+// fused != 0: the reductions over a and b that the rank-2 step needs (a.a, b.b, a.b, a^T X, b^T X) are expanded
+// through the table (a = dh + U p, b = w - V s1), so the step's coefficients are ready before sweep 2 and the row
+// update rides in that sweep (tests/uvd_pipeline_model.py restates this algebra on the host).
+__global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict__ G, int r, int fused, int update_U,
+                                                        float step, float tiny, SmallState* __restrict__ st) {
   __shared__ double A[kMaxRank][kLuLd];
-  __shared__ double sp[kMaxRank], ss1[kMaxRank];
+  __shared__ double sp[kMaxRank], ss1[kMaxRank], sat[kMaxRank], sbt[kMaxRank];
   const int lane = threadIdx.x;
   const int W = 2 * r, E = W + 2;
   for (int e = lane; e < r * r; e += 32) {
@@ -476,11 +525,13 @@ __global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict
   // p = V^T(dh);  t = U^T Qh = U^T dh + (U^T U) p                            psgd.py:569-570
   if (lane < r) sp[lane] = G[(r + lane) * E + W];
   __syncwarp();
+  double tl = 0.0;
   if (lane < r) {
     double s = G[lane * E + W];
     for (int j = 0; j < r; ++j) s += Gsym(G, E, lane, j) * sp[j];
     st->p[lane] = (float)sp[lane];
     st->t[lane] = (float)s;
+    tl = s;
   }
   // s1 = solve(IpVtU^T, U^T w)                                               psgd.py:577
   for (int e = lane; e < r * r; e += 32) {
@@ -506,45 +557,88 @@ __global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict
   warp_lu_solve(r, A, lane);
   if (lane < r) st->s2[lane] = (float)A[lane][r];
   if (lane == 0) st->max_nabla = 0.f;
+  if (!fused) return;
+
+  // ---- rank-2 step from the table ---------------------------------------------------------------
+  double aa = 0, bb = 0, ab = 0;
+  if (lane < r) {
+    const int i = lane;
+    double uup = 0, vvs = 0, uvs = 0;          // (U^T U p)_i, (V^T V s1)_i, (U^T V s1)_i
+    for (int j = 0; j < r; ++j) {
+      uup += Gsym(G, E, i, j) * sp[j];
+      vvs += Gsym(G, E, r + i, r + j) * ss1[j];
+      uvs += G[i * E + (r + j)] * ss1[j];
+    }
+    aa = sp[i] * (2.0 * G[i * E + W] + uup);                                   // 2 p.U^T dh + p^T U^T U p
+    bb = ss1[i] * (vvs - 2.0 * G[(r + i) * E + W + 1]);                        // s1^T V^T V s1 - 2 s1.V^T w
+    ab = sp[i] * (G[i * E + W + 1] - uvs) - ss1[i] * sp[i];                    // p.U^T w - p^T U^T V s1 - s1.V^T dh
+    st->Uta[i] = tl;                                                           // U^T a = U^T Qh
+    st->Utb[i] = G[i * E + W + 1] - uvs;                                       // U^T b = U^T w - U^T V s1
+    if (update_U) {
+      double pv = 0;                           // (p^T U^T V)_i
+      for (int j = 0; j < r; ++j) pv += sp[j] * G[j * E + (r + i)];
+      sat[i] = sp[i] + pv;                                                     // a^T V               psgd.py:589
+      sbt[i] = G[(r + i) * E + W + 1] - vvs;                                   // b^T V               psgd.py:591
+    } else {
+      sat[i] = tl;                                                             // a^T U = U^T Qh      psgd.py:603
+      sbt[i] = G[i * E + W + 1] - uvs;                                         // b^T U               psgd.py:604
+    }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    aa += __shfl_xor_sync(0xffffffffu, aa, o);
+    bb += __shfl_xor_sync(0xffffffffu, bb, o);
+    ab += __shfl_xor_sync(0xffffffffu, ab, o);
+  }
+  aa += G[W * E + W];                                                          // dh.dh
+  bb += G[(W + 1) * E + W + 1];                                                // w.w
+  ab += G[W * E + W + 1];                                                      // dh.w
+  if (lane == 0) { st->aa = aa; st->bb = bb; st->ab = ab; }
+  __syncwarp();                                // sat/sbt and st->UtU/VtV/IpVtU written above are read across lanes
+  rank2_coeffs(aa, bb, ab, sat, sbt, r, update_U, step, tiny, st, lane);
 }
 
 // G2 layout: [0]=a.a [1]=b.b [2]=a.b [3..3+r)=a^T X  [3+r..3+2r)=b^T X   (X = V on the U branch, U on the V branch)
 __global__ void __launch_bounds__(32) uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step,
                                                         float tiny, SmallState* __restrict__ st) {
   const int lane = threadIdx.x;
-  const double aa = G2[0], bb = G2[1], ab = G2[2];
-  const double* atX = G2 + 3;
-  const double* btX = G2 + 3 + r;
-  const double* XtX = update_U ? st->VtV : st->UtU;
-  // ||X atX^T||^2 = atX (X^T X) atX^T  etc.                                  psgd.py:594-596 / :608-610
-  double qaa = 0, qbb = 0, qab = 0;
+  if (lane == 0) st->mu_d = step / (st->max_nabla + tiny);                    // psgd.py:582
+  rank2_coeffs(G2[0], G2[1], G2[2], G2 + 3, G2 + 3 + r, r, update_U, step, tiny, st, lane);
+}
+
+// After the map sweep of the fused update+apply call.  G3: reduced sums over the UPDATED factors
+//   U'^T x0 | U'^T x1 | V'^T x0 | V'^T x1          with x0 = d g and x1 = d nablaD g,
+// so that  Z^T (d' g) = Z^T x0 - mu_d Z^T x1  for d' = d - mu_d d nablaD (mu_d is only known once max|nablaD| is, i.e.
+// after that sweep).  U'^T U' needs no sums at all: U' = U - a c1^T + b c2^T (U branch; U' = U on the V branch) expands
+// through quantities uvd_small1_kernel already has.  Leaves p, t of the apply in st.                 psgd.py:625-626
+__global__ void __launch_bounds__(32) uvd_small_ua_kernel(const double* __restrict__ G3, int r, int update_U, float step,
+                                                          float tiny, SmallState* __restrict__ st) {
+  __shared__ double sp[kMaxRank];
+  const int lane = threadIdx.x;
+  const float mu_d = step / (st->max_nabla + tiny);                           // psgd.py:582
+  if (lane == 0) st->mu_d = mu_d;
+  const double* Ux0 = G3;
+  const double* Ux1 = Ux0 + r;
+  const double* Vx0 = Ux1 + r;
+  const double* Vx1 = Vx0 + r;
+  if (lane < r) sp[lane] = Vx0[lane] - (double)mu_d * Vx1[lane];
+  __syncwarp();
   if (lane < r) {
-    double ra = 0, rb = 0;
-    for (int j = 0; j < r; ++j) { ra += XtX[lane * r + j] * atX[j]; rb += XtX[lane * r + j] * btX[j]; }
-    qaa = atX[lane] * ra; qbb = btX[lane] * rb; qab = atX[lane] * rb;
-  }
-#pragma unroll
-  for (int o = 16; o > 0; o >>= 1) {
-    qaa += __shfl_xor_sync(0xffffffffu, qaa, o);
-    qbb += __shfl_xor_sync(0xffffffffu, qbb, o);
-    qab += __shfl_xor_sync(0xffffffffu, qab, o);
-  }
-  const float norm = sqrtf(fabsf((float)(aa * qaa + bb * qbb - 2.0 * ab * qab)));
-  const float mu = step / (norm + tiny);                                      // psgd.py:597 / :611
-  if (lane == 0) {
-    st->mu_d = step / (st->max_nabla + tiny);                                 // psgd.py:582
-    st->mu = mu;
-  }
-  if (lane < r) {
-    if (update_U) {                                                           // psgd.py:600-601
-      double s1 = 0, s2 = 0;
-      for (int i = 0; i < r; ++i) { s1 += atX[i] * st->IpVtU[i * r + lane]; s2 += btX[i] * st->IpVtU[i * r + lane]; }
-      st->c1[lane] = mu * (float)s1;
-      st->c2[lane] = mu * (float)s2;
-    } else {
-      st->c1[lane] = (float)atX[lane];
-      st->c2[lane] = (float)btX[lane];
+    const int i = lane;
+    double s = Ux0[i] - (double)mu_d * Ux1[i];
+    const double aa = st->aa, bb = st->bb, ab = st->ab;
+    const double c1i = st->c1[i], c2i = st->c2[i], uai = st->Uta[i], ubi = st->Utb[i];
+    for (int j = 0; j < r; ++j) {
+      double uu = st->UtU[i * r + j];
+      if (update_U) {
+        const double c1j = st->c1[j], c2j = st->c2[j];
+        uu += -uai * c1j - c1i * st->Uta[j] + ubi * c2j + c2i * st->Utb[j] + aa * c1i * c1j - ab * (c1i * c2j + c2i * c1j) +
+              bb * c2i * c2j;
+      }
+      s += uu * sp[j];
     }
+    st->p[i] = (float)sp[i];
+    st->t[i] = (float)s;
   }
 }
 
@@ -572,22 +666,41 @@ constexpr int kMapThreads = (kMapConsumerWarps + 1) * 32;
 
 enum MapKind { kMapUpd2 = 0, kMapUpd3U = 1, kMapUpd3V = 2, kMapApply2 = 3, kMapMatvec2 = 4,
                kMapApplyNorm = 5,    // apply + sum of squares of the preconditioned gradient (UVd.step clip, psgd.py:752)
-               kMapApplyParam = 6 }; // apply fused with the parameter update (UVd.step without clipping, psgd.py:757-762)
+               kMapApplyParam = 6,   // apply fused with the parameter update (UVd.step without clipping, psgd.py:757-762)
+               kMapUpdFU = 7,        // fused update sweep: a, b, nablaD per row AND the rank-2 update of U (psgd.py:569-601)
+               kMapUpdFV = 8,        //   ... of V (psgd.py:603-615)
+               kMapUpdAppU = 9,      // kMapUpdFU + Gram sums of the updated factors for the apply that follows
+               kMapUpdAppV = 10,     // kMapUpdFV + the same
+               kMapApplyD = 11 };    // d update (psgd.py:584) fused with the apply's map sweep (psgd.py:625-626)
 
+// NM matrices + NV vectors staged per tile; kStoreMat / kStoreVec: which staged matrix / vector is updated in the
+// shared tile and written back with a TMA bulk store (-1: none)
 template <int KIND> struct MapTraits;
-template <> struct MapTraits<kMapUpd2>   { static constexpr int NM = 2, NV = 3; static constexpr bool kStore = false; };
-template <> struct MapTraits<kMapUpd3U>  { static constexpr int NM = 1, NV = 4; static constexpr bool kStore = true; };
-template <> struct MapTraits<kMapUpd3V>  { static constexpr int NM = 1, NV = 4; static constexpr bool kStore = true; };
-template <> struct MapTraits<kMapApply2> { static constexpr int NM = 2, NV = 2; static constexpr bool kStore = false; };
-template <> struct MapTraits<kMapMatvec2>{ static constexpr int NM = 1, NV = 1; static constexpr bool kStore = false; };
-template <> struct MapTraits<kMapApplyNorm>  { static constexpr int NM = 2, NV = 2; static constexpr bool kStore = false; };
-template <> struct MapTraits<kMapApplyParam> { static constexpr int NM = 2, NV = 4; static constexpr bool kStore = false; };
+template <> struct MapTraits<kMapUpd2>   { static constexpr int NM = 2, NV = 3, kStoreMat = -1, kStoreVec = -1; };
+template <> struct MapTraits<kMapUpd3U>  { static constexpr int NM = 1, NV = 4, kStoreMat = 0, kStoreVec = 3; };
+template <> struct MapTraits<kMapUpd3V>  { static constexpr int NM = 1, NV = 4, kStoreMat = 0, kStoreVec = 3; };
+template <> struct MapTraits<kMapApply2> { static constexpr int NM = 2, NV = 2, kStoreMat = -1, kStoreVec = -1; };
+template <> struct MapTraits<kMapMatvec2>{ static constexpr int NM = 1, NV = 1, kStoreMat = -1, kStoreVec = -1; };
+template <> struct MapTraits<kMapApplyNorm>  { static constexpr int NM = 2, NV = 2, kStoreMat = -1, kStoreVec = -1; };
+template <> struct MapTraits<kMapApplyParam> { static constexpr int NM = 2, NV = 4, kStoreMat = -1, kStoreVec = -1; };
+template <> struct MapTraits<kMapUpdFU>   { static constexpr int NM = 2, NV = 3, kStoreMat = 0, kStoreVec = -1; };
+template <> struct MapTraits<kMapUpdFV>   { static constexpr int NM = 2, NV = 3, kStoreMat = 1, kStoreVec = -1; };
+template <> struct MapTraits<kMapUpdAppU> { static constexpr int NM = 2, NV = 4, kStoreMat = 0, kStoreVec = -1; };
+template <> struct MapTraits<kMapUpdAppV> { static constexpr int NM = 2, NV = 4, kStoreMat = 1, kStoreVec = -1; };
+template <> struct MapTraits<kMapApplyD>  { static constexpr int NM = 2, NV = 3, kStoreMat = -1, kStoreVec = -1; };
+
+constexpr bool map_is_fused_update(int KIND) {
+  return KIND == kMapUpdFU || KIND == kMapUpdFV || KIND == kMapUpdAppU || KIND == kMapUpdAppV;
+}
+constexpr bool map_is_updapp(int KIND) { return KIND == kMapUpdAppU || KIND == kMapUpdAppV; }
+// floats per CTA partial record of the update+apply sweep: U'^T x0 | U'^T x1 | V'^T x0 | V'^T x1
+constexpr int updapp_count(int R) { return 4 * R; }
 
 struct MapOut {
   float* o0; float* o1; float* o2;   // per-row outputs (coalesced direct stores)
-  float* mat_out;                    // kStore kinds: updated matrix
-  float* vec_out;                    // kStore kinds: updated d
-  float* partial;                    // Upd2: [grid][3+2r] sums; ApplyNorm: [grid] sums of squares
+  float* mat_out;                    // store kinds: updated matrix
+  float* vec_out;                    // store kinds: updated d
+  float* partial;                    // Upd2: [grid][3+2r] sums; ApplyNorm: [grid] sums of squares; UpdApp: [grid][updapp_count]
   SmallState* st;
   float lr;                          // ApplyParam: learning rate
   int has_v;                         // ApplyParam: vec[3] holds the finite-difference perturbation to remove
@@ -604,12 +717,34 @@ struct Upd2Acc {
   }
 };
 
+// per-lane accumulators of the update+apply sweep: [U' V']^T [x0 x1] over the rows this lane owns
+template <int R, bool ON>
+struct UpdAppAcc {
+  float ux0[ON ? R : 1], ux1[ON ? R : 1], vx0[ON ? R : 1], vx1[ON ? R : 1];
+  __device__ __forceinline__ void zero() {
+    if constexpr (ON) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) { ux0[k] = 0.f; ux1[k] = 0.f; vx0[k] = 0.f; vx1[k] = 0.f; }
+    }
+  }
+  __device__ __forceinline__ void add(const float (&u)[R], const float (&v)[R], float x0, float x1) {
+    if constexpr (ON) {
+#pragma unroll
+      for (int i = 0; i < R; ++i) {
+        ux0[i] = fmaf(u[i], x0, ux0[i]); ux1[i] = fmaf(u[i], x1, ux1[i]);
+        vx0[i] = fmaf(v[i], x0, vx0[i]); vx1[i] = fmaf(v[i], x1, vx1[i]);
+      }
+    }
+  }
+};
+
 template <int R, int KIND>
 struct MapBody {
   // r-sized constants in registers
-  float k0[R], k1[R], k2[R], k3[R];
+  float k0[R], k1[R], k2[R], k3[R], k4[R], k5[R];
   float mu_d, mu;
   Upd2Acc<R> acc;
+  UpdAppAcc<R, map_is_updapp(KIND)> gacc;
   int update_U;
 
   __device__ __forceinline__ void init(const SmallState* st, int upd_u) {
@@ -618,6 +753,14 @@ struct MapBody {
 #pragma unroll
       for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; k2[k] = st->s1[k]; k3[k] = st->s2[k]; }
       acc.zero();
+    } else if constexpr (map_is_fused_update(KIND)) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        k0[k] = st->p[k]; k1[k] = st->t[k]; k2[k] = st->s1[k]; k3[k] = st->s2[k]; k4[k] = st->c1[k]; k5[k] = st->c2[k];
+      }
+      mu = st->mu;
+      acc.mx = 0.f;
+      gacc.zero();
     } else if constexpr (KIND == kMapUpd3U || KIND == kMapUpd3V) {
 #pragma unroll
       for (int k = 0; k < R; ++k) { k0[k] = st->c1[k]; k1[k] = st->c2[k]; }
@@ -629,13 +772,14 @@ struct MapBody {
     } else {
 #pragma unroll
       for (int k = 0; k < R; ++k) { k0[k] = st->p[k]; k1[k] = st->t[k]; }
+      if constexpr (KIND == kMapApplyD) mu_d = st->mu_d;
     }
   }
 
   // m0/m1: row pointers (shared or global); vec values v0..v3; `row` global row index;
-  // m0w: where to write the updated matrix row (shared tile or global)
+  // mw: where to write the updated matrix row (shared tile or global); vecw: likewise for the updated d
   __device__ __forceinline__ void row(const float* m0, const float* m1, float v0, float v1, float v2, float v3,
-                                      int64_t row, const MapOut& o, float* m0w, float* vecw) {
+                                      int64_t row, const MapOut& o, float* mw, float* vecw) {
     if constexpr (KIND == kMapUpd2) {
       // v0=d v1=h v2=v                                                       psgd.py:569-581
       float u[R], vv[R];
@@ -658,13 +802,42 @@ struct MapBody {
 #pragma unroll
         for (int k = 0; k < R; ++k) { acc.atX[k] = fmaf(Qh, u[k], acc.atX[k]); acc.btX[k] = fmaf(b, u[k], acc.btX[k]); }
       }
+    } else if constexpr (map_is_fused_update(KIND)) {
+      // v0=d v1=h v2=v (v3=g): the arithmetic of kMapUpd2 and kMapUpd3U/V on one pass     psgd.py:569-581, :600-601, :614-615
+      float u[R], vv[R];
+      load_row<R>(m0, u);
+      load_row<R>(m1, vv);
+      const float dh = v0 * v1;
+      const float Qh = dh + dot_row<R>(u, k0);
+      const float Ph = v0 * (Qh + dot_row<R>(vv, k1));
+      const float w = v2 / v0;
+      const float b = w - dot_row<R>(vv, k2);
+      const float invPv = (b - dot_row<R>(u, k3)) / v0;
+      const float nd = Ph * v1 - v2 * invPv;
+      o.o2[row] = nd;
+      acc.mx = fmaxf(acc.mx, fabsf(nd));
+      if constexpr (KIND == kMapUpdFU || KIND == kMapUpdAppU) {
+#pragma unroll
+        for (int k = 0; k < R; ++k) u[k] = u[k] - (Qh * k4[k] - b * k5[k]);
+        store_row<R>(mw, u);
+      } else {
+        const float sa = Qh + dot_row<R>(vv, k4);
+        const float sb = b + dot_row<R>(vv, k5);
+#pragma unroll
+        for (int k = 0; k < R; ++k) vv[k] = vv[k] - mu * (sa * k4[k] - sb * k5[k]);
+        store_row<R>(mw, vv);
+      }
+      if constexpr (map_is_updapp(KIND)) {
+        const float x0 = v0 * v3;          // d g
+        gacc.add(u, vv, x0, x0 * nd);      // sums over the UPDATED rows; d' g = x0 - mu_d x1
+      }
     } else if constexpr (KIND == kMapUpd3U) {
       // v0=a v1=b v2=nablaD v3=d ; U -= mu (a c1 - b c2) (c pre-scaled)      psgd.py:584, :600-601
       float u[R];
       load_row<R>(m0, u);
 #pragma unroll
       for (int k = 0; k < R; ++k) u[k] = u[k] - (v0 * k0[k] - v1 * k1[k]);
-      store_row<R>(m0w, u);
+      store_row<R>(mw, u);
       *vecw = v3 - (mu_d * v3) * v2;
     } else if constexpr (KIND == kMapUpd3V) {
       // V -= mu ((a + V atU^T) atU - (b + V btU^T) btU)                       psgd.py:584, :614-615
@@ -674,8 +847,18 @@ struct MapBody {
       const float sb = v1 + dot_row<R>(vv, k1);
 #pragma unroll
       for (int k = 0; k < R; ++k) vv[k] = vv[k] - mu * (sa * k0[k] - sb * k1[k]);
-      store_row<R>(m0w, vv);
+      store_row<R>(mw, vv);
       *vecw = v3 - (mu_d * v3) * v2;
+    } else if constexpr (KIND == kMapApplyD) {
+      // v0=d v1=nablaD v2=g: d' = d - mu_d d nablaD, then the apply on d'    psgd.py:584, :625-626
+      float u[R], vv[R];
+      load_row<R>(m0, u);
+      load_row<R>(m1, vv);
+      const float dn = v0 - (mu_d * v0) * v1;
+      const float dg = dn * v2;
+      const float y = dg + dot_row<R>(u, k0);
+      o.o0[row] = dn * (y + dot_row<R>(vv, k1));
+      o.o1[row] = dn;
     } else if constexpr (KIND == kMapApply2 || KIND == kMapApplyNorm || KIND == kMapApplyParam) {
       // v0=d v1=g                                                            psgd.py:625-626
       float u[R], vv[R];
@@ -708,12 +891,17 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
   using T = MapTraits<KIND>;
   using L = TileLayout<R, T::NM, T::NV, kMapTile>;
   static_assert(kMapTile == kMapConsumerWarps * 32, "one row per consumer lane per tile");
+  constexpr bool kStore = T::kStoreMat >= 0;
+  constexpr int SM = kStore ? T::kStoreMat : 0;                 // staged matrix that is updated in place
+  constexpr int SV = T::kStoreVec >= 0 ? T::kStoreVec : 0;
+  constexpr int kRedCols = 4 * kMaxRank;
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  __shared__ float red[kMapConsumerWarps][4 + 2 * kMaxRank];
+  __shared__ float red[kMapConsumerWarps][kRedCols];
+  __shared__ float red_mx[kMapConsumerWarps];
 
   float* smem; uint64_t* full; uint64_t* empty;
-  // kStore kinds: one elected lane releases the stage after its bulk store has drained the tile
-  pipeline_init<R, T::NM, T::NV, kMapTile>(smem, full, empty, smem_raw, T::kStore ? 1 : kMapConsumerWarps);
+  // store kinds: one elected lane releases the stage after its bulk store has drained the tile
+  pipeline_init<R, T::NM, T::NV, kMapTile>(smem, full, empty, smem_raw, kStore ? 1 : kMapConsumerWarps);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_full_tiles = a.n / kMapTile;
@@ -734,23 +922,23 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
         float* sb = smem + (size_t)stage * L::kStageFloats;
         {
           const int r0 = ct;
-          float* m0 = L::mat(sb, 0);
+          const float* m0 = L::mat(sb, 0);
           const float* m1 = L::mat(sb, T::NM > 1 ? 1 : 0);
           const float v0 = L::vec(sb, 0)[r0];
           const float v1 = T::NV > 1 ? L::vec(sb, T::NV > 1 ? 1 : 0)[r0] : 0.f;
           const float v2 = T::NV > 2 ? L::vec(sb, T::NV > 2 ? 2 : 0)[r0] : 0.f;
           const float v3 = T::NV > 3 ? L::vec(sb, T::NV > 3 ? 3 : 0)[r0] : 0.f;
-          body.row(m0 + r0 * R, m1 + r0 * R, v0, v1, v2, v3, tile * kMapTile + r0, o, m0 + r0 * R,
-                   &L::vec(sb, T::NV > 3 ? 3 : 0)[r0]);
+          body.row(m0 + r0 * R, m1 + r0 * R, v0, v1, v2, v3, tile * kMapTile + r0, o, L::mat(sb, SM) + r0 * R,
+                   &L::vec(sb, SV)[r0]);
         }
-        if constexpr (T::kStore) {
+        if constexpr (kStore) {
           // rows were updated in place in the shared tile: publish to the async proxy, then one lane
           // stores the tile with TMA and frees the stage once the engine has read it
           fence_proxy_async_smem();
           named_bar_sync(1, kMapConsumerWarps * 32);
           if (ct == 0) {
-            bulk_s2g(o.mat_out + tile * (int64_t)L::kMatFloats, L::mat(sb, 0), L::kMatFloats * 4);
-            bulk_s2g(o.vec_out + tile * (int64_t)kMapTile, L::vec(sb, 3), kMapTile * 4);
+            bulk_s2g(o.mat_out + tile * (int64_t)L::kMatFloats, L::mat(sb, SM), L::kMatFloats * 4);
+            if constexpr (T::kStoreVec >= 0) bulk_s2g(o.vec_out + tile * (int64_t)kMapTile, L::vec(sb, SV), kMapTile * 4);
             bulk_commit();
             bulk_wait_read0();
             mbar_arrive(&empty[stage]);
@@ -760,7 +948,7 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
           if (lane == 0) mbar_arrive(&empty[stage]);
         }
       }
-      if constexpr (T::kStore) {
+      if constexpr (kStore) {
         if (ct == 0) bulk_wait0();
       }
     }
@@ -781,8 +969,8 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
         const float v1 = T::NV > 1 ? a.vec[T::NV > 1 ? 1 : 0][r0] : 0.f;
         const float v2 = T::NV > 2 ? a.vec[T::NV > 2 ? 2 : 0][r0] : 0.f;
         const float v3 = T::NV > 3 ? a.vec[T::NV > 3 ? 3 : 0][r0] : 0.f;
-        body.row(m0, m1, v0, v1, v2, v3, r0, o, T::kStore ? o.mat_out + r0 * R : nullptr,
-                 T::kStore ? o.vec_out + r0 : nullptr);
+        body.row(m0, m1, v0, v1, v2, v3, r0, o, kStore ? o.mat_out + r0 * R : nullptr,
+                 T::kStoreVec >= 0 ? o.vec_out + r0 : nullptr);
       }
     }
     if constexpr (KIND == kMapApplyNorm) {
@@ -798,6 +986,18 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
       for (int k = 0; k < R; ++k) {
         float ta = warp_sum(body.acc.atX[k]), tb = warp_sum(body.acc.btX[k]);
         if (lane == 0) { red[warp][4 + k] = ta; red[warp][4 + R + k] = tb; }
+      }
+    }
+    if constexpr (map_is_fused_update(KIND)) {
+      const float mx = warp_max(body.acc.mx);
+      if (lane == 0) red_mx[warp] = mx;
+    }
+    if constexpr (map_is_updapp(KIND)) {
+#pragma unroll
+      for (int k = 0; k < R; ++k) {
+        const float t0 = warp_sum(body.gacc.ux0[k]), t1 = warp_sum(body.gacc.ux1[k]);
+        const float t2 = warp_sum(body.gacc.vx0[k]), t3 = warp_sum(body.gacc.vx1[k]);
+        if (lane == 0) { red[warp][k] = t0; red[warp][R + k] = t1; red[warp][2 * R + k] = t2; red[warp][3 * R + k] = t3; }
       }
     }
   }
@@ -827,6 +1027,51 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
       atomic_max_nonneg(&o.st->max_nabla, mx);
     }
   }
+  if constexpr (map_is_fused_update(KIND)) {
+    __syncthreads();
+    if constexpr (map_is_updapp(KIND)) {
+      constexpr int cnt = updapp_count(R);
+      for (int k = threadIdx.x; k < cnt; k += blockDim.x) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < kMapConsumerWarps; ++w) s += red[w][k];
+        o.partial[(size_t)blockIdx.x * cnt + k] = s;
+      }
+    }
+    if (threadIdx.x == 0) {
+      float mx = 0.f;
+#pragma unroll
+      for (int w = 0; w < kMapConsumerWarps; ++w) mx = fmaxf(mx, red_mx[w]);
+      atomic_max_nonneg(&o.st->max_nabla, mx);
+    }
+  }
+}
+
+// d -= (mu_d d) nablaD with mu_d = step / (max|nablaD| + tiny)                 psgd.py:582-584
+// (last pass of the fused update: max|nablaD| gates it, everything else already rode in the map sweep)
+__global__ void __launch_bounds__(256) d_update_kernel(float* __restrict__ d, const float* __restrict__ nd, int64_t n,
+                                                       float step, float tiny, const SmallState* __restrict__ st) {
+  const float mu_d = step / (st->max_nabla + tiny);
+  const int64_t stride = (int64_t)gridDim.x * blockDim.x;
+  const int64_t tid = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  const int64_t n4 = n / 4;
+  float4* d4 = reinterpret_cast<float4*>(d);
+  const float4* g4 = reinterpret_cast<const float4*>(nd);
+  int64_t i = tid;
+  for (; i + stride < n4; i += 2 * stride) {          // two independent 128-bit loads per array in flight
+    float4 x0 = d4[i], x1 = d4[i + stride];
+    const float4 y0 = g4[i], y1 = g4[i + stride];
+    x0.x -= (mu_d * x0.x) * y0.x; x0.y -= (mu_d * x0.y) * y0.y; x0.z -= (mu_d * x0.z) * y0.z; x0.w -= (mu_d * x0.w) * y0.w;
+    x1.x -= (mu_d * x1.x) * y1.x; x1.y -= (mu_d * x1.y) * y1.y; x1.z -= (mu_d * x1.z) * y1.z; x1.w -= (mu_d * x1.w) * y1.w;
+    d4[i] = x0; d4[i + stride] = x1;
+  }
+  for (; i < n4; i += stride) {
+    float4 x0 = d4[i];
+    const float4 y0 = g4[i];
+    x0.x -= (mu_d * x0.x) * y0.x; x0.y -= (mu_d * x0.y) * y0.y; x0.z -= (mu_d * x0.z) * y0.z; x0.w -= (mu_d * x0.w) * y0.w;
+    d4[i] = x0;
+  }
+  for (int64_t k = n4 * 4 + tid; k < n; k += stride) d[k] -= (mu_d * d[k]) * nd[k];
 }
 
 // =============================================================================================
@@ -895,7 +1140,10 @@ static int launch_gram(psgd_ctx* ctx, const SweepArgs& a, float* partial, int gr
 template <int R, int KIND>
 static int launch_map(psgd_ctx* ctx, const SweepArgs& a, const MapOut& o, int update_U, int grid) {
   ProfScope prof(ctx, KIND == kMapUpd2 ? PSGD_K_UVD_MAP_UPDATE2
-                      : (KIND == kMapUpd3U || KIND == kMapUpd3V) ? PSGD_K_UVD_MAP_UPDATE3 : PSGD_K_UVD_MAP_APPLY);
+                      : (KIND == kMapUpd3U || KIND == kMapUpd3V) ? PSGD_K_UVD_MAP_UPDATE3
+                      : (KIND == kMapUpdFU || KIND == kMapUpdFV) ? PSGD_K_UVD_MAP_FUSED
+                      : map_is_updapp(KIND) ? PSGD_K_UVD_MAP_UPDAPP
+                      : KIND == kMapApplyD ? PSGD_K_UVD_MAP_APPLY_D : PSGD_K_UVD_MAP_APPLY);
   using T = MapTraits<KIND>;
   using L = TileLayout<R, T::NM, T::NV, kMapTile>;
   auto kern = map_sweep_kernel<R, KIND>;
@@ -933,6 +1181,11 @@ static int ensure_attrs() {
   PSGD_CUDA_CHECK((map_attr<R, kMapMatvec2>()));
   PSGD_CUDA_CHECK((map_attr<R, kMapApplyNorm>()));
   PSGD_CUDA_CHECK((map_attr<R, kMapApplyParam>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpdFU>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpdFV>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpdAppU>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapUpdAppV>()));
+  PSGD_CUDA_CHECK((map_attr<R, kMapApplyD>()));
   done = true;
   return PSGD_OK;
 }
@@ -944,18 +1197,51 @@ struct Scratch {
   float* a; float* b; float* nd;   // N-vectors (update only)
 };
 
-static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, bool update, Scratch* s, int64_t extra_vec = 0) {
-  const size_t table = (size_t)(2 * r) * (2 * r + 2);
+// n_vecs N-vectors of scratch: 3 (a, b, nablaD) for the three-sweep update, 1 (nablaD) for the fused forms
+static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, int n_vecs, Scratch* s, int64_t extra_vec = 0) {
+  const size_t table = (size_t)(2 * r + 2) * (2 * r + 2);      // >= every partial record (Gram tables, update+apply sums)
   size_t bytes = WsCarver::padded(sizeof(float) * table * grid) + WsCarver::padded(sizeof(double) * table) +
-                 WsCarver::padded(sizeof(SmallState)) + (update ? 3 * WsCarver::padded(sizeof(float) * (size_t)n) : 0) +
+                 WsCarver::padded(sizeof(SmallState)) + n_vecs * WsCarver::padded(sizeof(float) * (size_t)n) +
                  WsCarver::padded(sizeof(float) * (size_t)extra_vec);
   PSGD_RETURN_IF(ctx->reserve(bytes));
   WsCarver c(ctx->ws);
   s->partial = c.take<float>(table * grid);
   s->G = c.take<double>(table);
   s->st = c.take<SmallState>(1);
-  if (update) { s->a = c.take<float>(n); s->b = c.take<float>(n); s->nd = c.take<float>(n); }
-  else if (extra_vec) s->a = c.take<float>(extra_vec);
+  s->a = s->b = s->nd = nullptr;
+  if (n_vecs >= 1) s->nd = c.take<float>(n);
+  if (n_vecs >= 3) { s->a = c.take<float>(n); s->b = c.take<float>(n); }
+  if (n_vecs == 0 && extra_vec) s->a = c.take<float>(extra_vec);
+  return PSGD_OK;
+}
+
+// psgd.py:562-567
+static int balance_pass(psgd_ctx* ctx, float* U, float* V, int64_t count, SmallState* sst) {
+  cudaStream_t st = ctx->stream;
+  zero_small_kernel<<<1, 1, 0, st>>>(sst);
+  PSGD_LAUNCH_CHECK(ctx);
+  maxabs2_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, count, sst);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &sst->maxU, 2));
+  balance_rho_kernel<<<1, 1, 0, st>>>(sst);
+  PSGD_LAUNCH_CHECK(ctx);
+  balance_scale_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, count, sst);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+// Sweep 1 of every update form + the r x r algebra that follows it.
+template <int R>
+static int update_head(psgd_ctx* ctx, const SweepArgs& a1, const Scratch& s, int grid, int fused, int update_U,
+                       float step, float tiny) {
+  cudaStream_t st = ctx->stream;
+  PSGD_RETURN_IF((launch_gram<R, kUpdate>(ctx, a1, s.partial, grid)));
+  constexpr int table = GramPlan<R, kUpdate>::TABLE;
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
+  uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, fused, update_U, step, tiny, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 
@@ -964,34 +1250,35 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
                        float step, float tiny, int balance, int update_U) {
   PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
+  const int fused = ctx->opt_uvd_fused;
   Scratch s;
-  PSGD_RETURN_IF(carve(ctx, n, R, grid, true, &s));
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, fused ? 1 : 3, &s));
   cudaStream_t st = ctx->stream;
 
-  if (balance) {
-    zero_small_kernel<<<1, 1, 0, st>>>(s.st);
-    PSGD_LAUNCH_CHECK(ctx);
-    maxabs2_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
-    PSGD_LAUNCH_CHECK(ctx);
-    PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &s.st->maxU, 2));
-    balance_rho_kernel<<<1, 1, 0, st>>>(s.st);
-    PSGD_LAUNCH_CHECK(ctx);
-    balance_scale_kernel<<<ctx->num_sms * 4, 256, 0, st>>>(U, V, n * R, s.st);
-    PSGD_LAUNCH_CHECK(ctx);
-  }
+  if (balance) PSGD_RETURN_IF(balance_pass(ctx, U, V, n * R, s.st));
 
   // sweep 1
   SweepArgs a1{};
   a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.n = n; a1.direct = ctx->opt_direct;
-  PSGD_RETURN_IF((launch_gram<R, kUpdate>(ctx, a1, s.partial, grid)));
-  constexpr int table = GramPlan<R, kUpdate>::W * GramPlan<R, kUpdate>::E;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
-  uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF((update_head<R>(ctx, a1, s, grid, fused, update_U, step, tiny)));
 
-  // sweep 2
+  if (fused) {
+    // sweep 2: a, b, nablaD per row + the rank-2 update of U (or V), whose coefficients came out of the Gram table
+    MapOut o2{};
+    o2.o2 = s.nd; o2.st = s.st; o2.mat_out = update_U ? U : V;
+    if (update_U) PSGD_RETURN_IF((launch_map<R, kMapUpdFU>(ctx, a1, o2, 1, grid)));
+    else PSGD_RETURN_IF((launch_map<R, kMapUpdFV>(ctx, a1, o2, 0, grid)));
+    PSGD_RETURN_IF(cross_rank_reduce(ctx, nullptr, 0, &s.st->max_nabla, 1));
+    // pass 3: only d waits for max|nablaD|
+    {
+      ProfScope prof(ctx, PSGD_K_UVD_D_UPDATE);
+      d_update_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(d, s.nd, n, step, tiny, s.st);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    return PSGD_OK;
+  }
+
+  // three-sweep form (psgd_set_option("uvd_fused", 0)): the reductions over a, b are taken directly in sweep 2
   MapOut o2{};
   o2.o0 = s.a; o2.o1 = s.b; o2.o2 = s.nd; o2.partial = s.partial; o2.st = s.st;
   PSGD_RETURN_IF((launch_map<R, kMapUpd2>(ctx, a1, o2, update_U, grid)));
@@ -1013,18 +1300,58 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   return PSGD_OK;
 }
 
+// update_precond_UVd_math_ followed by precond_grad_UVd_math on the updated state, as THREE sweeps:
+//   1  Gram table of (U, V, d h, v/d)                                              reads U V d h v
+//   2  a, b, nablaD per row, rank-2 update of U (or V) written back, and the apply's sums over the UPDATED rows
+//      [U' V']^T [d g | d nablaD g] (U'^T U' is expanded through the table)        reads U V d h v g, writes U' (V'), nablaD
+//   3  d' = d - mu_d d nablaD and out = d' (I + V'U'^T)(I + U'V'^T)(d' g)           reads U' V' d nablaD g, writes d', out
+// Same results as the two separate calls; each of U, V is read three times per step instead of five.
+template <int R>
+static int update_apply_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h,
+                             const float* g, float* out, int64_t n, float step, float tiny, int balance, int update_U) {
+  PSGD_RETURN_IF(ensure_attrs<R>());
+  const int grid = grid_for(ctx, n);
+  Scratch s;
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, 1, &s));
+  cudaStream_t st = ctx->stream;
+  if (balance) PSGD_RETURN_IF(balance_pass(ctx, U, V, n * R, s.st));
+
+  SweepArgs a1{};
+  a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.vec[3] = g; a1.n = n;
+  a1.direct = ctx->opt_direct;
+  PSGD_RETURN_IF((update_head<R>(ctx, a1, s, grid, 1, update_U, step, tiny)));
+
+  MapOut o2{};
+  o2.o2 = s.nd; o2.st = s.st; o2.mat_out = update_U ? U : V; o2.partial = s.partial;
+  if (update_U) PSGD_RETURN_IF((launch_map<R, kMapUpdAppU>(ctx, a1, o2, 1, grid)));
+  else PSGD_RETURN_IF((launch_map<R, kMapUpdAppV>(ctx, a1, o2, 0, grid)));
+  constexpr int cnt = updapp_count(R);
+  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, cnt, s.G);
+  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, cnt, &s.st->max_nabla, 1));
+  uvd_small_ua_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
+  PSGD_LAUNCH_CHECK(ctx);
+
+  SweepArgs a3{};
+  a3.mat[0] = U; a3.mat[1] = V; a3.vec[0] = d; a3.vec[1] = s.nd; a3.vec[2] = g; a3.n = n; a3.direct = ctx->opt_direct;
+  MapOut o3{};
+  o3.o0 = out; o3.o1 = d; o3.st = s.st;
+  PSGD_RETURN_IF((launch_map<R, kMapApplyD>(ctx, a3, o3, 0, grid)));
+  return PSGD_OK;
+}
+
 template <int R>
 static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* out,
                       int64_t n) {
   PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
   Scratch s;
-  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
-  constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
+  constexpr int table = GramPlan<R, kApply>::TABLE;
   reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
@@ -1075,12 +1402,12 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
   const int grid = grid_for(ctx, n);
   const bool clip = !isinf(max_norm);
   Scratch s;
-  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s, (clip && !pre_out) ? n : 0));
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s, (clip && !pre_out) ? n : 0));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
-  constexpr int table = GramPlan<R, kApply>::W * GramPlan<R, kApply>::E;
+  constexpr int table = GramPlan<R, kApply>::TABLE;
   reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
@@ -1110,12 +1437,12 @@ static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const floa
   PSGD_RETURN_IF(ensure_attrs<R>());
   const int grid = grid_for(ctx, n);
   Scratch s;
-  PSGD_RETURN_IF(carve(ctx, n, R, grid, false, &s));
+  PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = x; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kMatvec>(ctx, a, s.partial, grid)));
-  constexpr int table = GramPlan<R, kMatvec>::W * GramPlan<R, kMatvec>::E;
+  constexpr int table = GramPlan<R, kMatvec>::TABLE;
   reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
@@ -1145,6 +1472,12 @@ static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const floa
 int update(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, int64_t n, int r,
            float step, float tiny, int balance, int update_U) {
 #define CALL(R) update_impl<R>(ctx, U, V, d, v, h, n, step, tiny, balance, update_U)
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
+}
+int update_apply(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, const float* g,
+                 float* out, int64_t n, int r, float step, float tiny, int balance, int update_U) {
+#define CALL(R) update_apply_impl<R>(ctx, U, V, d, v, h, g, out, n, step, tiny, balance, update_U)
   PSGD_RANK_SWITCH(r, CALL)
 #undef CALL
 }
@@ -1192,6 +1525,19 @@ extern "C" int psgd_uvd_update(psgd_ctx* ctx, float* U, float* V, float* d, cons
   if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 5));
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   return uvd::update(ctx, U, V, d, v, h, n, r, step, tiny, balance, update_U);
+}
+
+extern "C" int psgd_uvd_update_apply(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h,
+                                     const float* g, float* out, int64_t n, int r, float step, float tiny, int balance,
+                                     int update_U) {
+  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
+  PSGD_REQUIRE(n >= 0 && r >= 1, PSGD_ERR_BAD_SHAPE, "UVd update+apply: bad sizes n=%lld r=%d", (long long)n, r);
+  if (n == 0 && !is_sharded(ctx)) return PSGD_OK;
+  const void* ptrs[] = {U, V, d, v, h, g, out};
+  if (n > 0) PSGD_RETURN_IF(check_uvd_ptrs(ptrs, 7));
+  PSGD_REQUIRE(n == 0 || (out != d && out != g), PSGD_ERR_BAD_POINTER, "UVd update+apply: out must not alias d or g");
+  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
+  return uvd::update_apply(ctx, U, V, d, v, h, g, out, n, r, step, tiny, balance, update_U);
 }
 
 extern "C" int psgd_uvd_apply(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g,

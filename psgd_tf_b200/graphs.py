@@ -1,14 +1,16 @@
 """CUDA-graph replay of the UVd update+apply step.
 
-One step of the UVd path is a fixed chain of ~12 kernels (3 sweeps + small r x r kernels for the update, 2 sweeps for
-the apply, plus one peer-exchange kernel per phase when the vector is sharded over GPUs, csrc/comm.cu).  At 100 M
+One step of the UVd path is a fixed chain of ~8 kernels (three sweeps + small r x r kernels in the fused
+update+apply form, ``psgd_uvd_update_apply``; ~11 as two separate calls), plus one peer-exchange kernel per phase when
+the vector is sharded over GPUs (csrc/comm.cu).  At 100 M
 parameters on one GPU the chain runs ~7 ms and launch latency is noise; sharded 8 ways it runs < 1 ms and the ~12
 launches + two Python/ctypes calls become a visible fraction.  The chain has no host dependency (coin flips are
 arguments, the cross-rank epoch counter lives in device memory), so it is captured once per (input buffers, coin
 flips) and replayed with a single ``cudaGraphLaunch``.
 
 This is plumbing around the reference API, not a different algorithm: the graph contains exactly the kernels that
-``update_precond_UVd_math_`` (psgd.py:554-617) followed by ``precond_grad_UVd_math`` (psgd.py:619-627) launch.
+``update_precond_and_grad_UVd`` launches -- or, with ``fused=False``, those of ``update_precond_UVd_math_``
+(psgd.py:554-617) followed by ``precond_grad_UVd_math`` (psgd.py:619-627).
 """
 from __future__ import annotations
 
@@ -29,11 +31,13 @@ class UVdStepGraphs:
     to the graph: consume it before the same key is replayed again.
     """
 
-    def __init__(self, U: torch.Tensor, V: torch.Tensor, d: torch.Tensor, step: float = 0.01, tiny: float = _psgd._tiny):
+    def __init__(self, U: torch.Tensor, V: torch.Tensor, d: torch.Tensor, step: float = 0.01, tiny: float = _psgd._tiny,
+                 fused: bool = True):
         if not (U.is_cuda and V.is_cuda and d.is_cuda):
             raise RuntimeError("UVdStepGraphs: state must live on a CUDA device (no CPU path)")
         self.U, self.V, self.d = U, V, d
         self.step_size, self.tiny = float(step), float(tiny)
+        self.fused = bool(fused)
         self._stream = torch.cuda.Stream(device=U.device)
         self._graphs: Dict[Tuple, Tuple[torch.cuda.CUDAGraph, torch.Tensor]] = {}
         self._warm = False
@@ -42,6 +46,9 @@ class UVdStepGraphs:
         self.kernel_launches = 0          # kernels executed through graph replays (the library's own counter sees only captures)
 
     def _eager(self, v, h, g, balance, update_U):
+        if self.fused:
+            return _psgd.update_precond_and_grad_UVd(self.U, self.V, self.d, v, h, g, self.step_size, self.tiny,
+                                                     balance=balance, update_U=update_U)
         _psgd.update_precond_UVd_math_(self.U, self.V, self.d, v, h, self.step_size, self.tiny, balance=balance,
                                        update_U=update_U)
         return _psgd.precond_grad_UVd_math(self.U, self.V, self.d, g)

@@ -438,6 +438,28 @@ def precond_grad_UVd_math(U, V, d, g):
     return out
 
 
+def update_precond_and_grad_UVd(U, V, d, v, h, g, step, tiny=_tiny, *, balance=None, update_U=None):
+    """``update_precond_UVd_math_(U, V, d, v, h, step, tiny)`` followed by ``precond_grad_UVd_math(U, V, d, g)`` -- the
+    sequence ``UVd.step`` runs (psgd.py:732-748) -- as ONE fused call (``psgd_uvd_update_apply``): three sweeps over
+    U, V instead of five.  Updates U, V, d in place and returns the preconditioned gradient of the UPDATED
+    preconditioner; same results as the two calls."""
+    U, V, d = _inplace(U, "U"), _inplace(V, "V"), _inplace(d, "d")
+    v, h, g = _in(v, "v"), _in(h, "h"), _in(g, "g")
+    n, r = U.shape
+    if V.shape != U.shape:
+        raise ValueError("update_precond_and_grad_UVd: U and V must have the same shape")
+    _col(d, n, "d"); _col(v, n, "v"); _col(h, n, "h"); _col(g, n, "g")
+    if balance is None:
+        balance = _rng.random() < 0.01
+    if update_U is None:
+        update_U = _rng.random() < 0.5
+    out = torch.empty_like(g)
+    ctx = get_context(U.device.index)
+    check(ctx.lib.psgd_uvd_update_apply(ctx.handle, _p(U), _p(V), _p(d), _p(v), _p(h), _p(g), _p(out), n, r,
+                                        _scalar(step), _scalar(tiny), int(bool(balance)), int(bool(update_U))))
+    return out
+
+
 # north-star spellings (BASELINE.json) of the same two functions
 update_precond_UVd = update_precond_UVd_math_
 precond_grad_UVd = precond_grad_UVd_math

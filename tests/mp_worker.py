@@ -78,6 +78,34 @@ def cpu_protocol(rank, world):
     Ur, Vr, dr = O.update_precond_UVd_math(f64["U"], f64["V"], f64["d"], f64["v"], f64["h"], 0.01, update_U=True)
     np.testing.assert_allclose(U_new, Ur[lo:hi], rtol=1e-9, atol=1e-15)
     np.testing.assert_allclose(d_new, dr[lo:hi, 0], rtol=1e-9)
+    # ---- protocol of the FUSED forms (psgd_uvd_update with "uvd_fused", psgd_uvd_update_apply): exchange 1 = the
+    # (2r+2)^2 Gram table, exchange 2 = max|nablaD| (+ 4r sums over the updated rows for the fused apply) -------------
+    from tests import uvd_pipeline_model as M
+    for update_U in (True, False):
+        sh = {k: c[k][lo:hi] for k in c}
+        G = torch.from_numpy(M.gram_table(sh["U"], sh["V"], sh["d"], sh["h"], sh["v"]))
+        dist.all_reduce(G)                                              # exchange 1: sums
+        k = M.small1(G.numpy(), r, update_U, 0.01)
+        Un, Vn, nd = M.fused_map(sh["U"], sh["V"], sh["d"], sh["h"], sh["v"], k, update_U)
+        x0 = (sh["d"] * sh["g"]).astype(np.float32)
+        x1 = (x0 * nd).astype(np.float32)
+        Z = np.concatenate([Un, Vn], 1).astype(np.float64)
+        sums = torch.from_numpy(np.concatenate([Z.T @ x0, Z.T @ x1], 1))                 # [2r, 2]
+        mx = torch.tensor([np.abs(nd).max() if hi > lo else 0.0], dtype=torch.float64)
+        dist.all_reduce(sums)                                           # exchange 2: 4r sums ...
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)                       # ... and one max
+        sums = sums.numpy()
+        mu_d = np.float32(0.01) / (np.float32(mx.item()) + O.TINY)
+        pp = sums[r:, 0] - np.float64(mu_d) * sums[r:, 1]
+        tt = sums[:r, 0] - np.float64(mu_d) * sums[:r, 1] + M.updated_UtU(k, update_U) @ pp
+        dn = (sh["d"] - (mu_d * sh["d"]) * nd).astype(np.float32)
+        y = dn * sh["g"] + Un @ pp.astype(np.float32)[:, None]
+        pre = dn * (y + Vn @ tt.astype(np.float32)[:, None])
+        Ur, Vr, dr = O.update_precond_UVd_math(c["U"], c["V"], c["d"], c["v"], c["h"], 0.01, update_U=update_U)
+        pr = O.precond_grad_UVd_math(Ur, Vr, dr, c["g"])
+        for got, want in ((Un, Ur), (Vn, Vr), (dn, dr), (pre, pr)):
+            if hi > lo:
+                assert np.linalg.norm(got.astype(np.float64) - want[lo:hi]) / np.linalg.norm(want) < 2e-6
 
 
 def gpu_uvd(rank, world, exchange="hook"):
@@ -103,6 +131,14 @@ def gpu_uvd(rank, world, exchange="hook"):
                 if hi > lo:
                     e = np.linalg.norm(got.cpu().numpy().astype(np.float64) - want[lo:hi]) / np.linalg.norm(want)
                     assert e < 1e-5, (n, r, kw, e)
+            # the fused update+apply call: same results, two exchanges instead of three
+            U, V, d = dev(c["U"][lo:hi]), dev(c["V"][lo:hi]), dev(c["d"][lo:hi])
+            pre = psgd.update_precond_and_grad_UVd(U, V, d, dev(c["v"][lo:hi]), dev(c["h"][lo:hi]), dev(c["g"][lo:hi]),
+                                                   0.01, psgd._tiny, **kw)
+            for got, want in ((U, Ur), (V, Vr), (d, dr), (pre, pr)):
+                if hi > lo:
+                    e = np.linalg.norm(got.cpu().numpy().astype(np.float64) - want[lo:hi]) / np.linalg.norm(want)
+                    assert e < 1e-5, ("fused", n, r, kw, e)
     # X-shape on mirrored chunk pairs, diagonal on plain chunks: only the max is exchanged
     n = 20_001
     c = cases.vec_case(7, n)
@@ -113,7 +149,8 @@ def gpu_uvd(rank, world, exchange="hook"):
     assert np.allclose(q.cpu().numpy(), want[lo:hi], rtol=1e-5)
     if exchange == "peer":
         done = ctx.comm_status()                  # raises if any in-kernel wait timed out
-        assert done == 3 * (3 + 4) + 1, done        # per size: 2+1 exchanges (plain step) + 3+1 (balance step); + diag
+        # per size: separate calls 2+1 exchanges (plain step) + 3+1 (balance step), fused call 2 + 3; + diag
+        assert done == 3 * (3 + 4 + 2 + 3) + 1, done
         gpu_uvd_graph(rank, world, ctx)
         ctx.comm_detach()
     else:
@@ -136,13 +173,12 @@ def gpu_uvd_graph(rank, world, ctx):
     e0 = ctx.comm_status()
     for i in range(8):
         v, h, g = ins[i % 2]
-        psgd.update_precond_UVd_math_(Ue, Ve, de, v, h, 0.01, psgd._tiny, balance=False, update_U=(i % 2 == 0))
-        want = psgd.precond_grad_UVd_math(Ue, Ve, de, g)
+        want = psgd.update_precond_and_grad_UVd(Ue, Ve, de, v, h, g, 0.01, psgd._tiny, balance=False, update_U=(i % 2 == 0))
         got = gs.step(v, h, g, False, i % 2 == 0)
         torch.cuda.synchronize()
         assert torch.equal(got, want) and torch.equal(Ug, Ue) and torch.equal(Vg, Ve) and torch.equal(dg, de), i
     assert gs.replays >= 5, gs.replays
-    assert ctx.comm_status() - e0 == 8 * 2 * 3, (ctx.comm_status(), e0)   # 3 exchanges per update+apply, eager + graph
+    assert ctx.comm_status() - e0 == 8 * 2 * 2, (ctx.comm_status(), e0)   # 2 exchanges per fused update+apply, eager + graph
 
 
 def gpu_kron(rank, world):

@@ -53,9 +53,12 @@ UVD_SIZES = [(1021, 10), (37, 3), (256, 10), (255, 10), (257, 10), (4096, 10), (
 
 @pytest.mark.parametrize("n,r", UVD_SIZES)
 @pytest.mark.parametrize("direct", [0, 1])
-def test_uvd_update_and_apply(psgd, n, r, direct):
+@pytest.mark.parametrize("fused", [1, 0])
+def test_uvd_update_and_apply(psgd, n, r, direct, fused):
+    """fused=1: two sweeps + d pass, rank-2 coefficients from the Gram table (default); fused=0: three sweeps."""
     ctx = psgd.get_context()
     ctx.set_option("direct", direct)
+    ctx.set_option("uvd_fused", fused)
     try:
         c = cases.uvd_case(1000 + n + r, n, r)
         for kw in (dict(update_U=True, balance=False), dict(update_U=False, balance=False),
@@ -75,9 +78,41 @@ def test_uvd_update_and_apply(psgd, n, r, direct):
         check(mv, O.IpUVtmatvec(c["U"], c["V"], c["g"]), what="IpUVtmatvec")
     finally:
         ctx.set_option("direct", 0)
+        ctx.set_option("uvd_fused", 1)
 
 
-def test_uvd_step_graph_replay_matches_eager(psgd):
+@pytest.mark.parametrize("n,r", UVD_SIZES)
+@pytest.mark.parametrize("direct", [0, 1])
+def test_uvd_fused_update_apply(psgd, n, r, direct):
+    """update_precond_and_grad_UVd (psgd_uvd_update_apply, three sweeps) == update then apply (psgd.py:732-748)."""
+    ctx = psgd.get_context()
+    ctx.set_option("direct", direct)
+    try:
+        c = cases.uvd_case(2000 + n + r, n, r, scale=3.0)
+        for kw in (dict(update_U=True, balance=False), dict(update_U=False, balance=False),
+                   dict(update_U=False, balance=True)):
+            U, V, d = dev(c["U"]), dev(c["V"]), dev(c["d"])
+            g = dev(c["g"])
+            pre = psgd.update_precond_and_grad_UVd(U, V, d, dev(c["v"]), dev(c["h"]), g, 0.01, psgd._tiny, **kw)
+            Ur, Vr, dr = O.update_precond_UVd_math(c["U"], c["V"], c["d"], c["v"], c["h"], 0.01, **kw)
+            check(U, Ur, what=f"U {kw}"); check(V, Vr, what=f"V {kw}"); check(d, dr, what=f"d {kw}")
+            assert pre.shape == (n, 1) and torch.equal(g, dev(c["g"]))
+            check(pre, O.precond_grad_UVd_math(Ur, Vr, dr, c["g"]), what=f"pre_grad {kw}")
+    finally:
+        ctx.set_option("direct", 0)
+
+
+def test_uvd_fused_update_apply_rejects_aliased_output(psgd):
+    c = cases.uvd_case(13, 512, 4)
+    ctx = psgd.get_context()
+    U, V, d, v, h = (dev(c[k]) for k in ("U", "V", "d", "v", "h"))
+    p = lambda t: t.data_ptr()
+    rc = ctx.lib.psgd_uvd_update_apply(ctx.handle, p(U), p(V), p(d), p(v), p(h), p(d), p(d), 512, 4, 0.01, 1e-38, 0, 1)
+    assert rc != 0 and b"alias" in ctx.lib.psgd_last_error()
+
+
+@pytest.mark.parametrize("fused", [True, False])
+def test_uvd_step_graph_replay_matches_eager(psgd, fused):
     """graphs.UVdStepGraphs replays exactly the kernels of update + apply: bit-identical state and output."""
     from psgd_tf_b200.graphs import UVdStepGraphs
     n, r = 50_021, 10
@@ -85,12 +120,15 @@ def test_uvd_step_graph_replay_matches_eager(psgd):
     ins = [tuple(dev(np.roll(c[k], s, 0)) for k in ("v", "h", "g")) for s in (0, 3)]
     Ue, Ve, de = dev(c["U"]), dev(c["V"]), dev(c["d"])
     Ug, Vg, dg = Ue.clone(), Ve.clone(), de.clone()
-    gs = UVdStepGraphs(Ug, Vg, dg, 0.01)
+    gs = UVdStepGraphs(Ug, Vg, dg, 0.01, fused=fused)
     for i in range(9):
         v, h, g = ins[i % 2]
         flips = dict(balance=(i == 6), update_U=(i % 3 != 0))
-        psgd.update_precond_UVd_math_(Ue, Ve, de, v, h, 0.01, psgd._tiny, **flips)
-        want = psgd.precond_grad_UVd_math(Ue, Ve, de, g)
+        if fused:
+            want = psgd.update_precond_and_grad_UVd(Ue, Ve, de, v, h, g, 0.01, psgd._tiny, **flips)
+        else:
+            psgd.update_precond_UVd_math_(Ue, Ve, de, v, h, 0.01, psgd._tiny, **flips)
+            want = psgd.precond_grad_UVd_math(Ue, Ve, de, g)
         got = gs.step(v, h, g, **flips)
         torch.cuda.synchronize()
         assert torch.equal(got, want), i
@@ -135,8 +173,10 @@ def test_uvd_is_deterministic(psgd):
         assert torch.equal(a, b)
 
 
-def test_uvd_trajectory_100_steps(psgd):
+@pytest.mark.parametrize("form", ["separate", "separate-3sweep", "fused"])
+def test_uvd_trajectory_100_steps(psgd, form):
     """Trajectory agreement over 100 steps with explicit inputs and coin flips (north star)."""
+    psgd.get_context().set_option("uvd_fused", 0 if form == "separate-3sweep" else 1)
     n, r = 1021, 10                                        # cfg2: rnn_xor_UVd_preconditioner.py sizes
     c = cases.uvd_case(5, n, r)
     rng = np.random.default_rng(6)
@@ -149,10 +189,14 @@ def test_uvd_trajectory_100_steps(psgd):
         h = (hdiag * v).astype(np.float32)
         g = rng.standard_normal((n, 1)).astype(np.float32)
         kw = dict(balance=(t % 25 == 7), update_U=bool(rng.random() < 0.5))
-        psgd.update_precond_UVd_math_(U, V, d, dev(v), dev(h), 0.01, psgd._tiny, **kw)
+        if form == "fused":
+            pre = psgd.update_precond_and_grad_UVd(U, V, d, dev(v), dev(h), dev(g), 0.01, psgd._tiny, **kw)
+        else:
+            psgd.update_precond_UVd_math_(U, V, d, dev(v), dev(h), 0.01, psgd._tiny, **kw)
+            pre = psgd.precond_grad_UVd_math(U, V, d, dev(g))
         Ur, Vr, dr = O.update_precond_UVd_math(Ur, Vr, dr, v, h, 0.01, **kw)
-        pre = psgd.precond_grad_UVd_math(U, V, d, dev(g))
         worst = max(worst, cases.rel_err(host(pre), O.precond_grad_UVd_math(Ur, Vr, dr, g)))
+    psgd.get_context().set_option("uvd_fused", 1)
     # per-step tolerance 1e-5; over a 100-step trajectory both float32 implementations drift independently
     assert worst < 1e-4, worst
     check(d, dr, 1e-4, "d after 100 steps"); check(U, Ur, 1e-4, "U after 100 steps"); check(V, Vr, 1e-4, "V after 100 steps")

@@ -144,17 +144,23 @@ def main():
                 "lsu_shared_pct", "issue_active_pct", "regs", "grid", "block", "warp_inst"]
         with open(os.path.join(DST, f"{tag}_ncu_full_summary.csv"), "w", newline="") as fh:
             fh.write("# ncu --set full --clock-control none --import-source on (tools/profile_gpu.sh); one row per captured launch.\n"
-                     "# uvd_full: the five sweeps of one UVd update+apply at N=1e8, r=10.  kron_full_head/tail: launches 0-1 and the\n"
+                     "# uvd_full: the sweeps of one UVd update+apply at N=1e8, r=10 (r01: five sweeps of the two-call form; later tags: the three sweeps of the fused call).  kron_full_head/tail: launches 0-1 and the\n"
                      "# last 8 GEMM launches of one Kron step (6 layers per grouped launch).  gemm4096: one dense 4096^3 product.\n")
             w = csv.DictWriter(fh, fieldnames=keys, extrasaction="ignore")
             w.writeheader()
             for d in allrows:
                 w.writerow(d)
-        # DRAM traffic per launch for bench.py's roofline.traffic
+        # DRAM traffic per launch for bench.py's roofline.traffic; entries of earlier captures (other kernels) are kept
         traffic = {}
+        prev = sorted(f for f in os.listdir(DST) if f.endswith("_traffic.json") and not f.startswith(tag + "_"))
+        if prev:
+            traffic.update(json.load(open(os.path.join(DST, prev[-1]))).get("bytes_per_launch", {}))
         names = {"gram_sweep_kernel<10, 0>": "uvd_gram_update", "map_sweep_kernel<10, 0>": "uvd_map_update2",
                  "map_sweep_kernel<10, 1>": "uvd_map_update3", "map_sweep_kernel<10, 2>": "uvd_map_update3",
-                 "gram_sweep_kernel<10, 1>": "uvd_gram_apply", "map_sweep_kernel<10, 3>": "uvd_map_apply"}
+                 "gram_sweep_kernel<10, 1>": "uvd_gram_apply", "map_sweep_kernel<10, 3>": "uvd_map_apply",
+                 "map_sweep_kernel<10, 7>": "uvd_map_fused", "map_sweep_kernel<10, 8>": "uvd_map_fused",
+                 "map_sweep_kernel<10, 9>": "uvd_map_updapp", "map_sweep_kernel<10, 10>": "uvd_map_updapp",
+                 "map_sweep_kernel<10, 11>": "uvd_map_apply_d", "d_update_kernel": "uvd_d_update"}
         for d in allrows:
             if d["capture"] == "uvd_full" and d["kernel"] in names and d.get("dram_read_MB") != "":
                 traffic[names[d["kernel"]]] = int((d["dram_read_MB"] + d["dram_write_MB"]) * 1e6)
@@ -164,7 +170,8 @@ def main():
         g = [d for d in allrows if d["capture"] == "gemm4096" and d.get("dram_read_MB") != ""]
         if g:
             traffic["gemm_tc_dense_4096"] = int((g[0]["dram_read_MB"] + g[0]["dram_write_MB"]) * 1e6)
-        json.dump({"source": f"profiles/{tag}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch)",
+        json.dump({"source": f"profiles/{tag}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
+                             "kernels not re-captured under this tag keep the previous capture's figure)",
                    "bytes_per_launch": traffic}, open(os.path.join(DST, f"{tag}_traffic.json"), "w"), indent=1)
     hs = "".join(hotspots(tag, n) for n in ("uvd_full", "kron_full_tail", "gemm4096", "gemm4096_ts"))
     if hs:
