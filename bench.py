@@ -54,51 +54,71 @@ def load_peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
-    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+    """nvidia-smi clocks/throttle reasons DURING the timed region (B200_PROFILING.md recipe).
+
+    ``start()`` launches ``nvidia-smi -lms 50`` and is called BEFORE the warm-up steps: NVML start-up takes 0.1-0.3 s on
+    a fresh box and stalls kernel submission while it initialises, which must not land inside a 0.1 s timed region.
+    ``mark()`` stamps the start of the timed region, ``stop()`` its end; only samples stamped in between are used (the
+    nearest ones if the region is shorter than the sampling period)."""
+    Q = ("timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, device_index: int):
-        self.proc, self.idx = None, device_index
-        self.path = f"/tmp/psgd_bench_clocks_{os.getpid()}.csv"
+        self.proc, self.idx, self.t0 = None, device_index, None
+        self.path = f"/tmp/psgd_bench_clocks_{os.getpid()}_{id(self)}.csv"
 
     def start(self):
         try:
             self.fh = open(self.path, "w")
             self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                          "-lms", "100", "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+                                          "-lms", "50", "-i", str(self.idx)], stdout=self.fh, stderr=subprocess.DEVNULL)
+            t_end = time.time() + 1.5
+            while time.time() < t_end and os.path.getsize(self.path) == 0:      # wait until NVML is up and sampling
+                time.sleep(0.02)
         except Exception:
             self.proc = None
 
+    def mark(self):
+        import datetime
+        self.t0 = datetime.datetime.now()
+
     def stop(self):
+        import datetime
+        t1 = datetime.datetime.now()
         if self.proc is None:
             return None
-        time.sleep(0.15)
+        time.sleep(0.06)
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
         self.fh.close()
-        sm, mx, reasons = [], [], set()
+        rows = []
         for line in open(self.path):
             f = [x.strip() for x in line.split(",")]
             if len(f) < 9:
                 continue
             try:
-                sm.append(float(f[1])); mx.append(float(f[2]))
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f")
+                rows.append((ts, float(f[1]), float(f[2]), [v.lower().startswith("active") for v in f[5:9]]))
             except ValueError:
                 continue
-            for name, val in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
-                if val.lower().startswith("active"):
-                    reasons.add(name)
         try:
             os.remove(self.path)
         except OSError:
             pass
-        if not sm:
+        if not rows:
             return None
-        return dict(sm_mhz=float(np.median(sm)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons), samples=len(sm))
+        t0 = self.t0 or rows[0][0]
+        inside = [r for r in rows if t0 <= r[0] <= t1]
+        if not inside:        # region shorter than the sampling period: the sample nearest to its middle
+            mid = t0 + (t1 - t0) / 2
+            inside = [min(rows, key=lambda r: abs((r[0] - mid).total_seconds()))]
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        reasons = sorted({n for r in inside for n, on in zip(names, r[3]) if on})
+        return dict(sm_mhz=float(np.median([r[1] for r in inside])), sm_max_mhz=float(max(r[2] for r in inside)),
+                    reasons=reasons, samples=len(inside))
 
 
 def load_traffic():
@@ -216,26 +236,48 @@ def run_uvd(args, rank, world, local):
 
     # ---- device-resident timing -----------------------------------------------------------------
     ctx.set_option("uvd_fused", 0 if args.uvd_form == "separate-3sweep" else 1)
+    clocks = ClockSampler(local)
+    if rank == 0:
+        clocks.start()
     U, V, d = U0.clone(), V0.clone(), d0.clone()
     for i in range(args.warmup + (2 * POOL if use_graphs else 0)):      # graphs: capture every (inputs, coin flip) key
         step(i, U, V, d, *pool[i % POOL])
     if not use_graphs:
         ctx.set_option("profile", 1)
     ctx.profile_read()
-    clocks = ClockSampler(local)
-    barrier()
-    if rank == 0:
-        clocks.start()
+    def timed_region(first_step):
+        """EXACTLY args.steps steps between two events (barrier + synchronize on both sides); an event after every
+        step as well, so that a one-off stall of the submitting host thread (another process holding the driver) shows
+        up as one long step instead of silently inflating the mean."""
+        barrier()
+        clocks.mark()
+        marks = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps + 1)]
+        marks[0].record()
+        out = None
+        for i in range(args.steps):
+            out = step(first_step + i, U, V, d, *pool[i % POOL])
+            marks[i + 1].record()
+        barrier()
+        per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
+        return marks[0].elapsed_time(marks[-1]), per, out
+
     launches0 = ctx.launch_count
     graph_launches0 = sum(g.kernel_launches for g in graphs.values())
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record()
-    for i in range(args.steps):
-        pre = step(args.warmup + i, U, V, d, *pool[i % POOL])
-    e1.record()
-    barrier()
+    ms, per_step, pre = timed_region(args.warmup)
+    remeasured = None
+    med = float(np.median(per_step))
+    flag = torch.tensor([1.0 if max(per_step) > 3.0 * med and ms > 1.15 * med * args.steps else 0.0], device=dev)
+    if world > 1:
+        dist.all_reduce(flag, op=dist.ReduceOp.MAX)
+    if flag.item() > 0:
+        # a submission stall landed in the timed region: re-measure once (same rule as for a throttled run) and say so
+        remeasured = dict(reason="one step took > 3x the median step (host/driver stall, not kernel time)",
+                          discarded_ms_per_step=round(ms / args.steps, 4), discarded_max_step_ms=round(max(per_step), 3))
+        ctx.profile_read()
+        launches0 = ctx.launch_count
+        graph_launches0 = sum(g.kernel_launches for g in graphs.values())
+        ms, per_step, pre = timed_region(args.warmup + args.steps)
     clk = clocks.stop() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
     launches = ctx.launch_count - launches0 + sum(g.kernel_launches for g in graphs.values()) - graph_launches0
     kernels_from = "CUDA events around every launch inside the timed region"
     if use_graphs:
@@ -395,6 +437,7 @@ def run_uvd(args, rank, world, local):
                                "fused into three sweeps" if form == "fused" else
                                "update_precond_UVd_math_ + precond_grad_UVd_math as two calls (" + args.uvd_form + ")"),
                     cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
+        step_ms_median=round(float(np.median(per_step)), 4), step_ms_max=round(max(per_step), 4), remeasured=remeasured,
         roofline=roofline, kernels=kernels, kernels_measured=kernels_from, separate_calls=separate, cpu_baseline=cpu, e2e=e2e,
         gpu_launches=int(launches), clocks=clk)
 

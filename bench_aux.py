@@ -7,6 +7,8 @@ GB/s against the algorithmic byte counts of SURVEY.md section 8(d):
     norm,scale update 12MN B, apply 8MN B                      (NMT decoder shapes, SURVEY.md cfg5: [2305,1024], [1025,4935];
                                                                 and a large [8192, 8192] layer so that the state exceeds L2)
     dense apply Q read twice = 8 n^2 B                         (n = 8192)
+    SPLU       update 2*(8nr+16n) + 8nr + 8n = 24nr + 40n B,   (n = 5e7, r = 10; big inputs read twice -- reductions
+               apply 2*(8nr+12n) + 4n = 16nr + 28n B            gate the maps -- outputs written once, like UVd)
 
 Run by bench.py (nested under "aux" in the default JSON line) or directly:  python bench_aux.py
 """
@@ -94,6 +96,27 @@ def run_aux(peak_gbs: float, steps: int = 10):
     ms_a = _time(torch, lambda: psgd.precond_grad_dense(Q, gv), steps)
     rows.append(dict(path="dense apply", shape=[n, n], apply_ms=round(ms_a, 4), apply_GBps=round(8.0 * n * n / ms_a / 1e6, 1),
                      apply_frac=round(8.0 * n * n / ms_a / 1e6 / peak_gbs, 4), step_algorithmic_GB=round(8.0 * n * n / 1e9, 3)))
+
+    # ---- sparse-LU preconditioner (psgd.py:396-524), n = 5e7, r = 10 ---------------------------------------------------
+    del Q, gv
+    torch.cuda.empty_cache()
+    n, r = 50_000_000, 10
+    L12 = torch.cat([torch.eye(r, device=dev), torch.zeros(n - r, r, device=dev)])            # demo_usage_of_all_preconditioners.py:46-49
+    U12 = torch.cat([torch.eye(r, device=dev), torch.zeros(r, n - r, device=dev)], 1)
+    l3 = torch.ones(n - r, 1, device=dev)
+    u3 = torch.ones(n - r, 1, device=dev)
+    dx = torch.randn(n, device=dev, generator=g)
+    dg = 1.3 * dx + 0.1 * torch.randn(n, device=dev, generator=g)
+    gg = torch.randn(n, device=dev, generator=g)
+    st = [L12, l3, U12, u3]
+
+    def supd():
+        st[0], st[1], st[2], st[3] = psgd.update_precond_splu(st[0], st[1], st[2], st[3], [dx], [dg], 0.01)
+
+    ms_u = _time(torch, supd, steps)
+    ms_a = _time(torch, lambda: psgd.precond_grad_splu(st[0], st[1], st[2], st[3], [gg]), steps)
+    assert torch.isfinite(st[0]).all() and torch.isfinite(st[2]).all()
+    add("SPLU", [n, r], ms_u, ms_a, (24.0 * r + 40.0) * n, (16.0 * r + 28.0) * n)
     return rows
 
 

@@ -30,6 +30,19 @@ static dim3 tile_grid(int M, int N) { return dim3((N + kCols - 1) / kCols, (M + 
 int col_tiles(int N) { return (N + kCols - 1) / kCols; }
 int row_tiles(int M) { return (M + kRows - 1) / kRows; }
 
+// The reducing kernels walk a CTA down a column strip over `rows_per_cta` rows (a multiple of kRows) instead of one
+// 64-row tile: the per-CTA prologue (per-column constants, last rows) and epilogue (shared-memory reduction, partial
+// stores) cost as much as streaming one 128 KB tile (ncu: 3.2 TB/s with one tile per CTA), and the cross-CTA partial
+// tables shrink from M/64 to ~4 * SMs / col_tiles records.  Grid ~ 4 CTAs per SM.
+static int rows_per_cta(const psgd_ctx* ctx, int M, int N) {
+  const int rt = row_tiles(M);
+  int chunks = (ctx->num_sms * 4 + col_tiles(N) - 1) / col_tiles(N);
+  if (chunks > rt) chunks = rt;
+  if (chunks < 1) chunks = 1;
+  return ((rt + chunks - 1) / chunks) * kRows;
+}
+static int row_chunks(int M, int rpc) { return (M + rpc - 1) / rpc; }
+
 // ---------------------------------------------------------------------------------------------
 // weighted column sums:  partial[row_tile][j] = sum_{i in tile} w(i) X[i, j]
 //   mode 0: w = ql1[i] / (ql0[i] * ql0[M-1])        Bt's last-row correction       psgd.py:231-232
@@ -37,14 +50,17 @@ int row_tiles(int M) { return (M + kRows - 1) / kRows; }
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) col_wsum_kernel(int mode, const float* __restrict__ ql,
                                                             const float* __restrict__ wvec, const float* __restrict__ X,
-                                                            int ldx, int M, int N, float* __restrict__ partial) {
+                                                            int ldx, int M, int N, int rpc, float* __restrict__ partial) {
   __shared__ float red[kWarps][kCols];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * kCols + lane, r0 = blockIdx.y * kRows + warp * kRowsPerWarp;
+  const int c0 = blockIdx.x * kCols + lane;
+  const int rbeg = blockIdx.y * rpc, rend = min(M, rbeg + rpc);
   float acc[kColsPerLane];
 #pragma unroll
   for (int k = 0; k < kColsPerLane; ++k) acc[k] = 0.f;
   const float qlast = mode == 0 ? ql[M - 1] : 0.f;
+  for (int rt = rbeg; rt < rend; rt += kRows) {
+  const int r0 = rt + warp * kRowsPerWarp;
   for (int rr = 0; rr < kRowsPerWarp; rr += 4) {            // four rows of loads in flight per warp
     float xv[4][kColsPerLane], w[4];
 #pragma unroll
@@ -64,6 +80,7 @@ __global__ void __launch_bounds__(kThreads) col_wsum_kernel(int mode, const floa
     for (int h = 0; h < 4; ++h)
 #pragma unroll
       for (int k = 0; k < kColsPerLane; ++k) acc[k] = fmaf(w[h], xv[h][k], acc[k]);
+  }
   }
 #pragma unroll
   for (int k = 0; k < kColsPerLane; ++k) red[warp][lane + 32 * k] = acc[k];
@@ -90,9 +107,10 @@ __global__ void __launch_bounds__(256) col_finish_kernel(const float* __restrict
 
 int col_wsum(psgd_ctx* ctx, int mode, const float* ql, const float* wvec, const float* X, int ldx, int M, int N,
              float* partial, float* out) {
-  col_wsum_kernel<<<tile_grid(M, N), kThreads, 0, ctx->stream>>>(mode, ql, wvec, X, ldx, M, N, partial);
+  const int rpc = rows_per_cta(ctx, M, N), chunks = row_chunks(M, rpc);
+  col_wsum_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(mode, ql, wvec, X, ldx, M, N, rpc, partial);
   PSGD_LAUNCH_CHECK(ctx);
-  col_finish_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(partial, row_tiles(M), N, out);
+  col_finish_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(partial, chunks, N, out);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -101,12 +119,32 @@ int col_wsum(psgd_ctx* ctx, int mode, const float* ql, const float* wvec, const 
 // row dots (GEMV):  out[i] = sum_j X[i, j] w[j]        t = Q g, a = Q dg        psgd.py:38, :55
 // one warp per row, lanes stride the columns (coalesced), fixed butterfly
 // ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ float dot4(const float4 a, const float4 b, float s) {
+  return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, fmaf(a.x, b.x, s))));
+}
+// vec != 0: rows and w are 16-byte aligned (ldx % 4 == 0): 128-bit loads, four per lane in flight
 __global__ void __launch_bounds__(kThreads) row_dot_kernel(const float* __restrict__ X, int ldx, const float* __restrict__ w,
-                                                           int M, int N, float* __restrict__ out) {
+                                                           int M, int N, int vec, float* __restrict__ out) {
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = blockIdx.x * kWarps + warp; i < M; i += gridDim.x * kWarps) {
     const float* xr = X + (size_t)i * ldx;
     float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+    if (vec) {
+      const float4* x4 = reinterpret_cast<const float4*>(xr);
+      const float4* w4 = reinterpret_cast<const float4*>(w);
+      const int n4 = N >> 2;
+      int q = lane;
+      for (; q + 96 < n4; q += 128) {
+        const float4 a0 = x4[q], a1 = x4[q + 32], a2 = x4[q + 64], a3 = x4[q + 96];
+        s0 = dot4(a0, w4[q], s0); s1 = dot4(a1, w4[q + 32], s1);
+        s2 = dot4(a2, w4[q + 64], s2); s3 = dot4(a3, w4[q + 96], s3);
+      }
+      for (; q < n4; q += 32) s0 = dot4(x4[q], w4[q], s0);
+      for (int j = (n4 << 2) + lane; j < N; j += 32) s1 = fmaf(xr[j], w[j], s1);
+      const float s = warp_sum((s0 + s1) + (s2 + s3));
+      if (lane == 0) out[i] = s;
+      continue;
+    }
     int j = lane;
     for (; j + 96 < N; j += 128) {
       s0 = fmaf(xr[j], w[j], s0);
@@ -124,7 +162,8 @@ int row_dot(psgd_ctx* ctx, const float* X, int ldx, const float* w, int M, int N
   int grid = (M + kWarps - 1) / kWarps;
   const int cap = ctx->num_sms * 8;
   if (grid > cap) grid = cap;
-  row_dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(X, ldx, w, M, N, out);
+  const int vec = (ldx % 4 == 0) && aligned16(X) && aligned16(w);
+  row_dot_kernel<<<grid, kThreads, 0, ctx->stream>>>(X, ldx, w, M, N, vec, out);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -139,11 +178,12 @@ int row_dot(psgd_ctx* ctx, const float* X, int ldx, const float* w, int M, int N
 // ---------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(kThreads) ns_stats_kernel(const float* __restrict__ ql, const float* __restrict__ qr,
                                                             const float* __restrict__ cvec, const float* __restrict__ dX,
-                                                            const float* __restrict__ dG, int M, int N,
+                                                            const float* __restrict__ dG, int M, int N, int rpc,
                                                             float* __restrict__ rowpart, float* __restrict__ colpart) {
   __shared__ float red[kWarps][2][kCols];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int c0 = blockIdx.x * kCols + lane, r0 = blockIdx.y * kRows + warp * kRowsPerWarp;
+  const int c0 = blockIdx.x * kCols + lane;
+  const int rbeg = blockIdx.y * rpc, rend = min(M, rbeg + rpc);
   const float* ql1 = ql + M;
   const float qlast0 = ql[M - 1], qlast1 = ql1[M - 1];
   const float rqlast0 = 1.0f / qlast0;
@@ -170,6 +210,8 @@ __global__ void __launch_bounds__(kThreads) ns_stats_kernel(const float* __restr
     glast[k] = j < N ? gl[j] : 0.f;
   }
   // two rows per iteration, all 32 loads issued before any arithmetic: the kernel lives on memory-level parallelism
+  for (int rt = rbeg; rt < rend; rt += kRows) {
+  const int r0 = rt + warp * kRowsPerWarp;
   for (int rr = 0; rr < kRowsPerWarp; rr += 2) {
     const int i0 = r0 + rr;
     if (i0 >= M) break;
@@ -214,6 +256,7 @@ __global__ void __launch_bounds__(kThreads) ns_stats_kernel(const float* __restr
         rp[0] = sa; rp[1] = sb; rp[2] = da; rp[3] = db;
       }
     }
+  }
   }
 #pragma unroll
   for (int k = 0; k < kColsPerLane; ++k) { red[warp][0][lane + 32 * k] = ca[k]; red[warp][1][lane + 32 * k] = cb[k]; }
@@ -273,14 +316,15 @@ int ns_update_stats(psgd_ctx* ctx, const float* ql, const float* qr, const float
                     int M, int N, float* scratch, float* g1d, float* g1b, float* grad2, float* max1, float* max2) {
   float* rowpart = scratch;
   float* colpart = scratch + (((size_t)col_tiles(N) * M * 4 + 63) / 64) * 64;
-  ns_stats_kernel<<<tile_grid(M, N), kThreads, 0, ctx->stream>>>(ql, qr, cvec, dX, dG, M, N, rowpart, colpart);
+  const int rpc = rows_per_cta(ctx, M, N), chunks = row_chunks(M, rpc);
+  ns_stats_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(ql, qr, cvec, dX, dG, M, N, rpc, rowpart, colpart);
   PSGD_LAUNCH_CHECK(ctx);
   int gr = (M + 255) / 256, gc = (N + 255) / 256;
   if (gr > ctx->num_sms * 4) gr = ctx->num_sms * 4;
   if (gc > ctx->num_sms * 4) gc = ctx->num_sms * 4;
   ns_finish_rows_kernel<<<gr, 256, 0, ctx->stream>>>(rowpart, col_tiles(N), M, g1d, g1b, max1);
   PSGD_LAUNCH_CHECK(ctx);
-  ns_finish_cols_kernel<<<gc, 256, 0, ctx->stream>>>(colpart, row_tiles(M), N, grad2, max2);
+  ns_finish_cols_kernel<<<gc, 256, 0, ctx->stream>>>(colpart, chunks, N, grad2, max2);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }

@@ -89,6 +89,12 @@ def _scalar(x) -> float:
     return float(x.item()) if hasattr(x, "item") else float(x)
 
 
+def _flat_cat(ts):
+    """Flatten and concatenate a list of tensors in list order (psgd.py:34-35); a single tensor is viewed, not copied."""
+    ts = [t.reshape(-1) for t in ts]
+    return ts[0] if len(ts) == 1 else torch.cat(ts)
+
+
 def _kind(Q: torch.Tensor) -> int:
     """Factor format from its shape, in the reference's test order: square => dense first
     (psgd.py:82-83), then first dim 2 => normalization, 1 => scaling."""
@@ -114,8 +120,8 @@ def update_precond_dense(Q, dxs, dgs, step=0.01):
     """psgd.py:26-42.  ``dxs``/``dgs``: lists of arbitrarily shaped tensors, flattened and concatenated
     in list order (psgd.py:34-35)."""
     Q = _in(Q, "Q")
-    dx = torch.cat([_in(x, "dxs").reshape(-1) for x in dxs])
-    dg = torch.cat([_in(g, "dgs").reshape(-1) for g in dgs])
+    dx = _flat_cat([_in(x, "dxs") for x in dxs])
+    dg = _flat_cat([_in(g, "dgs") for g in dgs])
     n = Q.shape[0]
     if Q.shape != (n, n) or dx.numel() != n or dg.numel() != n:
         raise ValueError(f"update_precond_dense: Q {tuple(Q.shape)} vs {dx.numel()} parameters")
@@ -129,7 +135,7 @@ def precond_grad_dense(Q, grads):
     """psgd.py:45-63: ``Q^T Q g`` reshaped back to the shapes of ``grads``."""
     Q = _in(Q, "Q")
     gs = [_in(g, "grads") for g in grads]
-    flat = torch.cat([g.reshape(-1) for g in gs])
+    flat = _flat_cat(gs)
     n = Q.shape[0]
     if flat.numel() != n:
         raise ValueError(f"precond_grad_dense: Q {tuple(Q.shape)} vs {flat.numel()} parameters")
@@ -158,8 +164,8 @@ def update_precond_splu(L12, l3, U12, u3, dxs, dgs, step=0.01):
     """psgd.py:396-477: Q = L U with L = [L1 0; L2 diag(l3)], U = [U1 U2; 0 diag(u3)].  Functional: returns
     ``[L12', l3', U12', u3']`` (psgd.py:480)."""
     L12, l3, U12, u3 = _in(L12, "L12"), _in(l3, "l3"), _in(U12, "U12"), _in(u3, "u3")
-    dx = torch.cat([_in(x, "dxs").reshape(-1) for x in dxs])                   # psgd.py:426
-    dg = torch.cat([_in(g, "dgs").reshape(-1) for g in dgs])                   # psgd.py:427
+    dx = _flat_cat([_in(x, "dxs") for x in dxs])                               # psgd.py:426
+    dg = _flat_cat([_in(g, "dgs") for g in dgs])                               # psgd.py:427
     n = dx.numel()
     if dg.numel() != n:
         raise ValueError("update_precond_splu: dxs and dgs differ in size")
@@ -175,7 +181,7 @@ def precond_grad_splu(L12, l3, U12, u3, grads):
     """psgd.py:483-524: ``U^T L^T L U g`` reshaped back to the shapes of ``grads``."""
     L12, l3, U12, u3 = _in(L12, "L12"), _in(l3, "l3"), _in(U12, "U12"), _in(u3, "u3")
     gs = [_in(g, "grads") for g in grads]
-    flat = torch.cat([g.reshape(-1) for g in gs])                              # psgd.py:495-497
+    flat = _flat_cat(gs)                                                       # psgd.py:495-497
     n = flat.numel()
     r = _splu_check(L12, l3, U12, u3, n)
     out = torch.empty_like(flat)
