@@ -95,11 +95,13 @@ def load_library():
     with _lib_lock:
         if _lib is not None:
             return _lib
-        if not os.path.exists(LIB_PATH):
+        # PSGD_B200_LIB: another build of the same library (kernel-tuning A/B runs, tools/uvd_variants.py)
+        path = os.environ.get("PSGD_B200_LIB") or LIB_PATH
+        if not os.path.exists(path):
             raise ImportError(
-                f"{LIB_PATH} is missing: build it with `python -m psgd_tf_b200.build` "
+                f"{path} is missing: build it with `python -m psgd_tf_b200.build` "
                 "(psgd_tf_b200 has no CPU or pure-Python fallback)")
-        lib = C.CDLL(LIB_PATH)
+        lib = C.CDLL(path)
         for name, (restype, argtypes) in SIGNATURES.items():
             fn = getattr(lib, name)   # AttributeError if the .so does not export a declared symbol
             fn.restype = restype

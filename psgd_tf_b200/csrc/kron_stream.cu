@@ -33,10 +33,12 @@ int row_tiles(int M) { return (M + kRows - 1) / kRows; }
 // The reducing kernels walk a CTA down a column strip over `rows_per_cta` rows (a multiple of kRows) instead of one
 // 64-row tile: the per-CTA prologue (per-column constants, last rows) and epilogue (shared-memory reduction, partial
 // stores) cost as much as streaming one 128 KB tile (ncu: 3.2 TB/s with one tile per CTA), and the cross-CTA partial
-// tables shrink from M/64 to ~4 * SMs / col_tiles records.  Grid ~ 4 CTAs per SM.
-static int rows_per_cta(const psgd_ctx* ctx, int M, int N) {
+// tables shrink from M/64 records to a few.  The strips are sized so that the whole grid is ONE resident wave
+// (`ctas_per_sm` = what the kernel's registers allow): with long-running CTAs a second, partly filled wave costs as much
+// as a full one (ncu: 608 CTAs on 592 slots ran no faster than one tile per CTA).
+static int rows_per_cta(const psgd_ctx* ctx, int M, int N, int ctas_per_sm) {
   const int rt = row_tiles(M);
-  int chunks = (ctx->num_sms * 4 + col_tiles(N) - 1) / col_tiles(N);
+  int chunks = (ctx->num_sms * ctas_per_sm) / col_tiles(N);
   if (chunks > rt) chunks = rt;
   if (chunks < 1) chunks = 1;
   return ((rt + chunks - 1) / chunks) * kRows;
@@ -107,7 +109,7 @@ __global__ void __launch_bounds__(256) col_finish_kernel(const float* __restrict
 
 int col_wsum(psgd_ctx* ctx, int mode, const float* ql, const float* wvec, const float* X, int ldx, int M, int N,
              float* partial, float* out) {
-  const int rpc = rows_per_cta(ctx, M, N), chunks = row_chunks(M, rpc);
+  const int rpc = rows_per_cta(ctx, M, N, 4), chunks = row_chunks(M, rpc);       // 64 registers: 4 CTAs per SM
   col_wsum_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(mode, ql, wvec, X, ldx, M, N, rpc, partial);
   PSGD_LAUNCH_CHECK(ctx);
   col_finish_kernel<<<(N + 255) / 256, 256, 0, ctx->stream>>>(partial, chunks, N, out);
@@ -316,7 +318,7 @@ int ns_update_stats(psgd_ctx* ctx, const float* ql, const float* qr, const float
                     int M, int N, float* scratch, float* g1d, float* g1b, float* grad2, float* max1, float* max2) {
   float* rowpart = scratch;
   float* colpart = scratch + (((size_t)col_tiles(N) * M * 4 + 63) / 64) * 64;
-  const int rpc = rows_per_cta(ctx, M, N), chunks = row_chunks(M, rpc);
+  const int rpc = rows_per_cta(ctx, M, N, 2), chunks = row_chunks(M, rpc);       // 128 registers: 2 CTAs per SM
   ns_stats_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(ql, qr, cvec, dX, dG, M, N, rpc, rowpart, colpart);
   PSGD_LAUNCH_CHECK(ctx);
   int gr = (M + 255) / 256, gc = (N + 255) / 256;

@@ -135,6 +135,18 @@ __global__ void __launch_bounds__(32) small0_kernel(Args a, const float* __restr
   if (lane == 0) { st->rho = rho; st->maxL = 0.f; st->maxU = 0.f; }
 }
 
+// L2 is [m, r] row-major: a thread that walks its own row touches r scattered 4-byte words (one 128-byte line per ~3
+// rows), so every load instruction of a warp spans ~10 lines.  Instead a block stages the 256 consecutive rows of its
+// tile -- one contiguous run of 256 r floats -- into shared memory with fully coalesced loads (balanced by 1/rho on the
+// way in when updating), and threads then read (and in pass 4 rewrite) their rows there.
+template <int RM>
+__device__ __forceinline__ void stage_rows(float* tile, const float* __restrict__ src, long long j0, int rows, int r,
+                                           bool balance, float rho) {
+  const float* p = src + (size_t)j0 * r;
+  const int cnt = rows * r;
+  for (int e = threadIdx.x; e < cnt; e += kThreads) tile[e] = balance ? p[e] / rho : p[e];
+}
+
 // ---- pass 1 / A1:  partial[b][k] = sum_j (rho U2[k, j]) w[j],  w = dg2 (update) or g2 (apply) ------------------------
 template <int RM>
 __global__ void __launch_bounds__(kThreads) pass1_kernel(Args a) {
@@ -189,13 +201,14 @@ __global__ void __launch_bounds__(32) small1_kernel(Args a, int nblocks, int upd
 // ---- pass 2: per j  Qg2, iQtx2 (stored);  partial sums L2^T iQtx2 (off 0) and L2^T Qg2 (off kMaxR)   psgd.py:431-442 ----
 // apply (update = 0): Qg2 = L2 Ug1 + l3 u3 g2 (stored), partial L2^T Qg2                       psgd.py:507-512
 template <int RM>
-__global__ void __launch_bounds__(kThreads) pass2_kernel(Args a, int update) {
+__global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args a, int update) {
   const long long m = a.n - a.r;
   const int r = a.r;
   const State* st = a.st;
   const float rho = st->rho;
   const float* L2 = a.L12 + (size_t)r * r;
   const float* U2 = a.U12 + r;
+  __shared__ float tile[kThreads * RM];
   float ug1[RM], iu1[RM], pa[RM], pb[RM];
 #pragma unroll
   for (int k = 0; k < RM; ++k) {
@@ -203,7 +216,13 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(Args a, int update) {
     iu1[k] = (update && k < r) ? st->iUtx1[k] : 0.f;
     pa[k] = 0.f; pb[k] = 0.f;
   }
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
+    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
+    __syncthreads();
+    stage_rows<RM>(tile, L2, j0, rows, r, update != 0, rho);
+    __syncthreads();
+    if ((int)threadIdx.x >= rows) continue;
+    const long long j = j0 + threadIdx.x;
     const float l3 = update ? a.l3[j] / rho : a.l3[j];
     const float u3 = update ? rho * a.u3[j] : a.u3[j];
     float lrow[RM];
@@ -211,7 +230,7 @@ __global__ void __launch_bounds__(kThreads) pass2_kernel(Args a, int update) {
 #pragma unroll
     for (int k = 0; k < RM; ++k) {
       if (k < r) {
-        lrow[k] = update ? L2[(size_t)j * r + k] / rho : L2[(size_t)j * r + k];
+        lrow[k] = tile[threadIdx.x * r + k];
         dotL = fmaf(lrow[k], ug1[k], dotL);
         if (update) dotU = fmaf(rho * U2[(size_t)k * a.n + j], iu1[k], dotU);
       }
@@ -277,7 +296,7 @@ __global__ void __launch_bounds__(32) small2_kernel(Args a, int nblocks, int upd
 // ---- pass 3: Pg2, iPx2 per j (stored); partial U2 iPx2; max |grad2|, |grad3| of both factors   psgd.py:443-474 ----------
 // apply (update = 0): out[r + j] = U2[:, j] . LtQg1 + u3 l3 Qg2                                   psgd.py:513-516
 template <int RM>
-__global__ void __launch_bounds__(kThreads) pass3_kernel(Args a, int update, float* __restrict__ out) {
+__global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args a, int update, float* __restrict__ out) {
   __shared__ float redm[kWarps][2];
   const long long m = a.n - a.r;
   const int r = a.r;
@@ -297,8 +316,17 @@ __global__ void __launch_bounds__(kThreads) pass3_kernel(Args a, int update, flo
     dx1[k] = (ok && update) ? st->dx1[k] : 0.f;
     pc[k] = 0.f;
   }
+  __shared__ float tile[kThreads * RM];
   float mxL = 0.f, mxU = 0.f;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
+  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
+    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
+    if (update) {                       // the apply's third pass does not read L2
+      __syncthreads();
+      stage_rows<RM>(tile, L2, j0, rows, r, true, rho);
+      __syncthreads();
+    }
+    if ((int)threadIdx.x >= rows) continue;
+    const long long j = j0 + threadIdx.x;
     const float l3 = update ? a.l3[j] / rho : a.l3[j];
     const float u3 = update ? rho * a.u3[j] : a.u3[j];
     const float Qg2 = a.v0[j];
@@ -309,7 +337,7 @@ __global__ void __launch_bounds__(kThreads) pass3_kernel(Args a, int update, flo
       if (k < r) {
         urow[k] = update ? rho * U2[(size_t)k * a.n + j] : U2[(size_t)k * a.n + j];
         dotU = fmaf(urow[k], lt1[k], dotU);
-        if (update) dotL = fmaf(L2[(size_t)j * r + k] / rho, il1[k], dotL);
+        if (update) dotL = fmaf(tile[threadIdx.x * r + k], il1[k], dotL);
       }
     }
     const float LtQg2 = l3 * Qg2;                                           // :443 / :513
@@ -411,7 +439,7 @@ __global__ void __launch_bounds__(32) small3_kernel(Args a, int nblocks) {
 
 // ---- pass 4: new L2, l3, U2, u3                                                               psgd.py:464-478 ------------
 template <int RM>
-__global__ void __launch_bounds__(kThreads) pass4_kernel(Args a) {
+__global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args a) {
   const long long m = a.n - a.r;
   const int r = a.r;
   const State* st = a.st;
@@ -427,23 +455,37 @@ __global__ void __launch_bounds__(kThreads) pass4_kernel(Args a) {
     cL1[k] = ok ? st->cL1[k] : 0.f; cL2[k] = ok ? st->cL2[k] : 0.f;
     cU1[k] = ok ? st->cU1[k] : 0.f; cU2[k] = ok ? st->cU2[k] : 0.f;
   }
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
-    const float l3 = a.l3[j] / rho, u3 = rho * a.u3[j];
-    const float Qg2 = a.v0[j], iQtx2 = a.v1[j], Pg2 = a.v2[j], iPx2 = a.v3[j];
-    const float dgj = a.dg[r + j], dxj = a.dx[r + j];
-    const float g3L = Qg2 * Qg2 - iQtx2 * iQtx2;                           // :458
-    const float g3U = Pg2 * dgj - dxj * iPx2;                              // :471
+  __shared__ float tile[kThreads * RM];
+  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
+    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
+    __syncthreads();
+    stage_rows<RM>(tile, L2, j0, rows, r, true, rho);
+    __syncthreads();
+    if ((int)threadIdx.x < rows) {
+      const long long j = j0 + threadIdx.x;
+      const float l3 = a.l3[j] / rho, u3 = rho * a.u3[j];
+      const float Qg2 = a.v0[j], iQtx2 = a.v1[j], Pg2 = a.v2[j], iPx2 = a.v3[j];
+      const float dgj = a.dg[r + j], dxj = a.dx[r + j];
+      const float g3L = Qg2 * Qg2 - iQtx2 * iQtx2;                           // :458
+      const float g3U = Pg2 * dgj - dxj * iPx2;                              // :471
 #pragma unroll
-    for (int k = 0; k < RM; ++k) {
-      if (k < r) {
-        const float l = L2[(size_t)j * r + k] / rho;
-        L2o[(size_t)j * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;          // :464
-        const float u = rho * U2[(size_t)k * a.n + j];
-        U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
+      for (int k = 0; k < RM; ++k) {
+        if (k < r) {
+          const float l = tile[threadIdx.x * r + k];
+          tile[threadIdx.x * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;       // :464
+          const float u = rho * U2[(size_t)k * a.n + j];
+          U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
+        }
       }
+      a.l3_out[j] = l3 - stepL * g3L * l3;                                   // :465
+      a.u3_out[j] = u3 - stepU * g3U * u3;                                   // :478
     }
-    a.l3_out[j] = l3 - stepL * g3L * l3;                                   // :465
-    a.u3_out[j] = u3 - stepU * g3U * u3;                                   // :478
+    __syncthreads();
+    {                                   // the updated rows leave as one contiguous, coalesced run
+      float* po = L2o + (size_t)j0 * r;
+      const int cnt = rows * r;
+      for (int e = threadIdx.x; e < cnt; e += kThreads) po[e] = tile[e];
+    }
   }
 }
 
@@ -457,6 +499,8 @@ static int grid_for(const psgd_ctx* ctx, long long m) {
 #define SPLU_DISPATCH(r, KERN, ...)                                   \
   do {                                                                \
     if ((r) <= 8) KERN<8><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);        \
+    else if ((r) <= 10) KERN<10><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
+    else if ((r) <= 12) KERN<12><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
     else if ((r) <= 16) KERN<16><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
     else KERN<32><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);                \
   } while (0)

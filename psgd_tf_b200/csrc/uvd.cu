@@ -66,7 +66,20 @@ __host__ __device__ constexpr int gp_total(int R, int MODE) {
   for (int i = 0; i < gp_nrows(R, MODE); ++i) c += gp_row_count(R, MODE, i);
   return c;
 }
-constexpr int kAccPerRole = 104;
+// Tuning knobs of the Gram sweep (tools/uvd_variants.py builds A/B libraries with other values):
+//   PSGD_GRAM_ACC   accumulator floats per warp role (fewer -> more roles, more warps, each re-reading the row)
+//   PSGD_GRAM_WPR4  warps per role when the plan has 4 roles
+//   PSGD_GRAM_RCP   1: w = v * rcp(d) (2 roundings) instead of the IEEE division in the Gram sweep's x columns
+#ifndef PSGD_GRAM_ACC
+#define PSGD_GRAM_ACC 104
+#endif
+#ifndef PSGD_GRAM_WPR4
+#define PSGD_GRAM_WPR4 2
+#endif
+#ifndef PSGD_GRAM_RCP
+#define PSGD_GRAM_RCP 0
+#endif
+constexpr int kAccPerRole = PSGD_GRAM_ACC;
 __host__ __device__ constexpr int gp_nroles(int R, int MODE) { return (gp_total(R, MODE) + kAccPerRole - 1) / kAccPerRole; }
 // first table row of role `role` (role >= nroles gives the row count)
 __host__ __device__ constexpr int gp_begin(int R, int MODE, int role) {
@@ -92,7 +105,8 @@ struct GramPlan {
   static constexpr int TABLE = NR * E;            // floats per table ([NR][E], only the needed entries are meaningful)
   static constexpr int NROLES = gp_nroles(R, MODE);
   // warps per role: keep the CTA at <= 12 warps so ptxas may use > 128 registers per thread
-  static constexpr int WPR = NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES <= 5 ? 2 : 1)));
+  static constexpr int WPR =
+      NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES == 4 ? PSGD_GRAM_WPR4 : (NROLES <= 5 ? 2 : 1))));
   static constexpr int ROWS_PER_LANE = (WPR >= 4) ? 1 : (WPR >= 2 ? 2 : 4);
   static constexpr int TILE = WPR * 32 * ROWS_PER_LANE;          // rows per pipeline stage
   static constexpr int CONSUMER_WARPS = NROLES * WPR;
@@ -222,7 +236,11 @@ __device__ __forceinline__ RowX<R, MODE> make_x(float v0, float v1, float v2) {
   RowX<R, MODE> o;
   if constexpr (MODE == kUpdate) {
     o.x[0] = v0 * v1;   // d*h           psgd.py:569
+#if PSGD_GRAM_RCP
+    o.x[1] = v2 * __frcp_rn(v0);
+#else
     o.x[1] = v2 / v0;   // v/d           psgd.py:576
+#endif
   } else if constexpr (MODE == kApply) {
     o.x[0] = v0 * v1;   // d*g           psgd.py:625
   } else {
