@@ -143,8 +143,19 @@ template <int RM>
 __device__ __forceinline__ void stage_rows(float* tile, const float* __restrict__ src, long long j0, int rows, int r,
                                            bool balance, float rho) {
   const float* p = src + (size_t)j0 * r;
-  const int cnt = rows * r;
-  for (int e = threadIdx.x; e < cnt; e += kThreads) tile[e] = balance ? p[e] / rho : p[e];
+  const int cnt = rows * r;                       // <= kThreads * RM: at most RM elements per thread
+  float vals[RM];
+  // all loads first (ncu: with the division inside a rolled loop every element waited out its own DRAM latency)
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int e = threadIdx.x + i * kThreads;
+    vals[i] = e < cnt ? p[e] : 1.f;
+  }
+#pragma unroll
+  for (int i = 0; i < RM; ++i) {
+    const int e = threadIdx.x + i * kThreads;
+    if (e < cnt) tile[e] = balance ? vals[i] / rho : vals[i];
+  }
 }
 
 // ---- pass 1 / A1:  partial[b][k] = sum_j (rho U2[k, j]) w[j],  w = dg2 (update) or g2 (apply) ------------------------
@@ -484,7 +495,11 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
     {                                   // the updated rows leave as one contiguous, coalesced run
       float* po = L2o + (size_t)j0 * r;
       const int cnt = rows * r;
-      for (int e = threadIdx.x; e < cnt; e += kThreads) po[e] = tile[e];
+#pragma unroll
+      for (int i = 0; i < RM; ++i) {
+        const int e = threadIdx.x + i * kThreads;
+        if (e < cnt) po[e] = tile[e];
+      }
     }
   }
 }

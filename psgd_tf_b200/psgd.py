@@ -16,6 +16,7 @@ CPU fallback: CPU tensors raise.
 from __future__ import annotations
 
 import ctypes as C
+import math
 import random as _random
 import threading
 
@@ -634,17 +635,23 @@ class UVd:
         finite-difference mode, psgd.py:717-718), so ``v`` is removed again by the update (psgd.py:760-762)."""
         flat = lambda x: self._flatten(x if isinstance(x, (list, tuple)) else [x])
         n, r = self._U.shape
+        g = flat(grads)
+        _col(g, n, "grads")
         v = None
         if vs is not None:
             v, h = flat(vs), flat(Hvs)
-            if params_perturbed:      # compensate the levels of v and h (psgd.py:734-736)
-                update_precond_UVd_math_(self._U, self._V, self._d, v / self._delta_param_scale, h / self._delta_param_scale,
-                                         float(self.lr_preconditioner), self._tiny, balance=balance, update_U=update_U)
-            else:
-                update_precond_UVd_math_(self._U, self._V, self._d, v, h, float(self.lr_preconditioner), self._tiny,
-                                         balance=balance, update_U=update_U)
-        g = flat(grads)
-        _col(g, n, "grads")
+            # compensate the levels of v and h in the finite-difference mode (psgd.py:734-736)
+            vu, hu = (v / self._delta_param_scale, h / self._delta_param_scale) if params_perturbed else (v, h)
+            if math.isinf(float(self.grad_clip_max_norm)):
+                # update + preconditioned gradient as ONE fused call (three sweeps over U, V), then the parameter update
+                # as a streaming pass; with clipping the norm-reducing tail below is used instead
+                pre = update_precond_and_grad_UVd(self._U, self._V, self._d, vu, hu, g, float(self.lr_preconditioner),
+                                                  self._tiny, balance=balance, update_U=update_U)
+                apply_preconditioned_updates([self._flat_params], [pre], float(self.lr_params), None,
+                                             [v] if params_perturbed else None)                       # psgd.py:757-762
+                return pre if return_pre_grad else None
+            update_precond_UVd_math_(self._U, self._V, self._d, vu, hu, float(self.lr_preconditioner), self._tiny,
+                                     balance=balance, update_U=update_U)
         pre = torch.empty_like(g) if return_pre_grad else None
         ctx = get_context(self._U.device.index)
         vp = _p(v) if (params_perturbed and v is not None) else None

@@ -83,6 +83,37 @@ def test_class_step_with_equals_functional_api(psgd):
     assert torch.equal(W1.detach().reshape(-1), opt._flat_params[:510])
 
 
+@pytest.mark.parametrize("perturbed", [False, True])
+def test_class_step_with_without_clipping_uses_fused_call(psgd, perturbed):
+    """No clipping: step_with = the fused update+apply call + one streaming parameter pass; same results as the
+    reference sequence update_precond_UVd_math_ -> precond_grad_UVd_math -> assign_sub (psgd.py:732-762)."""
+    torch.manual_seed(3)
+    W = torch.randn(4099, device="cuda", requires_grad=True)
+    opt = psgd.UVd(W, rank_of_modification=10, lr_params=0.05, lr_preconditioner=0.02)
+    assert math.isinf(float(opt.grad_clip_max_norm))
+    n = 4099
+    U, V, d = opt._U.clone(), opt._V.clone(), opt._d.clone()
+    g = torch.randn(n, device="cuda")
+    scale = opt._delta_param_scale if perturbed else 1.0
+    v = torch.randn(n, device="cuda") * scale
+    h = 1.5 * v + 0.1 * scale * torch.randn(n, device="cuda")
+    if perturbed:
+        with torch.no_grad():
+            opt._flat_params.add_(v)                               # psgd.py:717-718
+    p0 = opt._flat_params.clone()
+    ctx = psgd.get_context()
+    before = ctx.launch_count
+    pre = opt.step_with([g], [v], [h], params_perturbed=perturbed, balance=False, update_U=False, return_pre_grad=True)
+    assert ctx.launch_count - before == 8                         # 7 of the fused call + the parameter pass
+    col = lambda t: t[:, None].contiguous()
+    psgd.update_precond_UVd_math_(U, V, d, col(v / scale), col(h / scale), 0.02, psgd._tiny, balance=False, update_U=False)
+    want = psgd.precond_grad_UVd_math(U, V, d, col(g)).reshape(-1)
+    assert torch.equal(opt._V, V) and torch.equal(opt._d, d) and torch.equal(opt._U, U)
+    assert cases.rel_err(pre.cpu().numpy(), want.cpu().numpy()) <= 1e-6
+    want_p = p0 - (0.05 * want + (v if perturbed else 0.0))
+    assert cases.rel_err(opt._flat_params.cpu().numpy(), want_p.cpu().numpy()) <= 1e-6
+
+
 @pytest.mark.parametrize("exact", [True, False])
 def test_class_step_converges_on_small_regression(psgd, exact):
     """step(closure) with exact and finite-difference Hessian-vector products (psgd.py:706-727) drives a tiny
