@@ -130,6 +130,9 @@ int psgd_uvd_update_apply(psgd_ctx* ctx, float* U, float* V, float* d, const flo
 int psgd_uvd_step_tail(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* param,
                        const float* v, float* pre_out, int64_t n, int r, float lr_params, float grad_clip_max_norm,
                        float tiny);
+/* Pipeline geometry the library compiled for the update Gram sweep at rank r (rows per shared-memory stage, stages,
+ * threads per CTA, warp roles) -- diagnostics and documentation only. */
+int psgd_uvd_plan_info(int r, int* tile_rows, int* stages, int* threads, int* roles);
 /* Replaces IpUVtmatvec (psgd.py:540-544): out = x + U (V^T x), x:[n,k] row-major. */
 int psgd_ipuvt_matvec(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out,
                       int64_t n, int r, int k);

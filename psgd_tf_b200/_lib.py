@@ -58,6 +58,7 @@ SIGNATURES = {
     "psgd_comm_status": (C.c_int, [C.c_void_p, C.POINTER(C.c_int64)]),
     "psgd_uvd_update": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]),
     "psgd_uvd_update_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 7 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_int, C.c_int]),
+    "psgd_uvd_plan_info": (C.c_int, [C.c_int] + [C.POINTER(C.c_int)] * 4),
     "psgd_uvd_apply": (C.c_int, [C.c_void_p] + [c_float_p] * 5 + [C.c_int64, C.c_int]),
     "psgd_uvd_step_tail": (C.c_int, [C.c_void_p] + [c_float_p] * 7 + [C.c_int64, C.c_int, C.c_float, C.c_float, C.c_float]),
     "psgd_ipuvt_matvec": (C.c_int, [C.c_void_p] + [c_float_p] * 4 + [C.c_int64, C.c_int, C.c_int]),

@@ -234,8 +234,15 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
     __syncthreads();
     if ((int)threadIdx.x >= rows) continue;
     const long long j = j0 + threadIdx.x;
-    const float l3 = update ? a.l3[j] / rho : a.l3[j];
-    const float u3 = update ? rho * a.u3[j] : a.u3[j];
+    // every global load of this row is issued before any arithmetic consumes one (ncu: interleaved, each use waited
+    // out its own DRAM latency)
+    float ucol[RM];
+#pragma unroll
+    for (int k = 0; k < RM; ++k) ucol[k] = (update && k < r) ? U2[(size_t)k * a.n + j] : 0.f;
+    const float l3raw = a.l3[j], u3raw = a.u3[j], dgj = a.dg[r + j];
+    const float dxj = update ? a.dx[r + j] : 0.f;
+    const float l3 = update ? l3raw / rho : l3raw;
+    const float u3 = update ? rho * u3raw : u3raw;
     float lrow[RM];
     float dotL = 0.f, dotU = 0.f;
 #pragma unroll
@@ -243,15 +250,15 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
       if (k < r) {
         lrow[k] = tile[threadIdx.x * r + k];
         dotL = fmaf(lrow[k], ug1[k], dotL);
-        if (update) dotU = fmaf(rho * U2[(size_t)k * a.n + j], iu1[k], dotU);
+        if (update) dotU = fmaf(rho * ucol[k], iu1[k], dotU);
       }
     }
-    const float Ug2 = u3 * a.dg[r + j];                                   // :431 / :507
+    const float Ug2 = u3 * dgj;                                            // :431 / :507
     const float Qg2 = dotL + l3 * Ug2;                                     // :434 / :510
     a.v0[j] = Qg2;
     float iQtx2 = 0.f;
     if (update) {
-      const float iUtx2 = (a.dx[r + j] - dotU) / u3;                       // :437
+      const float iUtx2 = (dxj - dotU) / u3;                               // :437
       iQtx2 = iUtx2 / l3;                                                  // :439
       a.v1[j] = iQtx2;
     }
@@ -338,15 +345,21 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
     }
     if ((int)threadIdx.x >= rows) continue;
     const long long j = j0 + threadIdx.x;
-    const float l3 = update ? a.l3[j] / rho : a.l3[j];
-    const float u3 = update ? rho * a.u3[j] : a.u3[j];
-    const float Qg2 = a.v0[j];
+    // all global loads of the row first (see pass 2)
+    float ucol[RM];
+#pragma unroll
+    for (int k = 0; k < RM; ++k) ucol[k] = k < r ? U2[(size_t)k * a.n + j] : 0.f;
+    const float l3raw = a.l3[j], u3raw = a.u3[j], Qg2 = a.v0[j];
+    const float iQtx2 = update ? a.v1[j] : 0.f;
+    const float dgj = update ? a.dg[r + j] : 0.f, dxj = update ? a.dx[r + j] : 0.f;
+    const float l3 = update ? l3raw / rho : l3raw;
+    const float u3 = update ? rho * u3raw : u3raw;
     float urow[RM];
     float dotU = 0.f, dotL = 0.f;
 #pragma unroll
     for (int k = 0; k < RM; ++k) {
       if (k < r) {
-        urow[k] = update ? rho * U2[(size_t)k * a.n + j] : U2[(size_t)k * a.n + j];
+        urow[k] = update ? rho * ucol[k] : ucol[k];
         dotU = fmaf(urow[k], lt1[k], dotU);
         if (update) dotL = fmaf(tile[threadIdx.x * r + k], il1[k], dotL);
       }
@@ -354,12 +367,10 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
     const float LtQg2 = l3 * Qg2;                                           // :443 / :513
     const float Pg2 = dotU + u3 * LtQg2;                                    // :446 / :516
     if (!update) { out[r + j] = Pg2; continue; }
-    const float iQtx2 = a.v1[j];
     const float iLiQtx2 = (iQtx2 - dotL) / l3;                              // :449
     const float iPx2 = iLiQtx2 / u3;                                        // :451
     a.v2[j] = Pg2;
     a.v3[j] = iPx2;
-    const float dgj = a.dg[r + j], dxj = a.dx[r + j];
     mxL = fmaxf(mxL, fabsf(Qg2 * Qg2 - iQtx2 * iQtx2));                     // grad3 of L   :458
     mxU = fmaxf(mxU, fabsf(Pg2 * dgj - dxj * iPx2));                        // grad3 of U   :471
 #pragma unroll
@@ -474,9 +485,15 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
     __syncthreads();
     if ((int)threadIdx.x < rows) {
       const long long j = j0 + threadIdx.x;
-      const float l3 = a.l3[j] / rho, u3 = rho * a.u3[j];
+      // all global loads of the row first: the stores to U2o below may alias U2 as far as the compiler knows, so inside
+      // the update loop every load would wait for the previous store's operand (ncu: ten serialised DRAM latencies)
+      float ucol[RM];
+#pragma unroll
+      for (int k = 0; k < RM; ++k) ucol[k] = k < r ? U2[(size_t)k * a.n + j] : 0.f;
+      const float l3raw = a.l3[j], u3raw = a.u3[j];
       const float Qg2 = a.v0[j], iQtx2 = a.v1[j], Pg2 = a.v2[j], iPx2 = a.v3[j];
       const float dgj = a.dg[r + j], dxj = a.dx[r + j];
+      const float l3 = l3raw / rho, u3 = rho * u3raw;
       const float g3L = Qg2 * Qg2 - iQtx2 * iQtx2;                           // :458
       const float g3U = Pg2 * dgj - dxj * iPx2;                              // :471
 #pragma unroll
@@ -484,7 +501,7 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
         if (k < r) {
           const float l = tile[threadIdx.x * r + k];
           tile[threadIdx.x * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;       // :464
-          const float u = rho * U2[(size_t)k * a.n + j];
+          const float u = rho * ucol[k];
           U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
         }
       }

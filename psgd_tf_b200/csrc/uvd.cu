@@ -27,10 +27,23 @@
 namespace psgd {
 namespace uvd {
 
-constexpr int kMapTile = 256;        // rows per pipeline stage of the map sweeps (one row per consumer lane)
-constexpr int kMaxStages = 8;
+// Pipeline depth knobs (tools/uvd_variants.py builds A/B libraries with other values)
+#ifndef PSGD_UVD_SMEM_KB
+#define PSGD_UVD_SMEM_KB 160
+#endif
+#ifndef PSGD_UVD_MAX_STAGES
+#define PSGD_UVD_MAX_STAGES 8
+#endif
+#ifndef PSGD_GRAM_RPL
+#define PSGD_GRAM_RPL 0            // rows per lane and pipeline stage in the Gram sweep; 0 = by warps per role
+#endif
+#ifndef PSGD_MAP_RPL
+#define PSGD_MAP_RPL 0             // rows per consumer lane and pipeline stage in the map sweeps; 0 = by stage size
+#endif
+constexpr int kMapLaneRows = 256;    // consumer lanes of a map sweep = rows it handles per step
+constexpr int kMaxStages = PSGD_UVD_MAX_STAGES;
 constexpr int kMaxRank = 16;
-constexpr size_t kSmemBudget = 160 * 1024;
+constexpr size_t kSmemBudget = PSGD_UVD_SMEM_KB * 1024;
 
 enum Mode { kUpdate = 0, kApply = 1, kMatvec = 2 };
 
@@ -107,7 +120,16 @@ struct GramPlan {
   // warps per role: keep the CTA at <= 12 warps so ptxas may use > 128 registers per thread
   static constexpr int WPR =
       NROLES == 1 ? 8 : (NROLES == 2 ? 4 : (NROLES == 3 ? 3 : (NROLES == 4 ? PSGD_GRAM_WPR4 : (NROLES <= 5 ? 2 : 1))));
-  static constexpr int ROWS_PER_LANE = (WPR >= 4) ? 1 : (WPR >= 2 ? 2 : 4);
+  // Rows per lane and pipeline stage.  Bigger tiles mean fewer barrier round trips and TMA operations per byte (measured
+  // at r = 10: 96 / 192 / 384-row tiles -> 2.15 / 1.63 / 1.46 ms per sweep); take the largest of 4, 2, 1 that still
+  // leaves at least four stages in the shared-memory budget.
+  static constexpr int ROW_BYTES = 4 * (W + (MODE == kUpdate ? 3 : (MODE == kApply ? 2 : 1)));
+  static constexpr int rpl_auto() {
+    for (int rpl = 4; rpl > 1; rpl /= 2)
+      if (kSmemBudget / ((size_t)WPR * 32 * rpl * ROW_BYTES) >= 4) return rpl;
+    return 1;
+  }
+  static constexpr int ROWS_PER_LANE = PSGD_GRAM_RPL ? PSGD_GRAM_RPL : rpl_auto();
   static constexpr int TILE = WPR * 32 * ROWS_PER_LANE;          // rows per pipeline stage
   static constexpr int CONSUMER_WARPS = NROLES * WPR;
   static constexpr int THREADS = (CONSUMER_WARPS + 1) * 32;
@@ -707,6 +729,16 @@ template <> struct MapTraits<kMapUpdAppU> { static constexpr int NM = 2, NV = 4,
 template <> struct MapTraits<kMapUpdAppV> { static constexpr int NM = 2, NV = 4, kStoreMat = 1, kStoreVec = -1; };
 template <> struct MapTraits<kMapApplyD>  { static constexpr int NM = 2, NV = 3, kStoreMat = -1, kStoreVec = -1; };
 
+// Rows per consumer lane and pipeline stage of a map sweep: two when at least three stages of 512 rows fit the
+// shared-memory budget, else one (measured at r = 10: 512-row tiles run the fused sweeps 2-4 % faster than 256-row ones).
+template <int R, int KIND>
+struct MapPlan {
+  using T = MapTraits<KIND>;
+  static constexpr int ROW_BYTES = 4 * (T::NM * R + T::NV);
+  static constexpr int RPL = PSGD_MAP_RPL ? PSGD_MAP_RPL : ((kSmemBudget / ((size_t)2 * kMapLaneRows * ROW_BYTES) >= 3) ? 2 : 1);
+  static constexpr int TILE = kMapLaneRows * RPL;
+};
+
 constexpr bool map_is_fused_update(int KIND) {
   return KIND == kMapUpdFU || KIND == kMapUpdFV || KIND == kMapUpdAppU || KIND == kMapUpdAppV;
 }
@@ -907,8 +939,10 @@ struct MapBody {
 template <int R, int KIND>
 __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, MapOut o, int update_U) {
   using T = MapTraits<KIND>;
+  constexpr int kMapTile = MapPlan<R, KIND>::TILE;
+  constexpr int kMapRowsPerLane = MapPlan<R, KIND>::RPL;
   using L = TileLayout<R, T::NM, T::NV, kMapTile>;
-  static_assert(kMapTile == kMapConsumerWarps * 32, "one row per consumer lane per tile");
+  static_assert(kMapLaneRows == kMapConsumerWarps * 32, "one consumer lane per row of a step");
   constexpr bool kStore = T::kStoreMat >= 0;
   constexpr int SM = kStore ? T::kStoreMat : 0;                 // staged matrix that is updated in place
   constexpr int SV = T::kStoreVec >= 0 ? T::kStoreVec : 0;
@@ -938,8 +972,9 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
         const uint32_t phase = (it / L::kStages) & 1;
         mbar_wait(&full[stage], phase);
         float* sb = smem + (size_t)stage * L::kStageFloats;
-        {
-          const int r0 = ct;
+#pragma unroll
+        for (int rr = 0; rr < kMapRowsPerLane; ++rr) {
+          const int r0 = ct + rr * (kMapConsumerWarps * 32);
           const float* m0 = L::mat(sb, 0);
           const float* m1 = L::mat(sb, T::NM > 1 ? 1 : 0);
           const float v0 = L::vec(sb, 0)[r0];
@@ -974,11 +1009,11 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
     {
       int64_t first, step;
       if (a.direct) {
-        first = (int64_t)blockIdx.x * kMapTile + ct;
-        step = (int64_t)gridDim.x * kMapTile;
+        first = (int64_t)blockIdx.x * (kMapConsumerWarps * 32) + ct;
+        step = (int64_t)gridDim.x * (kMapConsumerWarps * 32);
       } else {
         first = (blockIdx.x == (unsigned)(n_full_tiles % gridDim.x)) ? n_full_tiles * kMapTile + ct : a.n;
-        step = kMapTile;
+        step = kMapConsumerWarps * 32;
       }
       for (int64_t r0 = first; r0 < a.n; r0 += step) {
         const float* m0 = a.mat[0] + r0 * R;
@@ -1137,7 +1172,7 @@ __global__ void zero_small_kernel(SmallState* st) { st->maxU = 0.f; st->maxV = 0
 // host orchestration
 // =============================================================================================
 static int grid_for(const psgd_ctx* ctx, int64_t n) {
-  int64_t tiles = (n + kMapTile - 1) / kMapTile;
+  int64_t tiles = (n + kMapLaneRows - 1) / kMapLaneRows;
   int64_t g = ctx->num_sms;
   if (tiles < g) g = tiles > 0 ? tiles : 1;
   return (int)g;
@@ -1163,7 +1198,7 @@ static int launch_map(psgd_ctx* ctx, const SweepArgs& a, const MapOut& o, int up
                       : map_is_updapp(KIND) ? PSGD_K_UVD_MAP_UPDAPP
                       : KIND == kMapApplyD ? PSGD_K_UVD_MAP_APPLY_D : PSGD_K_UVD_MAP_APPLY);
   using T = MapTraits<KIND>;
-  using L = TileLayout<R, T::NM, T::NV, kMapTile>;
+  using L = TileLayout<R, T::NM, T::NV, MapPlan<R, KIND>::TILE>;
   auto kern = map_sweep_kernel<R, KIND>;
   kern<<<grid, kMapThreads, L::kSmemBytes, ctx->stream>>>(a, o, update_U);
   PSGD_LAUNCH_CHECK(ctx);
@@ -1175,7 +1210,7 @@ static int launch_map(psgd_ctx* ctx, const SweepArgs& a, const MapOut& o, int up
 template <int R, int KIND>
 static cudaError_t map_attr() {
   using T = MapTraits<KIND>;
-  using L = TileLayout<R, T::NM, T::NV, kMapTile>;
+  using L = TileLayout<R, T::NM, T::NV, MapPlan<R, KIND>::TILE>;
   return cudaFuncSetAttribute(map_sweep_kernel<R, KIND>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes);
 }
 template <int R, int MODE>
@@ -1618,4 +1653,19 @@ extern "C" int psgd_ipuvt_matvec(psgd_ctx* ctx, const float* U, const float* V, 
   cudaFreeAsync(xc, ctx->stream);
   cudaFreeAsync(oc, ctx->stream);
   return rc;
+}
+
+// Pipeline geometry of the update Gram sweep for rank r (diagnostics / documentation): rows per stage, stages, threads.
+extern "C" int psgd_uvd_plan_info(int r, int* tile_rows, int* stages, int* threads, int* roles) {
+#define CALL(R)                                                                              \
+  ([&]() {                                                                                   \
+    using P = uvd::GramPlan<R, uvd::kUpdate>;                                                \
+    using L = uvd::TileLayout<R, 2, 3, P::TILE>;                                             \
+    *tile_rows = P::TILE; *stages = L::kStages; *threads = P::THREADS; *roles = P::NROLES;   \
+    return (int)PSGD_OK;                                                                     \
+  })()
+  PSGD_REQUIRE(tile_rows && stages && threads && roles, PSGD_ERR_BAD_POINTER, "psgd_uvd_plan_info: null output");
+  using uvd::kMaxRank;
+  PSGD_RANK_SWITCH(r, CALL)
+#undef CALL
 }

@@ -15,11 +15,9 @@ sys.path.insert(0, ROOT)
 from psgd_tf_b200 import build as B   # noqa: E402
 
 VARIANTS = {
-    "rcp": ["-DPSGD_GRAM_RCP=1"],
-    "r2w4": ["-DPSGD_GRAM_ACC=140"],
-    "r2w4rcp": ["-DPSGD_GRAM_ACC=140", "-DPSGD_GRAM_RCP=1"],
-    "r4w3": ["-DPSGD_GRAM_ACC=66", "-DPSGD_GRAM_WPR4=3"],
-    "r4w3rcp": ["-DPSGD_GRAM_ACC=66", "-DPSGD_GRAM_WPR4=3", "-DPSGD_GRAM_RCP=1"],
+    "rpl2": ["-DPSGD_GRAM_RPL=2"],
+    "rpl4": ["-DPSGD_GRAM_RPL=4"],
+    "map2": ["-DPSGD_MAP_RPL=2"],
 }
 
 
