@@ -566,9 +566,30 @@ def run_reference_kron(args):
 
 
 # ---------------------------------------------------------------------------------------------
+_REAL_STDOUT = None
+
+
+def _claim_stdout():
+    """Rank 0 must print exactly ONE JSON line on stdout, but native libraries write there too (NCCL prints its version
+    banner to stdout on the first communicator).  Point fd 1 at stderr for the whole run and keep the real stdout aside
+    for the final line."""
+    global _REAL_STDOUT
+    if _REAL_STDOUT is None:
+        sys.stdout.flush()
+        _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
+
+
+def emit(obj):
+    out = _REAL_STDOUT or sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
+
+
 def main():
+    _claim_stdout()
     if os.environ.get("NCCL_DEBUG", "").upper() == "VERSION":
-        os.environ["NCCL_DEBUG"] = "WARN"        # keep NCCL's version banner off stdout: rank 0 prints ONE JSON line
+        os.environ["NCCL_DEBUG"] = "WARN"
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -597,13 +618,13 @@ def main():
     if args.impl == "reference":
         out = run_reference(args, rank, world)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
         return 0
 
     args.warmup = max(args.warmup, 3)       # timing rule: at least 3 warm-up steps
     import torch
     if not torch.cuda.is_available():
-        print(json.dumps({"error": "no CUDA device: psgd_tf_b200 has no CPU path"}), flush=True)
+        emit({"error": "no CUDA device: psgd_tf_b200 has no CPU path"})
         return 1
     if world > 1:
         import torch.distributed as dist
@@ -633,7 +654,7 @@ def main():
             from bench_aux import run_aux
             out["aux"] = run_aux(load_peaks()["hbm"], steps=10)
         if out is not None:
-            print(json.dumps(out), flush=True)
+            emit(out)
     finally:
         if world > 1:
             import torch.distributed as dist

@@ -54,6 +54,28 @@ __global__ void __launch_bounds__(256) balance_kernel(int kind_l, const float* Q
   }
 }
 
+// Both factors structured (normalization / scaling: a few thousand floats): maxima, rho and both rescaled copies in ONE
+// single-CTA launch instead of three (the update of such a pair is launch-latency bound at NMT sizes).
+constexpr int64_t kBalanceSmallMax = 65536;
+__global__ void __launch_bounds__(1024) balance_rescale_small_kernel(int kind_l, const float* __restrict__ Ql, int nl,
+                                                                     int kind_r, const float* __restrict__ Qr, int nr,
+                                                                     int64_t cl, int64_t cr, float* __restrict__ Qlb,
+                                                                     float* __restrict__ Qrb, Scal* sc) {
+  __shared__ float red[32][2];
+  float ml = -INFINITY, mr = -INFINITY;            // row 0 of a [2,n] / [1,n] factor; max WITHOUT abs, as the reference
+  for (int i = threadIdx.x; i < nl; i += blockDim.x) ml = fmaxf(ml, Ql[i]);
+  for (int i = threadIdx.x; i < nr; i += blockDim.x) mr = fmaxf(mr, Qr[i]);
+  ml = warp_max(ml); mr = warp_max(mr);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = ml; red[threadIdx.x >> 5][1] = mr; }
+  __syncthreads();
+  ml = red[0][0]; mr = red[0][1];
+  for (int w = 1; w < (int)(blockDim.x >> 5); ++w) { ml = fmaxf(ml, red[w][0]); mr = fmaxf(mr, red[w][1]); }
+  const float rho = sqrtf(ml / mr);
+  if (threadIdx.x == 0) { sc->max_l = ml; sc->max_r = mr; sc->rho = rho; sc->max1 = 0.f; sc->max2 = 0.f; }
+  for (int64_t i = threadIdx.x; i < cl; i += blockDim.x) Qlb[i] = Ql[i] / rho;
+  for (int64_t i = threadIdx.x; i < cr; i += blockDim.x) Qrb[i] = rho * Qr[i];
+}
+
 // out = in / rho  (left factor)   or   out = rho * in  (right factor)
 __global__ void __launch_bounds__(256) rescale_kernel(const float* __restrict__ in, float* __restrict__ out,
                                                        int64_t count, const Scal* __restrict__ sc, int divide) {
@@ -328,7 +350,13 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
   const int64_t cl = (int64_t)fsize(kl, M), cr = (int64_t)fsize(kr, N);
 
   // ---- balance: Ql /= rho, Qr *= rho                          psgd.py:166-170, :211-215, :288-292, :342-346
+  const bool small_pair = kl != PSGD_FACTOR_DENSE && kr != PSGD_FACTOR_DENSE && cl + cr <= kBalanceSmallMax;
   for (auto& L : Ls) {
+    if (small_pair) {
+      balance_rescale_small_kernel<<<1, 1024, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, cl, cr, L.Qlb, L.Qrb, L.sc);
+      PSGD_LAUNCH_CHECK(ctx);
+      continue;
+    }
     balance_kernel<<<1, 256, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, L.sc);
     PSGD_LAUNCH_CHECK(ctx);
     rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, st>>>(L.Ql, L.Qlb, cl, L.sc, 1);
@@ -384,9 +412,11 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     }
   } else {  // (NORM, SCALE): no dense factor at all -- A and Bt are never materialised (kron_stream.cu)
     for (auto& L : Ls) {
-      PSGD_RETURN_IF(ks::col_wsum(ctx, 0, L.Qlb, nullptr, L.dX, N, M, N, L.part, L.cvec));            // psgd.py:353-355
-      PSGD_RETURN_IF(ks::ns_update_stats(ctx, L.Qlb, L.Qrb, L.cvec, L.dX, L.dG, M, N, L.nspart, L.g1d, L.g1b, L.gvec,
-                                         &L.sc->max1, &L.sc->max2));                                  // :349-351, :356-366
+      int cchunks = 0;
+      PSGD_RETURN_IF(ks::col_wsum_partials(ctx, 0, L.Qlb, nullptr, L.dX, N, M, N, L.part, &cchunks));  // psgd.py:353-355
+      PSGD_RETURN_IF(ks::ns_update_stats(ctx, L.Qlb, L.Qrb, L.part, cchunks, L.dX, L.dG, M, N, L.nspart, L.g1d, L.g1b,
+                                         L.gvec, &L.sc->max1, &L.sc->max2, L.Ql_out, L.Qr_out, step, tiny));   // :349-369
+      if (ks::ns_finish_is_fused(M, N)) continue;
       norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :362-364
       PSGD_LAUNCH_CHECK(ctx);
       scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);        // :367-369

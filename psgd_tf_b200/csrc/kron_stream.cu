@@ -107,6 +107,15 @@ __global__ void __launch_bounds__(256) col_finish_kernel(const float* __restrict
   out[j] = s;
 }
 
+int col_wsum_partials(psgd_ctx* ctx, int mode, const float* ql, const float* wvec, const float* X, int ldx, int M, int N,
+                      float* partial, int* chunks_out) {
+  const int rpc = rows_per_cta(ctx, M, N, 4), chunks = row_chunks(M, rpc);       // 64 registers: 4 CTAs per SM
+  col_wsum_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(mode, ql, wvec, X, ldx, M, N, rpc, partial);
+  PSGD_LAUNCH_CHECK(ctx);
+  *chunks_out = chunks;
+  return PSGD_OK;
+}
+
 int col_wsum(psgd_ctx* ctx, int mode, const float* ql, const float* wvec, const float* X, int ldx, int M, int N,
              float* partial, float* out) {
   const int rpc = rows_per_cta(ctx, M, N, 4), chunks = row_chunks(M, rpc);       // 64 registers: 4 CTAs per SM
@@ -178,8 +187,12 @@ int row_dot(psgd_ctx* ctx, const float* X, int ldx, const float* w, int M, int N
 //   col j : sum_i A^2, sum_i Bt^2                                                  psgd.py:366
 // rowpart[col_tile][i][4], colpart[row_tile][2][N]
 // ---------------------------------------------------------------------------------------------
+// cpart/cchunks: the col_wsum partials of cvec (Bt's last-row correction), summed here in fixed order by every CTA for
+// its own columns -- one launch less than finishing them separately, which matters at NMT sizes where the whole update
+// is launch-latency bound.
 __global__ void __launch_bounds__(kThreads) ns_stats_kernel(const float* __restrict__ ql, const float* __restrict__ qr,
-                                                            const float* __restrict__ cvec, const float* __restrict__ dX,
+                                                            const float* __restrict__ cpart, int cchunks,
+                                                            const float* __restrict__ dX,
                                                             const float* __restrict__ dG, int M, int N, int rpc,
                                                             float* __restrict__ rowpart, float* __restrict__ colpart) {
   __shared__ float red[kWarps][2][kCols];
@@ -199,7 +212,10 @@ __global__ void __launch_bounds__(kThreads) ns_stats_kernel(const float* __restr
     const bool ok = j < N;
     cq[k] = ok ? qr[j] : 0.f;
     crq[k] = ok ? 1.0f / qr[j] : 0.f;
-    cv[k] = ok ? cvec[j] : 0.f;
+    float c = 0.f;
+    if (ok)
+      for (int t = 0; t < cchunks; ++t) c += cpart[(size_t)t * N + j];
+    cv[k] = c;
     const float g = ok ? gl[j] : 0.f, x = ok ? xl[j] : 0.f;
     alast[k] = (qlast0 * g + qlast1 * g) * cq[k];
     blast[k] = (rqlast0 * x - cv[k]) * crq[k];
@@ -314,13 +330,71 @@ size_t ns_update_scratch_floats(int M, int N) {
   return (size_t)col_tiles(N) * M * 4 + (size_t)row_tiles(M) * 2 * N + 64;
 }
 
-int ns_update_stats(psgd_ctx* ctx, const float* ql, const float* qr, const float* cvec, const float* dX, const float* dG,
-                    int M, int N, float* scratch, float* g1d, float* g1b, float* grad2, float* max1, float* max2) {
+// one CTA: grad1_diag / grad1_bias / grad2, both max-abs normalisers and the new factors               psgd.py:358-369
+// (small problems only -- at most kFinishSmallWork partial records to sum, e.g. the NMT shapes; replaces four launches.
+// At [8192, 8192] one CTA summing 336 K records was 40 us slower than the multi-CTA finish kernels.)
+constexpr long long kFinishSmallWork = 128 * 1024;
+__global__ void __launch_bounds__(1024) ns_finish_small_kernel(const float* __restrict__ rowpart, int ctiles,
+                                                               const float* __restrict__ colpart, int rchunks,
+                                                               const float* __restrict__ ql, const float* __restrict__ qr,
+                                                               float* __restrict__ g1d, float* __restrict__ g1b,
+                                                               float* __restrict__ grad2, float* __restrict__ ql_out,
+                                                               float* __restrict__ qr_out, int M, int N, float step, float tiny) {
+  __shared__ float red[32][2];
+  float mx1 = 0.f, mx2 = 0.f;
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {
+    float t0 = 0.f, t1 = 0.f, t2 = 0.f, t3 = 0.f;
+    for (int c = 0; c < ctiles; ++c) {
+      const float4 p = *reinterpret_cast<const float4*>(rowpart + ((size_t)c * M + i) * 4);
+      t0 += p.x; t1 += p.y; t2 += p.z; t3 += p.w;
+    }
+    const float d = t0 - t1;
+    const float b = (i == M - 1) ? 0.f : (t2 - t3);
+    g1d[i] = d; g1b[i] = b;
+    mx1 = fmaxf(mx1, fmaxf(fabsf(d), fabsf(b)));
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) {
+    float s0 = 0.f, s1 = 0.f;
+    for (int t = 0; t < rchunks; ++t) { s0 += colpart[((size_t)t * 2) * N + j]; s1 += colpart[((size_t)t * 2 + 1) * N + j]; }
+    const float g = s0 - s1;
+    grad2[j] = g;
+    mx2 = fmaxf(mx2, fabsf(g));
+  }
+  mx1 = warp_max(mx1); mx2 = warp_max(mx2);
+  if ((threadIdx.x & 31) == 0) { red[threadIdx.x >> 5][0] = mx1; red[threadIdx.x >> 5][1] = mx2; }
+  __syncthreads();                                   // also orders this CTA's g1d / g1b / grad2 stores before the re-reads
+  mx1 = 0.f; mx2 = 0.f;
+  for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { mx1 = fmaxf(mx1, red[w][0]); mx2 = fmaxf(mx2, red[w][1]); }
+  const float step1 = step / (mx1 + tiny);                                            // psgd.py:362
+  const float step2 = step / (mx2 + tiny);                                            // psgd.py:367
+  const float qlast = ql[M - 1];
+  for (int i = threadIdx.x; i < M; i += blockDim.x) {                                 // psgd.py:363-364
+    ql_out[i] = ql[i] - step1 * g1d[i] * ql[i];
+    ql_out[M + i] = ql[M + i] - step1 * (g1d[i] * ql[M + i] + qlast * g1b[i]);
+  }
+  for (int j = threadIdx.x; j < N; j += blockDim.x) qr_out[j] = qr[j] - step2 * grad2[j] * qr[j];      // psgd.py:369
+}
+
+bool ns_finish_is_fused(int M, int N) {
+  // upper bound of the records: col_tiles(N) per row + (at most row_tiles(M)) per column
+  return (long long)M * col_tiles(N) + (long long)N * row_tiles(M) <= kFinishSmallWork;
+}
+
+int ns_update_stats(psgd_ctx* ctx, const float* ql, const float* qr, const float* cpart, int cchunks, const float* dX,
+                    const float* dG, int M, int N, float* scratch, float* g1d, float* g1b, float* grad2, float* max1,
+                    float* max2, float* ql_out, float* qr_out, float step, float tiny) {
   float* rowpart = scratch;
   float* colpart = scratch + (((size_t)col_tiles(N) * M * 4 + 63) / 64) * 64;
   const int rpc = rows_per_cta(ctx, M, N, 2), chunks = row_chunks(M, rpc);       // 128 registers: 2 CTAs per SM
-  ns_stats_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(ql, qr, cvec, dX, dG, M, N, rpc, rowpart, colpart);
+  ns_stats_kernel<<<dim3(col_tiles(N), chunks), kThreads, 0, ctx->stream>>>(ql, qr, cpart, cchunks, dX, dG, M, N, rpc, rowpart,
+                                                                            colpart);
   PSGD_LAUNCH_CHECK(ctx);
+  if (ns_finish_is_fused(M, N)) {
+    ns_finish_small_kernel<<<1, 1024, 0, ctx->stream>>>(rowpart, col_tiles(N), colpart, chunks, ql, qr, g1d, g1b, grad2,
+                                                        ql_out, qr_out, M, N, step, tiny);
+    PSGD_LAUNCH_CHECK(ctx);
+    return PSGD_OK;
+  }
   int gr = (M + 255) / 256, gc = (N + 255) / 256;
   if (gr > ctx->num_sms * 4) gr = ctx->num_sms * 4;
   if (gc > ctx->num_sms * 4) gc = ctx->num_sms * 4;

@@ -116,6 +116,8 @@ def hotspots(tag: str, name: str, top: int = 25):
     if not os.path.exists(path):
         return ""
     rows = list(csv.reader(open(path, errors="replace")))
+    if not any(r and r[0] == "Address" for r in rows):
+        return ""
     hdr = next(i for i, r in enumerate(rows) if r and r[0] == "Address")
     kernel = rows[0][1] if len(rows[0]) > 1 else name
     cols = rows[hdr]
@@ -137,7 +139,7 @@ def main():
     for which in ("uvd", "kron"):
         launches(tag, which)
     allrows = []
-    for name in ("uvd_full", "kron_full_head", "kron_full_tail", "gemm4096"):
+    for name in ("uvd_full", "kron_full_head", "kron_full_tail", "gemm4096", "splu_full", "ns_full"):
         allrows += full_rows(tag, name)
     if allrows:
         keys = ["capture", "kernel", "time_us", "dram_read_MB", "dram_write_MB", "dram_pct", "sm_pct", "tensor_pipe_pct",
@@ -173,7 +175,7 @@ def main():
         json.dump({"source": f"profiles/{tag}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                              "kernels not re-captured under this tag keep the previous capture's figure)",
                    "bytes_per_launch": traffic}, open(os.path.join(DST, f"{tag}_traffic.json"), "w"), indent=1)
-    hs = "".join(hotspots(tag, n) for n in ("uvd_full", "kron_full_tail", "gemm4096", "gemm4096_ts"))
+    hs = "".join(hotspots(tag, n) for n in ("uvd_full", "uvd_map", "kron_full_tail", "gemm4096", "gemm4096_ts", "splu_full", "ns_full"))
     if hs:
         open(os.path.join(DST, f"{tag}_hotspots.txt"), "w").write(
             "# ncu --page source (per-instruction warp-state sampling) of the dominant kernels; -lineinfo builds.\n" + hs)
