@@ -66,7 +66,8 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 /* Per-kernel device timing.  After psgd_set_option(ctx, "profile", 1) every large kernel launch is bracketed
  * by CUDA events on ctx's stream; psgd_profile_read synchronises on them, writes up to `cap` (kernel id,
  * milliseconds, work) records in launch order, clears the log and returns the number written.  `work` (may be
- * NULL) is the launch's algorithmic work: dense-count flops for GEMM/TRSM launches, 0 where the caller knows the
+ * NULL) is the launch's algorithmic work: dense-count flops for GEMM/TRSM launches (with "profile" = 2: the flops the
+ * tcgen05 GEMM launch actually executes after triangular K clipping and tile skipping), 0 where the caller knows the
  * byte count from the shapes (UVd sweeps).  Kernel ids: */
 #define PSGD_K_UVD_GRAM_UPDATE 1 /* update sweep 1: Gram/vector reductions over U,V,d,h,v  */
 #define PSGD_K_UVD_MAP_UPDATE2 2 /* update sweep 2: per-row a,b,nablaD + max/sums            */

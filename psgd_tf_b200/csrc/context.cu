@@ -90,7 +90,7 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   PSGD_REQUIRE(ctx && key, PSGD_ERR_BAD_POINTER, "null context or key");
   if (strcmp(key, "direct") == 0) { ctx->opt_direct = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "uvd_fused") == 0) { ctx->opt_uvd_fused = value ? 1 : 0; return PSGD_OK; }
-  if (strcmp(key, "profile") == 0) { ctx->opt_profile = value ? 1 : 0; return PSGD_OK; }
+  if (strcmp(key, "profile") == 0) { ctx->opt_profile = value == 2 ? 2 : (value ? 1 : 0); return PSGD_OK; }
   if (strcmp(key, "assume_triangular") == 0) { ctx->opt_assume_tri = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_bn") == 0) {
     PSGD_REQUIRE(value == 128 || value == 256, PSGD_ERR_BAD_SHAPE, "tc_bn must be 128 or 256");

@@ -248,7 +248,7 @@ __device__ __forceinline__ void split_tile_smem(uint32_t hi_addr, uint32_t lo_ad
 // Does output tile (m0, n0) take part in the product at all?  (tiles skipped by triu are still WRITTEN, as zeros, by the
 // epilogue; tiles outside the block-pair pattern are not touched.)
 template <int BN>
-__device__ __forceinline__ bool tile_in_pattern(const Params& p, int m0, int n0) {
+__host__ __device__ __forceinline__ bool tile_in_pattern(const Params& p, int m0, int n0) {
   if (p.pair_b) {
     const int bm = m0 / p.pair_b;
     if ((bm & 1) || n0 / p.pair_b != bm + 1) return false;
@@ -256,24 +256,26 @@ __device__ __forceinline__ bool tile_in_pattern(const Params& p, int m0, int n0)
   return true;
 }
 template <int BN>
-__device__ __forceinline__ bool tile_computed(const Params& p, int m0, int n0) {
+__host__ __device__ __forceinline__ bool tile_computed(const Params& p, int m0, int n0) {
   return tile_in_pattern<BN>(p, m0, n0) && !(p.triu && m0 >= n0 + BN);
 }
 
 // K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
 template <int BN>
-__device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1) {
+__host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1) {
   const int K = p.K[prod];
   int lo = 0, hi = K;
+  auto up = [](int& v, int x) { if (x > v) v = x; };
+  auto down = [](int& v, int x) { if (x < v) v = x; };
   if (prod == 0) {
-    if (p.a_tri == 1) lo = max(lo, m0);                 // op(A)[m,k] = 0 for k < m
-    if (p.a_tri == 2) hi = min(hi, m0 + BM);            // op(A)[m,k] = 0 for k > m
-    if (p.b_tri == 1) hi = min(hi, n0 + BN);            // op(B)[k,n] = 0 for k > n
-    if (p.b_tri == 2) lo = max(lo, n0);                 // op(B)[k,n] = 0 for k < n
+    if (p.a_tri == 1) up(lo, m0);                       // op(A)[m,k] = 0 for k < m
+    if (p.a_tri == 2) down(hi, m0 + BM);                // op(A)[m,k] = 0 for k > m
+    if (p.b_tri == 1) down(hi, n0 + BN);                // op(B)[k,n] = 0 for k > n
+    if (p.b_tri == 2) up(lo, n0);                       // op(B)[k,n] = 0 for k < n
     if (p.pair_b) {
       const int base = (p.pair_kind == 1 ? n0 : m0) / p.pair_b * p.pair_b;
-      lo = max(lo, base);
-      hi = min(hi, base + p.pair_b);
+      up(lo, base);
+      down(hi, base + p.pair_b);
     }
   }
   kb0 = lo / BK;
@@ -731,6 +733,24 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   }
   int grid = p.tiles_m * p.tiles_n * count;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
+  if (ctx->opt_profile == 2) {
+    // psgd_set_option("profile", 2): report the flops the launch EXECUTES (K blocks left after the triangular clipping,
+    // tiles left after triu / block-pair skipping; one fp32-equivalent multiply-add per 3xTF32 triple) instead of the
+    // dense count of the op it implements
+    double kbs = 0.0;
+    for (int tm = 0; tm < p.tiles_m; ++tm)
+      for (int tn = 0; tn < p.tiles_n; ++tn) {
+        const int m0 = tm * BM, n0 = tn * BN;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          kbs += kb1 - kb0;
+        }
+      }
+    work = kbs * 2.0 * BM * BN * BK * count;
+  }
   ProfScope prof(ctx, PSGD_K_GEMM, work);
   kern<<<grid, kThreads, C::kSmemBytes, ctx->stream>>>(maps, p);
   PSGD_LAUNCH_CHECK(ctx);
