@@ -139,24 +139,58 @@ __global__ void __launch_bounds__(32) small0_kernel(Args a, const float* __restr
 // rows), so every load instruction of a warp spans ~10 lines.  Instead a block stages the 256 consecutive rows of its
 // tile -- one contiguous run of 256 r floats -- into shared memory with fully coalesced loads (balanced by 1/rho on the
 // way in when updating), and threads then read (and in pass 4 rewrite) their rows there.
-template <int RM>
-__device__ __forceinline__ void stage_rows(float* tile, const float* __restrict__ src, long long j0, int rows, int r,
-                                           bool balance, float rho) {
-  const float* p = src + (size_t)j0 * r;
-  const int cnt = rows * r;                       // <= kThreads * RM: at most RM elements per thread
-  float vals[RM];
-  // all loads first (ncu: with the division inside a rolled loop every element waited out its own DRAM latency)
-#pragma unroll
-  for (int i = 0; i < RM; ++i) {
-    const int e = threadIdx.x + i * kThreads;
-    vals[i] = e < cnt ? p[e] : 1.f;
-  }
-#pragma unroll
-  for (int i = 0; i < RM; ++i) {
-    const int e = threadIdx.x + i * kThreads;
-    if (e < cnt) tile[e] = balance ? vals[i] / rho : vals[i];
-  }
+__device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
+
+// Row tiles of L2 in shared memory, filled by cp.async (SASS LDGSTS: no registers, no use-stall) and double-buffered for
+// r <= 16, so the next tile streams in while the current one is consumed (one exposed DRAM latency per tile instead of
+// two).  Values are staged raw; the reader applies the balancing 1/rho.
+// acquire() and release() contain the block barriers: EVERY thread of the block must call each exactly once per tile, from
+// the same (non-divergent) place -- rows that do not exist are skipped inside an `if`, never with `continue`.
+template <int RM>
+struct RowTiles {
+  static constexpr int NBUF = RM <= 16 ? 2 : 1;
+  static constexpr int kFloats = NBUF * kThreads * RM;
+  float* buf;
+  const float* src;
+  long long m, stride;
+  int r, cur;
+  __device__ __forceinline__ int rows_at(long long j0) const { return (int)(m - j0 < kThreads ? m - j0 : kThreads); }
+  __device__ __forceinline__ void issue(int b, long long j0) {
+    const float* p = src + (size_t)j0 * r;
+    float* t = buf + b * (kThreads * RM);
+    const int cnt = rows_at(j0) * r;                 // <= kThreads * RM: at most RM elements per thread
+#pragma unroll
+    for (int i = 0; i < RM; ++i) {
+      const int e = threadIdx.x + i * kThreads;
+      if (e < cnt) cp_async4(t + e, p + e);
+    }
+    cp_async_commit();
+  }
+  __device__ __forceinline__ void begin(float* smem, const float* L2, long long m_, int r_, long long j0) {
+    buf = smem; src = L2; m = m_; r = r_; cur = 0;
+    stride = (long long)gridDim.x * kThreads;
+    if (j0 < m) issue(0, j0);
+  }
+  // tile j0 becomes readable (and, when double-buffered, the next one starts streaming in first)
+  __device__ __forceinline__ float* acquire(long long j0) {
+    const long long nxt = j0 + stride;
+    if (NBUF == 2 && nxt < m) { issue(cur ^ 1, nxt); cp_async_wait<1>(); }
+    else cp_async_wait<0>();
+    __syncthreads();
+    return buf + cur * (kThreads * RM);
+  }
+  // every thread is done with tile j0
+  __device__ __forceinline__ void release(long long j0) {
+    __syncthreads();
+    if (NBUF == 2) cur ^= 1;
+    else if (j0 + stride < m) issue(0, j0 + stride);
+  }
+};
 
 // ---- pass 1 / A1:  partial[b][k] = sum_j (rho U2[k, j]) w[j],  w = dg2 (update) or g2 (apply) ------------------------
 template <int RM>
@@ -219,7 +253,9 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
   const float rho = st->rho;
   const float* L2 = a.L12 + (size_t)r * r;
   const float* U2 = a.U12 + r;
-  __shared__ float tile[kThreads * RM];
+  __shared__ float tile_mem[RowTiles<RM>::kFloats];
+  RowTiles<RM> tiles;
+  tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);
   float ug1[RM], iu1[RM], pa[RM], pb[RM];
 #pragma unroll
   for (int k = 0; k < RM; ++k) {
@@ -228,11 +264,9 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
     pa[k] = 0.f; pb[k] = 0.f;
   }
   for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
-    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
-    __syncthreads();
-    stage_rows<RM>(tile, L2, j0, rows, r, update != 0, rho);
-    __syncthreads();
-    if ((int)threadIdx.x >= rows) continue;
+    const int rows = tiles.rows_at(j0);
+    const float* tile = tiles.acquire(j0);
+    if ((int)threadIdx.x < rows) {
     const long long j = j0 + threadIdx.x;
     // every global load of this row is issued before any arithmetic consumes one (ncu: interleaved, each use waited
     // out its own DRAM latency)
@@ -248,7 +282,7 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
 #pragma unroll
     for (int k = 0; k < RM; ++k) {
       if (k < r) {
-        lrow[k] = tile[threadIdx.x * r + k];
+        lrow[k] = update ? tile[threadIdx.x * r + k] / rho : tile[threadIdx.x * r + k];
         dotL = fmaf(lrow[k], ug1[k], dotL);
         if (update) dotU = fmaf(rho * ucol[k], iu1[k], dotU);
       }
@@ -265,6 +299,8 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
 #pragma unroll
     for (int k = 0; k < RM; ++k)
       if (k < r) { pa[k] = fmaf(lrow[k], iQtx2, pa[k]); pb[k] = fmaf(lrow[k], Qg2, pb[k]); }
+    }
+    tiles.release(j0);
   }
   block_reduce_to<RM>(pa, update ? r : 0, a.partial, 0);
   block_reduce_to<RM>(pb, r, a.partial, kMaxR);
@@ -334,16 +370,14 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
     dx1[k] = (ok && update) ? st->dx1[k] : 0.f;
     pc[k] = 0.f;
   }
-  __shared__ float tile[kThreads * RM];
+  __shared__ float tile_mem[RowTiles<RM>::kFloats];
+  RowTiles<RM> tiles;
+  if (update) tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);     // the apply's third pass does not read L2
   float mxL = 0.f, mxU = 0.f;
   for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
     const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
-    if (update) {                       // the apply's third pass does not read L2
-      __syncthreads();
-      stage_rows<RM>(tile, L2, j0, rows, r, true, rho);
-      __syncthreads();
-    }
-    if ((int)threadIdx.x >= rows) continue;
+    const float* tile = update ? tiles.acquire(j0) : tile_mem;
+    if ((int)threadIdx.x < rows) {
     const long long j = j0 + threadIdx.x;
     // all global loads of the row first (see pass 2)
     float ucol[RM];
@@ -361,12 +395,14 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
       if (k < r) {
         urow[k] = update ? rho * ucol[k] : ucol[k];
         dotU = fmaf(urow[k], lt1[k], dotU);
-        if (update) dotL = fmaf(tile[threadIdx.x * r + k], il1[k], dotL);
+        if (update) dotL = fmaf(tile[threadIdx.x * r + k] / rho, il1[k], dotL);
       }
     }
     const float LtQg2 = l3 * Qg2;                                           // :443 / :513
     const float Pg2 = dotU + u3 * LtQg2;                                    // :446 / :516
-    if (!update) { out[r + j] = Pg2; continue; }
+    if (!update) {
+      out[r + j] = Pg2;
+    } else {
     const float iLiQtx2 = (iQtx2 - dotL) / l3;                              // :449
     const float iPx2 = iLiQtx2 / u3;                                        // :451
     a.v2[j] = Pg2;
@@ -381,6 +417,9 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
         mxU = fmaxf(mxU, fabsf(pg1[k] * dgj - dx1[k] * iPx2));              // grad2 of U   :470
       }
     }
+    }
+    }
+    if (update) tiles.release(j0);
   }
   if (!update) return;
   block_reduce_to<RM>(pc, r, a.partial, 0);
@@ -477,12 +516,12 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
     cL1[k] = ok ? st->cL1[k] : 0.f; cL2[k] = ok ? st->cL2[k] : 0.f;
     cU1[k] = ok ? st->cU1[k] : 0.f; cU2[k] = ok ? st->cU2[k] : 0.f;
   }
-  __shared__ float tile[kThreads * RM];
+  __shared__ float tile_mem[RowTiles<RM>::kFloats];
+  RowTiles<RM> tiles;
+  tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);
   for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
-    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
-    __syncthreads();
-    stage_rows<RM>(tile, L2, j0, rows, r, true, rho);
-    __syncthreads();
+    const int rows = tiles.rows_at(j0);
+    float* tile = tiles.acquire(j0);
     if ((int)threadIdx.x < rows) {
       const long long j = j0 + threadIdx.x;
       // all global loads of the row first: the stores to U2o below may alias U2 as far as the compiler knows, so inside
@@ -499,7 +538,7 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
 #pragma unroll
       for (int k = 0; k < RM; ++k) {
         if (k < r) {
-          const float l = tile[threadIdx.x * r + k];
+          const float l = tile[threadIdx.x * r + k] / rho;
           tile[threadIdx.x * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;       // :464
           const float u = rho * ucol[k];
           U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
@@ -518,6 +557,7 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
         if (e < cnt) po[e] = tile[e];
       }
     }
+    tiles.release(j0);
   }
 }
 
