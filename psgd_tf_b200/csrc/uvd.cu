@@ -3,17 +3,22 @@
 // Replaces the TensorFlow op sequences of update_precond_UVd_math_ (psgd.py:554-617),
 // precond_grad_UVd_math (psgd.py:619-627) and IpUVtmatvec (psgd.py:540-544).
 //
-// Design (DESIGN.md section "UVd"): every big operand is indexed by parameter row, so each call is a
-// short chain of bandwidth-bound sweeps separated by tiny r x r solves:
+// Design: every big operand is indexed by parameter row, so each call is a short chain of
+// bandwidth-bound sweeps separated by tiny r x r kernels.  What sets the byte count is how many global reductions gate
+// the element-wise maps.  All reductions over a = Qh = dh + U p and b = Q^-T v = w - V s1 are expanded through ONE Gram
+// table, so only max|nablaD| is left as a second dependency:
 //
-//   update:  sweep 1  (reduce)  G = [U V]^T [U V | d*h | v/d]              -> r-sized Grams/vectors
-//            small 1            p, t, s1, s2  (two r x r LU solves)
-//            sweep 2  (map+reduce) a=Qh, b=Q^-T v, nablaD per row; max|nablaD|, a.a, b.b, a.b, a^T V ...
-//            small 2            mu_d, mu, rank-2 coefficient vectors
-//            sweep 3  (map)     d -= mu_d d nablaD ;  U (or V) -= rank-2 update
-//   apply:   sweep A1 (reduce)  U^T U, U^T(d g), V^T(d g)
-//            small A
-//            sweep A2 (map)     out = d (y + V t),  y = d g + U p
+//   update (default, "uvd_fused" = 1):
+//            sweep 1  (reduce)     G = [U V dh w]^T [U V dh w]   (dh = d*h, w = v/d)
+//            small 1               p, t, s1, s2 (two r x r LU solves) AND the rank-2 step: a.a, b.b, a.b, a^T X, b^T X
+//                                  expanded through G, Frobenius normaliser, coefficient vectors
+//            sweep 2  (map)        a, b, nablaD per row; max|nablaD|; U (or V) -= rank-2 update, written back
+//            pass 3                d -= mu_d d nablaD
+//   update ("uvd_fused" = 0, cross-check): sweep 2 stores a, b, nablaD and reduces a.a, ... directly; small 2; sweep 3
+//            writes d and U (or V).
+//   apply:   sweep A1 (reduce)  U^T U, U^T(d g), V^T(d g);  small A;  sweep A2 (map)  out = d (y + V t),  y = d g + U p
+//   update+apply (psgd_uvd_update_apply): sweep 1 as above; sweep 2 also accumulates [U' V']^T [d g | d nablaD g] over the
+//            UPDATED rows (U'^T U' is expanded through G once more); small UA; sweep 3 = d update fused with A2.
 //
 // Sweeps stage row tiles in shared memory with TMA bulk copies (cp.async.bulk, mbarrier pipeline,
 // one producer lane per CTA) so every global access is a full-line coalesced transaction although
