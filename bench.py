@@ -445,22 +445,20 @@ def run_uvd(args, rank, world, local):
 # ---------------------------------------------------------------------------------------------
 # CPU baseline / reference arm: the oracle (port of the reference's TF op sequence) on host cores
 # ---------------------------------------------------------------------------------------------
-def _blas_threads():
-    try:
-        from threadpoolctl import threadpool_info
-        return max([int(p.get("num_threads", 1)) for p in threadpool_info()] or [1])
-    except Exception:
-        return os.cpu_count() or 1
+def _cpu_threads():
+    """Host threads the CPU legs use: torch's intra-op pool (OpenMP element-wise kernels, MKL GEMM)."""
+    import torch
+    return int(torch.get_num_threads())
 
 
-def _oracle_uvd_step(O, st, i):
+def _oracle_uvd_step(T, st, i):
     U, V, d, v, h, g = st
-    U, V, d = O.update_precond_UVd_math(U, V, d, v, h, 0.01, balance=(i % 100 == 99), update_U=(i % 2 == 0))
-    pre = O.precond_grad_UVd_math(U, V, d, g)
+    U, V, d = T.update_precond_UVd_math(U, V, d, v, h, 0.01, balance=(i % 100 == 99), update_U=(i % 2 == 0))
+    pre = T.precond_grad_UVd_math(U, V, d, g)
     return (U, V, d, v, h, g), pre
 
 
-def _uvd_host_state(n, r, n_total):
+def _uvd_host_state(n, r, n_total, as_torch=False):
     rng = np.random.default_rng(2024)
     uv = (1.0 / (n_total * r)) ** 0.5
     U = (rng.standard_normal((n, r), dtype=np.float32) * uv)
@@ -469,36 +467,51 @@ def _uvd_host_state(n, r, n_total):
     v = rng.standard_normal((n, 1), dtype=np.float32)
     h = ((0.5 + 1.5 * rng.random((n, 1), dtype=np.float32)) * v + 0.1 * rng.standard_normal((n, 1), dtype=np.float32)).astype(np.float32)
     g = rng.standard_normal((n, 1), dtype=np.float32)
-    return (U, V, d, v, h, g)
+    st = (U, V, d, v, h, g)
+    if as_torch:
+        import torch
+        st = tuple(torch.from_numpy(x) for x in st)
+    return st
+
+
+_CPU_PORT = ("multi-threaded torch-CPU port of psgd.py:554-627 (oracle/psgd_oracle_torch.py: the reference's op sequence on "
+             "ATen/OpenMP/MKL kernels, checked against the NumPy oracle; TensorFlow is not installable in this image)")
+
+
+def _time_cpu_uvd(n_total, r, budget_s, steps, warmup, cap_rows=20_000_000):
+    """Time the CPU port on a bounded row sample and scale linearly in N (every op of the path is O(N r^2))."""
+    from oracle import psgd_oracle_torch as T
+    st = _uvd_host_state(200_000, r, n_total, as_torch=True)
+    _oracle_uvd_step(T, st, 0)
+    t0 = time.perf_counter(); _oracle_uvd_step(T, st, 0); per_row = (time.perf_counter() - t0) / 200_000
+    n_s = int(min(n_total, cap_rows, max(200_000, budget_s / max(per_row, 1e-12) / max(steps + warmup, 1))))
+    st = _uvd_host_state(n_s, r, n_total, as_torch=True)
+    for i in range(warmup):
+        st, _ = _oracle_uvd_step(T, st, i)
+    t0 = time.perf_counter()
+    for i in range(steps):
+        st, pre = _oracle_uvd_step(T, st, warmup + i)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return dt, n_s
 
 
 def cpu_baseline_uvd(n_total, r, budget_s, steps, warmup):
-    """Time the oracle on a bounded row sample and scale linearly in N (every op of the path is O(N r^2))."""
-    from oracle import psgd_oracle as O
-    st = _uvd_host_state(200_000, r, n_total)
-    t0 = time.perf_counter(); _oracle_uvd_step(O, st, 0); per_row = (time.perf_counter() - t0) / 200_000
-    n_s = int(min(n_total, max(200_000, budget_s / max(per_row, 1e-12) / (steps + warmup))))
-    n_s = min(n_s, 20_000_000)
-    st = _uvd_host_state(n_s, r, n_total)
-    for i in range(warmup):
-        st, _ = _oracle_uvd_step(O, st, i)
-    t0 = time.perf_counter()
-    for i in range(steps):
-        st, pre = _oracle_uvd_step(O, st, warmup + i)
-    dt = (time.perf_counter() - t0) / steps
+    dt, n_s = _time_cpu_uvd(n_total, r, budget_s, steps, warmup)
     full = dt * (n_total / n_s)
-    return dict(value=round(1.0 / full, 5), unit=UNIT, cores=_blas_threads(), kind="port",
-                sample=f"oracle (NumPy float32 restatement of psgd.py:554-627) on {n_s:,} of {n_total:,} rows, "
-                       f"{steps} timed steps, {dt * 1e3:.0f} ms/step on the sample, scaled linearly to the full vector; "
-                       f"host has {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}",
+    return dict(value=round(1.0 / full, 5), unit=UNIT, cores=_cpu_threads(), kind="port",
+                sample=f"{_CPU_PORT} on {n_s:,} of {n_total:,} rows, {steps} timed steps, {dt * 1e3:.0f} ms/step on the "
+                       f"sample, scaled linearly to the full vector; host has {os.cpu_count()} logical cores, "
+                       f"{_cpu_threads()} threads used",
                 ms_per_step_sample=round(dt * 1e3, 2), sample_rows=n_s)
 
 
 def run_reference(args, rank, world):
     """--impl reference: the reference's own CPU implementation of the path.  TensorFlow is not installable in this
-    image (no network), so this is the oracle port, on all host threads NumPy/BLAS will use; rank 0 only."""
+    image (no network), so this is the op-for-op CPU port on all host threads; rank 0 only."""
     if rank != 0:
         return None
+    import torch
+    torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun pins OMP_NUM_THREADS=1 per rank; this arm is rank 0 alone
     n_total, r = args.n, args.rank
     if args.workload == "kron":
         return run_reference_kron(args)
@@ -509,59 +522,51 @@ def run_reference(args, rank, world):
         out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "config", "cpu_baseline", "e2e")}
         args.workload = "all"
         return out
-    from oracle import psgd_oracle as O
-    st = _uvd_host_state(200_000, r, n_total)
-    t0 = time.perf_counter(); _oracle_uvd_step(O, st, 0); per_row = (time.perf_counter() - t0) / 200_000
-    budget = 100.0
-    n_s = int(min(n_total, max(100_000, budget / max(per_row, 1e-12) / (args.steps + args.warmup)), 20_000_000))
-    st = _uvd_host_state(n_s, r, n_total)
-    for i in range(args.warmup):
-        st, _ = _oracle_uvd_step(O, st, i)
-    t0 = time.perf_counter()
-    for i in range(args.steps):
-        st, pre = _oracle_uvd_step(O, st, args.warmup + i)
-    dt = (time.perf_counter() - t0) / args.steps
+    dt, n_s = _time_cpu_uvd(n_total, r, 100.0, args.steps, args.warmup)
     full_ms = dt * 1e3 * (n_total / n_s)
     value = 1e3 / full_ms
-    sample = (f"oracle port (TensorFlow unavailable) on {n_s:,} of {n_total:,} rows per step, scaled linearly to the full "
-              f"vector; {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}")
+    sample = (f"{_CPU_PORT} on {n_s:,} of {n_total:,} rows per step, scaled linearly to the full vector; "
+              f"{os.cpu_count()} logical cores, {_cpu_threads()} threads used")
     return dict(impl="reference", metric=METRIC, value=round(value, 5), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(full_ms, 2), higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"UVd rank-{r} update+apply on a flattened {n_total:,}-parameter vector (BASELINE configs[3])",
                             n_params=n_total, rank=r),
-                cpu_baseline=dict(value=round(value, 5), unit=UNIT, cores=_blas_threads(), kind="port", sample=sample),
+                cpu_baseline=dict(value=round(value, 5), unit=UNIT, cores=_cpu_threads(), kind="port", sample=sample),
                 e2e=dict(value=round(value, 5), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 
 def run_reference_kron(args):
-    from oracle import psgd_oracle as O
+    import torch
+    from oracle import psgd_oracle_torch as T
     n = args.kron_n
     L = args.layers
-    rng = np.random.default_rng(1000)
+    gen = torch.Generator().manual_seed(1000)
     # bounded sample: one layer at reduced size, scaled by the cubic flop count (26 n^3 per layer-step)
-    ns = min(n, 1024)
-    Ql = np.eye(ns, dtype=np.float32); Qr = np.eye(ns, dtype=np.float32)
+    ns = min(n, 2048)
+    Ql = torch.eye(ns); Qr = torch.eye(ns)
+
     def one(Ql, Qr):
-        dX = rng.standard_normal((ns, ns), dtype=np.float32); dG = rng.standard_normal((ns, ns), dtype=np.float32)
-        G = rng.standard_normal((ns, ns), dtype=np.float32)
-        Ql, Qr = O.update_precond_kron(Ql, Qr, dX, dG, 0.01)
-        return Ql, Qr, O.precond_grad_kron(Ql, Qr, G)
+        dX = torch.randn(ns, ns, generator=gen); dG = torch.randn(ns, ns, generator=gen)
+        G = torch.randn(ns, ns, generator=gen)
+        Ql, Qr = T.update_precond_dense_dense(Ql, Qr, dX, dG, 0.01)
+        return Ql, Qr, T.precond_grad_dense_dense(Ql, Qr, G)
     for _ in range(args.warmup):
         Ql, Qr, _p = one(Ql, Qr)
     t0 = time.perf_counter()
     for _ in range(args.steps):
         Ql, Qr, _p = one(Ql, Qr)
-    dt = (time.perf_counter() - t0) / args.steps
+    dt = (time.perf_counter() - t0) / max(args.steps, 1)
     full = dt * (n / ns) ** 3 * L
     value = 1.0 / full
-    sample = (f"oracle port (TensorFlow unavailable): one {ns}x{ns} dense-dense layer per step, scaled by (n/{ns})^3 x {L} "
-              f"layers; {os.cpu_count()} logical cores, BLAS threads = {_blas_threads()}")
+    sample = (f"multi-threaded torch-CPU port of psgd.py:156-192 (oracle/psgd_oracle_torch.py; TensorFlow unavailable): one "
+              f"{ns}x{ns} dense-dense layer per step ({dt * 1e3:.0f} ms), scaled by (n/{ns})^3 x {L} layers; "
+              f"{os.cpu_count()} logical cores, {_cpu_threads()} threads used")
     return dict(impl="reference", metric=METRIC, value=round(value, 6), unit=UNIT, n_gpus=1, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(full * 1e3, 1), higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32", data="synthetic",
                 config=dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply (BASELINE configs[2])"),
-                cpu_baseline=dict(value=round(value, 6), unit=UNIT, cores=_blas_threads(), kind="port", sample=sample),
+                cpu_baseline=dict(value=round(value, 6), unit=UNIT, cores=_cpu_threads(), kind="port", sample=sample),
                 e2e=dict(value=round(value, 6), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 

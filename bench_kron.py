@@ -223,26 +223,10 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
 
 
-def cpu_baseline_kron(L, n, ns=1024, steps=2):
-    from oracle import psgd_oracle as O
-    from bench import _blas_threads, UNIT
-    rng = np.random.default_rng(1000)
-    ns = min(ns, n)
-    Ql = np.eye(ns, dtype=np.float32); Qr = np.eye(ns, dtype=np.float32)
-
-    def one(Ql, Qr):
-        dX = rng.standard_normal((ns, ns), dtype=np.float32); dG = rng.standard_normal((ns, ns), dtype=np.float32)
-        G = rng.standard_normal((ns, ns), dtype=np.float32)
-        Ql, Qr = O.update_precond_kron(Ql, Qr, dX, dG, 0.01)
-        return Ql, Qr, O.precond_grad_kron(Ql, Qr, G)
-
-    Ql, Qr, _ = one(Ql, Qr)
-    t0 = time.perf_counter()
-    for _ in range(steps):
-        Ql, Qr, _ = one(Ql, Qr)
-    dt = (time.perf_counter() - t0) / steps
-    full = dt * (n / ns) ** 3 * L
-    return dict(value=round(1.0 / full, 6), unit=UNIT, cores=_blas_threads(), kind="port",
-                sample=f"oracle (NumPy/SciPy float32 restatement of psgd.py:156-192) on one {ns}x{ns} layer, {steps} timed "
-                       f"steps ({dt * 1e3:.0f} ms each), scaled by (n/{ns})^3 x {L} layers; host has {os.cpu_count()} logical "
-                       f"cores, BLAS threads = {_blas_threads()}")
+def cpu_baseline_kron(L, n, ns=2048, steps=2):
+    """The CPU port (multi-threaded torch-CPU restatement of psgd.py:156-192) on one reduced layer, scaled by the cubic
+    flop count -- the same sample `bench.py --impl reference --workload kron` times."""
+    import argparse
+    from bench import run_reference_kron
+    r = run_reference_kron(argparse.Namespace(kron_n=n, layers=L, steps=steps, warmup=1, scaling="strong"))
+    return r["cpu_baseline"]

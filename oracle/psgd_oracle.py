@@ -3,7 +3,8 @@
 This is an op-for-op NumPy restatement of the reference module
 ``/root/reference/preconditioned_stochastic_gradient_descent.py`` (called
 ``psgd.py`` below).  Only ``tests/``, ``__graft_entry__.smoke()`` and the
-``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it; the
+``cpu_baseline`` / ``--impl reference`` legs of ``bench.py`` may import it (those legs time its multi-threaded
+torch-CPU twin, ``psgd_oracle_torch.py``, which ``tests/test_oracle_torch.py`` checks against this file); the
 product package ``psgd_tf_b200`` never does.
 
 Pin status.  PINNED AT SOURCE LEVEL, UNPINNED AT TENSORFLOW-KERNEL LEVEL: the reference ships no tests
