@@ -62,3 +62,23 @@ def test_product_package_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dp, f)).read()
                 assert not pat.search(src), f"{f} references the oracle"
+
+
+def test_uvd_gram_plan_geometry_fits_the_sm_for_every_rank():
+    """psgd_uvd_plan_info (no GPU needed): the update Gram sweep's pipeline geometry per rank stays launchable on sm_100
+    (<= 1024 threads, >= 4 stages of whole-warp row tiles inside the 160 KB ring + static tables under 227 KB)."""
+    import ctypes as C
+    from psgd_tf_b200 import _lib
+    lib = _lib.load_library()
+    for r in range(1, 17):
+        tile, stages, threads, roles = (C.c_int() for _ in range(4))
+        assert lib.psgd_uvd_plan_info(r, C.byref(tile), C.byref(stages), C.byref(threads), C.byref(roles)) == 0
+        assert tile.value % 32 == 0 and tile.value >= 32
+        assert 4 <= stages.value <= 8
+        assert threads.value % 32 == 0 and 64 <= threads.value <= 1024
+        assert 1 <= roles.value <= 9
+        ring = stages.value * tile.value * 4 * (2 * r + 3)
+        assert ring <= 160 * 1024
+        table = (2 * r + 2) ** 2 * 4 * 8                      # per-warp-in-role tables (static shared memory), upper bound
+        assert ring + table <= 227 * 1024
+    assert lib.psgd_uvd_plan_info(17, C.byref(tile), C.byref(stages), C.byref(threads), C.byref(roles)) != 0
