@@ -48,3 +48,23 @@ def test_two_sweep_update_tracks_oracle_over_a_trajectory():
         U, V, d = M.update(U, V, d, v, h, 0.01, uu)
         Ur, Vr, dr = O.update_precond_UVd_math(Ur, Vr, dr, v, h, 0.01, balance=False, update_U=uu)
     assert cases.rel_err(U, Ur) < 1e-4 and cases.rel_err(V, Vr) < 1e-4 and cases.rel_err(d, dr) < 1e-4
+
+
+def test_expansion_holds_over_random_shapes_and_scales():
+    """Property check (hypothesis): for random N, r, factor scales and d ranges the Gram-table expansion reproduces the
+    oracle's update + apply to float32 round-off, on both branches."""
+    from hypothesis import given, settings, strategies as st
+
+    @settings(max_examples=40, deadline=None)
+    @given(n=st.integers(2, 3000), r=st.integers(1, 16), scale=st.sampled_from([0.1, 1.0, 10.0, 50.0]),
+           dlo=st.sampled_from([0.05, 0.5, 2.0]), update_U=st.booleans(), seed=st.integers(0, 10_000))
+    def check(n, r, scale, dlo, update_U, seed):
+        c = cases.uvd_case(seed, n, r, scale=scale)
+        d = (dlo * (1.0 + np.random.default_rng(seed).random((n, 1)))).astype(np.float32)
+        Ur, Vr, dr = O.update_precond_UVd_math(c["U"], c["V"], d, c["v"], c["h"], 0.01, balance=False, update_U=update_U)
+        pr = O.precond_grad_UVd_math(Ur, Vr, dr, c["g"])
+        U, V, dn, pre = M.update_apply(c["U"], c["V"], d, c["v"], c["h"], c["g"], 0.01, update_U)
+        for got, want in ((U, Ur), (V, Vr), (dn, dr), (pre, pr)):
+            assert cases.rel_err(got, want) < 5e-6
+
+    check()
