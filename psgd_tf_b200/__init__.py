@@ -18,7 +18,7 @@ from .psgd import (  # noqa: F401
     IpUVtmatvec, update_precond_UVd_math_, precond_grad_UVd_math,
     update_precond_UVd, precond_grad_UVd, update_precond_and_grad_UVd,
     update_precond_diag, precond_grad_diag, update_precond_Xmat, precond_grad_Xmat,
-    UVd, apply_preconditioned_updates, grad_differences,
+    UVd, apply_preconditioned_updates, grad_differences, MAX_UVD_RANK, MAX_SPLU_RANK,
 )
 from ._lib import PsgdError  # noqa: F401
 

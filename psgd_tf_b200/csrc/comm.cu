@@ -55,10 +55,24 @@ __device__ __forceinline__ unsigned long long globaltimer_ns() {
   return t;
 }
 
-// sum_buf: n_sum float64 partial sums (in place), max_buf: n_max non-negative float maxima (in place)
+// sum_buf: n_sum float64 partial sums (in place), max_buf: n_max non-negative float maxima (in place).
+// A peer that does not publish within kTimeoutNs makes the exchange FAIL, not degrade: the error is sticky in the slab
+// and mirrored to a host-mapped word (every later library call that needs an exchange returns PSGD_ERR_COMM without
+// a synchronisation), and this and all later exchanges hand NaNs to the consuming sweeps, so that no rank can go on
+// updating U, V, d or the parameters from stale or partial sums.
 __global__ void __launch_bounds__(256) exchange_kernel(Peers peers, int rank, int world, double* __restrict__ sum_buf,
-                                                       int n_sum, float* __restrict__ max_buf, int n_max) {
+                                                       int n_sum, float* __restrict__ max_buf, int n_max,
+                                                       unsigned int* __restrict__ host_err,
+                                                       unsigned long long timeout_ns) {
   Slab* mine = peers.slab[rank];
+  __shared__ unsigned int s_failed;
+  if (threadIdx.x == 0) s_failed = mine->head.error;
+  __syncthreads();
+  if (s_failed) {                               // sticky: an earlier exchange timed out
+    for (int k = threadIdx.x; k < n_sum; k += blockDim.x) sum_buf[k] = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = threadIdx.x; k < n_max; k += blockDim.x) max_buf[k] = __int_as_float(0x7fc00000);
+    return;
+  }
   const unsigned long long e = mine->head.epoch + 1;   // only this kernel writes it, and kernels of a stream are ordered
   const int par = (int)(e & 1);
   // 1. push
@@ -74,13 +88,20 @@ __global__ void __launch_bounds__(256) exchange_kernel(Peers peers, int rank, in
     st_release_sys(&peers.slab[threadIdx.x]->flags[par][rank], e);
     const unsigned long long t0 = globaltimer_ns();
     while (ld_acquire_sys(&mine->flags[par][threadIdx.x]) < e) {
-      if (globaltimer_ns() - t0 > kTimeoutNs) {
+      if (globaltimer_ns() - t0 > timeout_ns) {
         mine->head.error = 1;
+        s_failed = 1;
+        if (host_err) { *host_err = 1; __threadfence_system(); }
         break;
       }
     }
   }
   __syncthreads();
+  if (s_failed) {
+    for (int k = threadIdx.x; k < n_sum; k += blockDim.x) sum_buf[k] = __longlong_as_double(0x7ff8000000000000ll);
+    for (int k = threadIdx.x; k < n_max; k += blockDim.x) max_buf[k] = __int_as_float(0x7fc00000);
+    return;
+  }
   // 4. fixed-order reduction: identical bits on every rank
   for (int k = threadIdx.x; k < n_sum; k += blockDim.x) {
     double s = 0.0;
@@ -100,6 +121,8 @@ struct State {
   int rank = 0, world = 0;
   Slab* local = nullptr;
   Peers peers{};
+  unsigned int* host_err = nullptr;       // host-mapped (cudaHostAlloc): set by the kernel when a wait timed out
+  unsigned int* host_err_dev = nullptr;   // its device alias
 };
 
 }  // namespace comm
@@ -111,8 +134,15 @@ int cross_rank_reduce(psgd_ctx* ctx, double* sum_buf, int n_sum, float* max_buf,
     auto* st = static_cast<comm::State*>(ctx->comm);
     PSGD_REQUIRE(n_sum <= comm::kMaxSum && n_max <= comm::kMaxMax, PSGD_ERR_COMM,
                  "peer exchange: %d sums / %d maxima exceed the slab (%d / %d)", n_sum, n_max, comm::kMaxSum, comm::kMaxMax);
+    PSGD_REQUIRE(!st->host_err || *static_cast<volatile unsigned int*>(st->host_err) == 0, PSGD_ERR_COMM,
+                 "peer exchange: an earlier exchange timed out (a rank did not publish its partials within %llu s); "
+                 "the sharded state is invalid",
+                 comm::kTimeoutNs / 1000000000ull);
     ProfScope prof(ctx, PSGD_K_EXCHANGE);
-    comm::exchange_kernel<<<1, 256, 0, ctx->stream>>>(st->peers, st->rank, st->world, sum_buf, n_sum, max_buf, n_max);
+    comm::exchange_kernel<<<1, 256, 0, ctx->stream>>>(st->peers, st->rank, st->world, sum_buf, n_sum, max_buf, n_max,
+                                                      st->host_err_dev,
+                                                      ctx->opt_comm_timeout_ms > 0 ? (unsigned long long)ctx->opt_comm_timeout_ms * 1000000ull
+                                                                                   : comm::kTimeoutNs);
     PSGD_LAUNCH_CHECK(ctx);
     return PSGD_OK;
   }
@@ -145,6 +175,11 @@ extern "C" int psgd_comm_export(psgd_ctx* ctx, void* handle_out) {
     PSGD_CUDA_CHECK(cudaMalloc(&st->local, sizeof(comm::Slab)));
   }
   PSGD_CUDA_CHECK(cudaMemset(st->local, 0, sizeof(comm::Slab)));
+  if (!st->host_err) {
+    PSGD_CUDA_CHECK(cudaHostAlloc(reinterpret_cast<void**>(&st->host_err), sizeof(unsigned int), cudaHostAllocMapped));
+    PSGD_CUDA_CHECK(cudaHostGetDevicePointer(reinterpret_cast<void**>(&st->host_err_dev), st->host_err, 0));
+  }
+  *st->host_err = 0;
   PSGD_CUDA_CHECK(cudaDeviceSynchronize());
   cudaIpcMemHandle_t h;
   PSGD_CUDA_CHECK(cudaIpcGetMemHandle(&h, st->local));
@@ -191,6 +226,7 @@ extern "C" int psgd_comm_detach(psgd_ctx* ctx) {
   for (int p = 0; p < st->world; ++p)
     if (p != st->rank && st->peers.slab[p]) cudaIpcCloseMemHandle(st->peers.slab[p]);
   if (st->local) cudaFree(st->local);
+  if (st->host_err) cudaFreeHost(st->host_err);
   delete st;
   ctx->comm = nullptr;
   ctx->comm_world = 0;

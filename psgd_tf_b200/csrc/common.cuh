@@ -4,6 +4,7 @@
 
 #include <cuda_runtime.h>
 #include <stdint.h>
+#include <atomic>
 #include <stdio.h>
 #include <string>
 #include <vector>
@@ -43,6 +44,15 @@ void set_error(const char* fmt, ...);
 
 static inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
 
+// Function attributes (the > 48 KB dynamic shared-memory opt-in) are PER DEVICE, and contexts exist per (thread,
+// device): a call site remembers the devices it has configured in a bit mask (atomic: contexts of different threads
+// may race here; setting an attribute twice is harmless).
+struct DeviceOnce {
+  std::atomic<unsigned long long> mask{0};
+  bool done(int device) const { return device >= 0 && device < 64 && ((mask.load(std::memory_order_acquire) >> device) & 1ull); }
+  void set(int device) { if (device >= 0 && device < 64) mask.fetch_or(1ull << device, std::memory_order_release); }
+};
+
 }  // namespace psgd
 
 // ---------------------------------------------------------------------------------------------
@@ -64,6 +74,7 @@ struct psgd_ctx {
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
   int opt_tc_mode = 1;       // tcgen05 GEMM A operand: 1 = through tensor memory (TS), 0 = from shared memory (SS)
+  int opt_comm_timeout_ms = 0;   // peer exchange: wait limit per exchange (0 = the 20 s default)
   int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks
   psgd_allreduce_fn allreduce = nullptr;
   void* allreduce_user = nullptr;

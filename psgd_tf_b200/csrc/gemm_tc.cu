@@ -85,6 +85,10 @@ struct Params {
   const float* D[kMaxGroup];
   const float* mu_max[kMaxGroup];
   const float* colscale[kMaxGroup];
+  const int* a_full[kMaxGroup];   // run-time "operand is not triangular after all" flags (nullptr: hint valid)
+  const int* b_full[kMaxGroup];
+  const float* rho[kMaxGroup];    // rho_mode 1: C / *rho, 2: C * *rho
+  int rho_mode;
 };
 
 // ---------------------------------------------------------------------------------------------
@@ -262,16 +266,19 @@ __host__ __device__ __forceinline__ bool tile_computed(const Params& p, int m0, 
 
 // K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
 template <int BN>
-__host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1) {
+__host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1,
+                                                 int full = 0) {
   const int K = p.K[prod];
   int lo = 0, hi = K;
   auto up = [](int& v, int x) { if (x > v) v = x; };
   auto down = [](int& v, int x) { if (x < v) v = x; };
   if (prod == 0) {
-    if (p.a_tri == 1) up(lo, m0);                       // op(A)[m,k] = 0 for k < m
-    if (p.a_tri == 2) down(hi, m0 + BM);                // op(A)[m,k] = 0 for k > m
-    if (p.b_tri == 1) down(hi, n0 + BN);                // op(B)[k,n] = 0 for k > n
-    if (p.b_tri == 2) up(lo, n0);                       // op(B)[k,n] = 0 for k < n
+    // full: bit 0 = drop the hint on A, bit 1 = drop the hint on B (the factor turned out not to be triangular)
+    const int a_tri = (full & 1) ? 0 : p.a_tri, b_tri = (full & 2) ? 0 : p.b_tri;
+    if (a_tri == 1) up(lo, m0);                         // op(A)[m,k] = 0 for k < m
+    if (a_tri == 2) down(hi, m0 + BM);                  // op(A)[m,k] = 0 for k > m
+    if (b_tri == 1) down(hi, n0 + BN);                  // op(B)[k,n] = 0 for k > n
+    if (b_tri == 2) up(lo, n0);                         // op(B)[k,n] = 0 for k < n
     if (p.pair_b) {
       const int base = (p.pair_kind == 1 ? n0 : m0) / p.pair_b * p.pair_b;
       up(lo, base);
@@ -300,6 +307,17 @@ __global__ void __launch_bounds__(kThreads, 1)
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
+  // per-problem run-time flags that cancel the triangular K-range hints (every role derives the same K ranges from them)
+  __shared__ int s_full[kMaxGroup];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kMaxGroup) {
+    const int g = threadIdx.x - 64;
+    int f = 0;
+    if (g < p.count) {
+      if (p.a_full[g] && *p.a_full[g]) f |= 1;
+      if (p.b_full[g] && *p.b_full[g]) f |= 2;
+    }
+    s_full[g] = f;
+  }
   if (threadIdx.x == 0) {
     for (int s = 0; s < C::kStages; ++s) {
       mbar_init(&full[s], 1);
@@ -336,7 +354,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
-          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
           const CUtensorMap* ma = prod ? &maps.a1[grp] : &maps.a0[grp];
           const CUtensorMap* mb = prod ? &maps.b1[grp] : &maps.b0[grp];
           for (int kb = kb0; kb < kb1; ++kb, ++it) {
@@ -378,7 +396,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
-          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
           total_kb += kb1 - kb0;
         }
         if (total_kb == 0) continue;                      // epilogue writes zeros without touching TMEM
@@ -392,7 +410,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
-          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
           // product 1 is subtracted (a_negate); an A operand in TMEM is always K-major (the splitter transposes)
           const uint32_t idesc = make_idesc(BN, TS ? 0 : p.a_mn[prod], p.b_mn[prod], prod);
           // descriptors of K atom kk = descriptor of atom 0 + kk * step (start-address field, 16-byte units)
@@ -461,7 +479,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       for (int prod = 0; prod < 2; ++prod) {
         if (p.K[prod] <= 0) continue;
         int kb0, kb1;
-        k_range<BN>(p, prod, m0, n0, kb0, kb1);
+        k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
         for (int kb = kb0; kb < kb1; ++kb, ++it) {
           const int s = it % C::kStages;
           const uint32_t ph = (it / C::kStages) & 1;
@@ -555,12 +573,13 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float* const csg = p.colscale[grp];
       float mu = 0.f;
       if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
+      const float rho = p.rho_mode ? *p.rho[grp] : 1.0f;
       int total_kb = 0;
       if (!(p.triu && m0 >= n0 + BN)) {
         for (int prod = 0; prod < 2; ++prod) {
           if (p.K[prod] <= 0) continue;
           int kb0, kb1;
-          k_range<BN>(p, prod, m0, n0, kb0, kb1);
+          k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
           total_kb += kb1 - kb0;
         }
       }
@@ -604,6 +623,8 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             if (p.triu && m > n) x = 0.f;
             if (drow && n < p.N) x = drow[j] - mu * x;
+            if (p.rho_mode == 1) x = x / rho;
+            else if (p.rho_mode == 2) x = x * rho;
             if (n < p.N) mx = fmaxf(mx, fabsf(x));
             v[j] = x;
           }
@@ -678,7 +699,8 @@ static bool same_shape(const la::Gemm& x, const la::Gemm& y) {
          x.tb2 == y.tb2 && x.triu == y.triu && x.a_tri == y.a_tri && x.b_tri == y.b_tri && x.step == y.step &&
          x.tiny == y.tiny && x.colscale_recip == y.colscale_recip && x.colscale_sq == y.colscale_sq &&
          (x.D != nullptr) == (y.D != nullptr) && (x.K2 > 0) == (y.K2 > 0) && x.pair_b == y.pair_b &&
-         x.pair_kind == y.pair_kind && x.negate == y.negate;
+         x.pair_kind == y.pair_kind && x.negate == y.negate && x.rho_mode == y.rho_mode &&
+         (x.a_full != nullptr) == (y.a_full != nullptr) && (x.b_full != nullptr) == (y.b_full != nullptr);
 }
 
 // gs[0..count): identical shapes/flags, count <= kMaxGroup
@@ -706,10 +728,12 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   p.count = count;
   p.debug = ctx->opt_tc_debug;
   p.pair_b = g.pair_b; p.pair_kind = g.pair_kind; p.negate = g.negate ? 1 : 0;
+  p.rho_mode = g.rho ? g.rho_mode : 0;
   double work = 0.0;
   for (int i = 0; i < count; ++i) {
     const la::Gemm& q = gs[i];
     p.C[i] = q.C; p.maxabs[i] = q.maxabs; p.D[i] = q.D; p.mu_max[i] = q.mu_max; p.colscale[i] = q.colscale;
+    p.a_full[i] = q.a_full; p.b_full[i] = q.b_full; p.rho[i] = q.rho;
     work += 2.0 * q.M * q.N * ((double)q.K + q.K2);
     for (int prod = 0; prod < 2; ++prod) {
       const float* A = prod ? q.A2 : q.A;
@@ -726,10 +750,10 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
     }
   }
   auto kern = gemm_tc_kernel<BN, TS>;
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;             // one per template instantiation
+  if (!attr_done.done(ctx->device)) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
-    attr_done = true;
+    attr_done.set(ctx->device);
   }
   int grid = p.tiles_m * p.tiles_n * count;
   if (grid > ctx->num_sms) grid = ctx->num_sms;
@@ -855,10 +879,10 @@ __global__ void __launch_bounds__(kInvBlock) tri_inv_blocks_kernel(const __grid_
 static int invert_diag_blocks(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int n, int ldz) {
   const int blocks = (n + kInvBlock - 1) / kInvBlock;
   const size_t smem = 2 * (size_t)kInvBlock * (kInvBlock + 1) * sizeof(float);
-  static bool attr_done = false;
-  if (!attr_done) {
+  static DeviceOnce attr_done;
+  if (!attr_done.done(ctx->device)) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(tri_inv_blocks_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    attr_done = true;
+    attr_done.set(ctx->device);
   }
   for (int t0 = 0; t0 < count; t0 += kInvBatch) {
     const int cnt = count - t0 < kInvBatch ? count - t0 : kInvBatch;

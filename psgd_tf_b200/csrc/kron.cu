@@ -54,6 +54,69 @@ __global__ void __launch_bounds__(256) balance_kernel(int kind_l, const float* Q
   }
 }
 
+// ---- grouped forms for dense factors: one launch for all layers of a group --------------------------------------
+constexpr int kPrepBatch = 64;          // layers per launch (pointers travel as kernel parameters)
+struct PrepBatch {
+  const float* Ql[kPrepBatch];
+  const float* Qr[kPrepBatch];
+  Scal* sc[kPrepBatch];
+  int* fl[kPrepBatch];                  // "factor is not upper triangular" flags (nullptr: not scanned)
+  int* fr[kPrepBatch];
+};
+
+// grid = layers: maxima, rho and zeroed step maxima of every layer (balance_kernel for a whole group).  The rescaled
+// copies Ql/rho, rho*Qr are NOT formed for (dense, dense) pairs: rho cancels in A = Ql dG Qr^T and in
+// Bt = Ql^-T dX Qr^-1, so it only scales the returned factors and rides in the epilogue of the last product.
+__global__ void __launch_bounds__(256) balance_many_kernel(const __grid_constant__ PrepBatch b, int kind_l, int nl,
+                                                            int kind_r, int nr) {
+  const int l = blockIdx.x;
+  const float ml = factor_max(kind_l, b.Ql[l], nl);
+  const float mr = factor_max(kind_r, b.Qr[l], nr);
+  if (threadIdx.x == 0) {
+    Scal* sc = b.sc[l];
+    sc->max_l = ml; sc->max_r = mr;
+    sc->rho = sqrtf(ml / mr);
+    sc->max1 = 0.f; sc->max2 = 0.f;
+  }
+}
+
+// grid = (row chunks, 2 x layers): flag = 1 when the strictly lower triangle of a dense factor holds anything but
+// zeros.  The tensor-core products skip the K blocks that an upper-triangular factor leaves structurally zero; a
+// caller may hand over ANY square matrix (tf.matmul multiplies all of it, psgd.py:173), and then the flag cancels
+// the hint inside the GEMM kernel.  Reads n^2/2 floats per factor: 0.25 ms for the 48 factors of the 24 x 4096^2 stack.
+constexpr int kScanRows = 32;
+__global__ void __launch_bounds__(kPrepBatch) zero_flags_kernel(const __grid_constant__ PrepBatch b) {
+  if (b.fl[threadIdx.x]) *b.fl[threadIdx.x] = 0;
+  if (b.fr[threadIdx.x]) *b.fr[threadIdx.x] = 0;
+}
+__global__ void __launch_bounds__(256) tri_scan_kernel(const __grid_constant__ PrepBatch b, int nl, int nr) {
+  const int l = blockIdx.y >> 1, side = blockIdx.y & 1;
+  int* flag = side ? b.fr[l] : b.fl[l];
+  if (!flag) return;
+  const float* __restrict__ Q = side ? b.Qr[l] : b.Ql[l];
+  const int n = side ? nr : nl;
+  const int r0 = blockIdx.x * kScanRows;
+  if (r0 >= n) return;
+  const int r1 = min(n, r0 + kScanRows);
+  const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15u) == 0;
+  int any = 0;
+  for (int i = max(r0, 1); i < r1; ++i) {
+    const float* row = Q + (size_t)i * n;
+    int j0 = 0;
+    if (vec) {
+      const int n4 = i >> 2;
+      const float4* row4 = reinterpret_cast<const float4*>(row);
+      for (int j = threadIdx.x; j < n4; j += 256) {
+        const float4 v = row4[j];
+        any |= (v.x != 0.f) | (v.y != 0.f) | (v.z != 0.f) | (v.w != 0.f);
+      }
+      j0 = n4 << 2;
+    }
+    for (int j = j0 + threadIdx.x; j < i; j += 256) any |= (row[j] != 0.f);
+  }
+  if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
+}
+
 // Both factors structured (normalization / scaling: a few thousand floats): maxima, rho and both rescaled copies in ONE
 // single-CTA launch instead of three (the update of such a pair is launch-latency bound at NMT sizes).
 constexpr int64_t kBalanceSmallMax = 65536;
@@ -291,9 +354,20 @@ constexpr int kUpper = 1, kLower = 2;
 // Q - triu(.) Q), which lets the tensor-core engine skip structurally zero K blocks.  The hints
 // are dropped with psgd_set_option(ctx, "assume_triangular", 0) for callers that feed arbitrary square matrices.
 // All layers of a group share shapes, so each op of the reference's sequence is ONE (grouped) launch over the group.
-static int gemm_all(psgd_ctx* ctx, std::vector<la::Gemm>& gs, int a_tri = 0, int b_tri = 0) {
+// a_src / b_src say which caller-supplied factor a hint rests on (kFromL / kFromR: gs[i] belongs to (*Ls)[i], whose
+// run-time flag cancels the hint inside the kernel when that factor is not triangular); 0 = triangular by construction.
+constexpr int kFromL = 1, kFromR = 2;
+struct Layer;
+static const int* flag_of(const Layer& L, int src);
+static int gemm_all(psgd_ctx* ctx, std::vector<la::Gemm>& gs, int a_tri = 0, int b_tri = 0,
+                    const std::vector<Layer>* Ls = nullptr, int a_src = 0, int b_src = 0) {
   if (ctx->opt_assume_tri)
-    for (auto& g : gs) { g.a_tri = a_tri; g.b_tri = b_tri; }
+    for (size_t i = 0; i < gs.size(); ++i) {
+      la::Gemm& g = gs[i];
+      g.a_tri = a_tri; g.b_tri = b_tri;
+      if (Ls && a_src) g.a_full = flag_of((*Ls)[i], a_src);
+      if (Ls && b_src) g.b_full = flag_of((*Ls)[i], b_src);
+    }
   return tc::gemm_many(ctx, gs.data(), (int)gs.size(), false);
 }
 
@@ -310,7 +384,36 @@ struct Layer {
   float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv, *xwork;
   float *t1, *t2, *t3, *P, *addlast;
   float* nspart;   // (normalization, scaling): partial tables of the fused streaming kernels
+  int *fl, *fr;    // run-time "dense factor is not upper triangular" flags (nullptr: no scan, hints taken as given)
 };
+
+static const int* flag_of(const Layer& L, int src) { return src == kFromL ? L.fl : (src == kFromR ? L.fr : nullptr); }
+
+// Dense factors whose products may run on the tensor cores with triangular K-range hints get a run-time check.
+static bool wants_scan(const psgd_ctx* ctx, int kind, int n) {
+  return kind == PSGD_FACTOR_DENSE && ctx->opt_assume_tri && ctx->opt_gemm_path != 1 && (ctx->opt_gemm_path == 2 || n >= 256);
+}
+
+// flags of one group: zeroed, then set by tri_scan_kernel (one launch per kPrepBatch layers)
+static int scan_group(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N);
+
+static int scan_group(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N) {
+  if (Ls.empty() || (!Ls[0].fl && !Ls[0].fr)) return PSGD_OK;
+  const int nmax = M > N ? M : N;
+  for (size_t t0 = 0; t0 < Ls.size(); t0 += kPrepBatch) {
+    const int cnt = (int)std::min<size_t>(kPrepBatch, Ls.size() - t0);
+    PrepBatch b{};
+    for (int t = 0; t < cnt; ++t) {
+      const Layer& L = Ls[t0 + t];
+      b.Ql[t] = L.Ql; b.Qr[t] = L.Qr; b.fl[t] = L.fl; b.fr[t] = L.fr;
+    }
+    zero_flags_kernel<<<1, kPrepBatch, 0, ctx->stream>>>(b);
+    PSGD_LAUNCH_CHECK(ctx);
+    tri_scan_kernel<<<dim3((nmax + kScanRows - 1) / kScanRows, 2 * cnt), 256, 0, ctx->stream>>>(b, M, N);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
 
 static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const float* B, int ldb, bool tb, float* C,
                    int ldc) {
@@ -324,18 +427,32 @@ static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const 
 // ---------------------------------------------------------------------------------------------
 static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
   const size_t MN = (size_t)M * N;
-  size_t f = 64 + fsize(kl, M) + fsize(kr, N) + 4 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
+  const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;     // no rescaled factor copies (carve_update)
+  size_t f = 64 + (dd ? 0 : fsize(kl, M) + fsize(kr, N)) + 4 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
              2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
   f += tc::trsm_scratch_floats((int)(M > N ? M : N));
   if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) f += ks::ns_update_scratch_floats((int)M, (int)N) + 64;
   return f;
 }
 
-static void carve_update(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
+static void carve_flags(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
+  int* f = c.take<int>(2);
+  L.fl = wants_scan(ctx, kl, M) ? f : nullptr;
+  L.fr = wants_scan(ctx, kr, N) ? f + 1 : nullptr;
+}
+
+static void carve_update(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
   const size_t MN = (size_t)M * N;
   L.sc = c.take<Scal>(1);
-  L.Qlb = c.take<float>(fsize(kl, M));
-  L.Qrb = c.take<float>(fsize(kr, N));
+  carve_flags(ctx, c, L, kl, kr, M, N);
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
+    // (dense, dense): no rescaled copies, rho rides in the epilogue of the last products (see balance_many_kernel)
+    L.Qlb = const_cast<float*>(L.Ql);
+    L.Qrb = const_cast<float*>(L.Qr);
+  } else {
+    L.Qlb = c.take<float>(fsize(kl, M));
+    L.Qrb = c.take<float>(fsize(kr, N));
+  }
   L.A = c.take<float>(MN);
   L.Bt = c.take<float>(MN);
   L.T1 = c.take<float>(MN);
@@ -362,7 +479,16 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
 
   // ---- balance: Ql /= rho, Qr *= rho                          psgd.py:166-170, :211-215, :288-292, :342-346
   const bool small_pair = kl != PSGD_FACTOR_DENSE && kr != PSGD_FACTOR_DENSE && cl + cr <= kBalanceSmallMax;
+  const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;
+  for (size_t t0 = 0; dd && t0 < Ls.size(); t0 += kPrepBatch) {          // (dense, dense): ONE launch per group
+    const int cnt = (int)std::min<size_t>(kPrepBatch, Ls.size() - t0);
+    PrepBatch b{};
+    for (int t = 0; t < cnt; ++t) { b.Ql[t] = Ls[t0 + t].Ql; b.Qr[t] = Ls[t0 + t].Qr; b.sc[t] = Ls[t0 + t].sc; }
+    balance_many_kernel<<<cnt, 256, 0, st>>>(b, kl, M, kr, N);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
   for (auto& L : Ls) {
+    if (dd) break;
     if (small_pair) {
       balance_rescale_small_kernel<<<1, 1024, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, cl, cr, L.Qlb, L.Qrb, L.sc);
       PSGD_LAUNCH_CHECK(ctx);
@@ -375,15 +501,16 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, st>>>(L.Qr, L.Qrb, cr, L.sc, 0);
     PSGD_LAUNCH_CHECK(ctx);
   }
+  PSGD_RETURN_IF(scan_group(ctx, Ls, M, N));
 
   // ---- A = Ql dG Qr^T  and  Bt = Ql^-T dX Qr^-1 ------------------------------------------------
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
     gs.clear();                                                          // T1 = dG Qr^T            psgd.py:173
     for (auto& L : Ls) gs.push_back(mk(M, N, N, L.dG, N, false, L.Qrb, N, true, L.T1, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
     gs.clear();                                                          // A = Ql T1
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Qlb, M, false, L.T1, N, false, L.A, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
     ts.clear();                                                          // W = dX Qr^-1            psgd.py:174
     for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.T1, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
@@ -397,7 +524,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     }
     gs.clear();                                                          // A = (Ql dG) Qr^T        psgd.py:220
     for (auto& L : Ls) gs.push_back(mk(M, N, N, L.T1, N, false, L.Qrb, N, true, L.A, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
     for (auto& L : Ls) {
       PSGD_RETURN_IF(ks::col_wsum(ctx, 0, L.Qlb, nullptr, L.dX, N, M, N, L.part, L.cvec));
       norm_left_solve_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dX, L.cvec, L.T1, M, N, nullptr);   // :230-232
@@ -413,7 +540,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       g.colscale = L.Qrb;
       gs.push_back(g);
     }
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
     ts.clear();                                                          // Bt = Ql^-T dX           psgd.py:298
     for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
@@ -450,9 +577,10 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) {
       la::Gemm g = mk(M, M, M, L.grad1, M, false, L.Qlb, M, false, L.Ql_out, M);
       g.D = L.Qlb; g.ldd = M; g.mu_max = &L.sc->max1; g.step = step; g.tiny = tiny;
+      if (dd) { g.rho = &L.sc->rho; g.rho_mode = 1; }                    // Ql / rho                      psgd.py:169
       gs.push_back(g);
     }
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromL));
   } else {
     const int rows_grid = M < ctx->num_sms * 8 ? M : ctx->num_sms * 8;
     for (auto& L : Ls) {
@@ -476,9 +604,10 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) {
       la::Gemm g = mk(N, N, N, L.grad2, N, false, L.Qrb, N, false, L.Qr_out, N);
       g.D = L.Qrb; g.ldd = N; g.mu_max = &L.sc->max2; g.step = step; g.tiny = tiny;
+      if (dd) { g.rho = &L.sc->rho; g.rho_mode = 2; }                    // rho * Qr                      psgd.py:170
       gs.push_back(g);
     }
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromR));
   } else {
     for (auto& L : Ls) {
       PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, L.A, L.Bt, M, N, L.part, L.sa, L.sb));                  // :304 / :366
@@ -499,8 +628,9 @@ static size_t apply_ws_floats(int64_t M, int64_t N) {
   return 64 * 64 + 5 * MN + (size_t)M * M + (size_t)N * N + 4 * (size_t)(M + N) + col_partial_floats((int)M, (int)N);
 }
 
-static void carve_apply(WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
+static void carve_apply(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int kr, int M, int N) {
   const size_t MN = (size_t)M * N;
+  carve_flags(ctx, c, L, kl, kr, M, N);
   L.t1 = c.take<float>(MN);
   L.t2 = c.take<float>(MN);
   L.t3 = c.take<float>(MN);
@@ -526,13 +656,13 @@ static int right_dense_apply(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N
   auto O = [&](Layer& L) { return to_out ? L.out : L.t2; };
   if (M < N || chain_preferred(ctx, N, M)) {
     for (auto& L : Ls) gs.push_back(mk(M, N, N, X(L), N, false, L.Qr, N, true, L.t3, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
     gs.clear();
     for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t3, N, false, L.Qr, N, false, O(L), N));
-    return gemm_all(ctx, gs, 0, kUpper);
+    return gemm_all(ctx, gs, 0, kUpper, &Ls, 0, kFromR);
   }
   for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));
-  PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+  PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromR, kFromR));
   gs.clear();
   for (auto& L : Ls) gs.push_back(mk(M, N, N, X(L), N, false, L.P, N, false, O(L), N));
   return gemm_all(ctx, gs);
@@ -542,52 +672,53 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
   const size_t MN = (size_t)M * N;
   cudaStream_t st = ctx->stream;
   std::vector<la::Gemm> gs;
+  PSGD_RETURN_IF(scan_group(ctx, Ls, M, N));
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
     if (M < N) {                                                          // psgd.py:190
       if (chain_preferred(ctx, M, N)) {                                   // Ql^T (Ql G) instead of (Ql^T Ql) G
         for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.G, N, false, L.t3, N));
-        PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
         gs.clear();
         for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t3, N, false, L.t1, N));
-        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, 0));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0));
       } else {
         for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
-        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+        PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromL, kFromL));
         gs.clear();
         for (auto& L : Ls) gs.push_back(mk(M, N, M, L.P, M, false, L.G, N, false, L.t1, N));
         PSGD_RETURN_IF(gemm_all(ctx, gs));
       }
       gs.clear();
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t1, N, false, L.Qr, N, true, L.t2, N));
-      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
       gs.clear();
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t2, N, false, L.Qr, N, false, L.out, N));
-      return gemm_all(ctx, gs, 0, kUpper);
+      return gemm_all(ctx, gs, 0, kUpper, &Ls, 0, kFromR);
     }
     if (chain_preferred(ctx, N, M)) {                                     // (G Qr^T) Qr instead of G (Qr^T Qr)
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.Qr, N, true, L.t3, N));
-      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
       gs.clear();
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t3, N, false, L.Qr, N, false, L.t1, N));
-      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kUpper));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kUpper, &Ls, 0, kFromR));
     } else {
       for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));     // psgd.py:192
-      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromR, kFromR));
       gs.clear();
       for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.P, N, false, L.t1, N));
       PSGD_RETURN_IF(gemm_all(ctx, gs));
     }
     gs.clear();
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.t1, N, false, L.t2, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
     gs.clear();
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t2, N, false, L.out, N));
-    return gemm_all(ctx, gs, kLower, 0);
+    return gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0);
   }
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
     if (M < N && !chain_preferred(ctx, M, N)) {
       for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
-      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromL, kFromL));
       gs.clear();
       for (auto& L : Ls) {
         la::Gemm g = mk(M, N, M, L.P, M, false, L.G, N, false, L.out, N);
@@ -597,14 +728,14 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
       return gemm_all(ctx, gs);
     }
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.G, N, false, L.t1, N));
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
     gs.clear();
     for (auto& L : Ls) {
       la::Gemm g = mk(M, N, M, L.Ql, M, true, L.t1, N, false, L.out, N);
       g.colscale = L.Qr; g.colscale_sq = true;
       gs.push_back(g);
     }
-    return gemm_all(ctx, gs, kLower, 0);
+    return gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0);
   }
   // normalization-format left factor                                      psgd.py:258-270, :383-391
   if (kr == PSGD_FACTOR_SCALE) {                                           // one pass over G (kron_stream.cu)
@@ -710,8 +841,8 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
         std::swap(M, N);
       }
       keys[i - begin] = Key{kl, kr, M, N};
-      if (is_update) carve_update(c, L, kl, kr, M, N);
-      else carve_apply(c, L, kl, kr, M, N);
+      if (is_update) carve_update(ctx, c, L, kl, kr, M, N);
+      else carve_apply(ctx, c, L, kl, kr, M, N);
     }
     // group equal keys (stable)
     std::vector<char> done(end - begin, 0);
@@ -795,6 +926,11 @@ extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx,
   float* a = c.take<float>(n);
   float* b = c.take<float>(n);
   float* grad = c.take<float>((size_t)n * n);
+  std::vector<kron::Layer> one(1);                    // run-time check of the triangular hint on Q (see tri_scan_kernel)
+  one[0] = kron::Layer{};
+  one[0].Ql = Q; one[0].Qr = Q;
+  kron::carve_flags(ctx, c, one[0], PSGD_FACTOR_DENSE, -1, n, n);
+  PSGD_RETURN_IF(kron::scan_group(ctx, one, n, n));
   PSGD_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(kron::Scal), ctx->stream));
   PSGD_RETURN_IF(ks::row_dot(ctx, Q, n, dg, n, n, a));                        // a = Q dg          psgd.py:38
   PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx       psgd.py:39
@@ -806,7 +942,7 @@ extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx,
   la::Gemm g3 = kron::mk(n, n, n, grad, n, false, Q, n, false, Q_out, n);
   g3.D = Q; g3.ldd = n; g3.mu_max = &sc->max1; g3.step = step; g3.tiny = tiny;
   gs.push_back(g3);
-  return kron::gemm_all(ctx, gs, kron::kUpper, kron::kUpper);
+  return kron::gemm_all(ctx, gs, kron::kUpper, kron::kUpper, &one, 0, kron::kFromL);
 }
 
 extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n64) {

@@ -103,6 +103,8 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
       }
       if (g.triu && m > n) v = 0.f;
       if (g.D) v = g.D[(size_t)m * g.ldd + n] - mu * v;
+      if (g.rho_mode == 1) v = v / *g.rho;
+      else if (g.rho_mode == 2) v = v * *g.rho;
       mx = fmaxf(mx, fabsf(v));
       g.C[(size_t)m * g.ldc + n] = v;
     }

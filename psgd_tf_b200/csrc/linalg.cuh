@@ -30,6 +30,12 @@ struct Gemm {
   // K-range hints (product 0 only; the engines may skip structurally-zero K blocks, never required for correctness
   // of dense data): 0 none, 1 = op(.) upper triangular, 2 = lower triangular, viewed as op(A)[M,K] / op(B)[K,N]
   int a_tri = 0, b_tri = 0;
+  // Run-time validity of the hints: device flags written by kron::factor_scan (non-zero = the operand has entries
+  // outside its assumed triangle, e.g. a caller-supplied factor that is not upper triangular).  When set, the
+  // tensor-core engine drops the corresponding hint for that problem and multiplies the full matrix, which is what
+  // tf.matmul does (psgd.py:173).  nullptr = the hint is valid by construction.
+  const int* a_full = nullptr;
+  const int* b_full = nullptr;
   // block-pair pattern (tensor-core engine only; triangular block-inverse doubling): only output tiles in blocks
   // (k, k+1), k even, of size pair_b exist; K range = the block of the column (kind 1) or of the row (kind 2)
   int pair_b = 0, pair_kind = 0;
@@ -37,6 +43,10 @@ struct Gemm {
   const float* colscale = nullptr;   // acc *= colscale[n]   (or its reciprocal)
   bool colscale_recip = false;
   bool colscale_sq = false;          // use colscale[n]^2
+  // final scaling of the stored value by the balancing factor rho (psgd.py:166-170 folded into the last product of the
+  // update instead of materialising Ql/rho and rho*Qr): 1 = C / *rho, 2 = C * *rho
+  const float* rho = nullptr;
+  int rho_mode = 0;
 };
 
 int gemm_simt(psgd_ctx* ctx, const Gemm& g);

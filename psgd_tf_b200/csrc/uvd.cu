@@ -1226,9 +1226,9 @@ static cudaError_t gram_attr() {
   return cudaFuncSetAttribute(gram_sweep_kernel<R, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::kSmemBytes);
 }
 template <int R>
-static int ensure_attrs() {
-  static bool done = false;
-  if (done) return PSGD_OK;
+static int ensure_attrs(const psgd_ctx* ctx) {
+  static DeviceOnce done;                  // per rank instantiation, per device
+  if (done.done(ctx->device)) return PSGD_OK;
   PSGD_CUDA_CHECK((gram_attr<R, kUpdate>()));
   PSGD_CUDA_CHECK((gram_attr<R, kApply>()));
   PSGD_CUDA_CHECK((gram_attr<R, kMatvec>()));
@@ -1244,7 +1244,7 @@ static int ensure_attrs() {
   PSGD_CUDA_CHECK((map_attr<R, kMapUpdAppU>()));
   PSGD_CUDA_CHECK((map_attr<R, kMapUpdAppV>()));
   PSGD_CUDA_CHECK((map_attr<R, kMapApplyD>()));
-  done = true;
+  done.set(ctx->device);
   return PSGD_OK;
 }
 
@@ -1306,7 +1306,7 @@ static int update_head(psgd_ctx* ctx, const SweepArgs& a1, const Scratch& s, int
 template <int R>
 static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h, int64_t n,
                        float step, float tiny, int balance, int update_U) {
-  PSGD_RETURN_IF(ensure_attrs<R>());
+  PSGD_RETURN_IF(ensure_attrs<R>(ctx));
   const int grid = grid_for(ctx, n);
   const int fused = ctx->opt_uvd_fused;
   Scratch s;
@@ -1367,7 +1367,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
 template <int R>
 static int update_apply_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float* v, const float* h,
                              const float* g, float* out, int64_t n, float step, float tiny, int balance, int update_U) {
-  PSGD_RETURN_IF(ensure_attrs<R>());
+  PSGD_RETURN_IF(ensure_attrs<R>(ctx));
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 1, &s));
@@ -1401,7 +1401,7 @@ static int update_apply_impl(psgd_ctx* ctx, float* U, float* V, float* d, const 
 template <int R>
 static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* out,
                       int64_t n) {
-  PSGD_RETURN_IF(ensure_attrs<R>());
+  PSGD_RETURN_IF(ensure_attrs<R>(ctx));
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));
@@ -1456,7 +1456,7 @@ __global__ void __launch_bounds__(256) clip_update_kernel(float* __restrict__ pa
 template <int R>
 static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const float* d, const float* g, float* param,
                           const float* v, float* pre_out, int64_t n, float lr_params, float max_norm, float tiny) {
-  PSGD_RETURN_IF(ensure_attrs<R>());
+  PSGD_RETURN_IF(ensure_attrs<R>(ctx));
   const int grid = grid_for(ctx, n);
   const bool clip = !isinf(max_norm);
   Scratch s;
@@ -1492,7 +1492,7 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
 // IpUVtmatvec for one column: out = x + U (V^T x)
 template <int R>
 static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const float* x, float* out, int64_t n) {
-  PSGD_RETURN_IF(ensure_attrs<R>());
+  PSGD_RETURN_IF(ensure_attrs<R>(ctx));
   const int grid = grid_for(ctx, n);
   Scratch s;
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));

@@ -28,6 +28,12 @@ from ._lib import FACTOR_DENSE, FACTOR_NORM, FACTOR_SCALE, KronLayer, PsgdError,
 dtype = torch.float32                      # psgd.py:20
 _tiny = float(2.0 ** -126)                 # psgd.py:21-22: smallest normal float32
 
+# Capability limits of the CUDA kernels (the reference accepts any rank): the UVd sweeps are instantiated per rank
+# with register-resident Gram accumulators (csrc/uvd.cu, kMaxRank), the sparse-LU corner kernels run in one warp
+# (csrc/splu.cu, kMaxR).  Checked up front so that a too-large rank fails before any state is touched.
+MAX_UVD_RANK = 16
+MAX_SPLU_RANK = 32
+
 _ctx_local = threading.local()
 _rng = _random.Random()
 
@@ -96,6 +102,12 @@ def _flat_cat(ts):
     return ts[0] if len(ts) == 1 else torch.cat(ts)
 
 
+def _check_uvd_rank(r: int, what: str) -> None:
+    if not 1 <= int(r) <= MAX_UVD_RANK:
+        raise ValueError(f"{what}: rank_of_modification {r} is outside 1..{MAX_UVD_RANK}, the range the B200 UVd kernels "
+                         "are built for (the reference accepts any rank; see psgd_tf_b200.MAX_UVD_RANK)")
+
+
 def _kind(Q: torch.Tensor) -> int:
     """Factor format from its shape, in the reference's test order: square => dense first
     (psgd.py:82-83), then first dim 2 => normalization, 1 => scaling."""
@@ -124,7 +136,7 @@ def update_precond_dense(Q, dxs, dgs, step=0.01):
     dx = _flat_cat([_in(x, "dxs") for x in dxs])
     dg = _flat_cat([_in(g, "dgs") for g in dgs])
     n = Q.shape[0]
-    if Q.shape != (n, n) or dx.numel() != n or dg.numel() != n:
+    if Q.dim() != 2 or Q.shape != (n, n) or dx.numel() != n or dg.numel() != n:
         raise ValueError(f"update_precond_dense: Q {tuple(Q.shape)} vs {dx.numel()} parameters")
     out = torch.empty_like(Q)
     ctx = get_context(Q.device.index)
@@ -138,7 +150,7 @@ def precond_grad_dense(Q, grads):
     gs = [_in(g, "grads") for g in grads]
     flat = _flat_cat(gs)
     n = Q.shape[0]
-    if flat.numel() != n:
+    if Q.dim() != 2 or Q.shape != (n, n) or flat.numel() != n:
         raise ValueError(f"precond_grad_dense: Q {tuple(Q.shape)} vs {flat.numel()} parameters")
     out = torch.empty_like(flat)
     ctx = get_context(Q.device.index)
@@ -155,6 +167,8 @@ def precond_grad_dense(Q, grads):
 # ---------------------------------------------------------------------------------------------
 def _splu_check(L12, l3, U12, u3, n):
     r = U12.shape[0]
+    if not 1 <= r <= MAX_SPLU_RANK:
+        raise ValueError(f"SPLU: r = {r} is outside 1..{MAX_SPLU_RANK}, the range the B200 kernels are built for")
     if L12.shape != (n, r) or U12.shape != (r, n) or l3.numel() != n - r or u3.numel() != n - r:
         raise ValueError(f"SPLU: L12 {tuple(L12.shape)}, l3 {tuple(l3.shape)}, U12 {tuple(U12.shape)}, u3 {tuple(u3.shape)} "
                          f"do not describe a {n}-parameter preconditioner")
@@ -198,6 +212,27 @@ def precond_grad_splu(L12, l3, U12, u3, grads):
 # ---------------------------------------------------------------------------------------------
 # Kronecker product preconditioners                                          psgd.py:67-391
 # ---------------------------------------------------------------------------------------------
+_FACTOR_ROWS = {FACTOR_NORM: 2, FACTOR_SCALE: 1}
+
+
+def _check_kron_layer(what, kl, kr, Ql, Qr, X, dG=None, layer=None):
+    """Shape / device consistency of one layer (the kernels index Ql as [*, M], Qr as [*, N] and X as [M, N]; a
+    mismatch would read or write out of bounds).  Called by the single-layer AND the batched entry points."""
+    at = "" if layer is None else f" (layer {layer})"
+    names = (("Ql", Ql), ("Qr", Qr), ("dX" if dG is not None else "Grad", X)) + ((("dG", dG),) if dG is not None else ())
+    for nm, t in names:
+        if t.dim() != 2:
+            raise ValueError(f"{what}{at}: {nm} must be rank-2 (psgd.py:67-70, :113-115), got shape {tuple(t.shape)}")
+        if t.device != X.device:
+            raise ValueError(f"{what}{at}: {nm} is on {t.device}, expected {X.device}")
+    M, N = X.shape
+    ok = Ql.shape[1] == M and Qr.shape[1] == N and (dG is None or dG.shape == X.shape)
+    ok = ok and Ql.shape[0] == _FACTOR_ROWS.get(kl, M) and Qr.shape[0] == _FACTOR_ROWS.get(kr, N)
+    if not ok:
+        raise ValueError(f"{what}{at}: Ql {tuple(Ql.shape)}, Qr {tuple(Qr.shape)}, {names[2][0]} {tuple(X.shape)}"
+                         + (f", dG {tuple(dG.shape)}" if dG is not None else "") + " are inconsistent")
+
+
 def _kron_update(Ql, Qr, dX, dG, step, kinds=None):
     Ql, Qr, dX, dG = _in(Ql, "Ql"), _in(Qr, "Qr"), _in(dX, "dX"), _in(dG, "dG")
     for t, nm in ((Ql, "Ql"), (Qr, "Qr"), (dX, "dX"), (dG, "dG")):
@@ -208,9 +243,7 @@ def _kron_update(Ql, Qr, dX, dG, step, kinds=None):
     if (kl, kr) not in _SUPPORTED:
         print("Unknown Kronecker product preconditioner, no update")          # psgd.py:90
         return Ql, Qr
-    if dG.shape != dX.shape or Ql.shape[1] != M or Qr.shape[1] != N:
-        raise ValueError(f"update_precond_kron: Ql {tuple(Ql.shape)}, Qr {tuple(Qr.shape)}, dX {tuple(dX.shape)}, "
-                         f"dG {tuple(dG.shape)} are inconsistent")
+    _check_kron_layer("update_precond_kron", kl, kr, Ql, Qr, dX, dG)
     Ql_out, Qr_out = torch.empty_like(Ql), torch.empty_like(Qr)
     ctx = get_context(Ql.device.index)
     check(ctx.lib.psgd_kron_update(ctx.handle, kl, kr, _p(Ql), _p(Qr), _p(dX), _p(dG), _p(Ql_out), _p(Qr_out),
@@ -228,9 +261,7 @@ def _kron_apply(Ql, Qr, Grad, kinds=None):
     if (kl, kr) not in _SUPPORTED:
         print("Unknown Kronecker product preconditioner, no preconditioning")  # psgd.py:132
         return Grad
-    if Ql.shape[1] != M or Qr.shape[1] != N:
-        raise ValueError(f"precond_grad_kron: Ql {tuple(Ql.shape)}, Qr {tuple(Qr.shape)}, Grad {tuple(Grad.shape)} "
-                         "are inconsistent")
+    _check_kron_layer("precond_grad_kron", kl, kr, Ql, Qr, Grad)
     out = torch.empty_like(Grad)
     ctx = get_context(Ql.device.index)
     check(ctx.lib.psgd_kron_apply(ctx.handle, kl, kr, _p(Ql), _p(Qr), _p(Grad), _p(out), M, N))
@@ -301,15 +332,22 @@ def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
     Equivalent to ``[update_precond_kron(*a, step) for a in zip(Qls, Qrs, dXs, dGs)]``
     (mnist_with_lenet5.py:51)."""
     n = len(Qls)
+    if not (len(Qrs) == len(dXs) == len(dGs) == n):
+        raise ValueError("update_precond_kron_batched: the four lists differ in length")
     Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
     dXs = [_in(x, "dX") for x in dXs]; dGs = [_in(g, "dG") for g in dGs]
     outs, fields, keep = [None] * n, [], []
     for i in range(n):
+        if Qls[i].dim() != 2 or Qrs[i].dim() != 2:
+            raise ValueError(f"update_precond_kron_batched (layer {i}): factors must be rank-2")
         kl, kr = _kind(Qls[i]), _kind(Qrs[i])
         if (kl, kr) not in _SUPPORTED:
             print("Unknown Kronecker product preconditioner, no update")
             outs[i] = (Qls[i], Qrs[i])
             continue
+        _check_kron_layer("update_precond_kron_batched", kl, kr, Qls[i], Qrs[i], dXs[i], dGs[i], layer=i)
+        if dXs[i].device != dXs[0].device:
+            raise ValueError(f"update_precond_kron_batched (layer {i}): all layers of a call must live on one device")
         M, N = dXs[i].shape
         lo, ro = torch.empty_like(Qls[i]), torch.empty_like(Qrs[i])
         outs[i] = (lo, ro)
@@ -325,15 +363,22 @@ def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
 def precond_grad_kron_batched(Qls, Qrs, Grads):
     """``[precond_grad_kron(Ql, Qr, G) for ...]`` in one library call (mnist_with_lenet5.py:53)."""
     n = len(Qls)
+    if not (len(Qrs) == len(Grads) == n):
+        raise ValueError("precond_grad_kron_batched: the three lists differ in length")
     Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
     Grads = [_in(g, "Grad") for g in Grads]
     outs, fields = [None] * n, []
     for i in range(n):
+        if Qls[i].dim() != 2 or Qrs[i].dim() != 2:
+            raise ValueError(f"precond_grad_kron_batched (layer {i}): factors must be rank-2")
         kl, kr = _kind(Qls[i]), _kind(Qrs[i])
         if (kl, kr) not in _SUPPORTED:
             print("Unknown Kronecker product preconditioner, no preconditioning")
             outs[i] = Grads[i]
             continue
+        _check_kron_layer("precond_grad_kron_batched", kl, kr, Qls[i], Qrs[i], Grads[i], layer=i)
+        if Grads[i].device != Grads[0].device:
+            raise ValueError(f"precond_grad_kron_batched (layer {i}): all layers of a call must live on one device")
         M, N = Grads[i].shape
         o = torch.empty_like(Grads[i])
         outs[i] = o
@@ -406,6 +451,7 @@ def IpUVtmatvec(U, V, x):
     k = 1 if x.dim() == 1 else x.shape[1]
     if V.shape != U.shape or x.shape[0] != n:
         raise ValueError("IpUVtmatvec: shapes are inconsistent")
+    _check_uvd_rank(r, "IpUVtmatvec")
     out = torch.empty_like(x)
     ctx = get_context(U.device.index)
     check(ctx.lib.psgd_ipuvt_matvec(ctx.handle, _p(U), _p(V), _p(x), _p(out), n, r, k))
@@ -423,6 +469,7 @@ def update_precond_UVd_math_(U, V, d, v, h, step, tiny=_tiny, *, balance=None, u
     n, r = U.shape
     if V.shape != U.shape:
         raise ValueError("update_precond_UVd_math_: U and V must have the same shape")
+    _check_uvd_rank(r, "update_precond_UVd_math_")
     _col(d, n, "d"); _col(v, n, "v"); _col(h, n, "h")
     if balance is None:
         balance = _rng.random() < 0.01
@@ -438,6 +485,9 @@ def precond_grad_UVd_math(U, V, d, g):
     """psgd.py:619-627: ``d * (I + V U^T)(I + U V^T)(d * g)``; same shape as ``g``."""
     U, V, d, g = _in(U, "U"), _in(V, "V"), _in(d, "d"), _in(g, "g")
     n, r = U.shape
+    if V.shape != U.shape:
+        raise ValueError("precond_grad_UVd_math: U and V must have the same shape")
+    _check_uvd_rank(r, "precond_grad_UVd_math")
     _col(d, n, "d"); _col(g, n, "g")
     out = torch.empty_like(g)
     ctx = get_context(U.device.index)
@@ -455,6 +505,7 @@ def update_precond_and_grad_UVd(U, V, d, v, h, g, step, tiny=_tiny, *, balance=N
     n, r = U.shape
     if V.shape != U.shape:
         raise ValueError("update_precond_and_grad_UVd: U and V must have the same shape")
+    _check_uvd_rank(r, "update_precond_and_grad_UVd")
     _col(d, n, "d"); _col(v, n, "v"); _col(h, n, "h"); _col(g, n, "g")
     if balance is None:
         balance = _rng.random() < 0.01
@@ -562,6 +613,7 @@ class UVd:
     def __init__(self, params_with_grad, rank_of_modification: int = 10, preconditioner_init_scale=1.0,
                  lr_params=0.01, lr_preconditioner=0.01, grad_clip_max_norm=None,
                  preconditioner_update_probability=1.0, exact_hessian_vector_product: bool = True):
+        _check_uvd_rank(rank_of_modification, "UVd")         # before the parameters are re-homed into the flat buffer
         params = [params_with_grad] if isinstance(params_with_grad, torch.Tensor) else list(params_with_grad)
         flat_list = []
         for p in params:                                   # tf.nest.flatten (psgd.py:669)

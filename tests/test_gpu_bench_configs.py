@@ -1,0 +1,226 @@
+"""GPU parity at the two BENCHMARKED configurations and on the code paths only those sizes reach.
+
+* cfg3 (24 x 4096^2 dense-dense Kron stack, psgd.py:156-192): one layer at 2048^2 and at 4096^2, update + apply, against
+  the CPU oracle.  With the default ``trsm_base`` = 1024 these are the first sizes at which the recursive triangular
+  solve (``trsm_right_rec`` / ``trsm_left_rec`` in gemm_tc.cu) takes its split/update branch; the 2048^2 case is also
+  run for every base-block width and on the SIMT engine.
+* ill-conditioned factors (cond ~ 1e4): the solves apply EXPLICIT inverses of the diagonal base blocks, whose error
+  grows with cond(block) -- measured against the float64 twin, next to the float32 oracle's own error.
+* a factor that is NOT upper triangular, under the default options: tf.matmul multiplies the full matrix
+  (psgd.py:173) while tf.linalg.triangular_solve reads only the upper triangle (psgd.py:174); the run-time scan
+  (``tri_scan_kernel``) must cancel the tensor-core K-range hints.
+* cfg4 (UVd rank 10 on 1e8 parameters, psgd.py:554-627): update and the fused update+apply at N = 2e7 against the
+  multi-threaded torch-CPU twin of the oracle (the NumPy oracle runs its element-wise ops on one thread).
+
+Tolerance: 1e-5 relative Frobenius error per output (BASELINE.json north_star).
+"""
+import numpy as np
+import pytest
+import torch
+
+from oracle import psgd_oracle as O
+from tests import cases
+
+pytestmark = pytest.mark.gpu
+TOL = 1e-5
+F = np.float32
+
+
+@pytest.fixture(scope="module")
+def psgd():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device")
+    import psgd_tf_b200 as p
+    p.get_context()
+    return p
+
+
+def dev(x):
+    return torch.from_numpy(np.ascontiguousarray(x)).cuda()
+
+
+def host(t):
+    return t.detach().cpu().numpy()
+
+
+def bench_like_layer(seed, M, N):
+    """The bench's synthetic layer (bench_kron.py): dX ~ N(0,1), dG = S dX T + 0.1 N(0,1), G ~ N(0,1); factors one
+    update step away from the identity (mnist_with_lenet5.py:61-62), so that they are non-trivial upper triangles."""
+    rng = np.random.default_rng(seed)
+    S = (0.5 + 1.5 * rng.random((M, 1))).astype(F)
+    T = (0.5 + 1.5 * rng.random((1, N))).astype(F)
+    dX0 = rng.standard_normal((M, N), dtype=F)
+    dG0 = (S * dX0 * T + 0.1 * rng.standard_normal((M, N), dtype=F)).astype(F)
+    Ql, Qr = O.update_precond_kron(np.eye(M, dtype=F), np.eye(N, dtype=F), dX0, dG0, 0.01)
+    dX = rng.standard_normal((M, N), dtype=F)
+    dG = (S * dX * T + 0.1 * rng.standard_normal((M, N), dtype=F)).astype(F)
+    G = rng.standard_normal((M, N), dtype=F)
+    return dict(Ql=Ql.astype(F), Qr=Qr.astype(F), dX=dX, dG=dG, G=G)
+
+
+def run_layer(psgd, c):
+    ql, qr = psgd.update_precond_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["dX"]), dev(c["dG"]), 0.01)
+    pre = psgd.precond_grad_kron(ql, qr, dev(c["G"]))
+    torch.cuda.synchronize()
+    return host(ql), host(qr), host(pre)
+
+
+def oracle_layer(c, dtype=F):
+    a = {k: np.asarray(v, dtype) for k, v in c.items()}
+    ql, qr = O.update_precond_kron(a["Ql"], a["Qr"], a["dX"], a["dG"], 0.01)
+    return ql, qr, O.precond_grad_kron(ql, qr, a["G"])
+
+
+_ORACLE_CACHE = {}
+
+
+def cached_oracle(key, c):
+    if key not in _ORACLE_CACHE:
+        _ORACLE_CACHE[key] = oracle_layer(c)
+    return _ORACLE_CACHE[key]
+
+
+@pytest.mark.parametrize("n", [2048, 4096])
+def test_dense_dense_layer_at_bench_size(psgd, n):
+    """One layer of BASELINE configs[2] through the default options (tcgen05 3xTF32, trsm_base 1024, chained apply)."""
+    c = bench_like_layer(100 + n, n, n)
+    got = run_layer(psgd, c)
+    want = cached_oracle(("bench", n), c)
+    errs = [cases.rel_err(g, w) for g, w in zip(got, want)]
+    assert max(errs) <= TOL, dict(zip(("Ql", "Qr", "pre"), errs))
+    assert np.array_equal(np.tril(got[0], -1), np.zeros_like(got[0])), "Ql' must stay upper triangular"
+
+
+@pytest.mark.parametrize("base,path", [(128, 2), (256, 2), (512, 2), (1024, 2), (2048, 2), (1024, 1)])
+def test_trsm_recursion_every_base_width(psgd, base, path):
+    """2048^2: base 128..1024 take the split/update branch of the recursion at depth 4..1, 2048 is a single leaf whose
+    inverse is grown by four doubling levels; gemm_path 1 is the SIMT engine (left-looking 32-row solves)."""
+    ctx = psgd.get_context()
+    c = bench_like_layer(77, 2048, 2048)
+    want = cached_oracle(("rec", 2048), c)
+    ctx.set_option("trsm_base", base)
+    ctx.set_option("gemm_path", path)
+    try:
+        got = run_layer(psgd, c)
+    finally:
+        ctx.set_option("trsm_base", 1024)
+        ctx.set_option("gemm_path", 0)
+    errs = [cases.rel_err(g, w) for g, w in zip(got, want)]
+    assert max(errs) <= TOL, (base, path, errs)
+
+
+@pytest.mark.parametrize("M,N", [(1536, 2560), (2560, 1536)])
+def test_trsm_recursion_rectangular(psgd, M, N):
+    """Uneven split points (split_point rounds the half up to a base multiple) and both M<N / M>N apply branches."""
+    c = bench_like_layer(M + N, M, N)
+    got = run_layer(psgd, c)
+    want = oracle_layer(c)
+    errs = [cases.rel_err(g, w) for g, w in zip(got, want)]
+    assert max(errs) <= TOL, errs
+
+
+def ill_conditioned_factor(rng, n, cond):
+    """Upper triangular, diagonal log-spaced over `cond`, shuffled; off-diagonal mass 0.3/sqrt(n) relative to the row."""
+    s = np.exp(np.linspace(-0.5 * np.log(cond), 0.5 * np.log(cond), n))
+    rng.shuffle(s)
+    Q = np.diag(s) @ (np.eye(n) + np.triu(rng.standard_normal((n, n)), 1) * (0.3 / np.sqrt(n)))
+    return Q.astype(F)
+
+
+@pytest.mark.parametrize("n,base", [(1024, 1024), (2048, 1024), (2048, 128)])
+def test_ill_conditioned_factors(psgd, n, base):
+    """cond(Ql), cond(Qr) ~ 1e4.  Two float32 implementations of an ill-conditioned solve differ by O(cond * eps), so the
+    yardstick is the float64 twin: the CUDA path (explicit inverses of `base`-wide diagonal blocks) must be as close to
+    it as the float32 back-substitution oracle is, within a factor 4, or inside the 1e-5 tolerance outright."""
+    rng = np.random.default_rng(n + base)
+    c = cases.kron_case(n, "dense", "dense", n, n)
+    c["Ql"], c["Qr"] = ill_conditioned_factor(rng, n, 1e4), ill_conditioned_factor(rng, n, 1e4)
+    assert np.linalg.cond(c["Ql"].astype(np.float64)) > 3e3
+    ctx = psgd.get_context()
+    ctx.set_option("trsm_base", base)
+    try:
+        got = run_layer(psgd, c)
+    finally:
+        ctx.set_option("trsm_base", 1024)
+    w64 = oracle_layer(c, np.float64)
+    w32 = oracle_layer(c, F)
+    for name, g, a, b in zip(("Ql", "Qr", "pre"), got, w64, w32):
+        e_cuda, e_f32 = cases.rel_err(g, a), cases.rel_err(b, a)
+        assert e_cuda <= max(TOL, 4.0 * e_f32), f"{name}: CUDA vs float64 {e_cuda:.2e}, float32 oracle vs float64 {e_f32:.2e}"
+
+
+@pytest.mark.parametrize("n", [512, 1024])
+def test_non_triangular_factor_default_options(psgd, n):
+    """A full (not upper-triangular) Ql and Qr under the DEFAULT options: products use the whole matrix, solves the
+    upper triangle only -- exactly what the TensorFlow ops do."""
+    rng = np.random.default_rng(n)
+    c = cases.kron_case(n + 1, "dense", "dense", n, n)
+    for k in ("Ql", "Qr"):
+        c[k] = (c[k] + np.tril(rng.standard_normal((n, n)), -1) * (0.1 / np.sqrt(n))).astype(F)
+    got = run_layer(psgd, c)
+    want = oracle_layer(c)
+    errs = [cases.rel_err(g, w) for g, w in zip(got, want)]
+    assert max(errs) <= TOL, errs
+    # and the apply alone on the non-triangular inputs (its own scan)
+    pre = host(psgd.precond_grad_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["G"])))
+    assert cases.rel_err(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"])) <= TOL
+    # a single stray entry far below the diagonal is enough to cancel the hints
+    c2 = cases.kron_case(n + 2, "dense", "dense", n, n)
+    c2["Ql"][n - 1, 0] = 0.25
+    got2 = run_layer(psgd, c2)
+    want2 = oracle_layer(c2)
+    assert max(cases.rel_err(g, w) for g, w in zip(got2, want2)) <= TOL
+
+
+def test_dense_preconditioner_non_triangular(psgd):
+    """update_precond_dense with a full Q at a size that routes grad @ Q through the tensor cores (psgd.py:42)."""
+    c = cases.dense_case(19, [(16, 32), (512,)])          # n = 1024
+    n = c["Q"].shape[0]
+    c["Q"] = (c["Q"] + np.tril(np.random.default_rng(2).standard_normal((n, n)), -1) * (0.1 / np.sqrt(n))).astype(F)
+    Qn = psgd.update_precond_dense(dev(c["Q"]), [dev(x) for x in c["dxs"]], [dev(x) for x in c["dgs"]], 0.01)
+    assert cases.rel_err(host(Qn), O.update_precond_dense(c["Q"], c["dxs"], c["dgs"], 0.01)) <= TOL
+
+
+# ---------------------------------------------------------------------------------------------
+# UVd at 2e7 rows
+# ---------------------------------------------------------------------------------------------
+def uvd_big_case(n, r, seed=2024):
+    g = torch.Generator().manual_seed(seed)
+    uv = (1.0 / (1e8 * r)) ** 0.5            # the scale of the 1e8-parameter benchmark (psgd.py:687)
+    U = torch.randn(n, r, generator=g) * uv
+    V = torch.randn(n, r, generator=g) * uv
+    d = 0.5 + torch.rand(n, 1, generator=g)
+    v = torch.randn(n, 1, generator=g)
+    h = (0.5 + 1.5 * torch.rand(n, 1, generator=g)) * v + 0.1 * torch.randn(n, 1, generator=g)
+    gr = torch.randn(n, 1, generator=g)
+    return U, V, d, v, h, gr
+
+
+def trel(a, b):
+    a, b = a.double(), b.double()
+    return float((a - b).norm() / b.norm())
+
+
+@pytest.mark.parametrize("update_U", [True, False])
+def test_uvd_at_2e7_rows(psgd, update_U):
+    """Per-lane fp32 partial sums over ~2400 rows per lane and the Gram-table expansion of a.a, b.b (cancellation) at
+    the benchmark's row scale; N is not a multiple of the tile sizes."""
+    from oracle import psgd_oracle_torch as T
+    n, r = 20_000_003, 10
+    U, V, d, v, h, g = uvd_big_case(n, r)
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    Ur, Vr, dr = T.update_precond_UVd_math(U, V, d, v, h, 0.01, balance=False, update_U=update_U)
+    pr = T.precond_grad_UVd_math(Ur, Vr, dr, g)
+    # the reference's two calls
+    Ud, Vd, dd = U.cuda(), V.cuda(), d.cuda()
+    psgd.update_precond_UVd_math_(Ud, Vd, dd, v.cuda(), h.cuda(), 0.01, psgd._tiny, balance=False, update_U=update_U)
+    pre = psgd.precond_grad_UVd_math(Ud, Vd, dd, g.cuda())
+    errs = dict(U=trel(Ud.cpu(), Ur), V=trel(Vd.cpu(), Vr), d=trel(dd.cpu(), dr), pre=trel(pre.cpu(), pr))
+    assert max(errs.values()) <= TOL, errs
+    del Ud, Vd, dd, pre
+    # the fused update+apply call the bench headline times
+    Ud, Vd, dd = U.cuda(), V.cuda(), d.cuda()
+    pre = psgd.update_precond_and_grad_UVd(Ud, Vd, dd, v.cuda(), h.cuda(), g.cuda(), 0.01, psgd._tiny, balance=False,
+                                           update_U=update_U)
+    errs = dict(U=trel(Ud.cpu(), Ur), V=trel(Vd.cpu(), Vr), d=trel(dd.cpu(), dr), pre=trel(pre.cpu(), pr))
+    assert max(errs.values()) <= TOL, errs

@@ -14,7 +14,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(scope="module")
 def psgd():
     import psgd_tf_b200 as p
-    assert torch.cuda.is_available()
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (B200); run with -m gpu on the GPU box")
     p.get_context()
     return p
 

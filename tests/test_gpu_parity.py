@@ -25,7 +25,8 @@ GOLD.update(np.load(os.path.join(_GDIR, "reference_outputs.npz")))
 @pytest.fixture(scope="module")
 def psgd():
     import psgd_tf_b200 as p
-    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (B200); run with -m gpu on the GPU box")
     p.get_context()          # fails loudly if the extension is missing or the device is not sm_100
     return p
 

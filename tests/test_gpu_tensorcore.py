@@ -15,6 +15,8 @@ TOL = 1e-5
 
 @pytest.fixture(scope="module")
 def psgd():
+    if not torch.cuda.is_available():
+        pytest.skip("needs a CUDA device (B200); run with -m gpu on the GPU box")
     import psgd_tf_b200 as p
     p.get_context()
     return p
