@@ -165,6 +165,37 @@ def uvd_bytes(n, r, form="fused"):
     return per_kernel, step, 4 * n * (9 * r + 12)
 
 
+def uvd_config(n_total, r, world):
+    """The `config` object of the UVd workload -- built by ONE function for both arms (`--impl ours` and `--impl
+    reference` must name the same workload); everything specific to how an arm executes it goes under `run`."""
+    rows = chunk_of(n_total, world, 0)[1]
+    return dict(workload=f"UVd rank-{r} update+apply on a flattened {n_total:,}-parameter vector (BASELINE configs[3])",
+                n_params=n_total, rank=r, parallelism=f"chunk-sharded x{world}",
+                l2_policy="inputs larger than L2: >= %.1f GB of state+inputs streamed per GPU per step vs 126 MB L2" %
+                          ((4 * rows * (2 * r + 4)) / 1e9),
+                coin_flips="update_U alternates, balance every 100th step", step_size=0.01)
+
+
+def kron_config(L, n, world):
+    per = -(-L // world)
+    return dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply, batched (BASELINE configs[2])", layers=L, n=n,
+                parallelism=f"layer-sharded x{world} + all-gather of preconditioned gradients",
+                l2_policy=f"inputs larger than L2: {per * 5 * 4 * n * n / 1e9:.1f} GB of factors+inputs per GPU per step vs 126 MB L2",
+                step_size=0.01)
+
+
+def rel_err_chunked(a, b, chunks=16):
+    """||a - b||_F / ||b||_F of two (large) CPU tensors with float64 accumulation and bounded temporaries."""
+    import torch
+    a, b = a.reshape(-1), b.reshape(-1)
+    num = den = 0.0
+    step = -(-a.numel() // chunks)
+    for i in range(0, a.numel(), max(step, 1)):
+        x, y = a[i:i + step].double(), b[i:i + step].double()
+        num += float(torch.sum((x - y) ** 2)); den += float(torch.sum(y ** 2))
+    return (num / max(den, 1e-300)) ** 0.5
+
+
 def chunk_of(n, world, rank, align=256):
     per = -(-n // world)
     per = -(-per // align) * align
@@ -208,10 +239,10 @@ def run_uvd(args, rank, world, local):
     if world > 1:
         exchange = partition.install_exchange(ctx) if not args.nccl_hook else (partition.install_allreduce(ctx) or "all-reduce hook")
 
-    # CUDA graphs need a host-free chain: fine on one GPU and with the peer-memory exchange, not with the Python hook
-    # and only used where launch latency matters (sharded runs: < 1 ms of kernels per step at 8 GPUs).  On one GPU the
-    # timed loop stays eager so that every launch in it is bracketed by CUDA events for the per-kernel roofline.
-    use_graphs = (not args.no_graphs) and world > 1 and exchange == "peer-memory"
+    # CUDA graphs need a host-free chain: fine on one GPU and with the peer-memory exchange, not with the Python hook.
+    # The timed region replays graphs at EVERY N (one measurement mode for the whole scaling curve); the per-kernel
+    # roofline comes from an eager pass right after it, in which every launch is bracketed by CUDA events.
+    use_graphs = (not args.no_graphs) and (world == 1 or exchange == "peer-memory")
     graphs = {}
 
     form = {"fused": "fused"}.get(args.uvd_form, "separate")
@@ -219,10 +250,10 @@ def run_uvd(args, rank, world, local):
     def step(i, U, V, d, v, h, g):
         balance, update_U = (i % 100 == 99), (i % 2 == 0)
         if use_graphs:
-            gs = graphs.get(U.data_ptr())
+            gs = graphs.get((U.data_ptr(), form))
             if gs is None:
                 from psgd_tf_b200.graphs import UVdStepGraphs
-                gs = graphs[U.data_ptr()] = UVdStepGraphs(U, V, d, 0.01, psgd._tiny, fused=(form == "fused"))
+                gs = graphs[(U.data_ptr(), form)] = UVdStepGraphs(U, V, d, 0.01, psgd._tiny, fused=(form == "fused"))
             return gs.step(v, h, g, balance, update_U)
         if form == "fused":       # the sequence UVd.step runs (psgd.py:732-748) as one call: three sweeps over U, V
             return psgd.update_precond_and_grad_UVd(U, V, d, v, h, g, 0.01, psgd._tiny, balance=balance, update_U=update_U)
@@ -332,9 +363,9 @@ def run_uvd(args, rank, world, local):
 
     # ---- the same step through the reference's two separate calls (update_precond_UVd_math_, precond_grad_UVd_math) ----
     separate = None
-    if form == "fused" and not use_graphs and not args.no_separate:
+    if form == "fused" and not args.no_separate and (world == 1 or use_graphs):
         form = "separate"
-        for i in range(3):
+        for i in range(3 + (2 * POOL if use_graphs else 0)):
             step(i, U, V, d, *pool[i % POOL])
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -351,6 +382,21 @@ def run_uvd(args, rank, world, local):
                         step_frac_survey=round(survey_bytes / (sms * 1e-3) / 1e9 / peaks["hbm"], 4),
                         note="update_precond_UVd_math_ then precond_grad_UVd_math as two calls (4 sweeps + a pass over d)")
         form = "fused"
+
+    if roofline is not None and separate is not None:
+        roofline["two_call_form"] = dict(value=separate["value"], ms_per_step=separate["ms_per_step"],
+                                         step_frac_survey=separate["step_frac_survey"],
+                                         note="the reference's own call sequence (update_precond_UVd_math_, then "
+                                              "precond_grad_UVd_math) against SURVEY 8d's 4N(9r+12) bytes")
+
+    # ---- parity at the benchmarked configuration, outside every timed region --------------------------------
+    # One more step from the state the timed steps left behind, on the GPU (the fused call the headline times) and
+    # through the multi-threaded CPU twin of the oracle on the same inputs: relative Frobenius error per output.
+    parity = None
+    if world == 1 and not args.no_parity:
+        parity = uvd_parity(psgd, U, V, d, *pool[0], step_index=args.warmup + args.steps)
+        if roofline is not None:
+            roofline["parity_rel_err"] = parity["max_rel_err"]
 
     # ---- end to end: host (pinned) inputs, host read-back, copies inside the timed region -----------
     e2e = None
@@ -428,18 +474,52 @@ def run_uvd(args, rank, world, local):
         metric=METRIC, value=round(value, 3), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms / args.steps, 4), higher_is_better=True, scaling=args.scaling, vs_baseline=None,
         dtype="f32", data="synthetic",
-        config=dict(workload=f"UVd rank-{r} update+apply on a flattened {N_total:,}-parameter vector (BASELINE configs[3])",
-                    n_params=N_total, rank=r, rows_per_gpu=n, parallelism=f"chunk-sharded x{world}",
-                    l2_policy="inputs larger than L2: >= %.1f GB of state+inputs streamed per GPU per step vs 126 MB L2" %
-                              ((4 * n * (2 * r + 4)) / 1e9),
-                    coin_flips="update_U alternates, balance every 100th step", step_size=0.01,
-                    call_form=("update_precond_and_grad_UVd (psgd_uvd_update_apply): update + apply of psgd.py:732-748 "
-                               "fused into three sweeps" if form == "fused" else
-                               "update_precond_UVd_math_ + precond_grad_UVd_math as two calls (" + args.uvd_form + ")"),
-                    cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
+        config=uvd_config(N_total, r, world),
+        run=dict(rows_per_gpu=n,
+                 call_form=("update_precond_and_grad_UVd (psgd_uvd_update_apply): update + apply of psgd.py:732-748 "
+                            "fused into three sweeps" if form == "fused" else
+                            "update_precond_UVd_math_ + precond_grad_UVd_math as two calls (" + args.uvd_form + ")"),
+                 cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
+        parity=parity,
         step_ms_median=round(float(np.median(per_step)), 4), step_ms_max=round(max(per_step), 4), remeasured=remeasured,
         roofline=roofline, kernels=kernels, kernels_measured=kernels_from, separate_calls=separate, cpu_baseline=cpu, e2e=e2e,
         gpu_launches=int(launches), clocks=clk)
+
+
+def uvd_parity(psgd, U, V, d, v, h, g, step_index):
+    """CUDA (fused update+apply, the headline's kernels) against the CPU oracle at the FULL benchmarked size.
+
+    The oracle runs twice on the same inputs: in float64 (the yardstick) and in float32 (the reference's arithmetic).
+    At 1e8 rows the float32 op sequence is itself ill-conditioned in the rank-2 step of U / V (psgd.py:594-597: the
+    normaliser is a difference of O(N) float32 sums; tests/test_gpu_bench_configs.py::test_uvd_at_2e7_rows), so the
+    float32 oracle's own distance from float64 is reported next to ours: `max_rel_err` is CUDA vs the float64 twin."""
+    import torch
+    from oracle import psgd_oracle_torch as T
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    update_U = (step_index % 2 == 0)
+    hU, hV, hd, hv, hh, hg = (x.cpu() for x in (U, V, d, v, h, g))
+    pre = psgd.update_precond_and_grad_UVd(U, V, d, v, h, g, 0.01, psgd._tiny, balance=False, update_U=update_U)
+    got = dict(U=U.cpu(), V=V.cpu(), d=d.cpu(), pre_grad=pre.cpu())
+    Ur, Vr, dr = T.update_precond_UVd_math(hU, hV, hd, hv, hh, 0.01, balance=False, update_U=update_U)
+    w32 = dict(U=Ur, V=Vr, d=dr, pre_grad=T.precond_grad_UVd_math(Ur, Vr, dr, hg))
+    del Ur, Vr, dr
+    dbl = lambda x: x.double()
+    U6, V6, d6 = T.update_precond_UVd_math(dbl(hU), dbl(hV), dbl(hd), dbl(hv), dbl(hh), 0.01, balance=False, update_U=update_U)
+    w64 = dict(U=U6, V=V6, d=d6, pre_grad=T.precond_grad_UVd_math(U6, V6, d6, dbl(hg)))
+    del U6, V6, d6
+    e64 = {k: rel_err_chunked(got[k], w64[k]) for k in got}
+    e32 = {k: rel_err_chunked(got[k], w32[k]) for k in got}
+    own = {k: rel_err_chunked(w32[k], w64[k]) for k in got}
+    fmt = lambda dd: {k: float("%.3e" % e) for k, e in dd.items()}
+    ok = all(e64[k] <= max(1e-5, own[k]) for k in got)
+    return dict(max_rel_err=float("%.3e" % max(e64.values())), rel_err_vs_float64_oracle=fmt(e64),
+                rel_err_vs_float32_oracle=fmt(e32), float32_oracle_vs_float64_oracle=fmt(own),
+                tolerance=1e-5, passed=bool(ok), rows=int(U.shape[0]), branch="U" if update_U else "V",
+                against="oracle/psgd_oracle_torch.py (multi-threaded CPU twin of the NumPy oracle; psgd.py:554-627) in float64 "
+                        "and float32 on the same inputs, one step from the state the timed steps left; passed = every "
+                        "output within 1e-5 of the float64 twin, or as close to it as the float32 oracle is",
+                seconds=round(time.perf_counter() - t0, 1))
 
 
 # ---------------------------------------------------------------------------------------------
@@ -459,18 +539,19 @@ def _oracle_uvd_step(T, st, i):
 
 
 def _uvd_host_state(n, r, n_total, as_torch=False):
-    rng = np.random.default_rng(2024)
+    """Same distributions as the GPU arm's synthetic state (run_uvd), generated on the host."""
+    import torch
+    gen = torch.Generator().manual_seed(2024)
     uv = (1.0 / (n_total * r)) ** 0.5
-    U = (rng.standard_normal((n, r), dtype=np.float32) * uv)
-    V = (rng.standard_normal((n, r), dtype=np.float32) * uv)
-    d = np.ones((n, 1), np.float32)
-    v = rng.standard_normal((n, 1), dtype=np.float32)
-    h = ((0.5 + 1.5 * rng.random((n, 1), dtype=np.float32)) * v + 0.1 * rng.standard_normal((n, 1), dtype=np.float32)).astype(np.float32)
-    g = rng.standard_normal((n, 1), dtype=np.float32)
+    U = torch.randn(n, r, generator=gen) * uv
+    V = torch.randn(n, r, generator=gen) * uv
+    d = torch.ones(n, 1)
+    v = torch.randn(n, 1, generator=gen)
+    h = (0.5 + 1.5 * torch.rand(n, 1, generator=gen)) * v + 0.1 * torch.randn(n, 1, generator=gen)
+    g = torch.randn(n, 1, generator=gen)
     st = (U, V, d, v, h, g)
-    if as_torch:
-        import torch
-        st = tuple(torch.from_numpy(x) for x in st)
+    if not as_torch:
+        st = tuple(x.numpy() for x in st)
     return st
 
 
@@ -478,13 +559,18 @@ _CPU_PORT = ("multi-threaded torch-CPU port of psgd.py:554-627 (oracle/psgd_orac
              "ATen/OpenMP/MKL kernels, checked against the NumPy oracle; TensorFlow is not installable in this image)")
 
 
-def _time_cpu_uvd(n_total, r, budget_s, steps, warmup, cap_rows=20_000_000):
-    """Time the CPU port on a bounded row sample and scale linearly in N (every op of the path is O(N r^2))."""
+def _time_cpu_uvd(n_total, r, budget_s, steps, warmup, cap_rows=20_000_000, full=False):
+    """Time the CPU port.  full=True (the reference arm): every step runs ALL n_total rows.  Otherwise (the
+    `cpu_baseline` leg of the GPU arm, bounded to ~20 s) a row sample is timed and scaled linearly in N -- every op of
+    the path is O(N r^2)."""
     from oracle import psgd_oracle_torch as T
-    st = _uvd_host_state(200_000, r, n_total, as_torch=True)
-    _oracle_uvd_step(T, st, 0)
-    t0 = time.perf_counter(); _oracle_uvd_step(T, st, 0); per_row = (time.perf_counter() - t0) / 200_000
-    n_s = int(min(n_total, cap_rows, max(200_000, budget_s / max(per_row, 1e-12) / max(steps + warmup, 1))))
+    if full:
+        n_s = int(n_total)
+    else:
+        st = _uvd_host_state(200_000, r, n_total, as_torch=True)
+        _oracle_uvd_step(T, st, 0)
+        t0 = time.perf_counter(); _oracle_uvd_step(T, st, 0); per_row = (time.perf_counter() - t0) / 200_000
+        n_s = int(min(n_total, cap_rows, max(200_000, budget_s / max(per_row, 1e-12) / max(steps + warmup, 1))))
     st = _uvd_host_state(n_s, r, n_total, as_torch=True)
     for i in range(warmup):
         st, _ = _oracle_uvd_step(T, st, i)
@@ -514,58 +600,77 @@ def run_reference(args, rank, world):
     torch.set_num_threads(max(1, os.cpu_count() or 1))      # torchrun pins OMP_NUM_THREADS=1 per rank; this arm is rank 0 alone
     n_total, r = args.n, args.rank
     if args.workload == "kron":
-        return run_reference_kron(args)
+        return run_reference_kron(args, full=True, world=world)
     if args.workload == "all":
         args.workload = "uvd"
         out = run_reference(args, rank, world)
-        kr = run_reference_kron(args)
-        out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "config", "cpu_baseline", "e2e")}
+        kr = run_reference_kron(args, full=True, world=world)
+        out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "steps", "warmup", "config", "cpu_baseline", "e2e")}
         args.workload = "all"
         return out
-    dt, n_s = _time_cpu_uvd(n_total, r, 100.0, args.steps, args.warmup)
-    full_ms = dt * 1e3 * (n_total / n_s)
+    # the stated configuration, not a sample: every one of the K timed steps runs all n_total rows (10 GB of host state
+    # at 1e8 x rank 10, ~5 s per step on 16 threads)
+    dt, n_s = _time_cpu_uvd(n_total, r, 0.0, args.steps, args.warmup, full=True)
+    assert n_s == n_total
+    full_ms = dt * 1e3
     value = 1e3 / full_ms
-    sample = (f"{_CPU_PORT} on {n_s:,} of {n_total:,} rows per step, scaled linearly to the full vector; "
-              f"{os.cpu_count()} logical cores, {_cpu_threads()} threads used")
+    sample = (f"{_CPU_PORT}; FULL size: all {n_total:,} rows in each of the {args.steps} timed steps "
+              f"({args.warmup} warm-up), nothing scaled; {os.cpu_count()} logical cores, {_cpu_threads()} threads used")
     return dict(impl="reference", metric=METRIC, value=round(value, 5), unit=UNIT, n_gpus=world, steps=args.steps,
                 warmup=args.warmup, ms_per_step=round(full_ms, 2), higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"UVd rank-{r} update+apply on a flattened {n_total:,}-parameter vector (BASELINE configs[3])",
-                            n_params=n_total, rank=r),
+                config=uvd_config(n_total, r, world),
                 cpu_baseline=dict(value=round(value, 5), unit=UNIT, cores=_cpu_threads(), kind="port", sample=sample),
                 e2e=dict(value=round(value, 5), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
 
-def run_reference_kron(args):
+def run_reference_kron(args, full=True, world=1):
+    """The CPU port of psgd.py:156-192 on the Kron stack.  full=True (the reference arm): ALL `layers` layers at the
+    full n x n size in every step -- at ~1.2 s per 4096^2 layer-step on 16 threads a 24-layer step takes ~30 s, so the
+    step count is bounded (1 warm-up + at most 2 timed steps) to keep the whole arm within a few minutes; the figure
+    is measured, not scaled.  full=False (the `cpu_baseline` leg of the GPU arm, ~10-20 s): ONE full-size layer per
+    step, scaled by the layer count only (layers are independent and identical in cost)."""
     import torch
     from oracle import psgd_oracle_torch as T
     n = args.kron_n
     L = args.layers
+    Lrun = L if full else 1
+    steps = max(1, min(args.steps, 2))
+    warmup = min(args.warmup, 1)
     gen = torch.Generator().manual_seed(1000)
-    # bounded sample: one layer at reduced size, scaled by the cubic flop count (26 n^3 per layer-step)
-    ns = min(n, 2048)
-    Ql = torch.eye(ns); Qr = torch.eye(ns)
+    Ql = [torch.eye(n) for _ in range(Lrun)]
+    Qr = [torch.eye(n) for _ in range(Lrun)]
+    S = [0.5 + 1.5 * torch.rand(n, 1, generator=gen) for _ in range(Lrun)]
+    Tm = [0.5 + 1.5 * torch.rand(1, n, generator=gen) for _ in range(Lrun)]
+    dX = [torch.randn(n, n, generator=gen) for _ in range(Lrun)]
+    dG = [s * x * t + 0.1 * torch.randn(n, n, generator=gen) for s, x, t in zip(S, dX, Tm)]
+    G = [torch.randn(n, n, generator=gen) for _ in range(Lrun)]
 
-    def one(Ql, Qr):
-        dX = torch.randn(ns, ns, generator=gen); dG = torch.randn(ns, ns, generator=gen)
-        G = torch.randn(ns, ns, generator=gen)
-        Ql, Qr = T.update_precond_dense_dense(Ql, Qr, dX, dG, 0.01)
-        return Ql, Qr, T.precond_grad_dense_dense(Ql, Qr, G)
-    for _ in range(args.warmup):
-        Ql, Qr, _p = one(Ql, Qr)
+    def one_step():
+        for l in range(Lrun):
+            Ql[l], Qr[l] = T.update_precond_dense_dense(Ql[l], Qr[l], dX[l], dG[l], 0.01)
+            T.precond_grad_dense_dense(Ql[l], Qr[l], G[l])
+    for _ in range(warmup):
+        one_step()
     t0 = time.perf_counter()
-    for _ in range(args.steps):
-        Ql, Qr, _p = one(Ql, Qr)
-    dt = (time.perf_counter() - t0) / max(args.steps, 1)
-    full = dt * (n / ns) ** 3 * L
-    value = 1.0 / full
-    sample = (f"multi-threaded torch-CPU port of psgd.py:156-192 (oracle/psgd_oracle_torch.py; TensorFlow unavailable): one "
-              f"{ns}x{ns} dense-dense layer per step ({dt * 1e3:.0f} ms), scaled by (n/{ns})^3 x {L} layers; "
-              f"{os.cpu_count()} logical cores, {_cpu_threads()} threads used")
-    return dict(impl="reference", metric=METRIC, value=round(value, 6), unit=UNIT, n_gpus=1, steps=args.steps,
-                warmup=args.warmup, ms_per_step=round(full * 1e3, 1), higher_is_better=True, scaling=args.scaling,
+    for _ in range(steps):
+        one_step()
+    dt = (time.perf_counter() - t0) / steps
+    step_s = dt * (L / Lrun)
+    value = 1.0 / step_s
+    if full:
+        sample = (f"multi-threaded torch-CPU port of psgd.py:156-192 (oracle/psgd_oracle_torch.py; TensorFlow unavailable); FULL "
+                  f"size: all {L} layers of {n}x{n} in each of {steps} timed steps ({warmup} warm-up; the requested "
+                  f"--steps {args.steps} --warmup {args.warmup} are capped for this nested workload), nothing scaled; "
+                  f"{os.cpu_count()} logical cores, {_cpu_threads()} threads used")
+    else:
+        sample = (f"multi-threaded torch-CPU port of psgd.py:156-192 (oracle/psgd_oracle_torch.py; TensorFlow unavailable): one "
+                  f"full-size {n}x{n} dense-dense layer per step ({dt * 1e3:.0f} ms, {steps} timed steps), times {L} "
+                  f"independent layers; {os.cpu_count()} logical cores, {_cpu_threads()} threads used")
+    return dict(impl="reference", metric=METRIC, value=round(value, 6), unit=UNIT, n_gpus=world, steps=steps,
+                warmup=warmup, ms_per_step=round(step_s * 1e3, 1), higher_is_better=True, scaling=args.scaling,
                 vs_baseline=None, dtype="f32", data="synthetic",
-                config=dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply (BASELINE configs[2])"),
+                config=kron_config(L, n, world),
                 cpu_baseline=dict(value=round(value, 6), unit=UNIT, cores=_cpu_threads(), kind="port", sample=sample),
                 e2e=dict(value=round(value, 6), unit=UNIT, h2d_bytes_per_step=0, d2h_bytes_per_step=0))
 
@@ -616,6 +721,7 @@ def main():
     ap.add_argument("--no-separate", action="store_true", help="UVd: skip the extra timing of the two-call form")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-parity", action="store_true", help="skip the CUDA-vs-oracle check at the benchmarked size")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     rank, world, local = dist_env()
@@ -649,8 +755,13 @@ def main():
             if args.workload == "kron":
                 out = kr
             elif out is not None and kr is not None:
-                out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "scaling", "dtype", "config", "roofline",
-                                                   "kernels", "cpu_baseline", "e2e", "gpu_launches", "clocks")}
+                out["kron"] = {k: kr[k] for k in ("value", "unit", "ms_per_step", "scaling", "dtype", "config", "run", "roofline",
+                                                   "kernels", "parity", "cpu_baseline", "e2e", "gpu_launches", "clocks")}
+                if out.get("roofline") is not None:       # the second north-star workload's headline inside the parsed object
+                    out["roofline"]["kron_stack"] = dict(value=kr["value"], unit=kr["unit"], ms_per_step=kr["ms_per_step"],
+                                                         kernel_frac=(kr["roofline"] or {}).get("frac"),
+                                                         step_frac=(kr["roofline"] or {}).get("step_frac"),
+                                                         parity_rel_err=(kr["parity"] or {}).get("max_rel_err"))
         if args.workload == "all" and world == 1 and out is not None:
             # the other streaming rows of SURVEY.md section 8(a): diagonal, X-shape, (norm,scale) Kron pair, dense apply
             import gc

@@ -10,6 +10,17 @@ GB/s against the algorithmic byte counts of SURVEY.md section 8(d):
     SPLU       update 2*(8nr+16n) + 8nr + 8n = 24nr + 40n B,   (n = 5e7, r = 10; big inputs read twice -- reductions
                apply 2*(8nr+12n) + 4n = 16nr + 28n B            gate the maps -- outputs written once, like UVd)
 
+and the latency-bound configurations of BASELINE.json ("report us/step for one batched launch"):
+
+    cfg1  LeNet5, five (dense, dense) pairs  W in {[26,6], [151,16], [257,120], [121,84], [85,10]}   (mnist_with_lenet5.py:12-16)
+    cfg2  UVd rank 10 on N = 1021 parameters                                                         (rnn_xor_UVd_preconditioner.py:37-41)
+    cfg5  NMT, seven pairs in ONE batched call: enc-emb [9414,256] (scale,dense), enc-rnn [1281,1024] (norm,scale),
+          att-in [2048,10] (scale,dense), att-v [1,10] (dense,dense), dec-emb [4935,256] (scale,dense),
+          dec-rnn [2305,1024] (norm,scale), dec-fc [1025,4935] (norm,scale)     (neural_machine_translation_with_attention.py:98-148)
+each as one update+apply step launched eagerly from Python and replayed from a CUDA graph (psgd_tf_b200/graphs.py),
+plus the two mixed dense/structured Kron pairs at a size that fills the GPU: (norm, dense) [16384, 1024] and
+(dense, scale) [1024, 16384].
+
 Run by bench.py (nested under "aux" in the default JSON line) or directly:  python bench_aux.py
 """
 from __future__ import annotations
@@ -117,6 +128,158 @@ def run_aux(peak_gbs: float, steps: int = 10):
     ms_a = _time(torch, lambda: psgd.precond_grad_splu(st[0], st[1], st[2], st[3], [gg]), steps)
     assert torch.isfinite(st[0]).all() and torch.isfinite(st[2]).all()
     add("SPLU", [n, r], ms_u, ms_a, (24.0 * r + 40.0) * n, (16.0 * r + 28.0) * n)
+    del L12, U12, l3, u3, dx, dg, gg, st
+    torch.cuda.empty_cache()
+    rows.extend(run_small_configs(peak_gbs, steps=max(steps, 20)))
+    rows.extend(run_mixed_pairs(peak_gbs, steps=steps))
+    return rows
+
+
+def _factor(torch, kind, n, dev):
+    """Identity-type initial factors (README.md:48; neural_machine_translation_with_attention.py:94-95)."""
+    if kind == "dense":
+        return torch.eye(n, device=dev)
+    if kind == "norm":
+        return torch.stack([torch.ones(n, device=dev), torch.zeros(n, device=dev)])
+    return torch.ones(1, n, device=dev)
+
+
+def _kron_step_bytes(kl, kr, M, N):
+    """Compulsory HBM bytes of one update+apply of a pair: dX, dG, G read and the result written (16 MN), dX once more
+    when a global reduction gates the statistics ((norm, .) pairs), dense factors read once per use."""
+    b = 16.0 * M * N + (4.0 * M * N if kl == "norm" else 0.0)
+    for k, n in ((kl, M), (kr, N)):
+        if k == "dense":
+            b += 4.0 * n * n * 4          # update: product + solve; apply: two products
+    return b
+
+
+def run_small_configs(peak_gbs: float, steps: int = 20):
+    """cfg1 / cfg2 / cfg5: microseconds per update+apply step, eager and from a CUDA graph."""
+    import torch
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200.graphs import KronStepGraphs, UVdStepGraphs
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(11)
+    ctx = psgd.get_context()
+    rows = []
+
+    def kron_config(name, cite, layers):
+        Ql = [_factor(torch, kl, M, dev) for kl, kr, M, N in layers]
+        Qr = [_factor(torch, kr, N, dev) for kl, kr, M, N in layers]
+        sets = []
+        for _ in range(2):
+            dX = [torch.randn(M, N, device=dev, generator=g) for _, _, M, N in layers]
+            dG = [1.3 * x + 0.1 * torch.randn(x.shape, device=dev, generator=g) for x in dX]
+            G = [torch.randn(M, N, device=dev, generator=g) for _, _, M, N in layers]
+            sets.append((dX, dG, G))
+        state = [Ql, Qr]
+        k = [0]
+
+        def eager():
+            dX, dG, G = sets[k[0] & 1]; k[0] += 1
+            new = psgd.update_precond_kron_batched(state[0], state[1], dX, dG, 0.01)
+            state[0], state[1] = [a for a, _ in new], [b for _, b in new]
+            return psgd.precond_grad_kron_batched(state[0], state[1], G)
+
+        l0 = ctx.launch_count
+        eager()
+        per_step_launches = ctx.launch_count - l0
+        ms_e = _time(torch, eager, steps)
+        gr = KronStepGraphs(state[0], state[1], 0.01)
+
+        def graphed():
+            dX, dG, G = sets[k[0] & 1]; k[0] += 1
+            return gr.step(dX, dG, G)
+
+        for _ in range(6):            # eager warm-up + capture of the four (direction, input set) graphs
+            graphed()
+        ms_g = _time(torch, graphed, steps)
+        pre = graphed()
+        assert all(torch.isfinite(p).all() for p in pre) and all(torch.isfinite(a).all() for a, _ in gr.factors)
+        byts = sum(_kron_step_bytes(kl, kr, M, N) for kl, kr, M, N in layers)
+        rows.append(dict(path=name, cite=cite, layers=[[kl, kr, M, N] for kl, kr, M, N in layers],
+                         launches_per_step=int(per_step_launches), eager_us_per_step=round(ms_e * 1e3, 1),
+                         graph_us_per_step=round(ms_g * 1e3, 1), steps_per_s=round(1e3 / ms_g, 1),
+                         step_compulsory_MB=round(byts / 1e6, 2), graph_GBps=round(byts / ms_g / 1e6, 1),
+                         graph_frac=round(byts / ms_g / 1e6 / peak_gbs, 4)))
+
+    lenet = [("dense", "dense", M, N) for M, N in ((26, 6), (151, 16), (257, 120), (121, 84), (85, 10))]
+    kron_config("cfg1 LeNet5 five (dense,dense) pairs, one batched call", "mnist_with_lenet5.py:12-16,51-53", lenet)
+    nmt = [("scale", "dense", 9414, 256), ("norm", "scale", 1281, 1024), ("scale", "dense", 2048, 10),
+           ("dense", "dense", 1, 10), ("scale", "dense", 4935, 256), ("norm", "scale", 2305, 1024),
+           ("norm", "scale", 1025, 4935)]
+    kron_config("cfg5 NMT seven mixed pairs, one batched call", "neural_machine_translation_with_attention.py:98-148", nmt)
+    kron_config("cfg5 NMT, the three (norm,scale) pairs only", "neural_machine_translation_with_attention.py:118,138,146",
+                [l for l in nmt if l[:2] == ("norm", "scale")])
+
+    # ---- cfg2: UVd rank 10 on the RNN-XOR model's 1021 parameters ----------------------------------------------------
+    n, r = 1021, 10
+    U = torch.randn(n, r, device=dev, generator=g) * (1.0 / (n * r)) ** 0.5
+    V = torch.randn(n, r, device=dev, generator=g) * (1.0 / (n * r)) ** 0.5
+    d = torch.ones(n, 1, device=dev)
+    ins = []
+    for _ in range(2):
+        v = torch.randn(n, 1, device=dev, generator=g)
+        ins.append((v, 1.3 * v + 0.1 * torch.randn(n, 1, device=dev, generator=g), torch.randn(n, 1, device=dev, generator=g)))
+    k = [0]
+
+    def eager_uvd():
+        v, h, gg = ins[k[0] & 1]; k[0] += 1
+        return psgd.update_precond_and_grad_UVd(U, V, d, v, h, gg, 0.01, psgd._tiny, balance=False, update_U=bool(k[0] & 2))
+
+    l0 = ctx.launch_count
+    eager_uvd()
+    per_step_launches = ctx.launch_count - l0
+    ms_e = _time(torch, eager_uvd, steps)
+    gu = UVdStepGraphs(U, V, d, 0.01, psgd._tiny, fused=True)
+
+    def graphed_uvd():
+        v, h, gg = ins[k[0] & 1]; k[0] += 1
+        return gu.step(v, h, gg, False, bool(k[0] & 2))
+
+    for _ in range(10):
+        graphed_uvd()
+    ms_g = _time(torch, graphed_uvd, steps)
+    assert torch.isfinite(graphed_uvd()).all() and torch.isfinite(U).all()
+    rows.append(dict(path="cfg2 UVd rank 10, N = 1021 (fused update+apply call)", cite="rnn_xor_UVd_preconditioner.py:37-41",
+                     launches_per_step=int(per_step_launches), eager_us_per_step=round(ms_e * 1e3, 1),
+                     graph_us_per_step=round(ms_g * 1e3, 1), steps_per_s=round(1e3 / ms_g, 1)))
+    return rows
+
+
+def run_mixed_pairs(peak_gbs: float, steps: int = 10):
+    """(norm, dense) and (dense, scale): one dense factor on the tensor cores + the streaming pieces of the structured
+    one.  Dense flop count of the reference's op sequence: with the dense side n and the long side m,
+    update 2mn^2 (A) + mn^2 (solve) + 4mn^2 (two Gram products) + 2n^3, apply 4mn^2 -> 11 m n^2 + 2 n^3 per step."""
+    import torch
+    import psgd_tf_b200 as psgd
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(13)
+    rows = []
+    for kl, kr, M, N in (("norm", "dense", 16384, 1024), ("dense", "scale", 1024, 16384)):
+        state = [_factor(torch, kl, M, dev), _factor(torch, kr, N, dev)]
+        dX = torch.randn(M, N, device=dev, generator=g)
+        dG = 1.3 * dX + 0.1 * torch.randn(M, N, device=dev, generator=g)
+        G = torch.randn(M, N, device=dev, generator=g)
+
+        def upd():
+            state[0], state[1] = psgd.update_precond_kron(state[0], state[1], dX, dG, 0.01)
+
+        ms_u = _time(torch, upd, steps)
+        ms_a = _time(torch, lambda: psgd.precond_grad_kron(state[0], state[1], G), steps)
+        assert torch.isfinite(state[0]).all() and torch.isfinite(state[1]).all()
+        n, m = (N, M) if kr == "dense" else (M, N)
+        fl_u, fl_a = 7.0 * m * n * n + 2.0 * n ** 3, 4.0 * m * n * n
+        byts = _kron_step_bytes(kl, kr, M, N)
+        rows.append(dict(path=f"kron ({kl},{kr})", shape=[M, N], update_ms=round(ms_u, 4), apply_ms=round(ms_a, 4),
+                         steps_per_s=round(1e3 / (ms_u + ms_a), 2),
+                         update_TFLOPs=round(fl_u / ms_u / 1e9, 1), apply_TFLOPs=round(fl_a / ms_a / 1e9, 1),
+                         step_dense_GFLOP=round((fl_u + fl_a) / 1e9, 1), step_TFLOPs=round((fl_u + fl_a) / (ms_u + ms_a) / 1e9, 1),
+                         step_compulsory_GB=round(byts / 1e9, 3), step_GBps=round(byts / (ms_u + ms_a) / 1e6, 1),
+                         step_frac_hbm=round(byts / (ms_u + ms_a) / 1e6 / peak_gbs, 4)))
     return rows
 
 

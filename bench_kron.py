@@ -40,6 +40,7 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
     import torch.distributed as dist
     import psgd_tf_b200 as psgd
     from psgd_tf_b200 import partition
+    from bench import kron_config
 
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
@@ -53,7 +54,7 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
     Qr = [torch.eye(n, device=dev) for _ in mine]
     S = [0.5 + 1.5 * torch.rand(n, 1, device=dev, generator=gen) for _ in mine]
     T = [0.5 + 1.5 * torch.rand(1, n, device=dev, generator=gen) for _ in mine]
-    POOL = 2
+    POOL = 4          # cycle through >= 4 pre-generated input sets
     pool = []
     for _ in range(POOL):
         dX = [torch.randn(n, n, device=dev, generator=gen) for _ in mine]
@@ -132,6 +133,14 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
                              "clipping and tile skipping) over its launch time; step_*: the dense count of the "
                              "reference's op sequence (26 n^3 per layer-step) over the step time -- skipping "
                              "structurally-zero tiles legitimately raises that fraction above the kernel's")
+
+    # ---- parity at the benchmarked size, outside every timed region: layer 0's next step on the GPU and through the
+    # CPU twin of the oracle (psgd.py:156-192) on the same inputs, from the factors the timed steps left behind
+    parity = None
+    if rank == 0 and world == 1 and not getattr(args, "no_parity", False) and mine:
+        parity = kron_parity(psgd, Ql[0], Qr[0], pool[0][0][0], pool[0][1][0], pool[0][2][0])
+        if roofline is not None:
+            roofline["parity_rel_err"] = parity["max_rel_err"]
 
     # ---- end to end: host (pinned) dX, dG, G per step, preconditioned gradients read back ----------------
     # Same public API (the batched calls); the step's inputs are uploaded from pinned host memory and its results read
@@ -216,17 +225,33 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="f32 (3xTF32 tensor-core products, fp32 accumulate)", data="synthetic",
-        config=dict(workload=f"{L}-layer {n}x{n} dense-dense Kron update+apply, batched (BASELINE configs[2])", layers=L, n=n,
-                    layers_per_gpu=len(mine), parallelism=f"layer-sharded x{world} + all-gather of preconditioned gradients",
-                    l2_policy=f"inputs larger than L2: {len(mine) * 5 * 4 * n * n / 1e9:.1f} GB of factors+inputs per GPU per step vs 126 MB L2",
-                    step_size=0.01),
+        config=kron_config(L, n, world), run=dict(layers_per_gpu=len(mine)), parity=parity,
         roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
 
 
-def cpu_baseline_kron(L, n, ns=2048, steps=2):
-    """The CPU port (multi-threaded torch-CPU restatement of psgd.py:156-192) on one reduced layer, scaled by the cubic
-    flop count -- the same sample `bench.py --impl reference --workload kron` times."""
+def kron_parity(psgd, Ql, Qr, dX, dG, G):
+    import torch
+    from oracle import psgd_oracle_torch as T
+    from bench import rel_err_chunked
+    torch.set_num_threads(max(1, os.cpu_count() or 1))
+    t0 = time.perf_counter()
+    ql, qr = psgd.update_precond_kron(Ql, Qr, dX, dG, 0.01)
+    pre = psgd.precond_grad_kron(ql, qr, G)
+    got = dict(Ql=ql.cpu(), Qr=qr.cpu(), pre_grad=pre.cpu())
+    qlr, qrr = T.update_precond_dense_dense(Ql.cpu(), Qr.cpu(), dX.cpu(), dG.cpu(), 0.01)
+    want = dict(Ql=qlr, Qr=qrr, pre_grad=T.precond_grad_dense_dense(qlr, qrr, G.cpu()))
+    errs = {k: rel_err_chunked(got[k], want[k], 4) for k in got}
+    return dict(max_rel_err=float("%.3e" % max(errs.values())), rel_err={k: float("%.3e" % e) for k, e in errs.items()},
+                tolerance=1e-5, passed=bool(max(errs.values()) <= 1e-5), layer_shape=list(dX.shape),
+                against="oracle/psgd_oracle_torch.py (multi-threaded CPU twin of the NumPy oracle; psgd.py:156-192) on the "
+                        "same inputs: layer 0's next update + apply from the factors the timed steps left",
+                seconds=round(time.perf_counter() - t0, 1))
+
+
+def cpu_baseline_kron(L, n, steps=2):
+    """The CPU port (multi-threaded torch-CPU restatement of psgd.py:156-192) on ONE full-size layer per step, times
+    the layer count (bounded to ~10 s; `bench.py --impl reference` runs the whole stack)."""
     import argparse
     from bench import run_reference_kron
-    r = run_reference_kron(argparse.Namespace(kron_n=n, layers=L, steps=steps, warmup=1, scaling="strong"))
+    r = run_reference_kron(argparse.Namespace(kron_n=n, layers=L, steps=steps, warmup=1, scaling="strong"), full=False)
     return r["cpu_baseline"]

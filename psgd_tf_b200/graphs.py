@@ -83,3 +83,72 @@ class UVdStepGraphs:
                 self.kernel_launches += nk
         cur.wait_stream(s)
         return out
+
+
+class KronStepGraphs:
+    """CUDA-graph replay of one Kron training-step hot path over a (ragged) list of layers:
+    ``update_precond_kron_batched`` followed by ``precond_grad_kron_batched`` with the UPDATED factors
+    (mnist_with_lenet5.py:51-53, neural_machine_translation_with_attention.py:203-205).
+
+    Small layers (LeNet5, the NMT model's factors) are launch-latency bound: a 7-pair NMT step is ~60 launches of a few
+    microseconds each plus two Python/ctypes calls.  The chain has no host dependency, so it is captured once per set of
+    input buffers and replayed with one ``cudaGraphLaunch``.  The functional API returns NEW factors every step; to keep
+    addresses stable the factors ping-pong between two preallocated state sets (one graph per direction), so nothing is
+    copied.  ``factors`` returns the current ``[(Ql, Qr), ...]``; ``step`` returns the preconditioned gradients, which
+    belong to the graph (consume them before the same graph is replayed again)."""
+
+    def __init__(self, Qls, Qrs, step: float = 0.01):
+        if not all(q.is_cuda for q in list(Qls) + list(Qrs)):
+            raise RuntimeError("KronStepGraphs: factors must live on a CUDA device (no CPU path)")
+        self._state = [[(ql.clone(), qr.clone()) for ql, qr in zip(Qls, Qrs)],
+                       [(torch.empty_like(ql), torch.empty_like(qr)) for ql, qr in zip(Qls, Qrs)]]
+        self._cur = 0
+        self.step_size = float(step)
+        self._stream = torch.cuda.Stream(device=Qls[0].device)
+        self._graphs: Dict[Tuple, Tuple] = {}
+        self._warm = False
+        self._ws_bytes = -1
+        self.replays = 0
+        self.kernel_launches = 0
+
+    @property
+    def factors(self):
+        return self._state[self._cur]
+
+    def _eager(self, src, dst, dXs, dGs, Gs, pre_out=None):
+        Qls, Qrs = [a for a, _ in self._state[src]], [b for _, b in self._state[src]]
+        new = _psgd.update_precond_kron_batched(Qls, Qrs, dXs, dGs, self.step_size, outs=self._state[dst])
+        return _psgd.precond_grad_kron_batched([a for a, _ in new], [b for _, b in new], Gs, outs=pre_out)
+
+    def step(self, dXs, dGs, Gs):
+        dev = self._state[0][0][0].device
+        cur = torch.cuda.current_stream(dev)
+        s = self._stream
+        s.wait_stream(cur)
+        src, dst = self._cur, 1 - self._cur
+        with torch.cuda.stream(s):
+            ctx = _psgd.get_context(dev.index)
+            if ctx.workspace_bytes != self._ws_bytes:
+                self._graphs.clear()
+                self._warm = False
+            if not self._warm:
+                pre = self._eager(src, dst, dXs, dGs, Gs)
+                self._warm = True
+                self._ws_bytes = ctx.workspace_bytes
+            else:
+                key = (src,) + tuple(t.data_ptr() for t in list(dXs) + list(dGs) + list(Gs))
+                entry = self._graphs.get(key)
+                if entry is None:
+                    pre_out = [torch.empty_like(g) for g in Gs]
+                    graph = torch.cuda.CUDAGraph()
+                    before = ctx.launch_count
+                    with torch.cuda.graph(graph, stream=s):
+                        pre = self._eager(src, dst, dXs, dGs, Gs, pre_out)
+                    entry = self._graphs[key] = (graph, pre, ctx.launch_count - before)
+                graph, pre, nk = entry
+                graph.replay()
+                self.replays += 1
+                self.kernel_launches += nk
+        self._cur = dst
+        cur.wait_stream(s)
+        return pre

@@ -327,15 +327,19 @@ def _layer_array(ctx_fields):
     return arr
 
 
-def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
+def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01, outs=None):
     """Update every layer's factor pair in one library call.  Lists of tensors in, list of ``(Ql', Qr')`` out.
     Equivalent to ``[update_precond_kron(*a, step) for a in zip(Qls, Qrs, dXs, dGs)]``
-    (mnist_with_lenet5.py:51)."""
+    (mnist_with_lenet5.py:51).  ``outs``: optional list of preallocated ``(Ql', Qr')`` buffers (they must not alias the
+    inputs), so that a caller can ping-pong two state sets without allocating -- what CUDA-graph replay needs."""
     n = len(Qls)
     if not (len(Qrs) == len(dXs) == len(dGs) == n):
         raise ValueError("update_precond_kron_batched: the four lists differ in length")
     Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
     dXs = [_in(x, "dX") for x in dXs]; dGs = [_in(g, "dG") for g in dGs]
+    given = outs
+    if given is not None and len(given) != n:
+        raise ValueError("update_precond_kron_batched: outs differs in length")
     outs, fields, keep = [None] * n, [], []
     for i in range(n):
         if Qls[i].dim() != 2 or Qrs[i].dim() != 2:
@@ -349,7 +353,13 @@ def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
         if dXs[i].device != dXs[0].device:
             raise ValueError(f"update_precond_kron_batched (layer {i}): all layers of a call must live on one device")
         M, N = dXs[i].shape
-        lo, ro = torch.empty_like(Qls[i]), torch.empty_like(Qrs[i])
+        if given is not None:
+            lo, ro = _inplace(given[i][0], "Ql_out"), _inplace(given[i][1], "Qr_out")
+            if lo.shape != Qls[i].shape or ro.shape != Qrs[i].shape or lo.data_ptr() == Qls[i].data_ptr() or \
+                    ro.data_ptr() == Qrs[i].data_ptr():
+                raise ValueError(f"update_precond_kron_batched (layer {i}): outs must match the factors' shapes and not alias them")
+        else:
+            lo, ro = torch.empty_like(Qls[i]), torch.empty_like(Qrs[i])
         outs[i] = (lo, ro)
         fields.append(dict(kind_l=kl, kind_r=kr, M=M, N=N, Ql=Qls[i].data_ptr(), Qr=Qrs[i].data_ptr(),
                            dX=dXs[i].data_ptr(), dG=dGs[i].data_ptr(), Ql_out=lo.data_ptr(), Qr_out=ro.data_ptr()))
@@ -360,13 +370,17 @@ def update_precond_kron_batched(Qls, Qrs, dXs, dGs, step=0.01):
     return outs
 
 
-def precond_grad_kron_batched(Qls, Qrs, Grads):
-    """``[precond_grad_kron(Ql, Qr, G) for ...]`` in one library call (mnist_with_lenet5.py:53)."""
+def precond_grad_kron_batched(Qls, Qrs, Grads, outs=None):
+    """``[precond_grad_kron(Ql, Qr, G) for ...]`` in one library call (mnist_with_lenet5.py:53).  ``outs``: optional
+    preallocated result buffers (not aliasing ``Grads``)."""
     n = len(Qls)
     if not (len(Qrs) == len(Grads) == n):
         raise ValueError("precond_grad_kron_batched: the three lists differ in length")
     Qls = [_in(q, "Ql") for q in Qls]; Qrs = [_in(q, "Qr") for q in Qrs]
     Grads = [_in(g, "Grad") for g in Grads]
+    given = outs
+    if given is not None and len(given) != n:
+        raise ValueError("precond_grad_kron_batched: outs differs in length")
     outs, fields = [None] * n, []
     for i in range(n):
         if Qls[i].dim() != 2 or Qrs[i].dim() != 2:
@@ -380,7 +394,12 @@ def precond_grad_kron_batched(Qls, Qrs, Grads):
         if Grads[i].device != Grads[0].device:
             raise ValueError(f"precond_grad_kron_batched (layer {i}): all layers of a call must live on one device")
         M, N = Grads[i].shape
-        o = torch.empty_like(Grads[i])
+        if given is not None:
+            o = _inplace(given[i], "out")
+            if o.shape != Grads[i].shape or o.data_ptr() == Grads[i].data_ptr():
+                raise ValueError(f"precond_grad_kron_batched (layer {i}): outs must match Grads' shapes and not alias them")
+        else:
+            o = torch.empty_like(Grads[i])
         outs[i] = o
         fields.append(dict(kind_l=kl, kind_r=kr, M=M, N=N, Ql=Qls[i].data_ptr(), Qr=Qrs[i].data_ptr(),
                            G=Grads[i].data_ptr(), out=o.data_ptr()))

@@ -216,8 +216,17 @@ def test_uvd_rejects_bad_inputs(psgd):
     with pytest.raises(TypeError):
         psgd.precond_grad_UVd_math(dev(c["U"]).double(), dev(c["V"]), dev(c["d"]), dev(c["g"]))
     big = cases.uvd_case(11, 64, 17)
-    with pytest.raises(psgd.PsgdError, match="rank"):
+    with pytest.raises(ValueError, match="rank"):          # the Python mirror checks the documented limit up front
         psgd.precond_grad_UVd_math(dev(big["U"]), dev(big["V"]), dev(big["d"]), dev(big["g"]))
+    with pytest.raises(ValueError, match="rank"):          # ... before class UVd re-homes any parameter
+        w = torch.zeros(8, device="cuda", requires_grad=True)
+        psgd.UVd([w], rank_of_modification=psgd.MAX_UVD_RANK + 1)
+    assert w.data_ptr() != 0 and w.shape == (8,)
+    ctx = psgd.get_context()                                # and the C ABI itself refuses, with an error message
+    U, V, d, g = (dev(big[k]) for k in ("U", "V", "d", "g"))
+    out = torch.empty_like(g)
+    rc = ctx.lib.psgd_uvd_apply(ctx.handle, U.data_ptr(), V.data_ptr(), d.data_ptr(), g.data_ptr(), out.data_ptr(), 64, 17)
+    assert rc != 0 and b"rank" in ctx.lib.psgd_last_error()
 
 
 # ---------------------------------------------------------------------------------------------
@@ -358,6 +367,56 @@ def test_kron_lenet_batched_matches_per_layer(psgd):
         qlr, qrr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
         check(ql, qlr); check(qr, qrr)
         check(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"]))
+
+
+def test_kron_step_graph_replay_matches_eager(psgd):
+    """graphs.KronStepGraphs (factors ping-pong between two state sets, one CUDA graph per direction) replays exactly the
+    kernels of update_precond_kron_batched + precond_grad_kron_batched: bit-identical factors and results over a
+    mixed-format layer list (NMT-like: every canonical and mirrored combination)."""
+    from psgd_tf_b200.graphs import KronStepGraphs
+    layers = [("dense", "dense", 26, 6), ("scale", "dense", 300, 32), ("norm", "scale", 129, 260), ("dense", "norm", 24, 70),
+              ("dense", "dense", 1, 10), ("scale", "norm", 33, 40)]
+    cs = [cases.kron_case(900 + i, kl, kr, M, N) for i, (kl, kr, M, N) in enumerate(layers)]
+    ins = [([dev(np.roll(c["dX"], s, 0)) for c in cs], [dev(np.roll(c["dG"], s, 0)) for c in cs],
+            [dev(np.roll(c["G"], s, 0)) for c in cs]) for s in (0, 1)]
+    Ql, Qr = [dev(c["Ql"]) for c in cs], [dev(c["Qr"]) for c in cs]
+    gr = KronStepGraphs(Ql, Qr, 0.01)
+    for t in range(7):
+        dX, dG, G = ins[t & 1]
+        new = psgd.update_precond_kron_batched(Ql, Qr, dX, dG, 0.01)
+        Ql, Qr = [a for a, _ in new], [b for _, b in new]
+        want = psgd.precond_grad_kron_batched(Ql, Qr, G)
+        got = gr.step(dX, dG, G)
+        for a, b in zip(got, want):
+            assert torch.equal(a, b)
+        for (a, b), x, y in zip(gr.factors, Ql, Qr):
+            assert torch.equal(a, x) and torch.equal(b, y)
+    assert gr.replays >= 4
+    # one step of the graph-replayed state against the oracle as well
+    c0 = cs[0]
+    q = O.update_precond_kron(c0["Ql"], c0["Qr"], c0["dX"], c0["dG"], 0.01)
+    gr2 = KronStepGraphs([dev(c0["Ql"])], [dev(c0["Qr"])], 0.01)
+    pre = gr2.step([dev(c0["dX"])], [dev(c0["dG"])], [dev(c0["G"])])
+    check(pre[0], O.precond_grad_kron(q[0], q[1], c0["G"]))
+
+
+def test_kron_batched_rejects_inconsistent_layers(psgd):
+    """The batched forms run the same shape / device checks per layer as the single-layer entry points (a mismatched
+    layer would make the kernels index out of bounds)."""
+    c = cases.kron_case(3, "dense", "dense", 26, 6)
+    good = [dev(c[k]) for k in ("Ql", "Qr", "dX", "dG", "G")]
+    with pytest.raises(ValueError, match="layer 1"):
+        psgd.update_precond_kron_batched([good[0], good[0]], [good[1], good[1]], [good[2], dev(c["dX"][:20])],
+                                         [good[3], good[3]], 0.01)
+    with pytest.raises(ValueError, match="layer 0"):
+        psgd.precond_grad_kron_batched([dev(np.eye(25, dtype=np.float32))], [good[1]], [good[4]])
+    with pytest.raises(ValueError, match="length"):
+        psgd.precond_grad_kron_batched([good[0]], [good[1], good[1]], [good[4]])
+    with pytest.raises(ValueError):
+        psgd.precond_grad_UVd_math(dev(np.zeros((8, 2), np.float32)), dev(np.zeros((8, 3), np.float32)),
+                                   dev(np.ones((8, 1), np.float32)), dev(np.ones((8, 1), np.float32)))
+    with pytest.raises(ValueError):
+        psgd.precond_grad_dense(dev(np.zeros((6, 4), np.float32)), [dev(np.zeros(6, np.float32))])
 
 
 def test_kron_trajectory_100_steps(psgd):
