@@ -769,6 +769,15 @@ def main():
             torch.cuda.empty_cache()
             from bench_aux import run_aux
             out["aux"] = run_aux(load_peaks()["hbm"], steps=10)
+        if args.workload == "all" and world > 1:
+            # diagonal / X-shape on the sharded vector: every rank takes part, rank 0 reports
+            import gc
+            gc.collect()
+            torch.cuda.empty_cache()
+            from bench_aux import run_aux_sharded
+            rows = run_aux_sharded(load_peaks()["hbm"], rank, world)
+            if out is not None:
+                out["aux"] = rows
         if out is not None:
             emit(out)
     finally:

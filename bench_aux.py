@@ -283,6 +283,62 @@ def run_mixed_pairs(peak_gbs: float, steps: int = 10):
     return rows
 
 
+def run_aux_sharded(peak_gbs: float, rank: int, world: int, steps: int = 10, n_total: int = 100_000_000):
+    """Diagonal and X-shape at N > 1 GPUs: the vector is sharded by contiguous chunk (diagonal) or by
+    mirrored chunk pairs (X-shape, partition.xmat_shard_slices); the only exchange is the max of |nabla| per update,
+    through whatever exchange bench.py installed on the context (peer-memory kernel or the all-reduce hook).  Timed on
+    the device between barriers, max over ranks; GB/s is the whole job's."""
+    import torch
+    import torch.distributed as dist
+    import psgd_tf_b200 as psgd
+    from psgd_tf_b200 import partition
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    g = torch.Generator(device=dev).manual_seed(70 + rank)
+    rows = []
+
+    def timed(fn):
+        for _ in range(3):
+            fn()
+        dist.barrier(); torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        dist.barrier(); torch.cuda.synchronize()
+        t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    for name, bu, ba in (("diagonal", 28.0, 12.0), ("X-shape", 40.0, 16.0)):
+        if name == "diagonal":
+            lo, hi = partition.chunk_bounds(n_total, world, rank)
+            n = hi - lo
+        else:
+            n = sum(b - a for a, b in partition.xmat_shard_slices(n_total, world, rank))
+        v = torch.randn(n, device=dev, generator=g)
+        h = (0.5 + 1.5 * torch.rand(n, device=dev, generator=g)) * v + 0.1 * torch.randn(n, device=dev, generator=g)
+        gr = torch.randn(n, device=dev, generator=g)
+        a = torch.ones(n, device=dev)
+        b = torch.zeros(n, device=dev)
+        if name == "diagonal":
+            ms_u = timed(lambda: psgd.update_precond_diag(a, v, h, 0.01))
+            ms_a = timed(lambda: psgd.precond_grad_diag(a, gr))
+        else:
+            ms_u = timed(lambda: psgd.update_precond_Xmat(a, b, v, h, 0.01))
+            ms_a = timed(lambda: psgd.precond_grad_Xmat(a, b, gr))
+        assert torch.isfinite(a).all()
+        tot = (bu + ba) * n_total
+        rows.append(dict(path=f"{name} sharded x{world}", shape=[n_total], rows_per_gpu=int(n), update_ms=round(ms_u, 4),
+                         apply_ms=round(ms_a, 4), steps_per_s=round(1e3 / (ms_u + ms_a), 2),
+                         step_algorithmic_GB=round(tot / 1e9, 3), step_GBps=round(tot / (ms_u + ms_a) / 1e6, 1),
+                         step_frac=round(tot / (ms_u + ms_a) / 1e6 / (peak_gbs * world), 4)))
+        del v, h, gr, a, b
+        torch.cuda.empty_cache()
+    return rows
+
+
 if __name__ == "__main__":
     import torch
     from bench import load_peaks

@@ -78,6 +78,7 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 #define PSGD_K_UVD_MAP_FUSED 7   /* fused update sweep 2: a,b,nablaD per row + rank-2 update of U (or V) */
 #define PSGD_K_UVD_D_UPDATE 8    /* fused update pass 3: d -= mu_d d nablaD                              */
 #define PSGD_K_UVD_MAP_UPDAPP 9  /* update+apply sweep 2: PSGD_K_UVD_MAP_FUSED + Gram sums of the updated factors */
+#define PSGD_K_UVD_MID 14        /* between two sweeps: partial reduction + peer exchange + r x r algebra in one launch */
 #define PSGD_K_UVD_MAP_APPLY_D 13 /* update+apply sweep 3: d update fused with the apply's map sweep     */
 #define PSGD_K_GEMM 10           /* one tcgen05 3xTF32 GEMM launch                            */
 #define PSGD_K_GEMM_SIMT 12      /* one SIMT fp32 GEMM launch                                 */

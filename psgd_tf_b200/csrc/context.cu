@@ -103,8 +103,10 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
     ctx->opt_trsm_base = (int)value;
     return PSGD_OK;
   }
+  if (strcmp(key, "uvd_mid") == 0) { ctx->opt_uvd_mid = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "comm_timeout_ms") == 0) { ctx->opt_comm_timeout_ms = value > 0 ? (int)value : 0; return PSGD_OK; }
   if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }
+  if (strcmp(key, "tc_pair") == 0) { ctx->opt_tc_pair = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_mode") == 0) { ctx->opt_tc_mode = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "gemm_path") == 0) {
     PSGD_REQUIRE(value >= 0 && value <= 2, PSGD_ERR_BAD_SHAPE, "gemm_path must be 0 (auto), 1 (simt) or 2 (tcgen05)");

@@ -264,8 +264,8 @@ __host__ __device__ __forceinline__ bool tile_computed(const Params& p, int m0, 
   return tile_in_pattern<BN>(p, m0, n0) && !(p.triu && m0 >= n0 + BN);
 }
 
-// K-block range [kb0, kb1) of output tile (m0, n0) for product `p`
-template <int BN>
+// K-block range [kb0, kb1) of output tile (m0, n0) (BMt rows x BN columns) for product `p`
+template <int BN, int BMt = BM>
 __host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int m0, int n0, int& kb0, int& kb1,
                                                  int full = 0) {
   const int K = p.K[prod];
@@ -276,7 +276,7 @@ __host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int 
     // full: bit 0 = drop the hint on A, bit 1 = drop the hint on B (the factor turned out not to be triangular)
     const int a_tri = (full & 1) ? 0 : p.a_tri, b_tri = (full & 2) ? 0 : p.b_tri;
     if (a_tri == 1) up(lo, m0);                         // op(A)[m,k] = 0 for k < m
-    if (a_tri == 2) down(hi, m0 + BM);                  // op(A)[m,k] = 0 for k > m
+    if (a_tri == 2) down(hi, m0 + BMt);                 // op(A)[m,k] = 0 for k > m
     if (b_tri == 1) down(hi, n0 + BN);                  // op(B)[k,n] = 0 for k > n
     if (b_tri == 2) up(lo, n0);                         // op(B)[k,n] = 0 for k < n
     if (p.pair_b) {
@@ -648,6 +648,459 @@ __global__ void __launch_bounds__(kThreads, 1)
   if (warp == 1) tmem_dealloc(tmem_base, C::kTmemCols);
 }
 
+// =============================================================================================
+// CTA-pair variant (tcgen05 cta_group::2): one 256 x BN output tile per CLUSTER OF TWO CTAs.
+//
+// Why: the single-CTA kernel above is bound by shared-memory bandwidth, not by the tensor pipe (per 32-wide K stage it
+// moves 144 KB through shared memory against 768 tensor-core cycles: TMA fill, the splitter's read/write of B, and the
+// three MMAs each re-reading B).  With cta_group::2 the two SMs of a TPC execute ONE 256 x BN x 8 MMA: each CTA holds
+// its own 128 rows of A (split in registers, stored to its own tensor memory as before) but only HALF of the B tile
+// (BN/2 columns), and the hardware feeds both tensor cores from the two halves -- the B traffic per SM (TMA fill, split,
+// MMA reads) halves.  Two further savings ride along:
+//   * B's "hi" part is the RAW fp32 tile: kind::tf32 ignores the low 13 mantissa bits of its operands, i.e. it sees
+//     trunc_tf32(b).  The splitter then only writes lo = b - trunc_tf32(b) (exact in fp32, below 2^-10 |b|); the
+//     dropped term a_lo * b_lo stays below 2^-21 |a b| and has zero mean because a is split with round-to-nearest;
+//   * per stage and CTA: 24 KB TMA fill + 16 KB A read + 8 KB B read + 8 KB lo write + 24 KB MMA reads = 80 KB.
+// Roles and pipelines are those of gemm_tc_kernel; what changes is who signals whom:
+//   full[s]        local TMA -> local splitter                       (per CTA, as before)
+//   conv[s]        splitter warps of BOTH CTAs -> the LEADER's MMA warp (count 8; the peer arrives remotely)
+//   empty[s]       tcgen05.commit, multicast to both CTAs -> each CTA's TMA producer
+//   tmem_full[a]   tcgen05.commit, multicast                -> each CTA's epilogue warps
+//   tmem_empty[a]  epilogue warps of BOTH CTAs -> the leader's MMA warp (count 8)
+// Only the leader (cluster rank 0) issues MMAs; its instruction reads A from both CTAs' tensor memory and B from both
+// CTAs' shared memory at the SAME addresses, and accumulates into both CTAs' tensor memory.
+// =============================================================================================
+constexpr int BM2 = 256;
+
+template <int BN>
+struct Cfg2 {
+  static constexpr int kStages = 4;
+  static constexpr int kTileABytes = BM * BK * 4;             // this CTA's 128 rows of A: 16 KB
+  static constexpr int kTileBBytes = (BN / 2) * BK * 4;       // this CTA's half of the B tile: 8 KB at BN = 128
+  static constexpr int kStageBytes = kTileABytes + 2 * kTileBBytes;     // [A raw | B raw (= hi) | B lo]
+  static constexpr int kTxBytes = kTileABytes + kTileBBytes;
+  static constexpr int kBHiOff = kTileABytes;
+  static constexpr int kBLoOff = kTileABytes + kTileBBytes;
+  static constexpr int kAccCols = 2 * BN;
+  static constexpr int kATmemCol0 = kAccCols;
+  static constexpr int kTmemCols = 512;
+  static_assert(kAccCols + kStages * 2 * BK <= 512, "TMEM budget");
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_remote(uint64_t* bar, uint32_t cta) {
+  asm volatile(
+      "{\n"
+      ".reg .b32 ra;\n"
+      "mapa.shared::cluster.u32 ra, %0, %1;\n"
+      "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(cta)
+      : "memory");
+}
+// wait with cluster-scope acquire: the arrivals may come from the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {
+  uint32_t ok = 0;
+  while (!ok) {
+    asm volatile(
+        "{\n"
+        ".reg .pred p;\n"
+        "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n"
+        "selp.u32 %0, 1, 0, p;\n"
+        "}\n"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+  }
+}
+__device__ __forceinline__ void tmem_alloc2(uint32_t* smem_dst, uint32_t cols) {
+  asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_dst)), "r"(cols)
+               : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc2(uint32_t taddr, uint32_t cols) {
+  asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(cols) : "memory");
+}
+// arrives on the barrier at this offset in BOTH CTAs of the pair once all prior tcgen05 operations of this thread retire
+__device__ __forceinline__ void umma_commit2(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+                   smem_u32(bar)),
+               "h"((uint16_t)3)
+               : "memory");
+}
+// D[tmem, both CTAs] (+)= A[tmem, both CTAs: 2 x 128 rows] * B[smem: BN/2 columns from each CTA]
+__device__ __forceinline__ void umma2_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::tf32 [%0], [%1], %2, %3, {%5, %5, %5, %5, %5, %5, %5, %5}, p;\n"
+      "}\n" ::"r"(tmem_d),
+      "r"(tmem_a), "l"(desc_b), "r"(idesc), "r"(accumulate), "r"(0u)
+      : "memory");
+}
+__device__ __forceinline__ uint32_t make_idesc2(int n, int b_mn, int negate_a) {
+  uint32_t d = 0;
+  d |= 1u << 4;                        // c_format  = F32
+  d |= 2u << 7;                        // a_format  = TF32
+  d |= 2u << 10;                       // b_format  = TF32
+  d |= (uint32_t)(negate_a & 1) << 13; // a_negate
+  d |= (uint32_t)(b_mn & 1) << 16;     // b_major
+  d |= (uint32_t)(n >> 3) << 17;       // n_dim
+  d |= (uint32_t)(BM2 >> 4) << 24;     // m_dim = 256: 128 rows in each CTA of the pair
+  return d;
+}
+
+template <int BN>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
+    gemm_tc2_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ Params p) {
+  using C = Cfg2<BN>;
+  constexpr int BNH = BN / 2;                      // B columns staged by each CTA
+  extern __shared__ unsigned char smem_raw[];
+  unsigned char* smem = reinterpret_cast<unsigned char*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + (size_t)C::kStages * C::kStageBytes);
+  uint64_t* full = bars;                         // [kStages]
+  uint64_t* conv = bars + C::kStages;            // [kStages]   (used in the leader)
+  uint64_t* empty = bars + 2 * C::kStages;       // [kStages]
+  uint64_t* tmem_full = bars + 3 * C::kStages;   // [2]
+  uint64_t* tmem_empty = tmem_full + 2;          // [2]         (used in the leader)
+  uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();       // 0 = leader
+  const int pair = blockIdx.x >> 1, num_pairs = gridDim.x >> 1;
+
+  __shared__ int s_full[kMaxGroup];
+  if (threadIdx.x >= 64 && threadIdx.x < 64 + kMaxGroup) {
+    const int g = threadIdx.x - 64;
+    int f = 0;
+    if (g < p.count) {
+      if (p.a_full[g] && *p.a_full[g]) f |= 1;
+      if (p.b_full[g] && *p.b_full[g]) f |= 2;
+    }
+    s_full[g] = f;
+  }
+  if (threadIdx.x == 0) {
+    for (int s = 0; s < C::kStages; ++s) {
+      mbar_init(&full[s], 1);
+      mbar_init(&conv[s], 8);                    // 4 splitter warps of each CTA
+      mbar_init(&empty[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tmem_full[a], 1);
+      mbar_init(&tmem_empty[a], 8);              // 4 epilogue warps of each CTA
+    }
+    mbar_fence_init();
+  }
+  if (warp == 1) tmem_alloc2(tmem_ptr, C::kTmemCols);
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                            // both CTAs' barriers are initialised before anyone signals the peer
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_ptr;
+
+  const int tiles_per = p.tiles_m * p.tiles_n;   // tiles_m counts 256-row tiles here
+  const int num_tiles = tiles_per * p.count;
+  auto stage_ptr = [&](int s) { return smem + (size_t)s * C::kStageBytes; };
+
+  if (warp == 0) {
+    // ===================================== TMA producer (both CTAs) ==========================
+    if (elect_one_sync()) {
+      int it = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int grp = tile / tiles_per, lt = tile % tiles_per;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
+        const int m0 = tm * BM2, n0 = tn * BN;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
+        const int ma0 = m0 + (int)rank * BM;       // this CTA's rows of A
+        const int nb0 = n0 + (int)rank * BNH;      // this CTA's columns of B
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
+          const CUtensorMap* ma = prod ? &maps.a1[grp] : &maps.a0[grp];
+          const CUtensorMap* mb = prod ? &maps.b1[grp] : &maps.b0[grp];
+          for (int kb = kb0; kb < kb1; ++kb, ++it) {
+            const int s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            mbar_wait(&empty[s], ph ^ 1);
+            mbar_arrive_expect_tx(&full[s], C::kTxBytes);
+            unsigned char* sa = stage_ptr(s);
+            unsigned char* sb = sa + C::kBHiOff;
+            const int k0 = kb * BK;
+            if (!p.a_mn[prod]) {
+              tma_load_2d(sa, ma, k0, ma0, &full[s]);                      // box {32 k, 128 m}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BM / 32; ++j) tma_load_2d(sa + j * 4096, ma, ma0 + 32 * j, k0, &full[s]);   // box {32 m, 32 k}
+            }
+            if (!p.b_mn[prod]) {
+              tma_load_2d(sb, mb, k0, nb0, &full[s]);                      // box {32 k, BN/2 n}
+            } else {
+#pragma unroll
+              for (int j = 0; j < BNH / 32; ++j) tma_load_2d(sb + j * 4096, mb, nb0 + 32 * j, k0, &full[s]);
+            }
+          }
+        }
+      }
+    }
+    __syncwarp();
+  } else if (warp == 1) {
+    // ===================================== MMA issuer (leader CTA only) ======================
+    if (rank == 0) {
+      int it = 0, tcount = 0;
+      for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+        const int grp = tile / tiles_per, lt = tile % tiles_per;
+        const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
+        const int m0 = tm * BM2, n0 = tn * BN;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
+        int total_kb = 0;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
+          total_kb += kb1 - kb0;
+        }
+        if (total_kb == 0) continue;
+        int a = 0;
+        uint32_t tmem_d = 0;
+        uint32_t accumulate = 0;
+        int done = 0, in_chunk = 0;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
+          const uint32_t idesc = make_idesc2(BN, p.b_mn[prod], prod);
+          const uint64_t b_step = p.b_mn[prod] ? (1024 >> 4) : (32 >> 4);
+          for (int kb = kb0; kb < kb1; ++kb, ++it, ++done) {
+            const int s = it % C::kStages;
+            const uint32_t ph = (it / C::kStages) & 1;
+            if (in_chunk == 0) {
+              a = tcount & 1;
+              const uint32_t aph = (tcount >> 1) & 1;
+              ++tcount;
+              mbar_wait_cluster(&tmem_empty[a], aph ^ 1);
+              tmem_d = tmem_base + (uint32_t)(a * BN);
+              accumulate = 0;
+            }
+            mbar_wait_cluster(&conv[s], ph);
+            tc_fence_after();
+            const bool chunk_end = (in_chunk + 1 == kChunkKB) || (done + 1 == total_kb);
+            if (elect_one_sync()) {
+              const uint32_t st_base = smem_u32(stage_ptr(s));
+              const uint64_t dbh0 = operand_desc(st_base + C::kBHiOff, p.b_mn[prod], 0);
+              const uint64_t dbl0 = operand_desc(st_base + C::kBLoOff, p.b_mn[prod], 0);
+              uint32_t acc = accumulate;
+              if (!(p.debug & 4)) {
+                const uint32_t a_hi_t = tmem_base + (uint32_t)(C::kATmemCol0 + s * 2 * BK);
+                const uint32_t a_lo_t = a_hi_t + BK;
+#pragma unroll
+                for (int kk = 0; kk < BK / UMMA_K; ++kk) {
+                  umma2_tf32_ts(tmem_d, a_lo_t + kk * UMMA_K, dbh0 + kk * b_step, idesc, acc);     // small terms first
+                  umma2_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbl0 + kk * b_step, idesc, 1u);
+                  umma2_tf32_ts(tmem_d, a_hi_t + kk * UMMA_K, dbh0 + kk * b_step, idesc, 1u);
+                  acc = 1u;
+                }
+              }
+              umma_commit2(&empty[s]);                              // frees the stage in both CTAs
+              if (chunk_end) umma_commit2(&tmem_full[a]);           // chunk complete -> both CTAs' epilogue warps
+            }
+            __syncwarp();
+            accumulate = 1u;
+            in_chunk = chunk_end ? 0 : in_chunk + 1;
+          }
+        }
+      }
+    }
+  } else if (warp >= kSplitWarp0) {
+    // ===================================== 3xTF32 splitter (both CTAs) =======================
+    const int st = threadIdx.x - kSplitWarp0 * 32;            // 0..127
+    int it = 0;
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int grp = tile / tiles_per, lt = tile % tiles_per;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
+      const int m0 = tm * BM2, n0 = tn * BN;
+      if (!tile_computed<BN>(p, m0, n0)) continue;
+      for (int prod = 0; prod < 2; ++prod) {
+        if (p.K[prod] <= 0) continue;
+        int kb0, kb1;
+        k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
+        for (int kb = kb0; kb < kb1; ++kb, ++it) {
+          const int s = it % C::kStages;
+          const uint32_t ph = (it / C::kStages) & 1;
+          mbar_wait(&full[s], ph);
+          const uint32_t sa = smem_u32(stage_ptr(s));
+          const int row = (warp & 3) * 32 + lane;
+          constexpr int kBVec = C::kTileBBytes / (128 * 16);        // 16-byte vectors of B per thread (4 at BN = 128)
+          uint32_t araw[32];
+          uint4 braw[kBVec];
+          if (p.debug & 2) {
+#pragma unroll
+            for (int k = 0; k < 32; ++k) araw[k] = 0;
+          } else if (!p.a_mn[prod]) {
+            const uint32_t rp = sa + row * 128;
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+              const uint4 x = lds128(rp + ((c ^ (row & 7)) << 4));
+              araw[4 * c] = x.x; araw[4 * c + 1] = x.y; araw[4 * c + 2] = x.z; araw[4 * c + 3] = x.w;
+            }
+          } else {
+            const uint32_t blk = sa + (row >> 5) * 4096;
+            const int mb = (row & 31) * 4;
+#pragma unroll
+            for (int k = 0; k < 32; ++k) araw[k] = lds32(blk + k * 128 + (mb ^ ((k & 3) << 5)));
+          }
+          const uint32_t bh = sa + C::kBHiOff + st * 16, bl = sa + C::kBLoOff + st * 16;
+          if (!(p.debug & 1)) {
+#pragma unroll
+            for (int j = 0; j < kBVec; ++j) braw[j] = lds128(bh + j * 2048);
+          }
+          {
+            uint32_t ahi[32], alo[32];
+#pragma unroll
+            for (int k = 0; k < 32; ++k) split_tf32(araw[k], ahi[k], alo[k]);
+            const uint32_t t_a = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(C::kATmemCol0 + s * 2 * BK);
+            tmem_st32(t_a, ahi);
+            tmem_st32(t_a + BK, alo);
+          }
+          if (!(p.debug & 1)) {
+            // lo = b - trunc_tf32(b): the raw tile itself serves as "hi" (the tensor core drops the low 13 bits)
+#pragma unroll
+            for (int j = 0; j < kBVec; ++j) {
+              uint4 l;
+              l.x = __float_as_uint(__uint_as_float(braw[j].x) - __uint_as_float(braw[j].x & 0xffffe000u));
+              l.y = __float_as_uint(__uint_as_float(braw[j].y) - __uint_as_float(braw[j].y & 0xffffe000u));
+              l.z = __float_as_uint(__uint_as_float(braw[j].z) - __uint_as_float(braw[j].z & 0xffffe000u));
+              l.w = __float_as_uint(__uint_as_float(braw[j].w) - __uint_as_float(braw[j].w & 0xffffe000u));
+              sts128(bl + j * 2048, l);
+            }
+          }
+          tmem_st_wait();
+          tc_fence_before();              // TMEM stores ordered before the leader's tcgen05.mma (via conv[s])
+          fence_proxy_async_smem();       // generic-proxy writes of lo -> visible to tcgen05 (async proxy)
+          __syncwarp();
+          if (lane == 0) {
+            if (rank == 0) mbar_arrive(&conv[s]);
+            else mbar_arrive_remote(&conv[s], 0);
+          }
+        }
+      }
+    }
+  } else {
+    // ===================================== epilogue (both CTAs) ==============================
+    const int q = warp & 3;
+    int tcount = 0;
+    float mx = 0.f;
+    int mx_grp = -1;
+    auto flush_max = [&]() {
+      if (mx_grp >= 0 && p.maxabs[mx_grp]) {
+        const float w = warp_max(mx);
+        if (lane == 0 && w > 0.f) atomic_max_nonneg(p.maxabs[mx_grp], w);
+      }
+      mx = 0.f;
+    };
+    for (int tile = pair; tile < num_tiles; tile += num_pairs) {
+      const int grp = tile / tiles_per, lt = tile % tiles_per;
+      const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
+      const int m0 = tm * BM2, n0 = tn * BN;
+      const int m = m0 + (int)rank * BM + q * 32 + lane;
+      if (!tile_in_pattern<BN>(p, m0, n0)) continue;
+      if (grp != mx_grp) { flush_max(); mx_grp = grp; }
+      float* const Cg = p.C[grp];
+      const float* const Dg = p.D[grp];
+      const float* const csg = p.colscale[grp];
+      float mu = 0.f;
+      if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
+      const float rho = p.rho_mode ? *p.rho[grp] : 1.0f;
+      int total_kb = 0;
+      if (!(p.triu && m0 >= n0 + BN)) {
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
+          total_kb += kb1 - kb0;
+        }
+      }
+      float racc[BN];
+#pragma unroll
+      for (int j = 0; j < BN; ++j) racc[j] = 0.f;
+      for (int done = 0; done < total_kb; done += kChunkKB) {
+        const int a = tcount & 1;
+        const uint32_t aph = (tcount >> 1) & 1;
+        ++tcount;
+        mbar_wait(&tmem_full[a], aph);
+        tc_fence_after();
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          uint32_t r[32];
+          tmem_ld32(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(a * BN + c * 32), r);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) racc[c * 32 + j] += __uint_as_float(r[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) {
+          if (rank == 0) mbar_arrive(&tmem_empty[a]);
+          else mbar_arrive_remote(&tmem_empty[a], 0);
+        }
+      }
+      if (m < p.M) {
+#pragma unroll
+        for (int c = 0; c < BN / 32; ++c) {
+          const int nbase = n0 + c * 32;
+          if (nbase >= p.N) continue;
+          float* crow = Cg + (size_t)m * p.ldc + nbase;
+          const float* drow = Dg ? Dg + (size_t)m * p.ldd + nbase : nullptr;
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            const int n = nbase + j;
+            float x = racc[c * 32 + j];
+            if (p.negate) x = -x;
+            if (csg && n < p.N) {
+              float sc = csg[n];
+              if (p.colscale_sq) sc = sc * sc;
+              x = p.colscale_recip ? x * (1.0f / sc) : x * sc;
+            }
+            if (p.triu && m > n) x = 0.f;
+            if (drow && n < p.N) x = drow[j] - mu * x;
+            if (p.rho_mode == 1) x = x / rho;
+            else if (p.rho_mode == 2) x = x * rho;
+            if (n < p.N) mx = fmaxf(mx, fabsf(x));
+            v[j] = x;
+          }
+          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j)
+              if (nbase + j < p.N) crow[j] = v[j];
+          }
+        }
+      }
+    }
+    flush_max();
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  cluster_sync_all();                // the peer's smem / tensor memory / barriers stay valid until both CTAs are done
+  if (warp == 1) tmem_dealloc2(tmem_base, C::kTmemCols);
+}
+
 // ---------------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------------
@@ -781,9 +1234,86 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   return PSGD_OK;
 }
 
-// opt_tc_mode: 1 (default) = A operand through tensor memory ("TS"), 0 = both operands from shared memory ("SS")
+// CTA-pair launch (gemm_tc2_kernel): same problem description, 256-row tiles, clusters of two CTAs.
+template <int BN>
+static int launch_pair(psgd_ctx* ctx, const la::Gemm* gs, int count) {
+  using C = Cfg2<BN>;
+  const la::Gemm& g = gs[0];
+  static thread_local Params p;
+  static thread_local GroupMaps maps;
+  p = Params{};
+  p.M = g.M; p.N = g.N;
+  p.K[0] = g.K; p.K[1] = g.K2;
+  p.a_mn[0] = g.ta ? 1 : 0;
+  p.b_mn[0] = g.tb ? 0 : 1;
+  p.a_mn[1] = g.ta2 ? 1 : 0;
+  p.b_mn[1] = g.tb2 ? 0 : 1;
+  p.a_tri = g.a_tri; p.b_tri = g.b_tri;
+  p.ldc = g.ldc; p.ldd = g.ldd; p.triu = g.triu ? 1 : 0;
+  p.step = g.step; p.tiny = g.tiny;
+  p.colscale_recip = g.colscale_recip; p.colscale_sq = g.colscale_sq;
+  p.tiles_m = (g.M + BM2 - 1) / BM2;
+  p.tiles_n = (g.N + BN - 1) / BN;
+  p.count = count;
+  p.debug = ctx->opt_tc_debug;
+  p.negate = g.negate ? 1 : 0;
+  p.rho_mode = g.rho ? g.rho_mode : 0;
+  double work = 0.0;
+  for (int i = 0; i < count; ++i) {
+    const la::Gemm& q = gs[i];
+    p.C[i] = q.C; p.maxabs[i] = q.maxabs; p.D[i] = q.D; p.mu_max[i] = q.mu_max; p.colscale[i] = q.colscale;
+    p.a_full[i] = q.a_full; p.b_full[i] = q.b_full; p.rho[i] = q.rho;
+    work += 2.0 * q.M * q.N * ((double)q.K + q.K2);
+    for (int prod = 0; prod < 2; ++prod) {
+      const float* A = prod ? q.A2 : q.A;
+      const float* B = prod ? q.B2 : q.B;
+      const int lda = prod ? q.lda2 : q.lda, ldb = prod ? q.ldb2 : q.ldb;
+      const int K = prod ? q.K2 : q.K;
+      CUtensorMap* ta = prod ? &maps.a1[i] : &maps.a0[i];
+      CUtensorMap* tb = prod ? &maps.b1[i] : &maps.b0[i];
+      if (K <= 0) continue;
+      if (!p.a_mn[prod]) PSGD_RETURN_IF(make_map(ta, A, q.M, K, lda, BM, false));          // [M,K], box {32k, 128m}
+      else               PSGD_RETURN_IF(make_map(ta, A, K, q.M, lda, BK, true));           // [K,M], box {32m, 32k}
+      if (!p.b_mn[prod]) PSGD_RETURN_IF(make_map(tb, B, q.N, K, ldb, BN / 2, false));      // [N,K], box {32k, BN/2 n}
+      else               PSGD_RETURN_IF(make_map(tb, B, K, q.N, ldb, BK, true));           // [K,N], box {32n, 32k}
+    }
+  }
+  auto kern = gemm_tc2_kernel<BN>;
+  static DeviceOnce attr_done;
+  if (!attr_done.done(ctx->device)) {
+    PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
+    attr_done.set(ctx->device);
+  }
+  int pairs = p.tiles_m * p.tiles_n * count;
+  if (pairs > ctx->num_sms / 2) pairs = ctx->num_sms / 2;
+  if (ctx->opt_profile == 2) {
+    // executed flops, counted per CTA tile (128 rows): the K blocks of the PAIR tile are executed by both halves
+    double kbs = 0.0;
+    for (int tm = 0; tm < p.tiles_m; ++tm)
+      for (int tn = 0; tn < p.tiles_n; ++tn) {
+        const int m0 = tm * BM2, n0 = tn * BN;
+        if (!tile_computed<BN>(p, m0, n0)) continue;
+        for (int prod = 0; prod < 2; ++prod) {
+          if (p.K[prod] <= 0) continue;
+          int kb0, kb1;
+          k_range<BN, BM2>(p, prod, m0, n0, kb0, kb1);
+          kbs += kb1 - kb0;
+        }
+      }
+    work = kbs * 2.0 * BM2 * BN * BK * count;
+  }
+  ProfScope prof(ctx, PSGD_K_GEMM, work);
+  kern<<<2 * pairs, kThreads, C::kSmemBytes, ctx->stream>>>(maps, p);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
+// opt_tc_mode: 1 (default) = A operand through tensor memory ("TS"), 0 = both operands from shared memory ("SS").
+// opt_tc_pair: 1 (default) = CTA-pair kernel (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows
+// and is not a block-pair (triangular inverse doubling) launch.
 template <int BN>
 static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
+  if (ctx->opt_tc_pair && ctx->opt_tc_mode && gs[0].pair_b == 0 && gs[0].M >= BM2) return launch_pair<BN>(ctx, gs, count);
   return ctx->opt_tc_mode ? launch_impl<BN, true>(ctx, gs, count) : launch_impl<BN, false>(ctx, gs, count);
 }
 

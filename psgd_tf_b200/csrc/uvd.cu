@@ -27,7 +27,7 @@
 // so results are deterministic and identical for any grid size.
 #include <math.h>
 
-#include "common.cuh"
+#include "comm.cuh"
 
 namespace psgd {
 namespace uvd {
@@ -209,6 +209,7 @@ struct SweepArgs {
   const float* vec[4];
   int64_t n;          // rows
   int direct;         // 1: bypass the TMA pipeline (debug / cross-check)
+  unsigned int* zero_word;   // set to 0 by CTA 0 (the ticket of the mid kernel that consumes this sweep's partials)
 };
 
 // Producer lane: stream this CTA's full tiles into the ring.
@@ -398,6 +399,7 @@ __global__ void __launch_bounds__(GramPlan<R, MODE>::THREADS, 1)
 
   float* smem; uint64_t* full; uint64_t* empty;
   pipeline_init<R, 2, NV, P::TILE>(smem, full, empty, smem_raw, P::CONSUMER_WARPS);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.zero_word) *a.zero_word = 0u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_full_tiles = a.n / P::TILE;
@@ -510,6 +512,7 @@ struct SmallState {
   double aa, bb, ab;     // a.a, b.b, a.b
   double Uta[kMaxRank];  // U^T a
   double Utb[kMaxRank];  // U^T b
+  unsigned int ticket;   // mid kernel: CTAs done with their slice (zeroed by the sweep that precedes it)
 };
 
 // table accessors for G = Z^T [Z | X] stored [W][E] with only j >= i filled
@@ -554,11 +557,10 @@ __device__ __forceinline__ void rank2_coeffs(double aa, double bb, double ab, co
 // fused != 0: the reductions over a and b that the rank-2 step needs (a.a, b.b, a.b, a^T X, b^T X) are expanded
 // through the table (a = dh + U p, b = w - V s1), so the step's coefficients are ready before sweep 2 and the row
 // update rides in that sweep (tests/uvd_pipeline_model.py restates this algebra on the host).
-__global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict__ G, int r, int fused, int update_U,
-                                                        float step, float tiny, SmallState* __restrict__ st) {
+__device__ __forceinline__ void small1_device(const double* __restrict__ G, int r, int fused, int update_U, float step,
+                                              float tiny, SmallState* __restrict__ st, int lane) {
   __shared__ double A[kMaxRank][kLuLd];
   __shared__ double sp[kMaxRank], ss1[kMaxRank], sat[kMaxRank], sbt[kMaxRank];
-  const int lane = threadIdx.x;
   const int W = 2 * r, E = W + 2;
   for (int e = lane; e < r * r; e += 32) {
     const int i = e / r, j = e % r;
@@ -642,13 +644,20 @@ __global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict
   __syncwarp();                                // sat/sbt and st->UtU/VtV/IpVtU written above are read across lanes
   rank2_coeffs(aa, bb, ab, sat, sbt, r, update_U, step, tiny, st, lane);
 }
+__global__ void __launch_bounds__(32) uvd_small1_kernel(const double* __restrict__ G, int r, int fused, int update_U,
+                                                        float step, float tiny, SmallState* __restrict__ st) {
+  small1_device(G, r, fused, update_U, step, tiny, st, threadIdx.x);
+}
 
 // G2 layout: [0]=a.a [1]=b.b [2]=a.b [3..3+r)=a^T X  [3+r..3+2r)=b^T X   (X = V on the U branch, U on the V branch)
-__global__ void __launch_bounds__(32) uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step,
-                                                        float tiny, SmallState* __restrict__ st) {
-  const int lane = threadIdx.x;
+__device__ __forceinline__ void small2_device(const double* __restrict__ G2, int r, int update_U, float step, float tiny,
+                                              SmallState* __restrict__ st, int lane) {
   if (lane == 0) st->mu_d = step / (st->max_nabla + tiny);                    // psgd.py:582
   rank2_coeffs(G2[0], G2[1], G2[2], G2 + 3, G2 + 3 + r, r, update_U, step, tiny, st, lane);
+}
+__global__ void __launch_bounds__(32) uvd_small2_kernel(const double* __restrict__ G2, int r, int update_U, float step,
+                                                        float tiny, SmallState* __restrict__ st) {
+  small2_device(G2, r, update_U, step, tiny, st, threadIdx.x);
 }
 
 // After the map sweep of the fused update+apply call.  G3: reduced sums over the UPDATED factors
@@ -656,10 +665,9 @@ __global__ void __launch_bounds__(32) uvd_small2_kernel(const double* __restrict
 // so that  Z^T (d' g) = Z^T x0 - mu_d Z^T x1  for d' = d - mu_d d nablaD (mu_d is only known once max|nablaD| is, i.e.
 // after that sweep).  U'^T U' needs no sums at all: U' = U - a c1^T + b c2^T (U branch; U' = U on the V branch) expands
 // through quantities uvd_small1_kernel already has.  Leaves p, t of the apply in st.                 psgd.py:625-626
-__global__ void __launch_bounds__(32) uvd_small_ua_kernel(const double* __restrict__ G3, int r, int update_U, float step,
-                                                          float tiny, SmallState* __restrict__ st) {
+__device__ __forceinline__ void small_ua_device(const double* __restrict__ G3, int r, int update_U, float step, float tiny,
+                                                SmallState* __restrict__ st, int lane) {
   __shared__ double sp[kMaxRank];
-  const int lane = threadIdx.x;
   const float mu_d = step / (st->max_nabla + tiny);                           // psgd.py:582
   if (lane == 0) st->mu_d = mu_d;
   const double* Ux0 = G3;
@@ -686,12 +694,15 @@ __global__ void __launch_bounds__(32) uvd_small_ua_kernel(const double* __restri
     st->t[i] = (float)s;
   }
 }
+__global__ void __launch_bounds__(32) uvd_small_ua_kernel(const double* __restrict__ G3, int r, int update_U, float step,
+                                                          float tiny, SmallState* __restrict__ st) {
+  small_ua_device(G3, r, update_U, step, tiny, st, threadIdx.x);
+}
 
 // apply / matvec: p = V^T x ; t = U^T x + (U^T U) p
-__global__ void __launch_bounds__(32) uvd_small_apply_kernel(const double* __restrict__ G, int r,
-                                                             SmallState* __restrict__ st) {
+__device__ __forceinline__ void small_apply_device(const double* __restrict__ G, int r, SmallState* __restrict__ st,
+                                                   int lane) {
   __shared__ double sp[kMaxRank];
-  const int lane = threadIdx.x;
   const int W = 2 * r, E = W + 1;
   if (lane < r) sp[lane] = G[(r + lane) * E + W];
   __syncwarp();
@@ -700,6 +711,95 @@ __global__ void __launch_bounds__(32) uvd_small_apply_kernel(const double* __res
     for (int j = 0; j < r; ++j) s += Gsym(G, E, lane, j) * sp[j];
     st->p[lane] = (float)sp[lane];
     st->t[lane] = (float)s;
+  }
+}
+__global__ void __launch_bounds__(32) uvd_small_apply_kernel(const double* __restrict__ G, int r,
+                                                             SmallState* __restrict__ st) {
+  small_apply_device(G, r, st, threadIdx.x);
+}
+
+// =============================================================================================
+// "mid" kernel: everything between two sweeps in ONE launch.
+//   A. fixed-order float64 reduction of the per-CTA partial records, spread over kMidCtas CTAs (each owns a slice of the
+//      entries; within a slice `parts` threads per entry sum strided subsets of the CTAs, combined in index order) --
+//      the single 1024-thread CTA of reduce_partials_kernel took 15 us for the 148 x 484 update table;
+//   B. the LAST CTA to finish (atomic ticket) runs the cross-rank exchange of comm.cuh in place on the reduced record
+//      (sharded runs): push to every peer's slab over NVLink, flag, wait, fixed-rank-order sum;
+//   C. the same CTA stages the record in shared memory and one of its warps does the r x r algebra.
+// At 8 GPUs a sweep is ~0.2 ms, and the serial chain reduce -> exchange -> algebra (three launches, ~40 us, twice per
+// step) was what kept the chunk-sharded step at 90 % scaling efficiency.  Results are bit-identical to the separate
+// launches' only in the algebra; the reduction order differs (still fixed: it depends on (nblocks, count) alone).
+// =============================================================================================
+constexpr int kMidCtas = 32;
+constexpr int kMidThreads = 256;
+constexpr int kMidMaxCount = (2 * kMaxRank + 2) * (2 * kMaxRank + 2);
+enum MidKind { kMidNone = 0, kMidSmall1 = 1, kMidSmallUA = 2, kMidSmallApply = 3, kMidSmall2 = 4 };
+
+struct MidArgs {
+  const float* partial;     // [nblocks][count]
+  int nblocks, count;
+  double* G;                // [count] reduced (and all-reduced) record
+  unsigned int* ticket;     // zeroed by the sweep that produced `partial`; reset by the last CTA
+  SmallState* st;
+  int kind, r, fused, update_U;
+  float step, tiny;
+  // cross-rank exchange (world == 0: single GPU)
+  comm::Peers peers;
+  int rank, world;
+  float* max_buf;           // n_max non-negative maxima all-reduced together with the sums (e.g. &st->max_nabla)
+  int n_max;
+  unsigned int* host_err;
+  unsigned long long timeout_ns;
+};
+
+__global__ void __launch_bounds__(kMidThreads) uvd_mid_kernel(const __grid_constant__ MidArgs a) {
+  __shared__ double part_sum[kMidThreads];
+  __shared__ double sG[kMidMaxCount];
+  __shared__ unsigned int s_last;
+  const int tid = threadIdx.x;
+  // ---- A: this CTA's slice of the entries ----------------------------------------------------------------------
+  const int per = (a.count + gridDim.x - 1) / gridDim.x;
+  const int k0 = blockIdx.x * per;
+  const int slots = max(0, min(per, a.count - k0));
+  if (slots > 0) {
+    int parts = kMidThreads / slots;
+    if (parts > 32) parts = 32;
+    const int part = tid / slots, k = k0 + tid % slots;
+    if (part < parts) {
+      double s = 0.0;
+#pragma unroll 4
+      for (int b = part; b < a.nblocks; b += parts) s += (double)__ldcg(&a.partial[(size_t)b * a.count + k]);
+      part_sum[part * slots + (k - k0)] = s;
+    }
+    __syncthreads();
+    if (tid < slots) {
+      double s = 0.0;
+      for (int q = 0; q < parts; ++q) s += part_sum[q * slots + tid];
+      a.G[k0 + tid] = s;
+    }
+  }
+  // ---- ticket: the last CTA to get here goes on ----------------------------------------------------------------
+  __threadfence();
+  __syncthreads();
+  if (tid == 0) s_last = (atomicAdd(a.ticket, 1u) == gridDim.x - 1) ? 1u : 0u;
+  __syncthreads();
+  if (!s_last) return;
+  __threadfence();
+  if (tid == 0) *a.ticket = 0u;            // ready for the next mid kernel that shares this ticket
+  // ---- B: cross-rank exchange, in place on G --------------------------------------------------------------------
+  if (a.world > 0) {
+    comm::exchange_device(a.peers, a.rank, a.world, a.G, a.count, a.max_buf, a.n_max, a.host_err, a.timeout_ns);
+    __syncthreads();
+  }
+  // ---- C: r x r algebra from shared memory ------------------------------------------------------------------------
+  if (a.kind == kMidNone) return;
+  for (int k = tid; k < a.count; k += kMidThreads) sG[k] = __ldcg(&a.G[k]);
+  __syncthreads();
+  if (tid < 32) {
+    if (a.kind == kMidSmall1) small1_device(sG, a.r, a.fused, a.update_U, a.step, a.tiny, a.st, tid);
+    else if (a.kind == kMidSmallUA) small_ua_device(sG, a.r, a.update_U, a.step, a.tiny, a.st, tid);
+    else if (a.kind == kMidSmallApply) small_apply_device(sG, a.r, a.st, tid);
+    else if (a.kind == kMidSmall2) small2_device(sG, a.r, a.update_U, a.step, a.tiny, a.st, tid);
   }
 }
 
@@ -959,6 +1059,7 @@ __global__ void __launch_bounds__(kMapThreads, 1) map_sweep_kernel(SweepArgs a, 
   float* smem; uint64_t* full; uint64_t* empty;
   // store kinds: one elected lane releases the stage after its bulk store has drained the tile
   pipeline_init<R, T::NM, T::NV, kMapTile>(smem, full, empty, smem_raw, kStore ? 1 : kMapConsumerWarps);
+  if (blockIdx.x == 0 && threadIdx.x == 0 && a.zero_word) *a.zero_word = 0u;
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int64_t n_full_tiles = a.n / kMapTile;
@@ -1273,6 +1374,39 @@ static int carve(psgd_ctx* ctx, int64_t n, int r, int grid, int n_vecs, Scratch*
   return PSGD_OK;
 }
 
+// Everything between two sweeps: reduce the `nblocks` partial records of `count` floats into s.G (float64, fixed order),
+// all-reduce it over the ranks together with n_max maxima at max_buf, run the r x r algebra `kind`.  One launch
+// (uvd_mid_kernel) unless the torch.distributed hook is the exchange (host callback) or "uvd_mid" is off.
+static int mid_step(psgd_ctx* ctx, const Scratch& s, int nblocks, int count, int kind, int r, int fused, int update_U,
+                    float step, float tiny, float* max_buf, int n_max) {
+  cudaStream_t st = ctx->stream;
+  const bool hook_only = ctx->comm_world <= 0 && ctx->allreduce != nullptr;
+  if (!ctx->opt_uvd_mid || hook_only) {
+    reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, nblocks, count, s.G);
+    PSGD_LAUNCH_CHECK(ctx);
+    PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, count, max_buf, n_max));
+    if (kind == kMidSmall1) uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, r, fused, update_U, step, tiny, s.st);
+    else if (kind == kMidSmallUA) uvd_small_ua_kernel<<<1, 32, 0, st>>>(s.G, r, update_U, step, tiny, s.st);
+    else if (kind == kMidSmallApply) uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, r, s.st);
+    else if (kind == kMidSmall2) uvd_small2_kernel<<<1, 32, 0, st>>>(s.G, r, update_U, step, tiny, s.st);
+    if (kind != kMidNone) PSGD_LAUNCH_CHECK(ctx);
+    return PSGD_OK;
+  }
+  comm::DeviceArgs da;
+  PSGD_RETURN_IF(comm::device_args(ctx, count, n_max, &da));
+  MidArgs a{};
+  a.partial = s.partial; a.nblocks = nblocks; a.count = count; a.G = s.G; a.ticket = &s.st->ticket; a.st = s.st;
+  a.kind = kind; a.r = r; a.fused = fused; a.update_U = update_U; a.step = step; a.tiny = tiny;
+  a.peers = da.peers; a.rank = da.rank; a.world = da.world; a.max_buf = max_buf; a.n_max = n_max;
+  a.host_err = da.host_err; a.timeout_ns = da.timeout_ns;
+  PSGD_REQUIRE(count <= kMidMaxCount, PSGD_ERR_BAD_SHAPE, "mid kernel: record of %d entries exceeds %d", count, kMidMaxCount);
+  const int ctas = count < kMidCtas ? count : kMidCtas;
+  ProfScope prof(ctx, PSGD_K_UVD_MID);
+  uvd_mid_kernel<<<ctas, kMidThreads, 0, st>>>(a);
+  PSGD_LAUNCH_CHECK(ctx);
+  return PSGD_OK;
+}
+
 // psgd.py:562-567
 static int balance_pass(psgd_ctx* ctx, float* U, float* V, int64_t count, SmallState* sst) {
   cudaStream_t st = ctx->stream;
@@ -1292,15 +1426,9 @@ static int balance_pass(psgd_ctx* ctx, float* U, float* V, int64_t count, SmallS
 template <int R>
 static int update_head(psgd_ctx* ctx, const SweepArgs& a1, const Scratch& s, int grid, int fused, int update_U,
                        float step, float tiny) {
-  cudaStream_t st = ctx->stream;
   PSGD_RETURN_IF((launch_gram<R, kUpdate>(ctx, a1, s.partial, grid)));
   constexpr int table = GramPlan<R, kUpdate>::TABLE;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
-  uvd_small1_kernel<<<1, 32, 0, st>>>(s.G, R, fused, update_U, step, tiny, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
-  return PSGD_OK;
+  return mid_step(ctx, s, grid, table, kMidSmall1, R, fused, update_U, step, tiny, nullptr, 0);
 }
 
 template <int R>
@@ -1317,6 +1445,7 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
 
   // sweep 1
   SweepArgs a1{};
+  a1.zero_word = &s.st->ticket;
   a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.n = n; a1.direct = ctx->opt_direct;
   PSGD_RETURN_IF((update_head<R>(ctx, a1, s, grid, fused, update_U, step, tiny)));
 
@@ -1341,14 +1470,11 @@ static int update_impl(psgd_ctx* ctx, float* U, float* V, float* d, const float*
   o2.o0 = s.a; o2.o1 = s.b; o2.o2 = s.nd; o2.partial = s.partial; o2.st = s.st;
   PSGD_RETURN_IF((launch_map<R, kMapUpd2>(ctx, a1, o2, update_U, grid)));
   constexpr int cnt2 = 3 + 2 * R;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, cnt2, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, cnt2, &s.st->max_nabla, 1));
-  uvd_small2_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, cnt2, kMidSmall2, R, 0, update_U, step, tiny, &s.st->max_nabla, 1));
 
   // sweep 3
   SweepArgs a3{};
+  a3.zero_word = &s.st->ticket;
   a3.mat[0] = update_U ? U : V; a3.vec[0] = s.a; a3.vec[1] = s.b; a3.vec[2] = s.nd; a3.vec[3] = d;
   a3.n = n; a3.direct = ctx->opt_direct;
   MapOut o3{};
@@ -1375,6 +1501,7 @@ static int update_apply_impl(psgd_ctx* ctx, float* U, float* V, float* d, const 
   if (balance) PSGD_RETURN_IF(balance_pass(ctx, U, V, n * R, s.st));
 
   SweepArgs a1{};
+  a1.zero_word = &s.st->ticket;
   a1.mat[0] = U; a1.mat[1] = V; a1.vec[0] = d; a1.vec[1] = h; a1.vec[2] = v; a1.vec[3] = g; a1.n = n;
   a1.direct = ctx->opt_direct;
   PSGD_RETURN_IF((update_head<R>(ctx, a1, s, grid, 1, update_U, step, tiny)));
@@ -1384,13 +1511,10 @@ static int update_apply_impl(psgd_ctx* ctx, float* U, float* V, float* d, const 
   if (update_U) PSGD_RETURN_IF((launch_map<R, kMapUpdAppU>(ctx, a1, o2, 1, grid)));
   else PSGD_RETURN_IF((launch_map<R, kMapUpdAppV>(ctx, a1, o2, 0, grid)));
   constexpr int cnt = updapp_count(R);
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, cnt, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, cnt, &s.st->max_nabla, 1));
-  uvd_small_ua_kernel<<<1, 32, 0, st>>>(s.G, R, update_U, step, tiny, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, cnt, kMidSmallUA, R, 1, update_U, step, tiny, &s.st->max_nabla, 1));
 
   SweepArgs a3{};
+  a3.zero_word = &s.st->ticket;
   a3.mat[0] = U; a3.mat[1] = V; a3.vec[0] = d; a3.vec[1] = s.nd; a3.vec[2] = g; a3.n = n; a3.direct = ctx->opt_direct;
   MapOut o3{};
   o3.o0 = out; o3.o1 = d; o3.st = s.st;
@@ -1407,14 +1531,11 @@ static int apply_impl(psgd_ctx* ctx, const float* U, const float* V, const float
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
+  a.zero_word = &s.st->ticket;
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kApply>::TABLE;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
-  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, table, kMidSmallApply, R, 0, 0, 0.f, 0.f, nullptr, 0));
   MapOut o{};
   o.o0 = out; o.st = s.st;
   PSGD_RETURN_IF((launch_map<R, kMapApply2>(ctx, a, o, 0, grid)));
@@ -1463,14 +1584,11 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s, (clip && !pre_out) ? n : 0));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
+  a.zero_word = &s.st->ticket;
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = d; a.vec[1] = g; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kApply>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kApply>::TABLE;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
-  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, table, kMidSmallApply, R, 0, 0, 0.f, 0.f, nullptr, 0));
   MapOut o{};
   o.st = s.st;
   if (!clip) {
@@ -1481,9 +1599,7 @@ static int step_tail_impl(psgd_ctx* ctx, const float* U, const float* V, const f
   float* pre = pre_out ? pre_out : s.a;
   o.o0 = pre; o.partial = s.partial;
   PSGD_RETURN_IF((launch_map<R, kMapApplyNorm>(ctx, a, o, 0, grid)));
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, 1, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, 1, nullptr, 0));
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, 1, kMidNone, R, 0, 0, 0.f, 0.f, nullptr, 0));
   clip_update_kernel<<<ctx->num_sms * 8, 256, 0, st>>>(param, pre, v, n, lr_params, max_norm, tiny, s.G);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
@@ -1498,15 +1614,13 @@ static int matvec_impl(psgd_ctx* ctx, const float* U, const float* V, const floa
   PSGD_RETURN_IF(carve(ctx, n, R, grid, 0, &s));
   cudaStream_t st = ctx->stream;
   SweepArgs a{};
+  a.zero_word = &s.st->ticket;
   a.mat[0] = U; a.mat[1] = V; a.vec[0] = x; a.n = n; a.direct = ctx->opt_direct;
   PSGD_RETURN_IF((launch_gram<R, kMatvec>(ctx, a, s.partial, grid)));
   constexpr int table = GramPlan<R, kMatvec>::TABLE;
-  reduce_partials_kernel<<<1, kReduceThreads, 0, st>>>(s.partial, grid, table, s.G);
-  PSGD_LAUNCH_CHECK(ctx);
-  PSGD_RETURN_IF(cross_rank_reduce(ctx, s.G, table, nullptr, 0));
-  uvd_small_apply_kernel<<<1, 32, 0, st>>>(s.G, R, s.st);   // p = V^T x (t unused)
-  PSGD_LAUNCH_CHECK(ctx);
+  PSGD_RETURN_IF(mid_step(ctx, s, grid, table, kMidSmallApply, R, 0, 0, 0.f, 0.f, nullptr, 0));   // p = V^T x (t unused)
   SweepArgs a2{};
+  a2.zero_word = &s.st->ticket;
   a2.mat[0] = U; a2.vec[0] = x; a2.n = n; a2.direct = ctx->opt_direct;
   MapOut o{};
   o.o0 = out; o.st = s.st;

@@ -89,11 +89,34 @@ def chunk_bounds(n: int, world: int, rank: int, align: int = 256) -> Tuple[int, 
 
 
 def mirrored_chunk_bounds(n: int, world: int, rank: int, align: int = 256) -> Tuple[Tuple[int, int], Tuple[int, int]]:
-    """X-shape sharding: element i only ever meets n-1-i, so rank k owns a chunk of the first half and its mirror
-    image in the second half; no data exchange is needed, only the max all-reduce."""
-    half = (n + 1) // 2
-    lo, hi = chunk_bounds(half, world, rank, align)
+    """X-shape sharding: element i only ever meets n-1-i, so rank k owns a chunk [lo, hi) of the first n // 2 elements
+    and its mirror image [n-hi, n-lo) in the second half; no data exchange is needed, only the max all-reduce.  For odd
+    n the centre element n // 2 (its own mirror image) belongs to neither half: see :func:`xmat_shard_slices`."""
+    lo, hi = chunk_bounds(n // 2, world, rank, align)
     return (lo, hi), (n - hi, n - lo)
+
+
+def xmat_shard_slices(n: int, world: int, rank: int, align: int = 256) -> List[Tuple[int, int]]:
+    """Index ranges of the global vector that make up rank ``rank``'s LOCAL X-shape problem, in local order:
+    ``[lo, hi)``, the centre element when n is odd and this rank owns it, then ``[n-hi, n-lo)``.  The local vector is
+    itself a flip-symmetric problem (local element j meets local element n_local-1-j exactly when their global indices
+    are mirror images), so each rank calls ``update_precond_Xmat`` / ``precond_grad_Xmat`` on its concatenated shard
+    unchanged and the library only exchanges the max of |nabla| (csrc/elementwise.cu).  The centre goes to the last
+    rank with a non-empty chunk (rank 0 when n < 2), whose local length is then odd with the centre in the middle, which
+    is where the kernel zeroes nabla_b."""
+    (lo, hi), (mlo, mhi) = mirrored_chunk_bounds(n, world, rank, align)
+    parts = [(lo, hi)]
+    if n % 2 == 1:
+        owners = [k for k in range(world) if chunk_bounds(n // 2, world, k, align)[1] > chunk_bounds(n // 2, world, k, align)[0]]
+        if rank == (owners[-1] if owners else 0):
+            parts.append((n // 2, n // 2 + 1))
+    parts.append((mlo, mhi))
+    return parts
+
+
+def xmat_shard(x: torch.Tensor, world: int, rank: int, align: int = 256) -> torch.Tensor:
+    """This rank's local X-shape vector (a copy) cut from the global 1-D tensor ``x``."""
+    return torch.cat([x[a:b] for a, b in xmat_shard_slices(x.numel(), world, rank, align)])
 
 
 def assign_layers(costs: Sequence[float], world: int) -> List[List[int]]:

@@ -30,6 +30,33 @@ def cpu_protocol(rank, world):
             assert a[1] == b[0] and (a[0] % 256 == 0 or a[0] == a[1])
     (lo, hi), (mlo, mhi) = partition.mirrored_chunk_bounds(1001, world, rank)
     assert (mlo, mhi) == (1001 - hi, 1001 - lo)
+    # ---- X-shape on mirrored chunk pairs (+ the centre for odd n): the shards partition the vector, every local
+    # problem is flip-symmetric, and local X-shape math with ONE max all-reduce reproduces the unsharded oracle -------
+    for n in (1, 2, 7, 1000, 1001, 70_001):
+        sl = [partition.xmat_shard_slices(n, world, k) for k in range(world)]
+        seen = np.zeros(n, int)
+        for parts in sl:
+            for a, b in parts:
+                seen[a:b] += 1
+        assert (seen == 1).all(), (n, sl)
+        idx = np.concatenate([np.arange(a, b) for a, b in sl[rank]]).astype(int)
+        assert (idx + idx[::-1] == n - 1).all()                        # local flip == global flip
+        c = cases.vec_case(n, n)
+        la, lb, lv, lh = (c[k][idx].astype(np.float64) for k in ("a", "b", "v", "h"))
+        flip = lambda x: x[::-1]
+        Qh = la * lh + lb * flip(lh)
+        iq = (flip(la) * lv - flip(lb) * flip(lv)) / (la * flip(la) - lb * flip(lb))
+        na, nb = Qh * Qh - iq * iq, Qh * flip(Qh) - iq * flip(iq)
+        if len(idx) % 2 == 1:
+            nb[len(idx) // 2] = 0
+        mx = torch.tensor([max(np.abs(na).max(), np.abs(nb).max()) if len(idx) else 0.0], dtype=torch.float64)
+        dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+        mu = 0.01 / (mx.item() + float(O.TINY))
+        an, bn = la - mu * (na * la + nb * flip(lb)), lb - mu * (na * lb + nb * flip(la))
+        f64 = {k: c[k].astype(np.float64) for k in c}
+        ar, br = O.update_precond_Xmat(f64["a"], f64["b"], f64["v"], f64["h"], 0.01)
+        np.testing.assert_allclose(an, ar[idx], rtol=1e-10)
+        np.testing.assert_allclose(bn, br[idx], rtol=1e-10, atol=1e-300)
     # ---- layer assignment + all-gather -----------------------------------------------------------------
     shapes = cases.LENET_SHAPES
     owned = partition.assign_layers([partition.kron_layer_cost(m, n) for m, n in shapes], world)
@@ -147,10 +174,23 @@ def gpu_uvd(rank, world, exchange="hook"):
     psgd.update_precond_diag(q, dev(c["v"][lo:hi]), dev(c["h"][lo:hi]), 0.01)
     want = O.update_precond_diag(c["a"], c["v"], c["h"], 0.01)
     assert np.allclose(q.cpu().numpy(), want[lo:hi], rtol=1e-5)
+    # X-shape on mirrored chunk pairs (odd n: the centre sits on the last rank), against the unsharded oracle
+    n_x = 0
+    for n in (20_001, 100_000):
+        c = cases.vec_case(8 + n, n)
+        idx = np.concatenate([np.arange(a, b) for a, b in partition.xmat_shard_slices(n, world, rank)]).astype(int)
+        a_, b_ = dev(c["a"][idx]), dev(c["b"][idx])
+        psgd.update_precond_Xmat(a_, b_, dev(c["v"][idx]), dev(c["h"][idx]), 0.01)
+        ar, br = O.update_precond_Xmat(c["a"], c["b"], c["v"], c["h"], 0.01)
+        assert np.allclose(a_.cpu().numpy(), ar[idx], rtol=1e-5, atol=1e-7), ("xmat a", n)
+        assert np.allclose(b_.cpu().numpy(), br[idx], rtol=1e-5, atol=1e-7), ("xmat b", n)
+        pre = psgd.precond_grad_Xmat(a_, b_, dev(c["g"][idx]))                      # no exchange: purely local
+        assert np.allclose(pre.cpu().numpy(), O.precond_grad_Xmat(ar, br, c["g"])[idx], rtol=2e-5, atol=1e-6), ("xmat pre", n)
+        n_x += 1
     if exchange == "peer":
         done = ctx.comm_status()                  # raises if any in-kernel wait timed out
-        # per size: separate calls 2+1 exchanges (plain step) + 3+1 (balance step), fused call 2 + 3; + diag
-        assert done == 3 * (3 + 4 + 2 + 3) + 1, done
+        # per size: separate calls 2+1 exchanges (plain step) + 3+1 (balance step), fused call 2 + 3; + diag + X-shape
+        assert done == 3 * (3 + 4 + 2 + 3) + 1 + n_x, done
         gpu_uvd_graph(rank, world, ctx)
         ctx.comm_detach()
     else:

@@ -10,9 +10,10 @@ torch.manual_seed(0)
 ctx = psgd.get_context()
 
 
-def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128, mode=1):
+def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128, mode=1, pair=1):
     ctx.set_option("tc_bn", bn)
     ctx.set_option("tc_mode", mode)
+    ctx.set_option("tc_pair", pair)
     A = torch.randn((K, M) if ta else (M, K), device="cuda")
     B = torch.randn((N, K) if tb else (K, N), device="cuda")
     if a_tri:
@@ -33,7 +34,7 @@ def run(M, N, K, ta, tb, engine=2, triu=0, a_tri=0, b_tri=0, bn=128, mode=1):
     err = (Cm.double() - ref)
     rel = (err.norm() / ref.norm()).item()
     nan = torch.isnan(Cm).sum().item()
-    msg = f"M={M} N={N} K={K} ta={ta} tb={tb} eng={engine} mode={'TS' if mode else 'SS'} triu={triu} tri=({a_tri},{b_tri}): rel={rel:.3e} nan={nan}"
+    msg = f"M={M} N={N} K={K} ta={ta} tb={tb} eng={engine} mode={'TS' if mode else 'SS'}{'+pair' if (pair and mode) else ''} triu={triu} tri=({a_tri},{b_tri}): rel={rel:.3e} nan={nan}"
     if not (rel < 1e-5):
         # where are the errors? per 32x32 block
         e = torch.nan_to_num(err, nan=1e3).abs()
@@ -61,6 +62,40 @@ if __name__ == "__main__":
             run(512, 512, 512, 0, 0, a_tri=1, b_tri=1, triu=1, mode=mode)
             run(100, 4096, 2048, 1, 0, mode=mode)
             run(4096, 4096, 4096, 0, 1, mode=mode)
+    elif which == "pairbasic":
+        # CTA-pair kernel (cta_group::2): every operand layout, ragged edges, triangular hints, one tiny case first
+        run(256, 128, 32, 0, 1)
+        for ta, tb in ((0, 1), (1, 1), (0, 0), (1, 0)):
+            run(256, 256, 256, ta, tb)
+            run(384, 640, 320, ta, tb)
+            run(1000, 520, 264, ta, tb)
+        run(512, 512, 512, 0, 1, triu=1)
+        run(1024, 1024, 1024, 0, 0, a_tri=1, b_tri=1, triu=1)
+        run(1024, 1024, 1024, 1, 0, a_tri=2, b_tri=1)
+        run(4096, 4096, 4096, 0, 1)
+    elif which == "pairperf":
+        def timeit(args, n=20):
+            for _ in range(3):
+                check(ctx.lib.psgd_gemm(*args))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                check(ctx.lib.psgd_gemm(*args))
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        for (M, N, K) in ((4096, 4096, 4096), (4096, 4096, 1024), (4096, 1024, 1024), (1024, 4096, 1024)):
+            for (ta, tb) in ((0, 1), (0, 0), (1, 0)):
+                A = torch.randn((K, M) if ta else (M, K), device="cuda"); B = torch.randn((N, K) if tb else (K, N), device="cuda")
+                Cm = torch.empty(M, N, device="cuda")
+                args = (ctx.handle, 2, M, N, K, C.c_void_p(A.data_ptr()), A.shape[1], ta, C.c_void_p(B.data_ptr()), B.shape[1], tb,
+                        C.c_void_p(Cm.data_ptr()), N, 0, 0, 0)
+                out = []
+                for pair in (0, 1):
+                    ctx.set_option("tc_pair", pair)
+                    ms = timeit(args)
+                    out.append(f"{'pair  ' if pair else 'single'} {ms:.3f} ms {2 * M * N * K / ms / 1e9:6.1f} TF")
+                print(f"M={M} N={N} K={K} ta={ta} tb={tb}: " + " | ".join(out), flush=True)
+        ctx.set_option("tc_pair", 1)
     elif which == "ablate":
         # where does the time go?  (results are wrong with debug bits set)  + clocks/power under a sustained loop
         import subprocess, time
