@@ -271,8 +271,13 @@ def run_uvd(args, rank, world, local):
     if rank == 0:
         clocks.start()
     U, V, d = U0.clone(), V0.clone(), d0.clone()
-    for i in range(args.warmup + (2 * POOL if use_graphs else 0)):      # graphs: capture every (inputs, coin flip) key
-        step(i, U, V, d, *pool[i % POOL])
+    # Step k always uses input set k % POOL and coin flips (k % 100 == 99, k % 2 == 0), in the warm-up and in the timed
+    # region alike, so that every CUDA graph the timed region replays (keyed by input buffers + coin flips) has been
+    # captured during the warm-up.
+    run_step = lambda k: step(k, U, V, d, *pool[k % POOL])
+    n_warm = args.warmup + (2 * POOL if use_graphs else 0)
+    for i in range(n_warm):
+        run_step(i)
     if not use_graphs:
         ctx.set_option("profile", 1)
     ctx.profile_read()
@@ -286,7 +291,7 @@ def run_uvd(args, rank, world, local):
         marks[0].record()
         out = None
         for i in range(args.steps):
-            out = step(first_step + i, U, V, d, *pool[i % POOL])
+            out = run_step(first_step + i)
             marks[i + 1].record()
         barrier()
         per = [marks[i].elapsed_time(marks[i + 1]) for i in range(args.steps)]
@@ -294,7 +299,7 @@ def run_uvd(args, rank, world, local):
 
     launches0 = ctx.launch_count
     graph_launches0 = sum(g.kernel_launches for g in graphs.values())
-    ms, per_step, pre = timed_region(args.warmup)
+    ms, per_step, pre = timed_region(n_warm)
     remeasured = None
     med = float(np.median(per_step))
     flag = torch.tensor([1.0 if max(per_step) > 3.0 * med and ms > 1.15 * med * args.steps else 0.0], device=dev)
@@ -307,7 +312,7 @@ def run_uvd(args, rank, world, local):
         ctx.profile_read()
         launches0 = ctx.launch_count
         graph_launches0 = sum(g.kernel_launches for g in graphs.values())
-        ms, per_step, pre = timed_region(args.warmup + args.steps)
+        ms, per_step, pre = timed_region(n_warm + args.steps)
     clk = clocks.stop() if rank == 0 else None
     launches = ctx.launch_count - launches0 + sum(g.kernel_launches for g in graphs.values()) - graph_launches0
     kernels_from = "CUDA events around every launch inside the timed region"
@@ -318,7 +323,7 @@ def run_uvd(args, rank, world, local):
         ctx.set_option("profile", 1)
         ctx.profile_read()
         for i in range(min(args.steps, 6)):
-            step(args.warmup + i, U, V, d, *pool[i % POOL])
+            run_step(n_warm + i)
         torch.cuda.synchronize()
         use_graphs = True
         kernels_from = "separate eager pass right after the (graph-replayed) timed region"
@@ -365,13 +370,14 @@ def run_uvd(args, rank, world, local):
     separate = None
     if form == "fused" and not args.no_separate and (world == 1 or use_graphs):
         form = "separate"
-        for i in range(3 + (2 * POOL if use_graphs else 0)):
-            step(i, U, V, d, *pool[i % POOL])
+        n_warm2 = 3 + (2 * POOL if use_graphs else 0)
+        for i in range(n_warm2):
+            run_step(i)
         barrier()
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         s0.record()
         for i in range(args.steps):
-            step(args.warmup + i, U, V, d, *pool[i % POOL])
+            run_step(n_warm2 + i)
         s1.record()
         barrier()
         t = torch.tensor([s0.elapsed_time(s1)], device=dev)
@@ -450,7 +456,7 @@ def run_uvd(args, rank, world, local):
         barrier()
         f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         f0.record()
-        e2e_loop(args.steps, args.warmup)
+        e2e_loop(args.steps, 2 * args.warmup)          # even base, like the warm-up's: the same two graph keys
         f1.record()
         barrier()
         ems = f0.elapsed_time(f1)

@@ -73,8 +73,14 @@ struct psgd_ctx {
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
-  int opt_tc_pair = 1;       // tcgen05 GEMM: 1 = CTA-pair kernel (cta_group::2, 256-row tiles) where applicable, 0 = single-CTA only
+  int opt_tc_pair_sel = -1;  // debugging aid: >= 0 = only the sel-th tensor-core GEMM launch since the option was set uses the pair kernel
+  int tc_launch_seq = 0;
+  int opt_tc_pair = 0;       // tcgen05 GEMM: 1 = CTA-pair kernel (cta_group::2, 256-row tiles) where applicable, 0 = single-CTA only
   int opt_tc_mode = 1;       // tcgen05 GEMM A operand: 1 = through tensor memory (TS), 0 = from shared memory (SS)
+  int opt_kron_streams = 1;  // Kron batched calls: 1 = groups of different shape run concurrently on internal side streams
+  static constexpr int kSideStreams = 4;
+  cudaStream_t side[kSideStreams] = {};      // created on first use (kron.cu), joined back into `stream` before a call returns
+  cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
   int opt_uvd_mid = 1;       // UVd: 1 = one "mid" launch between sweeps (reduce + exchange + algebra), 0 = three launches
   int opt_comm_timeout_ms = 0;   // peer exchange: wait limit per exchange (0 = the 20 s default)
   int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks

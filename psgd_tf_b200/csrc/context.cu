@@ -69,6 +69,11 @@ extern "C" int psgd_destroy(psgd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->ws);
   }
+  for (int k = 0; k < psgd_ctx::kSideStreams; ++k) {
+    if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
+    if (ctx->ev_side[k]) cudaEventDestroy(ctx->ev_side[k]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   delete ctx;
   return PSGD_OK;
 }
@@ -103,9 +108,11 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
     ctx->opt_trsm_base = (int)value;
     return PSGD_OK;
   }
+  if (strcmp(key, "kron_streams") == 0) { ctx->opt_kron_streams = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "uvd_mid") == 0) { ctx->opt_uvd_mid = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "comm_timeout_ms") == 0) { ctx->opt_comm_timeout_ms = value > 0 ? (int)value : 0; return PSGD_OK; }
   if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }
+  if (strcmp(key, "tc_pair_sel") == 0) { ctx->opt_tc_pair_sel = (int)value; ctx->tc_launch_seq = 0; return PSGD_OK; }
   if (strcmp(key, "tc_pair") == 0) { ctx->opt_tc_pair = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_mode") == 0) { ctx->opt_tc_mode = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "gemm_path") == 0) {

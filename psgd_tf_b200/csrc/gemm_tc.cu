@@ -23,6 +23,7 @@
 // (transpose_a / transpose_b) is a descriptor flag, never a copy.  Triangular operands restrict each tile's K range
 // and triu outputs skip tiles below the diagonal.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include <vector>
 
@@ -79,7 +80,8 @@ struct Params {
   int pair_b, pair_kind;    // block-pair mode (triangular block-inverse doubling): only tiles with (m0/b even, n0/b == m0/b + 1)
                             // exist; K range = the n-block (kind 1) or the m-block (kind 2)
   int negate;               // C = -(acc)
-  int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs
+  int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs,
+                            // 8 skip the epilogue's global stores
   float* C[kMaxGroup];
   float* maxabs[kMaxGroup];
   const float* D[kMaxGroup];
@@ -380,6 +382,9 @@ __global__ void __launch_bounds__(kThreads, 1)
           }
         }
       }
+      // producer tail: nobody waits for the stage releases of the last kStages iterations; collect them before the CTA
+      // exits so that no tcgen05.commit arrival is still in flight towards shared memory that a later CTA re-initialises
+      for (int j = it > C::kStages ? it - C::kStages : 0; j < it; ++j) mbar_wait(&empty[j % C::kStages], (j / C::kStages) & 1);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -573,7 +578,9 @@ __global__ void __launch_bounds__(kThreads, 1)
       const float* const csg = p.colscale[grp];
       float mu = 0.f;
       if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
-      const float rho = p.rho_mode ? *p.rho[grp] : 1.0f;
+      // rho_mode 1: Ql / rho, 2: rho * Qr (psgd.py:169-170) as ONE multiply per element -- an IEEE division here would be
+      // expanded 128 times in the unrolled epilogue (+30 % SASS, measured 25 % slower end to end: instruction cache)
+      const float oscale = p.rho_mode == 1 ? 1.0f / *p.rho[grp] : (p.rho_mode == 2 ? *p.rho[grp] : 1.0f);
       int total_kb = 0;
       if (!(p.triu && m0 >= n0 + BN)) {
         for (int prod = 0; prod < 2; ++prod) {
@@ -603,7 +610,7 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[a]);
       }
-      if (m < p.M) {
+      if (m < p.M && !(p.debug & 8)) {
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int nbase = n0 + c * 32;
@@ -623,8 +630,7 @@ __global__ void __launch_bounds__(kThreads, 1)
             }
             if (p.triu && m > n) x = 0.f;
             if (drow && n < p.N) x = drow[j] - mu * x;
-            if (p.rho_mode == 1) x = x / rho;
-            else if (p.rho_mode == 2) x = x * rho;
+            if (p.rho_mode) x = x * oscale;
             if (n < p.N) mx = fmaxf(mx, fabsf(x));
             v[j] = x;
           }
@@ -669,6 +675,16 @@ __global__ void __launch_bounds__(kThreads, 1)
 //   tmem_empty[a]  epilogue warps of BOTH CTAs -> the leader's MMA warp (count 8)
 // Only the leader (cluster rank 0) issues MMAs; its instruction reads A from both CTAs' tensor memory and B from both
 // CTAs' shared memory at the SAME addresses, and accumulates into both CTAs' tensor memory.
+//
+// MEASURED (profiles/r02_gemm_ablation.txt, dense 4096^3, one B200): correct in every operand layout (1.0e-6 vs float64),
+// but SLOWER than the single-CTA kernel -- 1.08 ms (127 TFLOP/s fp32-equivalent) against 0.74-0.79 ms (175-187).  The
+// ablation says why: with splitting AND MMAs switched off ("TMA + barriers only") the pair pipeline still needs 1.04 ms,
+// the single-CTA one 0.52 ms.  The pair kernel is bound by the round trip of its stage ring, not by shared-memory
+// bandwidth: every stage now crosses the cluster twice (remote mbarrier arrive of the peer's splitter, multicast commit
+// back), and with A in tensor memory the ring cannot be deeper than 4 stages (2 x 128 accumulator columns + 4 x 64 A
+// columns = all 512), i.e. 96 KB in flight per SM against 128 KB for the single-CTA kernel.  It therefore stays OFF by
+// default (psgd_set_option("tc_pair", 1) selects it; tests/test_gpu_tensorcore.py keeps it honest); making it pay needs
+// a deeper ring (A through shared memory again, or BK = 16 stages) -- left as measured, not guessed.
 // =============================================================================================
 constexpr int BM2 = 256;
 
@@ -854,6 +870,12 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           }
         }
       }
+      // producer tail (BOTH CTAs): the leader's multicast tcgen05.commit arrivals on empty[] of the last kStages
+      // iterations are asynchronous and waited for by nobody; without this a late arrival can land after this CTA has
+      // exited, on the freshly initialised barrier of the next launch's CTA (same shared-memory layout), which then
+      // refills a stage the tensor core is still reading -- seen as rare, timing-dependent corruption of back-to-back
+      // launches (the triangular-solve recursion)
+      for (int j = it > C::kStages ? it - C::kStages : 0; j < it; ++j) mbar_wait(&empty[j % C::kStages], (j / C::kStages) & 1);
     }
     __syncwarp();
   } else if (warp == 1) {
@@ -1022,7 +1044,9 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const float* const csg = p.colscale[grp];
       float mu = 0.f;
       if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
-      const float rho = p.rho_mode ? *p.rho[grp] : 1.0f;
+      // rho_mode 1: Ql / rho, 2: rho * Qr (psgd.py:169-170) as ONE multiply per element -- an IEEE division here would be
+      // expanded 128 times in the unrolled epilogue (+30 % SASS, measured 25 % slower end to end: instruction cache)
+      const float oscale = p.rho_mode == 1 ? 1.0f / *p.rho[grp] : (p.rho_mode == 2 ? *p.rho[grp] : 1.0f);
       int total_kb = 0;
       if (!(p.triu && m0 >= n0 + BN)) {
         for (int prod = 0; prod < 2; ++prod) {
@@ -1055,7 +1079,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           else mbar_arrive_remote(&tmem_empty[a], 0);
         }
       }
-      if (m < p.M) {
+      if (m < p.M && !(p.debug & 8)) {
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int nbase = n0 + c * 32;
@@ -1075,8 +1099,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
             }
             if (p.triu && m > n) x = 0.f;
             if (drow && n < p.N) x = drow[j] - mu * x;
-            if (p.rho_mode == 1) x = x / rho;
-            else if (p.rho_mode == 2) x = x * rho;
+            if (p.rho_mode) x = x * oscale;
             if (n < p.N) mx = fmaxf(mx, fabsf(x));
             v[j] = x;
           }
@@ -1284,8 +1307,27 @@ static int launch_pair(psgd_ctx* ctx, const la::Gemm* gs, int count) {
     PSGD_CUDA_CHECK(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)C::kSmemBytes));
     attr_done.set(ctx->device);
   }
+  // persistent clusters: never launch more clusters than can be co-resident (a second wave would double the time of a
+  // statically scheduled tile loop).  Not every TPC has both SMs enabled, so this can be fewer than num_sms / 2.
+  static int max_clusters[64] = {0};
+  const int dv = ctx->device & 63;
+  if (max_clusters[dv] == 0) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(ctx->num_sms / 2 * 2);
+    cfg.blockDim = dim3(kThreads);
+    cfg.dynamicSmemBytes = C::kSmemBytes;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    int nc = 0;
+    cudaError_t e = cudaOccupancyMaxActiveClusters(&nc, kern, &cfg);
+    if (e != cudaSuccess || nc <= 0) { (void)cudaGetLastError(); nc = ctx->num_sms / 2; }
+    if (nc > ctx->num_sms / 2) nc = ctx->num_sms / 2;
+    max_clusters[dv] = nc;
+  }
   int pairs = p.tiles_m * p.tiles_n * count;
-  if (pairs > ctx->num_sms / 2) pairs = ctx->num_sms / 2;
+  if (pairs > max_clusters[dv]) pairs = max_clusters[dv];
   if (ctx->opt_profile == 2) {
     // executed flops, counted per CTA tile (128 rows): the K blocks of the PAIR tile are executed by both halves
     double kbs = 0.0;
@@ -1309,11 +1351,17 @@ static int launch_pair(psgd_ctx* ctx, const la::Gemm* gs, int count) {
 }
 
 // opt_tc_mode: 1 (default) = A operand through tensor memory ("TS"), 0 = both operands from shared memory ("SS").
-// opt_tc_pair: 1 (default) = CTA-pair kernel (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows
-// and is not a block-pair (triangular inverse doubling) launch.
+// opt_tc_pair: 1 = CTA-pair kernel (cta_group::2, 256-row tiles) whenever the problem has at least 256 rows and is not a
+// block-pair (triangular inverse doubling) launch; 0 (default) = single-CTA kernel only (see the measurements above).
 template <int BN>
 static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
-  if (ctx->opt_tc_pair && ctx->opt_tc_mode && gs[0].pair_b == 0 && gs[0].M >= BM2) return launch_pair<BN>(ctx, gs, count);
+  const int seq = ctx->tc_launch_seq++;
+  const bool sel = ctx->opt_tc_pair_sel < 0 || ctx->opt_tc_pair_sel == seq;
+  if (ctx->opt_tc_pair_sel >= 0 && sel && getenv("PSGD_TC_TRACE"))
+    fprintf(stderr, "[tc %d] M=%d N=%d K=%d K2=%d ta=%d tb=%d triu=%d a_tri=%d b_tri=%d D=%d maxabs=%d rho=%d cs=%d pair_b=%d cnt=%d\n", seq,
+            gs[0].M, gs[0].N, gs[0].K, gs[0].K2, (int)gs[0].ta, (int)gs[0].tb, (int)gs[0].triu, gs[0].a_tri, gs[0].b_tri,
+            gs[0].D != nullptr, gs[0].maxabs != nullptr, gs[0].rho_mode, gs[0].colscale != nullptr, gs[0].pair_b, count);
+  if (ctx->opt_tc_pair && sel && ctx->opt_tc_mode && gs[0].pair_b == 0 && gs[0].M >= BM2) return launch_pair<BN>(ctx, gs, count);
   return ctx->opt_tc_mode ? launch_impl<BN, true>(ctx, gs, count) : launch_impl<BN, false>(ctx, gs, count);
 }
 
@@ -1404,6 +1452,12 @@ __global__ void __launch_bounds__(kInvBlock) tri_inv_blocks_kernel(const __grid_
   __syncthreads();
   if (j < jb)
     for (int i = 0; i < jb; ++i) Z[(size_t)(b0 + i) * ldz + b0 + j] = Zs[i][j];
+  // The block to the LEFT of every odd diagonal block is structurally zero (Z is upper triangular) but lives in
+  // uninitialised scratch.  128-row tiles never read it under the triangular K-range hints; the CTA-pair kernel's
+  // 256-row tiles do (one K range serves both halves of the tile: rows m0 .. m0+127 also see k up to m0+255), so it is
+  // written here -- found as stale-workspace garbage in the left leaves of the solve once a 128-wide run had gone before.
+  if ((blockIdx.x & 1) && j < kInvBlock)
+    for (int i = 0; i < jb; ++i) Z[(size_t)(b0 + i) * ldz + (b0 - kInvBlock) + j] = 0.f;
 }
 
 static int invert_diag_blocks(psgd_ctx* ctx, const Trsm* ts, int count, int ldq, int n, int ldz) {

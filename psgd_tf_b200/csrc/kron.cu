@@ -10,6 +10,7 @@
 //   update_precond_dense / precond_grad_dense          psgd.py:26-63
 // Large contractions go through the GEMM/TRSM vocabulary of linalg.cuh (SIMT fp32 or tcgen05 3xTF32,
 // chosen per layer size); everything touching a [2,N]/[1,N] factor is a bandwidth-bound kernel here.
+#include <algorithm>
 #include <vector>
 
 #include "linalg.cuh"
@@ -775,6 +776,16 @@ static int check_layer(const char* what, int kl, int kr, int64_t M, int64_t N) {
 
 struct Key { int kl, kr, M, N; };
 
+static int ensure_side_streams(psgd_ctx* ctx) {
+  if (ctx->ev_fork) return PSGD_OK;
+  for (int k = 0; k < psgd_ctx::kSideStreams; ++k) {
+    PSGD_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->side[k], cudaStreamNonBlocking));
+    PSGD_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_side[k], cudaEventDisableTiming));
+  }
+  PSGD_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming));
+  return PSGD_OK;
+}
+
 // Runs update (is_update) or apply over a ragged list of layers.  Mirrored formats ((dense,norm), (scale,dense),
 // (scale,norm)) are brought to canonical orientation by transposing dX,dG / G into scratch and swapping the factors
 // (exactly what the reference does, psgd.py:86, :102, :104, :128, :144, :146); layers with equal canonical
@@ -845,18 +856,60 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
       else carve_apply(ctx, c, L, kl, kr, M, N);
     }
     // group equal keys (stable)
+    struct Group { Key key; std::vector<Layer> layers; double cost; int slot; };
+    std::vector<Group> groups;
     std::vector<char> done(end - begin, 0);
     for (int i = 0; i < end - begin; ++i) {
       if (done[i]) continue;
-      std::vector<Layer> grp;
-      std::vector<int> idx;
+      Group g;
+      g.key = keys[i];
       for (int j = i; j < end - begin; ++j)
         if (!done[j] && keys[j].kl == keys[i].kl && keys[j].kr == keys[i].kr && keys[j].M == keys[i].M && keys[j].N == keys[i].N) {
-          grp.push_back(Ls[j]); idx.push_back(j); done[j] = 1;
+          g.layers.push_back(Ls[j]); done[j] = 1;
         }
-      if (is_update) PSGD_RETURN_IF(update_group(ctx, keys[i].kl, keys[i].kr, grp, keys[i].M, keys[i].N, step, tiny));
-      else PSGD_RETURN_IF(apply_group(ctx, keys[i].kl, keys[i].kr, grp, keys[i].M, keys[i].N));
+      const double M = g.key.M, N = g.key.N;
+      g.cost = g.layers.size() * (M * N * ((g.key.kl == PSGD_FACTOR_DENSE ? M : 8.0) + (g.key.kr == PSGD_FACTOR_DENSE ? N : 8.0)) + 2e5);
+      g.slot = 0;
+      groups.push_back(std::move(g));
     }
+    // Groups are independent (layers share nothing, scratch is carved per layer): a ragged list (LeNet5: five shapes,
+    // the NMT model: seven) runs its groups CONCURRENTLY on internal side streams, forked from and joined back into the
+    // context's stream -- each group is a latency-bound chain of small launches that leaves most SMs idle.  Events
+    // only, so the whole call stays capturable into a CUDA graph (where the groups become parallel branches).
+    int nslots = 1;
+    if (ctx->opt_kron_streams && groups.size() > 1) {
+      nslots = (int)std::min<size_t>(groups.size(), psgd_ctx::kSideStreams + 1);
+      std::vector<int> order(groups.size());
+      for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+      std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return groups[a].cost > groups[b].cost; });
+      std::vector<double> load(nslots, 0.0);
+      for (int gi : order) {                      // longest-processing-time first
+        int best = 0;
+        for (int s = 1; s < nslots; ++s) if (load[s] < load[best]) best = s;
+        groups[gi].slot = best; load[best] += groups[gi].cost;
+      }
+      PSGD_RETURN_IF(ensure_side_streams(ctx));
+      PSGD_CUDA_CHECK(cudaEventRecord(ctx->ev_fork, ctx->stream));
+      for (int s = 1; s < nslots; ++s) PSGD_CUDA_CHECK(cudaStreamWaitEvent(ctx->side[s - 1], ctx->ev_fork, 0));
+    }
+    cudaStream_t main_stream = ctx->stream;
+    int status = PSGD_OK;
+    for (auto& g : groups) {
+      ctx->stream = g.slot == 0 ? main_stream : ctx->side[g.slot - 1];
+      status = is_update ? update_group(ctx, g.key.kl, g.key.kr, g.layers, g.key.M, g.key.N, step, tiny)
+                         : apply_group(ctx, g.key.kl, g.key.kr, g.layers, g.key.M, g.key.N);
+      if (status != PSGD_OK) break;
+    }
+    ctx->stream = main_stream;
+    for (int s = 1; s < nslots; ++s) {            // join (also after an error: never leave a forked stream dangling)
+      cudaError_t e1 = cudaEventRecord(ctx->ev_side[s - 1], ctx->side[s - 1]);
+      cudaError_t e2 = cudaStreamWaitEvent(main_stream, ctx->ev_side[s - 1], 0);
+      if (status == PSGD_OK && (e1 != cudaSuccess || e2 != cudaSuccess)) {
+        set_error("kron: joining side stream %d failed: %s", s, cudaGetErrorString(e1 != cudaSuccess ? e1 : e2));
+        status = PSGD_ERR_CUDA;
+      }
+    }
+    PSGD_RETURN_IF(status);
     if (!is_update)
       for (int i = begin; i < end; ++i)
         if (untranspose_src[i - begin])   // canonical result is [N,M]; give the caller [M,N]

@@ -751,11 +751,11 @@ class UVd:
                     closure_returns = closure()
                     grads = torch.autograd.grad(first(closure_returns), params)
                 vs = [torch.randn_like(p) * self._delta_param_scale for p in params]
-                with torch.no_grad():
-                    self._flat_params.add_(self._flatten(vs))
+                # param += v and Hv = perturbed_grad - grad through the library's multi-tensor kernels (csrc/multi.cu)
+                apply_preconditioned_updates([self._flat_params], [self._flatten(vs)], -1.0)          # psgd.py:717-718
                 with torch.enable_grad():
                     perturbed_grads = torch.autograd.grad(first(closure()), params)
-                Hvs = [pg - g for pg, g in zip(perturbed_grads, grads)]
+                Hvs = grad_differences(perturbed_grads, grads)                                          # psgd.py:725
                 self.step_with(grads, vs, Hvs, params_perturbed=True)
         else:                                                                          # psgd.py:737-744
             with torch.enable_grad():

@@ -96,6 +96,50 @@ if __name__ == "__main__":
                     out.append(f"{'pair  ' if pair else 'single'} {ms:.3f} ms {2 * M * N * K / ms / 1e9:6.1f} TF")
                 print(f"M={M} N={N} K={K} ta={ta} tb={tb}: " + " | ".join(out), flush=True)
         ctx.set_option("tc_pair", 1)
+    elif which == "ksweep":
+        # per-tile fixed cost vs per-stage cost of the single-CTA kernel: time(K) at M = N = 4096, with and without the
+        # epilogue's global stores (debug bit 8; results wrong)
+        ctx.set_option("tc_pair", 0)
+        M = N = 4096
+        for dbg in (0, 8):
+            ctx.set_option("tc_debug", dbg)
+            for K in (128, 256, 512, 1024, 2048, 4096, 8192):
+                A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); Cm = torch.empty(M, N, device="cuda")
+                args = (ctx.handle, 2, M, N, K, C.c_void_p(A.data_ptr()), K, 0, C.c_void_p(B.data_ptr()), K, 1,
+                        C.c_void_p(Cm.data_ptr()), N, 0, 0, 0)
+                for _ in range(5):
+                    check(ctx.lib.psgd_gemm(*args))
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                for _ in range(50):
+                    check(ctx.lib.psgd_gemm(*args))
+                e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / 50
+                print(f"debug={dbg} K={K:5d}: {ms * 1e3:8.1f} us  {2 * M * N * K / ms / 1e9:6.1f} TF  per-tile(7 tiles/CTA) {ms * 1e3 / 7:6.1f} us", flush=True)
+        ctx.set_option("tc_debug", 0)
+    elif which == "pairablate":
+        # where does the pair kernel's time go?  (results are wrong with debug bits set)
+        M = N = K = 4096
+        A = torch.randn(M, K, device="cuda"); B = torch.randn(K, N, device="cuda"); Cm = torch.empty(M, N, device="cuda")
+        args = (ctx.handle, 2, M, N, K, C.c_void_p(A.data_ptr()), K, 0, C.c_void_p(B.data_ptr()), N, 1,
+                C.c_void_p(Cm.data_ptr()), N, 0, 0, 0)
+        def loop(n=200):
+            for _ in range(5):
+                check(ctx.lib.psgd_gemm(*args))
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(n):
+                check(ctx.lib.psgd_gemm(*args))
+            e1.record(); torch.cuda.synchronize()
+            return e0.elapsed_time(e1) / n
+        for pair in (1, 0):
+            ctx.set_option("tc_pair", pair)
+            for dbg, name in ((0, "full"), (1, "no B split"), (2, "no A split"), (3, "no split"), (4, "no MMA"), (7, "TMA + barriers only")):
+                ctx.set_option("tc_debug", dbg)
+                ms = loop()
+                print(f"{'pair  ' if pair else 'single'} {name:22s}: {ms:.3f} ms  {2 * M * N * K / ms / 1e9:6.1f} TFLOP/s-equiv", flush=True)
+            ctx.set_option("tc_debug", 0)
+        ctx.set_option("tc_pair", 1)
     elif which == "ablate":
         # where does the time go?  (results are wrong with debug bits set)  + clocks/power under a sustained loop
         import subprocess, time
