@@ -118,6 +118,19 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         kernels.append(dict(kernel=names.get(kid, str(kid)), launches=cnt, total_ms=round(tot, 3), avg_ms=round(tot / cnt, 4),
                             executed_TFLOP=round(work / 1e12, 3), achieved_TFLOPs=round(ach, 1),
                             frac=round(ach / ceiling, 4), share_of_step=round(tot / ms, 4)))
+    # per-launch view of ONE step (the launch sequence repeats every step): which of the step's grouped launches run below
+    # the plain-product rate.  Times are averaged over the timed steps, position by position.
+    per_step = len(prof) // max(args.steps, 1)
+    by_launch = []
+    if per_step and per_step * args.steps == len(prof):
+        for pos in range(per_step):
+            rows = [prof[st * per_step + pos] for st in range(args.steps)]
+            kid = rows[0][0]
+            ms_avg = sum(r[1] for r in rows) / len(rows)
+            work = rows[0][2]
+            by_launch.append(dict(pos=pos, kernel={10: "gemm_tc", 11: "tri_inv", 12: "gemm_simt"}.get(kid, str(kid)),
+                                  ms=round(ms_avg, 3), executed_TFLOP=round(work / 1e12, 3),
+                                  TFLOPs=round(work / (ms_avg * 1e-3) / 1e12, 1) if ms_avg > 0 else 0.0))
     dom = max(kernels, key=lambda k: k["total_ms"]) if kernels else None
     step_flops = kron_flops(n) * len(mine)
     step_ach = step_flops / (ms / args.steps * 1e-3) / 1e12
@@ -226,7 +239,8 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="f32 (3xTF32 tensor-core products, fp32 accumulate)", data="synthetic",
         config=kron_config(L, n, world), run=dict(layers_per_gpu=len(mine)), parity=parity,
-        roofline=roofline, kernels=kernels, cpu_baseline=cpu, e2e=e2e, gpu_launches=int(launches), clocks=clk)
+        roofline=roofline, kernels=kernels, launches_of_one_step=by_launch, cpu_baseline=cpu, e2e=e2e,
+        gpu_launches=int(launches), clocks=clk)
 
 
 def kron_parity(psgd, Ql, Qr, dX, dG, G):

@@ -73,6 +73,7 @@ struct psgd_ctx {
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
+  int opt_tc_epi = 2;        // tcgen05 GEMM epilogue stores: 2 = staged through shared memory (full 128-byte lines), 1 = 256-bit, 0 = 128-bit per row
   int opt_tc_pair_sel = -1;  // debugging aid: >= 0 = only the sel-th tensor-core GEMM launch since the option was set uses the pair kernel
   int tc_launch_seq = 0;
   int opt_tc_pair = 0;       // tcgen05 GEMM: 1 = CTA-pair kernel (cta_group::2, 256-row tiles) where applicable, 0 = single-CTA only

@@ -36,8 +36,10 @@ constexpr int BM = 128;
 constexpr int BK = 32;                 // floats per stage along K = one 128-byte swizzle span
 constexpr int UMMA_K = 8;              // tf32
 constexpr int kThreads = 320;          // 10 warps
-constexpr int kEpiWarp0 = 2, kSplitWarp0 = 6;
+constexpr int kSplitWarp0 = 6;         // warps 2-5: epilogue, 6-9: splitter
 constexpr int kChunkKB = 4;            // K-blocks (of 32) per tensor-core accumulation chain
+constexpr int kEpiLd = 36;             // row pitch (floats) of an epilogue warp's 32 x 32 shared-memory stage: 16-byte
+                                       // accesses by row (lane = row) and by row segment (8 lanes = one row) are both conflict-free
 
 // TS = true : A operand through tensor memory.  Stage = [A raw | B hi | B lo]; TMEM = 2 accumulators (2 x BN columns)
 //             + per stage 32 columns of A hi and 32 of A lo (BK = 32 tf32 values per row).
@@ -56,7 +58,8 @@ struct Cfg {
   static constexpr int kATmemCol0 = kAccCols;                 // TS only: first column of the A stages
   static constexpr int kTmemCols = TS ? 512 : 2 * BN;
   static_assert(!TS || kAccCols + kStages * 2 * BK <= 512, "TMEM budget");
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                       4 * 32 * kEpiLd * 4 /*epilogue transposition stages*/;
 };
 
 // One launch covers up to kMaxGroup problems of identical shape and flags ("batched launch over all layers"): a tile
@@ -80,6 +83,7 @@ struct Params {
   int pair_b, pair_kind;    // block-pair mode (triangular block-inverse doubling): only tiles with (m0/b even, n0/b == m0/b + 1)
                             // exist; K range = the n-block (kind 1) or the m-block (kind 2)
   int negate;               // C = -(acc)
+  int epi;                  // epilogue stores: 2 staged through shared memory (full lines), 1 256-bit stores, 0 row-wise 128-bit
   int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs,
                             // 8 skip the epilogue's global stores
   float* C[kMaxGroup];
@@ -292,6 +296,79 @@ __host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int 
   if (kb1 < kb0) kb1 = kb0;
 }
 
+// Final epilogue of one 32 x 32 chunk of a tile, in the COALESCED domain.  The accumulators live one row per lane; stored
+// straight from there, every warp store touches 32 different lines with 16 bytes each -- partial-sector writes that cost
+// ~13 us per 128 x 128 tile (tools/gemm_debug.py ksweep: 18.5 us per K = 128 tile with the stores, 4.7 us without; short-K
+// products ran at 130 instead of 190 TFLOP/s).  The chunk is therefore turned through a padded shared-memory stage of the
+// warp (kEpiLd), and this routine walks it by ROW SEGMENT: 8 lanes x 16 bytes = one complete 128-byte line of a row, four
+// rows per step, so C is written -- and D of  C = D - mu acc  read -- in whole lines, and the column scale / triu mask /
+// max|.| ride along.  A rolled loop in a function of its own on purpose: the unrolled row-wise epilogue was 1.5k
+// instructions per copy, and this kernel's throughput drops by 25 % when its hot code outgrows the instruction cache
+// (measured twice: an IEEE division, then a three-variant epilogue, each unrolled 128 times).
+__device__ __noinline__ float epilogue_rows(const Params& p, const float* __restrict__ stg, float* __restrict__ Cg,
+                                            const float* __restrict__ Dg, const float* __restrict__ csg, int mrow0, int nbase,
+                                            float mu, float oscale, int lane, float mx) {
+  const int col = (lane & 7) * 4;
+  const int n = nbase + col;
+  const bool fast_c = nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0;
+  const bool fast_d = fast_c && Dg && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(Dg) & 15) == 0;
+  float cs[4] = {1.f, 1.f, 1.f, 1.f};
+  if (csg) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (n + e < p.N) {
+        float sc = csg[n + e];
+        if (p.colscale_sq) sc = sc * sc;
+        cs[e] = p.colscale_recip ? 1.0f / sc : sc;
+      }
+  }
+  if (p.negate) {
+#pragma unroll
+    for (int e = 0; e < 4; ++e) cs[e] = -cs[e];
+  }
+#pragma unroll 1
+  for (int i = 0; i < 8; ++i) {
+    const int row = 4 * i + (lane >> 3);
+    const int mm = mrow0 + row;
+    if (mm >= p.M) continue;
+    const float4 a4 = *reinterpret_cast<const float4*>(stg + row * kEpiLd + col);
+    float x[4] = {a4.x * cs[0], a4.y * cs[1], a4.z * cs[2], a4.w * cs[3]};
+    if (p.triu) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (mm > n + e) x[e] = 0.f;
+    }
+    if (Dg) {
+      float d[4] = {0.f, 0.f, 0.f, 0.f};
+      if (fast_d) {
+        const float4 d4 = *reinterpret_cast<const float4*>(Dg + (size_t)mm * p.ldd + n);
+        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e)
+          if (n + e < p.N) d[e] = Dg[(size_t)mm * p.ldd + n + e];
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = d[e] - mu * x[e];
+    }
+    if (p.rho_mode) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[e] = x[e] * oscale;
+    }
+#pragma unroll
+    for (int e = 0; e < 4; ++e)
+      if (n + e < p.N) mx = fmaxf(mx, fabsf(x[e]));
+    if (fast_c) {
+      *reinterpret_cast<float4*>(Cg + (size_t)mm * p.ldc + n) = make_float4(x[0], x[1], x[2], x[3]);
+    } else {
+#pragma unroll
+      for (int e = 0; e < 4; ++e)
+        if (n + e < p.N) Cg[(size_t)mm * p.ldc + n + e] = x[e];
+    }
+  }
+  return mx;
+}
+
 template <int BN, bool TS>
 __global__ void __launch_bounds__(kThreads, 1)
     gemm_tc_kernel(const __grid_constant__ GroupMaps maps, const __grid_constant__ Params p) {
@@ -306,6 +383,7 @@ __global__ void __launch_bounds__(kThreads, 1)
   uint64_t* tmem_full = bars + 3 * C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256);   // 4 warps x [32][kEpiLd]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
 
@@ -570,7 +648,6 @@ __global__ void __launch_bounds__(kThreads, 1)
       const int grp = tile / tiles_per, lt = tile % tiles_per;
       const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM, n0 = tn * BN;
-      const int m = m0 + q * 32 + lane;
       if (!tile_in_pattern<BN>(p, m0, n0)) continue;
       if (grp != mx_grp) { flush_max(); mx_grp = grp; }
       float* const Cg = p.C[grp];
@@ -610,38 +687,20 @@ __global__ void __launch_bounds__(kThreads, 1)
         __syncwarp();
         if (lane == 0) mbar_arrive(&tmem_empty[a]);
       }
-      if (m < p.M && !(p.debug & 8)) {
+      // ---- final epilogue: registers -> shared-memory stage of this warp -> global (see epilogue_rows) ----------
+      if (!(p.debug & 8)) {
+        float* const stg = epi_stage + q * (32 * kEpiLd);
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int nbase = n0 + c * 32;
-          if (nbase >= p.N) continue;
-          float* crow = Cg + (size_t)m * p.ldc + nbase;
-          const float* drow = Dg ? Dg + (size_t)m * p.ldd + nbase : nullptr;
-          float v[32];
+          if (nbase < p.N) {                                            // uniform over the warp
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            float x = racc[c * 32 + j];
-            if (p.negate) x = -x;
-            if (csg && n < p.N) {
-              float sc = csg[n];
-              if (p.colscale_sq) sc = sc * sc;
-              x = p.colscale_recip ? x * (1.0f / sc) : x * sc;
-            }
-            if (p.triu && m > n) x = 0.f;
-            if (drow && n < p.N) x = drow[j] - mu * x;
-            if (p.rho_mode) x = x * oscale;
-            if (n < p.N) mx = fmaxf(mx, fabsf(x));
-            v[j] = x;
-          }
-          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < p.N) crow[j] = v[j];
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(stg + lane * kEpiLd + 4 * j4) =
+                  make_float4(racc[c * 32 + 4 * j4], racc[c * 32 + 4 * j4 + 1], racc[c * 32 + 4 * j4 + 2], racc[c * 32 + 4 * j4 + 3]);
+            __syncwarp();
+            mx = epilogue_rows(p, stg, Cg, Dg, csg, m0 + q * 32, nbase, mu, oscale, lane, mx);
+            __syncwarp();                                               // stage free for the next chunk
           }
         }
       }
@@ -701,7 +760,8 @@ struct Cfg2 {
   static constexpr int kATmemCol0 = kAccCols;
   static constexpr int kTmemCols = 512;
   static_assert(kAccCols + kStages * 2 * BK <= 512, "TMEM budget");
-  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr size_t kSmemBytes = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ +
+                                       4 * 32 * kEpiLd * 4 /*epilogue transposition stages*/;
 };
 
 __device__ __forceinline__ uint32_t cluster_ctarank() {
@@ -792,6 +852,7 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
   uint64_t* tmem_full = bars + 3 * C::kStages;   // [2]
   uint64_t* tmem_empty = tmem_full + 2;          // [2]         (used in the leader)
   uint32_t* tmem_ptr = reinterpret_cast<uint32_t*>(tmem_empty + 2);
+  float* epi_stage = reinterpret_cast<float*>(smem + (size_t)C::kStages * C::kStageBytes + 256);   // 4 warps x [32][kEpiLd]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const uint32_t rank = cluster_ctarank();       // 0 = leader
@@ -1036,7 +1097,6 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
       const int grp = tile / tiles_per, lt = tile % tiles_per;
       const int tm = lt / p.tiles_n, tn = lt % p.tiles_n;
       const int m0 = tm * BM2, n0 = tn * BN;
-      const int m = m0 + (int)rank * BM + q * 32 + lane;
       if (!tile_in_pattern<BN>(p, m0, n0)) continue;
       if (grp != mx_grp) { flush_max(); mx_grp = grp; }
       float* const Cg = p.C[grp];
@@ -1079,38 +1139,19 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
           else mbar_arrive_remote(&tmem_empty[a], 0);
         }
       }
-      if (m < p.M && !(p.debug & 8)) {
+      if (!(p.debug & 8)) {
+        float* const stg = epi_stage + q * (32 * kEpiLd);
 #pragma unroll
         for (int c = 0; c < BN / 32; ++c) {
           const int nbase = n0 + c * 32;
-          if (nbase >= p.N) continue;
-          float* crow = Cg + (size_t)m * p.ldc + nbase;
-          const float* drow = Dg ? Dg + (size_t)m * p.ldd + nbase : nullptr;
-          float v[32];
+          if (nbase < p.N) {
 #pragma unroll
-          for (int j = 0; j < 32; ++j) {
-            const int n = nbase + j;
-            float x = racc[c * 32 + j];
-            if (p.negate) x = -x;
-            if (csg && n < p.N) {
-              float sc = csg[n];
-              if (p.colscale_sq) sc = sc * sc;
-              x = p.colscale_recip ? x * (1.0f / sc) : x * sc;
-            }
-            if (p.triu && m > n) x = 0.f;
-            if (drow && n < p.N) x = drow[j] - mu * x;
-            if (p.rho_mode) x = x * oscale;
-            if (n < p.N) mx = fmaxf(mx, fabsf(x));
-            v[j] = x;
-          }
-          if (nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0) {
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              reinterpret_cast<float4*>(crow)[j] = make_float4(v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          } else {
-#pragma unroll
-            for (int j = 0; j < 32; ++j)
-              if (nbase + j < p.N) crow[j] = v[j];
+            for (int j4 = 0; j4 < 8; ++j4)
+              *reinterpret_cast<float4*>(stg + lane * kEpiLd + 4 * j4) =
+                  make_float4(racc[c * 32 + 4 * j4], racc[c * 32 + 4 * j4 + 1], racc[c * 32 + 4 * j4 + 2], racc[c * 32 + 4 * j4 + 3]);
+            __syncwarp();
+            mx = epilogue_rows(p, stg, Cg, Dg, csg, m0 + (int)rank * BM + q * 32, nbase, mu, oscale, lane, mx);
+            __syncwarp();
           }
         }
       }
@@ -1203,6 +1244,7 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   p.tiles_n = (g.N + BN - 1) / BN;
   p.count = count;
   p.debug = ctx->opt_tc_debug;
+  p.epi = ctx->opt_tc_epi;
   p.pair_b = g.pair_b; p.pair_kind = g.pair_kind; p.negate = g.negate ? 1 : 0;
   p.rho_mode = g.rho ? g.rho_mode : 0;
   double work = 0.0;

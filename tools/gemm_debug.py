@@ -101,8 +101,9 @@ if __name__ == "__main__":
         # epilogue's global stores (debug bit 8; results wrong)
         ctx.set_option("tc_pair", 0)
         M = N = 4096
-        for dbg in (0, 8):
+        for dbg, epi in ((0, 2), (8, 2)):
             ctx.set_option("tc_debug", dbg)
+            ctx.set_option("tc_epi", epi)
             for K in (128, 256, 512, 1024, 2048, 4096, 8192):
                 A = torch.randn(M, K, device="cuda"); B = torch.randn(N, K, device="cuda"); Cm = torch.empty(M, N, device="cuda")
                 args = (ctx.handle, 2, M, N, K, C.c_void_p(A.data_ptr()), K, 0, C.c_void_p(B.data_ptr()), K, 1,
@@ -115,8 +116,9 @@ if __name__ == "__main__":
                     check(ctx.lib.psgd_gemm(*args))
                 e1.record(); torch.cuda.synchronize()
                 ms = e0.elapsed_time(e1) / 50
-                print(f"debug={dbg} K={K:5d}: {ms * 1e3:8.1f} us  {2 * M * N * K / ms / 1e9:6.1f} TF  per-tile(7 tiles/CTA) {ms * 1e3 / 7:6.1f} us", flush=True)
+                print(f"debug={dbg} epi={epi} K={K:5d}: {ms * 1e3:8.1f} us  {2 * M * N * K / ms / 1e9:6.1f} TF  per-tile(7 tiles/CTA) {ms * 1e3 / 7:6.1f} us", flush=True)
         ctx.set_option("tc_debug", 0)
+        ctx.set_option("tc_epi", 2)
     elif which == "pairablate":
         # where does the pair kernel's time go?  (results are wrong with debug bits set)
         M = N = K = 4096
