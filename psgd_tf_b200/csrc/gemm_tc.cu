@@ -302,16 +302,22 @@ __host__ __device__ __forceinline__ void k_range(const Params& p, int prod, int 
 // products ran at 130 instead of 190 TFLOP/s).  The chunk is therefore turned through a padded shared-memory stage of the
 // warp (kEpiLd), and this routine walks it by ROW SEGMENT: 8 lanes x 16 bytes = one complete 128-byte line of a row, four
 // rows per step, so C is written -- and D of  C = D - mu acc  read -- in whole lines, and the column scale / triu mask /
-// max|.| ride along.  A rolled loop in a function of its own on purpose: the unrolled row-wise epilogue was 1.5k
+// max|.| ride along.  A compact function of its own on purpose: the unrolled row-wise epilogue was 1.5k
 // instructions per copy, and this kernel's throughput drops by 25 % when its hot code outgrows the instruction cache
 // (measured twice: an IEEE division, then a three-variant epilogue, each unrolled 128 times).
+// HAS_D = false: a rolled loop (compact: it is the hot path of most launches).  HAS_D = true (C = D - mu acc: Q' = Q - mu
+// grad Q and the in-place updates of the triangular solves): unrolled, with the eight D rows of the chunk loaded up front
+// -- taken one per iteration of a rolled loop, each waited out its own DRAM latency and those products ran at 80-90
+// TFLOP/s against 170+ for the same shapes without D; unrolling the common path instead cost it 20 % (code size, and a
+// 64-register save at every call), so the two are separate functions.
+template <bool HAS_D>
 __device__ __noinline__ float epilogue_rows(const Params& p, const float* __restrict__ stg, float* __restrict__ Cg,
                                             const float* __restrict__ Dg, const float* __restrict__ csg, int mrow0, int nbase,
                                             float mu, float oscale, int lane, float mx) {
   const int col = (lane & 7) * 4;
   const int n = nbase + col;
   const bool fast_c = nbase + 32 <= p.N && (p.ldc & 3) == 0 && (reinterpret_cast<uintptr_t>(Cg) & 15) == 0;
-  const bool fast_d = fast_c && Dg && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(Dg) & 15) == 0;
+  const bool fast_d = HAS_D && fast_c && (p.ldd & 3) == 0 && (reinterpret_cast<uintptr_t>(Dg) & 15) == 0;
   float cs[4] = {1.f, 1.f, 1.f, 1.f};
   if (csg) {
 #pragma unroll
@@ -326,11 +332,10 @@ __device__ __noinline__ float epilogue_rows(const Params& p, const float* __rest
 #pragma unroll
     for (int e = 0; e < 4; ++e) cs[e] = -cs[e];
   }
-#pragma unroll 1
-  for (int i = 0; i < 8; ++i) {
+  auto one_row = [&](int i, const float4& dpre) {
     const int row = 4 * i + (lane >> 3);
     const int mm = mrow0 + row;
-    if (mm >= p.M) continue;
+    if (mm >= p.M) return;
     const float4 a4 = *reinterpret_cast<const float4*>(stg + row * kEpiLd + col);
     float x[4] = {a4.x * cs[0], a4.y * cs[1], a4.z * cs[2], a4.w * cs[3]};
     if (p.triu) {
@@ -338,15 +343,11 @@ __device__ __noinline__ float epilogue_rows(const Params& p, const float* __rest
       for (int e = 0; e < 4; ++e)
         if (mm > n + e) x[e] = 0.f;
     }
-    if (Dg) {
-      float d[4] = {0.f, 0.f, 0.f, 0.f};
-      if (fast_d) {
-        const float4 d4 = *reinterpret_cast<const float4*>(Dg + (size_t)mm * p.ldd + n);
-        d[0] = d4.x; d[1] = d4.y; d[2] = d4.z; d[3] = d4.w;
-      } else {
+    if (HAS_D) {
+      float d[4] = {dpre.x, dpre.y, dpre.z, dpre.w};
+      if (!fast_d) {
 #pragma unroll
-        for (int e = 0; e < 4; ++e)
-          if (n + e < p.N) d[e] = Dg[(size_t)mm * p.ldd + n + e];
+        for (int e = 0; e < 4; ++e) d[e] = (n + e < p.N) ? Dg[(size_t)mm * p.ldd + n + e] : 0.f;
       }
 #pragma unroll
       for (int e = 0; e < 4; ++e) x[e] = d[e] - mu * x[e];
@@ -365,6 +366,20 @@ __device__ __noinline__ float epilogue_rows(const Params& p, const float* __rest
       for (int e = 0; e < 4; ++e)
         if (n + e < p.N) Cg[(size_t)mm * p.ldc + n + e] = x[e];
     }
+  };
+  if constexpr (HAS_D) {
+    float4 dreg[8];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int mm = mrow0 + 4 * i + (lane >> 3);
+      dreg[i] = (fast_d && mm < p.M) ? *reinterpret_cast<const float4*>(Dg + (size_t)mm * p.ldd + n) : make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) one_row(i, dreg[i]);
+  } else {
+    const float4 zero = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 1
+    for (int i = 0; i < 8; ++i) one_row(i, zero);
   }
   return mx;
 }
@@ -699,7 +714,8 @@ __global__ void __launch_bounds__(kThreads, 1)
               *reinterpret_cast<float4*>(stg + lane * kEpiLd + 4 * j4) =
                   make_float4(racc[c * 32 + 4 * j4], racc[c * 32 + 4 * j4 + 1], racc[c * 32 + 4 * j4 + 2], racc[c * 32 + 4 * j4 + 3]);
             __syncwarp();
-            mx = epilogue_rows(p, stg, Cg, Dg, csg, m0 + q * 32, nbase, mu, oscale, lane, mx);
+            mx = Dg ? epilogue_rows<true>(p, stg, Cg, Dg, csg, m0 + q * 32, nbase, mu, oscale, lane, mx)
+                    : epilogue_rows<false>(p, stg, Cg, Dg, csg, m0 + q * 32, nbase, mu, oscale, lane, mx);
             __syncwarp();                                               // stage free for the next chunk
           }
         }
@@ -1150,7 +1166,8 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(kThreads, 1)
               *reinterpret_cast<float4*>(stg + lane * kEpiLd + 4 * j4) =
                   make_float4(racc[c * 32 + 4 * j4], racc[c * 32 + 4 * j4 + 1], racc[c * 32 + 4 * j4 + 2], racc[c * 32 + 4 * j4 + 3]);
             __syncwarp();
-            mx = epilogue_rows(p, stg, Cg, Dg, csg, m0 + (int)rank * BM + q * 32, nbase, mu, oscale, lane, mx);
+            mx = Dg ? epilogue_rows<true>(p, stg, Cg, Dg, csg, m0 + (int)rank * BM + q * 32, nbase, mu, oscale, lane, mx)
+                    : epilogue_rows<false>(p, stg, Cg, Dg, csg, m0 + (int)rank * BM + q * 32, nbase, mu, oscale, lane, mx);
             __syncwarp();
           }
         }
