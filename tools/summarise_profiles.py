@@ -139,7 +139,7 @@ def main():
     for which in ("uvd", "kron"):
         launches(tag, which)
     allrows = []
-    for name in ("uvd_full", "kron_full_head", "kron_full_tail", "gemm4096", "splu_full", "ns_full"):
+    for name in ("uvd_full", "kron_full_head", "kron_full_tail", "kron_full", "gemm4096", "splu_full", "ns_full"):
         allrows += full_rows(tag, name)
     if allrows:
         keys = ["capture", "kernel", "time_us", "dram_read_MB", "dram_write_MB", "dram_pct", "sm_pct", "tensor_pipe_pct",
@@ -147,7 +147,7 @@ def main():
         with open(os.path.join(DST, f"{tag}_ncu_full_summary.csv"), "w", newline="") as fh:
             fh.write("# ncu --set full --clock-control none --import-source on (tools/profile_gpu.sh); one row per captured launch.\n"
                      "# uvd_full: the sweeps of one UVd update+apply at N=1e8, r=10 (r01: five sweeps of the two-call form; later tags: the three sweeps of the fused call).  kron_full_head/tail: launches 0-1 and the\n"
-                     "# last 8 GEMM launches of one Kron step (6 layers per grouped launch).  gemm4096: one dense 4096^3 product.\n")
+                     "# last 8 GEMM launches of one Kron step (6 layers per grouped launch); kron_full (r02 on): ALL tcgen05 GEMM launches of one step, in launch order.  gemm4096: one dense 4096^3 product.\n")
             w = csv.DictWriter(fh, fieldnames=keys, extrasaction="ignore")
             w.writeheader()
             for d in allrows:
@@ -175,7 +175,7 @@ def main():
         json.dump({"source": f"profiles/{tag}_ncu_full_summary.csv (dram__bytes_read.sum + dram__bytes_write.sum per launch; "
                              "kernels not re-captured under this tag keep the previous capture's figure)",
                    "bytes_per_launch": traffic}, open(os.path.join(DST, f"{tag}_traffic.json"), "w"), indent=1)
-    hs = "".join(hotspots(tag, n) for n in ("uvd_full", "uvd_map", "kron_full_tail", "gemm4096", "gemm4096_ts", "splu_full", "ns_full"))
+    hs = "".join(hotspots(tag, n) for n in ("uvd_full", "uvd_map", "kron_full_tail", "kron_full", "gemm4096", "gemm4096_ts", "splu_full", "ns_full"))
     if hs:
         open(os.path.join(DST, f"{tag}_hotspots.txt"), "w").write(
             "# ncu --page source (per-instruction warp-state sampling) of the dominant kernels; -lineinfo builds.\n" + hs)
