@@ -83,6 +83,7 @@ struct Params {
   int pair_b, pair_kind;    // block-pair mode (triangular block-inverse doubling): only tiles with (m0/b even, n0/b == m0/b + 1)
                             // exist; K range = the n-block (kind 1) or the m-block (kind 2)
   int negate;               // C = -(acc)
+  int d_tri;                // D is an upper-triangular factor that the b_full flag of the problem vouches for
   int epi;                  // epilogue stores: 2 staged through shared memory (full lines), 1 256-bit stores, 0 row-wise 128-bit
   int debug;                // timing ablations only (wrong results): 1 skip the B split, 2 skip the A split, 4 skip the MMAs,
                             // 8 skip the epilogue's global stores
@@ -666,7 +667,7 @@ __global__ void __launch_bounds__(kThreads, 1)
       if (!tile_in_pattern<BN>(p, m0, n0)) continue;
       if (grp != mx_grp) { flush_max(); mx_grp = grp; }
       float* const Cg = p.C[grp];
-      const float* const Dg = p.D[grp];
+      const float* Dg = p.D[grp];
       const float* const csg = p.colscale[grp];
       float mu = 0.f;
       if (Dg) mu = p.mu_max[grp] ? p.step / (*p.mu_max[grp] + p.tiny) : 1.0f;
@@ -680,6 +681,20 @@ __global__ void __launch_bounds__(kThreads, 1)
           int kb0, kb1;
           k_range<BN>(p, prod, m0, n0, kb0, kb1, s_full[grp]);
           total_kb += kb1 - kb0;
+        }
+      }
+      // Q' = Q - mu (grad Q): D IS the triangular factor Q.  Below the diagonal both the product and D are zero (the
+      // run-time scan vouches for Q), so those tiles -- 48 % of the launch -- are written as zeros without reading D.
+      if (Dg && p.d_tri && !(s_full[grp] & 2) && total_kb == 0 && m0 >= n0 + BN) Dg = nullptr;
+      if (Dg) {
+        // start this tile's 64 KB of D towards L2 now; the chunk drains below take the tile's whole MMA time, so the
+        // coalesced loads of the final epilogue find it there instead of waiting out DRAM once per 32-column chunk
+        const int pm = m0 + q * 32 + lane;
+        if (pm < p.M) {
+          const float* drow = Dg + (size_t)pm * p.ldd + n0;
+#pragma unroll
+          for (int c = 0; c < BN / 32; ++c)
+            if (n0 + c * 32 < p.N) asm volatile("prefetch.global.L2 [%0];" ::"l"(drow + c * 32));
         }
       }
       float racc[BN];
@@ -1234,7 +1249,8 @@ static bool same_shape(const la::Gemm& x, const la::Gemm& y) {
          x.tiny == y.tiny && x.colscale_recip == y.colscale_recip && x.colscale_sq == y.colscale_sq &&
          (x.D != nullptr) == (y.D != nullptr) && (x.K2 > 0) == (y.K2 > 0) && x.pair_b == y.pair_b &&
          x.pair_kind == y.pair_kind && x.negate == y.negate && x.rho_mode == y.rho_mode &&
-         (x.a_full != nullptr) == (y.a_full != nullptr) && (x.b_full != nullptr) == (y.b_full != nullptr);
+         (x.a_full != nullptr) == (y.a_full != nullptr) && (x.b_full != nullptr) == (y.b_full != nullptr) &&
+         x.d_tri == y.d_tri;
 }
 
 // gs[0..count): identical shapes/flags, count <= kMaxGroup
@@ -1262,6 +1278,7 @@ static int launch_impl(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   p.count = count;
   p.debug = ctx->opt_tc_debug;
   p.epi = ctx->opt_tc_epi;
+  p.d_tri = (g.d_tri && g.b_full && g.b_tri == 1 && g.a_tri == 1) ? 1 : 0;
   p.pair_b = g.pair_b; p.pair_kind = g.pair_kind; p.negate = g.negate ? 1 : 0;
   p.rho_mode = g.rho ? g.rho_mode : 0;
   double work = 0.0;

@@ -579,6 +579,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       la::Gemm g = mk(M, M, M, L.grad1, M, false, L.Qlb, M, false, L.Ql_out, M);
       g.D = L.Qlb; g.ldd = M; g.mu_max = &L.sc->max1; g.step = step; g.tiny = tiny;
       if (dd) { g.rho = &L.sc->rho; g.rho_mode = 1; }                    // Ql / rho                      psgd.py:169
+      g.d_tri = true;
       gs.push_back(g);
     }
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromL));
@@ -606,6 +607,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       la::Gemm g = mk(N, N, N, L.grad2, N, false, L.Qrb, N, false, L.Qr_out, N);
       g.D = L.Qrb; g.ldd = N; g.mu_max = &L.sc->max2; g.step = step; g.tiny = tiny;
       if (dd) { g.rho = &L.sc->rho; g.rho_mode = 2; }                    // rho * Qr                      psgd.py:170
+      g.d_tri = true;
       gs.push_back(g);
     }
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromR));

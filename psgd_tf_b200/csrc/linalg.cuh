@@ -25,6 +25,8 @@ struct Gemm {
   bool triu = false;              // zero the strictly lower triangle (tf.linalg.band_part(., 0, -1))
   float* maxabs = nullptr;        // atomic max of |C| (after masking) -- must be zeroed by the caller
   const float* D = nullptr; int ldd = 0;     // if set: C = D - mu * acc
+  bool d_tri = false;             // D is the same upper-triangular factor as op(B) (Q' = Q - mu grad Q): with b_full's
+                                  // blessing, tiles below the diagonal are zeros and D is not read for them
   const float* mu_max = nullptr;  // mu = step / (*mu_max + tiny)
   float step = 0.f, tiny = 0.f;
   // K-range hints (product 0 only; the engines may skip structurally-zero K blocks, never required for correctness

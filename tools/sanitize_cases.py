@@ -49,6 +49,15 @@ def kron_tc(mode):
     ctx.set_option("tc_mode", 1); ctx.set_option("gemm_path", 0); ctx.set_option("trsm_base", 1024)
 
 
+def kron_pair():
+    ctx.set_option("tc_pair", 1)
+    try:
+        kron_tc(1)
+        errs["kron_pair"] = errs.pop("kron_tc_mode1")
+    finally:
+        ctx.set_option("tc_pair", 0)
+
+
 def kron_stream():
     for kl, kr, M, N in (("norm", "scale", 300, 257), ("norm", "dense", 200, 64), ("scale", "dense", 130, 48)):
         c = cases.kron_case(9, kl, kr, M, N)
@@ -84,7 +93,7 @@ def vec():
     errs["diag"] = cases.rel_err(q.cpu().numpy(), O.update_precond_diag(x["a"], x["v"], x["h"], 0.01))
 
 
-jobs = {"uvd_tma": lambda: uvd(0), "uvd_direct": lambda: uvd(1), "kron_ts": lambda: kron_tc(1), "kron_ss": lambda: kron_tc(0),
+jobs = {"uvd_tma": lambda: uvd(0), "uvd_direct": lambda: uvd(1), "kron_ts": lambda: kron_tc(1), "kron_ss": lambda: kron_tc(0), "kron_pair": kron_pair,
         "kron_stream": kron_stream, "splu": splu, "vec": vec}
 for name, fn in jobs.items():
     if which in ("all", name):
