@@ -140,6 +140,33 @@ def load_traffic():
         return {}, None
 
 
+def bind_to_gpu_numa(local):
+    """Pin this rank's host threads (and, by first touch, the pinned staging buffers it allocates afterwards) to the NUMA
+    node its GPU hangs off.  torchrun starts every rank unbound; round 1's end-to-end numbers at 8 GPUs were host-copy
+    bound with all ranks' staging memory on node 0.  Best effort: returns a short description or None."""
+    try:
+        bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
+                             capture_output=True, text=True, timeout=20).stdout.strip().lower()
+        if not bus:
+            return None
+        dom, rest = bus.split(":", 1)
+        path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        node = int(open(path).read().strip())
+        if node < 0:
+            return None
+        cpus = []
+        for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
+            lo, _, hi = part.partition("-")
+            cpus.extend(range(int(lo), int(hi or lo) + 1))
+        allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
+        if not allowed:
+            return None
+        os.sched_setaffinity(0, allowed)
+        return f"numa node {node} ({len(allowed)} cpus)"
+    except Exception:
+        return None
+
+
 def dist_env():
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -485,7 +512,7 @@ def run_uvd(args, rank, world, local):
                  call_form=("update_precond_and_grad_UVd (psgd_uvd_update_apply): update + apply of psgd.py:732-748 "
                             "fused into three sweeps" if form == "fused" else
                             "update_precond_UVd_math_ + precond_grad_UVd_math as two calls (" + args.uvd_form + ")"),
-                 cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs)),
+                 cross_gpu_exchange=exchange, cuda_graphs=bool(use_graphs), host_binding=getattr(args, "numa_binding", None)),
         parity=parity,
         step_ms_median=round(float(np.median(per_step)), 4), step_ms_max=round(max(per_step), 4), remeasured=remeasured,
         roofline=roofline, kernels=kernels, kernels_measured=kernels_from, separate_calls=separate, cpu_baseline=cpu, e2e=e2e,
@@ -746,6 +773,7 @@ def main():
     if world > 1:
         import torch.distributed as dist
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        args.numa_binding = bind_to_gpu_numa(local)
         torch.cuda.set_device(local)
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     try:
