@@ -73,6 +73,7 @@ struct psgd_ctx {
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
+  int opt_tc_splitk = 1;     // tcgen05 GEMM: split K over grouped problems when the output has too few tiles to fill the GPU
   int opt_tc_epi = 2;        // tcgen05 GEMM epilogue stores: 2 = staged through shared memory (full 128-byte lines), 1 = 256-bit, 0 = 128-bit per row
   int opt_tc_pair_sel = -1;  // debugging aid: >= 0 = only the sel-th tensor-core GEMM launch since the option was set uses the pair kernel
   int tc_launch_seq = 0;
@@ -96,6 +97,17 @@ struct psgd_ctx {
 
   // Ensure at least `bytes` of workspace; contents are NOT preserved across growth.
   int reserve(size_t bytes);
+  // Second scratch area for the GEMM engine's own needs (split-K partials), one per stream slot so that groups running
+  // concurrently on the side streams do not share it.  slot 0 = the context's stream, k = side[k - 1].
+  void* aux[kSideStreams + 1] = {};
+  size_t aux_bytes[kSideStreams + 1] = {};
+  cudaStream_t main_stream_of_call = nullptr;      // the caller's stream while a batched call has forked (else nullptr)
+  int stream_slot() const {
+    for (int k = 0; k < kSideStreams; ++k)
+      if (side[k] && stream == side[k]) return k + 1;
+    return 0;
+  }
+  int reserve_aux(int slot, size_t bytes, float** out);
 };
 
 namespace psgd {

@@ -28,6 +28,18 @@ int psgd_ctx::reserve(size_t bytes) {
   return PSGD_OK;
 }
 
+int psgd_ctx::reserve_aux(int slot, size_t bytes, float** out) {
+  if (bytes > aux_bytes[slot]) {
+    if (aux[slot]) PSGD_CUDA_CHECK(cudaFreeAsync(aux[slot], stream));
+    aux[slot] = nullptr;
+    aux_bytes[slot] = 0;
+    PSGD_CUDA_CHECK(cudaMallocAsync(&aux[slot], bytes + bytes / 8, stream));
+    aux_bytes[slot] = bytes + bytes / 8;
+  }
+  *out = static_cast<float*>(aux[slot]);
+  return PSGD_OK;
+}
+
 extern "C" int psgd_abi_version(void) { return PSGD_B200_ABI_VERSION; }
 
 extern "C" const char* psgd_last_error(void) { return psgd::g_error; }
@@ -69,6 +81,8 @@ extern "C" int psgd_destroy(psgd_ctx* ctx) {
     cudaStreamSynchronize(ctx->stream);
     cudaFree(ctx->ws);
   }
+  for (int k = 0; k <= psgd_ctx::kSideStreams; ++k)
+    if (ctx->aux[k]) { cudaDeviceSynchronize(); cudaFree(ctx->aux[k]); }
   for (int k = 0; k < psgd_ctx::kSideStreams; ++k) {
     if (ctx->side[k]) cudaStreamDestroy(ctx->side[k]);
     if (ctx->ev_side[k]) cudaEventDestroy(ctx->ev_side[k]);
@@ -112,6 +126,7 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "uvd_mid") == 0) { ctx->opt_uvd_mid = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "comm_timeout_ms") == 0) { ctx->opt_comm_timeout_ms = value > 0 ? (int)value : 0; return PSGD_OK; }
   if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }
+  if (strcmp(key, "tc_splitk") == 0) { ctx->opt_tc_splitk = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_epi") == 0) { ctx->opt_tc_epi = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return PSGD_OK; }
   if (strcmp(key, "tc_pair_sel") == 0) { ctx->opt_tc_pair_sel = (int)value; ctx->tc_launch_seq = 0; return PSGD_OK; }
   if (strcmp(key, "tc_pair") == 0) { ctx->opt_tc_pair = value ? 1 : 0; return PSGD_OK; }

@@ -1441,11 +1441,138 @@ static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count) {
   return ctx->opt_tc_mode ? launch_impl<BN, true>(ctx, gs, count) : launch_impl<BN, false>(ctx, gs, count);
 }
 
+// ---------------------------------------------------------------------------------------------
+// split-K: a product with a small output and a long contraction (the 256 x 256 Gram differences of the NMT embedding
+// layers have K = 9414 / 4935: three 128 x 128 tiles, i.e. three SMs, walking 590 K blocks each).  The K range is cut
+// into S parts that run as S grouped problems of ONE launch into S partial outputs; a streaming kernel then sums the
+// parts in fixed order (deterministic) and applies the epilogue.  Only for problems without triangular K-range hints.
+// ---------------------------------------------------------------------------------------------
+struct FinishArgs {
+  const float* part;        // [nparts][M * N]
+  int nparts, nneg;         // the LAST nneg parts are subtracted (second product)
+  int M, N, ldc, ldd;
+  float* C;
+  const float* D;
+  const float* mu_max;
+  float step, tiny;
+  float* maxabs;
+  const float* colscale;
+  int colscale_recip, colscale_sq, triu, negate;
+  const float* rho;
+  int rho_mode;
+};
+
+__global__ void __launch_bounds__(256) splitk_finish_kernel(const FinishArgs a) {
+  const size_t MN = (size_t)a.M * a.N;
+  float mu = 0.f;
+  if (a.D) mu = a.mu_max ? a.step / (*a.mu_max + a.tiny) : 1.0f;
+  const float oscale = a.rho_mode == 1 ? 1.0f / *a.rho : (a.rho_mode == 2 ? *a.rho : 1.0f);
+  float mx = 0.f;
+  for (size_t e = (size_t)blockIdx.x * blockDim.x + threadIdx.x; e < MN; e += (size_t)gridDim.x * blockDim.x) {
+    const int m = (int)(e / a.N), n = (int)(e % a.N);
+    float x = 0.f;
+    for (int s = 0; s < a.nparts - a.nneg; ++s) x += a.part[(size_t)s * MN + e];
+    float y = 0.f;
+    for (int s = a.nparts - a.nneg; s < a.nparts; ++s) y += a.part[(size_t)s * MN + e];
+    x = x - y;
+    if (a.negate) x = -x;
+    if (a.colscale) {
+      float sc = a.colscale[n];
+      if (a.colscale_sq) sc = sc * sc;
+      x = a.colscale_recip ? x * (1.0f / sc) : x * sc;
+    }
+    if (a.triu && m > n) x = 0.f;
+    if (a.D) x = a.D[(size_t)m * a.ldd + n] - mu * x;
+    if (a.rho_mode) x = x * oscale;
+    mx = fmaxf(mx, fabsf(x));
+    a.C[(size_t)m * a.ldc + n] = x;
+  }
+  if (a.maxabs) {
+    mx = warp_max(mx);
+    if ((threadIdx.x & 31) == 0 && mx > 0.f) atomic_max_nonneg(a.maxabs, mx);
+  }
+}
+
+// Number of parts for problem g run `count` times in one group (0 = no split).
+static int splitk_parts(const psgd_ctx* ctx, const la::Gemm& g, int count) {
+  if (!ctx->opt_tc_splitk || g.a_tri || g.b_tri || g.pair_b || g.a_full || g.b_full) return 0;
+  const int tiles = ((g.M + BM - 1) / BM) * ((g.N + 127) / 128) * count;
+  const int kmax = g.K > g.K2 ? g.K : g.K2;
+  if (tiles * 3 > ctx->num_sms || kmax < 2048) return 0;
+  const int nprod = g.K2 > 0 ? 2 : 1;
+  int S = ctx->num_sms / tiles;
+  if (S > kmax / 512) S = kmax / 512;
+  if (S > kMaxGroup / (count * nprod)) S = kMaxGroup / (count * nprod);
+  return S >= 2 ? S : 0;
+}
+
+template <int BN>
+static int launch(psgd_ctx* ctx, const la::Gemm* gs, int count);
+
+static int gemm_splitk(psgd_ctx* ctx, const la::Gemm* gs, int count, int S) {
+  const la::Gemm& g0 = gs[0];
+  const size_t MN = (size_t)g0.M * g0.N;
+  const int nprod = g0.K2 > 0 ? 2 : 1;
+  // parts per problem: S for each product (a part is dropped when its K range is empty)
+  std::vector<la::Gemm> subs;
+  std::vector<int> nparts(count, 0), nneg(count, 0);
+  const int slot = ctx->stream_slot();
+  float* scratch = nullptr;
+  PSGD_RETURN_IF(ctx->reserve_aux(slot, (size_t)count * S * nprod * MN * sizeof(float), &scratch));
+  for (int prod = 0; prod < nprod; ++prod) {
+    const int K = prod ? g0.K2 : g0.K;
+    const int Kc = ((K + S - 1) / S + BK - 1) / BK * BK;
+    // full-size parts first (one grouped launch), the remainder part (shorter K) as a launch of its own
+    for (int pass = 0; pass < 2; ++pass) {
+      subs.clear();
+      for (int i = 0; i < count; ++i) {
+        const la::Gemm& g = gs[i];
+        const float* A = prod ? g.A2 : g.A;
+        const float* B = prod ? g.B2 : g.B;
+        const int lda = prod ? g.lda2 : g.lda, ldb = prod ? g.ldb2 : g.ldb;
+        const bool ta = prod ? g.ta2 : g.ta, tb = prod ? g.tb2 : g.tb;
+        for (int s = 0; s < S; ++s) {
+          const int k0 = s * Kc;
+          if (k0 >= K) break;
+          const int Ks = K - k0 < Kc ? K - k0 : Kc;
+          if ((Ks == Kc) != (pass == 0)) continue;
+          la::Gemm q;
+          q.M = g.M; q.N = g.N; q.K = Ks;
+          q.A = ta ? A + (size_t)k0 * lda : A + k0; q.lda = lda; q.ta = ta;
+          q.B = tb ? B + k0 : B + (size_t)k0 * ldb; q.ldb = ldb; q.tb = tb;
+          // part index within problem i: product 0 parts first, then product 1 parts (subtracted by the finish kernel)
+          const int pidx = nparts[i]++;
+          if (prod) nneg[i]++;
+          q.C = scratch + ((size_t)i * S * nprod + pidx) * MN; q.ldc = g.N;
+          subs.push_back(q);
+        }
+      }
+      for (size_t b = 0; b < subs.size(); b += kMaxGroup) {
+        const int cnt = (int)std::min<size_t>(kMaxGroup, subs.size() - b);
+        PSGD_RETURN_IF(launch<128>(ctx, subs.data() + b, cnt));
+      }
+    }
+  }
+  for (int i = 0; i < count; ++i) {
+    const la::Gemm& g = gs[i];
+    FinishArgs a{};
+    a.part = scratch + (size_t)i * S * nprod * MN; a.nparts = nparts[i]; a.nneg = nneg[i];
+    a.M = g.M; a.N = g.N; a.ldc = g.ldc; a.ldd = g.ldd; a.C = g.C; a.D = g.D; a.mu_max = g.mu_max; a.step = g.step; a.tiny = g.tiny;
+    a.maxabs = g.maxabs; a.colscale = g.colscale; a.colscale_recip = g.colscale_recip; a.colscale_sq = g.colscale_sq;
+    a.triu = g.triu ? 1 : 0; a.negate = g.negate ? 1 : 0; a.rho = g.rho; a.rho_mode = g.rho ? g.rho_mode : 0;
+    int blocks = (int)((MN + 255) / 256);
+    if (blocks > ctx->num_sms * 8) blocks = ctx->num_sms * 8;
+    splitk_finish_kernel<<<blocks, 256, 0, ctx->stream>>>(a);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
+
 int gemm_tc(psgd_ctx* ctx, const la::Gemm& g) {
   PSGD_REQUIRE(gemm_tc_supported(g), PSGD_ERR_BAD_SHAPE,
                "tcgen05 GEMM needs 16-byte aligned operands with leading dimensions that are multiples of 4");
   if (g.M <= 0 || g.N <= 0) return PSGD_OK;
-  return launch<128>(ctx, &g, 1);
+  return gemm_many(ctx, &g, 1, true);
 }
 
 static bool want_tc(const psgd_ctx* ctx, const la::Gemm& g) {
@@ -1466,7 +1593,11 @@ int gemm_many(psgd_ctx* ctx, const la::Gemm* gs, int count, bool force_tc) {
     }
     int j = i + 1;
     while (j < count && j - i < kMaxGroup && same_shape(gs[i], gs[j]) && gemm_tc_supported(gs[j])) ++j;
-    if (gs[i].M > 0 && gs[i].N > 0) PSGD_RETURN_IF(launch<128>(ctx, gs + i, j - i));
+    if (gs[i].M > 0 && gs[i].N > 0) {
+      const int S = splitk_parts(ctx, gs[i], j - i);
+      if (S) PSGD_RETURN_IF(gemm_splitk(ctx, gs + i, j - i, S));
+      else PSGD_RETURN_IF(launch<128>(ctx, gs + i, j - i));
+    }
     i = j;
   }
   return PSGD_OK;

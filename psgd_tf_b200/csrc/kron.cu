@@ -778,6 +778,22 @@ static int check_layer(const char* what, int kl, int kr, int64_t M, int64_t N) {
 
 struct Key { int kl, kr, M, N; };
 
+// q[count .. padded) = tiny positive: padding entries of a scaling factor that never win the balance maximum
+__global__ void pad_scale_kernel(float* q, int count, int padded) {
+  const int i = count + threadIdx.x;
+  if (i < padded) q[i] = 1e-30f;
+}
+static int round_up4(int x) { return (x + 3) / 4 * 4; }
+// A mirrored (scaling, dense) layer whose long side is not a multiple of 4 (the NMT embeddings: [9414, 256], [4935, 256])
+// would leave the tensor-core engine for the SIMT one: its transposed copies have the long side as leading dimension,
+// and TMA needs 16-byte multiples.  The library owns those copies, so it pads them (and the scaling factor) with up to 3
+// zero columns: they add nothing to A A^T - Bt Bt^T, their column statistics are zero, and the padded factor entries
+// (1e-30) neither win the balance maximum nor produce anything but zeros.
+static bool pad_mirrored(const psgd_ctx* ctx, int kl, int kr, int M, int N) {
+  return kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE && (M & 3) != 0 && N >= 256 && (N & 3) == 0 && M >= 256 &&
+         ctx->opt_gemm_path != 1;
+}
+
 static int ensure_side_streams(psgd_ctx* ctx) {
   if (ctx->ev_fork) return PSGD_OK;
   for (int k = 0; k < psgd_ctx::kSideStreams; ++k) {
@@ -803,7 +819,8 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
                    "kron update: null device pointer in layer %d", i);
     else
       PSGD_REQUIRE(q.Ql && q.Qr && q.G && q.out, PSGD_ERR_BAD_POINTER, "kron apply: null device pointer in layer %d", i);
-    const size_t f = is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N) : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N;
+    const size_t f = is_update ? update_ws_floats(q.kind_l, q.kind_r, round_up4((int)q.M), round_up4((int)q.N))
+                               : apply_ws_floats(round_up4((int)q.M), round_up4((int)q.N)) + 2 * (size_t)round_up4((int)q.M) * round_up4((int)q.N);
     need += f * sizeof(float) + 48 * 256;
   }
   // Bound the workspace: process the list in slices whose scratch fits the budget (large uniform stacks still group)
@@ -814,8 +831,9 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     int end = begin;
     while (end < count) {
       const psgd_kron_layer& q = in[end];
-      const size_t f = (is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N)
-                                  : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N) * sizeof(float) + 48 * 256;
+      const int Mr = round_up4((int)q.M), Nr = round_up4((int)q.N);        // mirrored layers may be padded to multiples of 4
+      const size_t f = (is_update ? update_ws_floats(q.kind_l, q.kind_r, Mr, Nr)
+                                  : apply_ws_floats(Mr, Nr) + 2 * (size_t)Mr * Nr) * sizeof(float) + 48 * 256;
       if (end > begin && bytes + f > budget) break;
       bytes += f;
       ++end;
@@ -825,6 +843,9 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     std::vector<Layer> Ls(end - begin);
     std::vector<Key> keys(end - begin);
     std::vector<float*> untranspose_src(end - begin, nullptr);
+    std::vector<int> untranspose_ld(end - begin, 0);
+    struct CopyBack { const float* src; float* dst; size_t count; };
+    std::vector<CopyBack> copy_back;
     for (int i = begin; i < end; ++i) {
       const psgd_kron_layer& q = in[i];
       Layer& L = Ls[i - begin];
@@ -835,23 +856,45 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
         L.Ql_out = q.Ql_out; L.Qr_out = q.Qr_out; L.out = q.out;
       } else {
         // canonical kernel on (Qr, Ql, X^T); results come back swapped / transposed
-        const size_t MN = (size_t)M * N;
+        const bool pad = pad_mirrored(ctx, kl, kr, M, N);
+        const int Mp = pad ? round_up4(M) : M;             // leading dimension (= canonical N) of the transposed copies
+        const size_t MN = (size_t)Mp * N;
         L.Ql = q.Qr; L.Qr = q.Ql; L.Ql_out = q.Qr_out; L.Qr_out = q.Ql_out;
+        if (pad) {
+          float* qpad = c.take<float>(Mp);
+          PSGD_CUDA_CHECK(cudaMemcpyAsync(qpad, q.Ql, (size_t)M * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+          pad_scale_kernel<<<1, 4, 0, ctx->stream>>>(qpad, M, Mp);
+          PSGD_LAUNCH_CHECK(ctx);
+          L.Qr = qpad;
+          if (is_update) {
+            float* qout = c.take<float>(Mp);
+            L.Qr_out = qout;
+            copy_back.push_back(CopyBack{qout, q.Ql_out, (size_t)M});
+          }
+        }
+        auto transposed = [&](const float* src, float** out) -> int {
+          float* t = c.take<float>(MN);
+          if (pad)      // zero the pad columns [M, Mp) of every row
+            PSGD_CUDA_CHECK(cudaMemset2DAsync(t + M, (size_t)Mp * sizeof(float), 0, (size_t)(Mp - M) * sizeof(float), N, ctx->stream));
+          PSGD_RETURN_IF(la::transpose(ctx, src, N, t, Mp, M, N));
+          *out = t;
+          return PSGD_OK;
+        };
         if (is_update) {
-          float* dXt = c.take<float>(MN);
-          float* dGt = c.take<float>(MN);
-          PSGD_RETURN_IF(la::transpose(ctx, q.dX, N, dXt, M, M, N));
-          PSGD_RETURN_IF(la::transpose(ctx, q.dG, N, dGt, M, M, N));
+          float *dXt = nullptr, *dGt = nullptr;
+          PSGD_RETURN_IF(transposed(q.dX, &dXt));
+          PSGD_RETURN_IF(transposed(q.dG, &dGt));
           L.dX = dXt; L.dG = dGt;
         } else {
-          float* Gt = c.take<float>(MN);
+          float* Gt = nullptr;
+          PSGD_RETURN_IF(transposed(q.G, &Gt));
           float* Ot = c.take<float>(MN);
-          PSGD_RETURN_IF(la::transpose(ctx, q.G, N, Gt, M, M, N));
           L.G = Gt; L.out = Ot;
           untranspose_src[i - begin] = Ot;
+          untranspose_ld[i - begin] = Mp;
         }
         std::swap(kl, kr);
-        std::swap(M, N);
+        M = N; N = Mp;                                     // canonical shape: [dense side, (padded) long side]
       }
       keys[i - begin] = Key{kl, kr, M, N};
       if (is_update) carve_update(ctx, c, L, kl, kr, M, N);
@@ -915,7 +958,9 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     if (!is_update)
       for (int i = begin; i < end; ++i)
         if (untranspose_src[i - begin])   // canonical result is [N,M]; give the caller [M,N]
-          PSGD_RETURN_IF(la::transpose(ctx, untranspose_src[i - begin], (int)in[i].M, in[i].out, (int)in[i].N, (int)in[i].N, (int)in[i].M));
+          PSGD_RETURN_IF(la::transpose(ctx, untranspose_src[i - begin], untranspose_ld[i - begin], in[i].out, (int)in[i].N, (int)in[i].N, (int)in[i].M));
+    for (const CopyBack& cb : copy_back)                  // padded scaling-factor results: the real entries go to the caller
+      PSGD_CUDA_CHECK(cudaMemcpyAsync(cb.dst, cb.src, cb.count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
     begin = end;
   }
   (void)need;

@@ -40,7 +40,7 @@ def gemm(psgd, engine, A, B, ta, tb, triu=0, a_tri=0, b_tri=0):
 
 @pytest.mark.parametrize("ta,tb", [(0, 1), (1, 1), (0, 0), (1, 0)])
 @pytest.mark.parametrize("M,N,K", [(256, 256, 256), (384, 640, 320), (1000, 520, 264), (128, 128, 32), (132, 36, 40),
-                                   (2048, 1024, 4096)])
+                                   (2048, 1024, 4096), (256, 256, 9416), (384, 128, 5000)])     # the last two: split-K
 def test_gemm_tc_matches_float64(psgd, M, N, K, ta, tb):
     g = torch.Generator(device="cuda").manual_seed(M + N + K)
     A = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g)
@@ -71,6 +71,26 @@ def test_gemm_tc_triangular_hints_and_mask(psgd):
     assert ((out3.double() - ref3).norm() / ref3.norm()).item() < 2e-6
 
 
+@pytest.mark.parametrize("pair", [0, 1])
+def test_gemm_tc_pair_kernel_and_splitk_options(psgd, pair):
+    """The optional cta_group::2 kernel (tc_pair) and the split-K path against float64, with the options toggled."""
+    ctx = psgd.get_context()
+    g = torch.Generator(device="cuda").manual_seed(99 + pair)
+    ctx.set_option("tc_pair", pair)
+    try:
+        for (M, N, K, ta, tb) in ((512, 384, 1024, 0, 1), (300, 260, 520, 1, 0), (256, 256, 9416, 0, 1)):
+            A = torch.randn((K, M) if ta else (M, K), device="cuda", generator=g)
+            B = torch.randn((N, K) if tb else (K, N), device="cuda", generator=g)
+            ref = (A.double().t() if ta else A.double()) @ (B.double().t() if tb else B.double())
+            for splitk in (1, 0):
+                ctx.set_option("tc_splitk", splitk)
+                out = gemm(psgd, 2, A, B, ta, tb)
+                assert ((out.double() - ref).norm() / ref.norm()).item() < 2e-6, (M, N, K, pair, splitk)
+    finally:
+        ctx.set_option("tc_pair", 0)
+        ctx.set_option("tc_splitk", 1)
+
+
 def test_gemm_tc_rejects_unaligned_leading_dimension(psgd):
     A = torch.randn(256, 258, device="cuda")
     B = torch.randn(258, 256, device="cuda")
@@ -83,7 +103,9 @@ def test_gemm_tc_rejects_unaligned_leading_dimension(psgd):
 
 KRON_TC = [("dense", "dense", 512, 512), ("dense", "dense", 384, 640), ("dense", "dense", 640, 384),
            ("norm", "dense", 700, 512), ("dense", "scale", 512, 900), ("scale", "dense", 1000, 256),
-           ("dense", "norm", 512, 600), ("dense", "dense", 1024, 1024)]
+           ("dense", "norm", 512, 600), ("dense", "dense", 1024, 1024),
+           # NMT embedding shapes (mirrored, long side not a multiple of 4: padded transposed copies + split-K Gram products)
+           ("scale", "dense", 1001, 256), ("scale", "dense", 4935, 256), ("scale", "dense", 9414, 256)]
 
 
 @pytest.mark.parametrize("kl,kr,M,N", KRON_TC)
