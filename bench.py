@@ -148,23 +148,25 @@ def bind_to_gpu_numa(local):
         bus = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(local)],
                              capture_output=True, text=True, timeout=20).stdout.strip().lower()
         if not bus:
-            return None
+            return "unbound: nvidia-smi gave no PCI bus id"
         dom, rest = bus.split(":", 1)
         path = f"/sys/bus/pci/devices/{dom[-4:]}:{rest}/numa_node"
+        if not os.path.exists(path):
+            return f"unbound: {path} does not exist"
         node = int(open(path).read().strip())
         if node < 0:
-            return None
+            return "unbound: the platform reports numa_node = -1 for the GPU (no NUMA information in this container)"
         cpus = []
         for part in open(f"/sys/devices/system/node/node{node}/cpulist").read().strip().split(","):
             lo, _, hi = part.partition("-")
             cpus.extend(range(int(lo), int(hi or lo) + 1))
         allowed = sorted(set(cpus) & set(os.sched_getaffinity(0)))
         if not allowed:
-            return None
+            return f"unbound: no allowed cpu on numa node {node}"
         os.sched_setaffinity(0, allowed)
         return f"numa node {node} ({len(allowed)} cpus)"
-    except Exception:
-        return None
+    except Exception as e:
+        return f"unbound: {type(e).__name__}: {e}"
 
 
 def dist_env():

@@ -75,13 +75,16 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         pool.append((dX, dG, G))
     shapes = [(n, n)] * L
 
+    gbuf = partition.KronGatherBuffer(shapes, owned, rank, dev) if world > 1 else None
+
     def step(i, Ql, Qr, dX, dG, G):
         new = psgd.update_precond_kron_batched(Ql, Qr, dX, dG, 0.01)
         Ql2, Qr2 = [a for a, _ in new], [b for _, b in new]
-        pre = psgd.precond_grad_kron_batched(Ql2, Qr2, G)
-        if world > 1:
-            pre = partition.all_gather_layers(pre, owned, shapes, rank)
-        return Ql2, Qr2, pre
+        if gbuf is None:
+            return Ql2, Qr2, psgd.precond_grad_kron_batched(Ql2, Qr2, G)
+        # the apply writes straight into this rank's slice of the gather buffer; ONE in-place all-gather follows
+        psgd.precond_grad_kron_batched(Ql2, Qr2, G, outs=gbuf.local_outs())
+        return Ql2, Qr2, gbuf.gather()
 
     def barrier():
         if world > 1:

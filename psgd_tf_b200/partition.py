@@ -144,6 +144,38 @@ def kron_layer_cost(M: int, N: int, kind_l: int = 0, kind_r: int = 0) -> float:
     return c
 
 
+class KronGatherBuffer:
+    """In-place all-gather of a UNIFORM layer-sharded Kron stack (every layer the same shape, every rank the same number
+    of layers): one ``[world * per, M, N]`` buffer per rank; ``local_outs()`` are views of this rank's slice of it, to be
+    passed as ``outs=`` to :func:`psgd_tf_b200.precond_grad_kron_batched` so the apply's last product writes its result
+    where NCCL sends it from -- no ``torch.stack``, no staging copy -- and ``gather()`` is ONE in-place
+    ``all_gather_into_tensor`` (input = the rank's own slice of the output).  Two buffers alternate so that the result of
+    step t stays valid while step t+1 is being computed."""
+
+    def __init__(self, shapes, owned, rank: int, device, nbuf: int = 2):
+        if len({tuple(s) for s in shapes}) != 1 or len({len(o) for o in owned}) != 1:
+            raise ValueError("KronGatherBuffer: needs a uniform stack (use all_gather_layers for ragged ones)")
+        self.owned, self.rank, self.per = owned, rank, len(owned[0])
+        self.shape = tuple(shapes[0])
+        self.bufs = [torch.empty((len(owned) * self.per,) + self.shape, device=device, dtype=torch.float32) for _ in range(nbuf)]
+        self.cur = 0
+
+    def local_outs(self):
+        self.cur = (self.cur + 1) % len(self.bufs)
+        b = self.bufs[self.cur]
+        return [b[self.rank * self.per + j] for j in range(self.per)]
+
+    def gather(self, group=None):
+        import torch.distributed as dist
+        b = self.bufs[self.cur]
+        dist.all_gather_into_tensor(b, b[self.rank * self.per:(self.rank + 1) * self.per], group=group)
+        full = [None] * (len(self.owned) * self.per)
+        for k, layer_ids in enumerate(self.owned):
+            for j, li in enumerate(layer_ids):
+                full[li] = b[k * self.per + j]
+        return full
+
+
 def all_gather_layers(outs_local: Sequence[torch.Tensor], owned: List[List[int]], shapes: Sequence[Tuple[int, int]],
                       rank: int, group=None) -> List[torch.Tensor]:
     """All-gather of preconditioned gradients for a layer-sharded Kron stack: every rank ends up with every layer's

@@ -70,6 +70,13 @@ def cpu_protocol(rank, world):
     full = partition.all_gather_layers([torch.full((8, 8), float(i)) for i in owned_u[rank]], owned_u, uni, rank)
     for i, t in enumerate(full):
         assert torch.all(t == float(i))
+    gb = partition.KronGatherBuffer(uni, owned_u, rank, torch.device("cpu")) if len({len(o) for o in owned_u}) == 1 else None
+    for rep_ in range(3 if gb is not None else 0):          # two alternating buffers
+        for j, o in enumerate(gb.local_outs()):
+            o.fill_(float(owned_u[rank][j] + 10 * rep_))
+        full = gb.gather()
+        for i, t in enumerate(full):
+            assert torch.all(t == float(i + 10 * rep_))
     # ---- reduction protocol of the sharded UVd update (mirrors psgd_tf_b200/csrc/uvd.cu) ------------------------
     n, r = 1021, 4
     c = cases.uvd_case(42, n, r)
