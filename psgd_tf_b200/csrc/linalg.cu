@@ -13,18 +13,22 @@ struct GemmDev {
   Gemm g;
 };
 
-__device__ __forceinline__ void load_tiles(const float* __restrict__ A, int lda, bool ta, const float* __restrict__ B,
-                                           int ldb, bool tb, int M, int N, int K, int m0, int n0, int k0,
-                                           float (*As)[BM + PAD], float (*Bs)[BN + PAD], int tid) {
+// One K step of one product: this thread's 4 + 4 elements of the A and B tiles, global -> registers (fetch) and
+// registers -> shared memory (stash).  Kept apart so that the loads of step s+1 are in flight while step s is multiplied:
+// with the loads issued inside the loop body every K step of these latency-bound small products (LeNet5: 257 x 120 x 120)
+// waited out a global-memory round trip -- 16 us per launch, ncu -- and a layer's update is a chain of ~14 such launches.
+struct TileRegs {
+  float a[(BM * BK) / 256], b[(BN * BK) / 256];
+};
+__device__ __forceinline__ void fetch_tiles(const float* __restrict__ A, int lda, bool ta, const float* __restrict__ B, int ldb,
+                                            bool tb, int M, int N, int K, int m0, int n0, int k0, int tid, TileRegs& r) {
 #pragma unroll
   for (int e = 0; e < (BM * BK) / 256; ++e) {
     const int idx = tid + 256 * e;
     int m, k;
     if (ta) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
     const int gm = m0 + m, gk = k0 + k;
-    float v = 0.f;
-    if (gm < M && gk < K) v = ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk];
-    As[k][m] = v;
+    r.a[e] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
   }
 #pragma unroll
   for (int e = 0; e < (BN * BK) / 256; ++e) {
@@ -32,9 +36,24 @@ __device__ __forceinline__ void load_tiles(const float* __restrict__ A, int lda,
     int n, k;
     if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
     const int gn = n0 + n, gk = k0 + k;
-    float v = 0.f;
-    if (gn < N && gk < K) v = tb ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn];
-    Bs[k][n] = v;
+    r.b[e] = (gn < N && gk < K) ? (tb ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
+  }
+}
+__device__ __forceinline__ void stash_tiles(bool ta, bool tb, int tid, const TileRegs& r, float (*As)[BM + PAD],
+                                            float (*Bs)[BN + PAD]) {
+#pragma unroll
+  for (int e = 0; e < (BM * BK) / 256; ++e) {
+    const int idx = tid + 256 * e;
+    int m, k;
+    if (ta) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
+    As[k][m] = r.a[e];
+  }
+#pragma unroll
+  for (int e = 0; e < (BN * BK) / 256; ++e) {
+    const int idx = tid + 256 * e;
+    int n, k;
+    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+    Bs[k][n] = r.b[e];
   }
 }
 
@@ -58,28 +77,41 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
 
-  for (int pass = 0; pass < 2; ++pass) {
-    const float* A = pass ? g.A2 : g.A;
-    const float* B = pass ? g.B2 : g.B;
-    const int lda = pass ? g.lda2 : g.lda, ldb = pass ? g.ldb2 : g.ldb;
-    const bool ta = pass ? g.ta2 : g.ta, tb = pass ? g.tb2 : g.tb;
-    const int K = pass ? g.K2 : g.K;
-    const float sign = pass ? -1.f : 1.f;
-    if (K <= 0 || A == nullptr) continue;
-    for (int k0 = 0; k0 < K; k0 += BK) {
-      load_tiles(A, lda, ta, B, ldb, tb, g.M, g.N, K, m0, n0, k0, As, Bs, tid);
-      __syncthreads();
+  // the K steps of product 0, then those of the (subtracted) product 1, as ONE software-pipelined sequence
+  const int steps0 = (g.K > 0 && g.A) ? (g.K + BK - 1) / BK : 0;
+  const int steps1 = (g.K2 > 0 && g.A2) ? (g.K2 + BK - 1) / BK : 0;
+  const int steps = steps0 + steps1;
+  auto fetch = [&](int s, TileRegs& r) {
+    const bool p1 = s >= steps0;
+    const int k0 = (p1 ? s - steps0 : s) * BK;
+    if (p1) fetch_tiles(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.M, g.N, g.K2, m0, n0, k0, tid, r);
+    else fetch_tiles(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.M, g.N, g.K, m0, n0, k0, tid, r);
+  };
+  TileRegs cur, nxt;
+  if (steps > 0) {
+    fetch(0, cur);
+    stash_tiles(steps0 > 0 ? g.ta : g.ta2, steps0 > 0 ? g.tb : g.tb2, tid, cur, As, Bs);
+  }
+  __syncthreads();
+  for (int s = 0; s < steps; ++s) {
+    const bool more = s + 1 < steps;
+    if (more) fetch(s + 1, nxt);                       // in flight during the multiply below
+    const float sign = s >= steps0 ? -1.f : 1.f;
 #pragma unroll
-      for (int k = 0; k < BK; ++k) {
-        const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-        const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-        const float a[4] = {sign * a4.x, sign * a4.y, sign * a4.z, sign * a4.w};
-        const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int k = 0; k < BK; ++k) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
+      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
+      const float a[4] = {sign * a4.x, sign * a4.y, sign * a4.z, sign * a4.w};
+      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-        for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < 4; ++i)
 #pragma unroll
-          for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
-      }
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) {
+      const bool p1 = s + 1 >= steps0;
+      stash_tiles(p1 ? g.ta2 : g.ta, p1 ? g.tb2 : g.tb, tid, nxt, As, Bs);
       __syncthreads();
     }
   }
