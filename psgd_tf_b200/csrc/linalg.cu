@@ -5,92 +5,94 @@ namespace psgd {
 namespace la {
 
 // ---------------------------------------------------------------------------------------------
-// GEMM: 64x64x16 tiles, 256 threads, 4x4 outputs per thread, fp32 FMA accumulation
+// GEMM: T x T x 16 tiles (T = 64: 4x4 outputs per thread; T = 32: 2x2), 256 threads, fp32 FMA accumulation.
+// The 32-wide tile is for problems whose 64-wide grid would leave most SMs idle (LeNet5 layers: 257 x 120 is 10 CTAs of
+// 64 x 64, each a chain of K/16 barrier-separated steps -- 16 us per launch; 36 CTAs of 32 x 32 do a quarter of the work
+// per step).  Same accumulation order per output element in both, so results do not depend on the tile choice.
 // ---------------------------------------------------------------------------------------------
-constexpr int BM = 64, BN = 64, BK = 16, PAD = 4;
+constexpr int BK = 16, PAD = 4;
 
-struct GemmDev {
-  Gemm g;
-};
-
-// One K step of one product: this thread's 4 + 4 elements of the A and B tiles, global -> registers (fetch) and
-// registers -> shared memory (stash).  Kept apart so that the loads of step s+1 are in flight while step s is multiplied:
-// with the loads issued inside the loop body every K step of these latency-bound small products (LeNet5: 257 x 120 x 120)
-// waited out a global-memory round trip -- 16 us per launch, ncu -- and a layer's update is a chain of ~14 such launches.
+// One K step of one product: this thread's elements of the A and B tiles, global -> registers (fetch) and registers ->
+// shared memory (stash).  Kept apart so that the loads of step s+1 are in flight while step s is multiplied.
+template <int T>
 struct TileRegs {
-  float a[(BM * BK) / 256], b[(BN * BK) / 256];
+  float a[(T * BK) / 256], b[(T * BK) / 256];
 };
+template <int T>
 __device__ __forceinline__ void fetch_tiles(const float* __restrict__ A, int lda, bool ta, const float* __restrict__ B, int ldb,
-                                            bool tb, int M, int N, int K, int m0, int n0, int k0, int tid, TileRegs& r) {
+                                            bool tb, int M, int N, int K, int m0, int n0, int k0, int tid, TileRegs<T>& r) {
 #pragma unroll
-  for (int e = 0; e < (BM * BK) / 256; ++e) {
+  for (int e = 0; e < (T * BK) / 256; ++e) {
     const int idx = tid + 256 * e;
     int m, k;
-    if (ta) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
+    if (ta) { m = idx % T; k = idx / T; } else { k = idx % BK; m = idx / BK; }
     const int gm = m0 + m, gk = k0 + k;
     r.a[e] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
   }
 #pragma unroll
-  for (int e = 0; e < (BN * BK) / 256; ++e) {
+  for (int e = 0; e < (T * BK) / 256; ++e) {
     const int idx = tid + 256 * e;
     int n, k;
-    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % T; k = idx / T; }
     const int gn = n0 + n, gk = k0 + k;
     r.b[e] = (gn < N && gk < K) ? (tb ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
   }
 }
-__device__ __forceinline__ void stash_tiles(bool ta, bool tb, int tid, const TileRegs& r, float (*As)[BM + PAD],
-                                            float (*Bs)[BN + PAD]) {
+template <int T>
+__device__ __forceinline__ void stash_tiles(bool ta, bool tb, int tid, const TileRegs<T>& r, float (*As)[T + PAD],
+                                            float (*Bs)[T + PAD]) {
 #pragma unroll
-  for (int e = 0; e < (BM * BK) / 256; ++e) {
+  for (int e = 0; e < (T * BK) / 256; ++e) {
     const int idx = tid + 256 * e;
     int m, k;
-    if (ta) { m = idx % BM; k = idx / BM; } else { k = idx % BK; m = idx / BK; }
+    if (ta) { m = idx % T; k = idx / T; } else { k = idx % BK; m = idx / BK; }
     As[k][m] = r.a[e];
   }
 #pragma unroll
-  for (int e = 0; e < (BN * BK) / 256; ++e) {
+  for (int e = 0; e < (T * BK) / 256; ++e) {
     const int idx = tid + 256 * e;
     int n, k;
-    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % BN; k = idx / BN; }
+    if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % T; k = idx / T; }
     Bs[k][n] = r.b[e];
   }
 }
 
+template <int T>
 __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
-  __shared__ __align__(16) float As[BK][BM + PAD];
-  __shared__ __align__(16) float Bs[BK][BN + PAD];
+  constexpr int R = T / 16;                         // outputs per thread along each dimension
+  __shared__ __align__(16) float As[BK][T + PAD];
+  __shared__ __align__(16) float Bs[BK][T + PAD];
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
-  const int m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
-  if (g.triu && m0 >= n0 + BN) {
+  const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
+  if (g.triu && m0 >= n0 + T) {
     // tile entirely below the diagonal: result is zero after masking
-    for (int e = tid; e < BM * BN; e += 256) {
-      const int m = m0 + e / BN, n = n0 + e % BN;
+    for (int e = tid; e < T * T; e += 256) {
+      const int m = m0 + e / T, n = n0 + e % T;
       if (m < g.M && n < g.N) g.C[(size_t)m * g.ldc + n] = 0.f;
     }
     return;
   }
-  float acc[4][4];
+  float acc[R][R];
 #pragma unroll
-  for (int i = 0; i < 4; ++i)
+  for (int i = 0; i < R; ++i)
 #pragma unroll
-    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+    for (int j = 0; j < R; ++j) acc[i][j] = 0.f;
 
   // the K steps of product 0, then those of the (subtracted) product 1, as ONE software-pipelined sequence
   const int steps0 = (g.K > 0 && g.A) ? (g.K + BK - 1) / BK : 0;
   const int steps1 = (g.K2 > 0 && g.A2) ? (g.K2 + BK - 1) / BK : 0;
   const int steps = steps0 + steps1;
-  auto fetch = [&](int s, TileRegs& r) {
+  auto fetch = [&](int s, TileRegs<T>& r) {
     const bool p1 = s >= steps0;
     const int k0 = (p1 ? s - steps0 : s) * BK;
-    if (p1) fetch_tiles(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.M, g.N, g.K2, m0, n0, k0, tid, r);
-    else fetch_tiles(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.M, g.N, g.K, m0, n0, k0, tid, r);
+    if (p1) fetch_tiles<T>(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.M, g.N, g.K2, m0, n0, k0, tid, r);
+    else fetch_tiles<T>(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.M, g.N, g.K, m0, n0, k0, tid, r);
   };
-  TileRegs cur, nxt;
+  TileRegs<T> cur, nxt;
   if (steps > 0) {
     fetch(0, cur);
-    stash_tiles(steps0 > 0 ? g.ta : g.ta2, steps0 > 0 ? g.tb : g.tb2, tid, cur, As, Bs);
+    stash_tiles<T>(steps0 > 0 ? g.ta : g.ta2, steps0 > 0 ? g.tb : g.tb2, tid, cur, As, Bs);
   }
   __syncthreads();
   for (int s = 0; s < steps; ++s) {
@@ -99,19 +101,18 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
     const float sign = s >= steps0 ? -1.f : 1.f;
 #pragma unroll
     for (int k = 0; k < BK; ++k) {
-      const float4 a4 = *reinterpret_cast<const float4*>(&As[k][ty * 4]);
-      const float4 b4 = *reinterpret_cast<const float4*>(&Bs[k][tx * 4]);
-      const float a[4] = {sign * a4.x, sign * a4.y, sign * a4.z, sign * a4.w};
-      const float b[4] = {b4.x, b4.y, b4.z, b4.w};
+      float a[R], b[R];
 #pragma unroll
-      for (int i = 0; i < 4; ++i)
+      for (int i = 0; i < R; ++i) { a[i] = sign * As[k][ty * R + i]; b[i] = Bs[k][tx * R + i]; }
 #pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int i = 0; i < R; ++i)
+#pragma unroll
+        for (int j = 0; j < R; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
     }
     __syncthreads();
     if (more) {
       const bool p1 = s + 1 >= steps0;
-      stash_tiles(p1 ? g.ta2 : g.ta, p1 ? g.tb2 : g.tb, tid, nxt, As, Bs);
+      stash_tiles<T>(p1 ? g.ta2 : g.ta, p1 ? g.tb2 : g.tb, tid, nxt, As, Bs);
       __syncthreads();
     }
   }
@@ -120,12 +121,12 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
   if (g.D) mu = g.mu_max ? g.step / (*g.mu_max + g.tiny) : 1.0f;
   float mx = 0.f;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int m = m0 + ty * 4 + i;
+  for (int i = 0; i < R; ++i) {
+    const int m = m0 + ty * R + i;
     if (m >= g.M) continue;
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int n = n0 + tx * 4 + j;
+    for (int j = 0; j < R; ++j) {
+      const int n = n0 + tx * R + j;
       if (n >= g.N) continue;
       float v = acc[i][j];
       if (g.colscale) {
@@ -149,8 +150,14 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
 
 int gemm_simt(psgd_ctx* ctx, const Gemm& g) {
   if (g.M <= 0 || g.N <= 0) return PSGD_OK;
-  dim3 grid((g.N + BN - 1) / BN, (g.M + BM - 1) / BM);
-  gemm_simt_kernel<<<grid, 256, 0, ctx->stream>>>(g);
+  const int ctas64 = ((g.N + 63) / 64) * ((g.M + 63) / 64);
+  if (ctas64 * 2 <= ctx->num_sms) {
+    dim3 grid((g.N + 31) / 32, (g.M + 31) / 32);
+    gemm_simt_kernel<32><<<grid, 256, 0, ctx->stream>>>(g);
+  } else {
+    dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
+    gemm_simt_kernel<64><<<grid, 256, 0, ctx->stream>>>(g);
+  }
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -176,14 +183,27 @@ __global__ void __launch_bounds__(256) trsm_left_block_kernel(const float* __res
   for (int i0 = ib0; i0 < ib1; i0 += NB) {
     const int ib = min(NB, ib1 - i0);   // rows in this step
     float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr, lr+8, lr+16, lr+24 ; column lc
+    // tiles of the next k0 step are fetched into registers while the current one is multiplied (these solves are
+    // latency chains: one global round trip per 32 x 32 tile otherwise)
+    float qn[4], xn[4];
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int k = lr + 8 * e;
+        qn[e] = (i0 + lc < ib1) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;
+        xn[e] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
+      }
+    };
+    if (ib0 < i0) fetch(ib0);
     for (int k0 = ib0; k0 < i0; k0 += NB) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int k = lr + 8 * e;
-        Qs[k][lc] = (i0 + lc < ib1) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;
-        Xs[k][lc] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
+        Qs[k][lc] = qn[e];
+        Xs[k][lc] = xn[e];
       }
       __syncthreads();
+      if (k0 + NB < i0) fetch(k0 + NB);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const float x = Xs[k][lc];
@@ -202,14 +222,22 @@ __global__ void __launch_bounds__(256) trsm_left_block_kernel(const float* __res
       Xs[i][lc] = b;
     }
     __syncthreads();
-    if (tid < NB && c0 + tid < m) {
-      const int c = tid;
-      for (int i = 0; i < ib; ++i) {
-        float s = Xs[i][c];
-        for (int k = 0; k < i; ++k) s = fmaf(-Qs[k][i], Xs[k][c], s);
-        s = s / Qs[i][i];
-        Xs[i][c] = s;
-        X[(size_t)(i0 + i) * ldx + c0 + c] = s;
+    // Right-looking over the 32 rows with ALL 256 threads: row i is finished by the thread that owns it, one barrier,
+    // then every thread folds x_i into the rows it owns.  Same operations in the same order as the row-by-row loop it
+    // replaces (each b_j sees -q_kj x_k for k = 0, 1, ... with one fused rounding each), which one thread per column ran
+    // as a serial chain of ~500 dependent shared-memory round trips per block (124 us per solve at n = 257, ncu).
+    for (int i = 0; i < ib; ++i) {
+      if (lr == (i & 7)) {
+        const float x = Xs[i][lc] / Qs[i][i];
+        Xs[i][lc] = x;
+        if (c0 + lc < m) X[(size_t)(i0 + i) * ldx + c0 + lc] = x;
+      }
+      __syncthreads();
+      const float xi = Xs[i][lc];
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int j = lr + 8 * e;
+        if (j > i && j < ib) Xs[j][lc] = fmaf(-Qs[i][j], xi, Xs[j][lc]);
       }
     }
     __syncthreads();   // X rows of this step are visible to the next step's k-loop (same CTA)
@@ -230,14 +258,25 @@ __global__ void __launch_bounds__(256) trsm_right_block_kernel(const float* __re
   for (int j0 = jb0; j0 < jb1; j0 += NB) {
     const int jb = min(NB, jb1 - j0);
     float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr+8e, column lc
+    float qn[4], xn[4];                     // next k0 step's tiles, in flight during the multiply
+    auto fetch = [&](int k0) {
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const int r = lr + 8 * e;
+        qn[e] = (j0 + lc < jb1) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
+        xn[e] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
+      }
+    };
+    if (jb0 < j0) fetch(jb0);
     for (int k0 = jb0; k0 < j0; k0 += NB) {
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const int r = lr + 8 * e;
-        Qs[r][lc] = (j0 + lc < jb1) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
-        Xs[r][lc] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
+        Qs[r][lc] = qn[e];
+        Xs[r][lc] = xn[e];
       }
       __syncthreads();
+      if (k0 + NB < j0) fetch(k0 + NB);
 #pragma unroll
       for (int k = 0; k < NB; ++k) {
         const float q = Qs[k][lc];
@@ -255,14 +294,26 @@ __global__ void __launch_bounds__(256) trsm_right_block_kernel(const float* __re
       Xs[r][lc] = b;
     }
     __syncthreads();
-    if (tid < NB && r0 + tid < m) {
-      const int r = tid;
-      for (int j = 0; j < jb; ++j) {
-        float s = Xs[r][j];
-        for (int k = 0; k < j; ++k) s = fmaf(-Xs[r][k], Qs[k][j], s);
-        s = s / Qs[j][j];
-        Xs[r][j] = s;
-        X[(size_t)(r0 + r) * ldx + j0 + j] = s;
+    // right-looking over the 32 columns with all 256 threads (see trsm_left_block_kernel): column j is finished by the
+    // threads that own it, one barrier, then every thread folds it into its own columns; same operations, same order
+    for (int j = 0; j < jb; ++j) {
+      if (lc == j) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = lr + 8 * e;
+          const float x = Xs[r][j] / Qs[j][j];
+          Xs[r][j] = x;
+          if (r0 + r < m) X[(size_t)(r0 + r) * ldx + j0 + j] = x;
+        }
+      }
+      __syncthreads();
+      if (lc > j && lc < jb) {
+        const float q = Qs[j][lc];
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const int r = lr + 8 * e;
+          Xs[r][lc] = fmaf(-Xs[r][j], q, Xs[r][lc]);
+        }
       }
     }
     __syncthreads();
