@@ -107,6 +107,19 @@ def run_aux(peak_gbs: float, steps: int = 10):
     ms_a = _time(torch, lambda: psgd.precond_grad_dense(Q, gv), steps)
     rows.append(dict(path="dense apply", shape=[n, n], apply_ms=round(ms_a, 4), apply_GBps=round(8.0 * n * n / ms_a / 1e6, 1),
                      apply_frac=round(8.0 * n * n / ms_a / 1e6 / peak_gbs, 4), step_algorithmic_GB=round(8.0 * n * n / 1e9, 3)))
+    # dense update (psgd.py:26-44): a = Q dg, b = Q^-T dx (vector solve), Q - mu triu(a a^T - b b^T) Q (one n^3 product)
+    dxv = [torch.randn(n, device=dev, generator=g)]
+    dgv = [1.3 * dxv[0] + 0.1 * torch.randn(n, device=dev, generator=g)]
+    qs = [Q]
+
+    def dupd():
+        qs[0] = psgd.update_precond_dense(qs[0], dxv, dgv, 0.01)
+
+    ms_u = _time(torch, dupd, max(3, steps // 4))
+    assert torch.isfinite(qs[0]).all()
+    rows.append(dict(path="dense update", shape=[n, n], update_ms=round(ms_u, 3),
+                     update_TFLOPs_dense_count=round(2.0 * n ** 3 / ms_u / 1e9, 1)))
+    del dxv, dgv, qs
 
     # ---- sparse-LU preconditioner (psgd.py:396-524), n = 5e7, r = 10 ---------------------------------------------------
     del Q, gv

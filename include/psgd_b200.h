@@ -60,7 +60,9 @@ int64_t psgd_workspace_bytes(const psgd_ctx* ctx);
 /* Options.  "direct": streaming kernels 0 = TMA bulk-copy pipeline (default), 1 = direct global loads (debug
  * cross-check; same arithmetic).  "uvd_fused": psgd_uvd_update 1 = two sweeps + a pass over d, the rank-2 step's
  * coefficients taken from the Gram table (default), 0 = three sweeps with direct reductions over a, b (cross-check).
- * "profile": see below.  Others ("gemm_path", "tc_bn", "trsm_base", "assume_triangular", ...) tune the dense Kron engine. */
+ * "profile": see below.  "dense_scan": psgd_dense_update 1 = the O(n^2) column-scan form of Q - mu triu(a a^T - b b^T) Q
+ * (default), 0 = the reference's n^3 matrix product (cross-check).  Others ("gemm_path", "tc_bn", "trsm_base",
+ * "assume_triangular", ...) tune the dense Kron engine. */
 int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 
 /* Per-kernel device timing.  After psgd_set_option(ctx, "profile", 1) every large kernel launch is bracketed
@@ -83,6 +85,7 @@ int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value);
 #define PSGD_K_GEMM 10           /* one tcgen05 3xTF32 GEMM launch                            */
 #define PSGD_K_GEMM_SIMT 12      /* one SIMT fp32 GEMM launch                                 */
 #define PSGD_K_TRSM 11           /* one triangular-solve step                                 */
+#define PSGD_K_DENSE_SCAN 15     /* dense update: |grad| maximum + the two column-scan passes that write Q' (work = bytes) */
 int psgd_profile_read(psgd_ctx* ctx, int* ids, float* ms, double* work, int cap);
 
 /* Cross-rank reduction hook for the chunk-sharded (multi-GPU) streaming paths.  When set, the

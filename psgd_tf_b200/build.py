@@ -16,7 +16,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT_DIR = os.path.join(HERE, "_C")
 LIB_PATH = os.path.join(OUT_DIR, "libpsgd_b200.so")
-SOURCES = ["context.cu", "comm.cu", "uvd.cu", "elementwise.cu", "linalg.cu", "gemm_tc.cu", "kron_stream.cu", "kron.cu", "multi.cu", "splu.cu"]
+SOURCES = ["context.cu", "comm.cu", "uvd.cu", "elementwise.cu", "linalg.cu", "gemm_tc.cu", "kron_stream.cu", "kron.cu", "dense.cu", "multi.cu", "splu.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
     "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr",

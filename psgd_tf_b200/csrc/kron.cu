@@ -101,6 +101,18 @@ __global__ void __launch_bounds__(256) tri_scan_kernel(const __grid_constant__ P
   const int r1 = min(n, r0 + kScanRows);
   const bool vec = (n & 3) == 0 && (reinterpret_cast<uintptr_t>(Q) & 15u) == 0;
   int any = 0;
+  if (n <= 1024) {
+    // small factor: the chunk as ONE flat strided loop, so that its loads are independent and in flight together
+    // (a loop over rows is a chain of 32 short, latency-bound passes: 12 us at n = 257)
+    const int total = (r1 - r0) * n;
+#pragma unroll 4
+    for (int e = threadIdx.x; e < total; e += 256) {
+      const int i = r0 + e / n, j = e % n;
+      if (j < i) any |= (Q[(size_t)i * n + j] != 0.f);
+    }
+    if (__syncthreads_or(any) && threadIdx.x == 0) *flag = 1;
+    return;
+  }
   for (int i = max(r0, 1); i < r1; ++i) {
     const float* row = Q + (size_t)i * n;
     int j0 = 0;
@@ -392,7 +404,9 @@ static const int* flag_of(const Layer& L, int src) { return src == kFromL ? L.fl
 
 // Dense factors whose products may run on the tensor cores with triangular K-range hints get a run-time check.
 static bool wants_scan(const psgd_ctx* ctx, int kind, int n) {
-  return kind == PSGD_FACTOR_DENSE && ctx->opt_assume_tri && ctx->opt_gemm_path != 1 && (ctx->opt_gemm_path == 2 || n >= 256);
+  // (a factor whose order is not a multiple of 4 never reaches the tensor-core engine: gemm_tc_supported)
+  return kind == PSGD_FACTOR_DENSE && ctx->opt_assume_tri && ctx->opt_gemm_path != 1 && (n % 4) == 0 &&
+         (ctx->opt_gemm_path == 2 || n >= 256);
 }
 
 // flags of one group: zeroed, then set by tri_scan_kernel (one launch per kPrepBatch layers)
@@ -1008,54 +1022,4 @@ extern "C" int psgd_kron_apply_batched(psgd_ctx* ctx, const psgd_kron_layer* lay
   PSGD_REQUIRE(count >= 0 && (layers || count == 0), PSGD_ERR_BAD_POINTER, "kron batched apply: null layer list");
   PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
   return kron::run_layers(ctx, layers, count, false, 0.f, 0.f);
-}
-
-// ---------------------------------------------------------------------------------------------
-// dense full-matrix preconditioner                                      psgd.py:26-63
-// ---------------------------------------------------------------------------------------------
-extern "C" int psgd_dense_update(psgd_ctx* ctx, const float* Q, const float* dx, const float* dg, float* Q_out,
-                                 int64_t n64, float step, float tiny) {
-  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
-  PSGD_REQUIRE(n64 >= 1 && n64 < (1 << 20), PSGD_ERR_BAD_SHAPE, "dense update: n=%lld", (long long)n64);
-  PSGD_REQUIRE(Q && dx && dg && Q_out, PSGD_ERR_BAD_POINTER, "dense update: null device pointer");
-  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  const int n = (int)n64;
-  PSGD_RETURN_IF(ctx->reserve(((size_t)n * n + 4 * (size_t)n) * sizeof(float) + 16 * 256));
-  WsCarver c(ctx->ws);
-  kron::Scal* sc = c.take<kron::Scal>(1);
-  float* a = c.take<float>(n);
-  float* b = c.take<float>(n);
-  float* grad = c.take<float>((size_t)n * n);
-  std::vector<kron::Layer> one(1);                    // run-time check of the triangular hint on Q (see tri_scan_kernel)
-  one[0] = kron::Layer{};
-  one[0].Ql = Q; one[0].Qr = Q;
-  kron::carve_flags(ctx, c, one[0], PSGD_FACTOR_DENSE, -1, n, n);
-  PSGD_RETURN_IF(kron::scan_group(ctx, one, n, n));
-  PSGD_CUDA_CHECK(cudaMemsetAsync(sc, 0, sizeof(kron::Scal), ctx->stream));
-  PSGD_RETURN_IF(ks::row_dot(ctx, Q, n, dg, n, n, a));                        // a = Q dg          psgd.py:38
-  PSGD_RETURN_IF(la::trsm_left_upper_adjoint(ctx, Q, n, dx, 1, b, 1, n, 1));   // b = Q^-T dx       psgd.py:39
-  la::Gemm g2 = kron::mk(n, n, 1, a, 1, false, a, 1, true, grad, n);          // triu(a a^T - b b^T)   psgd.py:40
-  g2.K2 = 1; g2.A2 = b; g2.lda2 = 1; g2.B2 = b; g2.ldb2 = 1; g2.tb2 = true;
-  g2.triu = true; g2.maxabs = &sc->max1;
-  PSGD_RETURN_IF(la::gemm_simt(ctx, g2));
-  std::vector<la::Gemm> gs;                                                   // Q - step0 grad Q  psgd.py:41-42
-  la::Gemm g3 = kron::mk(n, n, n, grad, n, false, Q, n, false, Q_out, n);
-  g3.D = Q; g3.ldd = n; g3.mu_max = &sc->max1; g3.step = step; g3.tiny = tiny;
-  gs.push_back(g3);
-  return kron::gemm_all(ctx, gs, kron::kUpper, kron::kUpper, &one, 0, kron::kFromL);
-}
-
-extern "C" int psgd_dense_apply(psgd_ctx* ctx, const float* Q, const float* g, float* out, int64_t n64) {
-  PSGD_REQUIRE(ctx, PSGD_ERR_BAD_POINTER, "null context");
-  PSGD_REQUIRE(n64 >= 1 && n64 < (1 << 20), PSGD_ERR_BAD_SHAPE, "dense apply: n=%lld", (long long)n64);
-  PSGD_REQUIRE(Q && g && out, PSGD_ERR_BAD_POINTER, "dense apply: null device pointer");
-  PSGD_CUDA_CHECK(cudaSetDevice(ctx->device));
-  const int n = (int)n64;
-  // two bandwidth-bound GEMVs: Q is read exactly twice (8 n^2 bytes), coalesced both times
-  PSGD_RETURN_IF(ctx->reserve(((size_t)n + (size_t)ks::row_tiles(n) * n) * sizeof(float) + 2048));
-  WsCarver c(ctx->ws);
-  float* t = c.take<float>(n);
-  float* part = c.take<float>((size_t)ks::row_tiles(n) * n);
-  PSGD_RETURN_IF(ks::row_dot(ctx, Q, n, g, n, n, t));                        // t = Q g            psgd.py:55
-  return ks::col_wsum(ctx, 1, nullptr, t, Q, n, n, n, part, out);            // out = Q^T t
 }

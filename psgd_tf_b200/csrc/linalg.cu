@@ -1,73 +1,75 @@
 // SIMT fp32 engine of the device linear-algebra vocabulary (see linalg.cuh).
 #include "linalg.cuh"
+#include "kron_stream.cuh"
 
 namespace psgd {
 namespace la {
 
 // ---------------------------------------------------------------------------------------------
-// GEMM: T x T x 16 tiles (T = 64: 4x4 outputs per thread; T = 32: 2x2), 256 threads, fp32 FMA accumulation.
-// The 32-wide tile is for problems whose 64-wide grid would leave most SMs idle (LeNet5 layers: 257 x 120 is 10 CTAs of
-// 64 x 64, each a chain of K/16 barrier-separated steps -- 16 us per launch; 36 CTAs of 32 x 32 do a quarter of the work
-// per step).  Same accumulation order per output element in both, so results do not depend on the tile choice.
+// GEMM, general engine: 64 x 64 x 16 tiles, 4 x 4 outputs per thread, 256 threads, fp32 FMA accumulation in ascending K
+// order.  Problems whose 64-wide grid would leave most SMs idle go to gemm_small_kernel below.
 // ---------------------------------------------------------------------------------------------
-constexpr int BK = 16, PAD = 4;
+constexpr int PAD = 4;
 
 // One K step of one product: this thread's elements of the A and B tiles, global -> registers (fetch) and registers ->
 // shared memory (stash).  Kept apart so that the loads of step s+1 are in flight while step s is multiplied.
-template <int T>
+template <int T, int BK, int NT>
 struct TileRegs {
-  float a[(T * BK) / 256], b[(T * BK) / 256];
+  float a[(T * BK) / NT], b[(T * BK) / NT];
 };
-template <int T>
+template <int T, int BK, int NT>
 __device__ __forceinline__ void fetch_tiles(const float* __restrict__ A, int lda, bool ta, const float* __restrict__ B, int ldb,
-                                            bool tb, int M, int N, int K, int m0, int n0, int k0, int tid, TileRegs<T>& r) {
+                                            bool tb, int M, int N, int K, int m0, int n0, int k0, int tid,
+                                            TileRegs<T, BK, NT>& r) {
 #pragma unroll
-  for (int e = 0; e < (T * BK) / 256; ++e) {
-    const int idx = tid + 256 * e;
+  for (int e = 0; e < (T * BK) / NT; ++e) {
+    const int idx = tid + NT * e;
     int m, k;
     if (ta) { m = idx % T; k = idx / T; } else { k = idx % BK; m = idx / BK; }
     const int gm = m0 + m, gk = k0 + k;
     r.a[e] = (gm < M && gk < K) ? (ta ? A[(size_t)gk * lda + gm] : A[(size_t)gm * lda + gk]) : 0.f;
   }
 #pragma unroll
-  for (int e = 0; e < (T * BK) / 256; ++e) {
-    const int idx = tid + 256 * e;
+  for (int e = 0; e < (T * BK) / NT; ++e) {
+    const int idx = tid + NT * e;
     int n, k;
     if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % T; k = idx / T; }
     const int gn = n0 + n, gk = k0 + k;
     r.b[e] = (gn < N && gk < K) ? (tb ? B[(size_t)gn * ldb + gk] : B[(size_t)gk * ldb + gn]) : 0.f;
   }
 }
-template <int T>
-__device__ __forceinline__ void stash_tiles(bool ta, bool tb, int tid, const TileRegs<T>& r, float (*As)[T + PAD],
+template <int T, int BK, int NT>
+__device__ __forceinline__ void stash_tiles(bool ta, bool tb, int tid, const TileRegs<T, BK, NT>& r, float (*As)[T + PAD],
                                             float (*Bs)[T + PAD]) {
 #pragma unroll
-  for (int e = 0; e < (T * BK) / 256; ++e) {
-    const int idx = tid + 256 * e;
+  for (int e = 0; e < (T * BK) / NT; ++e) {
+    const int idx = tid + NT * e;
     int m, k;
     if (ta) { m = idx % T; k = idx / T; } else { k = idx % BK; m = idx / BK; }
     As[k][m] = r.a[e];
   }
 #pragma unroll
-  for (int e = 0; e < (T * BK) / 256; ++e) {
-    const int idx = tid + 256 * e;
+  for (int e = 0; e < (T * BK) / NT; ++e) {
+    const int idx = tid + NT * e;
     int n, k;
     if (tb) { k = idx % BK; n = idx / BK; } else { n = idx % T; k = idx / T; }
     Bs[k][n] = r.b[e];
   }
 }
 
-template <int T>
-__global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
+template <int T, int BK, int NT>
+__global__ void __launch_bounds__(NT) gemm_simt_kernel(Gemm g) {
   constexpr int R = T / 16;                         // outputs per thread along each dimension
-  __shared__ __align__(16) float As[BK][T + PAD];
-  __shared__ __align__(16) float Bs[BK][T + PAD];
+  static_assert(NT == 256, "16 x 16 threads");
+  __shared__ __align__(16) float tiles[2 * BK * (T + PAD)];
+  float (*As)[T + PAD] = reinterpret_cast<float (*)[T + PAD]>(tiles);
+  float (*Bs)[T + PAD] = reinterpret_cast<float (*)[T + PAD]>(tiles + BK * (T + PAD));
   const int tid = threadIdx.x;
   const int tx = tid % 16, ty = tid / 16;
   const int m0 = blockIdx.y * T, n0 = blockIdx.x * T;
   if (g.triu && m0 >= n0 + T) {
     // tile entirely below the diagonal: result is zero after masking
-    for (int e = tid; e < T * T; e += 256) {
+    for (int e = tid; e < T * T; e += NT) {
       const int m = m0 + e / T, n = n0 + e % T;
       if (m < g.M && n < g.N) g.C[(size_t)m * g.ldc + n] = 0.f;
     }
@@ -83,16 +85,16 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
   const int steps0 = (g.K > 0 && g.A) ? (g.K + BK - 1) / BK : 0;
   const int steps1 = (g.K2 > 0 && g.A2) ? (g.K2 + BK - 1) / BK : 0;
   const int steps = steps0 + steps1;
-  auto fetch = [&](int s, TileRegs<T>& r) {
+  auto fetch = [&](int s, TileRegs<T, BK, NT>& r) {
     const bool p1 = s >= steps0;
     const int k0 = (p1 ? s - steps0 : s) * BK;
-    if (p1) fetch_tiles<T>(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.M, g.N, g.K2, m0, n0, k0, tid, r);
-    else fetch_tiles<T>(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.M, g.N, g.K, m0, n0, k0, tid, r);
+    if (p1) fetch_tiles<T, BK, NT>(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.M, g.N, g.K2, m0, n0, k0, tid, r);
+    else fetch_tiles<T, BK, NT>(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.M, g.N, g.K, m0, n0, k0, tid, r);
   };
-  TileRegs<T> cur, nxt;
+  TileRegs<T, BK, NT> cur, nxt;
   if (steps > 0) {
     fetch(0, cur);
-    stash_tiles<T>(steps0 > 0 ? g.ta : g.ta2, steps0 > 0 ? g.tb : g.tb2, tid, cur, As, Bs);
+    stash_tiles<T, BK, NT>(steps0 > 0 ? g.ta : g.ta2, steps0 > 0 ? g.tb : g.tb2, tid, cur, As, Bs);
   }
   __syncthreads();
   for (int s = 0; s < steps; ++s) {
@@ -112,7 +114,7 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
     __syncthreads();
     if (more) {
       const bool p1 = s + 1 >= steps0;
-      stash_tiles<T>(p1 ? g.ta2 : g.ta, p1 ? g.tb2 : g.tb, tid, nxt, As, Bs);
+      stash_tiles<T, BK, NT>(p1 ? g.ta2 : g.ta, p1 ? g.tb2 : g.tb, tid, nxt, As, Bs);
       __syncthreads();
     }
   }
@@ -148,203 +150,501 @@ __global__ void __launch_bounds__(256) gemm_simt_kernel(Gemm g) {
   }
 }
 
+// ---------------------------------------------------------------------------------------------
+// Small problems (the 64 x 64 grid would leave most SMs idle: LeNet5 layers): one 32 x 32 output tile per CTA of 1024
+// threads.  A 32 x 32 x K product on 8 warps is a chain of dependent shared-memory loads and FMAs (2 x 2 outputs per
+// thread: 5 instructions per FMA, issued at a sixth of the rate -- 10 us per launch at K = 257, ncu).  Here each
+// thread keeps a 4 x 4 block of the tile (two 128-bit loads per 16 FMAs) and 1/16 of the K range: 8 column blocks x 4 K
+// slices per warp, 8 row blocks x 4 K slices across the warps.  The K slices meet by warp shuffles, then through shared
+// memory in a fixed order, and the epilogue runs one element per thread, coalesced.
+// ---------------------------------------------------------------------------------------------
+constexpr int ST = 32, SBK = 64, SLD = ST + PAD;
+__global__ void __launch_bounds__(1024) gemm_small_kernel(Gemm g) {
+  __shared__ __align__(16) float tiles[2 * SBK * SLD];
+  float (*As)[SLD] = reinterpret_cast<float (*)[SLD]>(tiles);
+  float (*Bs)[SLD] = reinterpret_cast<float (*)[SLD]>(tiles + SBK * SLD);
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int m0 = blockIdx.y * ST, n0 = blockIdx.x * ST;
+  const int om = tid >> 5, on = tid & 31;              // output role: one element of the tile
+  if (g.triu && m0 >= n0 + ST) {                      // tile entirely below the diagonal: zero after masking
+    if (m0 + om < g.M && n0 + on < g.N) g.C[(size_t)(m0 + om) * g.ldc + n0 + on] = 0.f;
+    return;
+  }
+  const int ti = w & 7, tj = lane & 7;                // multiply role: rows 4 ti.., columns 4 tj.. of the tile,
+  const int kq = ((w >> 3) << 2) + (lane >> 3);       // K rows 4 kq .. 4 kq + 3 of every step
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.f;
+
+  const int steps0 = (g.K > 0 && g.A) ? (g.K + SBK - 1) / SBK : 0;
+  const int steps1 = (g.K2 > 0 && g.A2) ? (g.K2 + SBK - 1) / SBK : 0;
+  const int steps = steps0 + steps1;
+  // Tile traffic of this thread: two elements of A and two of B per step.  Everything that does not change from step
+  // to step (global pointer, K offset, validity of the row / column, slot in shared memory) is worked out once per
+  // product -- with 1024 threads the address arithmetic of a generic fetch costs more issue slots than the multiply.
+  // The subtracted product is negated on its way in, so the multiply loop never looks at a sign.
+  const float* pa[2]; const float* pb[2];
+  int ka[2], kb[2], sa[2], sb[2];
+  bool oka[2], okb[2];
+  size_t stride_a = 0, stride_b = 0;
+  int kdim = 0, knext = 0;
+  float sgn = 1.f;
+  auto setup = [&](const float* A, int lda, bool ta, const float* B, int ldb, bool tb, int K, float sign) {
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      const int idx = tid + 1024 * e;
+      int m, k;
+      if (ta) { m = idx % ST; k = idx / ST; } else { k = idx % SBK; m = idx / SBK; }
+      oka[e] = m0 + m < g.M; ka[e] = k; sa[e] = k * SLD + m;
+      pa[e] = oka[e] ? (ta ? A + (size_t)k * lda + m0 + m : A + (size_t)(m0 + m) * lda + k) : A;
+      int n;
+      if (tb) { k = idx % SBK; n = idx / SBK; } else { n = idx % ST; k = idx / ST; }
+      okb[e] = n0 + n < g.N; kb[e] = k; sb[e] = SBK * SLD + k * SLD + n;
+      pb[e] = okb[e] ? (tb ? B + (size_t)(n0 + n) * ldb + k : B + (size_t)k * ldb + n0 + n) : B;
+    }
+    stride_a = ta ? (size_t)SBK * lda : (size_t)SBK;
+    stride_b = tb ? (size_t)SBK : (size_t)SBK * ldb;
+    kdim = K; knext = 0; sgn = sign;
+  };
+  float ra[2], rb[2];
+  int fs = 0;                                             // next step to fetch
+  auto fetch = [&]() {
+    if (fs == steps0 && steps1 > 0) setup(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.K2, -1.f);
+#pragma unroll
+    for (int e = 0; e < 2; ++e) {
+      ra[e] = (oka[e] && knext + ka[e] < kdim) ? sgn * *pa[e] : 0.f;
+      rb[e] = (okb[e] && knext + kb[e] < kdim) ? *pb[e] : 0.f;
+      pa[e] += stride_a; pb[e] += stride_b;
+    }
+    knext += SBK; ++fs;
+  };
+  if (steps0 > 0) setup(g.A, g.lda, g.ta, g.B, g.ldb, g.tb, g.K, 1.f);
+  if (steps > 0) {
+    fetch();
+#pragma unroll
+    for (int e = 0; e < 2; ++e) { tiles[sa[e]] = ra[e]; tiles[sb[e]] = rb[e]; }
+  }
+  __syncthreads();
+  for (int s = 0; s < steps; ++s) {
+    const bool more = s + 1 < steps;
+    if (more) fetch();                                    // in flight during the multiply below
+    const int da[2] = {sa[0], sa[1]}, db[2] = {sb[0], sb[1]};   // slots of the step just fetched (product switch)
+#pragma unroll
+    for (int kk = 0; kk < 4; ++kk) {
+      const int k = 4 * kq + kk;
+      const float4 a = *reinterpret_cast<const float4*>(&As[k][4 * ti]);
+      const float4 b = *reinterpret_cast<const float4*>(&Bs[k][4 * tj]);
+      const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(av[i], bv[j], acc[i][j]);
+    }
+    __syncthreads();
+    if (more) {
+#pragma unroll
+      for (int e = 0; e < 2; ++e) { tiles[da[e]] = ra[e]; tiles[db[e]] = rb[e]; }
+      __syncthreads();
+    }
+  }
+  // K slices: inside the warp (lanes 8 and 16 apart), then the four warps of a row block through shared memory
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v = acc[i][j];
+      v += __shfl_xor_sync(0xffffffffu, v, 8);
+      v += __shfl_xor_sync(0xffffffffu, v, 16);
+      acc[i][j] = v;
+    }
+  float (*red)[ST][ST + 1] = reinterpret_cast<float (*)[ST][ST + 1]>(tiles);   // the tiles are dead behind the last barrier
+  static_assert(4 * ST * (ST + 1) <= 2 * SBK * SLD, "partial sums reuse the tile buffers");
+  if (lane < 8) {
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) red[w >> 3][4 * ti + i][4 * tj + j] = acc[i][j];
+  }
+  __syncthreads();
+  const int m = m0 + om, n = n0 + on;
+  float mx = 0.f;
+  if (m < g.M && n < g.N) {
+    float v = (red[0][om][on] + red[1][om][on]) + (red[2][om][on] + red[3][om][on]);
+    if (g.colscale) {
+      float sc = g.colscale[n];
+      if (g.colscale_sq) sc = sc * sc;
+      v = g.colscale_recip ? v * (1.0f / sc) : v * sc;
+    }
+    if (g.triu && m > n) v = 0.f;
+    if (g.D) {
+      const float mu = g.mu_max ? g.step / (*g.mu_max + g.tiny) : 1.0f;
+      v = g.D[(size_t)m * g.ldd + n] - mu * v;
+    }
+    if (g.rho_mode == 1) v = v / *g.rho;
+    else if (g.rho_mode == 2) v = v * *g.rho;
+    mx = fabsf(v);
+    g.C[(size_t)m * g.ldc + n] = v;
+  }
+  if (g.maxabs) {
+    mx = warp_max(mx);
+    if (lane == 0 && mx > 0.f) atomic_max_nonneg(g.maxabs, mx);
+  }
+}
+
 int gemm_simt(psgd_ctx* ctx, const Gemm& g) {
   if (g.M <= 0 || g.N <= 0) return PSGD_OK;
   const int ctas64 = ((g.N + 63) / 64) * ((g.M + 63) / 64);
   if (ctas64 * 2 <= ctx->num_sms) {
-    dim3 grid((g.N + 31) / 32, (g.M + 31) / 32);
-    gemm_simt_kernel<32><<<grid, 256, 0, ctx->stream>>>(g);
+    dim3 grid((g.N + ST - 1) / ST, (g.M + ST - 1) / ST);
+    gemm_small_kernel<<<grid, 1024, 0, ctx->stream>>>(g);
   } else {
     dim3 grid((g.N + 63) / 64, (g.M + 63) / 64);
-    gemm_simt_kernel<64><<<grid, 256, 0, ctx->stream>>>(g);
+    gemm_simt_kernel<64, 16, 256><<<grid, 256, 0, ctx->stream>>>(g);
   }
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------
-// triangular solves, left-looking, 32-row blocks: one launch per block step
+// Triangular solves for layers below the tensor-core thresholds (LeNet5 / NMT factors, odd sizes, the vector solve of
+// the dense preconditioner).  One CTA of 1024 threads per 32-wide slab of the right-hand side (32 columns of B for the
+// left solve, 32 rows for the right one) and per PANEL of up to 512 unknowns:
+//   * the panel's 32 x 32 diagonal blocks are inverted up front, one warp per block, in shared memory (back
+//     substitution on the identity, one column per lane), so that a block step is a 32 x 32 x 32 product and not a
+//     32-long chain of divide / barrier / update rounds;
+//   * the slab of the right-hand side lives in shared memory for the whole panel and is overwritten by the solution,
+//     so a step never waits on a global-memory round trip for values this CTA produced itself;
+//   * only the off-diagonal tiles of Q stream in from global memory (64 x 32 at a time, double buffered, the next
+//     tile -- also across a step boundary -- in flight while the current one is multiplied);
+//   * both solves are the same computation  out[u][s] = sum_k Q[k][u] X[k][s]  (u: unknown inside the block, s: position
+//     inside the slab), so one kernel serves both; they differ in how (unknown, slab) maps to memory.  Each thread keeps
+//     4 unknowns x 1 slab position and a quarter of the K range (one 128-bit broadcast load of Q and one load of X per 4
+//     FMAs; with one output per thread the kernel was bound by shared-memory wavefronts, 2 per FMA: 74 us at n = 257);
+//     the four K quarters meet through shared memory in a fixed order.
+// ncu, round 2, n = 257, m = 120: the 256-thread row-by-row kernels before these ran 26 k dependent instructions per
+// warp at 8 cycles each (2 warps per scheduler): 120 us + 108 us per layer; these take 39 us + 17 us, of which ~9 us each
+// is the inversion of the diagonal blocks.  Panels beyond the first get the contribution of the solved part from one
+// SIMT GEMM each (host loop below).
 // ---------------------------------------------------------------------------------------------
-constexpr int NB = 32;
+constexpr int NB = 32;             // diagonal block
+constexpr int kPanel = 512;        // unknowns per launch
+constexpr int kPanelBlocks = kPanel / NB;
+constexpr int KT = 64;             // K rows per staged tile of Q
+constexpr int XP = NB + 1;         // pitch of the slab / staging arrays that are read with scalar loads
+constexpr size_t kTrsmSmem =
+    ((size_t)kPanelBlocks * NB * NB + (size_t)kPanel * XP + 2 * KT * NB + NB * XP + 4 * NB * XP) * sizeof(float);
 
-// Rows [ib0, ib1) of  X = Q^-T B  for one 32-column slab per CTA, assuming rows < ib0 of the right-hand side have
-// already been eliminated (B holds B - Q[0:ib0, :]^T X[0:ib0, :] there).  Left-looking over 32-row steps:
-//   X[I,:] = Qii^-T ( B[I,:] - sum_{ib0 <= k < i0} Q[k, I]^T X[k, :] )
-// Columns are independent, so the whole row range is solved in one launch.
-__global__ void __launch_bounds__(256) trsm_left_block_kernel(const float* __restrict__ Q, int ldq,
-                                                              const float* B, int ldb, float* X, int ldx, int m,
-                                                              int ib0, int ib1) {
-  __shared__ float Qs[NB][NB + 1];   // Qs[k][i] = Q[k0+k, i0+i]
-  __shared__ float Xs[NB][NB + 1];   // Xs[k][c] = X[k0+k, c0+c]
-  const int tid = threadIdx.x;
-  const int c0 = blockIdx.x * NB;
-  const int lr = tid / NB;          // 0..7
-  const int lc = tid % NB;          // 0..31
-  for (int i0 = ib0; i0 < ib1; i0 += NB) {
-    const int ib = min(NB, ib1 - i0);   // rows in this step
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr, lr+8, lr+16, lr+24 ; column lc
-    // tiles of the next k0 step are fetched into registers while the current one is multiplied (these solves are
-    // latency chains: one global round trip per 32 x 32 tile otherwise)
-    float qn[4], xn[4];
-    auto fetch = [&](int k0) {
+// In-place inverse of one upper-triangular 32 x 32 block held in shared memory (row-major, pitch 32), by one warp:
+// lane c solves U x = e_c from the last row up; row i of U is dead once every lane has used it, so x_i overwrites it.
+// The reciprocals of the diagonal are formed by all lanes at once and the dot product runs as two independent chains.
+__device__ __forceinline__ void invert_block_warp(float* U, int lane) {
+  const float rdiag = 1.0f / U[lane * NB + lane];
+  float x[NB];
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = lr + 8 * e;
-        qn[e] = (i0 + lc < ib1) ? Q[(size_t)(k0 + k) * ldq + i0 + lc] : 0.f;
-        xn[e] = (c0 + lc < m) ? X[(size_t)(k0 + k) * ldx + c0 + lc] : 0.f;
-      }
-    };
-    if (ib0 < i0) fetch(ib0);
-    for (int k0 = ib0; k0 < i0; k0 += NB) {
+  for (int i = NB - 1; i >= 0; --i) {
+    float sa = (i == lane) ? 1.f : 0.f, sb = 0.f;
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int k = lr + 8 * e;
-        Qs[k][lc] = qn[e];
-        Xs[k][lc] = xn[e];
-      }
-      __syncthreads();
-      if (k0 + NB < i0) fetch(k0 + NB);
-#pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        const float x = Xs[k][lc];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = fmaf(Qs[k][lr + 8 * e], x, acc[e]);
-      }
-      __syncthreads();
+    for (int k = i + 1; k < NB; k += 2) {
+      sa = fmaf(-U[i * NB + k], x[k], sa);
+      if (k + 1 < NB) sb = fmaf(-U[i * NB + k + 1], x[k + 1], sb);
     }
-    // diagonal block: forward substitution with Qii^T (only the upper triangle of Qii is read)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int i = lr + 8 * e;
-      Qs[i][lc] = (i < ib && lc < ib && i <= lc) ? Q[(size_t)(i0 + i) * ldq + i0 + lc] : 0.f;   // Qs[k][i], k<=i
-      float b = 0.f;
-      if (i < ib && c0 + lc < m) b = B[(size_t)(i0 + i) * ldb + c0 + lc] - acc[e];
-      Xs[i][lc] = b;
+    x[i] = (sa + sb) * __shfl_sync(0xffffffffu, rdiag, i);
+    __syncwarp();
+    U[i * NB + lane] = x[i];
+  }
+  __syncwarp();
+}
+
+// Diagonal blocks of Q[b0 : b1, b0 : b1] -> W (block t at W + t * 1024), upper triangles only; rows / columns beyond b1
+// are padded with the identity.  Warps 0 .. blocks-1 work, the others fall through.
+__device__ __forceinline__ void load_and_invert_blocks(const float* __restrict__ Q, int ldq, int b0, int b1, float* W,
+                                                       int warp, int lane) {
+  const int blocks = (b1 - b0 + NB - 1) / NB;
+  if (warp < blocks) {
+    float* U = W + warp * NB * NB;
+    const int d0 = b0 + warp * NB;
+#pragma unroll 8
+    for (int i = 0; i < NB; ++i) {
+      float v = (i == lane) ? 1.f : 0.f;
+      if (d0 + i < b1 && d0 + lane < b1) v = (lane >= i) ? Q[(size_t)(d0 + i) * ldq + d0 + lane] : 0.f;
+      U[i * NB + lane] = v;
     }
-    __syncthreads();
-    // Right-looking over the 32 rows with ALL 256 threads: row i is finished by the thread that owns it, one barrier,
-    // then every thread folds x_i into the rows it owns.  Same operations in the same order as the row-by-row loop it
-    // replaces (each b_j sees -q_kj x_k for k = 0, 1, ... with one fused rounding each), which one thread per column ran
-    // as a serial chain of ~500 dependent shared-memory round trips per block (124 us per solve at n = 257, ncu).
-    for (int i = 0; i < ib; ++i) {
-      if (lr == (i & 7)) {
-        const float x = Xs[i][lc] / Qs[i][i];
-        Xs[i][lc] = x;
-        if (c0 + lc < m) X[(size_t)(i0 + i) * ldx + c0 + lc] = x;
-      }
-      __syncthreads();
-      const float xi = Xs[i][lc];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int j = lr + 8 * e;
-        if (j > i && j < ib) Xs[j][lc] = fmaf(-Qs[i][j], xi, Xs[j][lc]);
-      }
-    }
-    __syncthreads();   // X rows of this step are visible to the next step's k-loop (same CTA)
+    __syncwarp();
+    invert_block_warp(U, lane);
   }
 }
 
-// Columns [jb0, jb1) of  X = B Q^-1  for one 32-row slab per CTA, assuming columns < jb0 have been eliminated.
-//   X[:,J] = ( B[:,J] - sum_{jb0 <= k < j0} X[:, k] Q[k, J] ) Qjj^-1
-__global__ void __launch_bounds__(256) trsm_right_block_kernel(const float* __restrict__ Q, int ldq,
-                                                               const float* B, int ldb, float* X, int ldx, int m,
-                                                               int jb0, int jb1) {
-  __shared__ float Qs[NB][NB + 1];   // Qs[k][j] = Q[k0+k, j0+j]
-  __shared__ float Xs[NB][NB + 1];   // Xs[r][k] = X[r0+r, k0+k]
-  const int tid = threadIdx.x;
-  const int r0 = blockIdx.x * NB;
-  const int lr = tid / NB;          // 0..7
-  const int lc = tid % NB;          // 0..31
-  for (int j0 = jb0; j0 < jb1; j0 += NB) {
-    const int jb = min(NB, jb1 - j0);
-    float acc[4] = {0.f, 0.f, 0.f, 0.f};   // rows lr+8e, column lc
-    float qn[4], xn[4];                     // next k0 step's tiles, in flight during the multiply
-    auto fetch = [&](int k0) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = lr + 8 * e;
-        qn[e] = (j0 + lc < jb1) ? Q[(size_t)(k0 + r) * ldq + j0 + lc] : 0.f;
-        xn[e] = (r0 + r < m) ? X[(size_t)(r0 + r) * ldx + k0 + lc] : 0.f;
-      }
-    };
-    if (jb0 < j0) fetch(jb0);
-    for (int k0 = jb0; k0 < j0; k0 += NB) {
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int r = lr + 8 * e;
-        Qs[r][lc] = qn[e];
-        Xs[r][lc] = xn[e];
-      }
+// Unknowns [b0, b1) (at most kPanel) of one slab, assuming the unknowns before b0 have been eliminated already (B holds
+// the right-hand side minus their contribution):
+//   LEFT :  X = Q^-T B, unknown t = row of X, slab = 32 columns:   X[T,:] = Wtt^T ( B[T,:] - sum_k Q[k,T]^T X[k,:] )
+//   RIGHT:  X = B Q^-1, unknown t = column of X, slab = 32 rows:   X[:,T] = ( B[:,T] - sum_k X[:,k] Q[k,T] ) Wtt
+// with Wtt = Qtt^-1 and k over the earlier blocks of the panel.
+template <bool LEFT>
+__global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restrict__ Q, int ldq, const float* B, int ldb,
+                                                          float* X, int ldx, int m, int b0, int b1) {
+  extern __shared__ __align__(16) float trsm_smem[];
+  float* W = trsm_smem;                                   // [blocks][32][32]   inverted diagonal blocks
+  float* Xs = W + kPanelBlocks * NB * NB;                 // [unknown][XP]      right-hand side, then the solution
+  float* Qs = Xs + kPanel * XP;                           // [2][KT][32]        Qs[k][u] = Q[k0+k, u0+u]
+  float* Bs = Qs + 2 * KT * NB;                           // [32][XP]           right-hand side of the block step
+  float* Ps = Bs + NB * XP;                               // [4][32][XP]        partial sums of the K quarters
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int s0 = blockIdx.x * NB;
+  const int span = ((b1 - b0 + NB - 1) / NB) * NB;
+  // (unknown t, slab position s) in global memory
+  auto at = [&](int t, int s, int ld) -> size_t {
+    return LEFT ? (size_t)t * ld + s0 + s : (size_t)(s0 + s) * ld + t;
+  };
+  if (LEFT) {
+    for (int t = w; t < span; t += 32)
+      Xs[t * XP + lane] = (b0 + t < b1 && s0 + lane < m) ? B[at(b0 + t, lane, ldb)] : 0.f;
+  } else {
+    for (int t = lane; t < span; t += 32)
+      Xs[t * XP + w] = (b0 + t < b1 && s0 + w < m) ? B[at(b0 + t, w, ldb)] : 0.f;
+  }
+  load_and_invert_blocks(Q, ldq, b0, b1, W, w, lane);
+
+  // multiply role: K quarter kg, unknowns 4 ug .. 4 ug + 3 of the block, slab position = lane
+  const int kg = w >> 3, ug = w & 7;
+  // output role: one (unknown, slab position) per thread, lanes along the contiguous direction of X
+  const int ou = LEFT ? w : lane, os = LEFT ? lane : w;
+  const bool os_ok = s0 + os < m;
+
+  // off-diagonal tiles in the order they are consumed: (block u0, k0), k0 = b0, b0 + KT, ... < u0
+  float q0, q1;
+  auto fetch = [&](int u0, int k0) {
+    const int col = u0 + lane;
+    const int ka = k0 + w, kb = k0 + w + 32;
+    q0 = (ka < u0 && col < b1) ? Q[(size_t)ka * ldq + col] : 0.f;
+    q1 = (kb < u0 && col < b1) ? Q[(size_t)kb * ldq + col] : 0.f;
+  };
+  int pu = b0 + NB, pk = b0;                              // the tile in flight
+  if (pu < b1) fetch(pu, pk);
+  int buf = 0;
+  __syncthreads();
+  for (int u0 = b0; u0 < b1; u0 += NB) {
+    float acc[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int k0 = b0; k0 < u0; k0 += KT) {
+      float* Qb = Qs + buf * KT * NB;
+      Qb[w * NB + lane] = q0;
+      Qb[(w + 32) * NB + lane] = q1;
       __syncthreads();
-      if (k0 + NB < j0) fetch(k0 + NB);
+      pk += KT;
+      if (pk >= pu) { pu += NB; pk = b0; }
+      if (pu < b1) fetch(pu, pk);
+      const float* qb = Qb + (kg * (KT / 4)) * NB + 4 * ug;
+      const float* xs = Xs + (k0 - b0 + kg * (KT / 4)) * XP + lane;
 #pragma unroll
-      for (int k = 0; k < NB; ++k) {
-        const float q = Qs[k][lc];
-#pragma unroll
-        for (int e = 0; e < 4; ++e) acc[e] = fmaf(Xs[lr + 8 * e][k], q, acc[e]);
+      for (int k = 0; k < KT / 4; ++k) {
+        const float4 q = *reinterpret_cast<const float4*>(qb + k * NB);
+        const float x = xs[k * XP];
+        acc[0] = fmaf(q.x, x, acc[0]); acc[1] = fmaf(q.y, x, acc[1]);
+        acc[2] = fmaf(q.z, x, acc[2]); acc[3] = fmaf(q.w, x, acc[3]);
       }
-      __syncthreads();
+      buf ^= 1;
     }
+    const int to = u0 - b0 + ou;                          // this thread's unknown inside the panel (output role)
+    float bval = Xs[to * XP + os];
+    if (u0 > b0) {
 #pragma unroll
-    for (int e = 0; e < 4; ++e) {
-      const int r = lr + 8 * e;
-      Qs[r][lc] = (r < jb && lc < jb && r <= lc) ? Q[(size_t)(j0 + r) * ldq + j0 + lc] : 0.f;   // Qs[k][j], k<=j
-      float b = 0.f;
-      if (r0 + r < m && lc < jb) b = B[(size_t)(r0 + r) * ldb + j0 + lc] - acc[e];
-      Xs[r][lc] = b;
+      for (int e = 0; e < 4; ++e) Ps[(kg * NB + 4 * ug + e) * XP + lane] = acc[e];
+      __syncthreads();
+      const float* pp = Ps + ou * XP + os;
+      bval -= (pp[0] + pp[NB * XP]) + (pp[2 * NB * XP] + pp[3 * NB * XP]);
+    }
+    Bs[ou * XP + os] = bval;
+    __syncthreads();
+    {
+      const float* wb = W + ((u0 - b0) / NB) * NB * NB + (kg * (NB / 4)) * NB + 4 * ug;   // Wtt[k][u], zero for k > u
+      const float* bs = Bs + (kg * (NB / 4)) * XP + lane;
+      float xa[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int k = 0; k < NB / 4; ++k) {
+        const float4 q = *reinterpret_cast<const float4*>(wb + k * NB);
+        const float bb = bs[k * XP];
+        xa[0] = fmaf(q.x, bb, xa[0]); xa[1] = fmaf(q.y, bb, xa[1]);
+        xa[2] = fmaf(q.z, bb, xa[2]); xa[3] = fmaf(q.w, bb, xa[3]);
+      }
+#pragma unroll
+      for (int e = 0; e < 4; ++e) Ps[(kg * NB + 4 * ug + e) * XP + lane] = xa[e];
     }
     __syncthreads();
-    // right-looking over the 32 columns with all 256 threads (see trsm_left_block_kernel): column j is finished by the
-    // threads that own it, one barrier, then every thread folds it into its own columns; same operations, same order
-    for (int j = 0; j < jb; ++j) {
-      if (lc == j) {
+    const float* pp = Ps + ou * XP + os;
+    const float x = (pp[0] + pp[NB * XP]) + (pp[2 * NB * XP] + pp[3 * NB * XP]);
+    Xs[to * XP + os] = x;
+    if (u0 + ou < b1 && os_ok) X[at(u0 + ou, os, ldx)] = x;
+    // every later use of Xs / Bs / Ps sits behind the barrier that follows the next tile stash
+  }
+}
+
+// Vector right-hand side (the dense preconditioner's b = Q^-T dx, psgd.py:39): unknowns [b0, b1) of one panel by ONE CTA.
+// With a single column there is nothing to tile: every element of Q is used once, so the rows of Q[b0:u0, u0:u0+32]
+// are read straight from global memory (32 lanes = 32 consecutive columns, the warps stride the rows), the 32 warps'
+// partial dots meet in shared memory, and warp 0 applies the inverted diagonal block.  The contribution of the
+// unknowns before b0 arrives as the vector `sub` = Q[0:b0, b0:b1]^T x[0:b0] (ks::col_wsum: the bandwidth-bound bulk of
+// the solve, spread over the whole GPU) and is subtracted here.
+constexpr size_t kTrsvSmem = ((size_t)kPanelBlocks * NB * NB + kPanel + NB * XP + NB) * sizeof(float);
+__global__ void __launch_bounds__(1024) trsv_panel_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ B,
+                                                          float* X, int b0, int b1, const float* __restrict__ sub) {
+  extern __shared__ __align__(16) float trsm_smem[];
+  float* W = trsm_smem;                                   // [blocks][32][32]
+  float* xs = W + kPanelBlocks * NB * NB;                 // [kPanel]  right-hand side, then the solution
+  float* red = xs + kPanel;                               // [32][XP]
+  float* bs = red + NB * XP;                              // [32]
+  const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
+  const int span = ((b1 - b0 + NB - 1) / NB) * NB;
+  // the panel's triangle of Q on its way into L2 before the block steps ask for it
+  for (int idx = tid; idx < span * (span / NB); idx += 1024) {
+    const int r = idx / (span / NB), cb = idx % (span / NB);
+    if (cb * NB + NB - 1 >= r && b0 + r < b1 && b0 + cb * NB < b1)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(Q + (size_t)(b0 + r) * ldq + b0 + cb * NB));
+  }
+  for (int t = tid; t < span; t += 1024) {
+    float v = 0.f;
+    if (b0 + t < b1) {
+      v = B[b0 + t];
+      if (sub) v -= sub[t];
+    }
+    xs[t] = v;
+  }
+  // this thread's elements of the NEXT block step, Q[b0 + w + 32 i, u0 + lane]: loaded a step ahead (they do not depend
+  // on the solution), so that a step is two barriers and warp 0's 32 x 32 product, not a round trip to L2
+  float qv[kPanelBlocks - 1];
+  auto prefetch_step = [&](int u0) {
+    const int its = (u0 - b0) / NB, col = u0 + lane;
+    const float* q = Q + (size_t)(b0 + w) * ldq + col;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lr + 8 * e;
-          const float x = Xs[r][j] / Qs[j][j];
-          Xs[r][j] = x;
-          if (r0 + r < m) X[(size_t)(r0 + r) * ldx + j0 + j] = x;
-        }
-      }
-      __syncthreads();
-      if (lc > j && lc < jb) {
-        const float q = Qs[j][lc];
+    for (int i = 0; i < kPanelBlocks - 1; ++i) qv[i] = (i < its && col < b1) ? q[(size_t)i * NB * ldq] : 0.f;
+  };
+  if (b0 + NB < b1) prefetch_step(b0 + NB);
+  load_and_invert_blocks(Q, ldq, b0, b1, W, w, lane);
+  __syncthreads();
+  for (int u0 = b0; u0 < b1; u0 += NB) {
+    const int col = u0 + lane;
+    const int its = (u0 - b0) / NB;
+    float acc = 0.f;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const int r = lr + 8 * e;
-          Xs[r][lc] = fmaf(-Xs[r][j], q, Xs[r][lc]);
-        }
+    for (int i = 0; i < kPanelBlocks - 1; ++i)
+      if (i < its) acc = fmaf(qv[i], xs[w + NB * i], acc);
+    if (u0 + NB < b1) prefetch_step(u0 + NB);
+    red[w * XP + lane] = acc;
+    __syncthreads();
+    if (w == 0) {
+      float sa = 0.f, sb = 0.f;
+#pragma unroll
+      for (int r = 0; r < NB; r += 2) { sa += red[r * XP + lane]; sb += red[(r + 1) * XP + lane]; }
+      bs[lane] = xs[u0 - b0 + lane] - (sa + sb);
+      __syncwarp();
+      const float* Wb = W + ((u0 - b0) / NB) * NB * NB;
+      float x0 = 0.f, x1 = 0.f;
+#pragma unroll
+      for (int k = 0; k < NB; k += 2) {                  // Wb[k][lane] = 0 for k > lane
+        x0 = fmaf(Wb[k * NB + lane], bs[k], x0);
+        x1 = fmaf(Wb[(k + 1) * NB + lane], bs[k + 1], x1);
       }
+      const float x = x0 + x1;
+      xs[u0 - b0 + lane] = x;
+      if (col < b1) X[col] = x;
     }
     __syncthreads();
   }
+}
+
+static DeviceOnce trsm_attr_done;
+static int ensure_trsm_attrs(psgd_ctx* ctx) {
+  if (trsm_attr_done.done(ctx->device)) return PSGD_OK;
+  PSGD_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+  PSGD_CUDA_CHECK(cudaFuncSetAttribute(trsm_panel_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsmSmem));
+  PSGD_CUDA_CHECK(cudaFuncSetAttribute(trsv_panel_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kTrsvSmem));
+  trsm_attr_done.set(ctx->device);
+  return PSGD_OK;
 }
 
 int trsm_left_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int ib0,
                     int ib1) {
   if (ib1 <= ib0 || m <= 0) return PSGD_OK;
+  PSGD_REQUIRE(ib1 - ib0 <= kPanel, PSGD_ERR_BAD_SHAPE, "trsm panel of %d rows", ib1 - ib0);
+  PSGD_RETURN_IF(ensure_trsm_attrs(ctx));
   ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (ib1 - ib0) * (ib1 - ib0));
-  trsm_left_block_kernel<<<(m + NB - 1) / NB, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, ib0, ib1);
+  trsm_panel_kernel<true><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, ib0, ib1);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 int trsm_right_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int jb0,
                      int jb1) {
   if (jb1 <= jb0 || m <= 0) return PSGD_OK;
+  PSGD_REQUIRE(jb1 - jb0 <= kPanel, PSGD_ERR_BAD_SHAPE, "trsm panel of %d columns", jb1 - jb0);
+  PSGD_RETURN_IF(ensure_trsm_attrs(ctx));
   ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (jb1 - jb0) * (jb1 - jb0));
-  trsm_right_block_kernel<<<(m + NB - 1) / NB, 256, 0, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, jb0, jb1);
+  trsm_panel_kernel<false><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, jb0, jb1);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
 
+size_t trsv_ws_floats(int n) { return n > kPanel ? ((size_t)ks::row_tiles(n) + 1) * kPanel : 0; }
+
+// x = Q^-T b for one vector: panels of 512 unknowns; before each panel but the first, Q[0:p0, p0:p1]^T x[0:p0] as
+// column sums over the whole GPU (the n^2 / 2 floats of Q that the solve has to read go by at HBM speed), then the
+// panel itself on one CTA.  `ws`: trsv_ws_floats(n) floats.
+int trsv_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* b, float* x, int n, float* ws) {
+  if (n <= 0) return PSGD_OK;
+  PSGD_RETURN_IF(ensure_trsm_attrs(ctx));
+  ProfScope prof(ctx, PSGD_K_TRSM, (double)n * n);
+  for (int p0 = 0; p0 < n; p0 += kPanel) {
+    const int p1 = p0 + kPanel < n ? p0 + kPanel : n;
+    const float* sub = nullptr;
+    if (p0 > 0) {
+      PSGD_RETURN_IF(ks::col_wsum(ctx, 1, nullptr, x, Q + p0, ldq, p0, p1 - p0, ws + kPanel, ws));
+      sub = ws;
+    }
+    trsv_panel_kernel<<<1, 1024, kTrsvSmem, ctx->stream>>>(Q, ldq, b, x, p0, p1, sub);
+    PSGD_LAUNCH_CHECK(ctx);
+  }
+  return PSGD_OK;
+}
+
+// Panels after the first: the solved part's contribution comes off the right-hand side in one GEMM, written where the
+// solution of the panel will go (X may alias B: the GEMM is elementwise in D and C), then the panel is solved in place.
 int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx,
                             int n, int m) {
-  return trsm_left_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, n);
+  for (int p0 = 0; p0 < n; p0 += kPanel) {
+    const int p1 = p0 + kPanel < n ? p0 + kPanel : n;
+    if (p0 == 0) {
+      PSGD_RETURN_IF(trsm_left_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, p1));
+      continue;
+    }
+    Gemm g;                                                // X[P,:] = B[P,:] - Q[0:p0, P]^T X[0:p0, :]
+    g.M = p1 - p0; g.N = m; g.K = p0;
+    g.A = Q + p0; g.lda = ldq; g.ta = true;
+    g.B = X; g.ldb = ldx;
+    g.C = X + (size_t)p0 * ldx; g.ldc = ldx;
+    g.D = B + (size_t)p0 * ldb; g.ldd = ldb;
+    PSGD_RETURN_IF(gemm_simt(ctx, g));
+    PSGD_RETURN_IF(trsm_left_block(ctx, Q, ldq, X, ldx, X, ldx, m, p0, p1));
+  }
+  return PSGD_OK;
 }
 
 int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
                      int n) {
-  return trsm_right_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, n);
+  for (int p0 = 0; p0 < n; p0 += kPanel) {
+    const int p1 = p0 + kPanel < n ? p0 + kPanel : n;
+    if (p0 == 0) {
+      PSGD_RETURN_IF(trsm_right_block(ctx, Q, ldq, B, ldb, X, ldx, m, 0, p1));
+      continue;
+    }
+    Gemm g;                                                // X[:,P] = B[:,P] - X[:, 0:p0] Q[0:p0, P]
+    g.M = m; g.N = p1 - p0; g.K = p0;
+    g.A = X; g.lda = ldx;
+    g.B = Q + p0; g.ldb = ldq;
+    g.C = X + p0; g.ldc = ldx;
+    g.D = B + p0; g.ldd = ldb;
+    PSGD_RETURN_IF(gemm_simt(ctx, g));
+    PSGD_RETURN_IF(trsm_right_block(ctx, Q, ldq, X, ldx, X, ldx, m, p0, p1));
+  }
+  return PSGD_OK;
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -61,8 +61,12 @@ int trsm_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float*
 int trsm_right_upper(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m,
                      int n);
 
-// Block forms used by the recursive tensor-core TRSM (gemm_tc.cu): solve only rows [ib0, ib1) / columns [jb0, jb1),
-// assuming the contribution of earlier rows / columns has already been subtracted from B.  One launch each.
+// x = Q^-T b for ONE right-hand side (contiguous vectors), n of any size; ws: trsv_ws_floats(n) floats of workspace.
+size_t trsv_ws_floats(int n);
+int trsv_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float* b, float* x, int n, float* ws);
+
+// Panel forms: solve only rows [ib0, ib1) / columns [jb0, jb1) (at most 512 of them), assuming the contribution of
+// earlier rows / columns has already been subtracted from B.  One launch each.
 int trsm_left_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int ib0,
                     int ib1);
 int trsm_right_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int ldb, float* X, int ldx, int m, int jb0,

@@ -281,6 +281,53 @@ def test_kron_all_format_combinations(psgd, kl, kr, M, N):
     check(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"]), what="pre_grad")
 
 
+@pytest.mark.parametrize("M,N", [(257, 120), (120, 257), (513, 33), (33, 513), (1101, 70), (70, 1101), (545, 130), (1025, 1)])
+def test_kron_dense_pairs_on_the_panel_solves(psgd, M, N):
+    """Dense pairs below the tensor-core thresholds (odd sizes, thin gradients): triangular solves by the 1024-thread
+    panel kernels of csrc/linalg.cu -- one panel (n <= 512), several panels joined by SIMT GEMMs (n > 512), partial last
+    blocks, slabs with fewer than 32 right-hand sides (psgd.py:171-172)."""
+    c = cases.kron_case(9100 + 3 * M + N, "dense", "dense", M, N)
+    ql, qr = psgd.update_precond_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["dX"]), dev(c["dG"]), 0.01)
+    qlr, qrr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
+    check(ql, qlr, what="Ql"); check(qr, qrr, what="Qr")
+    pre = psgd.precond_grad_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["G"]))
+    check(pre, O.precond_grad_kron(c["Ql"], c["Qr"], c["G"]), what="pre_grad")
+
+
+@pytest.mark.parametrize("n", [1, 2, 33, 129, 600, 1500])
+@pytest.mark.parametrize("scan", [1, 0])
+@pytest.mark.parametrize("full", [False, True])
+def test_dense_update_scan_form_and_vector_solve_over_panels(psgd, n, scan, full):
+    """Dense update (psgd.py:26-42) beyond one 512-row panel of the vector solve; scan = 1: Q - mu triu(a a^T - b b^T) Q as
+    column suffix scans (O(n^2)), scan = 0: the reference's n^3 product.  full: Q with a non-zero lower triangle -- the
+    solve reads only the upper one (tf.linalg.triangular_solve), the products all of it (tf.matmul)."""
+    c = cases.dense_case(4100 + n, [(n,)])
+    Q = c["Q"].copy()
+    if full:
+        Q += np.tril(0.05 * np.random.default_rng(n).standard_normal((n, n)).astype(np.float32), -1)
+    ctx = psgd.get_context()
+    ctx.set_option("dense_scan", scan)
+    try:
+        Qn = psgd.update_precond_dense(dev(Q), [dev(x) for x in c["dxs"]], [dev(x) for x in c["dgs"]], 0.01)
+    finally:
+        ctx.set_option("dense_scan", 1)
+    check(Qn, O.update_precond_dense(Q, c["dxs"], c["dgs"], 0.01), what="Q")
+
+
+def test_dense_update_scan_trajectory(psgd):
+    """50 dense updates in a row, scan form, against the oracle's trajectory."""
+    n = 300
+    c = cases.dense_case(77, [(n,)])
+    rng = np.random.default_rng(78)
+    Qd, Qo = dev(c["Q"]), c["Q"]
+    for _ in range(50):
+        dx = rng.standard_normal(n).astype(np.float32)
+        dg = (dx * (0.5 + rng.random(n)) + 0.1 * rng.standard_normal(n)).astype(np.float32)
+        Qd = psgd.update_precond_dense(Qd, [dev(dx)], [dev(dg)], 0.01)
+        Qo = O.update_precond_dense(Qo, [dx], [dg], 0.01)
+    check(Qd, Qo, tol=5e-5, what="Q after 50 steps")
+
+
 @pytest.mark.parametrize("M,N", [(2305, 1024), (1025, 4935), (300, 7), (5, 3000), (64, 256), (65, 257), (3, 1)])
 @pytest.mark.parametrize("mirror", [False, True])
 def test_kron_norm_scale_fused_streaming_kernels(psgd, M, N, mirror):

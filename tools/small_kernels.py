@@ -34,3 +34,13 @@ for e in prof.key_averages():
 for us, cnt, name in sorted(rows, reverse=True):
     print(f"{us:8.1f} us/step  x{cnt:2d}  {name}")
 print("sum", sum(r[0] for r in rows))
+
+# launch order of the last profiled step, with each kernel's own duration and the gap before it
+evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and e.device_time > 0], key=lambda e: e.time_range.start)
+per = len(evs) // 10
+last = evs[-per:]
+prev_end = None
+for e in last:
+    gap = (e.time_range.start - prev_end) if prev_end is not None else 0.0
+    print(f"  +{gap:6.1f} us gap  {e.device_time:7.1f} us  {e.name[:80]}")
+    prev_end = e.time_range.end
