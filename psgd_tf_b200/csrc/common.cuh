@@ -73,6 +73,7 @@ struct psgd_ctx {
   int opt_tc_bn = 128;       // tcgen05 GEMM tile width (128 or 256)
   int opt_trsm_base = 1024;  // tensor-core triangular solves: width of the diagonal blocks applied via their explicit inverse
   int opt_tc_debug = 0;      // tcgen05 GEMM timing ablations (wrong results; tools/gemm_debug.py only)
+  long long* opt_stamp_ptr = nullptr;   // tools only: device buffer that the panel-solve kernels fill with clock64() stamps
   int opt_dense_scan = 1;    // dense update: 1 = column scans (O(n^2)), 0 = the reference's n^3 product (cross-check)
   int opt_tc_splitk = 1;     // tcgen05 GEMM: split K over grouped problems when the output has too few tiles to fill the GPU
   int opt_tc_epi = 2;        // tcgen05 GEMM epilogue stores: 2 = staged through shared memory (full 128-byte lines), 1 = 256-bit, 0 = 128-bit per row

@@ -126,6 +126,7 @@ extern "C" int psgd_set_option(psgd_ctx* ctx, const char* key, int64_t value) {
   if (strcmp(key, "uvd_mid") == 0) { ctx->opt_uvd_mid = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "comm_timeout_ms") == 0) { ctx->opt_comm_timeout_ms = value > 0 ? (int)value : 0; return PSGD_OK; }
   if (strcmp(key, "tc_debug") == 0) { ctx->opt_tc_debug = (int)value; return PSGD_OK; }
+  if (strcmp(key, "stamp_ptr") == 0) { ctx->opt_stamp_ptr = reinterpret_cast<long long*>(value); return PSGD_OK; }
   if (strcmp(key, "dense_scan") == 0) { ctx->opt_dense_scan = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_splitk") == 0) { ctx->opt_tc_splitk = value ? 1 : 0; return PSGD_OK; }
   if (strcmp(key, "tc_epi") == 0) { ctx->opt_tc_epi = value < 0 ? 0 : (value > 2 ? 2 : (int)value); return PSGD_OK; }

@@ -479,27 +479,34 @@ __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restric
   }
 }
 
-// Vector right-hand side (the dense preconditioner's b = Q^-T dx, psgd.py:39): unknowns [b0, b1) of one panel by ONE CTA.
-// With a single column there is nothing to tile: every element of Q is used once, so the rows of Q[b0:u0, u0:u0+32]
-// are read straight from global memory (32 lanes = 32 consecutive columns, the warps stride the rows), the 32 warps'
-// partial dots meet in shared memory, and warp 0 applies the inverted diagonal block.  The contribution of the
-// unknowns before b0 arrives as the vector `sub` = Q[0:b0, b0:b1]^T x[0:b0] (ks::col_wsum: the bandwidth-bound bulk of
-// the solve, spread over the whole GPU) and is subtracted here.
-constexpr size_t kTrsvSmem = ((size_t)kPanelBlocks * NB * NB + kPanel + NB * XP + NB) * sizeof(float);
+// Vector right-hand side (the dense preconditioner's b = Q^-T dx, psgd.py:39): unknowns [b0, b1) of one panel by ONE CTA,
+// right-looking.  Thread t owns unknown b0 + t: once warp 0 has finished a block of 32 unknowns with the inverted diagonal
+// block, every thread to the right of the block takes the block's contribution off its own right-hand side,
+//   rhs[t] -= sum_{k in block} Q[k, b0 + t] x[k],
+// with the 32 rows of Q it needs read a step ahead (they do not depend on the solution) as 32 coalesced loads -- lanes
+// are consecutive columns -- so a step is two barriers, one 32 x 32 product on warp 0 and a chain of 32 FMAs.  (The
+// left-looking form of the tiled kernel above reduces over the warps every step and issues its predicated loads for all
+// 15 possible earlier blocks: 41 us per 512-row panel against 9 us of start-up, ncu.)  The contribution of the unknowns
+// before b0 arrives as the vector `sub` = Q[0:b0, b0:b1]^T x[0:b0] (ks::col_wsum: the bandwidth-bound bulk of the solve,
+// spread over the whole GPU) and is subtracted here.
+constexpr size_t kTrsvSmem = ((size_t)kPanelBlocks * NB * NB + kPanel + NB) * sizeof(float);
 __global__ void __launch_bounds__(1024) trsv_panel_kernel(const float* __restrict__ Q, int ldq, const float* __restrict__ B,
-                                                          float* X, int b0, int b1, const float* __restrict__ sub) {
+                                                          float* X, int b0, int b1, const float* __restrict__ sub,
+                                                          long long* stamps) {
   extern __shared__ __align__(16) float trsm_smem[];
+  int nstamp = 0;
+  auto stamp = [&]() { if (stamps && threadIdx.x == 0) stamps[nstamp++] = clock64(); };   // tools/trsv_stamps.py
+  stamp();
   float* W = trsm_smem;                                   // [blocks][32][32]
-  float* xs = W + kPanelBlocks * NB * NB;                 // [kPanel]  right-hand side, then the solution
-  float* red = xs + kPanel;                               // [32][XP]
-  float* bs = red + NB * XP;                              // [32]
+  float* xs = W + kPanelBlocks * NB * NB;                 // [kPanel]  right-hand side of the unknowns still open
+  float* xn = xs + kPanel;                                // [32]      the block just solved
   const int tid = threadIdx.x, w = tid >> 5, lane = tid & 31;
   const int span = ((b1 - b0 + NB - 1) / NB) * NB;
   // the panel's triangle of Q on its way into L2 before the block steps ask for it
-  for (int idx = tid; idx < span * (span / NB); idx += 1024) {
-    const int r = idx / (span / NB), cb = idx % (span / NB);
-    if (cb * NB + NB - 1 >= r && b0 + r < b1 && b0 + cb * NB < b1)
-      asm volatile("prefetch.global.L2 [%0];" ::"l"(Q + (size_t)(b0 + r) * ldq + b0 + cb * NB));
+  if (lane < span / NB) {                                  // lane = column block, the warps stride the rows
+    const float* qp = Q + (size_t)(b0 + w) * ldq + b0 + lane * NB;
+    for (int r = w; r < b1 - b0 && r <= lane * NB + NB - 1; r += 32, qp += (size_t)32 * ldq)
+      asm volatile("prefetch.global.L2 [%0];" ::"l"(qp));
   }
   for (int t = tid; t < span; t += 1024) {
     float v = 0.f;
@@ -509,35 +516,29 @@ __global__ void __launch_bounds__(1024) trsv_panel_kernel(const float* __restric
     }
     xs[t] = v;
   }
-  // this thread's elements of the NEXT block step, Q[b0 + w + 32 i, u0 + lane]: loaded a step ahead (they do not depend
-  // on the solution), so that a step is two barriers and warp 0's 32 x 32 product, not a round trip to L2
-  float qv[kPanelBlocks - 1];
-  auto prefetch_step = [&](int u0) {
-    const int its = (u0 - b0) / NB, col = u0 + lane;
-    const float* q = Q + (size_t)(b0 + w) * ldq + col;
-#pragma unroll
-    for (int i = 0; i < kPanelBlocks - 1; ++i) qv[i] = (i < its && col < b1) ? q[(size_t)i * NB * ldq] : 0.f;
-  };
-  if (b0 + NB < b1) prefetch_step(b0 + NB);
+  stamp();
   load_and_invert_blocks(Q, ldq, b0, b1, W, w, lane);
+  stamp();
+  const bool mine = tid < span && b0 + tid < b1;          // warp w owns block w of the panel
+  float qv[NB];
+  // Q[u0 + k, b0 + tid], k < 32, for the blocks right of u0.  Warp-uniform branch and a running pointer: with 32 warps in
+  // the CTA, per-element predicates and 64-bit address arithmetic executed by every warp (also the idle ones) cost
+  // 5.3 k cycles per step (clock64 stamps, tools/trsv_stamps.py) against 0.5 k for everything else.
+  auto load_rows = [&](int u0) {
+    if (b0 + w * NB < u0 + NB || w * NB >= span) return;
+    const int kmax = b1 - u0 < NB ? b1 - u0 : NB;
+    const float* q = Q + (size_t)u0 * ldq + b0 + tid;
+#pragma unroll
+    for (int k = 0; k < NB; ++k, q += ldq) qv[k] = (k < kmax && mine) ? *q : 0.f;
+  };
   __syncthreads();
+  stamp();
+  load_rows(b0);
   for (int u0 = b0; u0 < b1; u0 += NB) {
-    const int col = u0 + lane;
-    const int its = (u0 - b0) / NB;
-    float acc = 0.f;
-#pragma unroll
-    for (int i = 0; i < kPanelBlocks - 1; ++i)
-      if (i < its) acc = fmaf(qv[i], xs[w + NB * i], acc);
-    if (u0 + NB < b1) prefetch_step(u0 + NB);
-    red[w * XP + lane] = acc;
-    __syncthreads();
+    stamp();
     if (w == 0) {
-      float sa = 0.f, sb = 0.f;
-#pragma unroll
-      for (int r = 0; r < NB; r += 2) { sa += red[r * XP + lane]; sb += red[(r + 1) * XP + lane]; }
-      bs[lane] = xs[u0 - b0 + lane] - (sa + sb);
-      __syncwarp();
       const float* Wb = W + ((u0 - b0) / NB) * NB * NB;
+      const float* bs = xs + (u0 - b0);
       float x0 = 0.f, x1 = 0.f;
 #pragma unroll
       for (int k = 0; k < NB; k += 2) {                  // Wb[k][lane] = 0 for k > lane
@@ -545,11 +546,23 @@ __global__ void __launch_bounds__(1024) trsv_panel_kernel(const float* __restric
         x1 = fmaf(Wb[(k + 1) * NB + lane], bs[k + 1], x1);
       }
       const float x = x0 + x1;
-      xs[u0 - b0 + lane] = x;
-      if (col < b1) X[col] = x;
+      xn[lane] = x;
+      if (u0 + lane < b1) X[u0 + lane] = x;
     }
+    stamp();
+    __syncthreads();
+    stamp();
+    if (mine && b0 + w * NB >= u0 + NB) {
+      float acc = xs[tid];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) acc = fmaf(-qv[k], xn[k], acc);
+      xs[tid] = acc;
+    }
+    if (u0 + NB < b1) load_rows(u0 + NB);
+    stamp();
     __syncthreads();
   }
+  stamp();
 }
 
 static DeviceOnce trsm_attr_done;
@@ -599,7 +612,7 @@ int trsv_left_upper_adjoint(psgd_ctx* ctx, const float* Q, int ldq, const float*
       PSGD_RETURN_IF(ks::col_wsum(ctx, 1, nullptr, x, Q + p0, ldq, p0, p1 - p0, ws + kPanel, ws));
       sub = ws;
     }
-    trsv_panel_kernel<<<1, 1024, kTrsvSmem, ctx->stream>>>(Q, ldq, b, x, p0, p1, sub);
+    trsv_panel_kernel<<<1, 1024, kTrsvSmem, ctx->stream>>>(Q, ldq, b, x, p0, p1, sub, p0 == 0 ? ctx->opt_stamp_ptr : nullptr);
     PSGD_LAUNCH_CHECK(ctx);
   }
   return PSGD_OK;
