@@ -338,19 +338,32 @@ constexpr size_t kTrsmSmem =
 
 // In-place inverse of one upper-triangular 32 x 32 block held in shared memory (row-major, pitch 32), by one warp:
 // lane c solves U x = e_c from the last row up; row i of U is dead once every lane has used it, so x_i overwrites it.
-// The reciprocals of the diagonal are formed by all lanes at once and the dot product runs as two independent chains.
+// The reciprocals of the diagonal are formed by all lanes at once.  Row i is read as 128-bit loads, four at a time, ahead
+// of the FMAs that use them, and the dot product runs as four independent chains: with one scalar load in front of
+// each FMA (what the compiler emits for the plain loop under the 64-register cap of a 1024-thread CTA) the 496 FMAs cost
+// a shared-memory round trip each -- 17.2 k cycles per block, as much as all 16 block steps of a panel (clock64 stamps).
 __device__ __forceinline__ void invert_block_warp(float* U, int lane) {
   const float rdiag = 1.0f / U[lane * NB + lane];
   float x[NB];
 #pragma unroll
   for (int i = NB - 1; i >= 0; --i) {
-    float sa = (i == lane) ? 1.f : 0.f, sb = 0.f;
+    float s0 = (i == lane) ? 1.f : 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
 #pragma unroll
-    for (int k = i + 1; k < NB; k += 2) {
-      sa = fmaf(-U[i * NB + k], x[k], sa);
-      if (k + 1 < NB) sb = fmaf(-U[i * NB + k + 1], x[k + 1], sb);
+    for (int h = 0; h < 2; ++h) {                        // columns 16 h .. 16 h + 15 of row i
+      float4 u[4];
+#pragma unroll
+      for (int g = 0; g < 4; ++g)
+        if (16 * h + 4 * g + 3 > i) u[g] = *reinterpret_cast<const float4*>(U + i * NB + 16 * h + 4 * g);
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        const int k = 16 * h + 4 * g;
+        if (k + 0 > i) s0 = fmaf(-u[g].x, x[k + 0], s0);
+        if (k + 1 > i) s1 = fmaf(-u[g].y, x[k + 1], s1);
+        if (k + 2 > i) s2 = fmaf(-u[g].z, x[k + 2], s2);
+        if (k + 3 > i) s3 = fmaf(-u[g].w, x[k + 3], s3);
+      }
     }
-    x[i] = (sa + sb) * __shfl_sync(0xffffffffu, rdiag, i);
+    x[i] = ((s0 + s1) + (s2 + s3)) * __shfl_sync(0xffffffffu, rdiag, i);
     __syncwarp();
     U[i * NB + lane] = x[i];
   }
@@ -358,18 +371,31 @@ __device__ __forceinline__ void invert_block_warp(float* U, int lane) {
 }
 
 // Diagonal blocks of Q[b0 : b1, b0 : b1] -> W (block t at W + t * 1024), upper triangles only; rows / columns beyond b1
-// are padded with the identity.  Warps 0 .. blocks-1 work, the others fall through.
+// are padded with the identity.  Warps 0 .. blocks-1 work, the others fall through.  The 32 loads of a lane are
+// unconditional (clamped addresses, masked afterwards) so that they are all in flight together: as predicated loads
+// feeding a store each they went out one L2 round trip at a time, 14 k cycles per block.
 __device__ __forceinline__ void load_and_invert_blocks(const float* __restrict__ Q, int ldq, int b0, int b1, float* W,
                                                        int warp, int lane) {
   const int blocks = (b1 - b0 + NB - 1) / NB;
   if (warp < blocks) {
     float* U = W + warp * NB * NB;
     const int d0 = b0 + warp * NB;
-#pragma unroll 8
-    for (int i = 0; i < NB; ++i) {
-      float v = (i == lane) ? 1.f : 0.f;
-      if (d0 + i < b1 && d0 + lane < b1) v = (lane >= i) ? Q[(size_t)(d0 + i) * ldq + d0 + lane] : 0.f;
-      U[i * NB + lane] = v;
+    const int col = d0 + lane < b1 ? d0 + lane : b1 - 1;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float v[NB / 2];
+#pragma unroll
+      for (int j = 0; j < NB / 2; ++j) {
+        const int i = h * (NB / 2) + j;
+        const int row = d0 + i < b1 ? d0 + i : b1 - 1;
+        v[j] = Q[(size_t)row * ldq + col];
+      }
+#pragma unroll
+      for (int j = 0; j < NB / 2; ++j) {
+        const int i = h * (NB / 2) + j;
+        const bool in = d0 + i < b1 && d0 + lane < b1;
+        U[i * NB + lane] = in ? (lane >= i ? v[j] : 0.f) : (i == lane ? 1.f : 0.f);
+      }
     }
     __syncwarp();
     invert_block_warp(U, lane);
