@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(1024) gemm_small_kernel(Gemm g) {
   // Tile traffic of this thread: two elements of A and two of B per step.  Everything that does not change from step
   // to step (global pointer, K offset, validity of the row / column, slot in shared memory) is worked out once per
   // product -- with 1024 threads the address arithmetic of a generic fetch costs more issue slots than the multiply.
-  // The subtracted product is negated on its way in, so the multiply loop never looks at a sign.
+  // The subtracted product is negated on its way into shared memory, so the multiply loop never looks at a sign.
   const float* pa[2]; const float* pb[2];
   int ka[2], kb[2], sa[2], sb[2];
   bool oka[2], okb[2];
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(1024) gemm_small_kernel(Gemm g) {
     if (fs == steps0 && steps1 > 0) setup(g.A2, g.lda2, g.ta2, g.B2, g.ldb2, g.tb2, g.K2, -1.f);
 #pragma unroll
     for (int e = 0; e < 2; ++e) {
-      ra[e] = (oka[e] && knext + ka[e] < kdim) ? sgn * *pa[e] : 0.f;
+      ra[e] = (oka[e] && knext + ka[e] < kdim) ? *pa[e] : 0.f;
       rb[e] = (okb[e] && knext + kb[e] < kdim) ? *pb[e] : 0.f;
       pa[e] += stride_a; pb[e] += stride_b;
     }
@@ -224,13 +224,15 @@ __global__ void __launch_bounds__(1024) gemm_small_kernel(Gemm g) {
   if (steps > 0) {
     fetch();
 #pragma unroll
-    for (int e = 0; e < 2; ++e) { tiles[sa[e]] = ra[e]; tiles[sb[e]] = rb[e]; }
+    for (int e = 0; e < 2; ++e) { tiles[sa[e]] = sgn * ra[e]; tiles[sb[e]] = rb[e]; }
   }
   __syncthreads();
   for (int s = 0; s < steps; ++s) {
     const bool more = s + 1 < steps;
     if (more) fetch();                                    // in flight during the multiply below
-    const int da[2] = {sa[0], sa[1]}, db[2] = {sb[0], sb[1]};   // slots of the step just fetched (product switch)
+    const int da[2] = {sa[0], sa[1]}, db[2] = {sb[0], sb[1]};   // slots and sign of the step just fetched (product switch);
+    const float sg = sgn;                                       // the sign goes on at the stash: nothing may depend
+                                                                // on the loads before the multiply below has been issued
 #pragma unroll
     for (int kk = 0; kk < 4; ++kk) {
       const int k = 4 * kq + kk;
@@ -245,7 +247,7 @@ __global__ void __launch_bounds__(1024) gemm_small_kernel(Gemm g) {
     __syncthreads();
     if (more) {
 #pragma unroll
-      for (int e = 0; e < 2; ++e) { tiles[da[e]] = ra[e]; tiles[db[e]] = rb[e]; }
+      for (int e = 0; e < 2; ++e) { tiles[da[e]] = sg * ra[e]; tiles[db[e]] = rb[e]; }
       __syncthreads();
     }
   }
@@ -409,8 +411,11 @@ __device__ __forceinline__ void load_and_invert_blocks(const float* __restrict__
 // with Wtt = Qtt^-1 and k over the earlier blocks of the panel.
 template <bool LEFT>
 __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restrict__ Q, int ldq, const float* B, int ldb,
-                                                          float* X, int ldx, int m, int b0, int b1) {
+                                                          float* X, int ldx, int m, int b0, int b1, long long* stamps) {
   extern __shared__ __align__(16) float trsm_smem[];
+  int nstamp = 0;
+  auto stamp = [&]() { if (stamps && threadIdx.x == 0 && blockIdx.x == 0) stamps[nstamp++] = clock64(); };   // tools/trsv_stamps.py
+  stamp();
   float* W = trsm_smem;                                   // [blocks][32][32]   inverted diagonal blocks
   float* Xs = W + kPanelBlocks * NB * NB;                 // [unknown][XP]      right-hand side, then the solution
   float* Qs = Xs + kPanel * XP;                           // [2][KT][32]        Qs[k][u] = Q[k0+k, u0+u]
@@ -430,7 +435,9 @@ __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restric
     for (int t = lane; t < span; t += 32)
       Xs[t * XP + w] = (b0 + t < b1 && s0 + w < m) ? B[at(b0 + t, w, ldb)] : 0.f;
   }
+  stamp();
   load_and_invert_blocks(Q, ldq, b0, b1, W, w, lane);
+  stamp();
 
   // multiply role: K quarter kg, unknowns 4 ug .. 4 ug + 3 of the block, slab position = lane
   const int kg = w >> 3, ug = w & 7;
@@ -451,6 +458,7 @@ __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restric
   int buf = 0;
   __syncthreads();
   for (int u0 = b0; u0 < b1; u0 += NB) {
+    stamp();
     float acc[4] = {0.f, 0.f, 0.f, 0.f};
     for (int k0 = b0; k0 < u0; k0 += KT) {
       float* Qb = Qs + buf * KT * NB;
@@ -471,6 +479,7 @@ __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restric
       }
       buf ^= 1;
     }
+    stamp();
     const int to = u0 - b0 + ou;                          // this thread's unknown inside the panel (output role)
     float bval = Xs[to * XP + os];
     if (u0 > b0) {
@@ -501,6 +510,7 @@ __global__ void __launch_bounds__(1024) trsm_panel_kernel(const float* __restric
     const float x = (pp[0] + pp[NB * XP]) + (pp[2 * NB * XP] + pp[3 * NB * XP]);
     Xs[to * XP + os] = x;
     if (u0 + ou < b1 && os_ok) X[at(u0 + ou, os, ldx)] = x;
+    stamp();
     // every later use of Xs / Bs / Ps sits behind the barrier that follows the next tile stash
   }
 }
@@ -607,7 +617,7 @@ int trsm_left_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int 
   PSGD_REQUIRE(ib1 - ib0 <= kPanel, PSGD_ERR_BAD_SHAPE, "trsm panel of %d rows", ib1 - ib0);
   PSGD_RETURN_IF(ensure_trsm_attrs(ctx));
   ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (ib1 - ib0) * (ib1 - ib0));
-  trsm_panel_kernel<true><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, ib0, ib1);
+  trsm_panel_kernel<true><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, ib0, ib1, ctx->opt_stamp_ptr);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -617,7 +627,7 @@ int trsm_right_block(psgd_ctx* ctx, const float* Q, int ldq, const float* B, int
   PSGD_REQUIRE(jb1 - jb0 <= kPanel, PSGD_ERR_BAD_SHAPE, "trsm panel of %d columns", jb1 - jb0);
   PSGD_RETURN_IF(ensure_trsm_attrs(ctx));
   ProfScope prof(ctx, PSGD_K_TRSM, (double)m * (jb1 - jb0) * (jb1 - jb0));
-  trsm_panel_kernel<false><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, jb0, jb1);
+  trsm_panel_kernel<false><<<(m + NB - 1) / NB, 1024, kTrsmSmem, ctx->stream>>>(Q, ldq, B, ldb, X, ldx, m, jb0, jb1, ctx->opt_stamp_ptr ? ctx->opt_stamp_ptr + 128 : nullptr);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }

@@ -93,7 +93,22 @@ def vec():
     errs["diag"] = cases.rel_err(q.cpu().numpy(), O.update_precond_diag(x["a"], x["v"], x["h"], 0.01))
 
 
-jobs = {"uvd_tma": lambda: uvd(0), "uvd_direct": lambda: uvd(1), "kron_ts": lambda: kron_tc(1), "kron_ss": lambda: kron_tc(0), "kron_pair": kron_pair,
+def small():
+    """SIMT engine of csrc/linalg.cu (panel solves, small GEMM) and the dense preconditioner's scans + vector solve."""
+    for M, N in ((257, 120), (70, 545), (33, 1)):
+        c = cases.kron_case(11, "dense", "dense", M, N)
+        ql, qr = psgd.update_precond_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["dX"]), dev(c["dG"]), 0.01)
+        pre = psgd.precond_grad_kron(ql, qr, dev(c["G"]))
+        qlr, qrr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
+        errs[f"kron_small_{M}x{N}"] = max(cases.rel_err(ql.cpu().numpy(), qlr), cases.rel_err(qr.cpu().numpy(), qrr),
+                                          cases.rel_err(pre.cpu().numpy(), O.precond_grad_kron(qlr, qrr, c["G"])))
+    for n in (33, 700):
+        c = cases.dense_case(12 + n, [(n,)])
+        Qn = psgd.update_precond_dense(dev(c["Q"]), [dev(x) for x in c["dxs"]], [dev(x) for x in c["dgs"]], 0.01)
+        errs[f"dense_update_{n}"] = cases.rel_err(Qn.cpu().numpy(), O.update_precond_dense(c["Q"], c["dxs"], c["dgs"], 0.01))
+
+
+jobs = {"small": small, "uvd_tma": lambda: uvd(0), "uvd_direct": lambda: uvd(1), "kron_ts": lambda: kron_tc(1), "kron_ss": lambda: kron_tc(0), "kron_pair": kron_pair,
         "kron_stream": kron_stream, "splu": splu, "vec": vec}
 for name, fn in jobs.items():
     if which in ("all", name):

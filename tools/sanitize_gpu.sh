@@ -4,7 +4,7 @@
 OUT=${1:-gpurun_out/sanitize}
 mkdir -p "$OUT"
 SAN=/usr/local/cuda/bin/compute-sanitizer
-for job in uvd_tma uvd_direct kron_ts kron_ss kron_pair kron_stream splu vec; do
+for job in ${JOBS:-small uvd_tma uvd_direct kron_ts kron_ss kron_pair kron_stream splu vec}; do
   for tool in memcheck racecheck; do
     timeout 420 $SAN --tool $tool --print-limit 20 --log-file "$OUT/${tool}_${job}.log" \
       python tools/sanitize_cases.py $job > "$OUT/${tool}_${job}.out" 2>&1
