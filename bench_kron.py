@@ -75,16 +75,30 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         pool.append((dX, dG, G))
     shapes = [(n, n)] * L
 
-    gbuf = partition.KronGatherBuffer(shapes, owned, rank, dev) if world > 1 else None
+    gmode = getattr(args, "kron_gather", "once")
+    gbuf = None
+    if world > 1:
+        gbuf = (partition.KronPeerGather if gmode.startswith("peer") else partition.KronGatherBuffer)(shapes, owned, rank, dev)
 
     def step(i, Ql, Qr, dX, dG, G):
         new = psgd.update_precond_kron_batched(Ql, Qr, dX, dG, 0.01)
         Ql2, Qr2 = [a for a, _ in new], [b for _, b in new]
         if gbuf is None:
             return Ql2, Qr2, psgd.precond_grad_kron_batched(Ql2, Qr2, G)
-        # the apply writes straight into this rank's slice of the gather buffer; ONE in-place all-gather follows
-        psgd.precond_grad_kron_batched(Ql2, Qr2, G, outs=gbuf.local_outs())
-        return Ql2, Qr2, gbuf.gather()
+        # the apply writes straight into this rank's entries of the gather buffer (no torch.stack, no staging copy)
+        outs = gbuf.local_outs()
+        if gmode == "once":          # whole batched apply, then ONE in-place NCCL all-gather
+            psgd.precond_grad_kron_batched(Ql2, Qr2, G, outs=outs)
+            return Ql2, Qr2, gbuf.gather()
+        if gmode == "peer-once":     # whole batched apply, then copy-engine pushes to every peer
+            psgd.precond_grad_kron_batched(Ql2, Qr2, G, outs=outs)
+            return Ql2, Qr2, gbuf.gather()
+        # layer by layer, each followed by the transfer of its slot, which runs under the apply of the next layer:
+        # "slots" = NCCL all-gather per slot, "peer" = copy-engine pushes per slot
+        for j in range(len(outs)):
+            psgd.precond_grad_kron_batched(Ql2[j:j + 1], Qr2[j:j + 1], G[j:j + 1], outs=outs[j:j + 1])
+            gbuf.push_slot(j) if gmode == "peer" else gbuf.gather_slot(j)
+        return Ql2, Qr2, gbuf.finish()
 
     def barrier():
         if world > 1:
@@ -118,6 +132,20 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
     ms = float(t.item())
     assert all(torch.isfinite(p).all() for p in pre[:1])
     value = args.steps / (ms / 1e3)
+    gather_check = None
+    if world > 1:
+        # every rank holds every layer's result after the gather: per-layer float64 checksums of what each OWNER
+        # computed against the checksums of what arrived here (bit-exact transfer => equal sums)
+        mine_sums = torch.stack([pre[li].double().sum() for li in mine])
+        all_sums = [torch.empty_like(mine_sums) for _ in range(world)]
+        dist.all_gather(all_sums, mine_sums)
+        want = torch.empty(L, dtype=torch.float64, device=dev)
+        for k, layer_ids in enumerate(owned):
+            for j, li in enumerate(layer_ids):
+                want[li] = all_sums[k][j]
+        got = torch.stack([p.double().sum() for p in pre])
+        gather_check = bool(torch.equal(got, want))
+        assert gather_check, "all-gathered preconditioned gradients differ from their owners' results"
 
     # ---- roofline: tensor pipe, 3xTF32 => ceiling = measured TF32 GEMM peak / 3 ---------------------
     tf32, tf32_sus = tf32_peak_tflops(torch)
@@ -256,7 +284,9 @@ def run_kron(args, rank, world, local, METRIC, UNIT, load_peaks, ClockSampler):
         metric=METRIC, value=round(value, 4), unit=UNIT, n_gpus=world, steps=args.steps, warmup=args.warmup,
         ms_per_step=round(ms / args.steps, 3), higher_is_better=True, scaling="strong", vs_baseline=None,
         dtype="f32 (3xTF32 tensor-core products, fp32 accumulate)", data="synthetic",
-        config=kron_config(L, n, world), run=dict(layers_per_gpu=len(mine)), parity=parity,
+        config=kron_config(L, n, world),
+        run=dict(layers_per_gpu=len(mine), gather=gmode if world > 1 else None,
+                 gather_checksums_match=gather_check), parity=parity,
         roofline=roofline, kernels=kernels, launches_of_one_step=by_launch, cpu_baseline=cpu, e2e=e2e,
         gpu_launches=int(launches), clocks=clk)
 

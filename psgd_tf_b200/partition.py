@@ -146,34 +146,119 @@ def kron_layer_cost(M: int, N: int, kind_l: int = 0, kind_r: int = 0) -> float:
 
 class KronGatherBuffer:
     """In-place all-gather of a UNIFORM layer-sharded Kron stack (every layer the same shape, every rank the same number
-    of layers): one ``[world * per, M, N]`` buffer per rank; ``local_outs()`` are views of this rank's slice of it, to be
-    passed as ``outs=`` to :func:`psgd_tf_b200.precond_grad_kron_batched` so the apply's last product writes its result
-    where NCCL sends it from -- no ``torch.stack``, no staging copy -- and ``gather()`` is ONE in-place
-    ``all_gather_into_tensor`` (input = the rank's own slice of the output).  Two buffers alternate so that the result of
-    step t stays valid while step t+1 is being computed."""
+    of layers ``per``).  One ``[per, world, M, N]`` buffer per rank, slot-major: ``local_outs()`` are views of this
+    rank's entries ``[j, rank]``, to be passed as ``outs=`` to :func:`psgd_tf_b200.precond_grad_kron_batched` so the
+    apply's last product writes its result where NCCL sends it from -- no ``torch.stack``, no staging copy.
+
+    ``gather_slot(j)`` issues the in-place ``all_gather_into_tensor`` of slot ``j`` (the j-th layer of every rank,
+    contiguous in the buffer) asynchronously, as soon as the apply of that layer has been enqueued: NCCL's stream waits
+    for the compute stream at that point only, so the transfer of slot j runs while slot j+1 is being applied.
+    ``finish()`` joins the compute stream with all of them and returns every layer's result.  ``gather()`` = all slots,
+    then ``finish()``.  Two buffers alternate so that the result of step t stays valid while step t+1 is being computed."""
 
     def __init__(self, shapes, owned, rank: int, device, nbuf: int = 2):
         if len({tuple(s) for s in shapes}) != 1 or len({len(o) for o in owned}) != 1:
             raise ValueError("KronGatherBuffer: needs a uniform stack (use all_gather_layers for ragged ones)")
-        self.owned, self.rank, self.per = owned, rank, len(owned[0])
+        self.owned, self.rank, self.per, self.world = owned, rank, len(owned[0]), len(owned)
         self.shape = tuple(shapes[0])
-        self.bufs = [torch.empty((len(owned) * self.per,) + self.shape, device=device, dtype=torch.float32) for _ in range(nbuf)]
+        self.bufs = [torch.empty((self.per, self.world) + self.shape, device=device, dtype=torch.float32) for _ in range(nbuf)]
+        self.cur = 0
+        self._works = []
+
+    def local_outs(self):
+        self.cur = (self.cur + 1) % len(self.bufs)
+        b = self.bufs[self.cur]
+        return [b[j, self.rank] for j in range(self.per)]
+
+    def gather_slot(self, j: int, group=None):
+        import torch.distributed as dist
+        b = self.bufs[self.cur]
+        # flat views: concatenation along dim 0 is the one layout every backend accepts (gloo rejects the stacked form)
+        self._works.append(dist.all_gather_into_tensor(b[j].view(-1), b[j, self.rank].view(-1), group=group, async_op=True))
+
+    def finish(self):
+        for w in self._works:
+            w.wait()
+        self._works = []
+        b = self.bufs[self.cur]
+        full = [None] * (self.world * self.per)
+        for k, layer_ids in enumerate(self.owned):
+            for j, li in enumerate(layer_ids):
+                full[li] = b[j, k]
+        return full
+
+    def gather(self, group=None):
+        for j in range(self.per):
+            self.gather_slot(j, group)
+        return self.finish()
+
+
+class KronPeerGather:
+    """All-gather of a uniform layer-sharded Kron stack by COPY ENGINES over NVLink: no SMs, so the transfer of layer j
+    really runs under the apply of layer j+1 (an NCCL all-gather needs SMs that the persistent GEMM kernels hold, and a
+    GEMM launch that finds some of its SMs taken ends late by the collective's duration).
+
+    One process per GPU on one NVSwitch box.  Every rank allocates ``[world, per, M, N]`` buffers (rank-major: rank k's
+    layers at ``[k]``), exports them with CUDA IPC (``torch.multiprocessing.reductions.reduce_tensor``; handles exchanged
+    once through ``all_gather_object``) and maps every peer's buffers.  ``local_outs()`` are this rank's entries of its
+    own buffer (``outs=`` of the batched apply); ``push_slot(j)`` enqueues, on side streams that wait for the compute
+    stream at that point only, one contiguous device-to-device copy of layer j into every peer's buffer;
+    ``finish()`` closes the step with a tiny all-reduce enqueued behind the copies -- no rank gets past it before every
+    rank's copies have landed -- joins the compute stream and returns every layer's result.  Two buffers alternate: a peer
+    that is one step ahead writes into the other one."""
+
+    def __init__(self, shapes, owned, rank: int, device, nbuf: int = 2, group=None, push_streams: int = 2):
+        import torch.distributed as dist
+        from torch.multiprocessing.reductions import reduce_tensor
+        if len({tuple(s) for s in shapes}) != 1 or len({len(o) for o in owned}) != 1:
+            raise ValueError("KronPeerGather: needs a uniform stack (use all_gather_layers for ragged ones)")
+        self.owned, self.rank, self.per, self.world, self.group = owned, rank, len(owned[0]), len(owned), group
+        self.shape = tuple(shapes[0])
+        self.bufs = [torch.empty((self.world, self.per) + self.shape, device=device, dtype=torch.float32) for _ in range(nbuf)]
+        self.peers = []                                   # peers[b][k]: rank k's buffer b, mapped here
+        for b in self.bufs:
+            exported = [None] * self.world
+            dist.all_gather_object(exported, reduce_tensor(b), group=group)
+            self.peers.append([b if k == rank else fn(*a) for k, (fn, a) in enumerate(exported)])
+        self.streams = [torch.cuda.Stream(device=device) for _ in range(push_streams)]
+        self.flag = torch.zeros(1, device=device)
         self.cur = 0
 
     def local_outs(self):
         self.cur = (self.cur + 1) % len(self.bufs)
         b = self.bufs[self.cur]
-        return [b[self.rank * self.per + j] for j in range(self.per)]
+        return [b[self.rank, j] for j in range(self.per)]
 
-    def gather(self, group=None):
+    def push_slot(self, j: int):
+        ready = torch.cuda.current_stream().record_event()
+        src = self.bufs[self.cur][self.rank, j]
+        for s in self.streams:
+            s.wait_event(ready)
+        for i in range(self.world - 1):                   # staggered: not every rank starts on the same destination
+            dst = self.peers[self.cur][(self.rank + 1 + i) % self.world]
+            with torch.cuda.stream(self.streams[i % len(self.streams)]):
+                dst[self.rank, j].copy_(src, non_blocking=True)
+
+    def finish(self):
         import torch.distributed as dist
+        s0 = self.streams[0]
+        for s in self.streams[1:]:
+            s0.wait_event(s.record_event())
+        with torch.cuda.stream(s0):
+            dist.all_reduce(self.flag, group=self.group)            # behind this rank's copies; completes when all ranks joined
+            done = s0.record_event()
+        torch.cuda.current_stream().wait_event(done)
         b = self.bufs[self.cur]
-        dist.all_gather_into_tensor(b, b[self.rank * self.per:(self.rank + 1) * self.per], group=group)
-        full = [None] * (len(self.owned) * self.per)
+        full = [None] * (self.world * self.per)
         for k, layer_ids in enumerate(self.owned):
             for j, li in enumerate(layer_ids):
-                full[li] = b[k * self.per + j]
+                full[li] = b[k, j]
         return full
+
+    def gather(self):
+        for j in range(self.per):
+            self.push_slot(j)
+        return self.finish()
 
 
 def all_gather_layers(outs_local: Sequence[torch.Tensor], owned: List[List[int]], shapes: Sequence[Tuple[int, int]],

@@ -246,6 +246,31 @@ def gpu_kron(rank, world):
             want = O.precond_grad_kron(ql, qr, c["G"])
             e = cases.rel_err(full[i].cpu().numpy(), want)
             assert e < 1e-5, (shapes[i], e)
+        if len({tuple(sh) for sh in shapes}) != 1 or len({len(o) for o in owned}) != 1:
+            continue
+        # uniform stack: the in-place gather buffers (NCCL per slot; copy-engine pushes into IPC-mapped peer buffers), the
+        # apply writing straight into them, three steps in a row so that both alternating buffers are used twice
+        for cls, overlapped in ((partition.KronGatherBuffer, False), (partition.KronGatherBuffer, True),
+                                (partition.KronPeerGather, False), (partition.KronPeerGather, True)):
+            gb = cls(shapes, owned, rank, torch.device("cuda", rank))
+            Ql, Qr = [a for a, _ in new], [b for _, b in new]
+            for rep in range(3):
+                G = [dev(cs[i]["G"] * (1.0 + rep)) for i in mine]
+                outs = gb.local_outs()
+                if overlapped:
+                    for j in range(len(outs)):
+                        psgd.precond_grad_kron_batched(Ql[j:j + 1], Qr[j:j + 1], G[j:j + 1], outs=outs[j:j + 1])
+                        gb.push_slot(j) if cls is partition.KronPeerGather else gb.gather_slot(j)
+                    full = gb.finish()
+                else:
+                    psgd.precond_grad_kron_batched(Ql, Qr, G, outs=outs)
+                    full = gb.gather()
+                for i, c in enumerate(cs):
+                    ql, qr = O.update_precond_kron(c["Ql"], c["Qr"], c["dX"], c["dG"], 0.01)
+                    want = O.precond_grad_kron(ql, qr, c["G"] * np.float32(1.0 + rep))
+                    e = cases.rel_err(full[i].cpu().numpy(), want)
+                    assert e < 1e-5, (cls.__name__, overlapped, rep, i, e)
+            dist.barrier()
 
 
 def main():
