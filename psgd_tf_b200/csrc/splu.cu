@@ -22,6 +22,10 @@
 // r <= 32 (the reference's demo uses r = 10, demo_usage_of_all_preconditioners.py:45).
 #include <math.h>
 
+#include <mutex>
+#include <set>
+#include <utility>
+
 #include "common.cuh"
 
 namespace psgd {
@@ -135,80 +139,131 @@ __global__ void __launch_bounds__(32) small0_kernel(Args a, const float* __restr
   if (lane == 0) { st->rho = rho; st->maxL = 0.f; st->maxU = 0.f; }
 }
 
-// L2 is [m, r] row-major: a thread that walks its own row touches r scattered 4-byte words (one 128-byte line per ~3
-// rows), so every load instruction of a warp spans ~10 lines.  Instead a block stages the 256 consecutive rows of its
-// tile -- one contiguous run of 256 r floats -- into shared memory with fully coalesced loads (balanced by 1/rho on the
-// way in when updating), and threads then read (and in pass 4 rewrite) their rows there.
+// Everything a pass reads per parameter index j -- the row L2[j, :], the column U2[:, j], and up to NV vectors -- goes
+// through ONE multi-stage cp.async ring in shared memory (SASS LDGSTS: no registers, no use-stall): tile t + S - 1 is
+// streaming in while tile t is consumed, so the passes run at the rate the loads can be ISSUED, not at one DRAM latency
+// per tile (round 1: direct loads, 16 resident warps per SM each stalled on its own 14 loads -- 30-53 % of HBM).
+//   * L2 is [m, r] row-major: a thread that walked its own row would touch r scattered words (one 128-byte line per ~3
+//     rows); the tile's 256 consecutive rows are one contiguous run of 256 r floats, copied fully coalesced (16 bytes at a
+//     time when the run is aligned) and read back row-wise from shared memory (pass 4 also rewrites them there and
+//     stores the run contiguously);
+//   * U2 is [r, n] row-major: r coalesced 4-byte copies per thread, laid out [k][thread];
+//   * vectors: one 4-byte copy each, laid out [v][thread].
+// Values are staged raw; the reader applies the balancing factor.  One block barrier per tile: after it every thread
+// has finished tile t - 1, whose stage is exactly the one the copies of tile t + S - 1 go to.
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory"); }
 
-// Row tiles of L2 in shared memory, filled by cp.async (SASS LDGSTS: no registers, no use-stall) and double-buffered for
-// r <= 16, so the next tile streams in while the current one is consumed (one exposed DRAM latency per tile instead of
-// two).  Values are staged raw; the reader applies the balancing 1/rho.
-// acquire() and release() contain the block barriers: EVERY thread of the block must call each exactly once per tile, from
-// the same (non-divergent) place -- rows that do not exist are skipped inside an `if`, never with `continue`.
 template <int RM>
-struct RowTiles {
-  static constexpr int NBUF = RM <= 16 ? 2 : 1;
-  static constexpr int kFloats = NBUF * kThreads * RM;
-  float* buf;
-  const float* src;
-  long long m, stride;
-  int r, cur;
+constexpr int ring_stages() { return RM <= 16 ? 3 : 2; }
+
+template <int RM, int NV>
+struct Ring {
+  static constexpr int S = ring_stages<RM>();
+  static constexpr int kStageFloats = kThreads * (2 * RM + NV);
+  static constexpr size_t kBytes = (size_t)S * kStageFloats * sizeof(float);
+  float* base;
+  const float* L2;            // nullptr: the pass does not read L2
+  const float* U2;            // nullptr: the pass does not read U2
+  const float* vec[NV];       // already offset so that index j addresses parameter r + j; nullptr entries are skipped
+  long long m, n, first, stride;
+  int r, t;
+  bool l2_aligned;
+
+  __device__ __forceinline__ float* stage(int s) const { return base + s * kStageFloats; }
   __device__ __forceinline__ int rows_at(long long j0) const { return (int)(m - j0 < kThreads ? m - j0 : kThreads); }
-  __device__ __forceinline__ void issue(int b, long long j0) {
-    const float* p = src + (size_t)j0 * r;
-    float* t = buf + b * (kThreads * RM);
-    const int cnt = rows_at(j0) * r;                 // <= kThreads * RM: at most RM elements per thread
+  __device__ __forceinline__ void issue(int s, long long j0) {
+    if (j0 < m) {
+      float* st = stage(s);
+      const int rows = rows_at(j0);
+      if (L2) {
+        const float* p = L2 + (size_t)j0 * r;
+        const int cnt = rows * r;                       // <= kThreads * RM
+        if (l2_aligned && (cnt & 3) == 0) {
 #pragma unroll
-    for (int i = 0; i < RM; ++i) {
-      const int e = threadIdx.x + i * kThreads;
-      if (e < cnt) cp_async4(t + e, p + e);
+          for (int i = 0; i < (RM + 3) / 4; ++i) {
+            const int e = 4 * ((int)threadIdx.x + i * kThreads);
+            if (e < cnt) cp_async16(st + e, p + e);
+          }
+        } else {
+#pragma unroll
+          for (int i = 0; i < RM; ++i) {
+            const int e = threadIdx.x + i * kThreads;
+            if (e < cnt) cp_async4(st + e, p + e);
+          }
+        }
+      }
+      if ((int)threadIdx.x < rows) {
+        const long long j = j0 + threadIdx.x;
+        if (U2) {
+          float* uc = st + kThreads * RM + threadIdx.x;
+#pragma unroll
+          for (int k = 0; k < RM; ++k)
+            if (k < r) cp_async4(uc + k * kThreads, U2 + (size_t)k * n + j);
+        }
+        float* vv = st + kThreads * 2 * RM + threadIdx.x;
+#pragma unroll
+        for (int v = 0; v < NV; ++v)
+          if (vec[v]) cp_async4(vv + v * kThreads, vec[v] + j);
+      }
     }
-    cp_async_commit();
+    cp_async_commit();                                  // one group per slot, empty or not: the wait counts groups
   }
-  __device__ __forceinline__ void begin(float* smem, const float* L2, long long m_, int r_, long long j0) {
-    buf = smem; src = L2; m = m_; r = r_; cur = 0;
+  __device__ __forceinline__ void begin(float* smem, long long m_, long long n_, int r_) {
+    base = smem; m = m_; n = n_; r = r_; t = 0;
+    first = (long long)blockIdx.x * kThreads;
     stride = (long long)gridDim.x * kThreads;
-    if (j0 < m) issue(0, j0);
+    // a full tile is kThreads * r floats, a multiple of 4: every tile start is 16-byte aligned iff the array is
+    l2_aligned = L2 && (reinterpret_cast<uintptr_t>(L2) & 15u) == 0;
+    for (int s = 0; s < S - 1; ++s) issue(s, first + s * stride);
   }
-  // tile j0 becomes readable (and, when double-buffered, the next one starts streaming in first)
+  // Tile j0 (the t-th of this block) becomes readable; EVERY thread of the block calls this exactly once per tile.
   __device__ __forceinline__ float* acquire(long long j0) {
-    const long long nxt = j0 + stride;
-    if (NBUF == 2 && nxt < m) { issue(cur ^ 1, nxt); cp_async_wait<1>(); }
-    else cp_async_wait<0>();
+    cp_async_wait<S - 2>();
     __syncthreads();
-    return buf + cur * (kThreads * RM);
+    issue((t + S - 1) % S, j0 + (S - 1) * stride);
+    float* st = stage(t % S);
+    ++t;
+    return st;
   }
-  // every thread is done with tile j0
-  __device__ __forceinline__ void release(long long j0) {
-    __syncthreads();
-    if (NBUF == 2) cur ^= 1;
-    else if (j0 + stride < m) issue(0, j0 + stride);
-  }
+  // accessors into a stage
+  __device__ __forceinline__ static float* lrow(float* st, int r_) { return st + threadIdx.x * r_; }
+  __device__ __forceinline__ static const float* ucol(const float* st) { return st + kThreads * RM + threadIdx.x; }   // [k * kThreads]
+  __device__ __forceinline__ static float vecv(const float* st, int v) { return st[kThreads * 2 * RM + v * kThreads + threadIdx.x]; }
 };
 
 // ---- pass 1 / A1:  partial[b][k] = sum_j (rho U2[k, j]) w[j],  w = dg2 (update) or g2 (apply) ------------------------
 template <int RM>
 __global__ void __launch_bounds__(kThreads) pass1_kernel(Args a) {
+  extern __shared__ __align__(16) float ring_mem[];
   const long long m = a.n - a.r;
   const int r = a.r;
   const float rho = a.st->rho;
-  const float* U2 = a.U12 + r;
-  const float* w = a.dg + r;
+  Ring<RM, 1> ring;
+  ring.L2 = nullptr; ring.U2 = a.U12 + r; ring.vec[0] = a.dg + r;
+  ring.begin(ring_mem, m, a.n, r);
   float acc[RM];
 #pragma unroll
   for (int k = 0; k < RM; ++k) acc[k] = 0.f;
-  for (long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x; j < m; j += (long long)gridDim.x * blockDim.x) {
-    const float wj = w[j];
+  for (long long j0 = ring.first; j0 < m; j0 += ring.stride) {
+    const int rows = ring.rows_at(j0);
+    const float* st = ring.acquire(j0);
+    if ((int)threadIdx.x < rows) {
+      const float wj = ring.vecv(st, 0);
+      const float* uc = ring.ucol(st);
 #pragma unroll
-    for (int k = 0; k < RM; ++k)
-      if (k < r) acc[k] = fmaf(rho * U2[(size_t)k * a.n + j], wj, acc[k]);
+      for (int k = 0; k < RM; ++k)
+        if (k < r) acc[k] = fmaf(rho * uc[k * kThreads], wj, acc[k]);
+    }
   }
+  cp_async_wait<0>();
   block_reduce_to<RM>(acc, r, a.partial, 0);
 }
 
@@ -247,15 +302,16 @@ __global__ void __launch_bounds__(32) small1_kernel(Args a, int nblocks, int upd
 // apply (update = 0): Qg2 = L2 Ug1 + l3 u3 g2 (stored), partial L2^T Qg2                       psgd.py:507-512
 template <int RM>
 __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args a, int update) {
+  extern __shared__ __align__(16) float ring_mem[];
   const long long m = a.n - a.r;
   const int r = a.r;
   const State* st = a.st;
   const float rho = st->rho;
-  const float* L2 = a.L12 + (size_t)r * r;
-  const float* U2 = a.U12 + r;
-  __shared__ float tile_mem[RowTiles<RM>::kFloats];
-  RowTiles<RM> tiles;
-  tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);
+  Ring<RM, 4> ring;
+  ring.L2 = a.L12 + (size_t)r * r;
+  ring.U2 = update ? a.U12 + r : nullptr;
+  ring.vec[0] = a.l3; ring.vec[1] = a.u3; ring.vec[2] = a.dg + r; ring.vec[3] = update ? a.dx + r : nullptr;
+  ring.begin(ring_mem, m, a.n, r);
   float ug1[RM], iu1[RM], pa[RM], pb[RM];
 #pragma unroll
   for (int k = 0; k < RM; ++k) {
@@ -263,45 +319,42 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass2_kernel(Args 
     iu1[k] = (update && k < r) ? st->iUtx1[k] : 0.f;
     pa[k] = 0.f; pb[k] = 0.f;
   }
-  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
-    const int rows = tiles.rows_at(j0);
-    const float* tile = tiles.acquire(j0);
+  for (long long j0 = ring.first; j0 < m; j0 += ring.stride) {
+    const int rows = ring.rows_at(j0);
+    float* sg = ring.acquire(j0);
     if ((int)threadIdx.x < rows) {
-    const long long j = j0 + threadIdx.x;
-    // every global load of this row is issued before any arithmetic consumes one (ncu: interleaved, each use waited
-    // out its own DRAM latency)
-    float ucol[RM];
+      const long long j = j0 + threadIdx.x;
+      const float* tile = ring.lrow(sg, r);
+      const float* uc = ring.ucol(sg);
+      const float l3raw = ring.vecv(sg, 0), u3raw = ring.vecv(sg, 1), dgj = ring.vecv(sg, 2);
+      const float dxj = update ? ring.vecv(sg, 3) : 0.f;
+      const float l3 = update ? l3raw / rho : l3raw;
+      const float u3 = update ? rho * u3raw : u3raw;
+      float lrow[RM];
+      float dotL = 0.f, dotU = 0.f;
 #pragma unroll
-    for (int k = 0; k < RM; ++k) ucol[k] = (update && k < r) ? U2[(size_t)k * a.n + j] : 0.f;
-    const float l3raw = a.l3[j], u3raw = a.u3[j], dgj = a.dg[r + j];
-    const float dxj = update ? a.dx[r + j] : 0.f;
-    const float l3 = update ? l3raw / rho : l3raw;
-    const float u3 = update ? rho * u3raw : u3raw;
-    float lrow[RM];
-    float dotL = 0.f, dotU = 0.f;
-#pragma unroll
-    for (int k = 0; k < RM; ++k) {
-      if (k < r) {
-        lrow[k] = update ? tile[threadIdx.x * r + k] / rho : tile[threadIdx.x * r + k];
-        dotL = fmaf(lrow[k], ug1[k], dotL);
-        if (update) dotU = fmaf(rho * ucol[k], iu1[k], dotU);
+      for (int k = 0; k < RM; ++k) {
+        if (k < r) {
+          lrow[k] = update ? tile[k] / rho : tile[k];
+          dotL = fmaf(lrow[k], ug1[k], dotL);
+          if (update) dotU = fmaf(rho * uc[k * kThreads], iu1[k], dotU);
+        }
       }
-    }
-    const float Ug2 = u3 * dgj;                                            // :431 / :507
-    const float Qg2 = dotL + l3 * Ug2;                                     // :434 / :510
-    a.v0[j] = Qg2;
-    float iQtx2 = 0.f;
-    if (update) {
-      const float iUtx2 = (dxj - dotU) / u3;                               // :437
-      iQtx2 = iUtx2 / l3;                                                  // :439
-      a.v1[j] = iQtx2;
-    }
+      const float Ug2 = u3 * dgj;                                            // :431 / :507
+      const float Qg2 = dotL + l3 * Ug2;                                     // :434 / :510
+      a.v0[j] = Qg2;
+      float iQtx2 = 0.f;
+      if (update) {
+        const float iUtx2 = (dxj - dotU) / u3;                               // :437
+        iQtx2 = iUtx2 / l3;                                                  // :439
+        a.v1[j] = iQtx2;
+      }
 #pragma unroll
-    for (int k = 0; k < RM; ++k)
-      if (k < r) { pa[k] = fmaf(lrow[k], iQtx2, pa[k]); pb[k] = fmaf(lrow[k], Qg2, pb[k]); }
+      for (int k = 0; k < RM; ++k)
+        if (k < r) { pa[k] = fmaf(lrow[k], iQtx2, pa[k]); pb[k] = fmaf(lrow[k], Qg2, pb[k]); }
     }
-    tiles.release(j0);
   }
+  cp_async_wait<0>();
   block_reduce_to<RM>(pa, update ? r : 0, a.partial, 0);
   block_reduce_to<RM>(pb, r, a.partial, kMaxR);
 }
@@ -351,13 +404,12 @@ __global__ void __launch_bounds__(32) small2_kernel(Args a, int nblocks, int upd
 // apply (update = 0): out[r + j] = U2[:, j] . LtQg1 + u3 l3 Qg2                                   psgd.py:513-516
 template <int RM>
 __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args a, int update, float* __restrict__ out) {
+  extern __shared__ __align__(16) float ring_mem[];
   __shared__ float redm[kWarps][2];
   const long long m = a.n - a.r;
   const int r = a.r;
   State* st = a.st;
   const float rho = st->rho;
-  const float* L2 = a.L12 + (size_t)r * r;
-  const float* U2 = a.U12 + r;
   float lt1[RM], il1[RM], qg1[RM], iq1[RM], pg1[RM], dx1[RM], pc[RM];
 #pragma unroll
   for (int k = 0; k < RM; ++k) {
@@ -370,57 +422,59 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass3_kernel(Args 
     dx1[k] = (ok && update) ? st->dx1[k] : 0.f;
     pc[k] = 0.f;
   }
-  __shared__ float tile_mem[RowTiles<RM>::kFloats];
-  RowTiles<RM> tiles;
-  if (update) tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);     // the apply's third pass does not read L2
+  Ring<RM, 6> ring;
+  ring.L2 = update ? a.L12 + (size_t)r * r : nullptr;           // the apply's third pass does not read L2
+  ring.U2 = a.U12 + r;
+  ring.vec[0] = a.l3; ring.vec[1] = a.u3; ring.vec[2] = a.v0;
+  ring.vec[3] = update ? a.v1 : nullptr; ring.vec[4] = update ? a.dg + r : nullptr; ring.vec[5] = update ? a.dx + r : nullptr;
+  ring.begin(ring_mem, m, a.n, r);
   float mxL = 0.f, mxU = 0.f;
-  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
-    const int rows = (int)(m - j0 < kThreads ? m - j0 : kThreads);
-    const float* tile = update ? tiles.acquire(j0) : tile_mem;
+  for (long long j0 = ring.first; j0 < m; j0 += ring.stride) {
+    const int rows = ring.rows_at(j0);
+    float* sg = ring.acquire(j0);
     if ((int)threadIdx.x < rows) {
-    const long long j = j0 + threadIdx.x;
-    // all global loads of the row first (see pass 2)
-    float ucol[RM];
+      const long long j = j0 + threadIdx.x;
+      const float* tile = ring.lrow(sg, r);
+      const float* uc = ring.ucol(sg);
+      const float l3raw = ring.vecv(sg, 0), u3raw = ring.vecv(sg, 1), Qg2 = ring.vecv(sg, 2);
+      const float iQtx2 = update ? ring.vecv(sg, 3) : 0.f;
+      const float dgj = update ? ring.vecv(sg, 4) : 0.f, dxj = update ? ring.vecv(sg, 5) : 0.f;
+      const float l3 = update ? l3raw / rho : l3raw;
+      const float u3 = update ? rho * u3raw : u3raw;
+      float urow[RM];
+      float dotU = 0.f, dotL = 0.f;
 #pragma unroll
-    for (int k = 0; k < RM; ++k) ucol[k] = k < r ? U2[(size_t)k * a.n + j] : 0.f;
-    const float l3raw = a.l3[j], u3raw = a.u3[j], Qg2 = a.v0[j];
-    const float iQtx2 = update ? a.v1[j] : 0.f;
-    const float dgj = update ? a.dg[r + j] : 0.f, dxj = update ? a.dx[r + j] : 0.f;
-    const float l3 = update ? l3raw / rho : l3raw;
-    const float u3 = update ? rho * u3raw : u3raw;
-    float urow[RM];
-    float dotU = 0.f, dotL = 0.f;
+      for (int k = 0; k < RM; ++k) {
+        if (k < r) {
+          const float u = uc[k * kThreads];
+          urow[k] = update ? rho * u : u;
+          dotU = fmaf(urow[k], lt1[k], dotU);
+          if (update) dotL = fmaf(tile[k] / rho, il1[k], dotL);
+        }
+      }
+      const float LtQg2 = l3 * Qg2;                                           // :443 / :513
+      const float Pg2 = dotU + u3 * LtQg2;                                    // :446 / :516
+      if (!update) {
+        out[r + j] = Pg2;
+      } else {
+        const float iLiQtx2 = (iQtx2 - dotL) / l3;                            // :449
+        const float iPx2 = iLiQtx2 / u3;                                      // :451
+        a.v2[j] = Pg2;
+        a.v3[j] = iPx2;
+        mxL = fmaxf(mxL, fabsf(Qg2 * Qg2 - iQtx2 * iQtx2));                   // grad3 of L   :458
+        mxU = fmaxf(mxU, fabsf(Pg2 * dgj - dxj * iPx2));                      // grad3 of U   :471
 #pragma unroll
-    for (int k = 0; k < RM; ++k) {
-      if (k < r) {
-        urow[k] = update ? rho * ucol[k] : ucol[k];
-        dotU = fmaf(urow[k], lt1[k], dotU);
-        if (update) dotL = fmaf(tile[threadIdx.x * r + k] / rho, il1[k], dotL);
+        for (int k = 0; k < RM; ++k) {
+          if (k < r) {
+            pc[k] = fmaf(urow[k], iPx2, pc[k]);
+            mxL = fmaxf(mxL, fabsf(Qg2 * qg1[k] - iQtx2 * iq1[k]));           // grad2 of L   :457
+            mxU = fmaxf(mxU, fabsf(pg1[k] * dgj - dx1[k] * iPx2));            // grad2 of U   :470
+          }
+        }
       }
     }
-    const float LtQg2 = l3 * Qg2;                                           // :443 / :513
-    const float Pg2 = dotU + u3 * LtQg2;                                    // :446 / :516
-    if (!update) {
-      out[r + j] = Pg2;
-    } else {
-    const float iLiQtx2 = (iQtx2 - dotL) / l3;                              // :449
-    const float iPx2 = iLiQtx2 / u3;                                        // :451
-    a.v2[j] = Pg2;
-    a.v3[j] = iPx2;
-    mxL = fmaxf(mxL, fabsf(Qg2 * Qg2 - iQtx2 * iQtx2));                     // grad3 of L   :458
-    mxU = fmaxf(mxU, fabsf(Pg2 * dgj - dxj * iPx2));                        // grad3 of U   :471
-#pragma unroll
-    for (int k = 0; k < RM; ++k) {
-      if (k < r) {
-        pc[k] = fmaf(urow[k], iPx2, pc[k]);
-        mxL = fmaxf(mxL, fabsf(Qg2 * qg1[k] - iQtx2 * iq1[k]));             // grad2 of L   :457
-        mxU = fmaxf(mxU, fabsf(pg1[k] * dgj - dx1[k] * iPx2));              // grad2 of U   :470
-      }
-    }
-    }
-    }
-    if (update) tiles.release(j0);
   }
+  cp_async_wait<0>();
   if (!update) return;
   block_reduce_to<RM>(pc, r, a.partial, 0);
   mxL = warp_max(mxL); mxU = warp_max(mxU);
@@ -501,12 +555,11 @@ __global__ void __launch_bounds__(32) small3_kernel(Args a, int nblocks) {
 // ---- pass 4: new L2, l3, U2, u3                                                               psgd.py:464-478 ------------
 template <int RM>
 __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args a) {
+  extern __shared__ __align__(16) float ring_mem[];
   const long long m = a.n - a.r;
   const int r = a.r;
   const State* st = a.st;
   const float rho = st->rho, stepL = st->stepL, stepU = st->stepU;
-  const float* L2 = a.L12 + (size_t)r * r;
-  const float* U2 = a.U12 + r;
   float* L2o = a.L12_out + (size_t)r * r;
   float* U2o = a.U12_out + r;
   float cL1[RM], cL2[RM], cU1[RM], cU2[RM];
@@ -516,31 +569,31 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
     cL1[k] = ok ? st->cL1[k] : 0.f; cL2[k] = ok ? st->cL2[k] : 0.f;
     cU1[k] = ok ? st->cU1[k] : 0.f; cU2[k] = ok ? st->cU2[k] : 0.f;
   }
-  __shared__ float tile_mem[RowTiles<RM>::kFloats];
-  RowTiles<RM> tiles;
-  tiles.begin(tile_mem, L2, m, r, (long long)blockIdx.x * kThreads);
-  for (long long j0 = (long long)blockIdx.x * kThreads; j0 < m; j0 += (long long)gridDim.x * kThreads) {
-    const int rows = tiles.rows_at(j0);
-    float* tile = tiles.acquire(j0);
+  Ring<RM, 8> ring;
+  ring.L2 = a.L12 + (size_t)r * r;
+  ring.U2 = a.U12 + r;
+  ring.vec[0] = a.l3; ring.vec[1] = a.u3; ring.vec[2] = a.v0; ring.vec[3] = a.v1; ring.vec[4] = a.v2; ring.vec[5] = a.v3;
+  ring.vec[6] = a.dg + r; ring.vec[7] = a.dx + r;
+  ring.begin(ring_mem, m, a.n, r);
+  for (long long j0 = ring.first; j0 < m; j0 += ring.stride) {
+    const int rows = ring.rows_at(j0);
+    float* sg = ring.acquire(j0);
     if ((int)threadIdx.x < rows) {
       const long long j = j0 + threadIdx.x;
-      // all global loads of the row first: the stores to U2o below may alias U2 as far as the compiler knows, so inside
-      // the update loop every load would wait for the previous store's operand (ncu: ten serialised DRAM latencies)
-      float ucol[RM];
-#pragma unroll
-      for (int k = 0; k < RM; ++k) ucol[k] = k < r ? U2[(size_t)k * a.n + j] : 0.f;
-      const float l3raw = a.l3[j], u3raw = a.u3[j];
-      const float Qg2 = a.v0[j], iQtx2 = a.v1[j], Pg2 = a.v2[j], iPx2 = a.v3[j];
-      const float dgj = a.dg[r + j], dxj = a.dx[r + j];
+      float* tile = ring.lrow(sg, r);
+      const float* uc = ring.ucol(sg);
+      const float l3raw = ring.vecv(sg, 0), u3raw = ring.vecv(sg, 1);
+      const float Qg2 = ring.vecv(sg, 2), iQtx2 = ring.vecv(sg, 3), Pg2 = ring.vecv(sg, 4), iPx2 = ring.vecv(sg, 5);
+      const float dgj = ring.vecv(sg, 6), dxj = ring.vecv(sg, 7);
       const float l3 = l3raw / rho, u3 = rho * u3raw;
       const float g3L = Qg2 * Qg2 - iQtx2 * iQtx2;                           // :458
       const float g3U = Pg2 * dgj - dxj * iPx2;                              // :471
 #pragma unroll
       for (int k = 0; k < RM; ++k) {
         if (k < r) {
-          const float l = tile[threadIdx.x * r + k] / rho;
-          tile[threadIdx.x * r + k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;       // :464
-          const float u = rho * ucol[k];
+          const float l = tile[k] / rho;
+          tile[k] = l - stepL * (Qg2 * cL1[k] - iQtx2 * cL2[k]) - stepL * g3L * l;                          // :464
+          const float u = rho * uc[k * kThreads];
           U2o[(size_t)k * a.n + j] = u - stepU * (cU1[k] * dgj - cU2[k] * iPx2) - stepU * g3U * u;        // :477
         }
       }
@@ -548,17 +601,29 @@ __global__ void __launch_bounds__(kThreads, RM <= 12 ? 2 : 1) pass4_kernel(Args 
       a.u3_out[j] = u3 - stepU * g3U * u3;                                   // :478
     }
     __syncthreads();
-    {                                   // the updated rows leave as one contiguous, coalesced run
-      float* po = L2o + (size_t)j0 * r;
+    {                                   // the updated rows leave as one contiguous, coalesced run; the stage is
+      float* po = L2o + (size_t)j0 * r; // not refilled before the barrier of the next acquire()
       const int cnt = rows * r;
 #pragma unroll
       for (int i = 0; i < RM; ++i) {
         const int e = threadIdx.x + i * kThreads;
-        if (e < cnt) po[e] = tile[e];
+        if (e < cnt) po[e] = sg[e];
       }
     }
-    tiles.release(j0);
   }
+  cp_async_wait<0>();
+}
+
+template <typename K>
+static int ensure_smem(psgd_ctx* ctx, K kernel, size_t bytes) {
+  static std::mutex mu;
+  static std::set<std::pair<int, const void*>> done;
+  std::lock_guard<std::mutex> lock(mu);
+  const std::pair<int, const void*> key(ctx->device, reinterpret_cast<const void*>(kernel));
+  if (done.count(key)) return PSGD_OK;
+  PSGD_CUDA_CHECK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes));
+  done.insert(key);
+  return PSGD_OK;
 }
 
 static int grid_for(const psgd_ctx* ctx, long long m) {
@@ -568,13 +633,18 @@ static int grid_for(const psgd_ctx* ctx, long long m) {
   return (int)(b < 1 ? 1 : b);
 }
 
-#define SPLU_DISPATCH(r, KERN, ...)                                   \
+#define SPLU_LAUNCH(RM, NV, KERN, ...)                                                              \
+  do {                                                                                              \
+    PSGD_RETURN_IF(splu::ensure_smem(ctx, KERN<RM>, splu::Ring<RM, NV>::kBytes));                   \
+    KERN<RM><<<grid, splu::kThreads, splu::Ring<RM, NV>::kBytes, st>>>(__VA_ARGS__);                \
+  } while (0)
+#define SPLU_DISPATCH(r, NV, KERN, ...)                               \
   do {                                                                \
-    if ((r) <= 8) KERN<8><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);        \
-    else if ((r) <= 10) KERN<10><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
-    else if ((r) <= 12) KERN<12><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
-    else if ((r) <= 16) KERN<16><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__); \
-    else KERN<32><<<grid, splu::kThreads, 0, st>>>(__VA_ARGS__);                \
+    if ((r) <= 8) SPLU_LAUNCH(8, NV, KERN, __VA_ARGS__);              \
+    else if ((r) <= 10) SPLU_LAUNCH(10, NV, KERN, __VA_ARGS__);       \
+    else if ((r) <= 12) SPLU_LAUNCH(12, NV, KERN, __VA_ARGS__);       \
+    else if ((r) <= 16) SPLU_LAUNCH(16, NV, KERN, __VA_ARGS__);       \
+    else SPLU_LAUNCH(32, NV, KERN, __VA_ARGS__);                      \
   } while (0)
 
 static int check_common(psgd_ctx* ctx, long long n, int r) {
@@ -616,19 +686,19 @@ extern "C" int psgd_splu_update(psgd_ctx* ctx, const float* L12, const float* l3
   PSGD_LAUNCH_CHECK(ctx);
   splu::small0_kernel<<<1, 32, 0, st>>>(a, pmax, grid, 1);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass1_kernel, a);
+  SPLU_DISPATCH(r, 1, splu::pass1_kernel, a);
   PSGD_LAUNCH_CHECK(ctx);
   splu::small1_kernel<<<1, 32, 0, st>>>(a, grid, 1);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass2_kernel, a, 1);
+  SPLU_DISPATCH(r, 4, splu::pass2_kernel, a, 1);
   PSGD_LAUNCH_CHECK(ctx);
   splu::small2_kernel<<<1, 32, 0, st>>>(a, grid, 1, nullptr);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass3_kernel, a, 1, (float*)nullptr);
+  SPLU_DISPATCH(r, 6, splu::pass3_kernel, a, 1, (float*)nullptr);
   PSGD_LAUNCH_CHECK(ctx);
   splu::small3_kernel<<<1, 32, 0, st>>>(a, grid);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass4_kernel, a);
+  SPLU_DISPATCH(r, 8, splu::pass4_kernel, a);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
@@ -653,15 +723,15 @@ extern "C" int psgd_splu_apply(psgd_ctx* ctx, const float* L12, const float* l3,
   cudaStream_t st = ctx->stream;
   splu::small0_kernel<<<1, 32, 0, st>>>(a, nullptr, 0, 0);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass1_kernel, a);
+  SPLU_DISPATCH(r, 1, splu::pass1_kernel, a);
   PSGD_LAUNCH_CHECK(ctx);
   splu::small1_kernel<<<1, 32, 0, st>>>(a, grid, 0);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass2_kernel, a, 0);
+  SPLU_DISPATCH(r, 4, splu::pass2_kernel, a, 0);
   PSGD_LAUNCH_CHECK(ctx);
   splu::small2_kernel<<<1, 32, 0, st>>>(a, grid, 0, out);
   PSGD_LAUNCH_CHECK(ctx);
-  SPLU_DISPATCH(r, splu::pass3_kernel, a, 0, out);
+  SPLU_DISPATCH(r, 6, splu::pass3_kernel, a, 0, out);
   PSGD_LAUNCH_CHECK(ctx);
   return PSGD_OK;
 }
