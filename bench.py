@@ -754,8 +754,9 @@ def main():
     ap.add_argument("--uvd-form", default="fused", choices=["fused", "separate", "separate-3sweep"],
                     help="UVd: fused update+apply call (default), the reference's two calls, or those with the three-sweep update")
     ap.add_argument("--no-separate", action="store_true", help="UVd: skip the extra timing of the two-call form")
-    ap.add_argument("--kron-gather", default="once", choices=["once", "slots", "peer", "peer-once"],
-                    help="Kron multi-GPU, how the preconditioned gradients reach every rank: once = one in-place NCCL "
+    ap.add_argument("--kron-gather", default="auto", choices=["auto", "once", "slots", "peer", "peer-once"],
+                    help="Kron multi-GPU, how the preconditioned gradients reach every rank: auto = slots at <= 3 layers per GPU, "
+                         "else once; once = one in-place NCCL "
                          "all-gather after the batched apply; slots = NCCL all-gather per layer slot as its apply finishes; "
                          "peer = copy-engine pushes into IPC-mapped peer buffers per layer slot (no SMs); peer-once = the same "
                          "after the whole batched apply")
