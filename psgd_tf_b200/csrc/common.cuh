@@ -85,6 +85,9 @@ struct psgd_ctx {
   static constexpr int kSideStreams = 4;
   cudaStream_t side[kSideStreams] = {};      // created on first use (kron.cu), joined back into `stream` before a call returns
   cudaEvent_t ev_fork = nullptr, ev_side[kSideStreams] = {};
+  // second stream per slot: the two independent halves of a small (dense, dense) update run side by side (kron.cu)
+  cudaStream_t branch[kSideStreams + 1] = {};
+  cudaEvent_t ev_branch_go[kSideStreams + 1] = {}, ev_branch_done[kSideStreams + 1] = {};
   int opt_uvd_mid = 1;       // UVd: 1 = one "mid" launch between sweeps (reduce + exchange + algebra), 0 = three launches
   int opt_comm_timeout_ms = 0;   // peer exchange: wait limit per exchange (0 = the 20 s default)
   int opt_assume_tri = 1;    // dense Kron factors are upper triangular: let GEMMs skip structurally-zero K blocks
@@ -107,6 +110,8 @@ struct psgd_ctx {
   int stream_slot() const {
     for (int k = 0; k < kSideStreams; ++k)
       if (side[k] && stream == side[k]) return k + 1;
+    for (int k = 1; k <= kSideStreams; ++k)
+      if (branch[k] && stream == branch[k]) return k;
     return 0;
   }
   int reserve_aux(int slot, size_t bytes, float** out);

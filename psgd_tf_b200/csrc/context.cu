@@ -88,6 +88,11 @@ extern "C" int psgd_destroy(psgd_ctx* ctx) {
     if (ctx->ev_side[k]) cudaEventDestroy(ctx->ev_side[k]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int k = 0; k <= psgd_ctx::kSideStreams; ++k) {
+    if (ctx->branch[k]) cudaStreamDestroy(ctx->branch[k]);
+    if (ctx->ev_branch_go[k]) cudaEventDestroy(ctx->ev_branch_go[k]);
+    if (ctx->ev_branch_done[k]) cudaEventDestroy(ctx->ev_branch_done[k]);
+  }
   delete ctx;
   return PSGD_OK;
 }

@@ -485,6 +485,69 @@ static void carve_update(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int
   L.nspart = (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) ? c.take<float>(ks::ns_update_scratch_floats(M, N)) : nullptr;
 }
 
+// grad2 = triu(A^T A - Bt^T Bt), Qr' = Qr - step2 grad2 Qr (times rho for (dense, dense) pairs)      psgd.py:176-179
+static int update_right_dense(psgd_ctx* ctx, std::vector<Layer>& Ls, int M, int N, float step, float tiny, bool dd) {
+  std::vector<la::Gemm> gs;
+  for (auto& L : Ls) {
+    la::Gemm g = mk(N, N, M, L.A, N, true, L.A, N, false, L.grad2, N);
+    g.K2 = M; g.A2 = L.Bt; g.lda2 = N; g.ta2 = true; g.B2 = L.Bt; g.ldb2 = N; g.tb2 = false;
+    g.triu = true; g.maxabs = &L.sc->max2;
+    gs.push_back(g);
+  }
+  PSGD_RETURN_IF(gemm_all(ctx, gs));
+  gs.clear();
+  for (auto& L : Ls) {
+    la::Gemm g = mk(N, N, N, L.grad2, N, false, L.Qrb, N, false, L.Qr_out, N);
+    g.D = L.Qrb; g.ldd = N; g.mu_max = &L.sc->max2; g.step = step; g.tiny = tiny;
+    if (dd) { g.rho = &L.sc->rho; g.rho_mode = 2; }                      // rho * Qr                      psgd.py:170
+    g.d_tri = true;
+    gs.push_back(g);
+  }
+  return gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromR);
+}
+
+// A small (dense, dense) update is a chain of 13 latency-bound launches, but only half of them depend on each other:
+//   A = Ql dG Qr^T  ||  Bt = Ql^-T dX Qr^-1,   then   (grad1, Ql')  ||  (grad2, Qr').
+// Below the tensor-core sizes the two halves run on two streams (the slot's own and its `branch`), forked and joined
+// with events, so the call stays CUDA-graph capturable and the halves become parallel branches of the graph.
+struct Branch {
+  psgd_ctx* ctx;
+  cudaStream_t main, br;
+  int slot;
+  bool on;
+  int fork() {          // the branch may start once everything enqueued on main so far is done
+    if (!on) return PSGD_OK;
+    PSGD_CUDA_CHECK(cudaEventRecord(ctx->ev_branch_go[slot], main));
+    PSGD_CUDA_CHECK(cudaStreamWaitEvent(br, ctx->ev_branch_go[slot], 0));
+    return PSGD_OK;
+  }
+  int join() {          // main continues once the branch is done
+    if (!on) return PSGD_OK;
+    PSGD_CUDA_CHECK(cudaEventRecord(ctx->ev_branch_done[slot], br));
+    PSGD_CUDA_CHECK(cudaStreamWaitEvent(main, ctx->ev_branch_done[slot], 0));
+    return PSGD_OK;
+  }
+  void to_branch() { if (on) ctx->stream = br; }
+  void to_main() { ctx->stream = main; }
+};
+
+static int make_branch(psgd_ctx* ctx, int kl, int kr, int M, int N, Branch* b) {
+  b->ctx = ctx; b->main = ctx->stream; b->br = ctx->stream; b->slot = ctx->stream_slot(); b->on = false;
+  const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;
+  const bool tc_sized = M >= 256 && N >= 256 && (M % 4) == 0 && (N % 4) == 0;
+  if (!dd || !ctx->opt_kron_streams || ctx->opt_profile || M >= 512 || N >= 512 || tc_sized || ctx->opt_gemm_path == 2)
+    return PSGD_OK;
+  const int s = b->slot;
+  if (!ctx->branch[s]) {
+    PSGD_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->branch[s], cudaStreamNonBlocking));
+    PSGD_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_branch_go[s], cudaEventDisableTiming));
+    PSGD_CUDA_CHECK(cudaEventCreateWithFlags(&ctx->ev_branch_done[s], cudaEventDisableTiming));
+  }
+  b->br = ctx->branch[s];
+  b->on = true;
+  return PSGD_OK;
+}
+
 static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, int M, int N, float step, float tiny) {
   const size_t MN = (size_t)M * N;
   cudaStream_t st = ctx->stream;
@@ -519,19 +582,28 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
   PSGD_RETURN_IF(scan_group(ctx, Ls, M, N));
 
   // ---- A = Ql dG Qr^T  and  Bt = Ql^-T dX Qr^-1 ------------------------------------------------
+  Branch br;
+  PSGD_RETURN_IF(make_branch(ctx, kl, kr, M, N, &br));
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE) {
+    PSGD_RETURN_IF(br.fork());
     gs.clear();                                                          // T1 = dG Qr^T            psgd.py:173
     for (auto& L : Ls) gs.push_back(mk(M, N, N, L.dG, N, false, L.Qrb, N, true, L.T1, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
     gs.clear();                                                          // A = Ql T1
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Qlb, M, false, L.T1, N, false, L.A, N));
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
+    br.to_branch();
+    // forked: W goes where Bt will be and the left solve runs in place (the panel solves allow X == B), because T1 is
+    // busy on the other stream
     ts.clear();                                                          // W = dX Qr^-1            psgd.py:174
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.T1, L.zinv, L.xwork});
-    PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, br.on ? L.Bt : L.T1, L.zinv, L.xwork});
+    int rc = tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N);
     ts.clear();                                                          // Bt = Ql^-T W
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.T1, L.Bt, L.zinv, L.xwork});
-    PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, br.on ? L.Bt : L.T1, L.Bt, L.zinv, L.xwork});
+    if (rc == PSGD_OK) rc = tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N);
+    br.to_main();
+    PSGD_RETURN_IF(rc);
+    PSGD_RETURN_IF(br.join());
   } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
     for (auto& L : Ls) {
       norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dG, L.T1, M, N, nullptr, 0);   // :218-219
@@ -578,7 +650,8 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     return PSGD_OK;
   }
 
-  // ---- left factor -----------------------------------------------------------------------------
+  // ---- left factor (main stream) and right factor (branch, when forked) -----------------------------
+  PSGD_RETURN_IF(br.fork());
   if (kl == PSGD_FACTOR_DENSE) {
     gs.clear();                                                          // grad1 = triu(A A^T - Bt Bt^T)   psgd.py:175
     for (auto& L : Ls) {
@@ -607,6 +680,13 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     }
   }
   // ---- right factor ----------------------------------------------------------------------------
+  if (br.on) {
+    br.to_branch();
+    const int rc = update_right_dense(ctx, Ls, M, N, step, tiny, true);
+    br.to_main();
+    PSGD_RETURN_IF(rc);
+    return br.join();
+  }
   if (kr == PSGD_FACTOR_DENSE) {
     gs.clear();                                                          // grad2 = triu(A^T A - Bt^T Bt)   psgd.py:176
     for (auto& L : Ls) {

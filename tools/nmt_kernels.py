@@ -39,3 +39,11 @@ rows = [(e.device_time_total / 10.0, e.count / 10.0, e.key[:100]) for e in prof.
 for us, cnt, name in sorted(rows, reverse=True):
     print(f"{us:8.1f} us/step  x{cnt:5.1f}  {name}")
 print("layers", nmt, "sum us", round(sum(r[0] for r in rows), 1))
+if len(nmt) == 1:
+    evs = sorted([e for e in prof.events() if e.device_type.name == "CUDA" and e.device_time > 0], key=lambda e: e.time_range.start)
+    per = len(evs) // 10
+    prev_end = None
+    for e in evs[-per:]:
+        gap = (e.time_range.start - prev_end) if prev_end is not None else 0.0
+        print(f"  +{gap:6.1f} us gap  {e.device_time:7.1f} us  {e.name[:90]}")
+        prev_end = e.time_range.end
