@@ -326,9 +326,10 @@ int gemm_simt(psgd_ctx* ctx, const Gemm& g) {
 //     FMAs; with one output per thread the kernel was bound by shared-memory wavefronts, 2 per FMA: 74 us at n = 257);
 //     the four K quarters meet through shared memory in a fixed order.
 // ncu, round 2, n = 257, m = 120: the 256-thread row-by-row kernels before these ran 26 k dependent instructions per
-// warp at 8 cycles each (2 warps per scheduler): 120 us + 108 us per layer; these take 39 us + 17 us, of which ~9 us each
-// is the inversion of the diagonal blocks.  Panels beyond the first get the contribution of the solved part from one
-// SIMT GEMM each (host loop below).
+// warp at 8 cycles each (2 warps per scheduler): 120 us + 108 us per layer; these take 35 us + 13 us (clock64 stamps,
+// tools/trsm_stamps.py: slab load 2.5 k cycles, block inversions 7.8 k, then per block step ~2.0 k per 64-row tile of Q
+// and 1.6 k for the reduction + diagonal product).  Panels beyond the first get the contribution of the solved part from
+// one SIMT GEMM each (host loop below).
 // ---------------------------------------------------------------------------------------------
 constexpr int NB = 32;             // diagonal block
 constexpr int kPanel = 512;        // unknowns per launch
