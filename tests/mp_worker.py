@@ -74,7 +74,12 @@ def cpu_protocol(rank, world):
     for rep_ in range(3 if gb is not None else 0):          # two alternating buffers
         for j, o in enumerate(gb.local_outs()):
             o.fill_(float(owned_u[rank][j] + 10 * rep_))
-        full = gb.gather()
+        if rep_ == 1:                                        # slot by slot, as the overlapped form of the bench issues them
+            for j in range(gb.per):
+                gb.gather_slot(j)
+            full = gb.finish()
+        else:
+            full = gb.gather()
         for i, t in enumerate(full):
             assert torch.all(t == float(i + 10 * rep_))
     # ---- reduction protocol of the sharded UVd update (mirrors psgd_tf_b200/csrc/uvd.cu) ------------------------
