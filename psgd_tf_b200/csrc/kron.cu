@@ -534,9 +534,13 @@ struct Branch {
 static int make_branch(psgd_ctx* ctx, int kl, int kr, int M, int N, Branch* b) {
   b->ctx = ctx; b->main = ctx->stream; b->br = ctx->stream; b->slot = ctx->stream_slot(); b->on = false;
   const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;
+  const bool ds = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE;
   const bool tc_sized = M >= 256 && N >= 256 && (M % 4) == 0 && (N % 4) == 0;
-  if (!dd || !ctx->opt_kron_streams || ctx->opt_profile || M >= 512 || N >= 512 || tc_sized || ctx->opt_gemm_path == 2)
-    return PSGD_OK;
+  if (!ctx->opt_kron_streams || ctx->opt_profile || ctx->opt_gemm_path == 2) return PSGD_OK;
+  // (dense, dense): both halves on the SIMT engine.  (dense, scaling) -- the NMT embeddings, canonical [256, 9416]:
+  // the products may be tensor-core launches, but the branch only ever runs the SIMT panel solve (n < 512) and
+  // streaming kernels next to them, so the GEMM engine's per-slot scratch is used by one stream at a time.
+  if (!(dd && M < 512 && N < 512 && !tc_sized) && !(ds && M < 512)) return PSGD_OK;
   const int s = b->slot;
   if (!ctx->branch[s]) {
     PSGD_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->branch[s], cudaStreamNonBlocking));
@@ -621,6 +625,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.T1, L.Bt, L.zinv, L.xwork});
     PSGD_RETURN_IF(tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N));
   } else if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {
+    PSGD_RETURN_IF(br.fork());
     gs.clear();                                                          // A = (Ql dG) * qr        psgd.py:295-296
     for (auto& L : Ls) {
       la::Gemm g = mk(M, N, M, L.Qlb, M, false, L.dG, N, false, L.A, N);
@@ -628,13 +633,21 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       gs.push_back(g);
     }
     PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
-    ts.clear();                                                          // Bt = Ql^-T dX           psgd.py:298
-    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv, L.xwork});
-    PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
-    for (auto& L : Ls) {
-      col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Bt, L.Qrb, M, N);                  // :299
-      PSGD_LAUNCH_CHECK(ctx);
-    }
+    br.to_branch();
+    auto bt_chain = [&]() -> int {
+      ts.clear();                                                        // Bt = Ql^-T dX           psgd.py:298
+      for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.dX, L.Bt, L.zinv, L.xwork});
+      PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
+      for (auto& L : Ls) {
+        col_scale_recip_kernel<<<ew_grid(ctx, MN, 256), 256, 0, ctx->stream>>>(L.Bt, L.Qrb, M, N);       // :299
+        PSGD_LAUNCH_CHECK(ctx);
+      }
+      return PSGD_OK;
+    };
+    const int rcb = bt_chain();
+    br.to_main();
+    PSGD_RETURN_IF(rcb);
+    PSGD_RETURN_IF(br.join());
   } else {  // (NORM, SCALE): no dense factor at all -- A and Bt are never materialised (kron_stream.cu)
     for (auto& L : Ls) {
       int cchunks = 0;
@@ -679,42 +692,27 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       PSGD_LAUNCH_CHECK(ctx);
     }
   }
-  // ---- right factor ----------------------------------------------------------------------------
-  if (br.on) {
-    br.to_branch();
-    const int rc = update_right_dense(ctx, Ls, M, N, step, tiny, true);
-    br.to_main();
-    PSGD_RETURN_IF(rc);
-    return br.join();
-  }
+  // ---- right factor (on the branch stream when forked) -------------------------------------------
+  br.to_branch();
+  int rc = PSGD_OK;
   if (kr == PSGD_FACTOR_DENSE) {
-    gs.clear();                                                          // grad2 = triu(A^T A - Bt^T Bt)   psgd.py:176
-    for (auto& L : Ls) {
-      la::Gemm g = mk(N, N, M, L.A, N, true, L.A, N, false, L.grad2, N);
-      g.K2 = M; g.A2 = L.Bt; g.lda2 = N; g.ta2 = true; g.B2 = L.Bt; g.ldb2 = N; g.tb2 = false;
-      g.triu = true; g.maxabs = &L.sc->max2;
-      gs.push_back(g);
-    }
-    PSGD_RETURN_IF(gemm_all(ctx, gs));
-    gs.clear();                                                          // Qr' = Qr - step2 grad2 Qr       psgd.py:178-179
-    for (auto& L : Ls) {
-      la::Gemm g = mk(N, N, N, L.grad2, N, false, L.Qrb, N, false, L.Qr_out, N);
-      g.D = L.Qrb; g.ldd = N; g.mu_max = &L.sc->max2; g.step = step; g.tiny = tiny;
-      if (dd) { g.rho = &L.sc->rho; g.rho_mode = 2; }                    // rho * Qr                      psgd.py:170
-      g.d_tri = true;
-      gs.push_back(g);
-    }
-    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromR));
+    rc = update_right_dense(ctx, Ls, M, N, step, tiny, dd);
   } else {
-    for (auto& L : Ls) {
-      PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, L.A, L.Bt, M, N, L.part, L.sa, L.sb));                  // :304 / :366
-      scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.sa, L.sb, N, L.gvec, L.sc);
-      PSGD_LAUNCH_CHECK(ctx);
-      scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);   // :307
-      PSGD_LAUNCH_CHECK(ctx);
-    }
+    auto scale_right = [&]() -> int {
+      for (auto& L : Ls) {
+        PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, L.A, L.Bt, M, N, L.part, L.sa, L.sb));                // :304 / :366
+        scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.sa, L.sb, N, L.gvec, L.sc);
+        PSGD_LAUNCH_CHECK(ctx);
+        scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);   // :307
+        PSGD_LAUNCH_CHECK(ctx);
+      }
+      return PSGD_OK;
+    };
+    rc = scale_right();
   }
-  return PSGD_OK;
+  br.to_main();
+  PSGD_RETURN_IF(rc);
+  return br.join();
 }
 
 // ---------------------------------------------------------------------------------------------
