@@ -152,6 +152,22 @@ def test_ill_conditioned_factors(psgd, n, base):
               f"CUDA vs float32 oracle {cases.rel_err(g, b):.2e}")
 
 
+@pytest.mark.parametrize("M,N", [(257, 120), (96, 300), (700, 64)])
+def test_ill_conditioned_factors_small_layers(psgd, M, N):
+    """The same yardstick for the SIMT engine's panel solves (explicit inverses of 32-wide diagonal blocks, one or two
+    panels): cond ~ 1e4 factors of LeNet-like layers."""
+    rng = np.random.default_rng(M * 1000 + N)
+    c = cases.kron_case(M + N, "dense", "dense", M, N)
+    c["Ql"], c["Qr"] = ill_conditioned_factor(rng, M, 1e4), ill_conditioned_factor(rng, N, 1e4)
+    got = run_layer(psgd, c)
+    w64 = oracle_layer(c, np.float64)
+    w32 = oracle_layer(c, F)
+    for name, g, a, b in zip(("Ql", "Qr", "pre"), got, w64, w32):
+        e_cuda, e_f32 = cases.rel_err(g, a), cases.rel_err(b, a)
+        assert e_cuda <= max(TOL, 4.0 * e_f32), f"{name}: CUDA vs float64 {e_cuda:.2e}, float32 oracle vs float64 {e_f32:.2e}"
+        print(f"ill-conditioned {M}x{N} {name}: CUDA vs float64 {e_cuda:.2e}, float32 oracle vs float64 {e_f32:.2e}")
+
+
 @pytest.mark.parametrize("n", [512, 1024])
 def test_non_triangular_factor_default_options(psgd, n):
     """A full (not upper-triangular) Ql and Qr under the DEFAULT options: products use the whole matrix, solves the
