@@ -289,7 +289,7 @@ __global__ void __launch_bounds__(256) norm_new_ql_kernel(const float* __restric
 
 // grad2 = colsumA2 - colsumB2 ; max |grad2| -> sc->max2           psgd.py:304-305
 __global__ void __launch_bounds__(128) scale_grad_kernel(const float* __restrict__ sa, const float* __restrict__ sb, int N,
-                                                          float* __restrict__ grad2, Scal* __restrict__ sc) {
+                                                          float* __restrict__ grad2, float* __restrict__ maxabs) {
   float mx = 0.f;
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
     const float g = sa[j] - sb[j];
@@ -297,13 +297,13 @@ __global__ void __launch_bounds__(128) scale_grad_kernel(const float* __restrict
     mx = fmaxf(mx, fabsf(g));
   }
   mx = warp_max(mx);
-  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(&sc->max2, mx);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(maxabs, mx);
 }
 // qr' = qr - step2 grad2 qr                                       psgd.py:307
 __global__ void __launch_bounds__(128) scale_new_qr_kernel(const float* __restrict__ qr, const float* __restrict__ grad2,
                                                             float* __restrict__ out, int N, float step, float tiny,
-                                                            const Scal* __restrict__ sc) {
-  const float step2 = step / (sc->max2 + tiny);
+                                                            const float* __restrict__ maxabs) {
+  const float step2 = step / (*maxabs + tiny);
   for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x)
     out[j] = qr[j] - step2 * grad2[j] * qr[j];
 }
@@ -335,6 +335,36 @@ __global__ void __launch_bounds__(256) col_scale_recip_kernel(float* __restrict_
   const int64_t total = (int64_t)M * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
     X[e] = X[e] * (1.0f / qr[e % N]);
+}
+
+// (scaling, dense) in its own orientation (the reference transposes to (dense, scaling): psgd.py:102-104).  One warp per
+// row i:  A[i,:] = ql[i] T[i,:],  Bt[i,:] = W[i,:] / ql[i]  in place, and the row sums of their squares -- the scaling
+// factor's gradient (psgd.py:304 for the transposed problem) -- in the same pass.
+__global__ void __launch_bounds__(256) scale_rows_stats_kernel(float* __restrict__ A, float* __restrict__ Bt,
+                                                                const float* __restrict__ ql, int M, int N,
+                                                                float* __restrict__ sa, float* __restrict__ sb) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = blockIdx.x * 8 + warp; i < M; i += gridDim.x * 8) {
+    const float q = ql[i], rq = 1.0f / q;
+    float* a = A + (size_t)i * N;
+    float* b = Bt + (size_t)i * N;
+    float s0 = 0.f, s1 = 0.f;
+    for (int j = lane; j < N; j += 32) {
+      const float x = a[j] * q, y = b[j] * rq;
+      a[j] = x; b[j] = y;
+      s0 = fmaf(x, x, s0); s1 = fmaf(y, y, s1);
+    }
+    s0 = warp_sum(s0); s1 = warp_sum(s1);
+    if (lane == 0) { sa[i] = s0; sb[i] = s1; }
+  }
+}
+// X[i,:] *= ql[i]^2                                               psgd.py:321 for the transposed problem
+__global__ void __launch_bounds__(256) row_scale_sq_kernel(float* __restrict__ X, const float* __restrict__ ql, int M, int N) {
+  const int64_t total = (int64_t)M * N;
+  for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+    const float q = ql[e / N];
+    X[e] = X[e] * (q * q);
+  }
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -394,7 +424,7 @@ struct Layer {
   float *Ql_out, *Qr_out, *out;
   // scratch
   Scal* sc;
-  float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *sa, *sb, *gvec, *zinv, *xwork;
+  float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *gvl, *sa, *sb, *gvec, *zinv, *xwork;
   float *t1, *t2, *t3, *P, *addlast;
   float* nspart;   // (normalization, scaling): partial tables of the fused streaming kernels
   int *fl, *fr;    // run-time "dense factor is not upper triangular" flags (nullptr: no scan, hints taken as given)
@@ -443,7 +473,8 @@ static la::Gemm mk(int M, int N, int K, const float* A, int lda, bool ta, const 
 static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
   const size_t MN = (size_t)M * N;
   const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;     // no rescaled factor copies (carve_update)
-  size_t f = 64 + (dd ? 0 : fsize(kl, M) + fsize(kr, N)) + 4 * MN + (size_t)M * M + (size_t)N * N + 8 * (size_t)(M + N) +
+  size_t f = 64 + (dd ? 0 : fsize(kl, M) + fsize(kr, N)) + 4 * MN + (kl == PSGD_FACTOR_DENSE ? (size_t)M * M : 0) +
+             (kr == PSGD_FACTOR_DENSE ? (size_t)N * N : 0) + 8 * (size_t)(M + N) +
              2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
   f += tc::trsm_scratch_floats((int)(M > N ? M : N));
   if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) f += ks::ns_update_scratch_floats((int)M, (int)N) + 64;
@@ -477,6 +508,7 @@ static void carve_update(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int
   L.grad2 = kr == PSGD_FACTOR_DENSE ? c.take<float>((size_t)N * N) : nullptr;
   L.g1d = c.take<float>(M);
   L.g1b = c.take<float>(M);
+  L.gvl = c.take<float>(M);
   L.sa = c.take<float>(N);
   L.sb = c.take<float>(N);
   L.gvec = c.take<float>(N);
@@ -540,7 +572,8 @@ static int make_branch(psgd_ctx* ctx, int kl, int kr, int M, int N, Branch* b) {
   // (dense, dense): both halves on the SIMT engine.  (dense, scaling) -- the NMT embeddings, canonical [256, 9416]:
   // the products may be tensor-core launches, but the branch only ever runs the SIMT panel solve (n < 512) and
   // streaming kernels next to them, so the GEMM engine's per-slot scratch is used by one stream at a time.
-  if (!(dd && M < 512 && N < 512 && !tc_sized) && !(ds && M < 512)) return PSGD_OK;
+  const bool sd = kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE;
+  if (!(dd && M < 512 && N < 512 && !tc_sized) && !(ds && M < 512) && !(sd && N < 512)) return PSGD_OK;
   const int s = b->slot;
   if (!ctx->branch[s]) {
     PSGD_CUDA_CHECK(cudaStreamCreateWithFlags(&ctx->branch[s], cudaStreamNonBlocking));
@@ -562,6 +595,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
   // ---- balance: Ql /= rho, Qr *= rho                          psgd.py:166-170, :211-215, :288-292, :342-346
   const bool small_pair = kl != PSGD_FACTOR_DENSE && kr != PSGD_FACTOR_DENSE && cl + cr <= kBalanceSmallMax;
   const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;
+  const bool sd = kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE;    // run in its own orientation, no transposes
   for (size_t t0 = 0; dd && t0 < Ls.size(); t0 += kPrepBatch) {          // (dense, dense): ONE launch per group
     const int cnt = (int)std::min<size_t>(kPrepBatch, Ls.size() - t0);
     PrepBatch b{};
@@ -573,6 +607,17 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     if (dd) break;
     if (small_pair) {
       balance_rescale_small_kernel<<<1, 1024, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, cl, cr, L.Qlb, L.Qrb, L.sc);
+      PSGD_LAUNCH_CHECK(ctx);
+      continue;
+    }
+    if (sd) {
+      // the reference balances the transposed problem (dense factor first): rho = sqrt(max diag(Qr) / max ql),
+      // Qr / rho, ql * rho                                                                  psgd.py:102-104, :288-292
+      balance_kernel<<<1, 256, 0, st>>>(kr, L.Qr, N, kl, L.Ql, M, L.sc);
+      PSGD_LAUNCH_CHECK(ctx);
+      rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, st>>>(L.Ql, L.Qlb, cl, L.sc, 0);
+      PSGD_LAUNCH_CHECK(ctx);
+      rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, st>>>(L.Qr, L.Qrb, cr, L.sc, 1);
       PSGD_LAUNCH_CHECK(ctx);
       continue;
     }
@@ -608,6 +653,39 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     br.to_main();
     PSGD_RETURN_IF(rc);
     PSGD_RETURN_IF(br.join());
+  } else if (sd) {
+    // (scaling, dense), X [M, N] with the dense factor on the right.  The reference computes the (dense, scaling) update of
+    // the transposed problem (psgd.py:102-104 -> :288-307); written out for X itself that is
+    //   A = diag(ql) (dG Qr^T),  Bt = diag(1/ql) (dX Qr^-1),  grad(Qr) = triu(A^T A - Bt^T Bt),  grad(ql)_i = |A_i|^2 - |Bt_i|^2
+    // -- the right-factor products of the (dense, dense) pair and one streaming pass, no transposed copies of dX, dG.
+    PSGD_RETURN_IF(br.fork());
+    gs.clear();                                                          // T = dG Qr^T -> A
+    for (auto& L : Ls) gs.push_back(mk(M, N, N, L.dG, N, false, L.Qrb, N, true, L.A, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
+    br.to_branch();
+    ts.clear();                                                          // W = dX Qr^-1 -> Bt
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qrb, L.dX, L.Bt, L.zinv, L.xwork});
+    const int rcw = tc::trsm_right_many(ctx, ts.data(), (int)ts.size(), N, N, N, M, N);
+    br.to_main();
+    PSGD_RETURN_IF(rcw);
+    PSGD_RETURN_IF(br.join());
+    const int rows_grid = (M + 7) / 8 < ctx->num_sms * 8 ? (M + 7) / 8 : ctx->num_sms * 8;
+    for (auto& L : Ls) {
+      scale_rows_stats_kernel<<<rows_grid, 256, 0, st>>>(L.A, L.Bt, L.Qlb, M, N, L.g1d, L.g1b);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    PSGD_RETURN_IF(br.fork());
+    for (auto& L : Ls) {                                                 // ql' = ql - step grad ql   psgd.py:304-307
+      scale_grad_kernel<<<ew_grid(ctx, M, 128), 128, 0, st>>>(L.g1d, L.g1b, M, L.gvl, &L.sc->max1);
+      PSGD_LAUNCH_CHECK(ctx);
+      scale_new_qr_kernel<<<ew_grid(ctx, M, 128), 128, 0, st>>>(L.Qlb, L.gvl, L.Ql_out, M, step, tiny, &L.sc->max1);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    br.to_branch();                                                      // Qr' = Qr - step triu(A^T A - Bt^T Bt) Qr
+    const int rcr = update_right_dense(ctx, Ls, M, N, step, tiny, false);
+    br.to_main();
+    PSGD_RETURN_IF(rcr);
+    return br.join();
   } else if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_DENSE) {
     for (auto& L : Ls) {
       norm_left_mul_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.Qlb, L.dG, L.T1, M, N, nullptr, 0);   // :218-219
@@ -657,7 +735,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       if (ks::ns_finish_is_fused(M, N)) continue;
       norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :362-364
       PSGD_LAUNCH_CHECK(ctx);
-      scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);        // :367-369
+      scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, &L.sc->max2);        // :367-369
       PSGD_LAUNCH_CHECK(ctx);
     }
     return PSGD_OK;
@@ -701,9 +779,9 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     auto scale_right = [&]() -> int {
       for (auto& L : Ls) {
         PSGD_RETURN_IF(col_reduce(ctx, 2, nullptr, L.A, L.Bt, M, N, L.part, L.sa, L.sb));                // :304 / :366
-        scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.sa, L.sb, N, L.gvec, L.sc);
+        scale_grad_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.sa, L.sb, N, L.gvec, &L.sc->max2);
         PSGD_LAUNCH_CHECK(ctx);
-        scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, L.sc);   // :307
+        scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, ctx->stream>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, &L.sc->max2);   // :307
         PSGD_LAUNCH_CHECK(ctx);
       }
       return PSGD_OK;
@@ -810,6 +888,28 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t2, N, false, L.out, N));
     return gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0);
   }
+  if (kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE) {
+    // the reference's (dense, scaling) apply of the transposed problem (psgd.py:144-146 -> :318-322) written for G itself:
+    // out = diag(ql^2) G Qr^T Qr, the small Gram matrix first when that is what the reference does for G^T (N < M)
+    if (N < M && !chain_preferred(ctx, N, M)) {
+      for (auto& L : Ls) gs.push_back(mk(N, N, N, L.Qr, N, true, L.Qr, N, false, L.P, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromR, kFromR));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.P, N, false, L.out, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs));
+    } else {
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.G, N, false, L.Qr, N, true, L.t1, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kLower, &Ls, 0, kFromR));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, N, L.t1, N, false, L.Qr, N, false, L.out, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, 0, kUpper, &Ls, 0, kFromR));
+    }
+    for (auto& L : Ls) {
+      row_scale_sq_kernel<<<ew_grid(ctx, MN, 256), 256, 0, st>>>(L.out, L.Ql, M, N);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    return PSGD_OK;
+  }
   if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_SCALE) {               // psgd.py:318-322
     if (M < N && !chain_preferred(ctx, M, N)) {
       for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
@@ -870,22 +970,6 @@ static int check_layer(const char* what, int kl, int kr, int64_t M, int64_t N) {
 
 struct Key { int kl, kr, M, N; };
 
-// q[count .. padded) = tiny positive: padding entries of a scaling factor that never win the balance maximum
-__global__ void pad_scale_kernel(float* q, int count, int padded) {
-  const int i = count + threadIdx.x;
-  if (i < padded) q[i] = 1e-30f;
-}
-static int round_up4(int x) { return (x + 3) / 4 * 4; }
-// A mirrored (scaling, dense) layer whose long side is not a multiple of 4 (the NMT embeddings: [9414, 256], [4935, 256])
-// would leave the tensor-core engine for the SIMT one: its transposed copies have the long side as leading dimension,
-// and TMA needs 16-byte multiples.  The library owns those copies, so it pads them (and the scaling factor) with up to 3
-// zero columns: they add nothing to A A^T - Bt Bt^T, their column statistics are zero, and the padded factor entries
-// (1e-30) neither win the balance maximum nor produce anything but zeros.
-static bool pad_mirrored(const psgd_ctx* ctx, int kl, int kr, int M, int N) {
-  return kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE && (M & 3) != 0 && N >= 256 && (N & 3) == 0 && M >= 256 &&
-         ctx->opt_gemm_path != 1;
-}
-
 static int ensure_side_streams(psgd_ctx* ctx) {
   if (ctx->ev_fork) return PSGD_OK;
   for (int k = 0; k < psgd_ctx::kSideStreams; ++k) {
@@ -911,8 +995,8 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
                    "kron update: null device pointer in layer %d", i);
     else
       PSGD_REQUIRE(q.Ql && q.Qr && q.G && q.out, PSGD_ERR_BAD_POINTER, "kron apply: null device pointer in layer %d", i);
-    const size_t f = is_update ? update_ws_floats(q.kind_l, q.kind_r, round_up4((int)q.M), round_up4((int)q.N))
-                               : apply_ws_floats(round_up4((int)q.M), round_up4((int)q.N)) + 2 * (size_t)round_up4((int)q.M) * round_up4((int)q.N);
+    const size_t f = is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N)
+                               : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N;
     need += f * sizeof(float) + 48 * 256;
   }
   // Bound the workspace: process the list in slices whose scratch fits the budget (large uniform stacks still group)
@@ -923,9 +1007,8 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     int end = begin;
     while (end < count) {
       const psgd_kron_layer& q = in[end];
-      const int Mr = round_up4((int)q.M), Nr = round_up4((int)q.N);        // mirrored layers may be padded to multiples of 4
-      const size_t f = (is_update ? update_ws_floats(q.kind_l, q.kind_r, Mr, Nr)
-                                  : apply_ws_floats(Mr, Nr) + 2 * (size_t)Mr * Nr) * sizeof(float) + 48 * 256;
+      const size_t f = (is_update ? update_ws_floats(q.kind_l, q.kind_r, q.M, q.N)
+                                  : apply_ws_floats(q.M, q.N) + 2 * (size_t)q.M * q.N) * sizeof(float) + 48 * 256;
       if (end > begin && bytes + f > budget) break;
       bytes += f;
       ++end;
@@ -935,40 +1018,23 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     std::vector<Layer> Ls(end - begin);
     std::vector<Key> keys(end - begin);
     std::vector<float*> untranspose_src(end - begin, nullptr);
-    std::vector<int> untranspose_ld(end - begin, 0);
-    struct CopyBack { const float* src; float* dst; size_t count; };
-    std::vector<CopyBack> copy_back;
     for (int i = begin; i < end; ++i) {
       const psgd_kron_layer& q = in[i];
       Layer& L = Ls[i - begin];
       L = Layer{};
       int kl = q.kind_l, kr = q.kind_r, M = (int)q.M, N = (int)q.N;
-      if (is_canonical(kl, kr)) {
+      // (scaling, dense) -- the NMT embeddings [9414, 256] -- has kernels for its own orientation (update_group /
+      // apply_group); the other two mirrored formats go through the canonical kernels on transposed copies
+      if (is_canonical(kl, kr) || (kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE)) {
         L.Ql = q.Ql; L.Qr = q.Qr; L.dX = q.dX; L.dG = q.dG; L.G = q.G;
         L.Ql_out = q.Ql_out; L.Qr_out = q.Qr_out; L.out = q.out;
       } else {
         // canonical kernel on (Qr, Ql, X^T); results come back swapped / transposed
-        const bool pad = pad_mirrored(ctx, kl, kr, M, N);
-        const int Mp = pad ? round_up4(M) : M;             // leading dimension (= canonical N) of the transposed copies
-        const size_t MN = (size_t)Mp * N;
+        const size_t MN = (size_t)M * N;
         L.Ql = q.Qr; L.Qr = q.Ql; L.Ql_out = q.Qr_out; L.Qr_out = q.Ql_out;
-        if (pad) {
-          float* qpad = c.take<float>(Mp);
-          PSGD_CUDA_CHECK(cudaMemcpyAsync(qpad, q.Ql, (size_t)M * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
-          pad_scale_kernel<<<1, 4, 0, ctx->stream>>>(qpad, M, Mp);
-          PSGD_LAUNCH_CHECK(ctx);
-          L.Qr = qpad;
-          if (is_update) {
-            float* qout = c.take<float>(Mp);
-            L.Qr_out = qout;
-            copy_back.push_back(CopyBack{qout, q.Ql_out, (size_t)M});
-          }
-        }
         auto transposed = [&](const float* src, float** out) -> int {
           float* t = c.take<float>(MN);
-          if (pad)      // zero the pad columns [M, Mp) of every row
-            PSGD_CUDA_CHECK(cudaMemset2DAsync(t + M, (size_t)Mp * sizeof(float), 0, (size_t)(Mp - M) * sizeof(float), N, ctx->stream));
-          PSGD_RETURN_IF(la::transpose(ctx, src, N, t, Mp, M, N));
+          PSGD_RETURN_IF(la::transpose(ctx, src, N, t, M, M, N));
           *out = t;
           return PSGD_OK;
         };
@@ -983,10 +1049,9 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
           float* Ot = c.take<float>(MN);
           L.G = Gt; L.out = Ot;
           untranspose_src[i - begin] = Ot;
-          untranspose_ld[i - begin] = Mp;
         }
         std::swap(kl, kr);
-        M = N; N = Mp;                                     // canonical shape: [dense side, (padded) long side]
+        std::swap(M, N);                                   // canonical shape
       }
       keys[i - begin] = Key{kl, kr, M, N};
       if (is_update) carve_update(ctx, c, L, kl, kr, M, N);
@@ -1050,9 +1115,7 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
     if (!is_update)
       for (int i = begin; i < end; ++i)
         if (untranspose_src[i - begin])   // canonical result is [N,M]; give the caller [M,N]
-          PSGD_RETURN_IF(la::transpose(ctx, untranspose_src[i - begin], untranspose_ld[i - begin], in[i].out, (int)in[i].N, (int)in[i].N, (int)in[i].M));
-    for (const CopyBack& cb : copy_back)                  // padded scaling-factor results: the real entries go to the caller
-      PSGD_CUDA_CHECK(cudaMemcpyAsync(cb.dst, cb.src, cb.count * sizeof(float), cudaMemcpyDeviceToDevice, ctx->stream));
+          PSGD_RETURN_IF(la::transpose(ctx, untranspose_src[i - begin], (int)in[i].M, in[i].out, (int)in[i].N, (int)in[i].N, (int)in[i].M));
     begin = end;
   }
   (void)need;
