@@ -980,10 +980,10 @@ static int ensure_side_streams(psgd_ctx* ctx) {
   return PSGD_OK;
 }
 
-// Runs update (is_update) or apply over a ragged list of layers.  Mirrored formats ((dense,norm), (scale,dense),
-// (scale,norm)) are brought to canonical orientation by transposing dX,dG / G into scratch and swapping the factors
-// (exactly what the reference does, psgd.py:86, :102, :104, :128, :144, :146); layers with equal canonical
-// (kinds, shape) then run as one group so every GEMM/TRSM of the op sequence is a single grouped launch.
+// Runs update (is_update) or apply over a ragged list of layers.  The mirrored formats (dense,norm) and (scale,norm) are
+// brought to canonical orientation by transposing dX,dG / G into scratch and swapping the factors (exactly what the
+// reference does, psgd.py:86, :104, :128, :146); (scale,dense) -- psgd.py:102, :144 -- runs in its own orientation.
+// Layers with equal (kinds, shape) then run as one group so every GEMM/TRSM of the op sequence is a single grouped launch.
 static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool is_update, float step, float tiny) {
   if (count == 0) return PSGD_OK;
   size_t need = 0;
