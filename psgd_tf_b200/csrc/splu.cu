@@ -154,6 +154,9 @@ __global__ void __launch_bounds__(32) small0_kernel(Args a, const float* __restr
 __device__ __forceinline__ void cp_async4(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
+__device__ __forceinline__ void cp_async8(float* smem_dst, const float* gmem_src) {
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
+}
 __device__ __forceinline__ void cp_async16(float* smem_dst, const float* gmem_src) {
   asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(smem_dst)), "l"(gmem_src) : "memory");
 }
@@ -175,7 +178,7 @@ struct Ring {
   const float* vec[NV];       // already offset so that index j addresses parameter r + j; nullptr entries are skipped
   long long m, n, first, stride;
   int r, t;
-  bool l2_aligned;
+  bool l2_aligned, pair_ok;
 
   __device__ __forceinline__ float* stage(int s) const { return base + s * kStageFloats; }
   __device__ __forceinline__ int rows_at(long long j0) const { return (int)(m - j0 < kThreads ? m - j0 : kThreads); }
@@ -200,7 +203,22 @@ struct Ring {
           }
         }
       }
-      if ((int)threadIdx.x < rows) {
+      if (pair_ok && (rows & 1) == 0) {
+        // two parameter indices per copy: half the copy instructions (r even, n even, 8-byte aligned arrays)
+        if (2 * (int)threadIdx.x < rows) {
+          const long long j = j0 + 2 * threadIdx.x;
+          if (U2) {
+            float* uc = st + kThreads * RM + 2 * threadIdx.x;
+#pragma unroll
+            for (int k = 0; k < RM; ++k)
+              if (k < r) cp_async8(uc + k * kThreads, U2 + (size_t)k * n + j);
+          }
+          float* vv = st + kThreads * 2 * RM + 2 * threadIdx.x;
+#pragma unroll
+          for (int v = 0; v < NV; ++v)
+            if (vec[v]) cp_async8(vv + v * kThreads, vec[v] + j);
+        }
+      } else if ((int)threadIdx.x < rows) {
         const long long j = j0 + threadIdx.x;
         if (U2) {
           float* uc = st + kThreads * RM + threadIdx.x;
@@ -222,6 +240,9 @@ struct Ring {
     stride = (long long)gridDim.x * kThreads;
     // a full tile is kThreads * r floats, a multiple of 4: every tile start is 16-byte aligned iff the array is
     l2_aligned = L2 && (reinterpret_cast<uintptr_t>(L2) & 15u) == 0;
+    // tile starts are even; U2 row k starts at U2 + k n: pairs are 8-byte aligned iff the bases are and n is even
+    pair_ok = (n & 1) == 0 && (!U2 || (reinterpret_cast<uintptr_t>(U2) & 7u) == 0);
+    for (int v = 0; v < NV; ++v) pair_ok = pair_ok && (!vec[v] || (reinterpret_cast<uintptr_t>(vec[v]) & 7u) == 0);
     for (int s = 0; s < S - 1; ++s) issue(s, first + s * stride);
   }
   // Tile j0 (the t-th of this block) becomes readable; EVERY thread of the block calls this exactly once per tile.

@@ -53,7 +53,9 @@ def test_splu_matches_reference_source_vectors(psgd, seed, shapes, r):
                                       ([(100_003,)], 1), ([(64, 9)], 7),
                                       # more than one tile per CTA (grid = 592 CTAs x 256 rows): the cp.async ring in its
                                       # steady state, all three stages reused; r = 32 runs the two-stage ring
-                                      ([(700_001,)], 10), ([(610_000,), (77, 3)], 12), ([(400_003,)], 32), ([(1_000_000,)], 16)])
+                                      ([(700_001,)], 10), ([(610_000,), (77, 3)], 12), ([(400_003,)], 32), ([(1_000_000,)], 16),
+                                      # even n and r: the 8-byte copy pairs of the ring
+                                      ([(600_000,)], 10), ([(4096,), (10, 10)], 8)])
 def test_splu_matches_oracle(psgd, shapes, r):
     c = MR.splu_case(900 + r, shapes, r)
     new, pre = run(psgd, c)

@@ -69,17 +69,21 @@ def kron_stream():
 
 
 def splu():
+    for n in (3001, 3000):          # odd n: 4-byte copies in the ring; even n and r: 8-byte pairs
+        _splu(n, 10)
+
+
+def _splu(n, r):
     rng = np.random.default_rng(4)
-    n, r = 3001, 10
     L12 = np.concatenate([np.tril(0.1 * rng.standard_normal((r, r))) + np.eye(r), 0.1 * rng.standard_normal((n - r, r))]).astype(np.float32)
     U12 = np.concatenate([np.triu(0.1 * rng.standard_normal((r, r))) + np.eye(r), 0.1 * rng.standard_normal((r, n - r))], axis=1).astype(np.float32)
     l3 = (0.5 + rng.random((n - r, 1))).astype(np.float32); u3 = (0.5 + rng.random((n - r, 1))).astype(np.float32)
     dx = rng.standard_normal((n, 1)).astype(np.float32); dg = (1.5 * dx + 0.1 * rng.standard_normal((n, 1))).astype(np.float32)
     out = psgd.update_precond_splu(dev(L12), dev(l3), dev(U12), dev(u3), [dev(dx)], [dev(dg)], 0.01)
     want = O.update_precond_splu(L12, l3, U12, u3, [dx], [dg], 0.01)
-    errs["splu_update"] = max(cases.rel_err(a.cpu().numpy(), b) for a, b in zip(out, want))
+    errs[f"splu_update_{n}"] = max(cases.rel_err(a.cpu().numpy(), b) for a, b in zip(out, want))
     pre = psgd.precond_grad_splu(dev(L12), dev(l3), dev(U12), dev(u3), [dev(dx)])
-    errs["splu_apply"] = cases.rel_err(pre[0].cpu().numpy(), O.precond_grad_splu(L12, l3, U12, u3, [dx])[0])
+    errs[f"splu_apply_{n}"] = cases.rel_err(pre[0].cpu().numpy(), O.precond_grad_splu(L12, l3, U12, u3, [dx])[0])
 
 
 def vec():
