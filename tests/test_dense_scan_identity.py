@@ -1,0 +1,80 @@
+"""The algebra behind csrc/dense.cu, checked on the CPU in float64: the dense preconditioner's update
+
+    Q' = Q - mu * triu(a a^T - b b^T) Q                                   (psgd.py:40-42)
+
+needs no matrix product -- (triu(a a^T) Q)[i, k] = a_i * sum_{j >= i} a_j Q[j, k], a suffix scan down each column of Q --
+for ANY square Q, and the chunked form the kernels use (column sums per 128-row chunk, sums of the chunks below, rescan
+inside the chunk) gives the same numbers.  Also the small-layer solves' formulation: a block forward substitution with
+explicitly inverted 32 x 32 diagonal blocks (csrc/linalg.cu) against scipy's triangular solve."""
+import numpy as np
+import pytest
+from scipy.linalg import solve_triangular
+
+from oracle import psgd_oracle as O
+
+
+def scan_form(Q, a, b, mu, chunk=128):
+    n = Q.shape[0]
+    out = np.empty_like(Q)
+    chunks = [(lo, min(n, lo + chunk)) for lo in range(0, n, chunk)]
+    Pa = np.stack([a[lo:hi] @ Q[lo:hi] for lo, hi in chunks])          # pass 0: column sums of every chunk
+    Pb = np.stack([b[lo:hi] @ Q[lo:hi] for lo, hi in chunks])
+    below_a = np.zeros_like(Pa); below_b = np.zeros_like(Pb)            # suffix_kernel: everything below the chunk
+    for c in range(len(chunks) - 2, -1, -1):
+        below_a[c] = below_a[c + 1] + Pa[c + 1]
+        below_b[c] = below_b[c + 1] + Pb[c + 1]
+    for c, (lo, hi) in enumerate(chunks):                               # pass 1: rescan the chunk bottom to top
+        sa, sb = below_a[c].copy(), below_b[c].copy()
+        for i in range(hi - 1, lo - 1, -1):
+            sa += a[i] * Q[i]; sb += b[i] * Q[i]
+            out[i] = Q[i] - mu * (a[i] * sa - b[i] * sb)
+    return out
+
+
+@pytest.mark.parametrize("n", [1, 2, 127, 128, 129, 300])
+@pytest.mark.parametrize("full", [False, True])
+def test_scan_form_equals_matrix_product(n, full):
+    rng = np.random.default_rng(n + 7 * full)
+    Q = rng.standard_normal((n, n))
+    if not full:
+        Q = np.triu(Q)
+    a, b = rng.standard_normal(n), rng.standard_normal(n)
+    grad = np.triu(np.outer(a, a) - np.outer(b, b))
+    mu = 0.01 / (np.abs(grad).max() + 1e-300)
+    want = Q - mu * grad @ Q
+    got = scan_form(Q, a, b, mu)
+    assert np.abs(got - want).max() <= 1e-12 * max(1.0, np.abs(want).max())
+
+
+def test_scan_form_reproduces_the_oracle_update():
+    rng = np.random.default_rng(3)
+    n = 200
+    Q = (np.triu(rng.standard_normal((n, n))) * 0.1 + np.eye(n)).astype(np.float64)
+    dx, dg = rng.standard_normal((n, 1)), rng.standard_normal((n, 1))
+    want = O.update_precond_dense(Q, [dx], [dg], 0.01)
+    a = (Q @ dg)[:, 0]
+    b = solve_triangular(Q, dx, lower=False, trans="T")[:, 0]
+    mx = np.abs(np.triu(np.outer(a, a) - np.outer(b, b))).max()
+    got = scan_form(Q, a, b, 0.01 / (mx + O._tiny(Q)))
+    assert np.abs(got - want).max() <= 1e-12
+
+
+def blocked_left_solve(Q, B, nb=32):
+    """X = Q^-T B by block steps with explicitly inverted diagonal blocks, as trsm_panel_kernel<LEFT> does."""
+    n = Q.shape[0]
+    X = np.zeros_like(B)
+    for i0 in range(0, n, nb):
+        i1 = min(n, i0 + nb)
+        W = np.linalg.inv(np.triu(Q[i0:i1, i0:i1]))
+        X[i0:i1] = W.T @ (B[i0:i1] - Q[:i0, i0:i1].T @ X[:i0])
+    return X
+
+
+@pytest.mark.parametrize("n,m", [(32, 5), (257, 120), (600, 33)])
+def test_block_inverse_solve_matches_substitution(n, m):
+    rng = np.random.default_rng(n + m)
+    Q = np.triu(rng.standard_normal((n, n))) * (0.3 / np.sqrt(n)) + np.diag(0.5 + rng.random(n))
+    B = rng.standard_normal((n, m))
+    want = solve_triangular(Q, B, lower=False, trans="T")
+    got = blocked_left_solve(Q, B)
+    assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
