@@ -1,4 +1,6 @@
-"""The algebra behind csrc/dense.cu, checked on the CPU in float64: the dense preconditioner's update
+"""Formulations the CUDA kernels use in place of the reference's op sequences, checked on the CPU in float64.
+
+csrc/dense.cu: the dense preconditioner's update
 
     Q' = Q - mu * triu(a a^T - b b^T) Q                                   (psgd.py:40-42)
 
@@ -78,3 +80,29 @@ def test_block_inverse_solve_matches_substitution(n, m):
     want = solve_triangular(Q, B, lower=False, trans="T")
     got = blocked_left_solve(Q, B)
     assert np.abs(got - want).max() <= 1e-10 * np.abs(want).max()
+
+
+def test_scale_dense_in_its_own_orientation_equals_the_reference_mirroring():
+    """(scaling, dense): the reference transposes to (dense, scaling) (psgd.py:102-104, :144-146); csrc/kron.cu runs
+    A = diag(ql)(dG Qr^T), Bt = diag(1/ql)(dX Qr^-1), grad(Qr) = triu(A^T A - Bt^T Bt), grad(ql)_i = |A_i|^2 - |Bt_i|^2 and
+    out = diag(ql^2) G Qr^T Qr on X itself.  Same numbers (float64)."""
+    rng = np.random.default_rng(11)
+    M, N = 37, 12
+    ql = (0.5 + rng.random((1, M)))
+    Qr = np.triu(rng.standard_normal((N, N))) * 0.2 + np.diag(0.5 + rng.random(N))
+    dX, dG, G = rng.standard_normal((M, N)), rng.standard_normal((M, N)), rng.standard_normal((M, N))
+    step, tiny = 0.01, O._tiny(Qr)
+    want_ql, want_qr = O.update_precond_kron(ql, Qr, dX, dG, step)
+    want_pre = O.precond_grad_kron(ql, Qr, G)
+    # own orientation, with the reference's balancing of the transposed problem (dense factor first)
+    rho = np.sqrt(np.max(np.diag(Qr)) / np.max(ql))
+    qrb, qlb = Qr / rho, ql * rho
+    A = qlb.T * (dG @ qrb.T)
+    Bt = solve_triangular(qrb, dX.T, lower=False, trans="T").T / qlb.T          # dX Qr^-1, rows scaled
+    g2 = np.triu(A.T @ A - Bt.T @ Bt)
+    got_qr = qrb - step / (np.abs(g2).max() + tiny) * g2 @ qrb
+    g1 = (A * A).sum(1) - (Bt * Bt).sum(1)
+    got_ql = qlb - step / (np.abs(g1).max() + tiny) * g1[None, :] * qlb
+    assert np.abs(got_qr - want_qr).max() <= 1e-12 and np.abs(got_ql - want_ql).max() <= 1e-12
+    got_pre = (ql.T ** 2) * (G @ Qr.T @ Qr)
+    assert np.abs(got_pre - want_pre).max() <= 1e-12 * np.abs(want_pre).max()
