@@ -106,3 +106,43 @@ def test_scale_dense_in_its_own_orientation_equals_the_reference_mirroring():
     assert np.abs(got_qr - want_qr).max() <= 1e-12 and np.abs(got_ql - want_ql).max() <= 1e-12
     got_pre = (ql.T ** 2) * (G @ Qr.T @ Qr)
     assert np.abs(got_pre - want_pre).max() <= 1e-12 * np.abs(want_pre).max()
+
+
+def test_dense_norm_in_its_own_orientation_equals_the_reference_mirroring():
+    """(dense, normalization): the reference transposes to (normalization, dense) (psgd.py:86, :128).  Written out for X
+    itself (Qr = diag(q0) with q1 in the last ROW... of its transpose, i.e. X Qr^T = X diag(q0) + X[:, -1] q1):
+      T = dG diag(q0) + dG[:, -1:] q1,  A = Ql T,
+      S = dX / q0 with last column  S[:, -1] -= dX @ (q1 / (q0 q0[-1])),  Bt = Ql^-T S,
+      grad(Ql) = triu(A A^T - Bt Bt^T),  d_j = |A[:, j]|^2 - |Bt[:, j]|^2,  bias_j = A[:, j].A[:, -1] - Bt[:, j].Bt[:, -1]."""
+    rng = np.random.default_rng(21)
+    M, N = 9, 14
+    Ql = np.triu(rng.standard_normal((M, M))) * 0.2 + np.diag(0.5 + rng.random(M))
+    qr = np.stack([0.5 + rng.random(N), 0.1 * rng.standard_normal(N)])
+    qr[1, -1] = 0.0
+    dX, dG, G = rng.standard_normal((M, N)), rng.standard_normal((M, N)), rng.standard_normal((M, N))
+    step, tiny = 0.01, O._tiny(Ql)
+    want_ql, want_qr = O.update_precond_kron(Ql, qr, dX, dG, step)
+    want_pre = O.precond_grad_kron(Ql, qr, G)
+    rho = np.sqrt(np.max(qr[0]) / np.max(np.diag(Ql)))      # the transposed problem balances the normalization factor first
+    q = qr / rho
+    Qlb = rho * Ql
+    q0, q1 = q[0], q[1]
+    T = dG * q0 + dG[:, -1:] * q1
+    A = Qlb @ T
+    S = dX / q0
+    S[:, -1] = S[:, -1] - dX @ (q1 / (q0 * q0[-1]))
+    Bt = solve_triangular(Qlb, S, lower=False, trans="T")
+    g1 = np.triu(A @ A.T - Bt @ Bt.T)
+    got_ql = Qlb - step / (np.abs(g1).max() + tiny) * g1 @ Qlb
+    d = (A * A).sum(0) - (Bt * Bt).sum(0)
+    bias = A[:, :-1].T @ A[:, -1] - Bt[:, :-1].T @ Bt[:, -1]
+    bias = np.concatenate([bias, np.zeros(1)])
+    s = step / (max(np.abs(d).max(), np.abs(bias).max()) + tiny)
+    got_qr = np.stack([q0 - s * d * q0, q1 - s * (d * q1 + q0[-1] * bias)])
+    assert np.abs(got_ql - want_ql).max() <= 1e-12 and np.abs(got_qr - want_qr).max() <= 1e-12
+    # apply: out = Ql^T Ql (G diag(q0) + G[:, -1] q1) then the transposed out-op
+    P = G * qr[0] + G[:, -1:] * qr[1]
+    P = Ql.T @ (Ql @ P)
+    out = P * qr[0]
+    out[:, -1] = out[:, -1] + P @ qr[1]
+    assert np.abs(out - want_pre).max() <= 1e-12 * np.abs(want_pre).max()
