@@ -278,8 +278,8 @@ __global__ void __launch_bounds__(128) row_stats_kernel(const float* __restrict_
 // new ql rows                                                     psgd.py:240-241
 __global__ void __launch_bounds__(256) norm_new_ql_kernel(const float* __restrict__ ql, const float* __restrict__ g1d,
                                                            const float* __restrict__ g1b, float* __restrict__ out, int M,
-                                                           float step, float tiny, const Scal* __restrict__ sc) {
-  const float step1 = step / (sc->max1 + tiny);
+                                                           float step, float tiny, const float* __restrict__ maxabs) {
+  const float step1 = step / (*maxabs + tiny);
   const float qlast = ql[M - 1];
   for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < M; i += gridDim.x * blockDim.x) {
     out[i] = ql[i] - step1 * g1d[i] * ql[i];
@@ -335,6 +335,74 @@ __global__ void __launch_bounds__(256) col_scale_recip_kernel(float* __restrict_
   const int64_t total = (int64_t)M * N;
   for (int64_t e = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x)
     X[e] = X[e] * (1.0f / qr[e % N]);
+}
+
+// (dense, normalization) in its own orientation (the reference transposes to (normalization, dense): psgd.py:86, :128).
+// The normalization factor q = [q0; q1] then multiplies from the right,  X Qr^T = X diag(q0) + X[:, N-1] q1,  and every
+// row of X is on its own: one warp per row.
+//   mode 0: out = X Qr^T                                                                  psgd.py:218-219, :258-259
+//   mode 1: out = X Qr^-1:  X[i,j] / q0[j], last column minus sum_j X[i,j] q1[j] / (q0[j] q0[N-1])      :230-232
+//   mode 2: out[i,j] = X[i,j] q0[j], last column plus sum_j X[i,j] q1[j]                                 :265-268
+// out may be X.
+__global__ void __launch_bounds__(256) norm_right_kernel(int mode, const float* __restrict__ q, const float* X, float* out,
+                                                          int M, int N) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const float* q1 = q + N;
+  const float qlast = q[N - 1];
+  for (int i = blockIdx.x * 8 + warp; i < M; i += gridDim.x * 8) {
+    const float* x = X + (size_t)i * N;
+    float* o = out + (size_t)i * N;
+    const float xlast = x[N - 1];
+    float s = 0.f;
+    if (mode == 1) {
+      for (int j = lane; j < N; j += 32) s = fmaf(q1[j] / (q[j] * qlast), x[j], s);
+    } else if (mode == 2) {
+      for (int j = lane; j < N; j += 32) s = fmaf(q1[j], x[j], s);
+    }
+    s = warp_sum(s);
+    for (int j = lane; j < N; j += 32) {
+      float v;
+      if (mode == 0) { v = q[j] * x[j]; v = v + q1[j] * xlast; }
+      else if (mode == 1) { v = (1.0f / q[j]) * x[j]; if (j == N - 1) v = v - s; }
+      else { v = q[j] * x[j]; if (j == N - 1) v = v + s; }
+      o[j] = v;
+    }
+  }
+}
+// column statistics of A, Bt for the normalization factor on the right           psgd.py:235-237 for the transposed problem
+//   partial[chunk][w][j], w = 0..3:  sum_i A^2,  sum_i Bt^2,  sum_i A[i,j] A[i,N-1],  sum_i Bt[i,j] Bt[i,N-1]
+__global__ void __launch_bounds__(128) norm_right_stats_kernel(const float* __restrict__ A, const float* __restrict__ Bt,
+                                                                int M, int N, float* __restrict__ partial) {
+  const int j = blockIdx.x * blockDim.x + threadIdx.x;
+  const int chunk = blockIdx.y;
+  const int i0 = chunk * kColChunkRows, i1 = min(M, i0 + kColChunkRows);
+  if (j >= N) return;
+  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  for (int i = i0; i < i1; ++i) {
+    const float a = A[(size_t)i * N + j], b = Bt[(size_t)i * N + j];
+    const float al = A[(size_t)i * N + N - 1], bl = Bt[(size_t)i * N + N - 1];
+    s0 = fmaf(a, a, s0); s1 = fmaf(b, b, s1);
+    s2 = fmaf(a, al, s2); s3 = fmaf(b, bl, s3);
+  }
+  float* p = partial + (size_t)chunk * 4 * N + j;
+  p[0] = s0; p[N] = s1; p[2 * (size_t)N] = s2; p[3 * (size_t)N] = s3;
+}
+// d[j] = sum A^2 - sum Bt^2,  bias[j] = sum A A_last - sum Bt Bt_last (0 for the last column),  max of their moduli
+__global__ void __launch_bounds__(128) norm_right_finish_kernel(const float* __restrict__ partial, int chunks, int N,
+                                                                 float* __restrict__ d, float* __restrict__ bias,
+                                                                 float* __restrict__ maxabs) {
+  float mx = 0.f;
+  for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < N; j += gridDim.x * blockDim.x) {
+    float t[4] = {0.f, 0.f, 0.f, 0.f};
+    for (int c = 0; c < chunks; ++c)
+      for (int w = 0; w < 4; ++w) t[w] += partial[((size_t)c * 4 + w) * N + j];
+    const float dj = t[0] - t[1];
+    const float bj = (j == N - 1) ? 0.f : (t[2] - t[3]);
+    d[j] = dj; bias[j] = bj;
+    mx = fmaxf(mx, fmaxf(fabsf(dj), fabsf(bj)));
+  }
+  mx = warp_max(mx);
+  if ((threadIdx.x & 31) == 0) atomic_max_nonneg(maxabs, mx);
 }
 
 // (scaling, dense) in its own orientation (the reference transposes to (dense, scaling): psgd.py:102-104).  One warp per
@@ -426,6 +494,7 @@ struct Layer {
   Scal* sc;
   float *Qlb, *Qrb, *A, *Bt, *T1, *cvec, *part, *grad1, *grad2, *g1d, *g1b, *gvl, *sa, *sb, *gvec, *zinv, *xwork;
   float *t1, *t2, *t3, *P, *addlast;
+  float* nrpart;   // (dense, normalization): partial column statistics, 4 per column and chunk
   float* nspart;   // (normalization, scaling): partial tables of the fused streaming kernels
   int *fl, *fr;    // run-time "dense factor is not upper triangular" flags (nullptr: no scan, hints taken as given)
 };
@@ -478,6 +547,7 @@ static size_t update_ws_floats(int kl, int kr, int64_t M, int64_t N) {
              2 * col_partial_floats((int)M, (int)N) + 2 * MN /* mirrored transposes */ + 64 * 64;
   f += tc::trsm_scratch_floats((int)(M > N ? M : N));
   if (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) f += ks::ns_update_scratch_floats((int)M, (int)N) + 64;
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_NORM) f += 2 * col_partial_floats((int)M, (int)N) + 64;
   return f;
 }
 
@@ -515,6 +585,7 @@ static void carve_update(const psgd_ctx* ctx, WsCarver& c, Layer& L, int kl, int
   L.zinv = c.take<float>(tc::trsm_scratch_floats(M > N ? M : N));
   L.xwork = c.take<float>(MN);
   L.nspart = (kl == PSGD_FACTOR_NORM && kr == PSGD_FACTOR_SCALE) ? c.take<float>(ks::ns_update_scratch_floats(M, N)) : nullptr;
+  L.nrpart = (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_NORM) ? c.take<float>(2 * col_partial_floats(M, N)) : nullptr;
 }
 
 // grad2 = triu(A^T A - Bt^T Bt), Qr' = Qr - step2 grad2 Qr (times rho for (dense, dense) pairs)      psgd.py:176-179
@@ -596,6 +667,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
   const bool small_pair = kl != PSGD_FACTOR_DENSE && kr != PSGD_FACTOR_DENSE && cl + cr <= kBalanceSmallMax;
   const bool dd = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_DENSE;
   const bool sd = kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE;    // run in its own orientation, no transposes
+  const bool dn = kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_NORM;     // likewise
   for (size_t t0 = 0; dd && t0 < Ls.size(); t0 += kPrepBatch) {          // (dense, dense): ONE launch per group
     const int cnt = (int)std::min<size_t>(kPrepBatch, Ls.size() - t0);
     PrepBatch b{};
@@ -607,6 +679,16 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     if (dd) break;
     if (small_pair) {
       balance_rescale_small_kernel<<<1, 1024, 0, st>>>(kl, L.Ql, M, kr, L.Qr, N, cl, cr, L.Qlb, L.Qrb, L.sc);
+      PSGD_LAUNCH_CHECK(ctx);
+      continue;
+    }
+    if (dn) {
+      // the transposed problem has the normalization factor first: rho = sqrt(max q0 / max diag(Ql)), q / rho, rho Ql
+      balance_kernel<<<1, 256, 0, st>>>(kr, L.Qr, N, kl, L.Ql, M, L.sc);                   // psgd.py:86, :211-215
+      PSGD_LAUNCH_CHECK(ctx);
+      rescale_kernel<<<ew_grid(ctx, cr, 256), 256, 0, st>>>(L.Qr, L.Qrb, cr, L.sc, 1);
+      PSGD_LAUNCH_CHECK(ctx);
+      rescale_kernel<<<ew_grid(ctx, cl, 256), 256, 0, st>>>(L.Ql, L.Qlb, cl, L.sc, 0);
       PSGD_LAUNCH_CHECK(ctx);
       continue;
     }
@@ -653,6 +735,51 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     br.to_main();
     PSGD_RETURN_IF(rc);
     PSGD_RETURN_IF(br.join());
+  } else if (dn) {
+    // (dense, normalization), X [M, N] with the normalization factor on the right; the reference's (normalization, dense)
+    // update of the transposed problem (psgd.py:86 -> :198-246) written out for X itself
+    // (tests/test_kernel_formulations.py):  A = Ql (dG Qr^T),  Bt = Ql^-T (dX Qr^-1),  grad(Ql) = triu(A A^T - Bt Bt^T),
+    // and the normalization factor's gradient from COLUMN statistics of A, Bt.
+    const int rows_grid = (M + 7) / 8 < ctx->num_sms * 8 ? (M + 7) / 8 : ctx->num_sms * 8;
+    for (auto& L : Ls) {
+      norm_right_kernel<<<rows_grid, 256, 0, st>>>(0, L.Qrb, L.dG, L.T1, M, N);             // T = dG Qr^T
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    gs.clear();                                                          // A = Ql T
+    for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Qlb, M, false, L.T1, N, false, L.A, N));
+    PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
+    for (auto& L : Ls) {
+      norm_right_kernel<<<rows_grid, 256, 0, st>>>(1, L.Qrb, L.dX, L.T1, M, N);             // S = dX Qr^-1
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    ts.clear();                                                          // Bt = Ql^-T S
+    for (auto& L : Ls) ts.push_back(tc::Trsm{L.Qlb, L.T1, L.Bt, L.zinv, L.xwork});
+    PSGD_RETURN_IF(tc::trsm_left_many(ctx, ts.data(), (int)ts.size(), M, N, N, M, N));
+    const int chunks = (M + kColChunkRows - 1) / kColChunkRows;
+    for (auto& L : Ls) {                                                 // q' from the column statistics    :235-241
+      norm_right_stats_kernel<<<dim3((N + 127) / 128, chunks), 128, 0, st>>>(L.A, L.Bt, M, N, L.nrpart);
+      PSGD_LAUNCH_CHECK(ctx);
+      norm_right_finish_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.nrpart, chunks, N, L.sa, L.sb, &L.sc->max2);
+      PSGD_LAUNCH_CHECK(ctx);
+      norm_new_ql_kernel<<<ew_grid(ctx, N, 256), 256, 0, st>>>(L.Qrb, L.sa, L.sb, L.Qr_out, N, step, tiny, &L.sc->max2);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    gs.clear();                                                          // grad1 = triu(A A^T - Bt Bt^T)     :243
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, M, N, L.A, N, false, L.A, N, true, L.grad1, M);
+      g.K2 = N; g.A2 = L.Bt; g.lda2 = N; g.ta2 = false; g.B2 = L.Bt; g.ldb2 = N; g.tb2 = true;
+      g.triu = true; g.maxabs = &L.sc->max1;
+      gs.push_back(g);
+    }
+    PSGD_RETURN_IF(gemm_all(ctx, gs));
+    gs.clear();                                                          // Ql' = Ql - step grad1 Ql          :244-246
+    for (auto& L : Ls) {
+      la::Gemm g = mk(M, M, M, L.grad1, M, false, L.Qlb, M, false, L.Ql_out, M);
+      g.D = L.Qlb; g.ldd = M; g.mu_max = &L.sc->max1; g.step = step; g.tiny = tiny;
+      g.d_tri = true;
+      gs.push_back(g);
+    }
+    return gemm_all(ctx, gs, kUpper, kUpper, &Ls, 0, kFromL);
   } else if (sd) {
     // (scaling, dense), X [M, N] with the dense factor on the right.  The reference computes the (dense, scaling) update of
     // the transposed problem (psgd.py:102-104 -> :288-307); written out for X itself that is
@@ -733,7 +860,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
       PSGD_RETURN_IF(ks::ns_update_stats(ctx, L.Qlb, L.Qrb, L.part, cchunks, L.dX, L.dG, M, N, L.nspart, L.g1d, L.g1b,
                                          L.gvec, &L.sc->max1, &L.sc->max2, L.Ql_out, L.Qr_out, step, tiny));   // :349-369
       if (ks::ns_finish_is_fused(M, N)) continue;
-      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :362-364
+      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, &L.sc->max1);   // :362-364
       PSGD_LAUNCH_CHECK(ctx);
       scale_new_qr_kernel<<<ew_grid(ctx, N, 128), 128, 0, st>>>(L.Qrb, L.gvec, L.Qr_out, N, step, tiny, &L.sc->max2);        // :367-369
       PSGD_LAUNCH_CHECK(ctx);
@@ -766,7 +893,7 @@ static int update_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, i
     for (auto& L : Ls) {
       row_stats_kernel<<<rows_grid, 128, 0, st>>>(L.A, L.Bt, M, N, L.g1d, L.g1b, L.sc);                  // :235-239
       PSGD_LAUNCH_CHECK(ctx);
-      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, L.sc);   // :240-241
+      norm_new_ql_kernel<<<ew_grid(ctx, M, 256), 256, 0, st>>>(L.Qlb, L.g1d, L.g1b, L.Ql_out, M, step, tiny, &L.sc->max1);   // :240-241
       PSGD_LAUNCH_CHECK(ctx);
     }
   }
@@ -888,6 +1015,33 @@ static int apply_group(psgd_ctx* ctx, int kl, int kr, std::vector<Layer>& Ls, in
     for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t2, N, false, L.out, N));
     return gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0);
   }
+  if (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_NORM) {
+    // the reference's (normalization, dense) apply of the transposed problem (psgd.py:128 -> :249-270) written for G itself:
+    // P = G Qr^T, then Ql^T Ql P with the association the reference picks for P^T, then the transposed out-op
+    const int rows_grid = (M + 7) / 8 < ctx->num_sms * 8 ? (M + 7) / 8 : ctx->num_sms * 8;
+    for (auto& L : Ls) {
+      norm_right_kernel<<<rows_grid, 256, 0, st>>>(0, L.Qr, L.G, L.t1, M, N);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    if (N < M || chain_preferred(ctx, M, N)) {                             // psgd.py:261 for the transposed problem
+      for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, false, L.t1, N, false, L.t2, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kUpper, 0, &Ls, kFromL, 0));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, M, L.Ql, M, true, L.t2, N, false, L.t3, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, 0, &Ls, kFromL, 0));
+    } else {                                                               // :263
+      for (auto& L : Ls) gs.push_back(mk(M, M, M, L.Ql, M, true, L.Ql, M, false, L.P, M));
+      PSGD_RETURN_IF(gemm_all(ctx, gs, kLower, kUpper, &Ls, kFromL, kFromL));
+      gs.clear();
+      for (auto& L : Ls) gs.push_back(mk(M, N, M, L.P, M, false, L.t1, N, false, L.t3, N));
+      PSGD_RETURN_IF(gemm_all(ctx, gs));
+    }
+    for (auto& L : Ls) {
+      norm_right_kernel<<<rows_grid, 256, 0, st>>>(2, L.Qr, L.t3, L.out, M, N);
+      PSGD_LAUNCH_CHECK(ctx);
+    }
+    return PSGD_OK;
+  }
   if (kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE) {
     // the reference's (dense, scaling) apply of the transposed problem (psgd.py:144-146 -> :318-322) written for G itself:
     // out = diag(ql^2) G Qr^T Qr, the small Gram matrix first when that is what the reference does for G^T (N < M)
@@ -980,9 +1134,10 @@ static int ensure_side_streams(psgd_ctx* ctx) {
   return PSGD_OK;
 }
 
-// Runs update (is_update) or apply over a ragged list of layers.  The mirrored formats (dense,norm) and (scale,norm) are
-// brought to canonical orientation by transposing dX,dG / G into scratch and swapping the factors (exactly what the
-// reference does, psgd.py:86, :104, :128, :146); (scale,dense) -- psgd.py:102, :144 -- runs in its own orientation.
+// Runs update (is_update) or apply over a ragged list of layers.  The mirrored format (scale,norm) is brought to
+// canonical orientation by transposing dX,dG / G into scratch and swapping the factors (exactly what the reference
+// does for all three mirrored formats, psgd.py:86, :102, :104, :128, :144, :146); (scale,dense) and (dense,norm) run in
+// their own orientation.
 // Layers with equal (kinds, shape) then run as one group so every GEMM/TRSM of the op sequence is a single grouped launch.
 static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool is_update, float step, float tiny) {
   if (count == 0) return PSGD_OK;
@@ -1023,9 +1178,11 @@ static int run_layers(psgd_ctx* ctx, const psgd_kron_layer* in, int count, bool 
       Layer& L = Ls[i - begin];
       L = Layer{};
       int kl = q.kind_l, kr = q.kind_r, M = (int)q.M, N = (int)q.N;
-      // (scaling, dense) -- the NMT embeddings [9414, 256] -- has kernels for its own orientation (update_group /
-      // apply_group); the other two mirrored formats go through the canonical kernels on transposed copies
-      if (is_canonical(kl, kr) || (kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE)) {
+      // (scaling, dense) -- the NMT embeddings [9414, 256] -- and (dense, normalization) have kernels for their own
+      // orientation (update_group / apply_group); (scaling, normalization) goes through the canonical kernels on
+      // transposed copies
+      if (is_canonical(kl, kr) || (kl == PSGD_FACTOR_SCALE && kr == PSGD_FACTOR_DENSE) ||
+          (kl == PSGD_FACTOR_DENSE && kr == PSGD_FACTOR_NORM)) {
         L.Ql = q.Ql; L.Qr = q.Qr; L.dX = q.dX; L.dG = q.dG; L.G = q.G;
         L.Ql_out = q.Ql_out; L.Qr_out = q.Qr_out; L.out = q.out;
       } else {
