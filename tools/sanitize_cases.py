@@ -59,7 +59,8 @@ def kron_pair():
 
 
 def kron_stream():
-    for kl, kr, M, N in (("norm", "scale", 300, 257), ("norm", "dense", 200, 64), ("scale", "dense", 130, 48)):
+    for kl, kr, M, N in (("norm", "scale", 300, 257), ("norm", "dense", 200, 64), ("scale", "dense", 130, 48),
+                         ("dense", "norm", 64, 200), ("scale", "norm", 257, 40)):
         c = cases.kron_case(9, kl, kr, M, N)
         ql, qr = psgd.update_precond_kron(dev(c["Ql"]), dev(c["Qr"]), dev(c["dX"]), dev(c["dG"]), 0.01)
         pre = psgd.precond_grad_kron(ql, qr, dev(c["G"]))
