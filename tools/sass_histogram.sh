@@ -4,7 +4,7 @@
 set -u
 cd "$(dirname "$0")/.."
 python -c 'from psgd_tf_b200 import build; build.build()' > /dev/null 2>&1
-for obj in gemm_tc uvd kron_stream elementwise splu comm; do
+for obj in gemm_tc uvd kron_stream elementwise splu dense linalg comm; do
   echo "== psgd_tf_b200/_C/$obj.o"
   cuobjdump -sass psgd_tf_b200/_C/$obj.o | grep -E '^\s+/\*[0-9a-f]+\*/' | sed -E 's/^\s+\/\*[0-9a-f]+\*\/\s+(@!?U?P[0-9T]+\s+)?//' | awk '{print $1}' | sed -E 's/;$//' \
     | grep -E '^(UTCHMMA|UTCQMMA|UTCBAR|UTMALDG|UTMASTG|UBLKCP|LDTM|STTM|UTCATOM|SYNCS|FFMA2|FFMA|LDGSTS|STG|LDG|LDS|STS|ELECT|UCGABAR|ACQBULK|BAR|ATOM|RED|MUFU|DFMA|HMMA)' \
